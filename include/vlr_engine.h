@@ -1,0 +1,249 @@
+/*
+ * vlr_engine.h — C-ABI of the B200-native per-locus posterior engine.
+ *
+ * This is the drop-in boundary for varlociraptor's `call variants` inner loop.
+ * The reference has no FFI; the seam this ABI replaces is the Rust call
+ *
+ *     let m = model.compute(event_universe.iter().cloned(), &data);
+ *                                      (src/calling/variants/calling.rs:760)
+ *
+ * together with its readers in `Caller::call_record` / `Caller::sample_infos`
+ * (calling.rs:762-813, 844-937) and the per-record preparation that feeds it
+ * (`preprocess_record`, calling.rs:457-630; `configure_model`, calling.rs:632-718).
+ * A Rust host keeps the CLI, scenario grammar and BCF I/O, flattens its
+ * `grammar::Scenario` / `VAFTree`s into `vlr_scenario_t` once per contig, packs
+ * batches of records into `vlr_batch_t` (structure of arrays) and gets back
+ * event posteriors, MAP allele frequencies and allele frequency distributions.
+ *
+ * Conventions
+ *  - plain C, no C++/torch types; every pointer is caller-owned memory;
+ *  - every entry point returns a vlr_status_t, never throws or aborts;
+ *    model invariants that `panic!` in the reference (NaN, prior > 0, ...)
+ *    become per-locus bits in `vlr_results_t::status`;
+ *  - a context is bound to one CUDA device and one stream and must not be
+ *    used from two threads at once; several contexts (one per GPU) may run
+ *    concurrently.
+ */
+#ifndef VLR_ENGINE_H
+#define VLR_ENGINE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VLR_ABI_VERSION 1
+#define VLR_MAX_SAMPLES 8
+#define VLR_MAX_EVENTS 24
+#define VLR_MAX_TREE_DEPTH 24
+#define VLR_N_ARTIFACT_CONFIGS 9 /* 0 = none, 1..8 = single-artifact configs */
+
+typedef int32_t vlr_status_t;
+enum {
+    VLR_OK = 0,
+    VLR_ERR_INVALID_ARGUMENT = 1,
+    VLR_ERR_UNSUPPORTED = 2,
+    VLR_ERR_CUDA = 3,
+    VLR_ERR_OUT_OF_MEMORY = 4,
+    VLR_ERR_NO_DEVICE = 5
+};
+
+/* ---- VAF tree (flattened grammar::vaftree::Node, src/grammar/vaftree.rs:58-88) ---- */
+enum {
+    VLR_NODE_SET = 0,     /* NodeKind::Sample with VAFSpectrum::Set   */
+    VLR_NODE_RANGE = 1,   /* NodeKind::Sample with VAFSpectrum::Range */
+    VLR_NODE_LFC = 2,     /* NodeKind::Log2FoldChange                 */
+    VLR_NODE_VARIANT = 3, /* NodeKind::Variant                        */
+    VLR_NODE_TRUE = 4,
+    VLR_NODE_FALSE = 5
+};
+
+/* utils/comparison.rs ComparisonOperator */
+enum { VLR_CMP_EQ = 0, VLR_CMP_GT = 1, VLR_CMP_GE = 2, VLR_CMP_LT = 3, VLR_CMP_LE = 4, VLR_CMP_NE = 5 };
+
+typedef struct {
+    int32_t kind;        /* VLR_NODE_* */
+    int32_t sample;      /* SET/RANGE: sample index; LFC: sample_a */
+    int32_t sample_b;    /* LFC */
+    int32_t cmp;         /* LFC: VLR_CMP_* */
+    int32_t first_child; /* children are nodes[first_child .. first_child+n_children) */
+    int32_t n_children;
+    int32_t vaf_offset;  /* SET: vafs are set_vafs[vaf_offset .. vaf_offset+n_vafs), ascending */
+    int32_t n_vafs;
+    int32_t left_exclusive;  /* RANGE */
+    int32_t right_exclusive; /* RANGE */
+    int32_t variant_positive; /* VARIANT */
+    int32_t refmask;          /* VARIANT: IUPAC set as bit mask A=1,C=2,G=4,T=8 */
+    int32_t altmask;
+    int32_t _pad;
+    double start; /* RANGE */
+    double end;   /* RANGE */
+    double lfc_value; /* LFC predicate value */
+} vlr_node_t;
+
+/* One scenario event (model::Event, src/variants/model/mod.rs:34-39) before the
+ * plain/artifact split; the engine derives the artifact twin itself
+ * (calling.rs:655-687). */
+typedef struct {
+    char name[64];
+    int32_t first_root; /* roots are nodes[first_root .. first_root+n_roots) */
+    int32_t n_roots;
+    int32_t has_artifact_twin; /* 0 for the absent event, 1 otherwise */
+    int32_t _pad;
+} vlr_event_t;
+
+enum { VLR_SPECTRUM_SET = 0, VLR_SPECTRUM_RANGE = 1 };
+typedef struct {
+    int32_t kind;
+    int32_t vaf_offset, n_vafs; /* into set_vafs */
+    int32_t left_exclusive, right_exclusive;
+    int32_t _pad;
+    double start, end;
+} vlr_spectrum_t;
+
+enum { VLR_INHERIT_NONE = 0, VLR_INHERIT_MENDELIAN = 1, VLR_INHERIT_CLONAL = 2, VLR_INHERIT_SUBCLONAL = 3 };
+
+/* grammar::Sample + calling.rs SampleInfos (calling.rs:1130-1213) */
+typedef struct {
+    double resolution;             /* grammar/mod.rs:427 */
+    double contamination_fraction; /* valid iff contamination_by >= 0 */
+    double germline_mutation_rate; /* NaN = none */
+    double somatic_effective_mutation_rate; /* NaN = none */
+    int32_t contamination_by;      /* -1 = not contaminated */
+    int32_t uniform_prior;         /* sample declares `universe` (grammar/mod.rs:499) */
+    int32_t ploidy;                /* -1 = none */
+    int32_t inheritance;           /* VLR_INHERIT_* */
+    int32_t parent_a, parent_b;    /* mendelian: (a,b); clonal/subclonal: a */
+    int32_t clonal_somatic;
+    int32_t universe_offset, n_universe; /* contig universe spectra (for the prior) */
+    int32_t _pad;
+} vlr_sample_t;
+
+typedef struct {
+    int32_t abi_version;
+    int32_t n_samples;
+    int32_t n_events;
+    int32_t n_nodes;
+    int32_t n_set_vafs;
+    int32_t n_spectra;
+    const vlr_sample_t* samples;
+    const vlr_event_t* events;
+    const vlr_node_t* nodes;
+    const double* set_vafs;
+    const vlr_spectrum_t* spectra;
+    double heterozygosity;  /* species heterozygosity (linear), NaN = none */
+    double vtf_indel, vtf_mnv, vtf_sv; /* VariantTypeFraction, grammar/mod.rs:375-415 */
+    int32_t full_prior;     /* !is_absent_only (calling.rs:1086) */
+    int32_t _pad;
+} vlr_scenario_t;
+
+/* ---- per-read flag word ---- */
+#define VLR_RF_STRAND_SHIFT 0      /* 2 bits: 0 Forward, 1 Reverse, 2 Both, 3 None */
+#define VLR_RF_ORIENT_SHIFT 2      /* 4 bits: bio-types SequenceReadPairOrientation:
+                                      0 F1R2, 1 F2R1, 2 R1F2, 3 R2F1, 4 F1F2, 5 R1R2, 6 F2F1, 7 R2R1, 8 None */
+#define VLR_RF_READPOS_MAJOR (1u << 6)
+#define VLR_RF_SOFTCLIPPED (1u << 7)
+#define VLR_RF_PAIRED (1u << 8)
+#define VLR_RF_MAX_MAPQ (1u << 9)
+#define VLR_RF_ALTLOCUS_SHIFT 10   /* 2 bits: 0 Major, 1 Some, 2 None */
+#define VLR_RF_HAS_HOMOPOLYMER_LEN (1u << 12)
+#define VLR_RF_HOMOPOLYMER_LEN_SHIFT 16 /* 8 bits, two's complement i8 */
+
+/* ---- per-locus flag word (WorkItem, calling.rs:943-962) ---- */
+#define VLR_LF_CHECK_ROB (1u << 0)
+#define VLR_LF_CHECK_SB (1u << 1)
+#define VLR_LF_CHECK_RPB (1u << 2)
+#define VLR_LF_CHECK_SCB (1u << 3)
+#define VLR_LF_CHECK_HE (1u << 4)
+#define VLR_LF_CHECK_ALB (1u << 5)
+#define VLR_LF_FILTER_NONSTANDARD (1u << 6) /* is_snv_or_mnv && !omit_read_orientation_bias (calling.rs:595-602) */
+#define VLR_LF_VARTYPE_SHIFT 8  /* 2 bits: 0 fraction 1 (SNV, METH, ...), 1 indel, 2 MNV, 3 SV */
+#define VLR_LF_HAS_SNV (1u << 10)
+#define VLR_LF_REFBASE_SHIFT 16 /* 8 bits ASCII */
+#define VLR_LF_ALTBASE_SHIFT 24
+
+/* Batch of loci, structure of arrays. Reads of locus i, sample s are rows
+ * read_offsets[i*S+s] .. read_offsets[i*S+s+1] of every per-read column, in
+ * pileup order. Probabilities are natural-log, f32 (lossless: on disk every
+ * value is f16 or f32, utils/mod.rs:448-474). */
+typedef struct {
+    int64_t n_loci;
+    int64_t n_reads;
+    const int64_t* read_offsets; /* [n_loci*S + 1] */
+    const float* prob_mapping;
+    const float* prob_ref;
+    const float* prob_alt;
+    const float* prob_missed_allele;
+    const float* prob_sample_alt;
+    const float* prob_double_overlap;
+    const float* prob_hit_base;
+    const uint32_t* read_flags;
+    const float* prob_homopolymer_artifact; /* optional (NULL); NaN = None */
+    const float* prob_homopolymer_variant;  /* optional (NULL); NaN = None */
+    const uint32_t* locus_flags;            /* [n_loci] */
+    const float* locus_heterozygosity_phred; /* optional; NaN = none (INFO HETEROZYGOSITY) */
+    const float* locus_semr_phred;           /* optional; NaN = none */
+} vlr_batch_t;
+
+/* per-locus status bits */
+#define VLR_ST_MARGINAL_ZERO (1u << 0)     /* all events have probability zero */
+#define VLR_ST_NAN (1u << 1)               /* a NaN appeared (reference: assert!/panic!) */
+#define VLR_ST_OVERSHOOT (1u << 2)         /* cap_numerical_overshoot would panic */
+#define VLR_ST_PRIOR_POSITIVE (1u << 3)    /* prior > 0 (prior.rs:378) */
+#define VLR_ST_GRID_OVERFLOW (1u << 4)     /* adaptive grid exceeded engine capacity */
+#define VLR_ST_BASE_EVENTS_OVERFLOW (1u << 5) /* base-event log exceeded capacity: MAP/AFD incomplete */
+#define VLR_ST_AFD_TRUNCATED (1u << 6)     /* AFD exceeded afd_capacity */
+#define VLR_ST_NO_MAP (1u << 7)            /* no MAP estimate (sample_infos returned None) */
+#define VLR_ST_IS_ARTIFACT (1u << 8)       /* artifact beats every other event (calling.rs:801-803) */
+#define VLR_ST_SINGLETON_ADJUSTED (1u << 9)      /* Hint::AdjustedSingletonEvidence */
+#define VLR_ST_FILTERED_NONSTANDARD (1u << 10)   /* Hint::FilteredNonStandardAlignments */
+
+typedef struct {
+    /* [n_loci][n_events+1]: ln posterior of every plain event in scenario order,
+     * then ln P(artifact) = ln_sum_exp(artifact twins) (calling.rs:772-799) */
+    double* log_posteriors;
+    double* log_marginal;  /* [n_loci], optional */
+    double* map_vaf;       /* [n_loci][S]; NaN if VLR_ST_NO_MAP */
+    int32_t* map_config;   /* [n_loci]; artifact config of the MAP base event (0 none) */
+    int32_t* best_event;   /* [n_loci]; index into the event universe: 2*e (plain) or 2*e+1 (twin) */
+    uint32_t* status;      /* [n_loci] */
+    uint32_t* n_base_events; /* [n_loci], optional: joint evaluations recorded */
+    /* allele frequency distribution (calling.rs:891-928), optional (afd_capacity = 0) */
+    int32_t afd_capacity;  /* entries per locus and sample */
+    int32_t _pad;
+    int32_t* afd_count;    /* [n_loci][S] */
+    double* afd_vaf;       /* [n_loci][S][afd_capacity] */
+    double* afd_logp;      /* [n_loci][S][afd_capacity] ln posterior */
+} vlr_results_t;
+
+typedef struct vlr_ctx vlr_ctx_t;
+
+/* Replaces Caller::configure_model (calling.rs:632-718): build the event
+ * universe (absent + plain + artifact twins) for one contig on `device`. */
+vlr_status_t vlr_ctx_create(const vlr_scenario_t* scenario, int32_t device, vlr_ctx_t** out);
+void vlr_ctx_destroy(vlr_ctx_t* ctx);
+
+/* Replaces model.compute + call_record + sample_infos (calling.rs:720-937) for a
+ * batch of records. Host buffers in, host buffers out; H2D, kernels and D2H
+ * run on the context's stream; returns after the results are in host memory. */
+vlr_status_t vlr_call_batch(vlr_ctx_t* ctx, const vlr_batch_t* batch, vlr_results_t* results);
+
+/* Same, with every pointer in `batch` and `results` a DEVICE pointer on the
+ * context's device. Asynchronous on `cuda_stream` (a cudaStream_t, 0 = the
+ * context's own stream); the caller synchronises. */
+vlr_status_t vlr_call_batch_device(vlr_ctx_t* ctx, const vlr_batch_t* batch, vlr_results_t* results,
+                                   void* cuda_stream);
+
+/* Number of kernels the last vlr_call_batch* launched (for bench accounting). */
+int64_t vlr_last_launch_count(const vlr_ctx_t* ctx);
+/* The context's stream (cudaStream_t) so callers can time with CUDA events. */
+void* vlr_ctx_stream(const vlr_ctx_t* ctx);
+const char* vlr_last_error(const vlr_ctx_t* ctx);
+const char* vlr_status_string(vlr_status_t status);
+int32_t vlr_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VLR_ENGINE_H */

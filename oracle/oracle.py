@@ -1,0 +1,83 @@
+"""ctypes binding of the CPU oracle (oracle/vlr_oracle.cpp).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs — never by the product package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from varlociraptor_b200 import abi
+from varlociraptor_b200.batch import CallResults, LocusBatch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libvlr_oracle.so")
+
+
+class OracleDiag(C.Structure):
+    _fields_ = [("margin_bias", C.POINTER(C.c_double)), ("margin_adaptive", C.POINTER(C.c_double)),
+                ("n_pileup_evals", C.POINTER(C.c_uint64)), ("n_read_evals", C.POINTER(C.c_uint64))]
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "vlr_oracle.cpp")
+    hdr = os.path.join(_HERE, "..", "include", "vlr_engine.h")
+    stale = (not os.path.exists(_LIB_PATH)) or (
+        os.path.exists(src) and max(os.path.getmtime(src), os.path.getmtime(hdr)) > os.path.getmtime(_LIB_PATH))
+    if force or stale:
+        subprocess.check_call(["make", "-C", _HERE, "-B" if force else "-s", "libvlr_oracle.so"])
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB_PATH)
+        _lib.vlr_oracle_call_batch.restype = C.c_int32
+        _lib.vlr_oracle_call_batch.argtypes = [C.POINTER(abi.Scenario), C.POINTER(abi.Batch), C.POINTER(abi.Results),
+                                               C.POINTER(OracleDiag), C.c_int32]
+        _lib.vlr_oracle_pileup_likelihood.restype = C.c_double
+        _lib.vlr_oracle_pileup_likelihood.argtypes = [C.POINTER(abi.Batch), C.c_int64, C.c_int64, C.c_double,
+                                                      C.c_double, C.c_double, C.c_int32]
+    return _lib
+
+
+class OracleOutput(CallResults):
+    def __init__(self, n_loci, n_samples, n_events, afd_capacity):
+        super().__init__(n_loci, n_samples, n_events, afd_capacity)
+        self.margin_bias = np.full(n_loci, np.inf)
+        self.margin_adaptive = np.full(n_loci, np.inf)
+        self.n_pileup_evals = np.zeros(n_loci, dtype=np.uint64)
+        self.n_read_evals = np.zeros(n_loci, dtype=np.uint64)
+
+    def knife_edge(self, bias_tol: float = 1e-9, adaptive_tol: float = 1e-7) -> np.ndarray:
+        """Loci whose result hinges on a discrete decision that is within rounding noise of flipping in the
+        reference algorithm itself ("knife-edge loci")."""
+        return (self.margin_bias < bias_tol) | (self.margin_adaptive < adaptive_tol)
+
+
+def call_batch(flat_scenario, batch: LocusBatch, afd_capacity: int = 0, n_threads: int = 1) -> OracleOutput:
+    out = OracleOutput(batch.n_loci, batch.n_samples, flat_scenario.n_events, afd_capacity)
+    cb = batch.as_c()
+    cr = out.as_c()
+    d = OracleDiag(abi.ptr(out.margin_bias, C.c_double), abi.ptr(out.margin_adaptive, C.c_double),
+                   abi.ptr(out.n_pileup_evals, C.c_uint64), abi.ptr(out.n_read_evals, C.c_uint64))
+    rc = lib().vlr_oracle_call_batch(C.byref(flat_scenario.c), C.byref(cb), C.byref(cr), C.byref(d), n_threads)
+    if rc != 0:
+        raise RuntimeError("oracle failed with status %d" % rc)
+    return out
+
+
+def pileup_likelihood(batch: LocusBatch, lo: int, hi: int, vaf: float, vaf_secondary: float = 0.0,
+                      purity: float = 1.0, contaminated: bool = False) -> float:
+    cb = batch.as_c()
+    return float(lib().vlr_oracle_pileup_likelihood(C.byref(cb), lo, hi, vaf, vaf_secondary, purity,
+                                                    1 if contaminated else 0))

@@ -1,0 +1,1555 @@
+// vlr_oracle.cpp — CPU ORACLE of varlociraptor's per-locus posterior engine.
+//
+// THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE. Only tests/, __graft_entry__.smoke()
+// and bench.py's cpu_baseline / --impl reference legs may load it. The product path
+// (varlociraptor_b200/csrc) never links or calls anything in this directory.
+//
+// It is a sequential fp64 restatement, in the reference's evaluation order, of
+//   src/variants/model/likelihood.rs          (per-read emission, pileup folds, caches)
+//   src/variants/model/modes/generic.rs       (VAF-tree density, posterior, joint likelihood)
+//   src/variants/model/prior.rs               (scenario prior)
+//   src/variants/model/bias/*.rs              (six artifact models)
+//   src/utils/adaptive_integration.rs         (unimodal adaptive ln-integration)
+//   src/utils/log2_fold_change.rs, src/grammar/formula.rs:1057-1263 (VAFRange),
+//   src/grammar/vaftree.rs:42-165 (contains), src/calling/variants/calling.rs:720-937
+// and of the rust-bio 2.0 (`bio::stats`) semantics those files call (crate absent from
+// /root/reference; restated from its published algorithm):
+//   LogProb::{ln_sum_exp, ln_add_exp, ln_one_minus_exp, cap_numerical_overshoot,
+//   ln_simpsons_integrate_exp, ln_trapezoidal_integrate_grid_exp}, bayesian::Model::compute,
+//   BayesFactor::evidence_kass_raftery; statrs 0.18 Hypergeometric::pmf; itertools-num linspace.
+//
+// PARITY PINNING: the reference cannot be compiled here (no cargo/rustc). The oracle is
+// pinned against the reference's own golden pair tests/resources/flamegraph_profiling/
+// {normal.vcf -> calls.vcf} (f32 PHRED / AFD text precision) and the likelihood.rs unit
+// tests (tests/test_oracle_*.py). At 1e-9 in log space parity is "unpinned" by the
+// reference's tests; the oracle defines that target.
+//
+// Where the reference is run-to-run non-deterministic (HashMap iteration order:
+// adaptive_integration.rs:70-82, calling.rs:762-769,851) the oracle fixes: candidates in
+// ascending x, first maximum wins; events in scenario order, last maximum wins for the best
+// event (itertools minmax); base events in first-recorded order for MAP ties.
+//
+// Build: see oracle/Makefile (g++ -O2 -ffp-contract=off: Rust never contracts a*b+c).
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "../include/vlr_engine.h"
+
+namespace {
+
+const double NEG_INF = -std::numeric_limits<double>::infinity();
+const double NUMERICAL_EPSILON = 1e-3; // utils/mod.rs:41
+
+// ---------------------------------------------------------------- rust-bio LogProb
+struct Diag {
+    uint32_t status = 0;
+    double margin_bias = std::numeric_limits<double>::infinity();     // relative distance of a threshold decision
+    double margin_adaptive = std::numeric_limits<double>::infinity(); // |f(best)-f(other)| in adaptive argmax
+    uint64_t n_pileup_evals = 0; // uncached pileup folds
+    uint64_t n_read_evals = 0;   // per-read emissions
+};
+
+inline void note_margin(Diag& d, double lhs, double rhs) {
+    double scale = std::max(std::max(std::fabs(lhs), std::fabs(rhs)), 1e-300);
+    double m = std::fabs(lhs - rhs) / scale;
+    if (m < d.margin_bias) d.margin_bias = m;
+}
+
+inline double ln_add_exp(double a, double b) {
+    double p0 = a, p1 = b;
+    if (p1 > p0) std::swap(p0, p1);
+    if (p0 == NEG_INF) return NEG_INF;
+    if (p1 == NEG_INF) return p0;
+    return p0 + std::log1p(std::exp(p1 - p0));
+}
+
+inline double ln_sum_exp(const std::vector<double>& probs) {
+    if (probs.empty()) return NEG_INF;
+    double pmax = probs[0];
+    size_t imax = 0;
+    for (size_t i = 1; i < probs.size(); ++i) {
+        if (probs[i] > pmax) {
+            pmax = probs[i];
+            imax = i;
+        }
+    }
+    if (pmax == NEG_INF) return NEG_INF;
+    if (pmax == std::numeric_limits<double>::infinity()) return pmax;
+    double s = 0.0;
+    for (size_t i = 0; i < probs.size(); ++i) {
+        if (i == imax || probs[i] == NEG_INF) continue;
+        s += std::exp(probs[i] - pmax);
+    }
+    return pmax + std::log1p(s);
+}
+
+inline double ln_one_minus_exp(double p, Diag& d) {
+    if (!(p <= 0.0)) d.status |= VLR_ST_NAN; // reference: assert!(p <= 0.0)
+    if (p < -0.693) return std::log1p(-std::exp(p));
+    return std::log(-std::expm1(p));
+}
+
+inline double cap_numerical_overshoot(double p, Diag& d) {
+    if (p <= 0.0) return p;
+    if (p - NUMERICAL_EPSILON <= 0.0) return 0.0;
+    d.status |= VLR_ST_OVERSHOOT; // reference panics
+    return 0.0;
+}
+
+// itertools-num linspace: a + step*i
+inline double linspace_at(double a, double b, int n, int i) {
+    double step = (n > 1) ? (b - a) / (double)(n - 1) : 0.0;
+    return a + step * (double)i;
+}
+
+// Kass-Raftery (rust-bio bayes_factors): 0 None, 1 Barely, 2 Positive, 3 Strong, 4 VeryStrong
+inline int kass_raftery(double m1, double m2) {
+    double k = std::exp(m1 - m2);
+    if (k <= 1.0) return 0;
+    if (k <= 3.0) return 1;
+    if (k <= 20.0) return 2;
+    if (k <= 150.0) return 3;
+    return 4;
+}
+
+// ---------------------------------------------------------------- observations
+enum { STRAND_F = 0, STRAND_R = 1, STRAND_BOTH = 2, STRAND_NONE = 3 };
+enum { ORIENT_F1R2 = 0, ORIENT_F2R1 = 1, ORIENT_NONE = 8 };
+enum { ALTLOCUS_MAJOR = 0, ALTLOCUS_SOME = 1, ALTLOCUS_NONE = 2 };
+
+struct Obs { // ProcessedReadObservation, read_observation.rs:221-280
+    double prob_mapping, prob_mismapping;
+    double prob_alt_orig, prob_ref_orig; // BayesFactor predicates use these (read_observation.rs:429-446)
+    double prob_alt, prob_ref;           // after singleton adjustment (accessors :409-415)
+    double prob_missed_allele, prob_sample_alt, prob_double_overlap, prob_single_overlap, prob_hit_base;
+    int strand, orientation, alt_locus;
+    bool major, softclipped, paired, is_max_mapq;
+    bool has_hlen;
+    int hlen;
+    bool has_hart, has_hvar;
+    double hart, hvar;
+
+    bool is_uniquely_mapping() const { return prob_mapping >= std::log(0.95); }
+    bool is_strong_alt_support() const { return kass_raftery(prob_alt_orig, prob_ref_orig) >= 3; }
+    bool is_strong_ref_support() const { return kass_raftery(prob_ref_orig, prob_alt_orig) >= 3; }
+    bool is_positive_ref_support() const { return kass_raftery(prob_ref_orig, prob_alt_orig) >= 2; }
+    bool is_ref_support() const { return prob_ref_orig > prob_alt_orig; }
+};
+typedef std::vector<Obs> Pileup;
+
+// ---------------------------------------------------------------- artifacts (bias/*.rs)
+struct Artifacts {
+    int id = 0;   // 0 none; 1 ALB 2 HE 3 SCB 4 RPB 5 ROB_F1R2 6 ROB_F2R1 7 SB_FWD 8 SB_REV
+                  // (order of Artifacts::all_artifact_combinations, bias/mod.rs:180-217)
+    int sb = 0;   // 0 None{forward_rate}, 1 Forward, 2 Reverse
+    double forward_rate = 0.5;
+    int rob = 0;  // 0 None, 1 F1R2, 2 F2R1
+    int rpb = 0, scb = 0, he = 0, alb = 0;
+    bool has_alt_loci = false;
+    bool is_artifact() const { return id != 0; }
+};
+
+const double LN_05 = std::log(0.5);
+
+// strand_bias.rs:28-53
+inline double sb_prob_alt(const Artifacts& a, const Obs& o) {
+    if (o.strand == STRAND_NONE) return 0.0;
+    if (a.sb == 1) return o.strand == STRAND_F ? 0.0 : NEG_INF;
+    if (a.sb == 2) return o.strand == STRAND_R ? 0.0 : NEG_INF;
+    if (o.strand == STRAND_BOTH) return o.prob_double_overlap;
+    double rate = (o.strand == STRAND_F) ? a.forward_rate : 1.0 - a.forward_rate;
+    return std::log(rate) + o.prob_single_overlap;
+}
+// read_orientation_bias.rs:17-29
+inline double rob_prob_alt(const Artifacts& a, const Obs& o) {
+    if (a.rob == 1) {
+        if (o.orientation == ORIENT_F1R2) return 0.0;
+        if (o.orientation == ORIENT_F2R1) return NEG_INF;
+    } else if (a.rob == 2) {
+        if (o.orientation == ORIENT_F2R1) return 0.0;
+        if (o.orientation == ORIENT_F1R2) return NEG_INF;
+    }
+    return LN_05;
+}
+// read_position_bias.rs:17-61
+inline double one_minus_prob_hit_base(const Obs& o, Diag& d) {
+    if (o.prob_hit_base != 0.0) return ln_one_minus_exp(o.prob_hit_base, d);
+    return 0.0;
+}
+inline double rpb_prob_any(const Obs& o, Diag& d) { return o.major ? o.prob_hit_base : one_minus_prob_hit_base(o, d); }
+inline double rpb_prob_alt(const Artifacts& a, const Obs& o, Diag& d) {
+    if (a.rpb == 0) return rpb_prob_any(o, d);
+    return o.major ? 0.0 : NEG_INF;
+}
+// softclip_bias.rs:14-24
+inline double scb_prob_alt(const Artifacts& a, const Obs& o) {
+    if (a.scb == 1) return o.softclipped ? 0.0 : NEG_INF;
+    return 0.0;
+}
+// homopolymer_error.rs:22-40
+inline double he_prob_alt(const Artifacts& a, const Obs& o) {
+    if (a.he == 1) return o.has_hart ? o.hart : 0.0;
+    return o.has_hvar ? o.hvar : 0.0;
+}
+// alt_locus_bias.rs:62-112
+inline double alb_prob_alt(const Artifacts& a, const Obs& o) {
+    if (a.alb == 1) {
+        if (a.has_alt_loci) return o.alt_locus == ALTLOCUS_MAJOR ? 0.0 : NEG_INF;
+        return o.is_max_mapq ? NEG_INF : 0.0;
+    }
+    return LN_05;
+}
+inline double alb_prob_ref(const Artifacts& a, const Obs& o) {
+    if (a.alb == 1 && a.has_alt_loci) return o.alt_locus == ALTLOCUS_MAJOR ? NEG_INF : 0.0;
+    return LN_05;
+}
+
+// bias/mod.rs:259-284 (sum order: strand, orientation, position, softclip, homopolymer, alt locus)
+inline double art_prob_alt(const Artifacts& a, const Obs& o, Diag& d) {
+    return sb_prob_alt(a, o) + rob_prob_alt(a, o) + rpb_prob_alt(a, o, d) + scb_prob_alt(a, o) + he_prob_alt(a, o) +
+           alb_prob_alt(a, o);
+}
+inline double art_prob_ref(const Artifacts& a, const Obs& o, Diag& d) {
+    return LN_05 + LN_05 + rpb_prob_any(o, d) + 0.0 + he_prob_alt(a, o) + alb_prob_ref(a, o);
+}
+inline double art_prob_any(const Artifacts&, const Obs& o, Diag& d) {
+    return LN_05 + LN_05 + rpb_prob_any(o, d) + 0.0 + 0.0 + LN_05;
+}
+
+// strand_bias.rs:79-123
+bool estimate_forward_rate(const std::vector<Pileup>& pileups, double& rate, Diag& d) {
+    std::vector<double> all, fwd;
+    for (auto& p : pileups)
+        for (auto& o : p)
+            if (o.is_strong_ref_support() && o.strand != STRAND_BOTH) all.push_back(o.prob_mapping);
+    for (auto& p : pileups)
+        for (auto& o : p)
+            if (o.is_strong_ref_support() && o.strand == STRAND_F) fwd.push_back(o.prob_mapping);
+    double strong_all = std::exp(ln_sum_exp(all));
+    double strong_forward = std::exp(ln_sum_exp(fwd));
+    note_margin(d, strong_all, 2.0);
+    if (strong_all > 2.0) {
+        double ff = strong_forward / strong_all;
+        note_margin(d, strong_all, 100.0);
+        if (strong_all > 100.0 && ff > 0.0 && ff < 1.0) {
+            rate = ff;
+            return true;
+        }
+        note_margin(d, ff, 0.4);
+        note_margin(d, ff, 0.6);
+        if (ff >= 0.4 && ff <= 0.6) {
+            rate = 0.5;
+            return true;
+        }
+    }
+    return false;
+}
+
+// read_orientation_bias.rs:38-97
+bool rob_is_informative(const std::vector<Pileup>& pileups) {
+    size_t n_uncertain = 0, n = 0, strong_ref_total = 0, strong_ref_f1r2 = 0;
+    for (auto& p : pileups) {
+        n += p.size();
+        for (auto& o : p) {
+            bool std_or = (o.orientation == ORIENT_F1R2 || o.orientation == ORIENT_F2R1);
+            if (!std_or) n_uncertain++;
+            if (o.is_strong_ref_support() && std_or) strong_ref_total++;
+            if (o.is_strong_ref_support() && o.orientation == ORIENT_F1R2) strong_ref_f1r2++;
+        }
+    }
+    bool enough = (double)n_uncertain < ((double)n / 2.0);
+    bool uniform = false;
+    if (strong_ref_total > 2) {
+        double fraction = (double)strong_ref_f1r2 / (double)strong_ref_total;
+        uniform = fraction >= 0.3 && fraction <= 0.7;
+    }
+    return enough && uniform;
+}
+
+// read_position_bias.rs:63-121
+bool rpb_has_valid_major_rate(const std::vector<Pileup>& pileups, Diag& d) {
+    for (auto& p : pileups) {
+        std::vector<double> all, major, rate;
+        for (auto& o : p)
+            if (o.is_strong_ref_support()) all.push_back(o.prob_mapping);
+        double expected_all = std::exp(ln_sum_exp(all));
+        note_margin(d, expected_all, 10.0);
+        if (expected_all > 10.0) {
+            for (auto& o : p)
+                if (o.is_strong_ref_support() && o.major) major.push_back(o.prob_mapping);
+            for (auto& o : p)
+                if (o.is_strong_ref_support()) rate.push_back(o.prob_mapping + o.prob_hit_base);
+            double expected_major = std::exp(ln_sum_exp(major));
+            double expected_major_rate = std::exp(ln_sum_exp(rate));
+            double major_rate = expected_major / expected_all;
+            note_margin(d, std::fabs(major_rate - expected_major_rate), 0.05);
+            if (expected_major > 0.0 && std::fabs(major_rate - expected_major_rate) < 0.05) return true;
+        }
+    }
+    return false;
+}
+
+// homopolymer_error.rs:46-72
+bool he_is_informative(const std::vector<Pileup>& pileups) {
+    for (auto& p : pileups) {
+        bool any_strong_alt = false, has_ins = false, has_del = false;
+        for (auto& o : p) {
+            if (o.is_strong_alt_support()) any_strong_alt = true;
+            int indel = o.has_hlen ? o.hlen : 0;
+            if (indel > 0) has_ins = true;
+            if (indel < 0) has_del = true;
+        }
+        if (!(!any_strong_alt || (has_ins && has_del))) return false;
+    }
+    return true;
+}
+
+bool has_alt_loci(const std::vector<Pileup>& pileups) {
+    size_t c = 0;
+    for (auto& p : pileups)
+        for (auto& o : p)
+            if (o.alt_locus != ALTLOCUS_NONE) c++;
+    return c > 0;
+}
+
+// alt_locus_bias.rs:124-144
+bool alb_is_informative(const std::vector<Pileup>& pileups) {
+    size_t n_alt = 0, nm_alt = 0, n_ref = 0, nm_ref = 0;
+    for (auto& p : pileups)
+        for (auto& o : p) {
+            if (o.is_strong_alt_support()) {
+                n_alt++;
+                if (!o.is_max_mapq) nm_alt++;
+            }
+            if (o.is_strong_ref_support()) {
+                n_ref++;
+                if (!o.is_max_mapq) nm_ref++;
+            }
+        }
+    bool enough_alt = n_alt > 0 && (double)nm_alt > ((double)n_alt * 0.1) && (n_alt - nm_alt) < 10;
+    bool enough_ref = n_ref > 0 && ((double)nm_ref < ((double)n_ref * 0.9));
+    return enough_alt && (has_alt_loci(pileups) || enough_ref);
+}
+
+// prob_alt of the single artifact component of config `a` (Bias::is_bias_evidence / is_possible)
+inline bool component_evidence(const Artifacts& a, const Obs& o, bool for_likely) {
+    switch (a.id) {
+    case 1: return alb_prob_alt(a, o) != NEG_INF;
+    case 2: // HomopolymerError::is_bias_evidence (homopolymer_error.rs:82-84); is_possible handled elsewhere
+        return for_likely ? ((o.has_hlen ? o.hlen : 0) != 0) : true;
+    case 3: return scb_prob_alt(a, o) != NEG_INF;
+    case 4: return o.major;
+    case 5:
+    case 6: return rob_prob_alt(a, o) != NEG_INF;
+    case 7:
+    case 8: return sb_prob_alt(a, o) != NEG_INF;
+    }
+    return true;
+}
+
+// Artifacts::{is_possible,is_informative,is_likely} (bias/mod.rs:232-257) for a single-artifact config;
+// non-artifact components return true.
+bool config_survives(const Artifacts& a, const std::vector<Pileup>& pileups, Diag& d) {
+    if (!a.is_artifact()) return true;
+    // is_possible
+    bool possible;
+    if (a.id == 2) {
+        possible = he_is_informative(pileups);
+    } else {
+        possible = false;
+        for (auto& p : pileups)
+            for (auto& o : p)
+                if (component_evidence(a, o, false)) possible = true;
+    }
+    if (!possible) return false;
+    // is_informative
+    bool informative = true;
+    switch (a.id) {
+    case 1: informative = alb_is_informative(pileups); break;
+    case 2: informative = he_is_informative(pileups); break;
+    case 3: {
+        informative = false;
+        for (auto& p : pileups)
+            for (auto& o : p)
+                if (o.softclipped) informative = true;
+        break;
+    }
+    case 4: informative = rpb_has_valid_major_rate(pileups, d); break;
+    case 5:
+    case 6: informative = rob_is_informative(pileups); break;
+    case 7:
+    case 8: {
+        double r;
+        informative = estimate_forward_rate(pileups, r, d);
+        break;
+    }
+    }
+    if (!informative) return false;
+    // is_likely (bias/mod.rs:62-104; HomopolymerError overrides with is_informative)
+    if (a.id == 2) return he_is_informative(pileups);
+    for (auto& p : pileups) {
+        size_t strong_all = 0;
+        for (auto& o : p)
+            if (o.is_uniquely_mapping() && o.is_strong_alt_support()) strong_all++;
+        bool likely;
+        if (strong_all >= 10) {
+            size_t ev = 0;
+            for (auto& o : p)
+                if (o.is_uniquely_mapping() && o.is_strong_alt_support() && component_evidence(a, o, true)) ev++;
+            double ratio = (double)ev / (double)strong_all;
+            likely = ratio >= 0.66666;
+        } else {
+            bool all_ref = true;
+            for (auto& o : p)
+                if (!o.is_ref_support()) all_ref = false;
+            if (all_ref) likely = false; // includes the empty pileup
+            else if (p.empty()) likely = false;
+            else likely = true;
+        }
+        if (likely) return true;
+    }
+    return false;
+}
+
+// ---------------------------------------------------------------- VAFRange (formula.rs:1057-1263)
+struct VAFRange {
+    double start, end;
+    bool lex, rex;
+    static VAFRange empty() { return {0.0, 0.0, true, true}; }
+    bool is_empty() const { return start == end && (lex || rex); }
+    bool is_singleton() const { return start == end && !(lex || rex); }
+    bool contains(double v) const {
+        bool l = lex ? (start < v) : (start <= v);
+        bool r = rex ? (end > v) : (end >= v);
+        return l && r;
+    }
+    bool equals(const VAFRange& o) const { return start == o.start && end == o.end && lex == o.lex && rex == o.rex; }
+    // overlap() == None
+    bool no_overlap(const VAFRange& o) const {
+        if (equals(o)) return false;
+        return (end < o.start || start > o.end) || (end <= o.start && (rex || o.lex)) ||
+               (start >= o.end && (lex || o.rex));
+    }
+    VAFRange intersect(const VAFRange& o) const {
+        if (no_overlap(o)) return empty();
+        VAFRange r;
+        r.start = std::max(start, o.start);
+        r.end = std::min(end, o.end);
+        r.lex = start > o.start ? lex : (start < o.start ? o.lex : (lex || o.lex));
+        r.rex = end < o.end ? rex : (end > o.end ? o.rex : (rex || o.rex));
+        return r;
+    }
+    bool adjustment_possible(size_t n) const { return (double)n * (end - start) > 1.0; }
+    double observable_max(size_t n) const {
+        if (n < 10 || !adjustment_possible(n)) return end;
+        double c = (double)n * end;
+        if (rex && std::fmod(c, 1.0) == 0.0) c -= 1.0;
+        c = std::floor(c);
+        if (c == 0.0) return end;
+        return std::floor(c) / (double)n;
+    }
+    double observable_min(size_t n) const {
+        double min_vaf;
+        if (n < 10 || !adjustment_possible(n)) {
+            min_vaf = start;
+        } else {
+            double c = (double)n * start;
+            bool done = false;
+            if (lex && std::fmod(c, 1.0) == 0.0) {
+                double adjusted_end = observable_max(n);
+                for (double offset : {1.0, 0.0}) {
+                    double s = std::ceil(c + offset) / (double)n;
+                    if (s <= 1.0 && s <= adjusted_end) {
+                        return s; // early return bypasses the final order check (formula.rs:1186-1190)
+                    }
+                }
+            }
+            if (!done) min_vaf = std::ceil(c) / (double)n;
+        }
+        if (min_vaf >= observable_max(n)) return start;
+        return min_vaf;
+    }
+};
+
+// log2_fold_change.rs
+struct LfcPred {
+    int cmp;
+    double value;
+};
+inline bool relative_eq(double a, double b) { // approx 0.5 defaults: epsilon = max_relative = f64::EPSILON
+    if (a == b) return true;
+    if (std::isinf(a) || std::isinf(b)) return false;
+    double diff = std::fabs(a - b);
+    const double eps = std::numeric_limits<double>::epsilon();
+    if (diff <= eps) return true;
+    double largest = std::max(std::fabs(a), std::fabs(b));
+    return diff <= largest * eps;
+}
+inline LfcPred lfc_invert(LfcPred p) {
+    switch (p.cmp) {
+    case VLR_CMP_EQ: return {VLR_CMP_EQ, p.value};
+    case VLR_CMP_GT: return {VLR_CMP_LE, -p.value};
+    case VLR_CMP_GE: return {VLR_CMP_LT, -p.value};
+    case VLR_CMP_LT: return {VLR_CMP_GE, -p.value};
+    case VLR_CMP_LE: return {VLR_CMP_GT, -p.value};
+    default: return {VLR_CMP_NE, p.value};
+    }
+}
+inline bool lfc_is_true(LfcPred p, double a, double b, Diag& d) {
+    double lfc;
+    if (a == 0.0 && b == 0.0) lfc = 0.0;
+    else {
+        lfc = std::log2(a) - std::log2(b);
+        if (std::isnan(lfc)) d.status |= VLR_ST_NAN;
+    }
+    switch (p.cmp) {
+    case VLR_CMP_EQ: return relative_eq(lfc, p.value);
+    case VLR_CMP_GT: return lfc > p.value;
+    case VLR_CMP_GE: return lfc >= p.value;
+    case VLR_CMP_LT: return lfc < p.value;
+    case VLR_CMP_LE: return lfc <= p.value;
+    default: return !relative_eq(lfc, p.value);
+    }
+}
+inline VAFRange lfc_infer_bounds(LfcPred p, double vaf) {
+    double proj = vaf / std::exp2(p.value);
+    if (proj < 0.0 || proj > 1.0) return VAFRange::empty();
+    switch (p.cmp) {
+    case VLR_CMP_EQ: return {proj, proj, false, false};
+    case VLR_CMP_GT: return {0.0, proj, false, true};
+    case VLR_CMP_GE: return {0.0, proj, false, false};
+    case VLR_CMP_LT: return {proj, 1.0, true, false};
+    case VLR_CMP_LE: return {proj, 1.0, false, false};
+    default: return {0.0, 1.0, false, false};
+    }
+}
+
+// ---------------------------------------------------------------- model state
+struct SampleEvent { // likelihood::Event
+    double vaf = 0.0;
+    bool discrete = true;
+    bool set = false;
+};
+struct Lfc {
+    int a, b;
+    LfcPred pred;
+};
+struct Operands { // LikelihoodOperands (generic.rs:116-175)
+    SampleEvent ev[VLR_MAX_SAMPLES];
+    std::vector<Lfc> lfcs;
+};
+
+struct BaseEvent {
+    double vaf[VLR_MAX_SAMPLES];
+    bool discrete[VLR_MAX_SAMPLES];
+    int cfg;
+    std::vector<Lfc> lfcs;
+    double joint;
+};
+
+struct Key {
+    uint64_t w[2 * VLR_MAX_SAMPLES + 2];
+    int n;
+    bool operator<(const Key& o) const {
+        if (n != o.n) return n < o.n;
+        return std::memcmp(w, o.w, sizeof(uint64_t) * n) < 0;
+    }
+};
+inline uint64_t dbits(double x) {
+    uint64_t u;
+    std::memcpy(&u, &x, 8);
+    return u;
+}
+
+struct Engine {
+    const vlr_scenario_t* sc;
+    int S;
+    // per locus
+    std::vector<Pileup> pileups;
+    bool has_snv = false;
+    uint8_t refbase = 0, altbase = 0;
+    int vartype = 0;
+    double het_override = NAN, semr_override = NAN; // ln
+    Diag diag;
+    // caches (generic.rs:43-53): one per sample
+    std::vector<std::map<Key, double>> lh_cache;
+    std::map<Key, double> prior_cache;
+    // recorded base events (rust-bio Model::compute)
+    std::vector<BaseEvent> base_events;
+    std::map<Key, size_t> base_index;
+
+    // ---------------- likelihood.rs
+    double prob_sample_alt(const Obs& o, double ln_af) {
+        if (ln_af != 0.0) return cap_numerical_overshoot(ln_af + o.prob_sample_alt, diag);
+        return ln_af;
+    }
+    double likelihood_mapping(double ln_af, const Artifacts& b, const Obs& o) {
+        double psa = prob_sample_alt(o, ln_af);
+        double psr = ln_one_minus_exp(psa, diag);
+        double ba = art_prob_alt(b, o, diag);
+        double br = art_prob_ref(b, o, diag);
+        double t0 = psa + ba + o.prob_alt;
+        double t1 = psr + o.prob_ref + br;
+        std::vector<double> v{t0, t1};
+        double p = ln_sum_exp(v);
+        if (std::isnan(p)) diag.status |= VLR_ST_NAN;
+        return p;
+    }
+    double single_obs(double ln_af, const Artifacts& b, const Obs& o) {
+        double prob = likelihood_mapping(ln_af, b, o);
+        double total = ln_add_exp(o.prob_mapping + prob, o.prob_mismapping + o.prob_missed_allele + art_prob_any(b, o, diag));
+        if (std::isnan(total)) diag.status |= VLR_ST_NAN;
+        return total;
+    }
+    double contaminated_obs(double purity, double impurity, double ln_af_p, double ln_af_s, const Artifacts& b,
+                            const Obs& o) {
+        double prob_primary = purity + likelihood_mapping(ln_af_p, b, o);
+        double prob_secondary = impurity + likelihood_mapping(ln_af_s, b, o);
+        double total = ln_add_exp(o.prob_mapping + ln_add_exp(prob_secondary, prob_primary),
+                                  o.prob_mismapping + o.prob_missed_allele + art_prob_any(b, o, diag));
+        if (std::isnan(total)) diag.status |= VLR_ST_NAN;
+        return total;
+    }
+
+    Key lh_key(const SampleEvent& p, const SampleEvent* s, int cfg) {
+        Key k;
+        k.n = 0;
+        k.w[k.n++] = dbits(p.vaf);
+        k.w[k.n++] = (uint64_t)cfg * 2 + (p.discrete ? 1 : 0);
+        if (s) {
+            k.w[k.n++] = dbits(s->vaf);
+            k.w[k.n++] = (uint64_t)cfg * 2 + (s->discrete ? 1 : 0);
+        }
+        return k;
+    }
+
+    // GenericLikelihood::compute (generic.rs:500-554)
+    double likelihood(const Operands& ops, const Artifacts& b) {
+        for (auto& l : ops.lfcs) {
+            if (!lfc_is_true(l.pred, ops.ev[l.a].vaf, ops.ev[l.b].vaf, diag)) return NEG_INF;
+        }
+        double p = 0.0;
+        for (int s = 0; s < S; ++s) {
+            const vlr_sample_t& sm = sc->samples[s];
+            const Pileup& pile = pileups[s];
+            double lh;
+            if (sm.contamination_by >= 0) {
+                const SampleEvent& sec = ops.ev[sm.contamination_by];
+                Key k = lh_key(ops.ev[s], &sec, b.id);
+                auto it = lh_cache[s].find(k);
+                if (it != lh_cache[s].end()) lh = it->second;
+                else {
+                    double purity = std::log(1.0 - sm.contamination_fraction);
+                    double impurity = ln_one_minus_exp(purity, diag);
+                    double laf_p = std::log(ops.ev[s].vaf), laf_s = std::log(sec.vaf);
+                    lh = 0.0;
+                    for (auto& o : pile) lh = lh + contaminated_obs(purity, impurity, laf_p, laf_s, b, o);
+                    diag.n_pileup_evals++;
+                    diag.n_read_evals += pile.size();
+                    if (std::isnan(lh)) diag.status |= VLR_ST_NAN;
+                    lh_cache[s][k] = lh;
+                }
+            } else {
+                Key k = lh_key(ops.ev[s], nullptr, b.id);
+                auto it = lh_cache[s].find(k);
+                if (it != lh_cache[s].end()) lh = it->second;
+                else {
+                    double laf = std::log(ops.ev[s].vaf);
+                    lh = 0.0;
+                    for (auto& o : pile) lh = lh + single_obs(laf, b, o);
+                    diag.n_pileup_evals++;
+                    diag.n_read_evals += pile.size();
+                    if (std::isnan(lh)) diag.status |= VLR_ST_NAN;
+                    lh_cache[s][k] = lh;
+                }
+            }
+            p += lh;
+        }
+        return p;
+    }
+
+    // ---------------- prior.rs
+    double vtf() const {
+        switch (vartype) {
+        case 1: return sc->vtf_indel;
+        case 2: return sc->vtf_mnv;
+        case 3: return sc->vtf_sv;
+        default: return 1.0;
+        }
+    }
+    bool semr(int s, double& out) const { // variant_or_vartype_somatic_effective_mutation_rate
+        if (!std::isnan(semr_override)) {
+            out = semr_override;
+            return true;
+        }
+        double r = sc->samples[s].somatic_effective_mutation_rate;
+        if (std::isnan(r)) return false;
+        out = std::log(r * vtf());
+        return true;
+    }
+    bool heterozygosity(double& out) const { // variant_or_vartype_heterozygosity
+        if (!std::isnan(het_override)) {
+            out = het_override;
+            return true;
+        }
+        if (std::isnan(sc->heterozygosity)) return false;
+        out = std::log(std::exp(std::log(sc->heterozygosity)) * vtf());
+        return true;
+    }
+    bool universe_contains(int s, double v) const {
+        const vlr_sample_t& sm = sc->samples[s];
+        for (int i = 0; i < sm.n_universe; ++i) {
+            const vlr_spectrum_t& sp = sc->spectra[sm.universe_offset + i];
+            if (sp.kind == VLR_SPECTRUM_SET) {
+                for (int j = 0; j < sp.n_vafs; ++j)
+                    if (sc->set_vafs[sp.vaf_offset + j] == v) return true;
+            } else {
+                VAFRange r{sp.start, sp.end, sp.left_exclusive != 0, sp.right_exclusive != 0};
+                if (r.contains(v)) return true;
+            }
+        }
+        return false;
+    }
+    double prob_somatic_mutation(double rate, double somatic_vaf) {
+        if (relative_eq(somatic_vaf, 0.0)) return ln_one_minus_exp(rate, diag);
+        return rate;
+    }
+    static double binomial(uint64_t n, uint64_t k) { // statrs factorial::binomial
+        if (k > n) return 0.0;
+        auto lnfact = [](uint64_t x) {
+            double f = 1.0;
+            for (uint64_t i = 2; i <= x; ++i) f *= (double)i;
+            return std::log(f);
+        };
+        return std::floor(0.5 + std::exp(lnfact(n) - lnfact(k) - lnfact(n - k)));
+    }
+    double prob_select(uint32_t ploidy, uint32_t source_alt, uint32_t target_alt, uint32_t target_ref) {
+        uint64_t population = ploidy, successes = source_alt, draws = target_alt + target_ref;
+        uint64_t x = target_alt;
+        double pmf;
+        if (x > draws) pmf = 0.0;
+        else pmf = binomial(successes, x) * binomial(population - successes, draws - x) / binomial(population, draws);
+        return std::log(pmf);
+    }
+    double prob_mendelian_alt_counts(uint32_t sp0, uint32_t sp1, uint32_t tp, uint32_t sa0, uint32_t sa1, uint32_t ta,
+                                     double rate) {
+        auto cases = [](uint32_t pl) {
+            std::vector<uint32_t> v;
+            if (pl % 2 == 0) v.push_back(pl / 2);
+            else {
+                double half = (double)pl / 2.0;
+                v.push_back((uint32_t)std::floor(half));
+                v.push_back((uint32_t)std::ceil(half));
+            }
+            return v;
+        };
+        std::vector<double> probs;
+        bool valid = false;
+        for (uint32_t p1 : cases(sp0))
+            for (uint32_t p2 : cases(sp1)) {
+                if (p1 + p2 != tp) continue;
+                valid = true;
+                for (uint32_t a1 = 0; a1 <= std::min(sa0, p1); ++a1)
+                    for (uint32_t a2 = 0; a2 <= std::min(sa1, p2); ++a2) {
+                        if (a1 + a2 <= ta) {
+                            double prob = prob_select(sp0, sa0, a1, p1 - a1) + prob_select(sp1, sa1, a2, p2 - a2);
+                            int missing = (int)ta - (int)(a1 + a2);
+                            probs.push_back(prob + std::log(rate) * (double)missing);
+                        }
+                    }
+            }
+        if (!valid) {
+            diag.status |= VLR_ST_NAN; // reference panics (prior.rs:672-676)
+            return NEG_INF;
+        }
+        return ln_sum_exp(probs);
+    }
+    double eff_somatic(int s, const Operands& ev, const std::vector<double>& g) { return ev.ev[s].vaf - g[s]; }
+
+    double calc_prob(const Operands& ev, std::vector<double> g) {
+        if ((int)g.size() == S) {
+            double prob = 0.0;
+            double het;
+            if (heterozygosity(het)) {
+                std::vector<int> pop;
+                for (int s = 0; s < S; ++s) {
+                    const vlr_sample_t& sm = sc->samples[s];
+                    if (sm.inheritance == VLR_INHERIT_NONE && sm.ploidy >= 0 && !sm.uniform_prior) pop.push_back(s);
+                }
+                uint32_t m = 0;
+                for (int s : pop) m += (uint32_t)std::round((double)sc->samples[s].ploidy * g[s]);
+                if (m > 0) prob = het - std::log((double)m);
+                else {
+                    uint32_t n = 0;
+                    for (int s : pop) n += (uint32_t)sc->samples[s].ploidy;
+                    std::vector<double> v;
+                    for (uint32_t i = 1; i <= n; ++i) v.push_back(het - std::log((double)i));
+                    prob = ln_one_minus_exp(ln_sum_exp(v), diag);
+                }
+            }
+            double sum = 0.0;
+            for (int s = 0; s < S; ++s) {
+                const vlr_sample_t& sm = sc->samples[s];
+                if (sm.uniform_prior) continue;
+                double rate;
+                switch (sm.inheritance) {
+                case VLR_INHERIT_MENDELIAN: {
+                    auto nalt = [&](int x) { return (uint32_t)std::round(g[x] * (double)sc->samples[x].ploidy); };
+                    double gr = sc->samples[s].germline_mutation_rate * vtf();
+                    double p = prob_mendelian_alt_counts(sc->samples[sm.parent_a].ploidy, sc->samples[sm.parent_b].ploidy,
+                                                         sm.ploidy, nalt(sm.parent_a), nalt(sm.parent_b), nalt(s), gr);
+                    if (semr(s, rate)) p += prob_somatic_mutation(rate, eff_somatic(s, ev, g));
+                    sum += p;
+                    break;
+                }
+                case VLR_INHERIT_CLONAL: {
+                    int parent = sm.parent_a;
+                    double p;
+                    if (!relative_eq(g[s], g[parent])) p = NEG_INF;
+                    else {
+                        bool has_rate = semr(s, rate);
+                        if (sm.clonal_somatic && has_rate) {
+                            double psv = eff_somatic(parent, ev, g);
+                            double sv = eff_somatic(s, ev, g);
+                            p = (psv != 0.0) ? 0.0 : prob_somatic_mutation(rate, sv);
+                        } else if (sm.clonal_somatic && !has_rate) {
+                            p = relative_eq(eff_somatic(s, ev, g), eff_somatic(parent, ev, g)) ? 0.0 : NEG_INF;
+                        } else if (has_rate) {
+                            p = prob_somatic_mutation(rate, eff_somatic(s, ev, g));
+                        } else p = 0.0;
+                    }
+                    sum += p;
+                    break;
+                }
+                case VLR_INHERIT_SUBCLONAL: {
+                    int parent = sm.parent_a;
+                    double p;
+                    if (!relative_eq(g[s], g[parent])) p = NEG_INF;
+                    else if (semr(s, rate)) {
+                        if (ev.ev[parent].vaf == 0.0 && g[s] == 0.0) p = prob_somatic_mutation(rate, ev.ev[s].vaf);
+                        else p = 0.0;
+                    } else {
+                        p = relative_eq(eff_somatic(s, ev, g), eff_somatic(parent, ev, g)) ? 0.0 : NEG_INF;
+                    }
+                    sum += p;
+                    break;
+                }
+                default:
+                    if (semr(s, rate)) sum += prob_somatic_mutation(rate, eff_somatic(s, ev, g));
+                }
+            }
+            prob += sum;
+            if (!(prob <= 0.0)) diag.status |= VLR_ST_PRIOR_POSITIVE;
+            return prob;
+        }
+        int s = (int)g.size();
+        const vlr_sample_t& sm = sc->samples[s];
+        double v = ev.ev[s].vaf;
+        auto push = [&](double x) {
+            std::vector<double> g2 = g;
+            g2.push_back(x);
+            return g2;
+        };
+        if (sm.ploidy == 0 && v != 0.0) return NEG_INF;
+        if (sm.uniform_prior) {
+            if (universe_contains(s, v)) return calc_prob(ev, push(0.0));
+            return NEG_INF;
+        }
+        if (!std::isnan(sm.somatic_effective_mutation_rate)) {
+            std::vector<double> probs;
+            for (int n_alt = 0; n_alt <= sm.ploidy; ++n_alt) {
+                double gv = sm.ploidy > 0 ? (double)n_alt / (double)sm.ploidy : 0.0;
+                probs.push_back(calc_prob(ev, push(gv)));
+            }
+            return ln_sum_exp(probs);
+        }
+        if (sm.ploidy >= 0 && !std::isnan(sc->heterozygosity)) {
+            double n_alt = (double)sm.ploidy * v;
+            if (relative_eq(n_alt, std::round(n_alt))) return calc_prob(ev, push(v));
+            return NEG_INF;
+        }
+        diag.status |= VLR_ST_NAN; // unreachable!() in the reference
+        return NEG_INF;
+    }
+
+    bool is_all_uniform() const {
+        for (int s = 0; s < S; ++s)
+            if (!sc->samples[s].uniform_prior) return false;
+        return true;
+    }
+
+    double prior_cached(const Operands& ev) {
+        Key k;
+        k.n = 0;
+        for (int s = 0; s < S; ++s) k.w[k.n++] = dbits(ev.ev[s].vaf);
+        auto it = prior_cache.find(k);
+        if (it != prior_cache.end()) return it->second;
+        double p = calc_prob(ev, {});
+        prior_cache[k] = p;
+        return p;
+    }
+
+    // Prior::compute (prior.rs:718-761)
+    double prior(const Operands& ev) {
+        bool absent = true, discrete = true;
+        for (int s = 0; s < S; ++s) {
+            if (ev.ev[s].vaf != 0.0) absent = false;
+            if (!ev.ev[s].discrete) discrete = false;
+        }
+        if (!sc->full_prior && !is_all_uniform()) {
+            if (!absent) {
+                double full = prior_cached(ev);
+                if (full == NEG_INF) return full;
+                Operands z;
+                for (int s = 0; s < S; ++s) {
+                    z.ev[s].vaf = 0.0;
+                    z.ev[s].discrete = true;
+                    z.ev[s].set = true;
+                }
+                return ln_one_minus_exp(prior_cached(z), diag);
+            }
+            return prior_cached(ev);
+        }
+        if (discrete) return prior_cached(ev);
+        return calc_prob(ev, {});
+    }
+
+    // ---------------- joint (rust-bio Model::joint_prob + recording)
+    double joint(const Operands& ops, const Artifacts& b) {
+        double j = prior(ops) + likelihood(ops, b);
+        Key k;
+        k.n = 0;
+        for (int s = 0; s < S; ++s) {
+            k.w[k.n++] = dbits(ops.ev[s].vaf);
+            k.w[k.n++] = ops.ev[s].discrete ? 1 : 0;
+        }
+        k.w[k.n++] = (uint64_t)b.id;
+        uint64_t h = 1469598103934665603ull;
+        for (auto& l : ops.lfcs) {
+            uint64_t parts[4] = {(uint64_t)l.a, (uint64_t)l.b, (uint64_t)l.pred.cmp, dbits(l.pred.value)};
+            for (uint64_t x : parts) h = (h ^ x) * 1099511628211ull;
+        }
+        k.w[k.n++] = ops.lfcs.empty() ? 0 : h;
+        auto it = base_index.find(k);
+        if (it == base_index.end()) {
+            BaseEvent be;
+            for (int s = 0; s < S; ++s) {
+                be.vaf[s] = ops.ev[s].vaf;
+                be.discrete[s] = ops.ev[s].discrete;
+            }
+            be.cfg = b.id;
+            be.lfcs = ops.lfcs;
+            be.joint = j;
+            base_index[k] = base_events.size();
+            base_events.push_back(be);
+        } else {
+            base_events[it->second].joint = j;
+        }
+        return j;
+    }
+
+    // ---------------- adaptive integration (adaptive_integration.rs:25-141)
+    template <typename F> double adaptive_integrate(F density, double min_point, double max_point, double res) {
+        std::map<double, double> probs; // keyed by x; insertion overwrites like HashMap::insert
+        auto grid_point = [&](double x) {
+            probs[x] = density(x);
+            return x;
+        };
+        auto mid_of = [](double l, double r) { return (r + l) / 2.0; };
+        double left = grid_point(min_point);
+        double right = grid_point(max_point);
+        bool have_first = false, have_middle = false;
+        double first_middle = 0.0, middle = 0.0;
+        while ((((right - left) >= res) && left < right) || !have_middle) {
+            middle = grid_point(mid_of(left, right));
+            have_middle = true;
+            double m1 = grid_point(mid_of(left, middle));
+            double m2 = grid_point(mid_of(middle, right));
+            if (!have_first) {
+                first_middle = middle;
+                have_first = true;
+            }
+            double xs[4] = {left, m1, m2, right};
+            double vs[4];
+            for (int i = 0; i < 4; ++i) vs[i] = probs[xs[i]];
+            int idx = 0;
+            for (int i = 1; i < 4; ++i)
+                if (vs[i] > vs[idx]) idx = i;
+            for (int i = 0; i < 4; ++i) {
+                if (i == idx || xs[i] == xs[idx]) continue;
+                if (vs[i] == NEG_INF && vs[idx] == NEG_INF) continue;
+                double m = std::fabs(vs[idx] - vs[i]);
+                if (m < diag.margin_adaptive) diag.margin_adaptive = m;
+            }
+            left = idx > 0 ? xs[idx - 1] : xs[idx];
+            right = idx < 3 ? xs[idx + 1] : xs[idx];
+        }
+        if (middle < first_middle) grid_point(mid_of(first_middle, max_point));
+        else grid_point(mid_of(min_point, first_middle));
+        double lo = std::max(middle - (res * 3.0), min_point);
+        for (int i = 0; i < 3; ++i) grid_point(linspace_at(lo, middle, 4, i));
+        double hi = std::min(middle + (res * 3.0), max_point);
+        for (int i = 1; i < 4; ++i) grid_point(linspace_at(middle, hi, 4, i));
+        // ln_trapezoidal_integrate_grid_exp over the sorted grid
+        double integral = NEG_INF;
+        auto it = probs.begin();
+        auto prev = it++;
+        for (; it != probs.end(); prev = it, ++it) {
+            double term = ln_add_exp(prev->second, it->second) + std::log(it->first - prev->first) - std::log(2.0);
+            integral = ln_add_exp(integral, term);
+        }
+        return integral;
+    }
+
+    template <typename F> double simpson(F density, double a, double b, int n) {
+        std::vector<double> probs;
+        for (int i = 1; i < n - 1; ++i) {
+            double weight = (double)(2 + (i % 2) * 2);
+            probs.push_back(density(linspace_at(a, b, n, i)) + std::log(weight));
+        }
+        probs.push_back(density(a));
+        probs.push_back(density(b));
+        double width = b - a;
+        return ln_sum_exp(probs) + std::log(width) - std::log((double)(n - 1)) - std::log(3.0);
+    }
+
+    // LikelihoodOperands::lfc_bounds (generic.rs:148-174)
+    bool lfc_bounds(const Operands& ops, int sample, VAFRange& out) {
+        bool have = false;
+        for (auto& l : ops.lfcs) {
+            bool got = false;
+            VAFRange b;
+            if (l.a == sample) {
+                if (ops.ev[l.b].set) {
+                    b = lfc_infer_bounds(lfc_invert(l.pred), ops.ev[l.b].vaf);
+                    got = true;
+                }
+            } else if (l.b == sample) {
+                if (ops.ev[l.a].set) {
+                    b = lfc_infer_bounds(l.pred, ops.ev[l.a].vaf);
+                    got = true;
+                }
+            }
+            if (got) {
+                out = have ? out.intersect(b) : b;
+                have = true;
+            }
+        }
+        return have;
+    }
+
+    static bool iupac_contains(int mask, uint8_t base) {
+        int b = 0;
+        switch (base) {
+        case 'A': case 'a': b = 1; break;
+        case 'C': case 'c': b = 2; break;
+        case 'G': case 'g': b = 4; break;
+        case 'T': case 't': b = 8; break;
+        }
+        return (mask & b) != 0;
+    }
+
+    // GenericPosterior::density (generic.rs:191-422)
+    double density(int ni, Operands& ops, const Artifacts& biases) {
+        const vlr_node_t& node = sc->nodes[ni];
+        auto subdensity = [&](Operands& o) -> double {
+            double p;
+            if (node.n_children == 0) p = joint(o, biases);
+            else if (node.n_children > 1) {
+                std::vector<double> v;
+                for (int c = 0; c < node.n_children; ++c) {
+                    Operands cl = o;
+                    v.push_back(density(node.first_child + c, cl, biases));
+                }
+                p = ln_sum_exp(v);
+            } else p = density(node.first_child, o, biases);
+            if (std::isnan(p)) diag.status |= VLR_ST_NAN;
+            return p;
+        };
+        switch (node.kind) {
+        case VLR_NODE_LFC:
+            ops.lfcs.push_back({node.sample, node.sample_b, {node.cmp, node.lfc_value}});
+            return subdensity(ops);
+        case VLR_NODE_FALSE: return NEG_INF;
+        case VLR_NODE_TRUE: return 0.0;
+        case VLR_NODE_VARIANT: {
+            if (has_snv) {
+                bool contains = iupac_contains(node.refmask, refbase) && iupac_contains(node.altmask, altbase);
+                if ((node.variant_positive && !contains) || (!node.variant_positive && contains)) return NEG_INF;
+                return subdensity(ops);
+            } else if (node.variant_positive) return NEG_INF;
+            return subdensity(ops);
+        }
+        default: break;
+        }
+        int sample = node.sample;
+        auto push_base = [&](double vaf, Operands& o, bool discrete) {
+            o.ev[sample].vaf = vaf;
+            o.ev[sample].discrete = discrete;
+            o.ev[sample].set = true;
+        };
+        VAFRange bounds;
+        bool have_bounds = lfc_bounds(ops, sample, bounds);
+        if (have_bounds && bounds.is_empty()) return NEG_INF;
+        const Pileup& pile = pileups[sample];
+        size_t n_obs = pile.size();
+        bool is_clear_ref = n_obs > 10;
+        if (is_clear_ref)
+            for (auto& o : pile)
+                if (!o.is_positive_ref_support()) {
+                    is_clear_ref = false;
+                    break;
+                }
+        if (node.kind == VLR_NODE_SET) {
+            bool all_pos = true;
+            for (int i = 0; i < node.n_vafs; ++i)
+                if (!(sc->set_vafs[node.vaf_offset + i] > 0.0)) all_pos = false;
+            if (is_clear_ref && all_pos) return NEG_INF;
+            std::vector<double> vafs;
+            for (int i = 0; i < node.n_vafs; ++i) {
+                double v = sc->set_vafs[node.vaf_offset + i];
+                if (!have_bounds || bounds.contains(v)) vafs.push_back(v);
+            }
+            if (vafs.size() == 1) {
+                push_base(vafs[0], ops, true);
+                return subdensity(ops);
+            }
+            std::vector<double> vals;
+            for (double v : vafs) {
+                Operands cl = ops;
+                push_base(v, cl, true);
+                vals.push_back(subdensity(cl));
+            }
+            return ln_sum_exp(vals);
+        }
+        // RANGE
+        VAFRange vafs{node.start, node.end, node.left_exclusive != 0, node.right_exclusive != 0};
+        if (have_bounds) vafs = vafs.intersect(bounds);
+        if (vafs.is_empty()) return NEG_INF;
+        if (is_clear_ref && vafs.start > 0.0) return NEG_INF;
+        if (vafs.is_singleton()) {
+            push_base(vafs.start, ops, true);
+            return subdensity(ops);
+        }
+        double res = sc->samples[sample].resolution;
+        double min_vaf = vafs.observable_min(n_obs);
+        double max_vaf = vafs.observable_max(n_obs);
+        if (!(min_vaf <= max_vaf)) diag.status |= VLR_ST_NAN; // reference asserts
+        auto dens = [&](double vaf) {
+            Operands cl = ops;
+            push_base(vaf, cl, false);
+            return subdensity(cl);
+        };
+        if ((max_vaf - min_vaf) < res) return simpson(dens, min_vaf, max_vaf, 3);
+        if (n_obs < 5) return simpson(dens, min_vaf, max_vaf, 11);
+        return adaptive_integrate(dens, min_vaf, max_vaf, res);
+    }
+
+    // VAFTree::contains / Node::contains (vaftree.rs:42-51,116-164)
+    bool node_contains(int ni, const BaseEvent& be, std::vector<Lfc>& lfcs, int exclude) {
+        const vlr_node_t& node = sc->nodes[ni];
+        bool contained = true;
+        switch (node.kind) {
+        case VLR_NODE_SET:
+        case VLR_NODE_RANGE: {
+            if (exclude == node.sample) return true;
+            double v = be.vaf[node.sample];
+            if (node.kind == VLR_NODE_SET) {
+                contained = false;
+                for (int i = 0; i < node.n_vafs; ++i)
+                    if (sc->set_vafs[node.vaf_offset + i] == v) contained = true;
+            } else {
+                VAFRange r{node.start, node.end, node.left_exclusive != 0, node.right_exclusive != 0};
+                contained = r.contains(v);
+            }
+            break;
+        }
+        case VLR_NODE_LFC: {
+            bool found_any = false;
+            std::vector<Lfc> keep;
+            for (auto& l : lfcs) {
+                bool found = l.a == node.sample && l.b == node.sample_b && l.pred.cmp == node.cmp &&
+                             l.pred.value == node.lfc_value;
+                found_any |= found;
+                if (!found) keep.push_back(l);
+            }
+            lfcs = keep;
+            contained = found_any;
+            break;
+        }
+        case VLR_NODE_FALSE: contained = false; break;
+        default: contained = true;
+        }
+        if (node.n_children == 0) return contained && lfcs.empty();
+        if (!contained) return false;
+        for (int c = 0; c < node.n_children; ++c) {
+            if (node.n_children == 1) {
+                if (node_contains(node.first_child + c, be, lfcs, exclude)) return true;
+            } else {
+                std::vector<Lfc> cl = lfcs;
+                if (node_contains(node.first_child + c, be, cl, exclude)) return true;
+            }
+        }
+        return false;
+    }
+    bool event_contains(int e, const BaseEvent& be, int exclude) {
+        const vlr_event_t& ev = sc->events[e];
+        for (int r = 0; r < ev.n_roots; ++r) {
+            std::vector<Lfc> lfcs = be.lfcs;
+            if (node_contains(ev.first_root + r, be, lfcs, exclude)) return true;
+        }
+        return false;
+    }
+
+    // ---------------- one locus: preprocess_record + call_record + sample_infos
+    void call_locus(const vlr_batch_t* b, int64_t locus, vlr_results_t* res) {
+        diag = Diag();
+        pileups.assign(S, Pileup());
+        lh_cache.assign(S, {});
+        prior_cache.clear();
+        base_events.clear();
+        base_index.clear();
+        uint32_t lf = b->locus_flags[locus];
+        has_snv = (lf & VLR_LF_HAS_SNV) != 0;
+        refbase = (lf >> VLR_LF_REFBASE_SHIFT) & 0xff;
+        altbase = (lf >> VLR_LF_ALTBASE_SHIFT) & 0xff;
+        vartype = (lf >> VLR_LF_VARTYPE_SHIFT) & 3;
+        het_override = NAN;
+        semr_override = NAN;
+        if (b->locus_heterozygosity_phred && !std::isnan(b->locus_heterozygosity_phred[locus]))
+            het_override = (double)b->locus_heterozygosity_phred[locus] * (-std::log(10.0) / 10.0);
+        if (b->locus_semr_phred && !std::isnan(b->locus_semr_phred[locus]))
+            semr_override = (double)b->locus_semr_phred[locus] * (-std::log(10.0) / 10.0);
+
+        // read_observations (preprocessing/mod.rs:869-910) + remove_nonstandard_alignments (pileup.rs:26-43)
+        bool filtered = false;
+        for (int s = 0; s < S; ++s) {
+            int64_t lo = b->read_offsets[locus * S + s], hi = b->read_offsets[locus * S + s + 1];
+            for (int64_t r = lo; r < hi; ++r) {
+                Obs o;
+                uint32_t f = b->read_flags[r];
+                o.strand = (f >> VLR_RF_STRAND_SHIFT) & 3;
+                o.orientation = (f >> VLR_RF_ORIENT_SHIFT) & 15;
+                if ((lf & VLR_LF_FILTER_NONSTANDARD) &&
+                    !(o.orientation == ORIENT_F1R2 || o.orientation == ORIENT_F2R1 || o.orientation == ORIENT_NONE)) {
+                    filtered = true;
+                    continue;
+                }
+                o.prob_mapping = (double)b->prob_mapping[r];
+                o.prob_mismapping = ln_one_minus_exp(o.prob_mapping, diag);
+                o.prob_alt_orig = o.prob_alt = (double)b->prob_alt[r];
+                o.prob_ref_orig = o.prob_ref = (double)b->prob_ref[r];
+                o.prob_missed_allele = (double)b->prob_missed_allele[r];
+                o.prob_sample_alt = (double)b->prob_sample_alt[r];
+                o.prob_double_overlap = (double)b->prob_double_overlap[r];
+                o.prob_single_overlap = ln_one_minus_exp(o.prob_double_overlap, diag);
+                o.prob_hit_base = (double)b->prob_hit_base[r];
+                o.major = (f & VLR_RF_READPOS_MAJOR) != 0;
+                o.softclipped = (f & VLR_RF_SOFTCLIPPED) != 0;
+                o.paired = (f & VLR_RF_PAIRED) != 0;
+                o.is_max_mapq = (f & VLR_RF_MAX_MAPQ) != 0;
+                o.alt_locus = (f >> VLR_RF_ALTLOCUS_SHIFT) & 3;
+                o.has_hlen = (f & VLR_RF_HAS_HOMOPOLYMER_LEN) != 0;
+                o.hlen = (int)(int8_t)((f >> VLR_RF_HOMOPOLYMER_LEN_SHIFT) & 0xff);
+                o.has_hart = b->prob_homopolymer_artifact && !std::isnan(b->prob_homopolymer_artifact[r]);
+                o.hart = o.has_hart ? (double)b->prob_homopolymer_artifact[r] : 0.0;
+                o.has_hvar = b->prob_homopolymer_variant && !std::isnan(b->prob_homopolymer_variant[r]);
+                o.hvar = o.has_hvar ? (double)b->prob_homopolymer_variant[r] : 0.0;
+                pileups[s].push_back(o);
+            }
+        }
+        if (filtered) diag.status |= VLR_ST_FILTERED_NONSTANDARD;
+        // adjust_singleton_evidence (read_observation.rs:548-562)
+        {
+            Obs* single = nullptr;
+            size_t n_alt = 0;
+            for (auto& p : pileups)
+                for (auto& o : p)
+                    if (o.prob_alt_orig > o.prob_ref_orig) {
+                        n_alt++;
+                        single = &o;
+                    }
+            if (n_alt == 1) {
+                single->prob_alt = LN_05;
+                single->prob_ref = LN_05;
+                diag.status |= VLR_ST_SINGLETON_ADJUSTED;
+            }
+        }
+
+        // event universe (calling.rs:655-687) + learn_parameters (calling.rs:750-757)
+        Artifacts none;
+        {
+            double r;
+            none.forward_rate = estimate_forward_rate(pileups, r, diag) ? r : 0.5;
+        }
+        std::vector<Artifacts> twins;
+        {
+            bool c_rob = lf & VLR_LF_CHECK_ROB, c_sb = lf & VLR_LF_CHECK_SB, c_rpb = lf & VLR_LF_CHECK_RPB,
+                 c_scb = lf & VLR_LF_CHECK_SCB, c_he = lf & VLR_LF_CHECK_HE, c_alb = lf & VLR_LF_CHECK_ALB;
+            auto mk = [&](int id) {
+                Artifacts a = none;
+                a.id = id;
+                return a;
+            };
+            if (c_alb) {
+                Artifacts a = mk(1);
+                a.alb = 1;
+                a.has_alt_loci = has_alt_loci(pileups);
+                twins.push_back(a);
+            }
+            if (c_he) {
+                Artifacts a = mk(2);
+                a.he = 1;
+                twins.push_back(a);
+            }
+            if (c_scb) {
+                Artifacts a = mk(3);
+                a.scb = 1;
+                twins.push_back(a);
+            }
+            if (c_rpb) {
+                Artifacts a = mk(4);
+                a.rpb = 1;
+                twins.push_back(a);
+            }
+            if (c_rob) {
+                Artifacts a = mk(5);
+                a.rob = 1;
+                twins.push_back(a);
+                a = mk(6);
+                a.rob = 2;
+                twins.push_back(a);
+            }
+            if (c_sb) {
+                Artifacts a = mk(7);
+                a.sb = 1;
+                twins.push_back(a);
+                a = mk(8);
+                a.sb = 2;
+                twins.push_back(a);
+            }
+        }
+        std::vector<const Artifacts*> surviving;
+        for (auto& a : twins)
+            if (config_survives(a, pileups, diag)) surviving.push_back(&a);
+
+        // Model::compute: joint per universe event
+        int E = sc->n_events;
+        std::vector<double> ev_joint; // universe order
+        std::vector<int> ev_scen;     // scenario event index
+        std::vector<bool> ev_art;
+        for (int e = 0; e < E; ++e) {
+            const vlr_event_t& ev = sc->events[e];
+            // GenericPosterior::compute (generic.rs:430-460)
+            {
+                std::vector<double> terms;
+                for (int r = 0; r < ev.n_roots; ++r) {
+                    Operands ops;
+                    terms.push_back(LN_05 + density(ev.first_root + r, ops, none));
+                }
+                ev_joint.push_back(ln_sum_exp(terms));
+                ev_scen.push_back(e);
+                ev_art.push_back(false);
+            }
+            if (ev.has_artifact_twin && !twins.empty()) {
+                double bias_prior = LN_05 + std::log(1.0 / (double)twins.size());
+                std::vector<double> terms;
+                for (auto* a : surviving)
+                    for (int r = 0; r < ev.n_roots; ++r) {
+                        Operands ops;
+                        terms.push_back(bias_prior + density(ev.first_root + r, ops, *a));
+                    }
+                ev_joint.push_back(ln_sum_exp(terms));
+                ev_scen.push_back(e);
+                ev_art.push_back(true);
+            }
+        }
+        double marginal = ln_sum_exp(ev_joint);
+        if (marginal == NEG_INF) diag.status |= VLR_ST_MARGINAL_ZERO;
+
+        // call_record (calling.rs:762-803)
+        size_t best = 0;
+        {
+            double bestv = ev_joint[0] - marginal;
+            for (size_t i = 1; i < ev_joint.size(); ++i) {
+                double v = ev_joint[i] - marginal;
+                if (v >= bestv) { // itertools minmax: last maximum wins
+                    bestv = v;
+                    best = i;
+                }
+            }
+        }
+        double* lp = res->log_posteriors + locus * (E + 1);
+        std::vector<double> art_post;
+        for (size_t i = 0; i < ev_joint.size(); ++i) {
+            double post = ev_joint[i] - marginal;
+            if (ev_art[i]) art_post.push_back(post);
+            else lp[ev_scen[i]] = post;
+        }
+        double prob_artifact = ln_sum_exp(art_post);
+        lp[E] = prob_artifact;
+        bool is_artifact = true;
+        for (int e = 0; e < E; ++e)
+            if (!(lp[e] < prob_artifact)) is_artifact = false;
+        if (is_artifact) diag.status |= VLR_ST_IS_ARTIFACT;
+        if (res->log_marginal) res->log_marginal[locus] = marginal;
+        if (res->best_event) res->best_event[locus] = 2 * ev_scen[best] + (ev_art[best] ? 1 : 0);
+        if (res->n_base_events) res->n_base_events[locus] = (uint32_t)base_events.size();
+
+        // sample_infos (calling.rs:844-937): descending posterior, stable
+        std::vector<size_t> order(base_events.size());
+        for (size_t i = 0; i < order.size(); ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(),
+                         [&](size_t a, size_t b2) { return base_events[a].joint > base_events[b2].joint; });
+        int best_scen = ev_scen[best];
+        const BaseEvent* map = nullptr;
+        for (size_t oi : order) {
+            const BaseEvent& be = base_events[oi];
+            if (be.cfg != 0 && !is_artifact) continue;
+            if (!event_contains(best_scen, be, -1)) continue;
+            map = &be;
+            break;
+        }
+        for (int s = 0; s < S; ++s) res->map_vaf[locus * S + s] = NAN;
+        if (res->map_config) res->map_config[locus] = 0;
+        if (res->afd_capacity > 0)
+            for (int s = 0; s < S; ++s) res->afd_count[locus * S + s] = 0;
+        if (!map) diag.status |= VLR_ST_NO_MAP;
+        else {
+            if (res->map_config) res->map_config[locus] = map->cfg;
+            for (int s = 0; s < S; ++s) {
+                res->map_vaf[locus * S + s] = map->cfg != 0 ? 0.0 : map->vaf[s];
+                if (res->afd_capacity > 0 && map->cfg == 0) {
+                    std::map<double, double> dist;
+                    for (size_t oi : order) {
+                        const BaseEvent& be = base_events[oi];
+                        if (!event_contains(best_scen, be, s)) continue;
+                        if (be.cfg != 0) continue;
+                        bool others = true;
+                        for (int t = 0; t < S; ++t) {
+                            if (t == s) continue;
+                            if (!(be.vaf[t] == map->vaf[t] && be.discrete[t] == map->discrete[t] && be.cfg == map->cfg))
+                                others = false;
+                        }
+                        if (others) dist[be.vaf[s]] = be.joint - marginal;
+                    }
+                    int n = 0;
+                    for (auto& kv : dist) {
+                        if (n >= res->afd_capacity) {
+                            diag.status |= VLR_ST_AFD_TRUNCATED;
+                            break;
+                        }
+                        res->afd_vaf[(locus * S + s) * res->afd_capacity + n] = kv.first;
+                        res->afd_logp[(locus * S + s) * res->afd_capacity + n] = kv.second;
+                        n++;
+                    }
+                    res->afd_count[locus * S + s] = n;
+                }
+            }
+        }
+        res->status[locus] = diag.status;
+    }
+};
+
+} // namespace
+
+extern "C" {
+
+// Extra per-locus diagnostics only the oracle provides (all optional).
+typedef struct {
+    double* margin_bias;     // [n_loci] min relative distance of a bias threshold decision
+    double* margin_adaptive; // [n_loci] min |f(best) - f(other)| over adaptive argmax decisions
+    uint64_t* n_pileup_evals; // [n_loci]
+    uint64_t* n_read_evals;   // [n_loci]
+} vlr_oracle_diag_t;
+
+// Same contract as vlr_call_batch (include/vlr_engine.h), computed sequentially on the CPU;
+// n_threads > 1 splits the locus range over worker threads (scatter/gather analogue).
+int32_t vlr_oracle_call_batch(const vlr_scenario_t* sc, const vlr_batch_t* batch, vlr_results_t* results,
+                              vlr_oracle_diag_t* diag, int32_t n_threads) {
+    if (!sc || !batch || !results || sc->abi_version != VLR_ABI_VERSION) return VLR_ERR_INVALID_ARGUMENT;
+    if (sc->n_samples < 1 || sc->n_samples > VLR_MAX_SAMPLES) return VLR_ERR_INVALID_ARGUMENT;
+    if (n_threads < 1) n_threads = 1;
+    auto work = [&](int64_t lo, int64_t hi) {
+        Engine eng;
+        eng.sc = sc;
+        eng.S = sc->n_samples;
+        for (int64_t i = lo; i < hi; ++i) {
+            eng.call_locus(batch, i, results);
+            if (diag) {
+                if (diag->margin_bias) diag->margin_bias[i] = eng.diag.margin_bias;
+                if (diag->margin_adaptive) diag->margin_adaptive[i] = eng.diag.margin_adaptive;
+                if (diag->n_pileup_evals) diag->n_pileup_evals[i] = eng.diag.n_pileup_evals;
+                if (diag->n_read_evals) diag->n_read_evals[i] = eng.diag.n_read_evals;
+            }
+        }
+    };
+    if (n_threads == 1) {
+        work(0, batch->n_loci);
+    } else {
+        std::vector<std::thread> th;
+        int64_t n = batch->n_loci;
+        for (int t = 0; t < n_threads; ++t) {
+            int64_t lo = n * t / n_threads, hi = n * (t + 1) / n_threads;
+            th.emplace_back(work, lo, hi);
+        }
+        for (auto& t : th) t.join();
+    }
+    return VLR_OK;
+}
+
+// Unit-level entry points used by tests that restate likelihood.rs:273-394.
+// Single-sample (contaminated_by < 0) or contaminated pileup log-likelihood with Artifacts::none().
+double vlr_oracle_pileup_likelihood(const vlr_batch_t* batch, int64_t lo, int64_t hi, double vaf, double vaf_secondary,
+                                    double purity, int32_t contaminated) {
+    Engine eng;
+    static vlr_scenario_t dummy;
+    eng.sc = &dummy;
+    eng.S = 1;
+    Artifacts none;
+    double lh = 0.0;
+    for (int64_t r = lo; r < hi; ++r) {
+        Obs o;
+        uint32_t f = batch->read_flags[r];
+        o.strand = (f >> VLR_RF_STRAND_SHIFT) & 3;
+        o.orientation = (f >> VLR_RF_ORIENT_SHIFT) & 15;
+        o.prob_mapping = (double)batch->prob_mapping[r];
+        o.prob_mismapping = ln_one_minus_exp(o.prob_mapping, eng.diag);
+        o.prob_alt_orig = o.prob_alt = (double)batch->prob_alt[r];
+        o.prob_ref_orig = o.prob_ref = (double)batch->prob_ref[r];
+        o.prob_missed_allele = (double)batch->prob_missed_allele[r];
+        o.prob_sample_alt = (double)batch->prob_sample_alt[r];
+        o.prob_double_overlap = (double)batch->prob_double_overlap[r];
+        o.prob_single_overlap = ln_one_minus_exp(o.prob_double_overlap, eng.diag);
+        o.prob_hit_base = (double)batch->prob_hit_base[r];
+        o.major = (f & VLR_RF_READPOS_MAJOR) != 0;
+        o.softclipped = (f & VLR_RF_SOFTCLIPPED) != 0;
+        o.paired = (f & VLR_RF_PAIRED) != 0;
+        o.is_max_mapq = (f & VLR_RF_MAX_MAPQ) != 0;
+        o.alt_locus = (f >> VLR_RF_ALTLOCUS_SHIFT) & 3;
+        o.has_hlen = false;
+        o.hlen = 0;
+        o.has_hart = o.has_hvar = false;
+        o.hart = o.hvar = 0.0;
+        if (contaminated) {
+            double pur = std::log(purity);
+            double imp = ln_one_minus_exp(pur, eng.diag);
+            lh = lh + eng.contaminated_obs(pur, imp, std::log(vaf), std::log(vaf_secondary), none, o);
+        } else {
+            lh = lh + eng.single_obs(std::log(vaf), none, o);
+        }
+    }
+    return lh;
+}
+
+int32_t vlr_oracle_abi_version(void) { return VLR_ABI_VERSION; }
+
+} // extern "C"
