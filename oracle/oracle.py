@@ -76,6 +76,11 @@ def call_batch(flat_scenario, batch: LocusBatch, afd_capacity: int = 0, n_thread
     return out
 
 
+def set_legacy_is_likely(on: bool) -> None:
+    """Golden-pair pinning only (see vlr_oracle.cpp, g_legacy_is_likely)."""
+    lib().vlr_oracle_set_legacy_is_likely(1 if on else 0)
+
+
 def pileup_likelihood(batch: LocusBatch, lo: int, hi: int, vaf: float, vaf_secondary: float = 0.0,
                       purity: float = 1.0, contaminated: bool = False) -> float:
     cb = batch.as_c()

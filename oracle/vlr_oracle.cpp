@@ -159,6 +159,15 @@ struct Artifacts {
 
 const double LN_05 = std::log(0.5);
 
+// Test-only switch: the golden pair tests/resources/flamegraph_profiling/calls.vcf was written by a
+// release from April 2024 (before v8.4.9, CHANGELOG.md:167-171 "fix for strand bias model"), whose
+// Bias::is_likely counted strong ALT observations without the is_uniquely_mapping() requirement HEAD has
+// (bias/mod.rs:66-72). With the switch on the oracle reproduces all 11 golden records; with it off (HEAD
+// semantics, the default and the parity target) 2 of them keep a strand-bias twin alive. The same release
+// predates v8.9.3's MAPQ-only alt-locus bias (CHANGELOG.md:5-9: "in case no alt mappings are provided by the
+// aligner, still detect ..."), so in legacy mode that bias needs alt loci to be present (1 more record).
+bool g_legacy_is_likely = false;
+
 // strand_bias.rs:28-53
 inline double sb_prob_alt(const Artifacts& a, const Obs& o) {
     if (o.strand == STRAND_NONE) return 0.0;
@@ -336,6 +345,7 @@ bool alb_is_informative(const std::vector<Pileup>& pileups) {
         }
     bool enough_alt = n_alt > 0 && (double)nm_alt > ((double)n_alt * 0.1) && (n_alt - nm_alt) < 10;
     bool enough_ref = n_ref > 0 && ((double)nm_ref < ((double)n_ref * 0.9));
+    if (g_legacy_is_likely) return enough_alt && has_alt_loci(pileups);
     return enough_alt && (has_alt_loci(pileups) || enough_ref);
 }
 
@@ -398,12 +408,14 @@ bool config_survives(const Artifacts& a, const std::vector<Pileup>& pileups, Dia
     for (auto& p : pileups) {
         size_t strong_all = 0;
         for (auto& o : p)
-            if (o.is_uniquely_mapping() && o.is_strong_alt_support()) strong_all++;
+            if ((g_legacy_is_likely || o.is_uniquely_mapping()) && o.is_strong_alt_support()) strong_all++;
         bool likely;
         if (strong_all >= 10) {
             size_t ev = 0;
             for (auto& o : p)
-                if (o.is_uniquely_mapping() && o.is_strong_alt_support() && component_evidence(a, o, true)) ev++;
+                if ((g_legacy_is_likely || o.is_uniquely_mapping()) && o.is_strong_alt_support() &&
+                    component_evidence(a, o, true))
+                    ev++;
             double ratio = (double)ev / (double)strong_all;
             likely = ratio >= 0.66666;
         } else {
@@ -1551,5 +1563,7 @@ double vlr_oracle_pileup_likelihood(const vlr_batch_t* batch, int64_t lo, int64_
 }
 
 int32_t vlr_oracle_abi_version(void) { return VLR_ABI_VERSION; }
+
+void vlr_oracle_set_legacy_is_likely(int32_t on) { g_legacy_is_likely = on != 0; }
 
 } // extern "C"

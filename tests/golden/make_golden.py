@@ -1,0 +1,93 @@
+"""Generates the committed golden fixtures from the reference's own test resources.
+
+Run in the build container (needs /root/reference; the GPU box does not have it):
+    python tests/golden/make_golden.py
+
+Outputs (committed):
+  flamegraph_obs.npz        the 11 preprocessed loci of tests/resources/flamegraph_profiling/normal.vcf
+                            decoded into the SoA batch layout (inputs of `call variants`)
+  flamegraph_expected.json  what the reference printed for them (calls.vcf): PROB_* (PHRED f32),
+                            AF, AFD text, DP, SAOBS/SROBS, plus the scenario
+  real_pileups.npz/.json    single-sample observation-format-15 pileups embedded in
+                            tests/resources/testcases/*/candidates.vcf (inputs only) with their scenario text
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+from varlociraptor_b200 import obs_codec  # noqa: E402
+from varlociraptor_b200.batch import LocusBatch  # noqa: E402
+
+REF = "/root/reference/tests/resources"
+
+
+def flamegraph():
+    d = os.path.join(REF, "flamegraph_profiling")
+    recs = obs_codec.parse_observation_vcf(os.path.join(d, "normal.vcf"))
+    batch = obs_codec.batch_from_records([recs])
+    batch.save(os.path.join(HERE, "flamegraph_obs.npz"))
+    expected = []
+    with open(os.path.join(d, "calls.vcf")) as f:
+        for line in f:
+            if line.startswith("#"):
+                continue
+            t = line.rstrip("\n").split("\t")
+            info = dict(kv.split("=", 1) for kv in t[7].split(";") if "=" in kv)
+            fmt = dict(zip(t[8].split(":"), t[9].split(":")))
+            afd = [(float(a), float(b)) for a, b in (x.split("=") for x in fmt["AFD"].split(","))]
+            expected.append({"chrom": t[0], "pos": int(t[1]), "info": {k: v for k, v in info.items()
+                                                                       if k.startswith("PROB_")},
+                             "DP": int(fmt["DP"]), "AF": float(fmt["AF"]), "SAOBS": fmt["SAOBS"],
+                             "SROBS": fmt["SROBS"], "AFD": afd})
+    with open(os.path.join(d, "scenario.yaml")) as f:
+        scenario = f.read()
+    assert [r["pos"] for r in recs] == [e["pos"] for e in expected]
+    with open(os.path.join(HERE, "flamegraph_expected.json"), "w") as f:
+        json.dump({"source": "tests/resources/flamegraph_profiling/{normal.vcf,calls.vcf,scenario.yaml}",
+                   "scenario_yaml": scenario, "records": expected}, f, indent=1)
+    print("flamegraph: %d loci, %d reads" % (batch.n_loci, batch.n_reads))
+
+
+def real_pileups():
+    root = os.path.join(REF, "testcases")
+    batches, meta = [], []
+    for name in sorted(os.listdir(root)):
+        cand = os.path.join(root, name, "candidates.vcf")
+        scen = os.path.join(root, name, "scenario.yaml")
+        if not (os.path.exists(cand) and os.path.exists(scen)):
+            continue
+        with open(cand, "rb") as f:
+            raw = f.read(20000)
+        if raw[:2] == b"\x1f\x8b" or raw[:3] == b"BCF":
+            continue
+        head = raw.decode("utf-8", "replace")
+        if "##varlociraptor_observation_format_version=15" not in head:
+            continue
+        recs = [r for r in obs_codec.parse_observation_vcf(cand) if "PROB_MAPPING" in r["info"]]
+        if not recs:
+            continue
+        try:
+            b = obs_codec.batch_from_records([recs])
+        except Exception as e:  # noqa: BLE001
+            print("skip %s: %s" % (name, e))
+            continue
+        with open(scen) as f:
+            scenario = f.read()
+        batches.append(b)
+        meta.append({"testcase": name, "n_loci": b.n_loci, "n_reads": b.n_reads,
+                     "records": [{"chrom": r["chrom"], "pos": r["pos"], "ref": r["ref"], "alt": r["alt"]}
+                                 for r in recs], "scenario_yaml": scenario})
+        print("%s: %d loci, %d reads" % (name, b.n_loci, b.n_reads))
+    LocusBatch.concat(batches).save(os.path.join(HERE, "real_pileups.npz"))
+    with open(os.path.join(HERE, "real_pileups.json"), "w") as f:
+        json.dump({"source": "tests/resources/testcases/*/candidates.vcf (observation format 15)",
+                   "testcases": meta}, f, indent=1)
+
+
+if __name__ == "__main__":
+    flamegraph()
+    real_pileups()

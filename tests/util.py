@@ -1,0 +1,73 @@
+"""Shared helpers for the test-suite (small hand-built batches, comparison metrics)."""
+import math
+
+import numpy as np
+
+from varlociraptor_b200 import abi
+from varlociraptor_b200.batch import LocusBatch
+
+LN05 = math.log(0.5)
+SNV_FLAGS = (abi.LF_CHECK_ROB | abi.LF_CHECK_SB | abi.LF_CHECK_RPB | abi.LF_CHECK_SCB | abi.LF_CHECK_ALB |
+             abi.LF_FILTER_NONSTANDARD | abi.LF_HAS_SNV | (ord("A") << abi.LF_REFBASE_SHIFT) |
+             (ord("G") << abi.LF_ALTBASE_SHIFT))
+
+
+def read(prob_mapping=0.0, prob_alt=0.0, prob_ref=-np.inf, prob_missed_allele=None, prob_sample_alt=0.0,
+         prob_double_overlap=0.0, prob_hit_base=math.log(0.01), strand=abi.STRAND_BOTH, orientation=abi.ORIENT_NONE,
+         major=False, softclipped=False, paired=True, max_mapq=True, alt_locus=abi.ALTLOCUS_NONE,
+         hlen=None, hart=None, hvar=None):
+    """One read in the shape of `model::tests::observation` (src/variants/model/mod.rs:374-402)."""
+    if prob_missed_allele is None:
+        prob_missed_allele = float(np.logaddexp(prob_ref, prob_alt)) - math.log(2.0)
+    f = (strand << abi.RF_STRAND_SHIFT) | (orientation << abi.RF_ORIENT_SHIFT) | (alt_locus << abi.RF_ALTLOCUS_SHIFT)
+    if major:
+        f |= abi.RF_READPOS_MAJOR
+    if softclipped:
+        f |= abi.RF_SOFTCLIPPED
+    if paired:
+        f |= abi.RF_PAIRED
+    if max_mapq:
+        f |= abi.RF_MAX_MAPQ
+    if hlen is not None:
+        f |= abi.RF_HAS_HOMOPOLYMER_LEN | ((hlen & 0xff) << abi.RF_HOMOPOLYMER_LEN_SHIFT)
+    return dict(prob_mapping=prob_mapping, prob_alt=prob_alt, prob_ref=prob_ref,
+                prob_missed_allele=prob_missed_allele, prob_sample_alt=prob_sample_alt,
+                prob_double_overlap=prob_double_overlap, prob_hit_base=prob_hit_base, flags=f,
+                hart=np.nan if hart is None else hart, hvar=np.nan if hvar is None else hvar)
+
+
+def batch_from_reads(loci, locus_flags=None, n_samples=None):
+    """loci: list (per locus) of lists (per sample) of lists of `read()` dicts."""
+    S = n_samples or len(loci[0])
+    offs = [0]
+    rows = []
+    for locus in loci:
+        assert len(locus) == S
+        for pile in locus:
+            rows.extend(pile)
+            offs.append(offs[-1] + len(pile))
+    cols = {k: np.array([r[k] for r in rows], dtype=np.float32) for k in abi.BATCH_F32_COLUMNS}
+    flags = np.array([r["flags"] for r in rows], dtype=np.uint32)
+    hart = np.array([r["hart"] for r in rows], dtype=np.float32)
+    hvar = np.array([r["hvar"] for r in rows], dtype=np.float32)
+    any_h = bool(np.any(~np.isnan(hart)) or np.any(~np.isnan(hvar)))
+    if locus_flags is None:
+        locus_flags = [SNV_FLAGS] * len(loci)
+    return LocusBatch(S, np.array(offs, dtype=np.int64), cols, flags, np.array(locus_flags, dtype=np.uint32),
+                      hart if any_h else None, hvar if any_h else None)
+
+
+def max_abs_delta(a, b):
+    """max |a - b| with the SURVEY §8(d) convention: 0 where both are -inf (or both NaN), +inf where one is."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    same = (a == b) | (np.isnan(a) & np.isnan(b))
+    with np.errstate(invalid="ignore"):
+        d = np.abs(a - b)
+    d[same] = 0.0
+    d[np.isnan(d)] = np.inf
+    return float(d.max()) if d.size else 0.0
+
+
+def phred(lp):
+    return -10.0 * np.asarray(lp, dtype=np.float64) / math.log(10.0)

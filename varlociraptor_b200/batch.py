@@ -112,6 +112,25 @@ class LocusBatch:
                           take(self.prob_homopolymer_variant, idx), take(self.locus_heterozygosity_phred, loci),
                           take(self.locus_semr_phred, loci))
 
+    def save(self, path: str) -> None:
+        d = {"n_samples": np.array(self.n_samples), "read_offsets": self.read_offsets, "read_flags": self.read_flags,
+             "locus_flags": self.locus_flags}
+        d.update(self.columns)
+        for k in ("prob_homopolymer_artifact", "prob_homopolymer_variant", "locus_heterozygosity_phred",
+                  "locus_semr_phred"):
+            if getattr(self, k) is not None:
+                d[k] = getattr(self, k)
+        np.savez_compressed(path, **d)
+
+    @staticmethod
+    def load(path: str) -> "LocusBatch":
+        z = np.load(path)
+        opt = {k: (z[k] if k in z.files else None) for k in (
+            "prob_homopolymer_artifact", "prob_homopolymer_variant", "locus_heterozygosity_phred",
+            "locus_semr_phred")}
+        return LocusBatch(int(z["n_samples"]), z["read_offsets"], {k: z[k] for k in abi.BATCH_F32_COLUMNS},
+                          z["read_flags"], z["locus_flags"], **opt)
+
     @staticmethod
     def concat(batches: List["LocusBatch"]) -> "LocusBatch":
         S = batches[0].n_samples

@@ -1,0 +1,253 @@
+"""Observation wire format -> SoA columns.
+
+Decodes the per-record INFO arrays `varlociraptor preprocess variants` writes
+(src/calling/variants/preprocessing/mod.rs:921-1038, read side :818-919) straight into
+the per-read columns of `LocusBatch`, without materialising one struct per read.
+
+Wire format (observation format version 15, preprocessing/mod.rs:810): every INFO tag is a
+bincode-1.3 byte stream (little endian, fixed-width ints), zero-padded to even length, split
+into u16s and stored as BCF integers. `Vec<T>` = u64 length + items; `MiniLogProb`
+(src/utils/mod.rs:448-474) = u32 variant (0 = f16 bits, 1 = f32 bits) + payload; plain enums =
+u32 variant index; `Option<T>` = u8 tag + payload; `bv::BitVec<u8>` = Option<Box<[u8]>>
+(u8 tag, u64 #blocks, blocks) + u64 bit length.
+"""
+from __future__ import annotations
+
+import struct
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import abi
+from .batch import LocusBatch
+
+OBSERVATION_FORMAT_VERSION = "15"
+
+_PROB_TAGS = {
+    "PROB_MAPPING": "prob_mapping", "PROB_REF": "prob_ref", "PROB_ALT": "prob_alt",
+    "PROB_MISSED_ALLELE": "prob_missed_allele", "PROB_SAMPLE_ALT": "prob_sample_alt",
+    "PROB_DOUBLE_OVERLAP": "prob_double_overlap", "PROB_HIT_BASE": "prob_hit_base",
+}
+
+
+class _Reader:
+    def __init__(self, ints: Sequence[int]):
+        self.b = np.asarray(ints, dtype=np.int64).astype(np.uint16).astype("<u2").tobytes()
+        self.i = 0
+
+    def u8(self) -> int:
+        v = self.b[self.i]
+        self.i += 1
+        return v
+
+    def u32(self) -> int:
+        v = struct.unpack_from("<I", self.b, self.i)[0]
+        self.i += 4
+        return v
+
+    def u64(self) -> int:
+        v = struct.unpack_from("<Q", self.b, self.i)[0]
+        self.i += 8
+        return v
+
+    def mini_logprob(self) -> float:
+        variant = self.u32()
+        if variant == 0:
+            v = np.frombuffer(self.b, dtype="<f2", count=1, offset=self.i)[0]
+            self.i += 2
+        elif variant == 1:
+            v = np.frombuffer(self.b, dtype="<f4", count=1, offset=self.i)[0]
+            self.i += 4
+        else:
+            raise ValueError("invalid MiniLogProb variant %d" % variant)
+        return float(v)
+
+
+def decode_mini_logprobs(ints: Sequence[int]) -> np.ndarray:
+    r = _Reader(ints)
+    n = r.u64()
+    return np.array([r.mini_logprob() for _ in range(n)], dtype=np.float32)
+
+
+def decode_optional_mini_logprobs(ints: Sequence[int]) -> np.ndarray:
+    """Vec<Option<MiniLogProb>>; None -> NaN."""
+    r = _Reader(ints)
+    n = r.u64()
+    out = np.full(n, np.nan, dtype=np.float32)
+    for k in range(n):
+        if r.u8():
+            out[k] = r.mini_logprob()
+    return out
+
+
+def decode_enum(ints: Sequence[int]) -> np.ndarray:
+    r = _Reader(ints)
+    n = r.u64()
+    return np.array([r.u32() for _ in range(n)], dtype=np.uint32)
+
+
+def decode_optional_i8(ints: Sequence[int]) -> Tuple[np.ndarray, np.ndarray]:
+    r = _Reader(ints)
+    n = r.u64()
+    has = np.zeros(n, dtype=bool)
+    val = np.zeros(n, dtype=np.int8)
+    for k in range(n):
+        if r.u8():
+            has[k] = True
+            val[k] = np.frombuffer(r.b, dtype=np.int8, count=1, offset=r.i)[0]
+            r.i += 1
+    return has, val
+
+
+def decode_bitvec(ints: Sequence[int]) -> np.ndarray:
+    r = _Reader(ints)
+    blocks = b""
+    if r.u8():
+        nblocks = r.u64()
+        blocks = r.b[r.i:r.i + nblocks]
+        r.i += nblocks
+    nbits = r.u64()
+    arr = np.frombuffer(blocks, dtype=np.uint8)
+    idx = np.arange(nbits)
+    if nbits == 0:
+        return np.zeros(0, dtype=bool)
+    return ((arr[idx // 8] >> (idx % 8)) & 1).astype(bool)
+
+
+def decode_record(info: Dict[str, Sequence[int]]):
+    """One record's INFO arrays -> (columns dict of f32 arrays, read_flags u32, hom_artifact, hom_variant)."""
+    cols = {dst: decode_mini_logprobs(info[tag]) for tag, dst in _PROB_TAGS.items()}
+    n = len(cols["prob_mapping"])
+    strand = decode_enum(info["STRAND"])
+    orient = decode_enum(info["READ_ORIENTATION"])
+    readpos = decode_enum(info["READ_POSITION"])  # Major = 0, Some = 1
+    altlocus = decode_enum(info["ALT_LOCUS"])
+    softclipped = decode_bitvec(info["SOFTCLIPPED"])
+    paired = decode_bitvec(info["PAIRED"])
+    max_mapq = decode_bitvec(info["IS_MAX_MAPQ"])
+    flags = (strand << abi.RF_STRAND_SHIFT) | (orient << abi.RF_ORIENT_SHIFT) | (altlocus << abi.RF_ALTLOCUS_SHIFT)
+    flags = flags.astype(np.uint32)
+    flags |= np.where(readpos == 0, abi.RF_READPOS_MAJOR, 0).astype(np.uint32)
+    flags |= np.where(softclipped[:n], abi.RF_SOFTCLIPPED, 0).astype(np.uint32)
+    flags |= np.where(paired[:n], abi.RF_PAIRED, 0).astype(np.uint32)
+    flags |= np.where(max_mapq[:n], abi.RF_MAX_MAPQ, 0).astype(np.uint32)
+    hart = hvar = None
+    # is_homopolymer_indel = the artifact tag is present and non-empty (preprocessing/mod.rs:874)
+    if "PROB_HOMOPOLYMER_ARTIFACT_OBSERVABLE" in info:
+        hart = decode_optional_mini_logprobs(info["PROB_HOMOPOLYMER_ARTIFACT_OBSERVABLE"])
+        hvar = decode_optional_mini_logprobs(info["PROB_HOMOPOLYMER_VARIANT_OBSERVABLE"])
+        has, val = decode_optional_i8(info["HOMOPOLYMER_INDEL_LEN"])
+        flags |= np.where(has, abi.RF_HAS_HOMOPOLYMER_LEN, 0).astype(np.uint32)
+        flags |= (val.view(np.uint8).astype(np.uint32) << abi.RF_HOMOPOLYMER_LEN_SHIFT)
+    return cols, flags, hart, hvar
+
+
+def parse_observation_vcf(path: str) -> List[dict]:
+    """Text dump (`bcftools view`) of an observation BCF -> list of records with integer INFO arrays."""
+    out = []
+    with open(path) as f:
+        for line in f:
+            if line.startswith("#"):
+                continue
+            t = line.rstrip("\n").split("\t")
+            info = {}
+            flags = set()
+            for kv in t[7].split(";"):
+                if "=" in kv:
+                    k, v = kv.split("=", 1)
+                    try:
+                        info[k] = [int(x) for x in v.split(",")]
+                    except ValueError:
+                        info[k] = v
+                else:
+                    flags.add(kv)
+            out.append({"chrom": t[0], "pos": int(t[1]), "ref": t[3], "alt": t[4], "info": info, "flags": flags})
+    return out
+
+
+def locus_flags_for(ref: str, alt: str, is_homopolymer_indel: bool, imprecise: bool = False,
+                    omit_strand_bias=False, omit_read_orientation_bias=False, omit_read_position_bias=False,
+                    omit_softclip_bias=False, omit_homopolymer_artifact_detection=False,
+                    omit_alt_locus_bias=False, vartype: Optional[int] = None) -> int:
+    """The per-record switches of `Caller::preprocess_record` (src/calling/variants/calling.rs:513-566)."""
+    if len(ref) == 1 and len(alt) == 1:
+        is_snv_or_mnv, snv = True, True
+    elif len(ref) == len(alt):
+        is_snv_or_mnv, snv = True, False
+    else:
+        is_snv_or_mnv, snv = False, False
+    precise = not imprecise
+    f = 0
+    if is_snv_or_mnv and not omit_read_orientation_bias and precise:
+        f |= abi.LF_CHECK_ROB
+    if not omit_strand_bias and precise:
+        f |= abi.LF_CHECK_SB
+    if is_snv_or_mnv and not omit_read_position_bias and precise:
+        f |= abi.LF_CHECK_RPB
+    if is_snv_or_mnv and not omit_softclip_bias and precise:
+        f |= abi.LF_CHECK_SCB
+    if is_homopolymer_indel and not omit_homopolymer_artifact_detection:
+        f |= abi.LF_CHECK_HE
+    if not omit_alt_locus_bias:
+        f |= abi.LF_CHECK_ALB
+    if is_snv_or_mnv and not omit_read_orientation_bias:
+        f |= abi.LF_FILTER_NONSTANDARD
+    if vartype is None:
+        # model::VariantType of the record (src/variants/model/mod.rs) -> variant-type fraction class
+        if alt in ("<DEL>", "<INS>", "<REP>"):
+            vartype = abi.VARTYPE_INDEL
+        elif alt in ("<INV>", "<DUP>", "<BND>") or "[" in alt or "]" in alt:
+            vartype = abi.VARTYPE_SV
+        elif alt.startswith("<"):
+            vartype = abi.VARTYPE_SNV  # METH, REF, ...: fraction 1 (grammar/mod.rs:403-412)
+        elif len(ref) == 1 and len(alt) == 1:
+            vartype = abi.VARTYPE_SNV
+        elif len(ref) == len(alt):
+            vartype = abi.VARTYPE_MNV
+        else:
+            vartype = abi.VARTYPE_INDEL
+    f |= vartype << abi.LF_VARTYPE_SHIFT
+    if snv:
+        f |= abi.LF_HAS_SNV | (ord(ref) << abi.LF_REFBASE_SHIFT) | (ord(alt) << abi.LF_ALTBASE_SHIFT)
+    return f
+
+
+def batch_from_records(per_sample_records: List[List[dict]], **omit) -> LocusBatch:
+    """Lock-step records of S samples (outer list = samples in sample-index order; an entry may be None
+    for a sample without observations, calling.rs:605-607) -> LocusBatch."""
+    S = len(per_sample_records)
+    L = len(per_sample_records[0])
+    cols = {k: [] for k in abi.BATCH_F32_COLUMNS}
+    flags, harts, hvars, lflags = [], [], [], []
+    offsets = [0]
+    any_h = False
+    for i in range(L):
+        hom = False
+        first = None
+        for s in range(S):
+            rec = per_sample_records[s][i]
+            if rec is None:
+                offsets.append(offsets[-1])
+                continue
+            first = first or rec
+            c, f, hart, hvar = decode_record(rec["info"])
+            n = len(f)
+            for k in abi.BATCH_F32_COLUMNS:
+                cols[k].append(c[k])
+            flags.append(f)
+            if hart is not None and len(hart) > 0:
+                hom = True
+                any_h = True
+                harts.append(hart)
+                hvars.append(hvar)
+            else:
+                harts.append(np.full(n, np.nan, dtype=np.float32))
+                hvars.append(np.full(n, np.nan, dtype=np.float32))
+            offsets.append(offsets[-1] + n)
+        lflags.append(locus_flags_for(first["ref"], first["alt"], hom, "IMPRECISE" in first["flags"], **omit))
+
+    def cat(lst, dt):
+        return np.concatenate(lst) if lst else np.zeros(0, dtype=dt)
+    return LocusBatch(S, np.array(offsets, dtype=np.int64), {k: cat(v, np.float32) for k, v in cols.items()},
+                      cat(flags, np.uint32), np.array(lflags, dtype=np.uint32),
+                      cat(harts, np.float32) if any_h else None, cat(hvars, np.float32) if any_h else None)

@@ -30,6 +30,11 @@ from . import abi
 NAN = float("nan")
 
 
+def _opt_float(x):
+    # PyYAML reads "1e-3" as a string (YAML 1.1 floats need a dot); serde_yaml reads a float
+    return None if x is None else float(x)
+
+
 # ----------------------------------------------------------------------------- spectra
 @dataclass(frozen=True)
 class VAFRange:
@@ -375,9 +380,9 @@ class Scenario:
             ploidy = d.get("ploidy")
             if isinstance(ploidy, dict):
                 raise NotImplementedError("per-contig/sex ploidy maps are resolved by the host")
-            sp = Species(d.get("heterozygosity"), d.get("germline-mutation-rate"),
-                         d.get("somatic-effective-mutation-rate"), ploidy,
-                         vtf.get("indel", 0.0125), vtf.get("mnv", 0.001), vtf.get("sv", 0.01))
+            sp = Species(_opt_float(d.get("heterozygosity")), _opt_float(d.get("germline-mutation-rate")),
+                         _opt_float(d.get("somatic-effective-mutation-rate")), ploidy,
+                         float(vtf.get("indel", 0.0125)), float(vtf.get("mnv", 0.001)), float(vtf.get("sv", 0.01)))
         samples = {}
         for name, d in doc["samples"].items():
             d = d or {}
@@ -388,8 +393,8 @@ class Scenario:
                 s.universe = parse_universe(d["universe"])
             if "contamination" in d:
                 s.contamination = Contamination(d["contamination"]["by"], float(d["contamination"]["fraction"]))
-            s.somatic_effective_mutation_rate = d.get("somatic-effective-mutation-rate")
-            s.germline_mutation_rate = d.get("germline-mutation-rate")
+            s.somatic_effective_mutation_rate = _opt_float(d.get("somatic-effective-mutation-rate"))
+            s.germline_mutation_rate = _opt_float(d.get("germline-mutation-rate"))
             s.ploidy = d.get("ploidy")
             s.sex = d.get("sex")
             if "inheritance" in d:
