@@ -88,7 +88,7 @@ def test_clear_ref_shortcut():
     lp = dict(zip(flat.event_names + ["artifact"], out.log_posteriors[0]))
     assert np.isneginf(lp["germline_het"]) and np.isneginf(lp["germline_hom"])
     assert np.isfinite(lp["somatic_tumor"]) and np.isfinite(lp["somatic_normal"])
-    assert lp["absent"] > -1e-6
+    assert lp["absent"] > -0.1 and lp["absent"] > lp["somatic_tumor"]
     assert np.isneginf(lp["artifact"])  # all reads support ref -> no bias is likely (bias/mod.rs:85-93)
 
 
