@@ -27,6 +27,7 @@
 #ifndef VLR_ENGINE_H
 #define VLR_ENGINE_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -198,6 +199,8 @@ typedef struct {
 #define VLR_ST_IS_ARTIFACT (1u << 8)       /* artifact beats every other event (calling.rs:801-803) */
 #define VLR_ST_SINGLETON_ADJUSTED (1u << 9)      /* Hint::AdjustedSingletonEvidence */
 #define VLR_ST_FILTERED_NONSTANDARD (1u << 10)   /* Hint::FilteredNonStandardAlignments */
+#define VLR_ST_WORKSPACE_OVERFLOW (1u << 11)     /* locus has more reads than vlr_ctx_reserve() provided for
+                                                    (device-pointer entry only); results of the locus are invalid */
 
 typedef struct {
     /* [n_loci][n_events+1]: ln posterior of every plain event in scenario order,
@@ -208,7 +211,7 @@ typedef struct {
     int32_t* map_config;   /* [n_loci]; artifact config of the MAP base event (0 none) */
     int32_t* best_event;   /* [n_loci]; index into the event universe: 2*e (plain) or 2*e+1 (twin) */
     uint32_t* status;      /* [n_loci] */
-    uint32_t* n_base_events; /* [n_loci], optional: joint evaluations recorded */
+    uint32_t* n_base_events; /* [n_loci], optional: number of joint (prior x likelihood) evaluations */
     /* allele frequency distribution (calling.rs:891-928), optional (afd_capacity = 0) */
     int32_t afd_capacity;  /* entries per locus and sample */
     int32_t _pad;
@@ -234,6 +237,16 @@ vlr_status_t vlr_call_batch(vlr_ctx_t* ctx, const vlr_batch_t* batch, vlr_result
  * context's own stream); the caller synchronises. */
 vlr_status_t vlr_call_batch_device(vlr_ctx_t* ctx, const vlr_batch_t* batch, vlr_results_t* results,
                                    void* cuda_stream);
+
+/* Capacity of the per-warp read-coefficient workspace, in reads per locus summed over samples (default 4096).
+ * vlr_call_batch() sizes it from the batch itself; callers of vlr_call_batch_device() whose loci can be deeper
+ * reserve once up front (the call allocates, so it is not asynchronous). */
+vlr_status_t vlr_ctx_reserve(vlr_ctx_t* ctx, int64_t max_reads_per_locus);
+
+/* Page-locked host memory for batch columns and result arrays: vlr_call_batch() overlaps its chunked host<->device
+ * copies with compute only when the caller's buffers are pinned (pageable memory still works, staged by the driver). */
+void* vlr_host_alloc(size_t bytes);
+void vlr_host_free(void* p);
 
 /* Number of kernels the last vlr_call_batch* launched (for bench accounting). */
 int64_t vlr_last_launch_count(const vlr_ctx_t* ctx);

@@ -55,6 +55,7 @@ struct Diag {
     double margin_adaptive = std::numeric_limits<double>::infinity(); // |f(best)-f(other)| in adaptive argmax
     uint64_t n_pileup_evals = 0; // uncached pileup folds
     uint64_t n_read_evals = 0;   // per-read emissions
+    uint32_t n_joint_calls = 0;  // joint_prob invocations (base events incl. repeats)
 };
 
 inline void note_margin(Diag& d, double lhs, double rhs) {
@@ -937,6 +938,7 @@ struct Engine {
     // ---------------- joint (rust-bio Model::joint_prob + recording)
     double joint(const Operands& ops, const Artifacts& b) {
         double j = prior(ops) + likelihood(ops, b);
+        diag.n_joint_calls++;
         Key k;
         k.n = 0;
         for (int s = 0; s < S; ++s) {
@@ -1414,7 +1416,7 @@ struct Engine {
         if (is_artifact) diag.status |= VLR_ST_IS_ARTIFACT;
         if (res->log_marginal) res->log_marginal[locus] = marginal;
         if (res->best_event) res->best_event[locus] = 2 * ev_scen[best] + (ev_art[best] ? 1 : 0);
-        if (res->n_base_events) res->n_base_events[locus] = (uint32_t)base_events.size();
+        if (res->n_base_events) res->n_base_events[locus] = diag.n_joint_calls;
 
         // sample_infos (calling.rs:844-937): descending posterior, stable
         std::vector<size_t> order(base_events.size());

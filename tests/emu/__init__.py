@@ -1,0 +1,38 @@
+"""ctypes binding of the single-lane host build of the engine core (tests/emu/emu_driver.cpp). TEST ONLY."""
+import ctypes as C
+import os
+import subprocess
+
+from varlociraptor_b200 import abi
+from varlociraptor_b200.batch import CallResults
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "libvlr_engine_emu.so")
+_SRC = [os.path.join(_HERE, "emu_driver.cpp"),
+        os.path.join(_HERE, "..", "..", "varlociraptor_b200", "csrc", "engine_core.cuh"),
+        os.path.join(_HERE, "..", "..", "varlociraptor_b200", "csrc", "scenario_prep.h"),
+        os.path.join(_HERE, "..", "..", "include", "vlr_engine.h")]
+_lib = None
+
+
+def build(force=False):
+    stale = not os.path.exists(_LIB) or max(os.path.getmtime(p) for p in _SRC) > os.path.getmtime(_LIB)
+    if force or stale:
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-DVLR_HOST_EMU", "-ffp-contract=off",
+                               "-Wno-unknown-pragmas", "-o", _LIB, _SRC[0]], cwd=_HERE)
+    return _LIB
+
+
+def call_batch(flat_scenario, batch, afd_capacity=0) -> CallResults:
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB)
+        _lib.vlr_emu_call_batch.restype = C.c_int32
+        _lib.vlr_emu_call_batch.argtypes = [C.POINTER(abi.Scenario), C.POINTER(abi.Batch), C.POINTER(abi.Results)]
+    out = CallResults(batch.n_loci, batch.n_samples, flat_scenario.n_events, afd_capacity)
+    cb, cr = batch.as_c(), out.as_c()
+    rc = _lib.vlr_emu_call_batch(C.byref(flat_scenario.c), C.byref(cb), C.byref(cr))
+    if rc != 0:
+        raise RuntimeError("emu failed with status %d" % rc)
+    return out

@@ -1,0 +1,161 @@
+"""GPU-less check of the engine's control flow: the single-lane host build of engine_core.cuh (tests/emu, test
+infrastructure only) against the oracle. The real parity tests are tests/test_gpu_parity.py (-m gpu)."""
+import json
+import os
+
+import numpy as np
+
+from oracle import oracle
+from tests import emu
+from tests.util import batch_from_reads, max_abs_delta, read
+from varlociraptor_b200 import LocusBatch, Scenario, abi, synth
+
+TOL = 1e-9
+
+
+def _compare(o, g):
+    ok = ~o.knife_edge()
+    assert max_abs_delta(o.log_posteriors[ok], g.log_posteriors[ok]) <= TOL
+    assert max_abs_delta(o.map_vaf[ok], g.map_vaf[ok]) == 0.0
+    assert np.array_equal(o.best_event[ok], g.best_event[ok])
+    assert np.array_equal(o.map_config[ok], g.map_config[ok])
+    assert np.array_equal(o.status[ok], g.status[ok])
+    assert np.array_equal(o.n_base_events[ok], g.n_base_events[ok])
+    if o.afd_capacity:
+        assert np.array_equal(o.afd_count[ok], g.afd_count[ok])
+        assert max_abs_delta(o.afd_vaf[ok], g.afd_vaf[ok]) == 0.0
+        assert max_abs_delta(o.afd_logp[ok], g.afd_logp[ok]) <= TOL
+
+
+def test_tumor_normal():
+    sc, b = synth.tumor_normal(150, seed=5)
+    flat = sc.flatten()
+    _compare(oracle.call_batch(flat, b, afd_capacity=96, n_threads=4), emu.call_batch(flat, b, afd_capacity=96))
+
+
+def test_pedigree_mixed_snv_indel():
+    sc, b = synth.pedigree(300, seed=6)
+    flat = sc.flatten()
+    _compare(oracle.call_batch(flat, b, afd_capacity=8, n_threads=4), emu.call_batch(flat, b, afd_capacity=8))
+
+
+def test_depth_skew():
+    sc, b = synth.tumor_normal(24, seed=8, depth_range=(10, 2000))
+    flat = sc.flatten()
+    _compare(oracle.call_batch(flat, b, n_threads=4), emu.call_batch(flat, b))
+
+
+def test_golden_and_real_pileups(golden_dir):
+    exp = json.load(open(os.path.join(golden_dir, "flamegraph_expected.json")))
+    flat = Scenario.from_yaml(exp["scenario_yaml"]).flatten()
+    b = LocusBatch.load(os.path.join(golden_dir, "flamegraph_obs.npz"))
+    _compare(oracle.call_batch(flat, b, afd_capacity=64), emu.call_batch(flat, b, afd_capacity=64))
+    meta = json.load(open(os.path.join(golden_dir, "real_pileups.json")))
+    allb = LocusBatch.load(os.path.join(golden_dir, "real_pileups.npz"))
+    lo = 0
+    n = 0
+    for tc in meta["testcases"]:
+        bb = allb.slice(lo, lo + tc["n_loci"])
+        lo += tc["n_loci"]
+        try:
+            sc = Scenario.from_yaml(tc["scenario_yaml"])
+        except NotImplementedError:
+            continue
+        if len(sc.sample_names) != 1:
+            continue
+        flat = sc.flatten()
+        _compare(oracle.call_batch(flat, bb, afd_capacity=128), emu.call_batch(flat, bb, afd_capacity=128))
+        n += 1
+    assert n >= 5
+
+
+def test_edge_cases():
+    flat = Scenario.tumor_normal(0.75).flatten()
+    ref = dict(prob_alt=np.log(1e-3 / 3), prob_ref=np.log1p(-1e-3), prob_mapping=np.log1p(-1e-6))
+    alt = dict(prob_ref=np.log(1e-3 / 3), prob_alt=np.log1p(-1e-3), prob_mapping=np.log1p(-1e-6))
+    mk = lambda d, i: read(strand=i % 2, orientation=i % 2, prob_double_overlap=-np.inf, **d)  # noqa: E731
+    loci = [
+        [[], []],
+        [[mk(ref, 0)], []],
+        [[mk(ref, i) for i in range(30)], [mk(ref, i) for i in range(30)]],
+        [[mk(ref, i) for i in range(30)], [mk(ref, i) for i in range(29)] + [mk(alt, 0)]],
+        [[mk(ref, i) for i in range(12)], [mk(alt, i) for i in range(12)]],
+        [[mk(alt, i) for i in range(12)], [mk(alt, i) for i in range(12)]],
+        [[read(prob_mapping=-np.inf, prob_alt=-1.0, prob_ref=-2.0, strand=0, orientation=0) for _ in range(6)],
+         [mk(alt, i) for i in range(3)]],
+        [[mk(ref, i) for i in range(8)] + [read(orientation=abi.ORIENT_F1F2, **alt)],
+         [mk(alt, i) for i in range(4)] + [mk(ref, i) for i in range(4)]],
+    ]
+    b = batch_from_reads(loci)
+    o = oracle.call_batch(flat, b, afd_capacity=128)
+    g = emu.call_batch(flat, b, afd_capacity=128)
+    _compare(o, g)
+    assert g.status[3] & abi.ST_SINGLETON_ADJUSTED
+    assert g.status[7] & abi.ST_FILTERED_NONSTANDARD
+
+
+LFC_YAML = """
+samples:
+  a:
+    universe: "[0.0,1.0]"
+    resolution: 0.05
+  b:
+    universe: "[0.0,1.0]"
+    resolution: 0.05
+events:
+  up: "l2fc(a,b) >= 1.0 & a:]0.0,1.0] & b:]0.0,1.0]"
+  same: "l2fc(a,b) < 1.0 & a:]0.0,1.0] & b:]0.0,1.0]"
+  only_a: "a:]0.0,1.0] & b:0.0"
+"""
+
+
+def test_log2_fold_change_and_variant_nodes():
+    sc = Scenario.from_yaml(LFC_YAML)
+    flat = sc.flatten()
+    _, b = synth.tumor_normal(40, seed=21, depth=30)
+    _compare(oracle.call_batch(flat, b, afd_capacity=128, n_threads=4), emu.call_batch(flat, b, afd_capacity=128))
+    sc2 = Scenario.from_yaml("""
+samples:
+  s:
+    universe: "[0.0,1.0]"
+events:
+  ct: "C>T & s:]0.0,1.0]"
+  other: "!C>T & s:]0.0,1.0]"
+""")
+    flat2 = sc2.flatten()
+    _, b2 = synth.tumor_normal(30, seed=22, depth=25)
+    one = LocusBatch(1, b2.read_offsets[::2].copy(), {k: v for k, v in b2.columns.items()}, b2.read_flags,
+                     b2.locus_flags)  # merge both pileups of each locus into one sample
+    _compare(oracle.call_batch(flat2, one, afd_capacity=64), emu.call_batch(flat2, one, afd_capacity=64))
+
+
+def test_population_and_somatic_priors():
+    """Prior branches beyond uniform/Mendelian: somatic rate (germline odometer), clonal/subclonal inheritance."""
+    sc = Scenario.from_yaml("""
+species:
+  heterozygosity: 0.001
+  somatic-effective-mutation-rate: 1e-6
+  ploidy: 2
+samples:
+  normal:
+    resolution: 0.1
+  tumor:
+    resolution: 0.05
+    inheritance:
+      clonal:
+        from: normal
+        somatic: false
+    contamination:
+      by: normal
+      fraction: 0.2
+events:
+  germline: "(normal:0.5 | normal:1.0)"
+  somatic_normal: "normal:]0.0,0.5[ | normal:]0.5,1.0["
+  somatic_tumor: "normal:0.0 & tumor:]0.0,1.0]"
+""")
+    flat = sc.flatten()
+    _, b = synth.tumor_normal(25, seed=31, depth=40)
+    _compare(oracle.call_batch(flat, b, afd_capacity=128, n_threads=4), emu.call_batch(flat, b, afd_capacity=128))
+    full = Scenario.from_yaml(synth.SIMPLE_PEDIGREE_YAML, full_prior=True).flatten()
+    _, b3 = synth.pedigree(60, seed=32, depth=30)
+    _compare(oracle.call_batch(full, b3), emu.call_batch(full, b3))

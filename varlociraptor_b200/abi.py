@@ -58,6 +58,7 @@ ST_NO_MAP = 1 << 7
 ST_IS_ARTIFACT = 1 << 8
 ST_SINGLETON_ADJUSTED = 1 << 9
 ST_FILTERED_NONSTANDARD = 1 << 10
+ST_WORKSPACE_OVERFLOW = 1 << 11
 
 ARTIFACT_CONFIG_NAMES = ["none", "ALB", "HE", "SCB", "RPB", "ROB_F1R2", "ROB_F2R1", "SB_FWD", "SB_REV"]
 

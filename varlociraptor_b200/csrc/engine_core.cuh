@@ -1,0 +1,1801 @@
+// engine_core.cuh — the per-locus posterior engine, written warp-cooperatively.
+//
+// One warp evaluates one locus. Control flow (VAF-tree walk, adaptive integration decisions, prior, event
+// bookkeeping) is warp-uniform: every lane holds bit-identical copies of the deciding values. Lanes split the two
+// things that are wide: the reads of a pileup (pre-pass statistics, per-read coefficients, likelihood product)
+// and the points of an integration grid (sort + trapezoid).
+//
+// What it replaces in the reference (file:line under /root/reference/src):
+//   calling/variants/calling.rs:586-626     pileup filtering, singleton adjustment      -> locus_prepass
+//   variants/model/bias/*.rs                artifact models, learn_parameters, filters  -> locus_prepass, read_coefficients
+//   variants/model/likelihood.rs:43-249     per-read emission + pileup fold             -> read_coefficients, sample_likelihood
+//   variants/model/modes/generic.rs:191-554 VAF-tree density, joint likelihood          -> density, joint
+//   utils/adaptive_integration.rs:25-141    unimodal adaptive integration               -> integrate_adaptive
+//   variants/model/prior.rs:298-761         scenario prior                              -> prior_*
+//   calling/variants/calling.rs:720-937     event posteriors, artifact, MAP, AFD        -> process_locus
+//
+// Numerical restructuring: in linear space the emission of one read is affine in the effective
+// alt-sampling probability x,  L_r = e^{K_r} (alpha_r x + beta_r (1-x) + gamma_r),  so all VAF-independent work
+// (bias terms, exp/log of the read's probabilities) is hoisted into three fp64 coefficients per (read, artifact
+// config) and one pileup evaluation is 2 FMAs + 1 MUL per read and ONE log per pileup.
+//
+// The file compiles for sm_100a (nvcc) and, with -DVLR_HOST_EMU, as a single-lane host build that exists only so
+// the control flow can be unit-tested without a GPU (tests/emu); the product library never contains that build.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../../include/vlr_engine.h"
+
+#ifdef VLR_HOST_EMU
+#define VLR_DEV inline
+#define VLR_DEV_NOINLINE
+#else
+#define VLR_DEV __device__ __forceinline__
+#define VLR_DEV_NOINLINE __device__ __noinline__
+#endif
+
+namespace vlrcore {
+
+constexpr int MAXS = VLR_MAX_SAMPLES;
+constexpr int MAXE = VLR_MAX_EVENTS;
+constexpr int NCFG = VLR_N_ARTIFACT_CONFIGS;
+constexpr int GRID_CAP = 128;   // points per adaptive integration (res >= ~1e-5)
+constexpr int LC_WAYS = 4;      // per-sample pileup-likelihood cache entries
+constexpr int MAX_LFC_NODES = 32;
+constexpr int AFD_TMP = 512;
+
+constexpr double NUMERICAL_EPSILON = 1e-3;        // utils/mod.rs:41
+constexpr double LN_05 = -0.6931471805599453;     // ln 0.5 (utils/mod.rs:45-47)
+constexpr double LN_2 = 0.6931471805599453;
+constexpr double LN_095 = -0.05129329438755058;   // ln 0.95 (utils/mod.rs:49-51)
+constexpr double LN_3 = 1.0986122886681098;       // Kass-Raftery thresholds 3, 20, 150 in log space
+constexpr double LN_20 = 2.995732273553991;
+constexpr double LN_150 = 5.0106352940962555;
+
+// ------------------------------------------------------------------------------------------------ warp layer
+#ifdef VLR_HOST_EMU
+constexpr int LANES = 1;
+VLR_DEV int lane_id() { return 0; }
+VLR_DEV void warp_sync() {}
+VLR_DEV int w_sum_i(int v) { return v; }
+VLR_DEV unsigned w_or_u(unsigned v) { return v; }
+VLR_DEV int w_max_i(int v) { return v; }
+VLR_DEV double w_sum_d(double v) { return v; }
+VLR_DEV double w_mul_d(double v) { return v; }
+VLR_DEV double w_max_d(double v) { return v; }
+VLR_DEV bool w_any(bool p) { return p; }
+VLR_DEV double w_bcast_d(double v, int) { return v; }
+VLR_DEV int d_hi(double x) {
+    uint64_t u;
+    memcpy(&u, &x, 8);
+    return (int)(u >> 32);
+}
+VLR_DEV int d_lo(double x) {
+    uint64_t u;
+    memcpy(&u, &x, 8);
+    return (int)(u & 0xffffffffu);
+}
+VLR_DEV double d_make(int hi, int lo) {
+    uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo;
+    double x;
+    memcpy(&x, &u, 8);
+    return x;
+}
+#else
+constexpr int LANES = 32;
+constexpr unsigned FULL = 0xffffffffu;
+VLR_DEV int lane_id() { return (int)(threadIdx.x & 31); }
+VLR_DEV void warp_sync() { __syncwarp(); }
+VLR_DEV int w_sum_i(int v) { return __reduce_add_sync(FULL, v); }
+VLR_DEV unsigned w_or_u(unsigned v) { return __reduce_or_sync(FULL, v); }
+VLR_DEV int w_max_i(int v) { return __reduce_max_sync(FULL, v); }
+// xor butterflies: a+b == b+a bitwise, so every lane ends with the identical value (needed for uniform control flow)
+VLR_DEV double w_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+VLR_DEV double w_mul_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v *= __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+VLR_DEV double w_max_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+VLR_DEV bool w_any(bool p) { return __any_sync(FULL, p) != 0; }
+VLR_DEV double w_bcast_d(double v, int src) { return __shfl_sync(FULL, v, src); }
+VLR_DEV int d_hi(double x) { return __double2hiint(x); }
+VLR_DEV int d_lo(double x) { return __double2loint(x); }
+VLR_DEV double d_make(int hi, int lo) { return __hiloint2double(hi, lo); }
+#endif
+
+VLR_DEV double neg_inf() { return -INFINITY; }
+
+// ------------------------------------------------------------------------------------------------ device views
+struct DevScenario {
+    int S, E, n_nodes, n_set_vafs, n_spectra, full_prior, all_uniform, n_lfc_nodes;
+    const vlr_sample_t* samples;
+    const vlr_event_t* events;
+    const vlr_node_t* nodes;
+    const double* set_vafs;
+    const vlr_spectrum_t* spectra;
+    const int* lfc_nodes; // ordinal -> node index (LFC nodes only)
+    const int* lfc_ordinal; // node index -> ordinal (or -1)
+    double heterozygosity; // linear, NaN = none
+    double vtf[4];         // variant type fraction by VLR_LF_VARTYPE class
+};
+
+struct DevBatch {
+    int64_t n_loci;
+    int64_t read_base; // first row held by the column pointers (chunked transfers)
+    const int64_t* read_offsets;
+    const float *pm, *pr, *pa, *pmiss, *psa, *pdo, *phb;
+    const uint32_t* rflags;
+    const float *hart, *hvar;
+    const uint32_t* lflags;
+    const float *het_phred, *semr_phred;
+};
+
+struct DevResults {
+    double* log_post;
+    double* log_marginal;
+    double* map_vaf;
+    int32_t* map_config;
+    int32_t* best_event;
+    uint32_t* status;
+    uint32_t* n_base_events;
+    int32_t afd_capacity;
+    int32_t* afd_count;
+    double* afd_vaf;
+    double* afd_logp;
+};
+
+// Per-warp scratch in global memory (private to the warp, so it lives in L1/L2).
+constexpr int BE_CAP = 4096; // recorded base events per locus (only when an AFD is requested)
+
+struct WarpWs {
+    double grid_x[MAXS][GRID_CAP];
+    double grid_f[MAXS][GRID_CAP];
+    double sort_x[GRID_CAP];
+    double sort_f[GRID_CAP];
+    double afd_x[AFD_TMP];
+    double afd_p[AFD_TMP];
+};
+
+// ------------------------------------------------------------------------------------------------ LogProb helpers
+// (rust-bio LogProb semantics)
+VLR_DEV_NOINLINE double ln_add_exp(double a, double b) {
+    double p0, p1;
+    if (b > a) {
+        p0 = b;
+        p1 = a;
+    } else {
+        p0 = a;
+        p1 = b;
+    }
+    if (p0 == neg_inf()) return neg_inf();
+    if (p1 == neg_inf()) return p0;
+    return p0 + log1p(exp(p1 - p0));
+}
+VLR_DEV_NOINLINE double ln_one_minus_exp(double p) {
+    if (p < -0.693) return log1p(-exp(p));
+    return log(-expm1(p));
+}
+// streaming ln_sum_exp accumulator (differs from the reference's max-first two-pass form by rounding only)
+struct Lse {
+    double m, s; // max so far, sum of exp(x - m)
+    int n;
+    VLR_DEV void init() {
+        m = neg_inf();
+        s = 0.0;
+        n = 0;
+    }
+    VLR_DEV_NOINLINE void add(double x) {
+        n++;
+        if (x == neg_inf()) return;
+        if (x != x) { // NaN poisons like the reference's arithmetic would
+            m = x;
+            return;
+        }
+        if (x > m) {
+            s = (m == neg_inf()) ? 1.0 : s * exp(m - x) + 1.0;
+            m = x;
+        } else {
+            s += exp(x - m);
+        }
+    }
+    VLR_DEV double value() const {
+        if (m == neg_inf() || m != m || m == INFINITY) return m;
+        return m + log1p(s - 1.0);
+    }
+};
+
+VLR_DEV int kass_raftery(double m1, double m2) {
+    // BayesFactor::new(m1, m2) = exp(m1 - m2) compared with 1, 3, 20, 150; evaluated in log space.
+    double d = m1 - m2;
+    if (d <= 0.0) return 0;
+    if (d <= LN_3) return 1;
+    if (d <= LN_20) return 2;
+    if (d <= LN_150) return 3;
+    return 4; // incl. NaN, like the chain of failed comparisons in the reference
+}
+
+VLR_DEV bool relative_eq(double a, double b) { // approx 0.5 defaults (epsilon = max_relative = f64::EPSILON)
+    if (a == b) return true;
+    if (isinf(a) || isinf(b)) return false;
+    double diff = fabs(a - b);
+    const double eps = 2.220446049250313e-16;
+    if (diff <= eps) return true;
+    double largest = fmax(fabs(a), fabs(b));
+    return diff <= largest * eps;
+}
+
+// ------------------------------------------------------------------------------------------------ VAFRange
+struct Range {
+    double start, end;
+    bool lex, rex;
+};
+VLR_DEV Range range_empty() { return Range{0.0, 0.0, true, true}; }
+VLR_DEV bool range_is_empty(const Range& r) { return r.start == r.end && (r.lex || r.rex); }
+VLR_DEV bool range_is_singleton(const Range& r) { return r.start == r.end && !(r.lex || r.rex); }
+VLR_DEV bool range_contains(const Range& r, double v) {
+    bool l = r.lex ? (r.start < v) : (r.start <= v);
+    bool rr = r.rex ? (r.end > v) : (r.end >= v);
+    return l && rr;
+}
+VLR_DEV bool range_no_overlap(const Range& a, const Range& o) { // formula.rs:1137-1170
+    if (a.start == o.start && a.end == o.end && a.lex == o.lex && a.rex == o.rex) return false;
+    return (a.end < o.start || a.start > o.end) || (a.end <= o.start && (a.rex || o.lex)) ||
+           (a.start >= o.end && (a.lex || o.rex));
+}
+VLR_DEV Range range_intersect(const Range& a, const Range& o) {
+    if (range_no_overlap(a, o)) return range_empty();
+    Range r;
+    r.start = fmax(a.start, o.start);
+    r.end = fmin(a.end, o.end);
+    r.lex = a.start > o.start ? a.lex : (a.start < o.start ? o.lex : (a.lex || o.lex));
+    r.rex = a.end < o.end ? a.rex : (a.end > o.end ? o.rex : (a.rex || o.rex));
+    return r;
+}
+VLR_DEV double range_observable_max(const Range& r, int n) { // formula.rs:1202-1224
+    if (n < 10 || !((double)n * (r.end - r.start) > 1.0)) return r.end;
+    double c = (double)n * r.end;
+    if (r.rex && fmod(c, 1.0) == 0.0) c -= 1.0;
+    c = floor(c);
+    if (c == 0.0) return r.end;
+    return c / (double)n;
+}
+VLR_DEV double range_observable_min(const Range& r, int n) { // formula.rs:1172-1200
+    double min_vaf;
+    if (n < 10 || !((double)n * (r.end - r.start) > 1.0)) {
+        min_vaf = r.start;
+    } else {
+        double c = (double)n * r.start;
+        if (r.lex && fmod(c, 1.0) == 0.0) {
+            double adjusted_end = range_observable_max(r, n);
+            double s1 = ceil(c + 1.0) / (double)n;
+            if (s1 <= 1.0 && s1 <= adjusted_end) return s1;
+            double s0 = ceil(c) / (double)n;
+            if (s0 <= 1.0 && s0 <= adjusted_end) return s0;
+        }
+        min_vaf = ceil(c) / (double)n;
+    }
+    if (min_vaf >= range_observable_max(r, n)) return r.start;
+    return min_vaf;
+}
+
+// log2 fold change predicates (utils/log2_fold_change.rs)
+VLR_DEV int lfc_invert_cmp(int cmp) {
+    switch (cmp) {
+    case VLR_CMP_GT: return VLR_CMP_LE;
+    case VLR_CMP_GE: return VLR_CMP_LT;
+    case VLR_CMP_LT: return VLR_CMP_GE;
+    case VLR_CMP_LE: return VLR_CMP_GT;
+    default: return cmp;
+    }
+}
+VLR_DEV Range lfc_infer_bounds(int cmp, double value, double vaf) {
+    double proj = vaf / exp2(value);
+    if (proj < 0.0 || proj > 1.0) return range_empty();
+    switch (cmp) {
+    case VLR_CMP_EQ: return Range{proj, proj, false, false};
+    case VLR_CMP_GT: return Range{0.0, proj, false, true};
+    case VLR_CMP_GE: return Range{0.0, proj, false, false};
+    case VLR_CMP_LT: return Range{proj, 1.0, true, false};
+    case VLR_CMP_LE: return Range{proj, 1.0, false, false};
+    default: return Range{0.0, 1.0, false, false};
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ per-locus state
+struct Ops { // generic.rs LikelihoodOperands
+    double vaf[MAXS];
+    uint32_t set_mask;  // samples whose event is present
+    uint32_t disc_mask; // is_discrete per sample
+    uint32_t lfc_mask;  // pushed LFC constraints by ordinal
+};
+
+struct Art { // bias::Artifacts restricted to "none" or exactly one artifact (bias/mod.rs:131-218)
+    int id;  // 0 none; 1 ALB 2 HE 3 SCB 4 RPB 5 ROB_F1R2 6 ROB_F2R1 7 SB_FWD 8 SB_REV
+    double forward_rate;
+    bool has_alt_loci;
+};
+
+struct Ctx {
+    const DevScenario* sc;
+    const DevBatch* b;
+    const DevResults* res;
+    WarpWs* ws;
+    double* coef; // per-warp coefficient arena: 4 doubles per kept read (alpha, beta, gamma, s)
+    double* be;   // per-warp base-event log (NULL unless an AFD is requested): BE_CAP x (2 + S) doubles
+    uint32_t n_rec;
+    int coef_cap;   // capacity of `coef` in reads
+    int coef_total; // kept reads of this locus over all samples
+    int64_t locus;
+    int lane;
+    uint32_t lf;
+    uint32_t status;
+    int vartype;
+    double het_override, semr_override; // ln, NaN = none
+    bool has_snv;
+    int refbase, altbase;
+    int64_t singleton_row; // absolute row of the read whose evidence is adjusted, or -1
+    Art art;
+    // per sample
+    int n_obs[MAXS];
+    int clear_ref[MAXS];
+    int s_one[MAXS];   // every kept read has prob_sample_alt == 0
+    int s_gt1[MAXS];   // some kept read has prob_sample_alt > 0
+    int coef_off[MAXS];
+    double ksum[MAXS];
+    // pileup likelihood cache (generic.rs:43-53; here LC_WAYS most recent entries per sample and config)
+    double lc_k1[MAXS][LC_WAYS], lc_k2[MAXS][LC_WAYS], lc_v[MAXS][LC_WAYS];
+    int lc_n[MAXS];
+    // events
+    int cur_slot; // 2*event + (artifact config ? 1 : 0)
+    double map_joint[2 * MAXE];
+    double map_vaf[2 * MAXE][MAXS];
+    uint32_t map_disc[2 * MAXE];
+    int map_cfg[2 * MAXE];
+    uint32_t map_has; // not enough bits for 48 slots -> use the arrays below
+    uint8_t map_set[2 * MAXE];
+    double prior_absent; // Prior of the all-zero event (absent-only mode), NaN = not computed yet
+    uint32_t n_base;
+    uint32_t n_pileup_evals;
+};
+
+VLR_DEV uint32_t locus_check(const Ctx& c, uint32_t bit) { return c.lf & bit; }
+
+// ------------------------------------------------------------------------------------------------ reads
+struct Read {
+    double pm, pa, pr, pmiss, psa, pdo, phb, hart, hvar;
+    uint32_t f;
+    bool has_hart, has_hvar;
+};
+VLR_DEV Read load_read(const DevBatch* b, int64_t row) {
+    int64_t i = row - b->read_base;
+    Read r;
+    r.pm = (double)b->pm[i];
+    r.pa = (double)b->pa[i];
+    r.pr = (double)b->pr[i];
+    r.pmiss = (double)b->pmiss[i];
+    r.psa = (double)b->psa[i];
+    r.pdo = (double)b->pdo[i];
+    r.phb = (double)b->phb[i];
+    r.f = b->rflags[i];
+    float ha = b->hart ? b->hart[i] : NAN, hv = b->hvar ? b->hvar[i] : NAN;
+    r.has_hart = !(ha != ha);
+    r.has_hvar = !(hv != hv);
+    r.hart = r.has_hart ? (double)ha : 0.0;
+    r.hvar = r.has_hvar ? (double)hv : 0.0;
+    return r;
+}
+VLR_DEV int rd_strand(uint32_t f) { return (f >> VLR_RF_STRAND_SHIFT) & 3; }
+VLR_DEV int rd_orient(uint32_t f) { return (f >> VLR_RF_ORIENT_SHIFT) & 15; }
+VLR_DEV int rd_altlocus(uint32_t f) { return (f >> VLR_RF_ALTLOCUS_SHIFT) & 3; }
+VLR_DEV int rd_hlen(uint32_t f) {
+    return (f & VLR_RF_HAS_HOMOPOLYMER_LEN) ? (int)(int8_t)((f >> VLR_RF_HOMOPOLYMER_LEN_SHIFT) & 0xff) : 0;
+}
+// pileup.rs:26-43 (only applied when the locus asks for it)
+VLR_DEV bool rd_kept(uint32_t lf, uint32_t f) {
+    if (!(lf & VLR_LF_FILTER_NONSTANDARD)) return true;
+    int o = rd_orient(f);
+    return o == 0 || o == 1 || o == 8;
+}
+
+// Outcome of the bias pre-pass
+struct BiasPlan {
+    int n_twins;           // unfiltered number of single-artifact configs (generic.rs:437-441)
+    int surviving[NCFG];   // config ids that pass is_possible && is_informative && is_likely
+    int n_surviving;
+    double forward_rate;
+    bool has_alt_loci;
+};
+
+// One pass over all reads of the locus: everything the reference derives from the pileups before the model runs.
+//   calling.rs:595-616 (filter + singleton), generic.rs:270-291 (n_obs, is_clear_ref),
+//   strand_bias.rs:79-123, read_orientation_bias.rs:38-97, read_position_bias.rs:63-121, softclip_bias.rs:32-39,
+//   homopolymer_error.rs:46-72, alt_locus_bias.rs:47-59,124-144, bias/mod.rs:37-104.
+VLR_DEV_NOINLINE void locus_prepass(Ctx& c, BiasPlan& plan) {
+    const DevBatch* b = c.b;
+    const int S = c.sc->S;
+    const uint32_t lf = c.lf;
+    // global accumulators
+    double g_sb_all = 0.0, g_sb_fwd = 0.0;
+    int g_n = 0, g_uncertain = 0, g_sr_std = 0, g_sr_f1r2 = 0, g_n_alt = 0, g_nm_alt = 0, g_n_ref = 0, g_nm_ref = 0;
+    int g_alt_support = 0;
+    long long g_alt_row = -1;
+    unsigned g_flags = 0; // bit0 has_alt_loci, 1 softclip, 2 pos_sb_fwd, 3 pos_sb_rev, 4 pos_rob1, 5 pos_rob2, 6 pos_rpb,
+                          // 7 pos_alb_loci, 8 pos_alb_mapq
+    bool he_informative = true;
+    bool rpb_valid = false;
+    // per sample "likely" inputs
+    int uq_salt[MAXS];
+    int ev_cnt[MAXS][10]; // index by config id 1..8; 9 = ALB evidence when no alt loci exist
+    int all_ref[MAXS];
+    int coef_total = 0;
+    for (int s = 0; s < S; ++s) {
+        int64_t lo = b->read_offsets[c.locus * S + s], hi = b->read_offsets[c.locus * S + s + 1];
+        int n = 0, n_notposref = 0, n_strong_alt = 0, n_ins = 0, n_del = 0, n_notref = 0, n_uq = 0;
+        int e1 = 0, e2 = 0, e3 = 0, e4 = 0, e5 = 0, e6 = 0, e7 = 0, e8 = 0, e9 = 0;
+        int n_snot0 = 0, n_sgt0 = 0;
+        double r_all = 0.0, r_major = 0.0, r_rate = 0.0;
+        for (int64_t row = lo + c.lane; row < hi; row += LANES) {
+            int64_t i = row - b->read_base;
+            uint32_t f = b->rflags[i];
+            if (!rd_kept(lf, f)) continue;
+            double pm = (double)b->pm[i], pa = (double)b->pa[i], pr = (double)b->pr[i];
+            double phb = (double)b->phb[i];
+            float psa = b->psa[i];
+            int kr_ref = kass_raftery(pr, pa), kr_alt = kass_raftery(pa, pr);
+            bool strong_ref = kr_ref >= 3, strong_alt = kr_alt >= 3;
+            int strand = rd_strand(f), orient = rd_orient(f), al = rd_altlocus(f);
+            bool major = (f & VLR_RF_READPOS_MAJOR) != 0, softclip = (f & VLR_RF_SOFTCLIPPED) != 0;
+            bool maxq = (f & VLR_RF_MAX_MAPQ) != 0;
+            int hl = rd_hlen(f);
+            n++;
+            n_snot0 += (psa != 0.0f);
+            n_sgt0 += (psa > 0.0f);
+            n_notposref += !(kr_ref >= 2);
+            n_strong_alt += strong_alt;
+            n_ins += hl > 0;
+            n_del += hl < 0;
+            n_notref += !(pr > pa);
+            if (pa > pr) {
+                g_alt_support++;
+                g_alt_row = row;
+            }
+            double w = exp(pm);
+            if (strong_ref) {
+                if (strand != 2) g_sb_all += w;
+                if (strand == 0) g_sb_fwd += w;
+                bool std_or = orient == 0 || orient == 1;
+                g_sr_std += std_or;
+                g_sr_f1r2 += orient == 0;
+                g_n_ref++;
+                g_nm_ref += !maxq;
+                r_all += w;
+                if (major) r_major += w;
+                r_rate += exp(pm + phb);
+            }
+            g_uncertain += !(orient == 0 || orient == 1);
+            if (strong_alt) {
+                g_n_alt++;
+                g_nm_alt += !maxq;
+            }
+            unsigned fl = 0;
+            fl |= (al != 2) ? 1u : 0u;
+            fl |= softclip ? 2u : 0u;
+            bool ev_sbf = strand == 0 || strand == 3, ev_sbr = strand == 1 || strand == 3;
+            bool ev_rob1 = orient != 1, ev_rob2 = orient != 0;
+            fl |= ev_sbf ? 4u : 0u;
+            fl |= ev_sbr ? 8u : 0u;
+            fl |= ev_rob1 ? 16u : 0u;
+            fl |= ev_rob2 ? 32u : 0u;
+            fl |= major ? 64u : 0u;
+            fl |= (al == 0) ? 128u : 0u;
+            fl |= (!maxq) ? 256u : 0u;
+            g_flags |= fl;
+            if (pm >= LN_095 && strong_alt) { // is_uniquely_mapping && is_strong_alt_support (bias/mod.rs:66-72)
+                n_uq++;
+                e1 += al == 0;
+                e9 += !maxq;
+                e2 += hl != 0;
+                e3 += softclip;
+                e4 += major;
+                e5 += ev_rob1;
+                e6 += ev_rob2;
+                e7 += ev_sbf;
+                e8 += ev_sbr;
+            }
+        }
+        n = w_sum_i(n);
+        c.n_obs[s] = n;
+        c.clear_ref[s] = (n > 10) && (w_sum_i(n_notposref) == 0);
+        c.s_one[s] = w_sum_i(n_snot0) == 0;
+        c.s_gt1[s] = w_sum_i(n_sgt0) != 0;
+        c.coef_off[s] = coef_total;
+        coef_total += n;
+        g_n += n;
+        bool any_strong_alt = w_sum_i(n_strong_alt) > 0;
+        bool has_ins = w_sum_i(n_ins) > 0, has_del = w_sum_i(n_del) > 0;
+        if (!(!any_strong_alt || (has_ins && has_del))) he_informative = false;
+        all_ref[s] = w_sum_i(n_notref) == 0;
+        uq_salt[s] = w_sum_i(n_uq);
+        ev_cnt[s][0] = 0;
+        ev_cnt[s][1] = w_sum_i(e1);
+        ev_cnt[s][2] = w_sum_i(e2);
+        ev_cnt[s][3] = w_sum_i(e3);
+        ev_cnt[s][4] = w_sum_i(e4);
+        ev_cnt[s][5] = w_sum_i(e5);
+        ev_cnt[s][6] = w_sum_i(e6);
+        ev_cnt[s][7] = w_sum_i(e7);
+        ev_cnt[s][8] = w_sum_i(e8);
+        ev_cnt[s][9] = w_sum_i(e9);
+        // read position bias: any pileup with a valid major rate (read_position_bias.rs:63-121)
+        double ra = w_sum_d(r_all);
+        if (ra > 10.0) {
+            double rm = w_sum_d(r_major), rr = w_sum_d(r_rate);
+            double major_rate = rm / ra;
+            if (rm > 0.0 && fabs(major_rate - rr) < 0.05) rpb_valid = true;
+        }
+    }
+    c.coef_total = coef_total;
+    g_sb_all = w_sum_d(g_sb_all);
+    g_sb_fwd = w_sum_d(g_sb_fwd);
+    g_uncertain = w_sum_i(g_uncertain);
+    g_sr_std = w_sum_i(g_sr_std);
+    g_sr_f1r2 = w_sum_i(g_sr_f1r2);
+    g_n_alt = w_sum_i(g_n_alt);
+    g_nm_alt = w_sum_i(g_nm_alt);
+    g_n_ref = w_sum_i(g_n_ref);
+    g_nm_ref = w_sum_i(g_nm_ref);
+    g_flags = w_or_u(g_flags);
+    g_alt_support = w_sum_i(g_alt_support);
+    // adjust_singleton_evidence (read_observation.rs:548-562)
+    c.singleton_row = -1;
+    if (g_alt_support == 1) {
+        int hi32 = w_max_i((int)(g_alt_row >> 31)); // rows are < 2^62; split to use the integer reductions
+        int lo31 = w_max_i((g_alt_row >> 31) == hi32 ? (int)(g_alt_row & 0x7fffffff) : -1);
+        c.singleton_row = ((int64_t)hi32 << 31) | (int64_t)lo31;
+        c.status |= VLR_ST_SINGLETON_ADJUSTED;
+    }
+    {
+        // Hint::FilteredNonStandardAlignments (calling.rs:600-602, 620-624)
+        int total = 0;
+        for (int s = 0; s < S; ++s)
+            total += (int)(b->read_offsets[c.locus * S + s + 1] - b->read_offsets[c.locus * S + s]);
+        if (total != g_n) c.status |= VLR_ST_FILTERED_NONSTANDARD;
+    }
+
+    // strand bias forward rate (strand_bias.rs:79-123)
+    bool sb_informative = false;
+    plan.forward_rate = 0.5;
+    if (g_sb_all > 2.0) {
+        double ff = g_sb_fwd / g_sb_all;
+        if (g_sb_all > 100.0 && ff > 0.0 && ff < 1.0) {
+            plan.forward_rate = ff;
+            sb_informative = true;
+        } else if (ff >= 0.4 && ff <= 0.6) {
+            plan.forward_rate = 0.5;
+            sb_informative = true;
+        }
+    }
+    plan.has_alt_loci = (g_flags & 1u) != 0;
+    // read orientation bias (read_orientation_bias.rs:38-97)
+    bool rob_informative = false;
+    {
+        bool enough = (double)g_uncertain < ((double)g_n / 2.0);
+        bool uniform = false;
+        if (g_sr_std > 2) {
+            double fraction = (double)g_sr_f1r2 / (double)g_sr_std;
+            uniform = fraction >= 0.3 && fraction <= 0.7;
+        }
+        rob_informative = enough && uniform;
+    }
+    // alt locus bias (alt_locus_bias.rs:124-144)
+    bool alb_informative;
+    {
+        bool enough_alt = g_n_alt > 0 && (double)g_nm_alt > ((double)g_n_alt * 0.1) && (g_n_alt - g_nm_alt) < 10;
+        bool enough_ref = g_n_ref > 0 && ((double)g_nm_ref < ((double)g_n_ref * 0.9));
+        alb_informative = enough_alt && (plan.has_alt_loci || enough_ref);
+    }
+
+    plan.n_twins = 0;
+    plan.n_surviving = 0;
+    for (int id = 1; id <= 8; ++id) {
+        uint32_t need = id == 1 ? VLR_LF_CHECK_ALB
+                        : id == 2 ? VLR_LF_CHECK_HE
+                        : id == 3 ? VLR_LF_CHECK_SCB
+                        : id == 4 ? VLR_LF_CHECK_RPB
+                        : id <= 6 ? VLR_LF_CHECK_ROB
+                                  : VLR_LF_CHECK_SB;
+        if (!(lf & need)) continue;
+        plan.n_twins++;
+        bool possible, informative;
+        switch (id) {
+        case 1:
+            possible = plan.has_alt_loci ? (g_flags & 128u) != 0 : (g_flags & 256u) != 0;
+            informative = alb_informative;
+            break;
+        case 2: possible = informative = he_informative; break;
+        case 3:
+            possible = (g_flags & 2u) != 0;
+            informative = (g_flags & 2u) != 0;
+            break;
+        case 4:
+            possible = (g_flags & 64u) != 0;
+            informative = rpb_valid;
+            break;
+        case 5:
+            possible = (g_flags & 16u) != 0;
+            informative = rob_informative;
+            break;
+        case 6:
+            possible = (g_flags & 32u) != 0;
+            informative = rob_informative;
+            break;
+        case 7:
+            possible = (g_flags & 4u) != 0;
+            informative = sb_informative;
+            break;
+        default:
+            possible = (g_flags & 8u) != 0;
+            informative = sb_informative;
+            break;
+        }
+        if (!(possible && informative)) continue;
+        bool likely = false;
+        if (id == 2) {
+            likely = he_informative; // homopolymer_error.rs:78-80
+        } else {
+            for (int s = 0; s < S; ++s) { // bias/mod.rs:62-104
+                bool l;
+                if (uq_salt[s] >= 10) {
+                    int ev = (id == 1 && !plan.has_alt_loci) ? ev_cnt[s][9] : ev_cnt[s][id];
+                    double ratio = (double)ev / (double)uq_salt[s];
+                    l = ratio >= 0.66666;
+                } else if (all_ref[s]) {
+                    l = false; // also the empty pileup
+                } else {
+                    l = true;
+                }
+                if (l) likely = true;
+            }
+        }
+        if (likely) plan.surviving[plan.n_surviving++] = id;
+    }
+}
+
+// Hoist everything VAF-independent of one (sample, artifact config) into per-read coefficients.
+//   L_r(x) = e^{K_r} * (alpha_r * x + beta_r * (1 - x) + gamma_r)
+//   ln alpha' = prob_mapping + bias.prob_alt + prob_alt     (likelihood.rs:213, :185/:107)
+//   ln beta'  = prob_mapping + prob_ref + bias.prob_ref      (likelihood.rs:215)
+//   ln gamma' = prob_mismapping + prob_missed_allele + bias.prob_any   (likelihood.rs:186-188)
+//   K_r = max of the three; x = effective alt-sampling probability (likelihood.rs:43-53, :98-103).
+VLR_DEV_NOINLINE void read_coefficients(Ctx& c, int s) {
+    const DevBatch* b = c.b;
+    const int S = c.sc->S;
+    const Art a = c.art;
+    int64_t lo = b->read_offsets[c.locus * S + s], hi = b->read_offsets[c.locus * S + s + 1];
+    double* out = c.coef + (int64_t)c.coef_off[s] * 4;
+    double ksum = 0.0;
+    bool dead = false, bad = false;
+    int base = 0; // kept reads before this chunk of LANES rows
+    for (int64_t row0 = lo; row0 < hi; row0 += LANES) {
+        int64_t row = row0 + c.lane;
+        bool valid = row < hi;
+        Read r;
+        bool kept = false;
+        if (valid) {
+            r = load_read(b, row);
+            kept = rd_kept(c.lf, r.f);
+        }
+#ifdef VLR_HOST_EMU
+        int pos = base;
+        int n_kept = kept ? 1 : 0;
+#else
+        unsigned m = __ballot_sync(FULL, kept);
+        int pos = base + __popc(m & ((1u << c.lane) - 1u));
+        int n_kept = __popc(m);
+#endif
+        if (kept) {
+            double pa = r.pa, pr = r.pr;
+            if (row == c.singleton_row) pa = pr = LN_05;
+            int strand = rd_strand(r.f), orient = rd_orient(r.f), al = rd_altlocus(r.f);
+            bool major = (r.f & VLR_RF_READPOS_MAJOR) != 0, softclip = (r.f & VLR_RF_SOFTCLIPPED) != 0;
+            bool maxq = (r.f & VLR_RF_MAX_MAPQ) != 0;
+            // strand bias (strand_bias.rs:28-53)
+            double sb_alt;
+            if (strand == 3) sb_alt = 0.0;
+            else if (a.id == 7) sb_alt = strand == 0 ? 0.0 : neg_inf();
+            else if (a.id == 8) sb_alt = strand == 1 ? 0.0 : neg_inf();
+            else if (strand == 2) sb_alt = r.pdo;
+            else {
+                double rate = strand == 0 ? a.forward_rate : 1.0 - a.forward_rate;
+                sb_alt = log(rate) + ln_one_minus_exp(r.pdo);
+            }
+            // read orientation bias (read_orientation_bias.rs:17-29)
+            double rob_alt = LN_05;
+            if (a.id == 5) rob_alt = orient == 0 ? 0.0 : (orient == 1 ? neg_inf() : LN_05);
+            else if (a.id == 6) rob_alt = orient == 1 ? 0.0 : (orient == 0 ? neg_inf() : LN_05);
+            // read position bias (read_position_bias.rs:17-61)
+            double rpb_any = major ? r.phb : (r.phb != 0.0 ? ln_one_minus_exp(r.phb) : 0.0);
+            double rpb_alt = a.id == 4 ? (major ? 0.0 : neg_inf()) : rpb_any;
+            // softclip bias (softclip_bias.rs:14-24)
+            double scb_alt = a.id == 3 ? (softclip ? 0.0 : neg_inf()) : 0.0;
+            // homopolymer error (homopolymer_error.rs:22-40): same term for alt and ref, none for any
+            double he = a.id == 2 ? (r.has_hart ? r.hart : 0.0) : (r.has_hvar ? r.hvar : 0.0);
+            // alt locus bias (alt_locus_bias.rs:62-112)
+            double alb_alt = LN_05, alb_ref = LN_05;
+            if (a.id == 1) {
+                if (a.has_alt_loci) {
+                    alb_alt = al == 0 ? 0.0 : neg_inf();
+                    alb_ref = al == 0 ? neg_inf() : 0.0;
+                } else {
+                    alb_alt = maxq ? neg_inf() : 0.0;
+                }
+            }
+            // bias/mod.rs:259-284 (summation order of the reference)
+            double bA = sb_alt + rob_alt + rpb_alt + scb_alt + he + alb_alt;
+            double bR = LN_05 + LN_05 + rpb_any + 0.0 + he + alb_ref;
+            double bAny = LN_05 + LN_05 + rpb_any + 0.0 + 0.0 + LN_05;
+            double pmis = ln_one_minus_exp(r.pm); // read_observation.rs:283-286
+            double lnA = r.pm + (bA + pa);
+            double lnR = r.pm + (pr + bR);
+            double lnC = pmis + r.pmiss + bAny;
+            double K = fmax(lnA, fmax(lnR, lnC));
+            double al_ = 0.0, be_ = 0.0, ga_ = 0.0;
+            if (K != K || lnA != lnA || lnR != lnR || lnC != lnC || K == INFINITY) {
+                bad = true;
+            } else if (K == neg_inf()) {
+                dead = true;
+            } else {
+                al_ = exp(lnA - K);
+                be_ = exp(lnR - K);
+                ga_ = exp(lnC - K);
+                ksum += K;
+            }
+            double* o = out + (int64_t)pos * 4;
+            o[0] = al_;
+            o[1] = be_;
+            o[2] = ga_;
+            o[3] = exp(r.psa);
+        }
+        base += n_kept;
+    }
+    ksum = w_sum_d(ksum);
+    if (w_any(bad)) {
+        c.status |= VLR_ST_NAN;
+        ksum = NAN;
+    } else if (w_any(dead)) {
+        ksum = neg_inf();
+    }
+    c.ksum[s] = ksum;
+    warp_sync();
+}
+
+// Pileup log-likelihood of sample s at (vaf, contaminant vaf): likelihood.rs:122-158 / :227-249.
+VLR_DEV_NOINLINE double sample_likelihood(Ctx& c, int s, double vaf, double vaf_by) {
+    const vlr_sample_t& sm = c.sc->samples[s];
+    const int n = c.n_obs[s];
+    if (n == 0) return 0.0; // empty fold = ln 1
+    const double ksum = c.ksum[s];
+    if (ksum != ksum) return NAN;
+    c.n_pileup_evals++;
+    double rho = 1.0, iota = 0.0;
+    if (sm.contamination_by >= 0) {
+        rho = 1.0 - sm.contamination_fraction; // e^{purity}
+        iota = 1.0 - rho;                      // e^{impurity} (likelihood.rs:77-84)
+    }
+    // x = rho * xp + iota * xs with xp = (vaf == 1 ? 1 : vaf * s_r), y = 1 - x accordingly
+    const bool p1 = vaf == 1.0, s1 = vaf_by == 1.0;
+    const double X1 = (p1 ? 0.0 : rho * vaf) + ((iota != 0.0 && !s1) ? iota * vaf_by : 0.0);
+    const double X0 = (p1 ? rho : 0.0) + ((iota != 0.0 && s1) ? iota : 0.0);
+    const double Yp = (p1 ? 0.0 : rho * (1.0 - vaf)) + ((iota != 0.0 && !s1) ? iota * (1.0 - vaf_by) : 0.0);
+    const double Y0 = (p1 ? 0.0 : rho) + ((iota != 0.0 && !s1) ? iota : 0.0);
+    const double* co = c.coef + (int64_t)c.coef_off[s] * 4;
+    double acc = 1.0;
+    int ex = 0;
+    bool zero = false;
+    const bool s_one = c.s_one[s] != 0, s_gt1 = c.s_gt1[s] != 0;
+    const double xu = X1 + X0;
+    int k = 0;
+    for (int r = c.lane; r < n; r += LANES) {
+        const double al = co[4 * r], be = co[4 * r + 1], ga = co[4 * r + 2];
+        double t;
+        if (s_one) {
+            t = fma(al, xu, fma(be, Yp, ga));
+        } else if (!s_gt1) {
+            const double sr = co[4 * r + 3];
+            t = fma(al, fma(sr, X1, X0), fma(be, fma(-sr, X1, Y0), ga));
+        } else {
+            // prob_sample_alt > 0: cap_numerical_overshoot applies per component (likelihood.rs:43-53)
+            const double sr = co[4 * r + 3];
+            double xp = p1 ? 1.0 : vaf * sr, xs = s1 ? 1.0 : vaf_by * sr;
+            if (xp > 1.0) {
+                if (log(xp) > NUMERICAL_EPSILON) c.status |= VLR_ST_OVERSHOOT;
+                xp = 1.0;
+            }
+            if (xs > 1.0) {
+                if (iota != 0.0 && log(xs) > NUMERICAL_EPSILON) c.status |= VLR_ST_OVERSHOOT;
+                xs = 1.0;
+            }
+            double x = rho * xp + iota * xs, y = rho * (1.0 - xp) + iota * (1.0 - xs);
+            t = fma(al, x, fma(be, y, ga));
+        }
+        if (t < 1e-30) { // rare: keep the running product a normal number
+            if (t <= 0.0) {
+                zero = true;
+                t = 1.0;
+            } else {
+                int e2;
+                t = frexp(t, &e2) * 2.0;
+                ex += e2 - 1;
+            }
+        }
+        acc *= t;
+        if (++k == 8) {
+            k = 0;
+            int hi = d_hi(acc);
+            ex += ((hi >> 20) & 0x7ff) - 1023;
+            acc = d_make((hi & 0x800fffff) | (1023 << 20), d_lo(acc));
+        }
+    }
+    {
+        int hi = d_hi(acc);
+        ex += ((hi >> 20) & 0x7ff) - 1023;
+        acc = d_make((hi & 0x800fffff) | (1023 << 20), d_lo(acc));
+    }
+    acc = w_mul_d(acc); // 32 mantissas in [1,2): < 2^32
+    ex = w_sum_i(ex);
+    unsigned ov = w_or_u(c.status & VLR_ST_OVERSHOOT);
+    c.status |= ov;
+    if (w_any(zero) || ksum == neg_inf()) return neg_inf();
+    if (acc != acc) {
+        c.status |= VLR_ST_NAN;
+        return NAN;
+    }
+    return (log(acc) + (double)ex * LN_2) + ksum;
+}
+
+VLR_DEV double cached_sample_likelihood(Ctx& c, int s, double vaf, double vaf_by) {
+    int n = c.lc_n[s];
+    int ways = n < LC_WAYS ? n : LC_WAYS;
+    for (int w = 0; w < ways; ++w)
+        if (c.lc_k1[s][w] == vaf && c.lc_k2[s][w] == vaf_by) return c.lc_v[s][w];
+    double v = sample_likelihood(c, s, vaf, vaf_by);
+    int slot = n % LC_WAYS;
+    c.lc_k1[s][slot] = vaf;
+    c.lc_k2[s][slot] = vaf_by;
+    c.lc_v[s][slot] = v;
+    c.lc_n[s] = n + 1;
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------ prior
+VLR_DEV double vtf(const Ctx& c) { return c.sc->vtf[c.vartype]; }
+VLR_DEV bool prior_semr(const Ctx& c, int s, double& out) { // prior.rs:250-257
+    if (!(c.semr_override != c.semr_override)) {
+        out = c.semr_override;
+        return true;
+    }
+    double r = c.sc->samples[s].somatic_effective_mutation_rate;
+    if (r != r) return false;
+    out = log(r * vtf(c));
+    return true;
+}
+VLR_DEV bool prior_het(const Ctx& c, double& out) { // prior.rs:263-270
+    if (!(c.het_override != c.het_override)) {
+        out = c.het_override;
+        return true;
+    }
+    double h = c.sc->heterozygosity;
+    if (h != h) return false;
+    out = log(exp(log(h)) * vtf(c));
+    return true;
+}
+VLR_DEV bool universe_contains(const Ctx& c, int s, double v) {
+    const vlr_sample_t& sm = c.sc->samples[s];
+    for (int i = 0; i < sm.n_universe; ++i) {
+        const vlr_spectrum_t& sp = c.sc->spectra[sm.universe_offset + i];
+        if (sp.kind == VLR_SPECTRUM_SET) {
+            for (int j = 0; j < sp.n_vafs; ++j)
+                if (c.sc->set_vafs[sp.vaf_offset + j] == v) return true;
+        } else {
+            Range r{sp.start, sp.end, sp.left_exclusive != 0, sp.right_exclusive != 0};
+            if (range_contains(r, v)) return true;
+        }
+    }
+    return false;
+}
+VLR_DEV double prob_somatic_mutation(double rate, double somatic_vaf) { // prior.rs:440-456
+    if (relative_eq(somatic_vaf, 0.0)) return ln_one_minus_exp(rate);
+    return rate;
+}
+VLR_DEV double binomial_coeff(unsigned n, unsigned k) { // statrs factorial::binomial
+    if (k > n) return 0.0;
+    double fn = 1.0, fk = 1.0, fnk = 1.0;
+    for (unsigned i = 2; i <= n; ++i) fn *= (double)i;
+    for (unsigned i = 2; i <= k; ++i) fk *= (double)i;
+    for (unsigned i = 2; i <= n - k; ++i) fnk *= (double)i;
+    return floor(0.5 + exp(log(fn) - log(fk) - log(fnk)));
+}
+VLR_DEV_NOINLINE double prob_select(unsigned ploidy, unsigned source_alt, unsigned target_alt, unsigned target_ref) {
+    unsigned draws = target_alt + target_ref, x = target_alt; // Hypergeometric(N = ploidy, K = source_alt, n = draws).pmf(x)
+    double pmf = x > draws ? 0.0
+                           : binomial_coeff(source_alt, x) * binomial_coeff(ploidy - source_alt, draws - x) /
+                                 binomial_coeff(ploidy, draws);
+    return log(pmf);
+}
+VLR_DEV_NOINLINE double prob_mendelian_alt_counts(Ctx& c, unsigned sp0, unsigned sp1, unsigned tp, unsigned sa0, unsigned sa1,
+                                         unsigned ta, double rate) { // prior.rs:600-678
+    unsigned c0[2], c1[2];
+    int n0, n1;
+    if (sp0 % 2 == 0) {
+        c0[0] = sp0 / 2;
+        n0 = 1;
+    } else {
+        c0[0] = (unsigned)floor((double)sp0 / 2.0);
+        c0[1] = (unsigned)ceil((double)sp0 / 2.0);
+        n0 = 2;
+    }
+    if (sp1 % 2 == 0) {
+        c1[0] = sp1 / 2;
+        n1 = 1;
+    } else {
+        c1[0] = (unsigned)floor((double)sp1 / 2.0);
+        c1[1] = (unsigned)ceil((double)sp1 / 2.0);
+        n1 = 2;
+    }
+    Lse acc;
+    acc.init();
+    bool valid = false;
+    for (int i = 0; i < n0; ++i)
+        for (int j = 0; j < n1; ++j) {
+            unsigned p1 = c0[i], p2 = c1[j];
+            if (p1 + p2 != tp) continue;
+            valid = true;
+            unsigned m1 = sa0 < p1 ? sa0 : p1, m2 = sa1 < p2 ? sa1 : p2;
+            for (unsigned a1 = 0; a1 <= m1; ++a1)
+                for (unsigned a2 = 0; a2 <= m2; ++a2)
+                    if (a1 + a2 <= ta) {
+                        double p = prob_select(sp0, sa0, a1, p1 - a1) + prob_select(sp1, sa1, a2, p2 - a2);
+                        int missing = (int)ta - (int)(a1 + a2);
+                        acc.add(p + log(rate) * (double)missing);
+                    }
+        }
+    if (!valid) {
+        c.status |= VLR_ST_NAN; // the reference panics (prior.rs:672-676)
+        return neg_inf();
+    }
+    return acc.value();
+}
+
+// prior.rs:298-384, recursion end: all germline VAFs chosen
+VLR_DEV_NOINLINE double prior_leaf(Ctx& c, const Ops& ev, const double* g) {
+    const DevScenario* sc = c.sc;
+    const int S = sc->S;
+    double prob = 0.0, het;
+    if (prior_het(c, het)) { // prior.rs:554-582
+        unsigned m = 0, n = 0;
+        for (int s = 0; s < S; ++s) {
+            const vlr_sample_t& sm = sc->samples[s];
+            if (sm.inheritance == VLR_INHERIT_NONE && sm.ploidy >= 0 && !sm.uniform_prior) {
+                m += (unsigned)round((double)sm.ploidy * g[s]);
+                n += (unsigned)sm.ploidy;
+            }
+        }
+        if (m > 0) {
+            prob = het - log((double)m);
+        } else {
+            Lse acc;
+            acc.init();
+            for (unsigned i = 1; i <= n; ++i) acc.add(het - log((double)i));
+            prob = ln_one_minus_exp(acc.value());
+        }
+    }
+    double sum = 0.0;
+    for (int s = 0; s < S; ++s) {
+        const vlr_sample_t& sm = sc->samples[s];
+        if (sm.uniform_prior) continue;
+        double rate;
+        switch (sm.inheritance) {
+        case VLR_INHERIT_MENDELIAN: {
+            const vlr_sample_t& pa = sc->samples[sm.parent_a];
+            const vlr_sample_t& pb = sc->samples[sm.parent_b];
+            unsigned na = (unsigned)round(g[sm.parent_a] * (double)pa.ploidy);
+            unsigned nb = (unsigned)round(g[sm.parent_b] * (double)pb.ploidy);
+            unsigned nc = (unsigned)round(g[s] * (double)sm.ploidy);
+            double gr = sm.germline_mutation_rate * vtf(c);
+            double p = prob_mendelian_alt_counts(c, (unsigned)pa.ploidy, (unsigned)pb.ploidy, (unsigned)sm.ploidy, na, nb,
+                                                 nc, gr);
+            if (prior_semr(c, s, rate)) p += prob_somatic_mutation(rate, ev.vaf[s] - g[s]);
+            sum += p;
+            break;
+        }
+        case VLR_INHERIT_CLONAL: { // prior.rs:458-514
+            int parent = sm.parent_a;
+            double p;
+            if (!relative_eq(g[s], g[parent])) p = neg_inf();
+            else {
+                bool has_rate = prior_semr(c, s, rate);
+                double psv = ev.vaf[parent] - g[parent], sv = ev.vaf[s] - g[s];
+                if (sm.clonal_somatic && has_rate) p = (psv != 0.0) ? 0.0 : prob_somatic_mutation(rate, sv);
+                else if (sm.clonal_somatic) p = relative_eq(sv, psv) ? 0.0 : neg_inf();
+                else if (has_rate) p = prob_somatic_mutation(rate, sv);
+                else p = 0.0;
+            }
+            sum += p;
+            break;
+        }
+        case VLR_INHERIT_SUBCLONAL: { // prior.rs:516-552
+            int parent = sm.parent_a;
+            double p;
+            if (!relative_eq(g[s], g[parent])) p = neg_inf();
+            else if (prior_semr(c, s, rate)) {
+                p = (ev.vaf[parent] == 0.0 && g[s] == 0.0) ? prob_somatic_mutation(rate, ev.vaf[s]) : 0.0;
+            } else {
+                p = relative_eq(ev.vaf[s] - g[s], ev.vaf[parent] - g[parent]) ? 0.0 : neg_inf();
+            }
+            sum += p;
+            break;
+        }
+        default:
+            if (prior_semr(c, s, rate)) sum += prob_somatic_mutation(rate, ev.vaf[s] - g[s]);
+        }
+    }
+    prob += sum;
+    if (!(prob <= 0.0)) c.status |= VLR_ST_PRIOR_POSITIVE; // assert!(*prob <= 0.0), prior.rs:378
+    return prob;
+}
+
+// prior.rs:385-437: the recursion over germline VAF assignments, unrolled into an odometer. Nested ln_sum_exp of the
+// reference == one ln_sum_exp over the flattened product (rounding-level difference only).
+VLR_DEV_NOINLINE double prior_full(Ctx& c, const Ops& ev) {
+    const DevScenario* sc = c.sc;
+    const int S = sc->S;
+    int nchoice[MAXS], idx[MAXS];
+    double g[MAXS];
+    bool any_multi = false;
+    for (int s = 0; s < S; ++s) {
+        const vlr_sample_t& sm = sc->samples[s];
+        double v = ev.vaf[s];
+        idx[s] = 0;
+        if (sm.ploidy == 0 && v != 0.0) return neg_inf();
+        if (sm.uniform_prior) {
+            if (!universe_contains(c, s, v)) return neg_inf();
+            nchoice[s] = 1;
+            g[s] = 0.0;
+        } else if (!(sm.somatic_effective_mutation_rate != sm.somatic_effective_mutation_rate)) {
+            if (sm.ploidy < 0) { // unreachable!() in the reference
+                c.status |= VLR_ST_NAN;
+                return neg_inf();
+            }
+            nchoice[s] = sm.ploidy + 1;
+            g[s] = 0.0;
+            any_multi = any_multi || nchoice[s] > 1;
+        } else if (sm.ploidy >= 0 && !(sc->heterozygosity != sc->heterozygosity)) {
+            double n_alt = (double)sm.ploidy * v;
+            if (!relative_eq(n_alt, round(n_alt))) return neg_inf();
+            nchoice[s] = 1;
+            g[s] = v;
+        } else {
+            c.status |= VLR_ST_NAN; // unreachable!() in the reference
+            return neg_inf();
+        }
+    }
+    if (!any_multi) return prior_leaf(c, ev, g);
+    Lse acc;
+    acc.init();
+    for (;;) {
+        for (int s = 0; s < S; ++s) {
+            const vlr_sample_t& sm = sc->samples[s];
+            if (nchoice[s] > 1 || (!sm.uniform_prior && !(sm.somatic_effective_mutation_rate !=
+                                                         sm.somatic_effective_mutation_rate)))
+                g[s] = sm.ploidy > 0 ? (double)idx[s] / (double)sm.ploidy : 0.0;
+        }
+        acc.add(prior_leaf(c, ev, g));
+        int s = S - 1;
+        for (; s >= 0; --s) {
+            if (++idx[s] < nchoice[s]) break;
+            idx[s] = 0;
+        }
+        if (s < 0) break;
+    }
+    return acc.value();
+}
+
+// Prior::compute (prior.rs:718-761)
+VLR_DEV_NOINLINE double prior_compute(Ctx& c, const Ops& ev) {
+    const DevScenario* sc = c.sc;
+    if (!sc->full_prior && !sc->all_uniform) {
+        bool absent = true;
+        for (int s = 0; s < sc->S; ++s)
+            if (ev.vaf[s] != 0.0) absent = false;
+        if (!absent) {
+            double full = prior_full(c, ev);
+            if (full == neg_inf()) return full;
+            if (c.prior_absent != c.prior_absent) {
+                Ops z;
+                for (int s = 0; s < MAXS; ++s) z.vaf[s] = 0.0;
+                z.set_mask = (1u << sc->S) - 1u;
+                z.disc_mask = z.set_mask;
+                z.lfc_mask = 0;
+                c.prior_absent = prior_full(c, z);
+            }
+            return ln_one_minus_exp(c.prior_absent);
+        }
+    }
+    return prior_full(c, ev);
+}
+
+// ------------------------------------------------------------------------------------------------ joint
+// GenericLikelihood::compute (generic.rs:500-554) + Prior + rust-bio Model::joint_prob bookkeeping
+VLR_DEV_NOINLINE double joint(Ctx& c, const Ops& ops) {
+    const DevScenario* sc = c.sc;
+    const int S = sc->S;
+    double prior = prior_compute(c, ops);
+    double lh = 0.0;
+    bool lfc_ok = true;
+    for (int k = 0; k < sc->n_lfc_nodes; ++k) {
+        if (!(ops.lfc_mask & (1u << k))) continue;
+        const vlr_node_t& nd = sc->nodes[sc->lfc_nodes[k]];
+        double a = ops.vaf[nd.sample], b2 = ops.vaf[nd.sample_b];
+        double lfc;
+        if (a == 0.0 && b2 == 0.0) lfc = 0.0;
+        else {
+            lfc = log2(a) - log2(b2);
+            if (lfc != lfc) c.status |= VLR_ST_NAN;
+        }
+        bool t;
+        switch (nd.cmp) {
+        case VLR_CMP_EQ: t = relative_eq(lfc, nd.lfc_value); break;
+        case VLR_CMP_GT: t = lfc > nd.lfc_value; break;
+        case VLR_CMP_GE: t = lfc >= nd.lfc_value; break;
+        case VLR_CMP_LT: t = lfc < nd.lfc_value; break;
+        case VLR_CMP_LE: t = lfc <= nd.lfc_value; break;
+        default: t = !relative_eq(lfc, nd.lfc_value);
+        }
+        if (!t) {
+            lfc_ok = false;
+            break;
+        }
+    }
+    if (!lfc_ok) lh = neg_inf();
+    else {
+        for (int s = 0; s < S; ++s) {
+            const vlr_sample_t& sm = sc->samples[s];
+            double by = sm.contamination_by >= 0 ? ops.vaf[sm.contamination_by] : 0.0;
+            lh += cached_sample_likelihood(c, s, ops.vaf[s], by);
+        }
+    }
+    double j = prior + lh;
+    if (j != j) c.status |= VLR_ST_NAN;
+    // rust-bio Model::joint_prob records every base event; only artifact-free ones can enter an AFD (calling.rs:912)
+    if (c.be != nullptr && c.art.id == 0) {
+        if (c.n_rec < (uint32_t)BE_CAP) {
+            if (c.lane == 0) {
+                double* e = c.be + (int64_t)c.n_rec * (2 + S);
+                e[0] = j;
+                e[1] = d_make((int)ops.lfc_mask, (int)ops.disc_mask);
+                for (int s = 0; s < S; ++s) e[2 + s] = ops.vaf[s];
+            }
+            c.n_rec++;
+        } else {
+            c.status |= VLR_ST_BASE_EVENTS_OVERFLOW;
+        }
+    }
+    // bookkeeping for MAP (calling.rs:851-870): best base event per (event, plain | artifact)
+    c.n_base++;
+    int slot = c.cur_slot;
+    if (!c.map_set[slot] || j > c.map_joint[slot]) {
+        c.map_set[slot] = 1;
+        c.map_joint[slot] = j;
+        c.map_cfg[slot] = c.art.id;
+        c.map_disc[slot] = ops.disc_mask;
+        for (int s = 0; s < S; ++s) c.map_vaf[slot][s] = ops.vaf[s];
+    }
+    return j;
+}
+
+// ------------------------------------------------------------------------------------------------ density
+VLR_DEV_NOINLINE double density(Ctx& c, int ni, Ops& ops, int level);
+
+VLR_DEV_NOINLINE double subdensity(Ctx& c, const vlr_node_t& node, Ops& ops, int level) {
+    double p;
+    if (node.n_children == 0) p = joint(c, ops);
+    else if (node.n_children > 1) {
+        Lse acc;
+        acc.init();
+        for (int k = 0; k < node.n_children; ++k) {
+            Ops cl = ops;
+            acc.add(density(c, node.first_child + k, cl, level));
+        }
+        p = acc.value();
+    } else {
+        p = density(c, node.first_child, ops, level);
+    }
+    if (p != p) c.status |= VLR_ST_NAN;
+    return p;
+}
+
+VLR_DEV bool ops_lfc_bounds(const Ctx& c, const Ops& ops, int sample, Range& out) { // generic.rs:148-174
+    const DevScenario* sc = c.sc;
+    bool have = false;
+    for (int k = 0; k < sc->n_lfc_nodes; ++k) {
+        if (!(ops.lfc_mask & (1u << k))) continue;
+        const vlr_node_t& nd = sc->nodes[sc->lfc_nodes[k]];
+        bool got = false;
+        Range b;
+        if (nd.sample == sample) {
+            if (ops.set_mask & (1u << nd.sample_b)) {
+                int cmp = lfc_invert_cmp(nd.cmp);
+                double val = (nd.cmp == VLR_CMP_EQ || nd.cmp == VLR_CMP_NE) ? nd.lfc_value : -nd.lfc_value;
+                b = lfc_infer_bounds(cmp, val, ops.vaf[nd.sample_b]);
+                got = true;
+            }
+        } else if (nd.sample_b == sample) {
+            if (ops.set_mask & (1u << nd.sample)) {
+                b = lfc_infer_bounds(nd.cmp, nd.lfc_value, ops.vaf[nd.sample]);
+                got = true;
+            }
+        }
+        if (got) {
+            out = have ? range_intersect(out, b) : b;
+            have = true;
+        }
+    }
+    return have;
+}
+
+VLR_DEV void ops_push(Ops& o, int sample, double vaf, bool discrete) {
+    o.vaf[sample] = vaf;
+    o.set_mask |= 1u << sample;
+    if (discrete) o.disc_mask |= 1u << sample;
+    else o.disc_mask &= ~(1u << sample);
+}
+
+VLR_DEV_NOINLINE double eval_point(Ctx& c, const vlr_node_t& node, const Ops& ops, double vaf, int level) {
+    Ops cl = ops;
+    ops_push(cl, node.sample, vaf, false);
+    return subdensity(c, node, cl, level + 1);
+}
+
+// ln_simpsons_integrate_exp (rust-bio)
+VLR_DEV_NOINLINE double integrate_simpson(Ctx& c, const vlr_node_t& node, const Ops& ops, double a, double b, int n, int level) {
+    Lse acc;
+    acc.init();
+    double step = (b - a) / (double)(n - 1);
+    for (int i = 1; i < n - 1; ++i) {
+        double w = (double)(2 + (i % 2) * 2);
+        acc.add(eval_point(c, node, ops, a + step * (double)i, level) + log(w));
+    }
+    acc.add(eval_point(c, node, ops, a, level));
+    acc.add(eval_point(c, node, ops, b, level));
+    return acc.value() + log(b - a) - log((double)(n - 1)) - log(3.0);
+}
+
+// utils/adaptive_integration.rs:25-141. Points are appended to the per-level grid (duplicates allowed: they sort
+// next to each other and contribute zero-width trapezoids); argmax ties: ascending x, first maximum wins.
+VLR_DEV_NOINLINE double integrate_adaptive(Ctx& c, const vlr_node_t& node, const Ops& ops, double min_point, double max_point,
+                                  double res, int level) {
+    double* gx = c.ws->grid_x[level];
+    double* gf = c.ws->grid_f[level];
+    int n = 0;
+    bool overflow = false;
+    auto visit = [&](double x) -> double {
+        double f = eval_point(c, node, ops, x, level);
+        if (n < GRID_CAP) {
+            if (c.lane == 0) {
+                gx[n] = x;
+                gf[n] = f;
+            }
+            n++;
+        } else {
+            overflow = true;
+        }
+        return f;
+    };
+    double left = min_point, right = max_point;
+    double f_left = visit(left), f_right = visit(right);
+    bool have_middle = false;
+    double first_middle = 0.0, middle = 0.0;
+    while ((((right - left) >= res) && left < right) || !have_middle) {
+        middle = (right + left) / 2.0;
+        visit(middle);
+        double m1 = (middle + left) / 2.0, m2 = (right + middle) / 2.0;
+        double f_m1 = visit(m1), f_m2 = visit(m2);
+        if (!have_middle) first_middle = middle;
+        have_middle = true;
+        double xs[4] = {left, m1, m2, right};
+        double fs[4] = {f_left, f_m1, f_m2, f_right};
+        int idx = 0;
+#pragma unroll
+        for (int i = 1; i < 4; ++i)
+            if (fs[i] > fs[idx]) idx = i;
+        // neighbours of the argmax; position() in the reference resolves duplicates to the first equal x
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (i < idx && xs[i] == xs[idx]) {
+                idx = i;
+                break;
+            }
+        double nl = idx > 0 ? xs[idx - 1] : xs[idx], nfl = idx > 0 ? fs[idx - 1] : fs[idx];
+        double nr = idx < 3 ? xs[idx + 1] : xs[idx], nfr = idx < 3 ? fs[idx + 1] : fs[idx];
+        left = nl;
+        f_left = nfl;
+        right = nr;
+        f_right = nfr;
+        if (overflow) break;
+    }
+    if (middle < first_middle) visit((max_point + first_middle) / 2.0);
+    else visit((first_middle + min_point) / 2.0);
+    {
+        double lo = fmax(middle - (res * 3.0), min_point);
+        double step = (middle - lo) / 3.0;
+        for (int i = 0; i < 3; ++i) visit(lo + step * (double)i);
+        double hi = fmin(middle + (res * 3.0), max_point);
+        step = (hi - middle) / 3.0;
+        for (int i = 1; i < 4; ++i) visit(middle + step * (double)i);
+    }
+    if (overflow) c.status |= VLR_ST_GRID_OVERFLOW;
+    warp_sync();
+    // sort by x (rank sort, lanes over points), then ln_trapezoidal_integrate_grid_exp with lanes over intervals
+    double* sx = c.ws->sort_x;
+    double* sf = c.ws->sort_f;
+    for (int i = c.lane; i < n; i += LANES) {
+        double xi = gx[i];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) {
+            double xj = gx[j];
+            rank += (xj < xi) || (xj == xi && j < i);
+        }
+        sx[rank] = xi;
+        sf[rank] = gf[i];
+    }
+    warp_sync();
+    double tmax = neg_inf();
+    for (int i = c.lane; i + 1 < n; i += LANES) {
+        double dx = sx[i + 1] - sx[i];
+        double t = (dx > 0.0) ? ln_add_exp(sf[i], sf[i + 1]) + log(dx) - LN_2 : neg_inf();
+        if (t != t) t = INFINITY; // poison through the max
+        tmax = fmax(tmax, t);
+    }
+    tmax = w_max_d(tmax);
+    if (tmax == neg_inf()) return neg_inf();
+    if (tmax == INFINITY) {
+        c.status |= VLR_ST_NAN;
+        return NAN;
+    }
+    double ssum = 0.0;
+    for (int i = c.lane; i + 1 < n; i += LANES) {
+        double dx = sx[i + 1] - sx[i];
+        if (dx > 0.0) {
+            double t = ln_add_exp(sf[i], sf[i + 1]) + log(dx) - LN_2;
+            if (t != neg_inf()) ssum += exp(t - tmax);
+        }
+    }
+    ssum = w_sum_d(ssum);
+    warp_sync();
+    return tmax + log(ssum);
+}
+
+VLR_DEV bool iupac_contains(int mask, int base) {
+    int bit = 0;
+    switch (base) {
+    case 'A': case 'a': bit = 1; break;
+    case 'C': case 'c': bit = 2; break;
+    case 'G': case 'g': bit = 4; break;
+    case 'T': case 't': bit = 8; break;
+    }
+    return (mask & bit) != 0;
+}
+
+// GenericPosterior::density (generic.rs:191-422)
+VLR_DEV_NOINLINE double density(Ctx& c, int ni, Ops& ops, int level) {
+    const DevScenario* sc = c.sc;
+    const vlr_node_t& node = sc->nodes[ni];
+    switch (node.kind) {
+    case VLR_NODE_LFC: ops.lfc_mask |= 1u << sc->lfc_ordinal[ni]; return subdensity(c, node, ops, level);
+    case VLR_NODE_FALSE: return neg_inf();
+    case VLR_NODE_TRUE: return 0.0;
+    case VLR_NODE_VARIANT: {
+        if (c.has_snv) {
+            bool contains = iupac_contains(node.refmask, c.refbase) && iupac_contains(node.altmask, c.altbase);
+            if ((node.variant_positive && !contains) || (!node.variant_positive && contains)) return neg_inf();
+            return subdensity(c, node, ops, level);
+        } else if (node.variant_positive) {
+            return neg_inf();
+        }
+        return subdensity(c, node, ops, level);
+    }
+    default: break;
+    }
+    const int sample = node.sample;
+    Range bounds;
+    bool have_bounds = ops_lfc_bounds(c, ops, sample, bounds);
+    if (have_bounds && range_is_empty(bounds)) return neg_inf();
+    const int n_obs = c.n_obs[sample];
+    const bool is_clear_ref = c.clear_ref[sample] != 0;
+    if (node.kind == VLR_NODE_SET) {
+        bool all_pos = true;
+        int n_in = 0;
+        double only = 0.0;
+        for (int i = 0; i < node.n_vafs; ++i) {
+            double v = sc->set_vafs[node.vaf_offset + i];
+            if (!(v > 0.0)) all_pos = false;
+            if (!have_bounds || range_contains(bounds, v)) {
+                n_in++;
+                only = v;
+            }
+        }
+        if (is_clear_ref && all_pos) return neg_inf();
+        if (n_in == 1) {
+            ops_push(ops, sample, only, true);
+            return subdensity(c, node, ops, level);
+        }
+        Lse acc;
+        acc.init();
+        for (int i = 0; i < node.n_vafs; ++i) {
+            double v = sc->set_vafs[node.vaf_offset + i];
+            if (have_bounds && !range_contains(bounds, v)) continue;
+            Ops cl = ops;
+            ops_push(cl, sample, v, true);
+            acc.add(subdensity(c, node, cl, level));
+        }
+        return acc.value();
+    }
+    Range vafs{node.start, node.end, node.left_exclusive != 0, node.right_exclusive != 0};
+    if (have_bounds) vafs = range_intersect(vafs, bounds);
+    if (range_is_empty(vafs)) return neg_inf();
+    if (is_clear_ref && vafs.start > 0.0) return neg_inf();
+    if (range_is_singleton(vafs)) {
+        ops_push(ops, sample, vafs.start, true);
+        return subdensity(c, node, ops, level);
+    }
+    const double res = sc->samples[sample].resolution;
+    const double min_vaf = range_observable_min(vafs, n_obs);
+    const double max_vaf = range_observable_max(vafs, n_obs);
+    if (!(min_vaf <= max_vaf)) c.status |= VLR_ST_NAN; // assert in the reference
+    if ((max_vaf - min_vaf) < res) return integrate_simpson(c, node, ops, min_vaf, max_vaf, 3, level);
+    if (n_obs < 5) return integrate_simpson(c, node, ops, min_vaf, max_vaf, 11, level);
+    if (level >= MAXS) {
+        c.status |= VLR_ST_GRID_OVERFLOW;
+        return neg_inf();
+    }
+    return integrate_adaptive(c, node, ops, min_vaf, max_vaf, res, level);
+}
+
+// ------------------------------------------------------------------------------------------------ locus driver
+// Caller::call_record + sample_infos (calling.rs:720-937) around rust-bio Model::compute.
+// vaftree.rs:116-164 (Node::contains); LFC constraints of the base event as a bit mask over LFC-node ordinals
+VLR_DEV_NOINLINE bool node_contains(const DevScenario* sc, int ni, const double* vaf, uint32_t& lfcs, int exclude) {
+    const vlr_node_t& node = sc->nodes[ni];
+    bool contained = true;
+    switch (node.kind) {
+    case VLR_NODE_SET:
+    case VLR_NODE_RANGE: {
+        if (exclude == node.sample) return true;
+        double v = vaf[node.sample];
+        if (node.kind == VLR_NODE_SET) {
+            contained = false;
+            for (int i = 0; i < node.n_vafs; ++i)
+                if (sc->set_vafs[node.vaf_offset + i] == v) contained = true;
+        } else {
+            Range r{node.start, node.end, node.left_exclusive != 0, node.right_exclusive != 0};
+            contained = range_contains(r, v);
+        }
+        break;
+    }
+    case VLR_NODE_LFC: {
+        bool found = false;
+        for (int k = 0; k < sc->n_lfc_nodes; ++k) {
+            if (!(lfcs & (1u << k))) continue;
+            const vlr_node_t& o = sc->nodes[sc->lfc_nodes[k]];
+            if (o.sample == node.sample && o.sample_b == node.sample_b && o.cmp == node.cmp &&
+                o.lfc_value == node.lfc_value) {
+                found = true;
+                lfcs &= ~(1u << k);
+            }
+        }
+        contained = found;
+        break;
+    }
+    case VLR_NODE_FALSE: contained = false; break;
+    default: contained = true;
+    }
+    if (node.n_children == 0) return contained && lfcs == 0;
+    if (!contained) return false;
+    for (int k = 0; k < node.n_children; ++k) {
+        if (node.n_children == 1) {
+            if (node_contains(sc, node.first_child + k, vaf, lfcs, exclude)) return true;
+        } else {
+            uint32_t cl = lfcs;
+            if (node_contains(sc, node.first_child + k, vaf, cl, exclude)) return true;
+        }
+    }
+    return false;
+}
+
+// Allele frequency distribution per sample (calling.rs:891-928) from the recorded artifact-free base events:
+// those compatible with the best event (ignoring the sample's own node) whose other samples equal the MAP.
+VLR_DEV_NOINLINE void afd_pass(Ctx& c, int best_scen, int map_slot, double marginal) {
+    const DevScenario* sc = c.sc;
+    const DevResults* res = c.res;
+    const int S = sc->S;
+    if (map_slot < 0 || c.map_cfg[map_slot] != 0) return; // artifact MAP: vaf_dist = None
+    const vlr_event_t& ev = sc->events[best_scen];
+    const int n_rec = (int)c.n_rec;
+    const int stride = 2 + S;
+    double* tx = c.ws->afd_x;
+    double* tp = c.ws->afd_p;
+    warp_sync();
+    for (int s = 0; s < S; ++s) {
+        int cnt = 0;
+        bool trunc = false;
+        for (int k0 = 0; k0 < n_rec; k0 += LANES) {
+            int k = k0 + c.lane;
+            bool ok = false;
+            double x = 0.0, p = 0.0;
+            if (k < n_rec) {
+                const double* e = c.be + (int64_t)k * stride;
+                uint32_t disc = (uint32_t)d_lo(e[1]), lfcs = (uint32_t)d_hi(e[1]);
+                ok = true;
+                for (int t = 0; t < S; ++t) {
+                    if (t == s) continue;
+                    bool d1 = (disc >> t) & 1u, d2 = (c.map_disc[map_slot] >> t) & 1u;
+                    if (!(e[2 + t] == c.map_vaf[map_slot][t] && d1 == d2)) ok = false;
+                }
+                if (ok) {
+                    bool contained = false;
+                    for (int r = 0; r < ev.n_roots && !contained; ++r) {
+                        uint32_t l = lfcs;
+                        contained = node_contains(sc, ev.first_root + r, e + 2, l, s);
+                    }
+                    ok = contained;
+                }
+                x = e[2 + s];
+                p = e[0] - marginal;
+            }
+#ifdef VLR_HOST_EMU
+            int pos = cnt, tot = ok ? 1 : 0;
+#else
+            unsigned m = __ballot_sync(FULL, ok);
+            int pos = cnt + __popc(m & ((1u << c.lane) - 1u)), tot = __popc(m);
+#endif
+            if (ok) {
+                if (pos < AFD_TMP) {
+                    tx[pos] = x;
+                    tp[pos] = p;
+                }
+            }
+            cnt += tot;
+        }
+        if (cnt > AFD_TMP) {
+            cnt = AFD_TMP;
+            trunc = true;
+        }
+        warp_sync();
+        // unique by vaf (a later, i.e. lower-posterior, duplicate overwrites in the reference), ascending
+        const int cap = res->afd_capacity;
+        int n_unique = 0;
+        for (int i0 = 0; i0 < cnt; i0 += LANES) {
+            int i = i0 + c.lane;
+            bool first = false;
+            int rank = 0;
+            double xi = 0.0, pi = 0.0;
+            if (i < cnt) {
+                xi = tx[i];
+                pi = tp[i];
+                first = true;
+                for (int j = 0; j < cnt; ++j) {
+                    double xj = tx[j];
+                    if (xj == xi) {
+                        if (j < i) first = false;
+                        double pj = tp[j];
+                        if (pj < pi) pi = pj;
+                    }
+                }
+                if (first) { // rank among first occurrences
+                    for (int j = 0; j < cnt; ++j) {
+                        double xj = tx[j];
+                        if (xj < xi) {
+                            bool jfirst = true;
+                            for (int q = 0; q < j; ++q)
+                                if (tx[q] == xj) {
+                                    jfirst = false;
+                                    break;
+                                }
+                            rank += jfirst;
+                        }
+                    }
+                }
+            }
+            if (first) {
+                if (rank < cap) {
+                    int64_t o = ((int64_t)c.locus * S + s) * cap + rank;
+                    res->afd_vaf[o] = xi;
+                    res->afd_logp[o] = pi;
+                } else {
+                    trunc = true;
+                }
+            }
+            n_unique += w_sum_i(first ? 1 : 0);
+        }
+        if (w_any(trunc)) c.status |= VLR_ST_AFD_TRUNCATED;
+        if (c.lane == 0) res->afd_count[(int64_t)c.locus * S + s] = n_unique < cap ? n_unique : cap;
+        warp_sync();
+    }
+}
+
+VLR_DEV void process_locus(const DevScenario* sc, const DevBatch* b, const DevResults* res, WarpWs* ws, double* coef,
+                           double* be, int coef_cap, int64_t locus, Ctx& c) {
+    const int S = sc->S, E = sc->E;
+    c.sc = sc;
+    c.b = b;
+    c.res = res;
+    c.ws = ws;
+    c.coef = coef;
+    c.be = res->afd_capacity > 0 ? be : nullptr;
+    c.n_rec = 0;
+    c.coef_cap = coef_cap;
+    c.locus = locus;
+    c.lane = lane_id();
+    c.status = 0;
+    c.lf = b->lflags[locus];
+    c.vartype = (c.lf >> VLR_LF_VARTYPE_SHIFT) & 3;
+    c.has_snv = (c.lf & VLR_LF_HAS_SNV) != 0;
+    c.refbase = (c.lf >> VLR_LF_REFBASE_SHIFT) & 0xff;
+    c.altbase = (c.lf >> VLR_LF_ALTBASE_SHIFT) & 0xff;
+    c.het_override = NAN;
+    c.semr_override = NAN;
+    const double phred_to_ln = -0.23025850929940456; // -ln(10)/10 (PHREDProb -> LogProb)
+    if (b->het_phred) {
+        float h = b->het_phred[locus];
+        if (!(h != h)) c.het_override = (double)h * phred_to_ln;
+    }
+    if (b->semr_phred) {
+        float h = b->semr_phred[locus];
+        if (!(h != h)) c.semr_override = (double)h * phred_to_ln;
+    }
+    c.prior_absent = NAN;
+    c.n_base = 0;
+    c.n_pileup_evals = 0;
+    for (int i = 0; i < 2 * E; ++i) c.map_set[i] = 0;
+
+    BiasPlan plan;
+    locus_prepass(c, plan);
+    if (c.coef_total > c.coef_cap) { // only reachable through vlr_call_batch_device without a sufficient reserve
+        if (c.lane == 0) {
+            for (int e = 0; e <= E; ++e) res->log_post[locus * (int64_t)(E + 1) + e] = NAN;
+            for (int s = 0; s < S; ++s) res->map_vaf[locus * S + s] = NAN;
+            if (res->log_marginal) res->log_marginal[locus] = NAN;
+            if (res->best_event) res->best_event[locus] = 0;
+            if (res->map_config) res->map_config[locus] = 0;
+            if (res->n_base_events) res->n_base_events[locus] = 0;
+            if (res->afd_capacity > 0)
+                for (int s = 0; s < S; ++s) res->afd_count[locus * S + s] = 0;
+            res->status[locus] = c.status | VLR_ST_WORKSPACE_OVERFLOW | VLR_ST_NO_MAP;
+        }
+        return;
+    }
+
+    // joint probability per universe event: plain events get ln 0.5, twins ln 0.5 + ln(1/#configs) (generic.rs:437-441)
+    Lse ev_plain[MAXE], ev_twin[MAXE];
+    for (int e = 0; e < E; ++e) {
+        ev_plain[e].init();
+        ev_twin[e].init();
+    }
+    const double twin_prior = plan.n_twins > 0 ? LN_05 + log(1.0 / (double)plan.n_twins) : neg_inf();
+    for (int ci = 0; ci <= plan.n_surviving; ++ci) {
+        c.art.id = ci == 0 ? 0 : plan.surviving[ci - 1];
+        c.art.forward_rate = plan.forward_rate;
+        c.art.has_alt_loci = plan.has_alt_loci;
+        for (int s = 0; s < S; ++s) {
+            c.lc_n[s] = 0;
+            read_coefficients(c, s);
+        }
+        for (int e = 0; e < E; ++e) {
+            const vlr_event_t& ev = sc->events[e];
+            if (ci > 0 && !ev.has_artifact_twin) continue;
+            c.cur_slot = 2 * e + (ci > 0 ? 1 : 0);
+            for (int r = 0; r < ev.n_roots; ++r) {
+                Ops ops;
+                for (int s = 0; s < MAXS; ++s) ops.vaf[s] = 0.0;
+                ops.set_mask = ops.disc_mask = ops.lfc_mask = 0;
+                double d = density(c, ev.first_root + r, ops, 0);
+                if (ci == 0) ev_plain[e].add(LN_05 + d);
+                else ev_twin[e].add(twin_prior + d);
+            }
+        }
+    }
+
+    // marginal over the event universe, in universe order [e plain, e twin]...
+    double joint_u[2 * MAXE];
+    int scen_u[2 * MAXE];
+    bool art_u[2 * MAXE];
+    int nu = 0;
+    Lse marg;
+    marg.init();
+    for (int e = 0; e < E; ++e) {
+        joint_u[nu] = ev_plain[e].value();
+        scen_u[nu] = e;
+        art_u[nu] = false;
+        marg.add(joint_u[nu]);
+        nu++;
+        if (sc->events[e].has_artifact_twin && plan.n_twins > 0) {
+            joint_u[nu] = ev_twin[e].value();
+            scen_u[nu] = e;
+            art_u[nu] = true;
+            marg.add(joint_u[nu]);
+            nu++;
+        }
+    }
+    const double marginal = marg.value();
+    if (marginal == neg_inf()) c.status |= VLR_ST_MARGINAL_ZERO;
+    if (marginal != marginal) c.status |= VLR_ST_NAN;
+
+    int best = 0;
+    {
+        double bestv = joint_u[0] - marginal;
+        for (int i = 1; i < nu; ++i) {
+            double v = joint_u[i] - marginal;
+            if (v >= bestv) { // itertools minmax_by_key: the last maximum wins (calling.rs:762-769)
+                bestv = v;
+                best = i;
+            }
+        }
+    }
+    Lse art;
+    art.init();
+    double* lp = res->log_post + locus * (int64_t)(E + 1);
+    double my_lp[MAXE + 1];
+    for (int i = 0; i < nu; ++i) {
+        double post = joint_u[i] - marginal;
+        if (art_u[i]) art.add(post);
+        else my_lp[scen_u[i]] = post;
+    }
+    const double prob_artifact = art.value();
+    my_lp[E] = prob_artifact;
+    bool is_artifact = true;
+    for (int e = 0; e < E; ++e)
+        if (!(my_lp[e] < prob_artifact)) is_artifact = false;
+    if (is_artifact) c.status |= VLR_ST_IS_ARTIFACT;
+
+    // MAP (calling.rs:844-890): events of a valid scenario are disjoint (grammar/mod.rs:238-272 rejects overlaps),
+    // so the base events contained in the best event are the ones its own tree produced.
+    const int best_scen = scen_u[best];
+    int map_slot = -1;
+    {
+        int sp = 2 * best_scen, st = 2 * best_scen + 1;
+        if (c.map_set[sp]) map_slot = sp;
+        if (is_artifact && c.map_set[st] && (map_slot < 0 || c.map_joint[st] > c.map_joint[sp])) map_slot = st;
+    }
+    if (map_slot < 0) c.status |= VLR_ST_NO_MAP;
+
+    if (c.lane == 0) {
+        for (int e = 0; e <= E; ++e) lp[e] = my_lp[e];
+        if (res->log_marginal) res->log_marginal[locus] = marginal;
+        if (res->best_event) res->best_event[locus] = 2 * best_scen + (art_u[best] ? 1 : 0);
+        if (res->n_base_events) res->n_base_events[locus] = c.n_base;
+        for (int s = 0; s < S; ++s) {
+            double v = NAN;
+            if (map_slot >= 0) v = c.map_cfg[map_slot] != 0 ? 0.0 : c.map_vaf[map_slot][s];
+            res->map_vaf[locus * S + s] = v;
+        }
+        if (res->map_config) res->map_config[locus] = map_slot >= 0 ? c.map_cfg[map_slot] : 0;
+        if (res->afd_capacity > 0)
+            for (int s = 0; s < S; ++s) res->afd_count[locus * S + s] = 0;
+    }
+    if (res->afd_capacity > 0) afd_pass(c, best_scen, map_slot, marginal);
+    if (c.lane == 0) res->status[locus] = c.status;
+}
+
+} // namespace vlrcore

@@ -1,0 +1,479 @@
+// vlr_engine.cu — sm_100a kernel and C-ABI (include/vlr_engine.h) of the per-locus posterior engine.
+//
+// Kernel: persistent grid (resident CTAs per SM x 148 SMs), one warp per locus, loci handed out through a global
+// atomic ticket so that the very uneven per-locus work (a few hundred to >100k per-read evaluations)
+// balances dynamically. All per-locus logic lives in engine_core.cuh.
+//
+// Host: vlr_call_batch() streams a host batch through NBUF slots (chunk of loci -> H2D -> kernel -> D2H, one CUDA
+// stream per slot) so copies overlap compute; vlr_call_batch_device() launches on device-resident buffers.
+// There is no CPU fallback: without a usable CUDA device vlr_ctx_create() fails with VLR_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "engine_core.cuh"
+#include "scenario_prep.h"
+
+using namespace vlrcore;
+
+namespace {
+
+constexpr int WARPS_PER_CTA = 8;
+constexpr int THREADS = WARPS_PER_CTA * 32;
+constexpr int NBUF = 3;
+
+struct KernelParams {
+    DevScenario sc;
+    DevBatch b;
+    DevResults r;
+    WarpWs* ws;
+    double* coef;
+    double* be;
+    unsigned long long* ticket;
+    int coef_cap;     // reads per warp
+    int64_t be_stride; // doubles per warp
+};
+
+__global__ void __launch_bounds__(THREADS) vlr_call_kernel(const __grid_constant__ KernelParams p) {
+    const int gw = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+    WarpWs* ws = p.ws + gw;
+    double* coef = p.coef + (int64_t)gw * p.coef_cap * 4;
+    double* be = p.be ? p.be + (int64_t)gw * p.be_stride : nullptr;
+    Ctx c;
+    for (;;) {
+        unsigned long long t = 0;
+        if ((threadIdx.x & 31) == 0) t = atomicAdd(p.ticket, 1ULL);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if ((int64_t)t >= p.b.n_loci) break;
+        process_locus(&p.sc, &p.b, &p.r, ws, coef, be, p.coef_cap, (int64_t)t, c);
+        __syncwarp();
+    }
+}
+
+#define CK(call)                                                                      \
+    do {                                                                              \
+        cudaError_t _e = (call);                                                      \
+        if (_e != cudaSuccess) return ctx->fail_cuda(_e, #call, __LINE__);            \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct Slot { // one in-flight chunk of vlr_call_batch
+    cudaStream_t stream = nullptr;
+    DevBuf offsets, cols[7], rflags, hart, hvar, lflags, het, semr;
+    DevBuf log_post, log_marginal, map_vaf, map_config, best_event, status, n_base, afd_count, afd_vaf, afd_logp;
+    DevBuf ws, coef, be, ticket;
+    int coef_cap = 0;
+    bool be_ready = false;
+};
+
+} // namespace
+
+struct vlr_ctx {
+    int device = 0;
+    int n_sms = 0;
+    int ctas_per_sm = 1;
+    int grid = 0;
+    int S = 0, E = 0;
+    ScenarioPrep prep;
+    DevScenario dsc;
+    DevBuf d_samples, d_events, d_nodes, d_set_vafs, d_spectra, d_lfc_nodes, d_lfc_ordinal;
+    cudaStream_t stream = nullptr; // the context's own stream (device-pointer entry)
+    Slot dev_slot;                 // workspace of the device-pointer entry
+    Slot slots[NBUF];
+    int64_t reserve_reads = 4096;
+    int64_t launches = 0;
+    std::string err;
+
+    vlr_status_t fail(vlr_status_t st, const std::string& msg) {
+        err = msg;
+        return st;
+    }
+    vlr_status_t fail_cuda(cudaError_t e, const char* what, int line) {
+        char buf[512];
+        snprintf(buf, sizeof buf, "CUDA error %d (%s) at vlr_engine.cu:%d: %s", (int)e, cudaGetErrorString(e), line, what);
+        err = buf;
+        return e == cudaErrorMemoryAllocation ? VLR_ERR_OUT_OF_MEMORY : VLR_ERR_CUDA;
+    }
+};
+
+namespace {
+
+vlr_status_t ensure_workspace(vlr_ctx* ctx, Slot& sl, int64_t max_reads, bool want_be) {
+    const int64_t n_warps = (int64_t)ctx->grid * WARPS_PER_CTA;
+    if (max_reads < 1) max_reads = 1;
+    if (max_reads > 0x7fffffff / 8) return ctx->fail(VLR_ERR_UNSUPPORTED, "locus with more than 2^28 reads");
+    CK(sl.ws.ensure(sizeof(WarpWs) * (size_t)n_warps));
+    if (max_reads > sl.coef_cap) {
+        int64_t cap = max_reads + max_reads / 8;
+        CK(sl.coef.ensure((size_t)n_warps * (size_t)cap * 4 * sizeof(double)));
+        sl.coef_cap = (int)cap;
+    }
+    if (want_be) CK(sl.be.ensure((size_t)n_warps * BE_CAP * (2 + ctx->S) * sizeof(double)));
+    CK(sl.ticket.ensure(sizeof(unsigned long long)));
+    return VLR_OK;
+}
+
+vlr_status_t launch(vlr_ctx* ctx, Slot& sl, const DevBatch& b, const DevResults& r, cudaStream_t stream) {
+    KernelParams p;
+    p.sc = ctx->dsc;
+    p.b = b;
+    p.r = r;
+    p.ws = (WarpWs*)sl.ws.p;
+    p.coef = (double*)sl.coef.p;
+    p.be = r.afd_capacity > 0 ? (double*)sl.be.p : nullptr;
+    p.ticket = (unsigned long long*)sl.ticket.p;
+    p.coef_cap = sl.coef_cap;
+    p.be_stride = (int64_t)BE_CAP * (2 + ctx->S);
+    CK(cudaMemsetAsync(sl.ticket.p, 0, sizeof(unsigned long long), stream));
+    if (b.n_loci > 0) {
+        vlr_call_kernel<<<ctx->grid, THREADS, 0, stream>>>(p);
+        CK(cudaGetLastError());
+        ctx->launches++;
+    }
+    return VLR_OK;
+}
+
+bool results_valid(const vlr_results_t* r) {
+    if (!r || !r->log_posteriors || !r->map_vaf || !r->status) return false;
+    if (r->afd_capacity < 0) return false;
+    if (r->afd_capacity > 0 && (!r->afd_count || !r->afd_vaf || !r->afd_logp)) return false;
+    return true;
+}
+bool batch_valid(const vlr_batch_t* b) {
+    if (!b || b->n_loci < 0 || b->n_reads < 0) return false;
+    if (b->n_loci == 0) return true;
+    if (!b->read_offsets || !b->locus_flags) return false;
+    if (b->n_reads > 0 && (!b->prob_mapping || !b->prob_ref || !b->prob_alt || !b->prob_missed_allele ||
+                           !b->prob_sample_alt || !b->prob_double_overlap || !b->prob_hit_base || !b->read_flags))
+        return false;
+    return true;
+}
+
+} // namespace
+
+extern "C" {
+
+int32_t vlr_abi_version(void) { return VLR_ABI_VERSION; }
+
+const char* vlr_status_string(vlr_status_t st) {
+    switch (st) {
+    case VLR_OK: return "ok";
+    case VLR_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case VLR_ERR_UNSUPPORTED: return "unsupported";
+    case VLR_ERR_CUDA: return "CUDA error";
+    case VLR_ERR_OUT_OF_MEMORY: return "out of device memory";
+    case VLR_ERR_NO_DEVICE: return "no CUDA device";
+    default: return "unknown status";
+    }
+}
+
+const char* vlr_last_error(const vlr_ctx_t* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+int64_t vlr_last_launch_count(const vlr_ctx_t* ctx) { return ctx ? ctx->launches : 0; }
+void* vlr_ctx_stream(const vlr_ctx_t* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+void* vlr_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void vlr_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+vlr_status_t vlr_ctx_create(const vlr_scenario_t* scenario, int32_t device, vlr_ctx_t** out) {
+    if (!out) return VLR_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (!scenario) return VLR_ERR_INVALID_ARGUMENT;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        return VLR_ERR_NO_DEVICE; // no CPU fallback by design
+    }
+    if (device < 0 || device >= n_dev) return VLR_ERR_INVALID_ARGUMENT;
+    vlr_ctx* ctx = new vlr_ctx;
+    auto bail = [&](vlr_status_t st) {
+        // keep the message retrievable: callers get no ctx on failure, so print it
+        fprintf(stderr, "vlr_ctx_create: %s\n", ctx->err.c_str());
+        vlr_ctx_destroy(ctx);
+        return st;
+    };
+    if (!ctx->prep.build(scenario)) {
+        ctx->err = ctx->prep.error;
+        return bail(VLR_ERR_INVALID_ARGUMENT);
+    }
+    ctx->device = device;
+    ctx->S = scenario->n_samples;
+    ctx->E = scenario->n_events;
+    cudaError_t e;
+#define CKB(call)                                            \
+    if ((e = (call)) != cudaSuccess) {                       \
+        ctx->fail_cuda(e, #call, __LINE__);                  \
+        return bail(e == cudaErrorMemoryAllocation ? VLR_ERR_OUT_OF_MEMORY : VLR_ERR_CUDA); \
+    }
+    CKB(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CKB(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        ctx->err = "device is not sm_100-class (this library is built for sm_100a only)";
+        return bail(VLR_ERR_UNSUPPORTED);
+    }
+    ctx->n_sms = prop.multiProcessorCount;
+    auto upload = [&](DevBuf& buf, const void* src, size_t bytes) -> cudaError_t {
+        cudaError_t e2 = buf.ensure(bytes ? bytes : 8);
+        if (e2 != cudaSuccess) return e2;
+        if (bytes) e2 = cudaMemcpy(buf.p, src, bytes, cudaMemcpyHostToDevice);
+        return e2;
+    };
+    CKB(upload(ctx->d_samples, scenario->samples, sizeof(vlr_sample_t) * scenario->n_samples));
+    CKB(upload(ctx->d_events, scenario->events, sizeof(vlr_event_t) * scenario->n_events));
+    CKB(upload(ctx->d_nodes, scenario->nodes, sizeof(vlr_node_t) * scenario->n_nodes));
+    CKB(upload(ctx->d_set_vafs, scenario->set_vafs, sizeof(double) * (size_t)std::max(0, scenario->n_set_vafs)));
+    CKB(upload(ctx->d_spectra, scenario->spectra, sizeof(vlr_spectrum_t) * (size_t)std::max(0, scenario->n_spectra)));
+    CKB(upload(ctx->d_lfc_nodes, ctx->prep.lfc_nodes.data(), sizeof(int) * ctx->prep.lfc_nodes.size()));
+    CKB(upload(ctx->d_lfc_ordinal, ctx->prep.lfc_ordinal.data(), sizeof(int) * ctx->prep.lfc_ordinal.size()));
+    ctx->dsc = ctx->prep.view((const vlr_sample_t*)ctx->d_samples.p, (const vlr_event_t*)ctx->d_events.p,
+                              (const vlr_node_t*)ctx->d_nodes.p, (const double*)ctx->d_set_vafs.p,
+                              (const vlr_spectrum_t*)ctx->d_spectra.p, (const int*)ctx->d_lfc_nodes.p,
+                              (const int*)ctx->d_lfc_ordinal.p);
+    // The tree walk recurses once per tree level (density -> subdensity -> density); frames hold an Ops copy and the
+    // integration state. Size the per-thread stack from the scenario's depth.
+    size_t stack = 10240 + (size_t)(ctx->prep.max_depth + 2) * 1024;
+    CKB(cudaDeviceSetLimit(cudaLimitStackSize, stack));
+    int per_sm = 0;
+    CKB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vlr_call_kernel, THREADS, 0));
+    if (per_sm < 1) per_sm = 1;
+    ctx->ctas_per_sm = per_sm;
+    ctx->grid = per_sm * ctx->n_sms;
+    CKB(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < NBUF; ++i) CKB(cudaStreamCreateWithFlags(&ctx->slots[i].stream, cudaStreamNonBlocking));
+#undef CKB
+    *out = ctx;
+    return VLR_OK;
+}
+
+void vlr_ctx_destroy(vlr_ctx_t* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    auto free_slot = [](Slot& s) {
+        if (s.stream) {
+            cudaStreamSynchronize(s.stream);
+            cudaStreamDestroy(s.stream);
+        }
+        s.offsets.release();
+        for (auto& c : s.cols) c.release();
+        DevBuf* all[] = {&s.rflags, &s.hart, &s.hvar, &s.lflags, &s.het, &s.semr, &s.log_post, &s.log_marginal,
+                         &s.map_vaf, &s.map_config, &s.best_event, &s.status, &s.n_base, &s.afd_count, &s.afd_vaf,
+                         &s.afd_logp, &s.ws, &s.coef, &s.be, &s.ticket};
+        for (DevBuf* b : all) b->release();
+    };
+    if (ctx->stream) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamDestroy(ctx->stream);
+    }
+    free_slot(ctx->dev_slot);
+    for (auto& s : ctx->slots) free_slot(s);
+    DevBuf* sc[] = {&ctx->d_samples, &ctx->d_events, &ctx->d_nodes, &ctx->d_set_vafs, &ctx->d_spectra,
+                    &ctx->d_lfc_nodes, &ctx->d_lfc_ordinal};
+    for (DevBuf* b : sc) b->release();
+    delete ctx;
+}
+
+vlr_status_t vlr_ctx_reserve(vlr_ctx_t* ctx, int64_t max_reads_per_locus) {
+    if (!ctx || max_reads_per_locus < 1) return VLR_ERR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(ctx->device));
+    if (max_reads_per_locus > ctx->reserve_reads) ctx->reserve_reads = max_reads_per_locus;
+    return ensure_workspace(ctx, ctx->dev_slot, ctx->reserve_reads, false);
+}
+
+vlr_status_t vlr_call_batch_device(vlr_ctx_t* ctx, const vlr_batch_t* batch, vlr_results_t* results, void* cuda_stream) {
+    if (!ctx) return VLR_ERR_INVALID_ARGUMENT;
+    if (!batch_valid(batch) || !results_valid(results)) return ctx->fail(VLR_ERR_INVALID_ARGUMENT, "invalid batch or results");
+    CK(cudaSetDevice(ctx->device));
+    ctx->launches = 0;
+    cudaStream_t stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    vlr_status_t st = ensure_workspace(ctx, ctx->dev_slot, ctx->reserve_reads, results->afd_capacity > 0);
+    if (st != VLR_OK) return st;
+    DevBatch b;
+    b.n_loci = batch->n_loci;
+    b.read_base = 0;
+    b.read_offsets = batch->read_offsets;
+    b.pm = batch->prob_mapping;
+    b.pr = batch->prob_ref;
+    b.pa = batch->prob_alt;
+    b.pmiss = batch->prob_missed_allele;
+    b.psa = batch->prob_sample_alt;
+    b.pdo = batch->prob_double_overlap;
+    b.phb = batch->prob_hit_base;
+    b.rflags = batch->read_flags;
+    b.hart = batch->prob_homopolymer_artifact;
+    b.hvar = batch->prob_homopolymer_variant;
+    b.lflags = batch->locus_flags;
+    b.het_phred = batch->locus_heterozygosity_phred;
+    b.semr_phred = batch->locus_semr_phred;
+    DevResults r;
+    r.log_post = results->log_posteriors;
+    r.log_marginal = results->log_marginal;
+    r.map_vaf = results->map_vaf;
+    r.map_config = results->map_config;
+    r.best_event = results->best_event;
+    r.status = results->status;
+    r.n_base_events = results->n_base_events;
+    r.afd_capacity = results->afd_capacity;
+    r.afd_count = results->afd_count;
+    r.afd_vaf = results->afd_vaf;
+    r.afd_logp = results->afd_logp;
+    return launch(ctx, ctx->dev_slot, b, r, stream);
+}
+
+vlr_status_t vlr_call_batch(vlr_ctx_t* ctx, const vlr_batch_t* batch, vlr_results_t* results) {
+    if (!ctx) return VLR_ERR_INVALID_ARGUMENT;
+    if (!batch_valid(batch) || !results_valid(results)) return ctx->fail(VLR_ERR_INVALID_ARGUMENT, "invalid batch or results");
+    CK(cudaSetDevice(ctx->device));
+    ctx->launches = 0;
+    const int S = ctx->S, E = ctx->E;
+    const int64_t L = batch->n_loci;
+    if (L == 0) return VLR_OK;
+    const int64_t* off = batch->read_offsets;
+    if (off[L * S] != batch->n_reads) return ctx->fail(VLR_ERR_INVALID_ARGUMENT, "read_offsets[n_loci*S] != n_reads");
+    // chunking: ~2M reads per chunk keeps copies >= tens of MB (PCIe-efficient) while 3 slots stay far below HBM size
+    const int64_t target_reads = 2 << 20;
+    const int64_t max_loci_chunk = 1 << 17;
+    const int cap = results->afd_capacity;
+    const float* cols[7] = {batch->prob_mapping, batch->prob_ref,         batch->prob_alt,     batch->prob_missed_allele,
+                            batch->prob_sample_alt, batch->prob_double_overlap, batch->prob_hit_base};
+    int64_t lo = 0;
+    int k = 0;
+    vlr_status_t st = VLR_OK;
+    while (lo < L) {
+        int64_t hi = lo, max_reads = 0;
+        const int64_t r0 = off[lo * S];
+        while (hi < L && hi - lo < max_loci_chunk) {
+            int64_t n = off[(hi + 1) * S] - off[hi * S];
+            if (n < 0) return ctx->fail(VLR_ERR_INVALID_ARGUMENT, "read_offsets must be non-decreasing");
+            if (hi > lo && off[(hi + 1) * S] - r0 > target_reads) break;
+            if (n > max_reads) max_reads = n;
+            ++hi;
+        }
+        const int64_t r1 = off[hi * S], nl = hi - lo, nr = r1 - r0;
+        Slot& sl = ctx->slots[k % NBUF];
+        cudaStream_t s = sl.stream;
+        // the slot's previous chunk (k - NBUF) must have drained before its buffers are reused
+        CK(cudaStreamSynchronize(s));
+        st = ensure_workspace(ctx, sl, max_reads, cap > 0);
+        if (st != VLR_OK) break;
+        CK(sl.offsets.ensure(sizeof(int64_t) * (size_t)(nl * S + 1)));
+        CK(cudaMemcpyAsync(sl.offsets.p, off + lo * S, sizeof(int64_t) * (size_t)(nl * S + 1), cudaMemcpyHostToDevice, s));
+        for (int c = 0; c < 7; ++c) {
+            CK(sl.cols[c].ensure(sizeof(float) * (size_t)std::max<int64_t>(nr, 1)));
+            if (nr) CK(cudaMemcpyAsync(sl.cols[c].p, cols[c] + r0, sizeof(float) * (size_t)nr, cudaMemcpyHostToDevice, s));
+        }
+        CK(sl.rflags.ensure(sizeof(uint32_t) * (size_t)std::max<int64_t>(nr, 1)));
+        if (nr) CK(cudaMemcpyAsync(sl.rflags.p, batch->read_flags + r0, sizeof(uint32_t) * (size_t)nr, cudaMemcpyHostToDevice, s));
+        auto opt_up = [&](DevBuf& buf, const float* src, int64_t first, int64_t n) -> cudaError_t {
+            if (!src) return cudaSuccess;
+            cudaError_t e = buf.ensure(sizeof(float) * (size_t)std::max<int64_t>(n, 1));
+            if (e != cudaSuccess || n == 0) return e;
+            return cudaMemcpyAsync(buf.p, src + first, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, s);
+        };
+        CK(opt_up(sl.hart, batch->prob_homopolymer_artifact, r0, nr));
+        CK(opt_up(sl.hvar, batch->prob_homopolymer_variant, r0, nr));
+        CK(opt_up(sl.het, batch->locus_heterozygosity_phred, lo, nl));
+        CK(opt_up(sl.semr, batch->locus_semr_phred, lo, nl));
+        CK(sl.lflags.ensure(sizeof(uint32_t) * (size_t)nl));
+        CK(cudaMemcpyAsync(sl.lflags.p, batch->locus_flags + lo, sizeof(uint32_t) * (size_t)nl, cudaMemcpyHostToDevice, s));
+        // results
+        CK(sl.log_post.ensure(sizeof(double) * (size_t)(nl * (E + 1))));
+        CK(sl.log_marginal.ensure(sizeof(double) * (size_t)nl));
+        CK(sl.map_vaf.ensure(sizeof(double) * (size_t)(nl * S)));
+        CK(sl.map_config.ensure(sizeof(int32_t) * (size_t)nl));
+        CK(sl.best_event.ensure(sizeof(int32_t) * (size_t)nl));
+        CK(sl.status.ensure(sizeof(uint32_t) * (size_t)nl));
+        CK(sl.n_base.ensure(sizeof(uint32_t) * (size_t)nl));
+        if (cap > 0) {
+            CK(sl.afd_count.ensure(sizeof(int32_t) * (size_t)(nl * S)));
+            CK(sl.afd_vaf.ensure(sizeof(double) * (size_t)(nl * S * cap)));
+            CK(sl.afd_logp.ensure(sizeof(double) * (size_t)(nl * S * cap)));
+        }
+        DevBatch b;
+        b.n_loci = nl;
+        b.read_base = r0; // offsets stay absolute; columns hold rows [r0, r1)
+        b.read_offsets = (const int64_t*)sl.offsets.p;
+        b.pm = (const float*)sl.cols[0].p;
+        b.pr = (const float*)sl.cols[1].p;
+        b.pa = (const float*)sl.cols[2].p;
+        b.pmiss = (const float*)sl.cols[3].p;
+        b.psa = (const float*)sl.cols[4].p;
+        b.pdo = (const float*)sl.cols[5].p;
+        b.phb = (const float*)sl.cols[6].p;
+        b.rflags = (const uint32_t*)sl.rflags.p;
+        b.hart = batch->prob_homopolymer_artifact ? (const float*)sl.hart.p : nullptr;
+        b.hvar = batch->prob_homopolymer_variant ? (const float*)sl.hvar.p : nullptr;
+        b.lflags = (const uint32_t*)sl.lflags.p;
+        b.het_phred = batch->locus_heterozygosity_phred ? (const float*)sl.het.p : nullptr;
+        b.semr_phred = batch->locus_semr_phred ? (const float*)sl.semr.p : nullptr;
+        DevResults r;
+        r.log_post = (double*)sl.log_post.p;
+        r.log_marginal = (double*)sl.log_marginal.p;
+        r.map_vaf = (double*)sl.map_vaf.p;
+        r.map_config = (int32_t*)sl.map_config.p;
+        r.best_event = (int32_t*)sl.best_event.p;
+        r.status = (uint32_t*)sl.status.p;
+        r.n_base_events = (uint32_t*)sl.n_base.p;
+        r.afd_capacity = cap;
+        r.afd_count = (int32_t*)sl.afd_count.p;
+        r.afd_vaf = (double*)sl.afd_vaf.p;
+        r.afd_logp = (double*)sl.afd_logp.p;
+        int64_t saved = ctx->launches;
+        st = launch(ctx, sl, b, r, s);
+        if (st != VLR_OK) break;
+        ctx->launches = saved + 1;
+        // D2H
+        CK(cudaMemcpyAsync(results->log_posteriors + lo * (E + 1), r.log_post, sizeof(double) * (size_t)(nl * (E + 1)), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(results->map_vaf + lo * S, r.map_vaf, sizeof(double) * (size_t)(nl * S), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(results->status + lo, r.status, sizeof(uint32_t) * (size_t)nl, cudaMemcpyDeviceToHost, s));
+        if (results->log_marginal) CK(cudaMemcpyAsync(results->log_marginal + lo, r.log_marginal, sizeof(double) * (size_t)nl, cudaMemcpyDeviceToHost, s));
+        if (results->map_config) CK(cudaMemcpyAsync(results->map_config + lo, r.map_config, sizeof(int32_t) * (size_t)nl, cudaMemcpyDeviceToHost, s));
+        if (results->best_event) CK(cudaMemcpyAsync(results->best_event + lo, r.best_event, sizeof(int32_t) * (size_t)nl, cudaMemcpyDeviceToHost, s));
+        if (results->n_base_events) CK(cudaMemcpyAsync(results->n_base_events + lo, r.n_base_events, sizeof(uint32_t) * (size_t)nl, cudaMemcpyDeviceToHost, s));
+        if (cap > 0) {
+            CK(cudaMemcpyAsync(results->afd_count + lo * S, r.afd_count, sizeof(int32_t) * (size_t)(nl * S), cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(results->afd_vaf + lo * S * cap, r.afd_vaf, sizeof(double) * (size_t)(nl * S * cap), cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(results->afd_logp + lo * S * cap, r.afd_logp, sizeof(double) * (size_t)(nl * S * cap), cudaMemcpyDeviceToHost, s));
+        }
+        lo = hi;
+        ++k;
+    }
+    for (int i = 0; i < NBUF; ++i) {
+        cudaError_t e = cudaStreamSynchronize(ctx->slots[i].stream);
+        if (e != cudaSuccess && st == VLR_OK) st = ctx->fail_cuda(e, "cudaStreamSynchronize", __LINE__);
+    }
+    return st;
+}
+
+} // extern "C"
