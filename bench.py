@@ -200,7 +200,8 @@ def main():
     if world > 1:
         rec = torch.empty((batch.n_loci, E + 1 + S + 1), dtype=torch.float64, device=device)
         gather_buf = [torch.empty_like(rec) for _ in range(world)] if rank == 0 else None
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=device)  # a real (non-default) stream: handle 0 would mean "the engine's own"
+    torch.cuda.set_stream(stream)
 
     def step_device():
         eng.call_batch_device(dbatch, dres, stream.cuda_stream)

@@ -11,6 +11,7 @@ _LIB = os.path.join(_HERE, "libvlr_engine_emu.so")
 _SRC = [os.path.join(_HERE, "emu_driver.cpp"),
         os.path.join(_HERE, "..", "..", "varlociraptor_b200", "csrc", "engine_core.cuh"),
         os.path.join(_HERE, "..", "..", "varlociraptor_b200", "csrc", "scenario_prep.h"),
+        os.path.join(_HERE, "..", "..", "varlociraptor_b200", "csrc", "engine_types.cuh"),
         os.path.join(_HERE, "..", "..", "include", "vlr_engine.h")]
 _lib = None
 

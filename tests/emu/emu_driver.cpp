@@ -7,11 +7,16 @@
 #include <cstring>
 #include <vector>
 
+#define VLR_VARIANT vlr_full
+#define VLR_VAR_MAXS VLR_MAX_SAMPLES
+#define VLR_VAR_MAXE VLR_MAX_EVENTS
+#define VLR_VAR_MAXD VLR_MAX_TREE_DEPTH
 #include "../../varlociraptor_b200/csrc/engine_core.cuh"
 #include "../../varlociraptor_b200/csrc/scenario_prep.h"
 
 extern "C" int32_t vlr_emu_call_batch(const vlr_scenario_t* sc, const vlr_batch_t* batch, vlr_results_t* results) {
     using namespace vlrcore;
+    using namespace vlr_full;
     ScenarioPrep prep;
     if (!prep.build(sc)) return VLR_ERR_INVALID_ARGUMENT;
     DevScenario ds = prep.view(sc->samples, sc->events, sc->nodes, sc->set_vafs, sc->spectra, prep.lfc_nodes.data(),
@@ -55,7 +60,7 @@ extern "C" int32_t vlr_emu_call_batch(const vlr_scenario_t* sc, const vlr_batch_
     std::vector<double> be((size_t)BE_CAP * (2 + S));
     WarpWs* ws = new WarpWs;
     Ctx* c = new Ctx;
-    for (int64_t i = 0; i < batch->n_loci; ++i) process_locus(&ds, &db, &dr, ws, coef.data(), be.data(), (int)max_reads, i, *c);
+    for (int64_t i = 0; i < batch->n_loci; ++i) process_locus(&ds, &db, &dr, ws, coef.data(), nullptr, 0, be.data(), (int)max_reads, i, *c);
     delete c;
     delete ws;
     return VLR_OK;

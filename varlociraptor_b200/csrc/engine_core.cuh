@@ -21,297 +21,17 @@
 //
 // The file compiles for sm_100a (nvcc) and, with -DVLR_HOST_EMU, as a single-lane host build that exists only so
 // the control flow can be unit-tested without a GPU (tests/emu); the product library never contains that build.
-#pragma once
+//
+// This header is a TEMPLATE BY INCLUSION: define VLR_VARIANT (namespace), VLR_VAR_MAXS, VLR_VAR_MAXE, VLR_VAR_MAXD
+// (capacity in samples, events, tree depth) and include it; vlr_engine.cu does so twice (a small variant whose
+// per-warp state fits a few hundred bytes of shared memory, and the full-capacity one).
+#include "engine_types.cuh"
 
-#include <math.h>
-#include <stdint.h>
-#include <string.h>
-
-#include "../../include/vlr_engine.h"
-
-#ifdef VLR_HOST_EMU
-#define VLR_DEV inline
-#define VLR_DEV_NOINLINE
-#else
-#define VLR_DEV __device__ __forceinline__
-#define VLR_DEV_NOINLINE __device__ __noinline__
-#endif
-
-namespace vlrcore {
-
-constexpr int MAXS = VLR_MAX_SAMPLES;
-constexpr int MAXE = VLR_MAX_EVENTS;
-constexpr int NCFG = VLR_N_ARTIFACT_CONFIGS;
-constexpr int GRID_CAP = 128;   // points per adaptive integration (res >= ~1e-5)
-constexpr int LC_WAYS = 4;      // per-sample pileup-likelihood cache entries
-constexpr int MAX_LFC_NODES = 32;
-constexpr int AFD_TMP = 512;
-
-constexpr double NUMERICAL_EPSILON = 1e-3;        // utils/mod.rs:41
-constexpr double LN_05 = -0.6931471805599453;     // ln 0.5 (utils/mod.rs:45-47)
-constexpr double LN_2 = 0.6931471805599453;
-constexpr double LN_095 = -0.05129329438755058;   // ln 0.95 (utils/mod.rs:49-51)
-constexpr double LN_3 = 1.0986122886681098;       // Kass-Raftery thresholds 3, 20, 150 in log space
-constexpr double LN_20 = 2.995732273553991;
-constexpr double LN_150 = 5.0106352940962555;
-
-// ------------------------------------------------------------------------------------------------ warp layer
-#ifdef VLR_HOST_EMU
-constexpr int LANES = 1;
-VLR_DEV int lane_id() { return 0; }
-VLR_DEV void warp_sync() {}
-VLR_DEV int w_sum_i(int v) { return v; }
-VLR_DEV unsigned w_or_u(unsigned v) { return v; }
-VLR_DEV int w_max_i(int v) { return v; }
-VLR_DEV double w_sum_d(double v) { return v; }
-VLR_DEV double w_mul_d(double v) { return v; }
-VLR_DEV double w_max_d(double v) { return v; }
-VLR_DEV bool w_any(bool p) { return p; }
-VLR_DEV double w_bcast_d(double v, int) { return v; }
-VLR_DEV int d_hi(double x) {
-    uint64_t u;
-    memcpy(&u, &x, 8);
-    return (int)(u >> 32);
-}
-VLR_DEV int d_lo(double x) {
-    uint64_t u;
-    memcpy(&u, &x, 8);
-    return (int)(u & 0xffffffffu);
-}
-VLR_DEV double d_make(int hi, int lo) {
-    uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo;
-    double x;
-    memcpy(&x, &u, 8);
-    return x;
-}
-#else
-constexpr int LANES = 32;
-constexpr unsigned FULL = 0xffffffffu;
-VLR_DEV int lane_id() { return (int)(threadIdx.x & 31); }
-VLR_DEV void warp_sync() { __syncwarp(); }
-VLR_DEV int w_sum_i(int v) { return __reduce_add_sync(FULL, v); }
-VLR_DEV unsigned w_or_u(unsigned v) { return __reduce_or_sync(FULL, v); }
-VLR_DEV int w_max_i(int v) { return __reduce_max_sync(FULL, v); }
-// xor butterflies: a+b == b+a bitwise, so every lane ends with the identical value (needed for uniform control flow)
-VLR_DEV double w_sum_d(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-    return v;
-}
-VLR_DEV double w_mul_d(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v *= __shfl_xor_sync(FULL, v, o);
-    return v;
-}
-VLR_DEV double w_max_d(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
-    return v;
-}
-VLR_DEV bool w_any(bool p) { return __any_sync(FULL, p) != 0; }
-VLR_DEV double w_bcast_d(double v, int src) { return __shfl_sync(FULL, v, src); }
-VLR_DEV int d_hi(double x) { return __double2hiint(x); }
-VLR_DEV int d_lo(double x) { return __double2loint(x); }
-VLR_DEV double d_make(int hi, int lo) { return __hiloint2double(hi, lo); }
-#endif
-
-VLR_DEV double neg_inf() { return -INFINITY; }
-
-// ------------------------------------------------------------------------------------------------ device views
-struct DevScenario {
-    int S, E, n_nodes, n_set_vafs, n_spectra, full_prior, all_uniform, n_lfc_nodes;
-    const vlr_sample_t* samples;
-    const vlr_event_t* events;
-    const vlr_node_t* nodes;
-    const double* set_vafs;
-    const vlr_spectrum_t* spectra;
-    const int* lfc_nodes; // ordinal -> node index (LFC nodes only)
-    const int* lfc_ordinal; // node index -> ordinal (or -1)
-    double heterozygosity; // linear, NaN = none
-    double vtf[4];         // variant type fraction by VLR_LF_VARTYPE class
-};
-
-struct DevBatch {
-    int64_t n_loci;
-    int64_t read_base; // first row held by the column pointers (chunked transfers)
-    const int64_t* read_offsets;
-    const float *pm, *pr, *pa, *pmiss, *psa, *pdo, *phb;
-    const uint32_t* rflags;
-    const float *hart, *hvar;
-    const uint32_t* lflags;
-    const float *het_phred, *semr_phred;
-};
-
-struct DevResults {
-    double* log_post;
-    double* log_marginal;
-    double* map_vaf;
-    int32_t* map_config;
-    int32_t* best_event;
-    uint32_t* status;
-    uint32_t* n_base_events;
-    int32_t afd_capacity;
-    int32_t* afd_count;
-    double* afd_vaf;
-    double* afd_logp;
-};
-
-// Per-warp scratch in global memory (private to the warp, so it lives in L1/L2).
-constexpr int BE_CAP = 4096; // recorded base events per locus (only when an AFD is requested)
-
-struct WarpWs {
-    double grid_x[MAXS][GRID_CAP];
-    double grid_f[MAXS][GRID_CAP];
-    double sort_x[GRID_CAP];
-    double sort_f[GRID_CAP];
-    double afd_x[AFD_TMP];
-    double afd_p[AFD_TMP];
-};
-
-// ------------------------------------------------------------------------------------------------ LogProb helpers
-// (rust-bio LogProb semantics)
-VLR_DEV_NOINLINE double ln_add_exp(double a, double b) {
-    double p0, p1;
-    if (b > a) {
-        p0 = b;
-        p1 = a;
-    } else {
-        p0 = a;
-        p1 = b;
-    }
-    if (p0 == neg_inf()) return neg_inf();
-    if (p1 == neg_inf()) return p0;
-    return p0 + log1p(exp(p1 - p0));
-}
-VLR_DEV_NOINLINE double ln_one_minus_exp(double p) {
-    if (p < -0.693) return log1p(-exp(p));
-    return log(-expm1(p));
-}
-// streaming ln_sum_exp accumulator (differs from the reference's max-first two-pass form by rounding only)
-struct Lse {
-    double m, s; // max so far, sum of exp(x - m)
-    int n;
-    VLR_DEV void init() {
-        m = neg_inf();
-        s = 0.0;
-        n = 0;
-    }
-    VLR_DEV_NOINLINE void add(double x) {
-        n++;
-        if (x == neg_inf()) return;
-        if (x != x) { // NaN poisons like the reference's arithmetic would
-            m = x;
-            return;
-        }
-        if (x > m) {
-            s = (m == neg_inf()) ? 1.0 : s * exp(m - x) + 1.0;
-            m = x;
-        } else {
-            s += exp(x - m);
-        }
-    }
-    VLR_DEV double value() const {
-        if (m == neg_inf() || m != m || m == INFINITY) return m;
-        return m + log1p(s - 1.0);
-    }
-};
-
-VLR_DEV int kass_raftery(double m1, double m2) {
-    // BayesFactor::new(m1, m2) = exp(m1 - m2) compared with 1, 3, 20, 150; evaluated in log space.
-    double d = m1 - m2;
-    if (d <= 0.0) return 0;
-    if (d <= LN_3) return 1;
-    if (d <= LN_20) return 2;
-    if (d <= LN_150) return 3;
-    return 4; // incl. NaN, like the chain of failed comparisons in the reference
-}
-
-VLR_DEV bool relative_eq(double a, double b) { // approx 0.5 defaults (epsilon = max_relative = f64::EPSILON)
-    if (a == b) return true;
-    if (isinf(a) || isinf(b)) return false;
-    double diff = fabs(a - b);
-    const double eps = 2.220446049250313e-16;
-    if (diff <= eps) return true;
-    double largest = fmax(fabs(a), fabs(b));
-    return diff <= largest * eps;
-}
-
-// ------------------------------------------------------------------------------------------------ VAFRange
-struct Range {
-    double start, end;
-    bool lex, rex;
-};
-VLR_DEV Range range_empty() { return Range{0.0, 0.0, true, true}; }
-VLR_DEV bool range_is_empty(const Range& r) { return r.start == r.end && (r.lex || r.rex); }
-VLR_DEV bool range_is_singleton(const Range& r) { return r.start == r.end && !(r.lex || r.rex); }
-VLR_DEV bool range_contains(const Range& r, double v) {
-    bool l = r.lex ? (r.start < v) : (r.start <= v);
-    bool rr = r.rex ? (r.end > v) : (r.end >= v);
-    return l && rr;
-}
-VLR_DEV bool range_no_overlap(const Range& a, const Range& o) { // formula.rs:1137-1170
-    if (a.start == o.start && a.end == o.end && a.lex == o.lex && a.rex == o.rex) return false;
-    return (a.end < o.start || a.start > o.end) || (a.end <= o.start && (a.rex || o.lex)) ||
-           (a.start >= o.end && (a.lex || o.rex));
-}
-VLR_DEV Range range_intersect(const Range& a, const Range& o) {
-    if (range_no_overlap(a, o)) return range_empty();
-    Range r;
-    r.start = fmax(a.start, o.start);
-    r.end = fmin(a.end, o.end);
-    r.lex = a.start > o.start ? a.lex : (a.start < o.start ? o.lex : (a.lex || o.lex));
-    r.rex = a.end < o.end ? a.rex : (a.end > o.end ? o.rex : (a.rex || o.rex));
-    return r;
-}
-VLR_DEV double range_observable_max(const Range& r, int n) { // formula.rs:1202-1224
-    if (n < 10 || !((double)n * (r.end - r.start) > 1.0)) return r.end;
-    double c = (double)n * r.end;
-    if (r.rex && fmod(c, 1.0) == 0.0) c -= 1.0;
-    c = floor(c);
-    if (c == 0.0) return r.end;
-    return c / (double)n;
-}
-VLR_DEV double range_observable_min(const Range& r, int n) { // formula.rs:1172-1200
-    double min_vaf;
-    if (n < 10 || !((double)n * (r.end - r.start) > 1.0)) {
-        min_vaf = r.start;
-    } else {
-        double c = (double)n * r.start;
-        if (r.lex && fmod(c, 1.0) == 0.0) {
-            double adjusted_end = range_observable_max(r, n);
-            double s1 = ceil(c + 1.0) / (double)n;
-            if (s1 <= 1.0 && s1 <= adjusted_end) return s1;
-            double s0 = ceil(c) / (double)n;
-            if (s0 <= 1.0 && s0 <= adjusted_end) return s0;
-        }
-        min_vaf = ceil(c) / (double)n;
-    }
-    if (min_vaf >= range_observable_max(r, n)) return r.start;
-    return min_vaf;
-}
-
-// log2 fold change predicates (utils/log2_fold_change.rs)
-VLR_DEV int lfc_invert_cmp(int cmp) {
-    switch (cmp) {
-    case VLR_CMP_GT: return VLR_CMP_LE;
-    case VLR_CMP_GE: return VLR_CMP_LT;
-    case VLR_CMP_LT: return VLR_CMP_GE;
-    case VLR_CMP_LE: return VLR_CMP_GT;
-    default: return cmp;
-    }
-}
-VLR_DEV Range lfc_infer_bounds(int cmp, double value, double vaf) {
-    double proj = vaf / exp2(value);
-    if (proj < 0.0 || proj > 1.0) return range_empty();
-    switch (cmp) {
-    case VLR_CMP_EQ: return Range{proj, proj, false, false};
-    case VLR_CMP_GT: return Range{0.0, proj, false, true};
-    case VLR_CMP_GE: return Range{0.0, proj, false, false};
-    case VLR_CMP_LT: return Range{proj, 1.0, true, false};
-    case VLR_CMP_LE: return Range{proj, 1.0, false, false};
-    default: return Range{0.0, 1.0, false, false};
-    }
-}
+namespace VLR_VARIANT {
+using namespace vlrcore;
+constexpr int MAXS = VLR_VAR_MAXS;
+constexpr int MAXE = VLR_VAR_MAXE;
+constexpr int MAXD = VLR_VAR_MAXD;
 
 // ------------------------------------------------------------------------------------------------ per-locus state
 struct Ops { // generic.rs LikelihoodOperands
@@ -327,6 +47,8 @@ struct Art { // bias::Artifacts restricted to "none" or exactly one artifact (bi
     bool has_alt_loci;
 };
 
+// One instance per warp, in SHARED memory: every lane sees the same (uniform) state, so a single copy replaces
+// 32 per-lane local-memory copies. Writes are either "all lanes store the identical value" or lane-0 + warp_sync().
 struct Ctx {
     const DevScenario* sc;
     const DevBatch* b;
@@ -338,7 +60,6 @@ struct Ctx {
     int coef_cap;   // capacity of `coef` in reads
     int coef_total; // kept reads of this locus over all samples
     int64_t locus;
-    int lane;
     uint32_t lf;
     uint32_t status;
     int vartype;
@@ -363,8 +84,15 @@ struct Ctx {
     double map_vaf[2 * MAXE][MAXS];
     uint32_t map_disc[2 * MAXE];
     int map_cfg[2 * MAXE];
-    uint32_t map_has; // not enough bits for 48 slots -> use the arrays below
     uint8_t map_set[2 * MAXE];
+    // operand stack of the tree walk (generic.rs clones LikelihoodOperands per branch / grid point)
+    Ops ops[MAXD + 2];
+    // per-event accumulators and end-of-locus scratch
+    Lse ev_plain[MAXE], ev_twin[MAXE];
+    double joint_u[2 * MAXE];
+    double my_lp[MAXE + 1];
+    int scen_u[2 * MAXE];
+    uint8_t art_u[2 * MAXE];
     double prior_absent; // Prior of the all-zero event (absent-only mode), NaN = not computed yet
     uint32_t n_base;
     uint32_t n_pileup_evals;
@@ -446,7 +174,7 @@ VLR_DEV_NOINLINE void locus_prepass(Ctx& c, BiasPlan& plan) {
         int e1 = 0, e2 = 0, e3 = 0, e4 = 0, e5 = 0, e6 = 0, e7 = 0, e8 = 0, e9 = 0;
         int n_snot0 = 0, n_sgt0 = 0;
         double r_all = 0.0, r_major = 0.0, r_rate = 0.0;
-        for (int64_t row = lo + c.lane; row < hi; row += LANES) {
+        for (int64_t row = lo + lane_id(); row < hi; row += LANES) {
             int64_t i = row - b->read_base;
             uint32_t f = b->rflags[i];
             if (!rd_kept(lf, f)) continue;
@@ -689,7 +417,7 @@ VLR_DEV_NOINLINE void read_coefficients(Ctx& c, int s) {
     bool dead = false, bad = false;
     int base = 0; // kept reads before this chunk of LANES rows
     for (int64_t row0 = lo; row0 < hi; row0 += LANES) {
-        int64_t row = row0 + c.lane;
+        int64_t row = row0 + lane_id();
         bool valid = row < hi;
         Read r;
         bool kept = false;
@@ -702,7 +430,7 @@ VLR_DEV_NOINLINE void read_coefficients(Ctx& c, int s) {
         int n_kept = kept ? 1 : 0;
 #else
         unsigned m = __ballot_sync(FULL, kept);
-        int pos = base + __popc(m & ((1u << c.lane) - 1u));
+        int pos = base + __popc(m & ((1u << lane_id()) - 1u));
         int n_kept = __popc(m);
 #endif
         if (kept) {
@@ -782,7 +510,7 @@ VLR_DEV_NOINLINE void read_coefficients(Ctx& c, int s) {
 }
 
 // Pileup log-likelihood of sample s at (vaf, contaminant vaf): likelihood.rs:122-158 / :227-249.
-VLR_DEV_NOINLINE double sample_likelihood(Ctx& c, int s, double vaf, double vaf_by) {
+VLR_DEV double sample_likelihood(Ctx& c, int s, double vaf, double vaf_by) {
     const vlr_sample_t& sm = c.sc->samples[s];
     const int n = c.n_obs[s];
     if (n == 0) return 0.0; // empty fold = ln 1
@@ -803,11 +531,11 @@ VLR_DEV_NOINLINE double sample_likelihood(Ctx& c, int s, double vaf, double vaf_
     const double* co = c.coef + (int64_t)c.coef_off[s] * 4;
     double acc = 1.0;
     int ex = 0;
-    bool zero = false;
+    bool zero = false, overshoot = false;
     const bool s_one = c.s_one[s] != 0, s_gt1 = c.s_gt1[s] != 0;
     const double xu = X1 + X0;
     int k = 0;
-    for (int r = c.lane; r < n; r += LANES) {
+    for (int r = lane_id(); r < n; r += LANES) {
         const double al = co[4 * r], be = co[4 * r + 1], ga = co[4 * r + 2];
         double t;
         if (s_one) {
@@ -820,11 +548,11 @@ VLR_DEV_NOINLINE double sample_likelihood(Ctx& c, int s, double vaf, double vaf_
             const double sr = co[4 * r + 3];
             double xp = p1 ? 1.0 : vaf * sr, xs = s1 ? 1.0 : vaf_by * sr;
             if (xp > 1.0) {
-                if (log(xp) > NUMERICAL_EPSILON) c.status |= VLR_ST_OVERSHOOT;
+                if (log(xp) > NUMERICAL_EPSILON) overshoot = true;
                 xp = 1.0;
             }
             if (xs > 1.0) {
-                if (iota != 0.0 && log(xs) > NUMERICAL_EPSILON) c.status |= VLR_ST_OVERSHOOT;
+                if (iota != 0.0 && log(xs) > NUMERICAL_EPSILON) overshoot = true;
                 xs = 1.0;
             }
             double x = rho * xp + iota * xs, y = rho * (1.0 - xp) + iota * (1.0 - xs);
@@ -855,8 +583,7 @@ VLR_DEV_NOINLINE double sample_likelihood(Ctx& c, int s, double vaf, double vaf_
     }
     acc = w_mul_d(acc); // 32 mantissas in [1,2): < 2^32
     ex = w_sum_i(ex);
-    unsigned ov = w_or_u(c.status & VLR_ST_OVERSHOOT);
-    c.status |= ov;
+    if (s_gt1 && w_any(overshoot)) c.status |= VLR_ST_OVERSHOOT;
     if (w_any(zero) || ksum == neg_inf()) return neg_inf();
     if (acc != acc) {
         c.status |= VLR_ST_NAN;
@@ -1137,11 +864,23 @@ VLR_DEV_NOINLINE double prior_compute(Ctx& c, const Ops& ev) {
 }
 
 // ------------------------------------------------------------------------------------------------ joint
-// GenericLikelihood::compute (generic.rs:500-554) + Prior + rust-bio Model::joint_prob bookkeeping
-VLR_DEV_NOINLINE double joint(Ctx& c, const Ops& ops) {
+// GenericLikelihood::compute (generic.rs:500-554) + Prior + rust-bio Model::joint_prob bookkeeping.
+// `od` indexes the operand stack c.ops[]. FORCE-INLINED: its one hot call site is the evaluation site of the
+// leaf-level adaptive integrator; everything else reaches it through joint_call().
+VLR_DEV double joint(Ctx& c, int od) {
     const DevScenario* sc = c.sc;
     const int S = sc->S;
-    double prior = prior_compute(c, ops);
+    const Ops& ops = c.ops[od];
+    double prior;
+    if (sc->all_uniform) { // every sample declares a universe: flat prior inside it (prior.rs:385-406, :737)
+        prior = 0.0;
+        for (int s = 0; s < S; ++s) {
+            const double v = ops.vaf[s];
+            if ((sc->samples[s].ploidy == 0 && v != 0.0) || !universe_contains(c, s, v)) prior = neg_inf();
+        }
+    } else {
+        prior = prior_compute(c, ops);
+    }
     double lh = 0.0;
     bool lfc_ok = true;
     for (int k = 0; k < sc->n_lfc_nodes; ++k) {
@@ -1181,7 +920,7 @@ VLR_DEV_NOINLINE double joint(Ctx& c, const Ops& ops) {
     // rust-bio Model::joint_prob records every base event; only artifact-free ones can enter an AFD (calling.rs:912)
     if (c.be != nullptr && c.art.id == 0) {
         if (c.n_rec < (uint32_t)BE_CAP) {
-            if (c.lane == 0) {
+            if (lane_id() == 0) {
                 double* e = c.be + (int64_t)c.n_rec * (2 + S);
                 e[0] = j;
                 e[1] = d_make((int)ops.lfc_mask, (int)ops.disc_mask);
@@ -1204,23 +943,25 @@ VLR_DEV_NOINLINE double joint(Ctx& c, const Ops& ops) {
     }
     return j;
 }
+VLR_DEV_NOINLINE double joint_call(Ctx& c, int od) { return joint(c, od); }
 
 // ------------------------------------------------------------------------------------------------ density
-VLR_DEV_NOINLINE double density(Ctx& c, int ni, Ops& ops, int level);
+VLR_DEV_NOINLINE double density(Ctx& c, int ni, int od, int level);
 
-VLR_DEV_NOINLINE double subdensity(Ctx& c, const vlr_node_t& node, Ops& ops, int level) {
+// Value of the subtree below `node` for the operands c.ops[od] (the `subdensity` closure of generic.rs:199-231).
+VLR_DEV_NOINLINE double subdensity(Ctx& c, const vlr_node_t& node, int od, int level) {
     double p;
-    if (node.n_children == 0) p = joint(c, ops);
+    if (node.n_children == 0) p = joint_call(c, od);
     else if (node.n_children > 1) {
         Lse acc;
         acc.init();
         for (int k = 0; k < node.n_children; ++k) {
-            Ops cl = ops;
-            acc.add(density(c, node.first_child + k, cl, level));
+            c.ops[od + 1] = c.ops[od];
+            acc.add(density(c, node.first_child + k, od + 1, level));
         }
         p = acc.value();
     } else {
-        p = density(c, node.first_child, ops, level);
+        p = density(c, node.first_child, od, level);
     }
     if (p != p) c.status |= VLR_ST_NAN;
     return p;
@@ -1262,38 +1003,62 @@ VLR_DEV void ops_push(Ops& o, int sample, double vaf, bool discrete) {
     else o.disc_mask &= ~(1u << sample);
 }
 
-VLR_DEV_NOINLINE double eval_point(Ctx& c, const vlr_node_t& node, const Ops& ops, double vaf, int level) {
-    Ops cl = ops;
-    ops_push(cl, node.sample, vaf, false);
-    return subdensity(c, node, cl, level + 1);
-}
-
-// ln_simpsons_integrate_exp (rust-bio)
-VLR_DEV_NOINLINE double integrate_simpson(Ctx& c, const vlr_node_t& node, const Ops& ops, double a, double b, int n, int level) {
+// ln_simpsons_integrate_exp (rust-bio): interior points first, then the two ends
+VLR_DEV_NOINLINE double integrate_simpson(Ctx& c, const vlr_node_t& node, int od, double a, double b, int n, int level) {
     Lse acc;
     acc.init();
-    double step = (b - a) / (double)(n - 1);
-    for (int i = 1; i < n - 1; ++i) {
-        double w = (double)(2 + (i % 2) * 2);
-        acc.add(eval_point(c, node, ops, a + step * (double)i, level) + log(w));
+    const double step = (b - a) / (double)(n - 1);
+    for (int j = 0; j < n; ++j) {
+        double x, lw = 0.0;
+        if (j < n - 2) {
+            const int i = j + 1;
+            x = a + step * (double)i;
+            lw = log((double)(2 + (i % 2) * 2));
+        } else {
+            x = (j == n - 2) ? a : b;
+        }
+        c.ops[od + 1] = c.ops[od];
+        ops_push(c.ops[od + 1], node.sample, x, false);
+        acc.add(subdensity(c, node, od + 1, level + 1) + lw);
     }
-    acc.add(eval_point(c, node, ops, a, level));
-    acc.add(eval_point(c, node, ops, b, level));
     return acc.value() + log(b - a) - log((double)(n - 1)) - log(3.0);
 }
 
-// utils/adaptive_integration.rs:25-141. Points are appended to the per-level grid (duplicates allowed: they sort
-// next to each other and contribute zero-width trapezoids); argmax ties: ascending x, first maximum wins.
-VLR_DEV_NOINLINE double integrate_adaptive(Ctx& c, const vlr_node_t& node, const Ops& ops, double min_point, double max_point,
-                                  double res, int level) {
+// utils/adaptive_integration.rs:25-141 as a small state machine with ONE evaluation site (so the leaf evaluation
+// chain can be inlined exactly once). Visit order equals the reference's: min, max; per iteration middle, m1, m2;
+// then the abandoned-arm midpoint and the 3 + 3 points around the optimum. Points are appended to the per-level grid
+// (duplicates sort next to each other and form zero-width trapezoids); argmax ties: ascending x, first maximum.
+template <bool LEAF>
+VLR_DEV double integrate_adaptive_impl(Ctx& c, const vlr_node_t& node, int od, double min_point, double max_point,
+                                       double res, int level) {
     double* gx = c.ws->grid_x[level];
     double* gf = c.ws->grid_f[level];
+    const int lane = lane_id();
     int n = 0;
     bool overflow = false;
-    auto visit = [&](double x) -> double {
-        double f = eval_point(c, node, ops, x, level);
+    int phase = 0, i = 0, k = 2;
+    double left = min_point, right = max_point, f_left = 0.0, f_right = 0.0;
+    double middle = 0.0, first_middle = 0.0, m1 = 0.0, m2 = 0.0, f_m1 = 0.0, f_m2 = 0.0;
+    double xlo = 0.0, xstep_lo = 0.0, xstep_hi = 0.0, x_aband = 0.0;
+    bool have_middle = false;
+    for (;;) {
+        // ---- next abscissa
+        double x;
+        if (phase == 0) x = i == 0 ? min_point : max_point;
+        else if (phase == 1) x = i == 0 ? middle : (i == 1 ? m1 : m2);
+        else x = i == 0 ? x_aband : (i <= 3 ? xlo + xstep_lo * (double)(i - 1) : middle + xstep_hi * (double)(i - 3));
+        // ---- the evaluation site
+        c.ops[od + 1] = c.ops[od];
+        ops_push(c.ops[od + 1], node.sample, x, false);
+        double f;
+        if (LEAF) {
+            f = joint(c, od + 1);
+            if (f != f) c.status |= VLR_ST_NAN;
+        } else {
+            f = subdensity(c, node, od + 1, level + 1);
+        }
         if (n < GRID_CAP) {
-            if (c.lane == 0) {
+            if (lane == 0) {
                 gx[n] = x;
                 gf[n] = f;
             }
@@ -1301,90 +1066,112 @@ VLR_DEV_NOINLINE double integrate_adaptive(Ctx& c, const vlr_node_t& node, const
         } else {
             overflow = true;
         }
-        return f;
-    };
-    double left = min_point, right = max_point;
-    double f_left = visit(left), f_right = visit(right);
-    bool have_middle = false;
-    double first_middle = 0.0, middle = 0.0;
-    while ((((right - left) >= res) && left < right) || !have_middle) {
-        middle = (right + left) / 2.0;
-        visit(middle);
-        double m1 = (middle + left) / 2.0, m2 = (right + middle) / 2.0;
-        double f_m1 = visit(m1), f_m2 = visit(m2);
-        if (!have_middle) first_middle = middle;
-        have_middle = true;
-        double xs[4] = {left, m1, m2, right};
-        double fs[4] = {f_left, f_m1, f_m2, f_right};
-        int idx = 0;
-#pragma unroll
-        for (int i = 1; i < 4; ++i)
-            if (fs[i] > fs[idx]) idx = i;
-        // neighbours of the argmax; position() in the reference resolves duplicates to the first equal x
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-            if (i < idx && xs[i] == xs[idx]) {
-                idx = i;
-                break;
+        // ---- consume
+        if (phase == 0) {
+            if (i == 0) f_left = f;
+            else f_right = f;
+        } else if (phase == 1) {
+            if (i == 1) f_m1 = f;
+            else if (i == 2) f_m2 = f;
+        }
+        if (++i < k) continue;
+        i = 0;
+        if (phase == 1) {
+            if (!have_middle) first_middle = middle;
+            have_middle = true;
+            // argmax over [left, m1, m2, right] (the middle itself is not a candidate); neighbours become the new bounds
+            int idx = 0;
+            double fb = f_left;
+            if (f_m1 > fb) {
+                idx = 1;
+                fb = f_m1;
             }
-        double nl = idx > 0 ? xs[idx - 1] : xs[idx], nfl = idx > 0 ? fs[idx - 1] : fs[idx];
-        double nr = idx < 3 ? xs[idx + 1] : xs[idx], nfr = idx < 3 ? fs[idx + 1] : fs[idx];
-        left = nl;
-        f_left = nfl;
-        right = nr;
-        f_right = nfr;
-        if (overflow) break;
-    }
-    if (middle < first_middle) visit((max_point + first_middle) / 2.0);
-    else visit((first_middle + min_point) / 2.0);
-    {
-        double lo = fmax(middle - (res * 3.0), min_point);
-        double step = (middle - lo) / 3.0;
-        for (int i = 0; i < 3; ++i) visit(lo + step * (double)i);
-        double hi = fmin(middle + (res * 3.0), max_point);
-        step = (hi - middle) / 3.0;
-        for (int i = 1; i < 4; ++i) visit(middle + step * (double)i);
+            if (f_m2 > fb) {
+                idx = 2;
+                fb = f_m2;
+            }
+            if (f_right > fb) idx = 3;
+            // position() in the reference resolves duplicate abscissae to the first equal x
+            if (idx == 3 && right == m2) idx = 2;
+            if (idx == 2 && m2 == m1) idx = 1;
+            if (idx == 1 && m1 == left) idx = 0;
+            double nl, nfl, nr, nfr;
+            if (idx == 0) {
+                nl = left; nfl = f_left; nr = m1; nfr = f_m1;
+            } else if (idx == 1) {
+                nl = left; nfl = f_left; nr = m2; nfr = f_m2;
+            } else if (idx == 2) {
+                nl = m1; nfl = f_m1; nr = right; nfr = f_right;
+            } else {
+                nl = m2; nfl = f_m2; nr = right; nfr = f_right;
+            }
+            left = nl; f_left = nfl; right = nr; f_right = nfr;
+        } else if (phase == 2) {
+            break;
+        }
+        // while (((right - left) >= res && left < right) || middle.is_none())
+        if (!overflow && ((((right - left) >= res) && left < right) || !have_middle)) {
+            phase = 1;
+            k = 3;
+            middle = (right + left) / 2.0;
+            m1 = (middle + left) / 2.0;
+            m2 = (right + middle) / 2.0;
+        } else {
+            phase = 2;
+            k = 7;
+            x_aband = (middle < first_middle) ? (max_point + first_middle) / 2.0 : (first_middle + min_point) / 2.0;
+            xlo = fmax(middle - (res * 3.0), min_point);
+            xstep_lo = (middle - xlo) / 3.0;
+            const double xhi = fmin(middle + (res * 3.0), max_point);
+            xstep_hi = (xhi - middle) / 3.0;
+        }
     }
     if (overflow) c.status |= VLR_ST_GRID_OVERFLOW;
     warp_sync();
     // sort by x (rank sort, lanes over points), then ln_trapezoidal_integrate_grid_exp with lanes over intervals
     double* sx = c.ws->sort_x;
     double* sf = c.ws->sort_f;
-    for (int i = c.lane; i < n; i += LANES) {
-        double xi = gx[i];
+    for (int a = lane; a < n; a += LANES) {
+        double xi = gx[a];
         int rank = 0;
         for (int j = 0; j < n; ++j) {
             double xj = gx[j];
-            rank += (xj < xi) || (xj == xi && j < i);
+            rank += (xj < xi) || (xj == xi && j < a);
         }
         sx[rank] = xi;
-        sf[rank] = gf[i];
+        sf[rank] = gf[a];
     }
     warp_sync();
     double tmax = neg_inf();
-    for (int i = c.lane; i + 1 < n; i += LANES) {
-        double dx = sx[i + 1] - sx[i];
-        double t = (dx > 0.0) ? ln_add_exp(sf[i], sf[i + 1]) + log(dx) - LN_2 : neg_inf();
+    double tloc[(GRID_CAP + LANES - 1) / LANES];
+    int q = 0;
+    for (int a = lane; a + 1 < n; a += LANES, ++q) {
+        double dx = sx[a + 1] - sx[a];
+        double t = (dx > 0.0) ? ln_add_exp(sf[a], sf[a + 1]) + log(dx) - LN_2 : neg_inf();
         if (t != t) t = INFINITY; // poison through the max
+        tloc[q] = t;
         tmax = fmax(tmax, t);
     }
     tmax = w_max_d(tmax);
+    warp_sync();
     if (tmax == neg_inf()) return neg_inf();
     if (tmax == INFINITY) {
         c.status |= VLR_ST_NAN;
         return NAN;
     }
     double ssum = 0.0;
-    for (int i = c.lane; i + 1 < n; i += LANES) {
-        double dx = sx[i + 1] - sx[i];
-        if (dx > 0.0) {
-            double t = ln_add_exp(sf[i], sf[i + 1]) + log(dx) - LN_2;
-            if (t != neg_inf()) ssum += exp(t - tmax);
-        }
-    }
+    for (int a = 0; a < q; ++a)
+        if (tloc[a] != neg_inf()) ssum += exp(tloc[a] - tmax);
     ssum = w_sum_d(ssum);
-    warp_sync();
     return tmax + log(ssum);
+}
+VLR_DEV_NOINLINE double integrate_adaptive_leaf(Ctx& c, const vlr_node_t& node, int od, double a, double b, double res,
+                                                int level) {
+    return integrate_adaptive_impl<true>(c, node, od, a, b, res, level);
+}
+VLR_DEV_NOINLINE double integrate_adaptive_inner(Ctx& c, const vlr_node_t& node, int od, double a, double b, double res,
+                                                 int level) {
+    return integrate_adaptive_impl<false>(c, node, od, a, b, res, level);
 }
 
 VLR_DEV bool iupac_contains(int mask, int base) {
@@ -1398,29 +1185,30 @@ VLR_DEV bool iupac_contains(int mask, int base) {
     return (mask & bit) != 0;
 }
 
-// GenericPosterior::density (generic.rs:191-422)
-VLR_DEV_NOINLINE double density(Ctx& c, int ni, Ops& ops, int level) {
+// GenericPosterior::density (generic.rs:191-422). c.ops[od] are the operands so far (modified in place where the
+// reference passes its &mut on, copied to c.ops[od + 1] where it clones).
+VLR_DEV_NOINLINE double density(Ctx& c, int ni, int od, int level) {
     const DevScenario* sc = c.sc;
     const vlr_node_t& node = sc->nodes[ni];
     switch (node.kind) {
-    case VLR_NODE_LFC: ops.lfc_mask |= 1u << sc->lfc_ordinal[ni]; return subdensity(c, node, ops, level);
+    case VLR_NODE_LFC: c.ops[od].lfc_mask |= 1u << sc->lfc_ordinal[ni]; return subdensity(c, node, od, level);
     case VLR_NODE_FALSE: return neg_inf();
     case VLR_NODE_TRUE: return 0.0;
     case VLR_NODE_VARIANT: {
         if (c.has_snv) {
             bool contains = iupac_contains(node.refmask, c.refbase) && iupac_contains(node.altmask, c.altbase);
             if ((node.variant_positive && !contains) || (!node.variant_positive && contains)) return neg_inf();
-            return subdensity(c, node, ops, level);
+            return subdensity(c, node, od, level);
         } else if (node.variant_positive) {
             return neg_inf();
         }
-        return subdensity(c, node, ops, level);
+        return subdensity(c, node, od, level);
     }
     default: break;
     }
     const int sample = node.sample;
-    Range bounds;
-    bool have_bounds = ops_lfc_bounds(c, ops, sample, bounds);
+    Range bounds = range_empty();
+    bool have_bounds = ops_lfc_bounds(c, c.ops[od], sample, bounds);
     if (have_bounds && range_is_empty(bounds)) return neg_inf();
     const int n_obs = c.n_obs[sample];
     const bool is_clear_ref = c.clear_ref[sample] != 0;
@@ -1438,17 +1226,17 @@ VLR_DEV_NOINLINE double density(Ctx& c, int ni, Ops& ops, int level) {
         }
         if (is_clear_ref && all_pos) return neg_inf();
         if (n_in == 1) {
-            ops_push(ops, sample, only, true);
-            return subdensity(c, node, ops, level);
+            ops_push(c.ops[od], sample, only, true);
+            return subdensity(c, node, od, level);
         }
         Lse acc;
         acc.init();
         for (int i = 0; i < node.n_vafs; ++i) {
             double v = sc->set_vafs[node.vaf_offset + i];
             if (have_bounds && !range_contains(bounds, v)) continue;
-            Ops cl = ops;
-            ops_push(cl, sample, v, true);
-            acc.add(subdensity(c, node, cl, level));
+            c.ops[od + 1] = c.ops[od];
+            ops_push(c.ops[od + 1], sample, v, true);
+            acc.add(subdensity(c, node, od + 1, level));
         }
         return acc.value();
     }
@@ -1457,20 +1245,21 @@ VLR_DEV_NOINLINE double density(Ctx& c, int ni, Ops& ops, int level) {
     if (range_is_empty(vafs)) return neg_inf();
     if (is_clear_ref && vafs.start > 0.0) return neg_inf();
     if (range_is_singleton(vafs)) {
-        ops_push(ops, sample, vafs.start, true);
-        return subdensity(c, node, ops, level);
+        ops_push(c.ops[od], sample, vafs.start, true);
+        return subdensity(c, node, od, level);
     }
     const double res = sc->samples[sample].resolution;
     const double min_vaf = range_observable_min(vafs, n_obs);
     const double max_vaf = range_observable_max(vafs, n_obs);
     if (!(min_vaf <= max_vaf)) c.status |= VLR_ST_NAN; // assert in the reference
-    if ((max_vaf - min_vaf) < res) return integrate_simpson(c, node, ops, min_vaf, max_vaf, 3, level);
-    if (n_obs < 5) return integrate_simpson(c, node, ops, min_vaf, max_vaf, 11, level);
-    if (level >= MAXS) {
+    if ((max_vaf - min_vaf) < res) return integrate_simpson(c, node, od, min_vaf, max_vaf, 3, level);
+    if (n_obs < 5) return integrate_simpson(c, node, od, min_vaf, max_vaf, 11, level);
+    if (level >= WS_LEVELS) {
         c.status |= VLR_ST_GRID_OVERFLOW;
         return neg_inf();
     }
-    return integrate_adaptive(c, node, ops, min_vaf, max_vaf, res, level);
+    if (node.n_children == 0) return integrate_adaptive_leaf(c, node, od, min_vaf, max_vaf, res, level);
+    return integrate_adaptive_inner(c, node, od, min_vaf, max_vaf, res, level);
 }
 
 // ------------------------------------------------------------------------------------------------ locus driver
@@ -1541,7 +1330,7 @@ VLR_DEV_NOINLINE void afd_pass(Ctx& c, int best_scen, int map_slot, double margi
         int cnt = 0;
         bool trunc = false;
         for (int k0 = 0; k0 < n_rec; k0 += LANES) {
-            int k = k0 + c.lane;
+            int k = k0 + lane_id();
             bool ok = false;
             double x = 0.0, p = 0.0;
             if (k < n_rec) {
@@ -1568,7 +1357,7 @@ VLR_DEV_NOINLINE void afd_pass(Ctx& c, int best_scen, int map_slot, double margi
             int pos = cnt, tot = ok ? 1 : 0;
 #else
             unsigned m = __ballot_sync(FULL, ok);
-            int pos = cnt + __popc(m & ((1u << c.lane) - 1u)), tot = __popc(m);
+            int pos = cnt + __popc(m & ((1u << lane_id()) - 1u)), tot = __popc(m);
 #endif
             if (ok) {
                 if (pos < AFD_TMP) {
@@ -1587,7 +1376,7 @@ VLR_DEV_NOINLINE void afd_pass(Ctx& c, int best_scen, int map_slot, double margi
         const int cap = res->afd_capacity;
         int n_unique = 0;
         for (int i0 = 0; i0 < cnt; i0 += LANES) {
-            int i = i0 + c.lane;
+            int i = i0 + lane_id();
             bool first = false;
             int rank = 0;
             double xi = 0.0, pi = 0.0;
@@ -1630,13 +1419,15 @@ VLR_DEV_NOINLINE void afd_pass(Ctx& c, int best_scen, int map_slot, double margi
             n_unique += w_sum_i(first ? 1 : 0);
         }
         if (w_any(trunc)) c.status |= VLR_ST_AFD_TRUNCATED;
-        if (c.lane == 0) res->afd_count[(int64_t)c.locus * S + s] = n_unique < cap ? n_unique : cap;
+        if (lane_id() == 0) res->afd_count[(int64_t)c.locus * S + s] = n_unique < cap ? n_unique : cap;
         warp_sync();
     }
 }
 
+// `coef_sm` (capacity sm_reads) is the warp's shared-memory coefficient arena, `coef` (capacity coef_cap) the global
+// one used when the locus has more kept reads than fit in shared memory.
 VLR_DEV void process_locus(const DevScenario* sc, const DevBatch* b, const DevResults* res, WarpWs* ws, double* coef,
-                           double* be, int coef_cap, int64_t locus, Ctx& c) {
+                           double* coef_sm, int sm_reads, double* be, int coef_cap, int64_t locus, Ctx& c) {
     const int S = sc->S, E = sc->E;
     c.sc = sc;
     c.b = b;
@@ -1647,7 +1438,6 @@ VLR_DEV void process_locus(const DevScenario* sc, const DevBatch* b, const DevRe
     c.n_rec = 0;
     c.coef_cap = coef_cap;
     c.locus = locus;
-    c.lane = lane_id();
     c.status = 0;
     c.lf = b->lflags[locus];
     c.vartype = (c.lf >> VLR_LF_VARTYPE_SHIFT) & 3;
@@ -1673,7 +1463,7 @@ VLR_DEV void process_locus(const DevScenario* sc, const DevBatch* b, const DevRe
     BiasPlan plan;
     locus_prepass(c, plan);
     if (c.coef_total > c.coef_cap) { // only reachable through vlr_call_batch_device without a sufficient reserve
-        if (c.lane == 0) {
+        if (lane_id() == 0) {
             for (int e = 0; e <= E; ++e) res->log_post[locus * (int64_t)(E + 1) + e] = NAN;
             for (int s = 0; s < S; ++s) res->map_vaf[locus * S + s] = NAN;
             if (res->log_marginal) res->log_marginal[locus] = NAN;
@@ -1686,9 +1476,11 @@ VLR_DEV void process_locus(const DevScenario* sc, const DevBatch* b, const DevRe
         }
         return;
     }
+    if (c.coef_total <= sm_reads) c.coef = coef_sm;
 
     // joint probability per universe event: plain events get ln 0.5, twins ln 0.5 + ln(1/#configs) (generic.rs:437-441)
-    Lse ev_plain[MAXE], ev_twin[MAXE];
+    Lse* ev_plain = c.ev_plain;
+    Lse* ev_twin = c.ev_twin;
     for (int e = 0; e < E; ++e) {
         ev_plain[e].init();
         ev_twin[e].init();
@@ -1707,10 +1499,10 @@ VLR_DEV void process_locus(const DevScenario* sc, const DevBatch* b, const DevRe
             if (ci > 0 && !ev.has_artifact_twin) continue;
             c.cur_slot = 2 * e + (ci > 0 ? 1 : 0);
             for (int r = 0; r < ev.n_roots; ++r) {
-                Ops ops;
+                Ops& ops = c.ops[0];
                 for (int s = 0; s < MAXS; ++s) ops.vaf[s] = 0.0;
                 ops.set_mask = ops.disc_mask = ops.lfc_mask = 0;
-                double d = density(c, ev.first_root + r, ops, 0);
+                double d = density(c, ev.first_root + r, 0, 0);
                 if (ci == 0) ev_plain[e].add(LN_05 + d);
                 else ev_twin[e].add(twin_prior + d);
             }
@@ -1718,22 +1510,22 @@ VLR_DEV void process_locus(const DevScenario* sc, const DevBatch* b, const DevRe
     }
 
     // marginal over the event universe, in universe order [e plain, e twin]...
-    double joint_u[2 * MAXE];
-    int scen_u[2 * MAXE];
-    bool art_u[2 * MAXE];
+    double* joint_u = c.joint_u;
+    int* scen_u = c.scen_u;
+    uint8_t* art_u = c.art_u;
     int nu = 0;
     Lse marg;
     marg.init();
     for (int e = 0; e < E; ++e) {
         joint_u[nu] = ev_plain[e].value();
         scen_u[nu] = e;
-        art_u[nu] = false;
+        art_u[nu] = 0;
         marg.add(joint_u[nu]);
         nu++;
         if (sc->events[e].has_artifact_twin && plan.n_twins > 0) {
             joint_u[nu] = ev_twin[e].value();
             scen_u[nu] = e;
-            art_u[nu] = true;
+            art_u[nu] = 1;
             marg.add(joint_u[nu]);
             nu++;
         }
@@ -1756,7 +1548,7 @@ VLR_DEV void process_locus(const DevScenario* sc, const DevBatch* b, const DevRe
     Lse art;
     art.init();
     double* lp = res->log_post + locus * (int64_t)(E + 1);
-    double my_lp[MAXE + 1];
+    double* my_lp = c.my_lp;
     for (int i = 0; i < nu; ++i) {
         double post = joint_u[i] - marginal;
         if (art_u[i]) art.add(post);
@@ -1780,7 +1572,7 @@ VLR_DEV void process_locus(const DevScenario* sc, const DevBatch* b, const DevRe
     }
     if (map_slot < 0) c.status |= VLR_ST_NO_MAP;
 
-    if (c.lane == 0) {
+    if (lane_id() == 0) {
         for (int e = 0; e <= E; ++e) lp[e] = my_lp[e];
         if (res->log_marginal) res->log_marginal[locus] = marginal;
         if (res->best_event) res->best_event[locus] = 2 * best_scen + (art_u[best] ? 1 : 0);
@@ -1795,7 +1587,12 @@ VLR_DEV void process_locus(const DevScenario* sc, const DevBatch* b, const DevRe
             for (int s = 0; s < S; ++s) res->afd_count[locus * S + s] = 0;
     }
     if (res->afd_capacity > 0) afd_pass(c, best_scen, map_slot, marginal);
-    if (c.lane == 0) res->status[locus] = c.status;
+    if (lane_id() == 0) res->status[locus] = c.status;
 }
 
-} // namespace vlrcore
+
+} // namespace VLR_VARIANT
+#undef VLR_VARIANT
+#undef VLR_VAR_MAXS
+#undef VLR_VAR_MAXE
+#undef VLR_VAR_MAXD

@@ -1,0 +1,295 @@
+// engine_types.cuh — warp primitives, device views, LogProb / VAFRange helpers shared by every engine variant.
+// See engine_core.cuh for the engine itself.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../../include/vlr_engine.h"
+
+#ifdef VLR_HOST_EMU
+#define VLR_DEV inline
+#define VLR_DEV_NOINLINE
+#else
+#define VLR_DEV __device__ __forceinline__
+#define VLR_DEV_NOINLINE __device__ __noinline__
+#endif
+
+namespace vlrcore {
+
+constexpr int WS_LEVELS = VLR_MAX_SAMPLES; // nested integration levels with scratch grids
+constexpr int NCFG = VLR_N_ARTIFACT_CONFIGS;
+constexpr int GRID_CAP = 128;   // points per adaptive integration (res >= ~1e-5)
+constexpr int LC_WAYS = 4;      // per-sample pileup-likelihood cache entries
+constexpr int MAX_LFC_NODES = 32;
+constexpr int AFD_TMP = 512;
+
+constexpr double NUMERICAL_EPSILON = 1e-3;        // utils/mod.rs:41
+constexpr double LN_05 = -0.6931471805599453;     // ln 0.5 (utils/mod.rs:45-47)
+constexpr double LN_2 = 0.6931471805599453;
+constexpr double LN_095 = -0.05129329438755058;   // ln 0.95 (utils/mod.rs:49-51)
+constexpr double LN_3 = 1.0986122886681098;       // Kass-Raftery thresholds 3, 20, 150 in log space
+constexpr double LN_20 = 2.995732273553991;
+constexpr double LN_150 = 5.0106352940962555;
+
+// ------------------------------------------------------------------------------------------------ warp layer
+#ifdef VLR_HOST_EMU
+constexpr int LANES = 1;
+VLR_DEV int lane_id() { return 0; }
+VLR_DEV void warp_sync() {}
+VLR_DEV int w_sum_i(int v) { return v; }
+VLR_DEV unsigned w_or_u(unsigned v) { return v; }
+VLR_DEV int w_max_i(int v) { return v; }
+VLR_DEV double w_sum_d(double v) { return v; }
+VLR_DEV double w_mul_d(double v) { return v; }
+VLR_DEV double w_max_d(double v) { return v; }
+VLR_DEV bool w_any(bool p) { return p; }
+VLR_DEV double w_bcast_d(double v, int) { return v; }
+VLR_DEV int d_hi(double x) {
+    uint64_t u;
+    memcpy(&u, &x, 8);
+    return (int)(u >> 32);
+}
+VLR_DEV int d_lo(double x) {
+    uint64_t u;
+    memcpy(&u, &x, 8);
+    return (int)(u & 0xffffffffu);
+}
+VLR_DEV double d_make(int hi, int lo) {
+    uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo;
+    double x;
+    memcpy(&x, &u, 8);
+    return x;
+}
+#else
+constexpr int LANES = 32;
+constexpr unsigned FULL = 0xffffffffu;
+VLR_DEV int lane_id() { return (int)(threadIdx.x & 31); }
+VLR_DEV void warp_sync() { __syncwarp(); }
+VLR_DEV int w_sum_i(int v) { return __reduce_add_sync(FULL, v); }
+VLR_DEV unsigned w_or_u(unsigned v) { return __reduce_or_sync(FULL, v); }
+VLR_DEV int w_max_i(int v) { return __reduce_max_sync(FULL, v); }
+// xor butterflies: a+b == b+a bitwise, so every lane ends with the identical value (needed for uniform control flow)
+VLR_DEV double w_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+VLR_DEV double w_mul_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v *= __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+VLR_DEV double w_max_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+VLR_DEV bool w_any(bool p) { return __any_sync(FULL, p) != 0; }
+VLR_DEV double w_bcast_d(double v, int src) { return __shfl_sync(FULL, v, src); }
+VLR_DEV int d_hi(double x) { return __double2hiint(x); }
+VLR_DEV int d_lo(double x) { return __double2loint(x); }
+VLR_DEV double d_make(int hi, int lo) { return __hiloint2double(hi, lo); }
+#endif
+
+VLR_DEV double neg_inf() { return -INFINITY; }
+
+// ------------------------------------------------------------------------------------------------ device views
+struct DevScenario {
+    int S, E, n_nodes, n_set_vafs, n_spectra, full_prior, all_uniform, n_lfc_nodes;
+    const vlr_sample_t* samples;
+    const vlr_event_t* events;
+    const vlr_node_t* nodes;
+    const double* set_vafs;
+    const vlr_spectrum_t* spectra;
+    const int* lfc_nodes; // ordinal -> node index (LFC nodes only)
+    const int* lfc_ordinal; // node index -> ordinal (or -1)
+    double heterozygosity; // linear, NaN = none
+    double vtf[4];         // variant type fraction by VLR_LF_VARTYPE class
+};
+
+struct DevBatch {
+    int64_t n_loci;
+    int64_t read_base; // first row held by the column pointers (chunked transfers)
+    const int64_t* read_offsets;
+    const float *pm, *pr, *pa, *pmiss, *psa, *pdo, *phb;
+    const uint32_t* rflags;
+    const float *hart, *hvar;
+    const uint32_t* lflags;
+    const float *het_phred, *semr_phred;
+};
+
+struct DevResults {
+    double* log_post;
+    double* log_marginal;
+    double* map_vaf;
+    int32_t* map_config;
+    int32_t* best_event;
+    uint32_t* status;
+    uint32_t* n_base_events;
+    int32_t afd_capacity;
+    int32_t* afd_count;
+    double* afd_vaf;
+    double* afd_logp;
+};
+
+// Per-warp scratch in global memory (private to the warp, so it lives in L1/L2).
+constexpr int BE_CAP = 4096; // recorded base events per locus (only when an AFD is requested)
+
+struct WarpWs {
+    double grid_x[WS_LEVELS][GRID_CAP];
+    double grid_f[WS_LEVELS][GRID_CAP];
+    double sort_x[GRID_CAP];
+    double sort_f[GRID_CAP];
+    double afd_x[AFD_TMP];
+    double afd_p[AFD_TMP];
+};
+
+// ------------------------------------------------------------------------------------------------ LogProb helpers
+// (rust-bio LogProb semantics)
+VLR_DEV_NOINLINE double ln_add_exp(double a, double b) {
+    double p0, p1;
+    if (b > a) {
+        p0 = b;
+        p1 = a;
+    } else {
+        p0 = a;
+        p1 = b;
+    }
+    if (p0 == neg_inf()) return neg_inf();
+    if (p1 == neg_inf()) return p0;
+    return p0 + log1p(exp(p1 - p0));
+}
+VLR_DEV_NOINLINE double ln_one_minus_exp(double p) {
+    if (p < -0.693) return log1p(-exp(p));
+    return log(-expm1(p));
+}
+// streaming ln_sum_exp accumulator (differs from the reference's max-first two-pass form by rounding only)
+struct Lse {
+    double m, s; // max so far, sum of exp(x - m)
+    int n;
+    VLR_DEV void init() {
+        m = neg_inf();
+        s = 0.0;
+        n = 0;
+    }
+    VLR_DEV_NOINLINE void add(double x) {
+        n++;
+        if (x == neg_inf()) return;
+        if (x != x) { // NaN poisons like the reference's arithmetic would
+            m = x;
+            return;
+        }
+        if (x > m) {
+            s = (m == neg_inf()) ? 1.0 : s * exp(m - x) + 1.0;
+            m = x;
+        } else {
+            s += exp(x - m);
+        }
+    }
+    VLR_DEV double value() const {
+        if (m == neg_inf() || m != m || m == INFINITY) return m;
+        return m + log1p(s - 1.0);
+    }
+};
+
+VLR_DEV int kass_raftery(double m1, double m2) {
+    // BayesFactor::new(m1, m2) = exp(m1 - m2) compared with 1, 3, 20, 150; evaluated in log space.
+    double d = m1 - m2;
+    if (d <= 0.0) return 0;
+    if (d <= LN_3) return 1;
+    if (d <= LN_20) return 2;
+    if (d <= LN_150) return 3;
+    return 4; // incl. NaN, like the chain of failed comparisons in the reference
+}
+
+VLR_DEV bool relative_eq(double a, double b) { // approx 0.5 defaults (epsilon = max_relative = f64::EPSILON)
+    if (a == b) return true;
+    if (isinf(a) || isinf(b)) return false;
+    double diff = fabs(a - b);
+    const double eps = 2.220446049250313e-16;
+    if (diff <= eps) return true;
+    double largest = fmax(fabs(a), fabs(b));
+    return diff <= largest * eps;
+}
+
+// ------------------------------------------------------------------------------------------------ VAFRange
+struct Range {
+    double start, end;
+    bool lex, rex;
+};
+VLR_DEV Range range_empty() { return Range{0.0, 0.0, true, true}; }
+VLR_DEV bool range_is_empty(const Range& r) { return r.start == r.end && (r.lex || r.rex); }
+VLR_DEV bool range_is_singleton(const Range& r) { return r.start == r.end && !(r.lex || r.rex); }
+VLR_DEV bool range_contains(const Range& r, double v) {
+    bool l = r.lex ? (r.start < v) : (r.start <= v);
+    bool rr = r.rex ? (r.end > v) : (r.end >= v);
+    return l && rr;
+}
+VLR_DEV bool range_no_overlap(const Range& a, const Range& o) { // formula.rs:1137-1170
+    if (a.start == o.start && a.end == o.end && a.lex == o.lex && a.rex == o.rex) return false;
+    return (a.end < o.start || a.start > o.end) || (a.end <= o.start && (a.rex || o.lex)) ||
+           (a.start >= o.end && (a.lex || o.rex));
+}
+VLR_DEV Range range_intersect(const Range& a, const Range& o) {
+    if (range_no_overlap(a, o)) return range_empty();
+    Range r;
+    r.start = fmax(a.start, o.start);
+    r.end = fmin(a.end, o.end);
+    r.lex = a.start > o.start ? a.lex : (a.start < o.start ? o.lex : (a.lex || o.lex));
+    r.rex = a.end < o.end ? a.rex : (a.end > o.end ? o.rex : (a.rex || o.rex));
+    return r;
+}
+VLR_DEV double range_observable_max(const Range& r, int n) { // formula.rs:1202-1224
+    if (n < 10 || !((double)n * (r.end - r.start) > 1.0)) return r.end;
+    double c = (double)n * r.end;
+    if (r.rex && fmod(c, 1.0) == 0.0) c -= 1.0;
+    c = floor(c);
+    if (c == 0.0) return r.end;
+    return c / (double)n;
+}
+VLR_DEV double range_observable_min(const Range& r, int n) { // formula.rs:1172-1200
+    double min_vaf;
+    if (n < 10 || !((double)n * (r.end - r.start) > 1.0)) {
+        min_vaf = r.start;
+    } else {
+        double c = (double)n * r.start;
+        if (r.lex && fmod(c, 1.0) == 0.0) {
+            double adjusted_end = range_observable_max(r, n);
+            double s1 = ceil(c + 1.0) / (double)n;
+            if (s1 <= 1.0 && s1 <= adjusted_end) return s1;
+            double s0 = ceil(c) / (double)n;
+            if (s0 <= 1.0 && s0 <= adjusted_end) return s0;
+        }
+        min_vaf = ceil(c) / (double)n;
+    }
+    if (min_vaf >= range_observable_max(r, n)) return r.start;
+    return min_vaf;
+}
+
+// log2 fold change predicates (utils/log2_fold_change.rs)
+VLR_DEV int lfc_invert_cmp(int cmp) {
+    switch (cmp) {
+    case VLR_CMP_GT: return VLR_CMP_LE;
+    case VLR_CMP_GE: return VLR_CMP_LT;
+    case VLR_CMP_LT: return VLR_CMP_GE;
+    case VLR_CMP_LE: return VLR_CMP_GT;
+    default: return cmp;
+    }
+}
+VLR_DEV Range lfc_infer_bounds(int cmp, double value, double vaf) {
+    double proj = vaf / exp2(value);
+    if (proj < 0.0 || proj > 1.0) return range_empty();
+    switch (cmp) {
+    case VLR_CMP_EQ: return Range{proj, proj, false, false};
+    case VLR_CMP_GT: return Range{0.0, proj, false, true};
+    case VLR_CMP_GE: return Range{0.0, proj, false, false};
+    case VLR_CMP_LT: return Range{proj, 1.0, true, false};
+    case VLR_CMP_LE: return Range{proj, 1.0, false, false};
+    default: return Range{0.0, 1.0, false, false};
+    }
+}
+
+
+} // namespace vlrcore

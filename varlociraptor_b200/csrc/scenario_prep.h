@@ -4,7 +4,7 @@
 #include <cmath>
 #include <vector>
 
-#include "engine_core.cuh"
+#include "engine_types.cuh"
 
 namespace vlrcore {
 

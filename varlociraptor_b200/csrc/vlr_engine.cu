@@ -15,6 +15,17 @@
 #include <string>
 #include <vector>
 
+// The engine core is instantiated twice by inclusion: a small variant (<= 3 samples, <= 8 events, tree depth <= 6:
+// tumor-normal, trios) whose per-warp state is ~2 KB of shared memory, and the full-capacity variant.
+#define VLR_VARIANT vlr_small
+#define VLR_VAR_MAXS 3
+#define VLR_VAR_MAXE 8
+#define VLR_VAR_MAXD 6
+#include "engine_core.cuh"
+#define VLR_VARIANT vlr_full
+#define VLR_VAR_MAXS VLR_MAX_SAMPLES
+#define VLR_VAR_MAXE VLR_MAX_EVENTS
+#define VLR_VAR_MAXD VLR_MAX_TREE_DEPTH
 #include "engine_core.cuh"
 #include "scenario_prep.h"
 
@@ -34,25 +45,39 @@ struct KernelParams {
     double* coef;
     double* be;
     unsigned long long* ticket;
-    int coef_cap;     // reads per warp
+    int coef_cap;      // reads per warp in the global arena
+    int sm_reads;      // reads per warp in the shared-memory arena
+    int ctx_stride;    // bytes of shared memory per warp for the Ctx
     int64_t be_stride; // doubles per warp
 };
 
-__global__ void __launch_bounds__(THREADS) vlr_call_kernel(const __grid_constant__ KernelParams p) {
-    const int gw = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
-    WarpWs* ws = p.ws + gw;
-    double* coef = p.coef + (int64_t)gw * p.coef_cap * 4;
-    double* be = p.be ? p.be + (int64_t)gw * p.be_stride : nullptr;
-    Ctx c;
-    for (;;) {
-        unsigned long long t = 0;
-        if ((threadIdx.x & 31) == 0) t = atomicAdd(p.ticket, 1ULL);
-        t = __shfl_sync(0xffffffffu, t, 0);
-        if ((int64_t)t >= p.b.n_loci) break;
-        process_locus(&p.sc, &p.b, &p.r, ws, coef, be, p.coef_cap, (int64_t)t, c);
-        __syncwarp();
+constexpr int SM_READS = 256; // 8 KB of coefficients per warp: covers 100 reads/sample x 2 samples (config 2)
+
+// Shared memory per CTA: [WARPS_PER_CTA x Ctx (uniform per-warp state)] [WARPS_PER_CTA x coefficient arena].
+#define VLR_DEFINE_KERNEL(NS)                                                                                     \
+    __global__ void __launch_bounds__(THREADS, 2) vlr_call_kernel_##NS(const __grid_constant__ KernelParams p) {  \
+        extern __shared__ __align__(16) unsigned char vlr_smem[];                                                 \
+        const int w = threadIdx.x >> 5;                                                                           \
+        const int gw = blockIdx.x * WARPS_PER_CTA + w;                                                            \
+        NS::Ctx& c = *reinterpret_cast<NS::Ctx*>(vlr_smem + (size_t)w * p.ctx_stride);                            \
+        double* coef_sm = reinterpret_cast<double*>(vlr_smem + (size_t)WARPS_PER_CTA * p.ctx_stride) +            \
+                          (size_t)w * p.sm_reads * 4;                                                             \
+        WarpWs* ws = p.ws + gw;                                                                                   \
+        double* coef = p.coef + (int64_t)gw * p.coef_cap * 4;                                                     \
+        double* be = p.be ? p.be + (int64_t)gw * p.be_stride : nullptr;                                           \
+        for (;;) {                                                                                                \
+            unsigned long long t = 0;                                                                             \
+            if ((threadIdx.x & 31) == 0) t = atomicAdd(p.ticket, 1ULL);                                           \
+            t = __shfl_sync(0xffffffffu, t, 0);                                                                   \
+            if ((int64_t)t >= p.b.n_loci) break;                                                                  \
+            NS::process_locus(&p.sc, &p.b, &p.r, ws, coef, coef_sm, p.sm_reads, be, p.coef_cap, (int64_t)t, c);   \
+            __syncwarp();                                                                                         \
+        }                                                                                                         \
     }
-}
+VLR_DEFINE_KERNEL(vlr_small)
+VLR_DEFINE_KERNEL(vlr_full)
+
+inline int align16(size_t x) { return (int)((x + 15) & ~(size_t)15); }
 
 #define CK(call)                                                                      \
     do {                                                                              \
@@ -97,6 +122,9 @@ struct vlr_ctx {
     int ctas_per_sm = 1;
     int grid = 0;
     int S = 0, E = 0;
+    bool small = false;   // which engine variant serves this scenario
+    int ctx_stride = 0;
+    size_t smem_bytes = 0;
     ScenarioPrep prep;
     DevScenario dsc;
     DevBuf d_samples, d_events, d_nodes, d_set_vafs, d_spectra, d_lfc_nodes, d_lfc_ordinal;
@@ -146,10 +174,13 @@ vlr_status_t launch(vlr_ctx* ctx, Slot& sl, const DevBatch& b, const DevResults&
     p.be = r.afd_capacity > 0 ? (double*)sl.be.p : nullptr;
     p.ticket = (unsigned long long*)sl.ticket.p;
     p.coef_cap = sl.coef_cap;
+    p.sm_reads = SM_READS;
+    p.ctx_stride = ctx->ctx_stride;
     p.be_stride = (int64_t)BE_CAP * (2 + ctx->S);
     CK(cudaMemsetAsync(sl.ticket.p, 0, sizeof(unsigned long long), stream));
     if (b.n_loci > 0) {
-        vlr_call_kernel<<<ctx->grid, THREADS, 0, stream>>>(p);
+        if (ctx->small) vlr_call_kernel_vlr_small<<<ctx->grid, THREADS, ctx->smem_bytes, stream>>>(p);
+        else vlr_call_kernel_vlr_full<<<ctx->grid, THREADS, ctx->smem_bytes, stream>>>(p);
         CK(cudaGetLastError());
         ctx->launches++;
     }
@@ -263,10 +294,19 @@ vlr_status_t vlr_ctx_create(const vlr_scenario_t* scenario, int32_t device, vlr_
                               (const int*)ctx->d_lfc_ordinal.p);
     // The tree walk recurses once per tree level (density -> subdensity -> density); frames hold an Ops copy and the
     // integration state. Size the per-thread stack from the scenario's depth.
-    size_t stack = 10240 + (size_t)(ctx->prep.max_depth + 2) * 1024;
+    size_t stack = 4096 + (size_t)(ctx->prep.max_depth + 2) * 1024;
     CKB(cudaDeviceSetLimit(cudaLimitStackSize, stack));
+    ctx->small = scenario->n_samples <= 3 && scenario->n_events <= 8 && ctx->prep.max_depth <= 6;
+    ctx->ctx_stride = align16(ctx->small ? sizeof(vlr_small::Ctx) : sizeof(vlr_full::Ctx));
+    ctx->smem_bytes = (size_t)WARPS_PER_CTA * ((size_t)ctx->ctx_stride + (size_t)SM_READS * 4 * sizeof(double));
     int per_sm = 0;
-    CKB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vlr_call_kernel, THREADS, 0));
+    if (ctx->small) {
+        CKB(cudaFuncSetAttribute(vlr_call_kernel_vlr_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bytes));
+        CKB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vlr_call_kernel_vlr_small, THREADS, ctx->smem_bytes));
+    } else {
+        CKB(cudaFuncSetAttribute(vlr_call_kernel_vlr_full, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bytes));
+        CKB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vlr_call_kernel_vlr_full, THREADS, ctx->smem_bytes));
+    }
     if (per_sm < 1) per_sm = 1;
     ctx->ctas_per_sm = per_sm;
     ctx->grid = per_sm * ctx->n_sms;
