@@ -47,6 +47,111 @@ struct Art { // bias::Artifacts restricted to "none" or exactly one artifact (bi
     bool has_alt_loci;
 };
 
+// utils/adaptive_integration.rs:25-141 as a small state machine that hands out the abscissae in batches:
+// [min, max]; per iteration [middle, m1, m2]; finally the abandoned-arm midpoint and the 3 + 3 points around the optimum.
+// The visit order equals the reference's. Argmax ties: ascending x, first maximum wins (the reference iterates a HashMap).
+struct Adaptive {
+    double minp, maxp, res;
+    double left, right, f_left, f_right, middle, first_middle;
+    int phase;
+    bool have_middle, stop;
+    VLR_DEV void init(double a, double b, double r) {
+        minp = a;
+        maxp = b;
+        res = r;
+        left = a;
+        right = b;
+        f_left = f_right = middle = first_middle = 0.0;
+        phase = 0;
+        have_middle = false;
+        stop = false;
+    }
+    // fills xs[0..k) and returns k (2, 3 or 7)
+    VLR_DEV int points(double* xs) const {
+        if (phase == 0) {
+            xs[0] = minp;
+            xs[1] = maxp;
+            return 2;
+        }
+        if (phase == 1) {
+            xs[0] = middle;
+            xs[1] = (middle + left) / 2.0;
+            xs[2] = (right + middle) / 2.0;
+            return 3;
+        }
+        xs[0] = (middle < first_middle) ? (maxp + first_middle) / 2.0 : (first_middle + minp) / 2.0;
+        const double lo = fmax(middle - (res * 3.0), minp);
+        const double slo = (middle - lo) / 3.0; // itertools-num linspace(lo, middle, 4).take(3)
+        xs[1] = lo + slo * 0.0;
+        xs[2] = lo + slo * 1.0;
+        xs[3] = lo + slo * 2.0;
+        const double hi = fmin(middle + (res * 3.0), maxp);
+        const double shi = (hi - middle) / 3.0; // linspace(middle, hi, 4).skip(1)
+        xs[4] = middle + shi * 1.0;
+        xs[5] = middle + shi * 2.0;
+        xs[6] = middle + shi * 3.0;
+        return 7;
+    }
+    // takes the values of the batch; returns false when the integration grid is complete
+    VLR_DEV bool consume(const double* xs, const double* fs, bool overflow) {
+        if (phase == 2) return false;
+        if (phase == 0) {
+            f_left = fs[0];
+            f_right = fs[1];
+        } else {
+            if (!have_middle) first_middle = middle;
+            have_middle = true;
+            const double m1 = xs[1], m2 = xs[2], f_m1 = fs[1], f_m2 = fs[2];
+            int idx = 0;
+            double fb = f_left;
+            if (f_m1 > fb) {
+                idx = 1;
+                fb = f_m1;
+            }
+            if (f_m2 > fb) {
+                idx = 2;
+                fb = f_m2;
+            }
+            if (f_right > fb) idx = 3;
+            // neighbours of the argmax in [left, m1, m2, right] become the new bounds (the middle is not a candidate)
+            const double nl = idx <= 1 ? left : (idx == 2 ? m1 : m2), nfl = idx <= 1 ? f_left : (idx == 2 ? f_m1 : f_m2);
+            const double nr = idx == 0 ? m1 : (idx == 1 ? m2 : right), nfr = idx == 0 ? f_m1 : (idx == 1 ? f_m2 : f_right);
+            left = nl;
+            f_left = nfl;
+            right = nr;
+            f_right = nfr;
+        }
+        // while (((right - left) >= res && left < right) || middle.is_none())
+        if (!overflow && ((((right - left) >= res) && left < right) || !have_middle)) {
+            phase = 1;
+            middle = (right + left) / 2.0;
+        } else {
+            phase = 2;
+        }
+        return true;
+    }
+};
+
+
+// ---- leaf fast path state -------------------------------------------------------------------------------------
+// Along a leaf-level integration only sample t's VAF changes. Everything else is hoisted: the prior factors and the
+// pileup likelihoods of the samples that do not see t (GenericLikelihood::compute, generic.rs:511-551, hits its
+// per-sample cache for them at every point), and for the (at most two) samples that do, their pileup constants.
+constexpr int NB = 4; // abscissae per batch (short batches are padded): ONE instantiation keeps the hot code small
+struct LeafDep {
+    const double2* co; // coefficient arena of the sample (shared or global memory)
+    double ksum, rho, iota, fixed_vaf, fixed_by;
+    int n, s;
+    bool vaf_is_x, by_is_x, has_by;
+};
+struct LeafFast {
+    LeafDep dep[2];
+    int n_dep;
+    double lh_const, prior_const;
+    bool prior_per_point; // the prior has to be evaluated per point (non-uniform priors, or a universe with holes)
+    bool uniform, t_ploidy0, coef_in_sm;
+};
+
 // One instance per warp, in SHARED memory: every lane sees the same (uniform) state, so a single copy replaces
 // 32 per-lane local-memory copies. Writes are either "all lanes store the identical value" or lane-0 + warp_sync().
 struct Ctx {
@@ -57,6 +162,7 @@ struct Ctx {
     double* coef; // per-warp coefficient arena: 4 doubles per kept read (alpha, beta, gamma, s)
     double* be;   // per-warp base-event log (NULL unless an AFD is requested): BE_CAP x (2 + S) doubles
     uint32_t n_rec;
+    int coef_in_sm; // the coefficients of this locus live in the warp's shared-memory arena
     int coef_cap;   // capacity of `coef` in reads
     int coef_total; // kept reads of this locus over all samples
     int64_t locus;
@@ -87,6 +193,11 @@ struct Ctx {
     uint8_t map_set[2 * MAXE];
     // operand stack of the tree walk (generic.rs clones LikelihoodOperands per branch / grid point)
     Ops ops[MAXD + 2];
+    // adaptive integration state per nesting level (at most one Range level per sample) and the leaf fast path
+    Adaptive ad[MAXS];
+    double xs[MAXS][8], fs[MAXS][8];
+    double lh[NB];
+    LeafFast leaf;
     // per-event accumulators and end-of-locus scratch
     Lse ev_plain[MAXE], ev_twin[MAXE];
     double joint_u[2 * MAXE];
@@ -98,7 +209,18 @@ struct Ctx {
     uint32_t n_pileup_evals;
 };
 
-VLR_DEV uint32_t locus_check(const Ctx& c, uint32_t bit) { return c.lf & bit; }
+// Shared memory of a CTA: [WARPS_PER_CTA x Ctx][WARPS_PER_CTA x SM_READS x 4 doubles]. Deriving the per-warp
+// references from the __shared__ symbol (instead of carrying generic pointers through calls) lets the compiler
+// emit LDS/STS for all of the uniform state.
+constexpr int CTX_STRIDE = (int)((sizeof(Ctx) + 15) & ~(size_t)15);
+#ifdef VLR_HOST_EMU
+VLR_DEV Ctx& warp_ctx(Ctx& c) { return c; }
+#else
+VLR_DEV Ctx& warp_ctx(Ctx&) { return *reinterpret_cast<Ctx*>(vlr_smem + (threadIdx.x >> 5) * CTX_STRIDE); }
+VLR_DEV double* warp_coef_sm() {
+    return reinterpret_cast<double*>(vlr_smem + WARPS_PER_CTA * CTX_STRIDE) + (threadIdx.x >> 5) * (SM_READS * 4);
+}
+#endif
 
 // ------------------------------------------------------------------------------------------------ reads
 struct Read {
@@ -150,7 +272,8 @@ struct BiasPlan {
 //   calling.rs:595-616 (filter + singleton), generic.rs:270-291 (n_obs, is_clear_ref),
 //   strand_bias.rs:79-123, read_orientation_bias.rs:38-97, read_position_bias.rs:63-121, softclip_bias.rs:32-39,
 //   homopolymer_error.rs:46-72, alt_locus_bias.rs:47-59,124-144, bias/mod.rs:37-104.
-VLR_DEV_NOINLINE void locus_prepass(Ctx& c, BiasPlan& plan) {
+VLR_DEV_NOINLINE void locus_prepass(Ctx& c_, BiasPlan& plan) {
+    Ctx& c = warp_ctx(c_);
     const DevBatch* b = c.b;
     const int S = c.sc->S;
     const uint32_t lf = c.lf;
@@ -199,7 +322,7 @@ VLR_DEV_NOINLINE void locus_prepass(Ctx& c, BiasPlan& plan) {
                 g_alt_support++;
                 g_alt_row = row;
             }
-            double w = exp(pm);
+            double w = m_exp(pm);
             if (strong_ref) {
                 if (strand != 2) g_sb_all += w;
                 if (strand == 0) g_sb_fwd += w;
@@ -210,7 +333,7 @@ VLR_DEV_NOINLINE void locus_prepass(Ctx& c, BiasPlan& plan) {
                 g_nm_ref += !maxq;
                 r_all += w;
                 if (major) r_major += w;
-                r_rate += exp(pm + phb);
+                r_rate += m_exp(pm + phb);
             }
             g_uncertain += !(orient == 0 || orient == 1);
             if (strong_alt) {
@@ -402,12 +525,13 @@ VLR_DEV_NOINLINE void locus_prepass(Ctx& c, BiasPlan& plan) {
 }
 
 // Hoist everything VAF-independent of one (sample, artifact config) into per-read coefficients.
-//   L_r(x) = e^{K_r} * (alpha_r * x + beta_r * (1 - x) + gamma_r)
+//   L_r(x) = e^{K_r} * (alpha_r * x + beta_r * (1 - x) + gamma_r); the arena keeps [alpha, beta, gamma, 1 - s_r]
 //   ln alpha' = prob_mapping + bias.prob_alt + prob_alt     (likelihood.rs:213, :185/:107)
 //   ln beta'  = prob_mapping + prob_ref + bias.prob_ref      (likelihood.rs:215)
 //   ln gamma' = prob_mismapping + prob_missed_allele + bias.prob_any   (likelihood.rs:186-188)
 //   K_r = max of the three; x = effective alt-sampling probability (likelihood.rs:43-53, :98-103).
-VLR_DEV_NOINLINE void read_coefficients(Ctx& c, int s) {
+VLR_DEV_NOINLINE void read_coefficients(Ctx& c_, int s) {
+    Ctx& c = warp_ctx(c_);
     const DevBatch* b = c.b;
     const int S = c.sc->S;
     const Art a = c.art;
@@ -447,7 +571,7 @@ VLR_DEV_NOINLINE void read_coefficients(Ctx& c, int s) {
             else if (strand == 2) sb_alt = r.pdo;
             else {
                 double rate = strand == 0 ? a.forward_rate : 1.0 - a.forward_rate;
-                sb_alt = log(rate) + ln_one_minus_exp(r.pdo);
+                sb_alt = m_log(rate) + ln_one_minus_exp(r.pdo);
             }
             // read orientation bias (read_orientation_bias.rs:17-29)
             double rob_alt = LN_05;
@@ -485,16 +609,16 @@ VLR_DEV_NOINLINE void read_coefficients(Ctx& c, int s) {
             } else if (K == neg_inf()) {
                 dead = true;
             } else {
-                al_ = exp(lnA - K);
-                be_ = exp(lnR - K);
-                ga_ = exp(lnC - K);
+                al_ = m_exp(lnA - K);
+                be_ = m_exp(lnR - K);
+                ga_ = m_exp(lnC - K);
                 ksum += K;
             }
             double* o = out + (int64_t)pos * 4;
             o[0] = al_;
             o[1] = be_;
             o[2] = ga_;
-            o[3] = exp(r.psa);
+            o[3] = -m_expm1(r.psa); // u_r = 1 - s_r, s_r = e^{prob_sample_alt}: exactly 0 when prob_sample_alt = 0
         }
         base += n_kept;
     }
@@ -509,54 +633,41 @@ VLR_DEV_NOINLINE void read_coefficients(Ctx& c, int s) {
     warp_sync();
 }
 
-// Pileup log-likelihood of sample s at (vaf, contaminant vaf): likelihood.rs:122-158 / :227-249.
-VLR_DEV double sample_likelihood(Ctx& c, int s, double vaf, double vaf_by) {
-    const vlr_sample_t& sm = c.sc->samples[s];
-    const int n = c.n_obs[s];
-    if (n == 0) return 0.0; // empty fold = ln 1
-    const double ksum = c.ksum[s];
-    if (ksum != ksum) return NAN;
-    c.n_pileup_evals++;
-    double rho = 1.0, iota = 0.0;
-    if (sm.contamination_by >= 0) {
-        rho = 1.0 - sm.contamination_fraction; // e^{purity}
-        iota = 1.0 - rho;                      // e^{impurity} (likelihood.rs:77-84)
-    }
-    // x = rho * xp + iota * xs with xp = (vaf == 1 ? 1 : vaf * s_r), y = 1 - x accordingly
-    const bool p1 = vaf == 1.0, s1 = vaf_by == 1.0;
-    const double X1 = (p1 ? 0.0 : rho * vaf) + ((iota != 0.0 && !s1) ? iota * vaf_by : 0.0);
-    const double X0 = (p1 ? rho : 0.0) + ((iota != 0.0 && s1) ? iota : 0.0);
-    const double Yp = (p1 ? 0.0 : rho * (1.0 - vaf)) + ((iota != 0.0 && !s1) ? iota * (1.0 - vaf_by) : 0.0);
-    const double Y0 = (p1 ? 0.0 : rho) + ((iota != 0.0 && !s1) ? iota : 0.0);
-    const double* co = c.coef + (int64_t)c.coef_off[s] * 4;
+// Product over the reads of one pileup of (alpha x + beta y + gamma), as mantissa in [1,2) per lane + binary exponent.
+// MODE 0: every read has prob_sample_alt = 0 (x, y are per-evaluation scalars); 1: per-read s_r <= 1; 2: some s_r > 1
+// (cap_numerical_overshoot per component, likelihood.rs:43-53). The arena holds [alpha, beta, gamma, s] per read.
+struct PileupArgs {
+    double xu, Yp, X1, X0, Y0, vaf, vaf_by, rho, iota;
+    bool p1, s1;
+};
+template <int MODE>
+VLR_DEV void pileup_product(const double2* __restrict__ co, int n, const PileupArgs& a, double& acc_out, int& ex_out,
+                            bool& zero_out, bool& overshoot_out) {
     double acc = 1.0;
-    int ex = 0;
+    int ex = 0, k = 0;
     bool zero = false, overshoot = false;
-    const bool s_one = c.s_one[s] != 0, s_gt1 = c.s_gt1[s] != 0;
-    const double xu = X1 + X0;
-    int k = 0;
     for (int r = lane_id(); r < n; r += LANES) {
-        const double al = co[4 * r], be = co[4 * r + 1], ga = co[4 * r + 2];
+        const double2 ab = co[2 * r];
+        const double2 gs = co[2 * r + 1];
         double t;
-        if (s_one) {
-            t = fma(al, xu, fma(be, Yp, ga));
-        } else if (!s_gt1) {
-            const double sr = co[4 * r + 3];
-            t = fma(al, fma(sr, X1, X0), fma(be, fma(-sr, X1, Y0), ga));
+        if (MODE == 0) {
+            t = fma(ab.x, a.xu, fma(ab.y, a.Yp, gs.x));
+        } else if (MODE == 1) {
+            const double sr = 1.0 - gs.y; // the arena keeps u_r = 1 - s_r
+            t = fma(ab.x, fma(sr, a.X1, a.X0), fma(ab.y, fma(-sr, a.X1, a.Y0), gs.x));
         } else {
-            // prob_sample_alt > 0: cap_numerical_overshoot applies per component (likelihood.rs:43-53)
-            const double sr = co[4 * r + 3];
-            double xp = p1 ? 1.0 : vaf * sr, xs = s1 ? 1.0 : vaf_by * sr;
+            const double sr = 1.0 - gs.y;
+            double xp = a.p1 ? 1.0 : a.vaf * sr, xs = a.s1 ? 1.0 : a.vaf_by * sr;
             if (xp > 1.0) {
-                if (log(xp) > NUMERICAL_EPSILON) overshoot = true;
+                if (m_log(xp) > NUMERICAL_EPSILON) overshoot = true;
                 xp = 1.0;
             }
             if (xs > 1.0) {
-                if (iota != 0.0 && log(xs) > NUMERICAL_EPSILON) overshoot = true;
+                if (a.iota != 0.0 && m_log(xs) > NUMERICAL_EPSILON) overshoot = true;
                 xs = 1.0;
             }
-            double x = rho * xp + iota * xs, y = rho * (1.0 - xp) + iota * (1.0 - xs);
-            t = fma(al, x, fma(be, y, ga));
+            double x = a.rho * xp + a.iota * xs, y = a.rho * (1.0 - xp) + a.iota * (1.0 - xs);
+            t = fma(ab.x, x, fma(ab.y, y, gs.x));
         }
         if (t < 1e-30) { // rare: keep the running product a normal number
             if (t <= 0.0) {
@@ -569,35 +680,90 @@ VLR_DEV double sample_likelihood(Ctx& c, int s, double vaf, double vaf_by) {
             }
         }
         acc *= t;
-        if (++k == 8) {
+        if (++k == 8) { // <= 8 factors >= 1e-30 each: still a normal number; pull the exponent out
             k = 0;
             int hi = d_hi(acc);
             ex += ((hi >> 20) & 0x7ff) - 1023;
             acc = d_make((hi & 0x800fffff) | (1023 << 20), d_lo(acc));
         }
     }
+    int hi = d_hi(acc);
+    ex += ((hi >> 20) & 0x7ff) - 1023;
+    acc_out = d_make((hi & 0x800fffff) | (1023 << 20), d_lo(acc));
+    ex_out = ex;
+    zero_out = zero;
+    overshoot_out = overshoot;
+}
+
+// Pileup log-likelihood of sample s at (vaf, contaminant vaf): likelihood.rs:122-158 / :227-249.
+VLR_DEV double sample_likelihood(Ctx& c, int s, double vaf, double vaf_by) {
+    const vlr_sample_t& sm = c.sc->samples[s];
+    const int n = c.n_obs[s];
+    if (n == 0) return 0.0; // empty fold = ln 1
+    const double ksum = c.ksum[s];
+    if (ksum != ksum) return NAN;
+    c.n_pileup_evals++;
+    PileupArgs a;
+    a.rho = 1.0;
+    a.iota = 0.0;
+    if (sm.contamination_by >= 0) {
+        a.rho = 1.0 - sm.contamination_fraction; // e^{purity}
+        a.iota = 1.0 - a.rho;                    // e^{impurity} (likelihood.rs:77-84)
+    }
+    // x = rho * xp + iota * xs with xp = (vaf == 1 ? 1 : vaf * s_r), y = 1 - x accordingly
+    a.vaf = vaf;
+    a.vaf_by = vaf_by;
+    a.p1 = vaf == 1.0;
+    a.s1 = vaf_by == 1.0;
+    const bool sec = a.iota != 0.0;
+    a.X1 = (a.p1 ? 0.0 : a.rho * vaf) + ((sec && !a.s1) ? a.iota * vaf_by : 0.0);
+    a.X0 = (a.p1 ? a.rho : 0.0) + ((sec && a.s1) ? a.iota : 0.0);
+    a.Yp = (a.p1 ? 0.0 : a.rho * (1.0 - vaf)) + ((sec && !a.s1) ? a.iota * (1.0 - vaf_by) : 0.0);
+    a.Y0 = (a.p1 ? 0.0 : a.rho) + ((sec && !a.s1) ? a.iota : 0.0);
+    a.xu = a.X1 + a.X0;
+    double acc;
+    int ex;
+    bool zero, overshoot;
+    const int mode = c.s_one[s] ? 0 : (c.s_gt1[s] ? 2 : 1);
+#ifndef VLR_HOST_EMU
+    if (c.coef_in_sm) { // the common case: coefficients in this warp's shared-memory arena -> LDS.128
+        const double2* co = reinterpret_cast<const double2*>(warp_coef_sm()) + (size_t)c.coef_off[s] * 2;
+        if (mode == 0) pileup_product<0>(co, n, a, acc, ex, zero, overshoot);
+        else if (mode == 1) pileup_product<1>(co, n, a, acc, ex, zero, overshoot);
+        else pileup_product<2>(co, n, a, acc, ex, zero, overshoot);
+    } else
+#endif
     {
-        int hi = d_hi(acc);
-        ex += ((hi >> 20) & 0x7ff) - 1023;
-        acc = d_make((hi & 0x800fffff) | (1023 << 20), d_lo(acc));
+        const double2* co = reinterpret_cast<const double2*>(c.coef) + (size_t)c.coef_off[s] * 2;
+        if (mode == 0) pileup_product<0>(co, n, a, acc, ex, zero, overshoot);
+        else if (mode == 1) pileup_product<1>(co, n, a, acc, ex, zero, overshoot);
+        else pileup_product<2>(co, n, a, acc, ex, zero, overshoot);
     }
     acc = w_mul_d(acc); // 32 mantissas in [1,2): < 2^32
     ex = w_sum_i(ex);
-    if (s_gt1 && w_any(overshoot)) c.status |= VLR_ST_OVERSHOOT;
+    if (mode == 2 && w_any(overshoot)) c.status |= VLR_ST_OVERSHOOT;
     if (w_any(zero) || ksum == neg_inf()) return neg_inf();
     if (acc != acc) {
         c.status |= VLR_ST_NAN;
         return NAN;
     }
-    return (log(acc) + (double)ex * LN_2) + ksum;
+    return (m_log(acc) + (double)ex * LN_2) + ksum;
 }
 
-VLR_DEV double cached_sample_likelihood(Ctx& c, int s, double vaf, double vaf_by) {
+VLR_DEV_NOINLINE double sample_likelihood_call(Ctx& c_, int s, double vaf, double vaf_by) {
+    Ctx& c = warp_ctx(c_);
+    return sample_likelihood(c, s, vaf, vaf_by);
+}
+
+// generic.rs:43-53 keeps an LRU of 10000 pileup likelihoods per sample; a VAF-tree walk revisits only the few most
+// recent (vaf, contaminant vaf) pairs of the outer levels, so LC_WAYS entries per sample catch the same hits.
+VLR_DEV_NOINLINE double cached_sample_likelihood(Ctx& c_, int s, double vaf, double vaf_by) {
+    Ctx& c = warp_ctx(c_);
     int n = c.lc_n[s];
     int ways = n < LC_WAYS ? n : LC_WAYS;
     for (int w = 0; w < ways; ++w)
         if (c.lc_k1[s][w] == vaf && c.lc_k2[s][w] == vaf_by) return c.lc_v[s][w];
-    double v = sample_likelihood(c, s, vaf, vaf_by);
+    double v = sample_likelihood_call(c, s, vaf, vaf_by);
     int slot = n % LC_WAYS;
     c.lc_k1[s][slot] = vaf;
     c.lc_k2[s][slot] = vaf_by;
@@ -615,7 +781,7 @@ VLR_DEV bool prior_semr(const Ctx& c, int s, double& out) { // prior.rs:250-257
     }
     double r = c.sc->samples[s].somatic_effective_mutation_rate;
     if (r != r) return false;
-    out = log(r * vtf(c));
+    out = m_log(r * vtf(c));
     return true;
 }
 VLR_DEV bool prior_het(const Ctx& c, double& out) { // prior.rs:263-270
@@ -625,10 +791,10 @@ VLR_DEV bool prior_het(const Ctx& c, double& out) { // prior.rs:263-270
     }
     double h = c.sc->heterozygosity;
     if (h != h) return false;
-    out = log(exp(log(h)) * vtf(c));
+    out = m_log(m_exp(m_log(h)) * vtf(c));
     return true;
 }
-VLR_DEV bool universe_contains(const Ctx& c, int s, double v) {
+VLR_DEV_NOINLINE bool universe_contains(const Ctx& c, int s, double v) {
     const vlr_sample_t& sm = c.sc->samples[s];
     for (int i = 0; i < sm.n_universe; ++i) {
         const vlr_spectrum_t& sp = c.sc->spectra[sm.universe_offset + i];
@@ -652,14 +818,14 @@ VLR_DEV double binomial_coeff(unsigned n, unsigned k) { // statrs factorial::bin
     for (unsigned i = 2; i <= n; ++i) fn *= (double)i;
     for (unsigned i = 2; i <= k; ++i) fk *= (double)i;
     for (unsigned i = 2; i <= n - k; ++i) fnk *= (double)i;
-    return floor(0.5 + exp(log(fn) - log(fk) - log(fnk)));
+    return floor(0.5 + m_exp(m_log(fn) - m_log(fk) - m_log(fnk)));
 }
 VLR_DEV_NOINLINE double prob_select(unsigned ploidy, unsigned source_alt, unsigned target_alt, unsigned target_ref) {
     unsigned draws = target_alt + target_ref, x = target_alt; // Hypergeometric(N = ploidy, K = source_alt, n = draws).pmf(x)
     double pmf = x > draws ? 0.0
                            : binomial_coeff(source_alt, x) * binomial_coeff(ploidy - source_alt, draws - x) /
                                  binomial_coeff(ploidy, draws);
-    return log(pmf);
+    return m_log(pmf);
 }
 VLR_DEV_NOINLINE double prob_mendelian_alt_counts(Ctx& c, unsigned sp0, unsigned sp1, unsigned tp, unsigned sa0, unsigned sa1,
                                          unsigned ta, double rate) { // prior.rs:600-678
@@ -695,7 +861,7 @@ VLR_DEV_NOINLINE double prob_mendelian_alt_counts(Ctx& c, unsigned sp0, unsigned
                     if (a1 + a2 <= ta) {
                         double p = prob_select(sp0, sa0, a1, p1 - a1) + prob_select(sp1, sa1, a2, p2 - a2);
                         int missing = (int)ta - (int)(a1 + a2);
-                        acc.add(p + log(rate) * (double)missing);
+                        acc.add(p + m_log(rate) * (double)missing);
                     }
         }
     if (!valid) {
@@ -706,7 +872,8 @@ VLR_DEV_NOINLINE double prob_mendelian_alt_counts(Ctx& c, unsigned sp0, unsigned
 }
 
 // prior.rs:298-384, recursion end: all germline VAFs chosen
-VLR_DEV_NOINLINE double prior_leaf(Ctx& c, const Ops& ev, const double* g) {
+VLR_DEV_NOINLINE double prior_leaf(Ctx& c_, const Ops& ev, const double* g) {
+    Ctx& c = warp_ctx(c_);
     const DevScenario* sc = c.sc;
     const int S = sc->S;
     double prob = 0.0, het;
@@ -720,11 +887,11 @@ VLR_DEV_NOINLINE double prior_leaf(Ctx& c, const Ops& ev, const double* g) {
             }
         }
         if (m > 0) {
-            prob = het - log((double)m);
+            prob = het - m_log((double)m);
         } else {
             Lse acc;
             acc.init();
-            for (unsigned i = 1; i <= n; ++i) acc.add(het - log((double)i));
+            for (unsigned i = 1; i <= n; ++i) acc.add(het - m_log((double)i));
             prob = ln_one_minus_exp(acc.value());
         }
     }
@@ -785,7 +952,8 @@ VLR_DEV_NOINLINE double prior_leaf(Ctx& c, const Ops& ev, const double* g) {
 
 // prior.rs:385-437: the recursion over germline VAF assignments, unrolled into an odometer. Nested ln_sum_exp of the
 // reference == one ln_sum_exp over the flattened product (rounding-level difference only).
-VLR_DEV_NOINLINE double prior_full(Ctx& c, const Ops& ev) {
+VLR_DEV_NOINLINE double prior_full(Ctx& c_, const Ops& ev) {
+    Ctx& c = warp_ctx(c_);
     const DevScenario* sc = c.sc;
     const int S = sc->S;
     int nchoice[MAXS], idx[MAXS];
@@ -840,7 +1008,8 @@ VLR_DEV_NOINLINE double prior_full(Ctx& c, const Ops& ev) {
 }
 
 // Prior::compute (prior.rs:718-761)
-VLR_DEV_NOINLINE double prior_compute(Ctx& c, const Ops& ev) {
+VLR_DEV_NOINLINE double prior_compute(Ctx& c_, const Ops& ev) {
+    Ctx& c = warp_ctx(c_);
     const DevScenario* sc = c.sc;
     if (!sc->full_prior && !sc->all_uniform) {
         bool absent = true;
@@ -890,7 +1059,7 @@ VLR_DEV double joint(Ctx& c, int od) {
         double lfc;
         if (a == 0.0 && b2 == 0.0) lfc = 0.0;
         else {
-            lfc = log2(a) - log2(b2);
+            lfc = m_log2(a) - m_log2(b2);
             if (lfc != lfc) c.status |= VLR_ST_NAN;
         }
         bool t;
@@ -943,13 +1112,17 @@ VLR_DEV double joint(Ctx& c, int od) {
     }
     return j;
 }
-VLR_DEV_NOINLINE double joint_call(Ctx& c, int od) { return joint(c, od); }
+VLR_DEV_NOINLINE double joint_call(Ctx& c_, int od) {
+    Ctx& c = warp_ctx(c_);
+    return joint(c, od);
+}
 
 // ------------------------------------------------------------------------------------------------ density
 VLR_DEV_NOINLINE double density(Ctx& c, int ni, int od, int level);
 
 // Value of the subtree below `node` for the operands c.ops[od] (the `subdensity` closure of generic.rs:199-231).
-VLR_DEV_NOINLINE double subdensity(Ctx& c, const vlr_node_t& node, int od, int level) {
+VLR_DEV_NOINLINE double subdensity(Ctx& c_, const vlr_node_t& node, int od, int level) {
+    Ctx& c = warp_ctx(c_);
     double p;
     if (node.n_children == 0) p = joint_call(c, od);
     else if (node.n_children > 1) {
@@ -1004,7 +1177,8 @@ VLR_DEV void ops_push(Ops& o, int sample, double vaf, bool discrete) {
 }
 
 // ln_simpsons_integrate_exp (rust-bio): interior points first, then the two ends
-VLR_DEV_NOINLINE double integrate_simpson(Ctx& c, const vlr_node_t& node, int od, double a, double b, int n, int level) {
+VLR_DEV_NOINLINE double integrate_simpson(Ctx& c_, const vlr_node_t& node, int od, double a, double b, int n, int level) {
+    Ctx& c = warp_ctx(c_);
     Lse acc;
     acc.init();
     const double step = (b - a) / (double)(n - 1);
@@ -1013,7 +1187,7 @@ VLR_DEV_NOINLINE double integrate_simpson(Ctx& c, const vlr_node_t& node, int od
         if (j < n - 2) {
             const int i = j + 1;
             x = a + step * (double)i;
-            lw = log((double)(2 + (i % 2) * 2));
+            lw = m_log((double)(2 + (i % 2) * 2));
         } else {
             x = (j == n - 2) ? a : b;
         }
@@ -1021,116 +1195,19 @@ VLR_DEV_NOINLINE double integrate_simpson(Ctx& c, const vlr_node_t& node, int od
         ops_push(c.ops[od + 1], node.sample, x, false);
         acc.add(subdensity(c, node, od + 1, level + 1) + lw);
     }
-    return acc.value() + log(b - a) - log((double)(n - 1)) - log(3.0);
+    return acc.value() + m_log(b - a) - m_log((double)(n - 1)) - m_log(3.0);
 }
 
-// utils/adaptive_integration.rs:25-141 as a small state machine with ONE evaluation site (so the leaf evaluation
-// chain can be inlined exactly once). Visit order equals the reference's: min, max; per iteration middle, m1, m2;
-// then the abandoned-arm midpoint and the 3 + 3 points around the optimum. Points are appended to the per-level grid
-// (duplicates sort next to each other and form zero-width trapezoids); argmax ties: ascending x, first maximum.
-template <bool LEAF>
-VLR_DEV double integrate_adaptive_impl(Ctx& c, const vlr_node_t& node, int od, double min_point, double max_point,
-                                       double res, int level) {
+// ln_trapezoidal_integrate_grid_exp over the n visited points of `level` (rust-bio): rank sort with
+// lanes over points, then lanes over intervals and one warp-wide log-sum-exp.
+VLR_DEV_NOINLINE double grid_trapezoid(Ctx& c_, int level, int n) {
+    Ctx& c = warp_ctx(c_);
+    const int lane = lane_id();
     double* gx = c.ws->grid_x[level];
     double* gf = c.ws->grid_f[level];
-    const int lane = lane_id();
-    int n = 0;
-    bool overflow = false;
-    int phase = 0, i = 0, k = 2;
-    double left = min_point, right = max_point, f_left = 0.0, f_right = 0.0;
-    double middle = 0.0, first_middle = 0.0, m1 = 0.0, m2 = 0.0, f_m1 = 0.0, f_m2 = 0.0;
-    double xlo = 0.0, xstep_lo = 0.0, xstep_hi = 0.0, x_aband = 0.0;
-    bool have_middle = false;
-    for (;;) {
-        // ---- next abscissa
-        double x;
-        if (phase == 0) x = i == 0 ? min_point : max_point;
-        else if (phase == 1) x = i == 0 ? middle : (i == 1 ? m1 : m2);
-        else x = i == 0 ? x_aband : (i <= 3 ? xlo + xstep_lo * (double)(i - 1) : middle + xstep_hi * (double)(i - 3));
-        // ---- the evaluation site
-        c.ops[od + 1] = c.ops[od];
-        ops_push(c.ops[od + 1], node.sample, x, false);
-        double f;
-        if (LEAF) {
-            f = joint(c, od + 1);
-            if (f != f) c.status |= VLR_ST_NAN;
-        } else {
-            f = subdensity(c, node, od + 1, level + 1);
-        }
-        if (n < GRID_CAP) {
-            if (lane == 0) {
-                gx[n] = x;
-                gf[n] = f;
-            }
-            n++;
-        } else {
-            overflow = true;
-        }
-        // ---- consume
-        if (phase == 0) {
-            if (i == 0) f_left = f;
-            else f_right = f;
-        } else if (phase == 1) {
-            if (i == 1) f_m1 = f;
-            else if (i == 2) f_m2 = f;
-        }
-        if (++i < k) continue;
-        i = 0;
-        if (phase == 1) {
-            if (!have_middle) first_middle = middle;
-            have_middle = true;
-            // argmax over [left, m1, m2, right] (the middle itself is not a candidate); neighbours become the new bounds
-            int idx = 0;
-            double fb = f_left;
-            if (f_m1 > fb) {
-                idx = 1;
-                fb = f_m1;
-            }
-            if (f_m2 > fb) {
-                idx = 2;
-                fb = f_m2;
-            }
-            if (f_right > fb) idx = 3;
-            // position() in the reference resolves duplicate abscissae to the first equal x
-            if (idx == 3 && right == m2) idx = 2;
-            if (idx == 2 && m2 == m1) idx = 1;
-            if (idx == 1 && m1 == left) idx = 0;
-            double nl, nfl, nr, nfr;
-            if (idx == 0) {
-                nl = left; nfl = f_left; nr = m1; nfr = f_m1;
-            } else if (idx == 1) {
-                nl = left; nfl = f_left; nr = m2; nfr = f_m2;
-            } else if (idx == 2) {
-                nl = m1; nfl = f_m1; nr = right; nfr = f_right;
-            } else {
-                nl = m2; nfl = f_m2; nr = right; nfr = f_right;
-            }
-            left = nl; f_left = nfl; right = nr; f_right = nfr;
-        } else if (phase == 2) {
-            break;
-        }
-        // while (((right - left) >= res && left < right) || middle.is_none())
-        if (!overflow && ((((right - left) >= res) && left < right) || !have_middle)) {
-            phase = 1;
-            k = 3;
-            middle = (right + left) / 2.0;
-            m1 = (middle + left) / 2.0;
-            m2 = (right + middle) / 2.0;
-        } else {
-            phase = 2;
-            k = 7;
-            x_aband = (middle < first_middle) ? (max_point + first_middle) / 2.0 : (first_middle + min_point) / 2.0;
-            xlo = fmax(middle - (res * 3.0), min_point);
-            xstep_lo = (middle - xlo) / 3.0;
-            const double xhi = fmin(middle + (res * 3.0), max_point);
-            xstep_hi = (xhi - middle) / 3.0;
-        }
-    }
-    if (overflow) c.status |= VLR_ST_GRID_OVERFLOW;
-    warp_sync();
-    // sort by x (rank sort, lanes over points), then ln_trapezoidal_integrate_grid_exp with lanes over intervals
     double* sx = c.ws->sort_x;
     double* sf = c.ws->sort_f;
+    warp_sync();
     for (int a = lane; a < n; a += LANES) {
         double xi = gx[a];
         int rank = 0;
@@ -1147,7 +1224,7 @@ VLR_DEV double integrate_adaptive_impl(Ctx& c, const vlr_node_t& node, int od, d
     int q = 0;
     for (int a = lane; a + 1 < n; a += LANES, ++q) {
         double dx = sx[a + 1] - sx[a];
-        double t = (dx > 0.0) ? ln_add_exp(sf[a], sf[a + 1]) + log(dx) - LN_2 : neg_inf();
+        double t = (dx > 0.0) ? ln_add_exp(sf[a], sf[a + 1]) + m_log(dx) - LN_2 : neg_inf();
         if (t != t) t = INFINITY; // poison through the max
         tloc[q] = t;
         tmax = fmax(tmax, t);
@@ -1161,17 +1238,333 @@ VLR_DEV double integrate_adaptive_impl(Ctx& c, const vlr_node_t& node, int od, d
     }
     double ssum = 0.0;
     for (int a = 0; a < q; ++a)
-        if (tloc[a] != neg_inf()) ssum += exp(tloc[a] - tmax);
+        if (tloc[a] != neg_inf()) ssum += m_exp(tloc[a] - tmax);
     ssum = w_sum_d(ssum);
-    return tmax + log(ssum);
+    return tmax + m_log(ssum);
 }
-VLR_DEV_NOINLINE double integrate_adaptive_leaf(Ctx& c, const vlr_node_t& node, int od, double a, double b, double res,
+
+// Generic adaptive integration: every point goes through subdensity()/joint() like in the reference.
+VLR_DEV_NOINLINE double integrate_adaptive_generic(Ctx& c_, const vlr_node_t& node, int od, double a, double b, double res,
+                                                   int level) {
+    Ctx& c = warp_ctx(c_);
+    double* gx = c.ws->grid_x[level];
+    double* gf = c.ws->grid_f[level];
+    Adaptive& st = c.ad[level];
+    st.init(a, b, res);
+    int n = 0;
+    bool overflow = false;
+    double* xs = c.xs[level];
+    double* fs = c.fs[level];
+    for (;;) {
+        const int k = st.points(xs);
+        for (int i = 0; i < k; ++i) {
+            c.ops[od + 1] = c.ops[od];
+            ops_push(c.ops[od + 1], node.sample, xs[i], false);
+            double f = subdensity(c, node, od + 1, level + 1);
+            fs[i] = f;
+            if (n < GRID_CAP) {
+                gx[n] = xs[i]; // every lane stores the same value: no divergence
+                gf[n] = f;
+                n++;
+            } else {
+                overflow = true;
+            }
+        }
+        if (!st.consume(xs, fs, overflow)) break;
+    }
+    if (overflow) c.status |= VLR_ST_GRID_OVERFLOW;
+    return grid_trapezoid(c, level, n);
+}
+
+// ---- leaf fast path -----------------------------------------------------------------------------------------
+// The NB abscissae of a batch are evaluated TOGETHER: one pass over the reads with NB independent product chains, NB
+// interleaved shuffle reductions and one log per point distributed over lanes - the instruction-level parallelism a
+// single-point evaluation lacks. The pieces are separate out-of-line functions and their uniform state lives in
+// shared memory (Ctx::leaf, ::ad, ::xs, ::fs) so that the per-point code stays small enough for the instruction
+// caches and the per-lane stack frames stay small enough for L1 (both were measured bottlenecks, profiles/).
+
+// Product over the reads for the NB points: per read x_r = xu - u_r X1, y_r = Yp + u_r X1 with u_r = 1 - s_r
+// (u_r = 0, i.e. prob_sample_alt = 0, reproduces the scalar xu / Yp exactly), term = alpha x_r + beta y_r + gamma.
+template <bool SM>
+VLR_DEV bool leaf_products(const LeafDep& d, const double* xu, const double* Yp, const double* X1, double* acc_out,
+                           int* ex_out) {
+    double acc[NB];
+    int ex[NB];
+    bool slow = false;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        acc[b] = 1.0;
+        ex[b] = 0;
+    }
+    int k = 0;
+    const double2* co = d.co;
+#ifndef VLR_HOST_EMU
+    if (SM) co = reinterpret_cast<const double2*>(vlr_smem + (__cvta_generic_to_shared(d.co) - __cvta_generic_to_shared(vlr_smem)));
+#endif
+    const int n = d.n;
+#pragma unroll 1
+    for (int r = lane_id(); r < n; r += LANES) {
+        const double2 ab = co[2 * r];
+        const double2 gu = co[2 * r + 1];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const double xr = fma(-gu.y, X1[b], xu[b]);
+            const double yr = fma(gu.y, X1[b], Yp[b]);
+            acc[b] *= fma(ab.x, xr, fma(ab.y, yr, gu.x));
+        }
+        if (++k == 4) { // <= 4 factors between exponent pulls; a tiny (< 1e-60) or zero factor takes the careful path
+            k = 0;
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                slow = slow || !(acc[b] >= 1e-240);
+                const int hi = d_hi(acc[b]);
+                ex[b] += ((hi >> 20) & 0x7ff) - 1023;
+                acc[b] = d_make((hi & 0x800fffff) | (1023 << 20), d_lo(acc[b]));
+            }
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        slow = slow || !(acc[b] >= 1e-240);
+        const int hi = d_hi(acc[b]);
+        ex_out[b] = ex[b] + ((hi >> 20) & 0x7ff) - 1023;
+        acc_out[b] = d_make((hi & 0x800fffff) | (1023 << 20), d_lo(acc[b]));
+    }
+    return slow;
+}
+
+// c.lh[b] += ln-likelihood of dependent pileup `which` at the NB points x[] (x points into shared memory)
+template <bool SM>
+VLR_DEV void leaf_dep_likelihood_impl(Ctx& c, int which, const double* x) {
+    const LeafDep& d = c.leaf.dep[which];
+    if (d.n == 0) return; // empty fold = ln 1
+    const double ksum = d.ksum;
+    if (ksum != ksum) {
+        for (int b = 0; b < NB; ++b) c.lh[b] = NAN;
+        return;
+    }
+    double xu[NB], Yp[NB], X1[NB];
+    {
+        const double rho = d.rho, iota = d.iota, fv = d.fixed_vaf, fb = d.fixed_by;
+        const bool vx = d.vaf_is_x, bx = d.by_is_x, hb = d.has_by, sec = iota != 0.0;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) { // x = rho xp + iota xs with xp = (vaf == 1 ? 1 : vaf s_r); see sample_likelihood
+            const double xb = x[b];
+            const double vaf = vx ? xb : fv;
+            const double vby = hb ? (bx ? xb : fb) : 0.0;
+            const bool p1 = vaf == 1.0, s1 = vby == 1.0;
+            X1[b] = (p1 ? 0.0 : rho * vaf) + ((sec && !s1) ? iota * vby : 0.0);
+            const double X0 = (p1 ? rho : 0.0) + ((sec && s1) ? iota : 0.0);
+            Yp[b] = (p1 ? 0.0 : rho * (1.0 - vaf)) + ((sec && !s1) ? iota * (1.0 - vby) : 0.0);
+            xu[b] = X1[b] + X0;
+        }
+    }
+    double acc[NB];
+    int ex[NB];
+    const bool slow = leaf_products<SM>(d, xu, Yp, X1, acc, ex);
+    if (w_any(slow)) { // zero / denormal-range factors: the careful single-point evaluation handles them
+        for (int b = 0; b < NB; ++b) {
+            const double vaf = d.vaf_is_x ? x[b] : d.fixed_vaf;
+            const double vby = d.has_by ? (d.by_is_x ? x[b] : d.fixed_by) : 0.0;
+            c.lh[b] += sample_likelihood_call(c, d.s, vaf, vby);
+        }
+        return;
+    }
+#ifdef VLR_HOST_EMU
+    for (int b = 0; b < NB; ++b) c.lh[b] += (m_log(acc[b]) + (double)ex[b] * LN_2) + ksum;
+#else
+    // interleaved butterflies: NB independent shuffle chains
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) {
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            acc[b] *= __shfl_xor_sync(FULL, acc[b], o);
+            ex[b] += __shfl_xor_sync(FULL, ex[b], o);
+        }
+    }
+    // one log per point: lane b takes point b, then lanes 0..NB-1 add into the shared accumulators
+    const int lane = lane_id();
+    double mine = acc[0];
+    int mex = ex[0];
+#pragma unroll
+    for (int b = 1; b < NB; ++b)
+        if (lane == b) {
+            mine = acc[b];
+            mex = ex[b];
+        }
+    const double l = (m_log(mine) + (double)mex * LN_2) + ksum;
+    if (lane < NB) c.lh[lane] += l;
+    warp_sync();
+#endif
+}
+VLR_DEV_NOINLINE void leaf_dep_likelihood_sm(Ctx& c_, int which, const double* x) {
+    leaf_dep_likelihood_impl<true>(warp_ctx(c_), which, x);
+}
+VLR_DEV_NOINLINE void leaf_dep_likelihood_gl(Ctx& c_, int which, const double* x) {
+    leaf_dep_likelihood_impl<false>(warp_ctx(c_), which, x);
+}
+
+// Decides whether the fast path can serve the integration of `node` (a leaf) and hoists its constants into c.leaf.
+VLR_DEV_NOINLINE bool leaf_setup(Ctx& c_, const vlr_node_t& node, int od, double a, double b) {
+    Ctx& c = warp_ctx(c_);
+    const DevScenario* sc = c.sc;
+    const int S = sc->S;
+    const int t = node.sample;
+    LeafFast& L = c.leaf;
+    if (c.ops[od].lfc_mask != 0) return false;
+    int n_dep = 0;
+    for (int s = 0; s < S; ++s) {
+        const int by = sc->samples[s].contamination_by;
+        if (s != t && by != t) continue;
+        if (n_dep == 2 || c.s_gt1[s]) return false;
+        LeafDep& d = L.dep[n_dep];
+        n_dep++;
+        d.s = s;
+        d.co = reinterpret_cast<const double2*>(c.coef) + (size_t)c.coef_off[s] * 2;
+        d.ksum = c.ksum[s];
+        d.n = c.n_obs[s];
+        d.rho = 1.0;
+        d.iota = 0.0;
+        d.has_by = by >= 0;
+        if (by >= 0) {
+            d.rho = 1.0 - sc->samples[s].contamination_fraction;
+            d.iota = 1.0 - d.rho;
+        }
+        d.vaf_is_x = s == t;
+        d.by_is_x = by == t;
+        d.fixed_vaf = c.ops[od].vaf[s];
+        d.fixed_by = by >= 0 ? c.ops[od].vaf[by] : 0.0;
+    }
+    L.n_dep = n_dep;
+    L.coef_in_sm = c.coef_in_sm != 0;
+    L.uniform = sc->all_uniform != 0;
+    L.t_ploidy0 = sc->samples[t].ploidy == 0;
+    double lh_const = 0.0, prior_const = 0.0;
+    const Ops& base = c.ops[od];
+    for (int s = 0; s < S; ++s) {
+        const int by = sc->samples[s].contamination_by;
+        if (s == t || by == t) continue;
+        lh_const += cached_sample_likelihood(c, s, base.vaf[s], by >= 0 ? base.vaf[by] : 0.0);
+    }
+    bool per_point = true;
+    if (L.uniform) { // flat prior inside every sample's universe (prior.rs:385-406)
+        for (int s = 0; s < S; ++s) {
+            if (s == t) continue;
+            const double v = base.vaf[s];
+            if ((sc->samples[s].ploidy == 0 && v != 0.0) || !universe_contains(c, s, v)) prior_const = neg_inf();
+        }
+        // one Range spectrum of t's universe covering [a, b] covers every abscissa of this integration
+        const vlr_sample_t& sm = sc->samples[t];
+        for (int i = 0; i < sm.n_universe; ++i) {
+            const vlr_spectrum_t& sp = sc->spectra[sm.universe_offset + i];
+            if (sp.kind != VLR_SPECTRUM_RANGE) continue;
+            Range r{sp.start, sp.end, sp.left_exclusive != 0, sp.right_exclusive != 0};
+            if (range_contains(r, a) && range_contains(r, b) && !(L.t_ploidy0 && b != 0.0)) per_point = false;
+        }
+    }
+    L.lh_const = lh_const;
+    L.prior_const = prior_const;
+    L.prior_per_point = per_point;
+    return true;
+}
+
+// prior per abscissa when it is not a loop constant (non-uniform priors, universes with holes)
+VLR_DEV_NOINLINE double leaf_prior_point(Ctx& c_, int t, int od, double x) {
+    Ctx& c = warp_ctx(c_);
+    if (c.leaf.uniform) {
+        if ((c.leaf.t_ploidy0 && x != 0.0) || !universe_contains(c, t, x)) return neg_inf();
+        return c.leaf.prior_const;
+    }
+    c.ops[od + 1] = c.ops[od];
+    ops_push(c.ops[od + 1], t, x, false);
+    return prior_compute(c, c.ops[od + 1]);
+}
+
+// base-event log for the AFD (the fast-path twin of the recording in joint())
+VLR_DEV_NOINLINE void leaf_record(Ctx& c_, int t, int od, double x, double f) {
+    Ctx& c = warp_ctx(c_);
+    const int S = c.sc->S;
+    if (c.n_rec < (uint32_t)BE_CAP) {
+        double* e = c.be + (int64_t)c.n_rec * (2 + S);
+        e[0] = f; // every lane stores the same values
+        e[1] = d_make(0, (int)(c.ops[od].disc_mask & ~(1u << t)));
+        for (int s = 0; s < S; ++s) e[2 + s] = s == t ? x : c.ops[od].vaf[s];
+        c.n_rec++;
+    } else {
+        c.status |= VLR_ST_BASE_EVENTS_OVERFLOW;
+    }
+}
+
+VLR_DEV_NOINLINE double integrate_adaptive_leaf(Ctx& c_, const vlr_node_t& node, int od, double a, double b, double res,
                                                 int level) {
-    return integrate_adaptive_impl<true>(c, node, od, a, b, res, level);
-}
-VLR_DEV_NOINLINE double integrate_adaptive_inner(Ctx& c, const vlr_node_t& node, int od, double a, double b, double res,
-                                                 int level) {
-    return integrate_adaptive_impl<false>(c, node, od, a, b, res, level);
+    Ctx& c = warp_ctx(c_);
+    if (!leaf_setup(c, node, od, a, b)) return integrate_adaptive_generic(c, node, od, a, b, res, level);
+    const int t = node.sample;
+    double* gx = c.ws->grid_x[level];
+    double* gf = c.ws->grid_f[level];
+    double* xs = c.xs[level];
+    double* fs = c.fs[level];
+    Adaptive& st = c.ad[level];
+    st.init(a, b, res);
+    int n = 0;
+    bool overflow = false, have_best = false;
+    double best_f = 0.0, best_x = 0.0;
+    const bool record = c.be != nullptr && c.art.id == 0;
+    const bool per_point = c.leaf.prior_per_point;
+    const bool in_sm = c.leaf.coef_in_sm, two = c.leaf.n_dep > 1;
+    const double lh_const = c.leaf.lh_const, prior_const = c.leaf.prior_const;
+    for (;;) {
+        const int k = st.points(xs);
+        // batches of exactly NB (short batches are padded with a repeated abscissa)
+        if (k == 2) xs[2] = xs[3] = xs[1];
+        else if (k == 3) xs[3] = xs[2];
+        else xs[7] = xs[6];
+        for (int off = 0; off < k; off += NB) {
+            c.lh[0] = c.lh[1] = c.lh[2] = c.lh[3] = lh_const;
+            if (in_sm) {
+                leaf_dep_likelihood_sm(c, 0, xs + off);
+                if (two) leaf_dep_likelihood_sm(c, 1, xs + off);
+            } else {
+                leaf_dep_likelihood_gl(c, 0, xs + off);
+                if (two) leaf_dep_likelihood_gl(c, 1, xs + off);
+            }
+            const int m = (k - off) < NB ? (k - off) : NB;
+            for (int i = 0; i < m; ++i) {
+                const double x = xs[off + i];
+                const double f = (per_point ? leaf_prior_point(c, t, od, x) : prior_const) + c.lh[i];
+                fs[off + i] = f;
+                if (f != f) c.status |= VLR_ST_NAN;
+                if (record) leaf_record(c, t, od, x, f);
+                if (!have_best || f > best_f) { // first maximum in visit order, merged into the MAP slot at the end
+                    have_best = true;
+                    best_f = f;
+                    best_x = x;
+                }
+                if (n < GRID_CAP) {
+                    gx[n] = x;
+                    gf[n] = f;
+                    n++;
+                } else {
+                    overflow = true;
+                }
+            }
+        }
+        c.n_base += (uint32_t)k;
+        if (!st.consume(xs, fs, overflow)) break;
+    }
+    {
+        const int S = c.sc->S;
+        const int slot = c.cur_slot;
+        if (have_best && (!c.map_set[slot] || best_f > c.map_joint[slot])) { // joint()'s MAP bookkeeping, batched
+            c.map_set[slot] = 1;
+            c.map_joint[slot] = best_f;
+            c.map_cfg[slot] = c.art.id;
+            c.map_disc[slot] = c.ops[od].disc_mask & ~(1u << t);
+            for (int s = 0; s < S; ++s) c.map_vaf[slot][s] = s == t ? best_x : c.ops[od].vaf[s];
+        }
+    }
+    if (overflow) c.status |= VLR_ST_GRID_OVERFLOW;
+    return grid_trapezoid(c, level, n);
 }
 
 VLR_DEV bool iupac_contains(int mask, int base) {
@@ -1187,7 +1580,8 @@ VLR_DEV bool iupac_contains(int mask, int base) {
 
 // GenericPosterior::density (generic.rs:191-422). c.ops[od] are the operands so far (modified in place where the
 // reference passes its &mut on, copied to c.ops[od + 1] where it clones).
-VLR_DEV_NOINLINE double density(Ctx& c, int ni, int od, int level) {
+VLR_DEV_NOINLINE double density(Ctx& c_, int ni, int od, int level) {
+    Ctx& c = warp_ctx(c_);
     const DevScenario* sc = c.sc;
     const vlr_node_t& node = sc->nodes[ni];
     switch (node.kind) {
@@ -1254,12 +1648,12 @@ VLR_DEV_NOINLINE double density(Ctx& c, int ni, int od, int level) {
     if (!(min_vaf <= max_vaf)) c.status |= VLR_ST_NAN; // assert in the reference
     if ((max_vaf - min_vaf) < res) return integrate_simpson(c, node, od, min_vaf, max_vaf, 3, level);
     if (n_obs < 5) return integrate_simpson(c, node, od, min_vaf, max_vaf, 11, level);
-    if (level >= WS_LEVELS) {
+    if (level >= MAXS) {
         c.status |= VLR_ST_GRID_OVERFLOW;
         return neg_inf();
     }
     if (node.n_children == 0) return integrate_adaptive_leaf(c, node, od, min_vaf, max_vaf, res, level);
-    return integrate_adaptive_inner(c, node, od, min_vaf, max_vaf, res, level);
+    return integrate_adaptive_generic(c, node, od, min_vaf, max_vaf, res, level);
 }
 
 // ------------------------------------------------------------------------------------------------ locus driver
@@ -1315,7 +1709,8 @@ VLR_DEV_NOINLINE bool node_contains(const DevScenario* sc, int ni, const double*
 
 // Allele frequency distribution per sample (calling.rs:891-928) from the recorded artifact-free base events:
 // those compatible with the best event (ignoring the sample's own node) whose other samples equal the MAP.
-VLR_DEV_NOINLINE void afd_pass(Ctx& c, int best_scen, int map_slot, double marginal) {
+VLR_DEV_NOINLINE void afd_pass(Ctx& c_, int best_scen, int map_slot, double marginal) {
+    Ctx& c = warp_ctx(c_);
     const DevScenario* sc = c.sc;
     const DevResults* res = c.res;
     const int S = sc->S;
@@ -1476,7 +1871,8 @@ VLR_DEV void process_locus(const DevScenario* sc, const DevBatch* b, const DevRe
         }
         return;
     }
-    if (c.coef_total <= sm_reads) c.coef = coef_sm;
+    c.coef_in_sm = c.coef_total <= sm_reads;
+    if (c.coef_in_sm) c.coef = coef_sm;
 
     // joint probability per universe event: plain events get ln 0.5, twins ln 0.5 + ln(1/#configs) (generic.rs:437-441)
     Lse* ev_plain = c.ev_plain;
@@ -1485,7 +1881,7 @@ VLR_DEV void process_locus(const DevScenario* sc, const DevBatch* b, const DevRe
         ev_plain[e].init();
         ev_twin[e].init();
     }
-    const double twin_prior = plan.n_twins > 0 ? LN_05 + log(1.0 / (double)plan.n_twins) : neg_inf();
+    const double twin_prior = plan.n_twins > 0 ? LN_05 + m_log(1.0 / (double)plan.n_twins) : neg_inf();
     for (int ci = 0; ci <= plan.n_surviving; ++ci) {
         c.art.id = ci == 0 ? 0 : plan.surviving[ci - 1];
         c.art.forward_rate = plan.forward_rate;

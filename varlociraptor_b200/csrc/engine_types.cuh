@@ -11,6 +11,9 @@
 #ifdef VLR_HOST_EMU
 #define VLR_DEV inline
 #define VLR_DEV_NOINLINE
+struct alignas(16) double2 {
+    double x, y;
+};
 #else
 #define VLR_DEV __device__ __forceinline__
 #define VLR_DEV_NOINLINE __device__ __noinline__
@@ -19,6 +22,17 @@
 namespace vlrcore {
 
 constexpr int WS_LEVELS = VLR_MAX_SAMPLES; // nested integration levels with scratch grids
+#ifndef VLR_WARPS_PER_CTA
+#define VLR_WARPS_PER_CTA 8
+#endif
+#ifndef VLR_MIN_CTAS
+#define VLR_MIN_CTAS 2
+#endif
+constexpr int WARPS_PER_CTA = VLR_WARPS_PER_CTA;
+constexpr int SM_READS = 256; // shared-memory coefficient arena per warp, in reads (8 KB): 2 x 100 reads fit
+#ifndef VLR_HOST_EMU
+extern __shared__ __align__(16) unsigned char vlr_smem[];
+#endif
 constexpr int NCFG = VLR_N_ARTIFACT_CONFIGS;
 constexpr int GRID_CAP = 128;   // points per adaptive integration (res >= ~1e-5)
 constexpr int LC_WAYS = 4;      // per-sample pileup-likelihood cache entries
@@ -146,6 +160,16 @@ struct WarpWs {
     double afd_p[AFD_TMP];
 };
 
+// ------------------------------------------------------------------------------------------------ math
+// Out-of-line fp64 transcendentals: CUDA inlines ~50-100 instructions per call site, and with dozens of call sites
+// the kernel outgrows the instruction caches (ncu: stall_no_instruction dominated the first versions). One copy each.
+VLR_DEV_NOINLINE double m_log(double x) { return log(x); }
+VLR_DEV_NOINLINE double m_exp(double x) { return exp(x); }
+VLR_DEV_NOINLINE double m_log1p(double x) { return log1p(x); }
+VLR_DEV_NOINLINE double m_expm1(double x) { return expm1(x); }
+VLR_DEV_NOINLINE double m_log2(double x) { return log2(x); }
+VLR_DEV_NOINLINE double m_exp2(double x) { return exp2(x); }
+
 // ------------------------------------------------------------------------------------------------ LogProb helpers
 // (rust-bio LogProb semantics)
 VLR_DEV_NOINLINE double ln_add_exp(double a, double b) {
@@ -159,15 +183,15 @@ VLR_DEV_NOINLINE double ln_add_exp(double a, double b) {
     }
     if (p0 == neg_inf()) return neg_inf();
     if (p1 == neg_inf()) return p0;
-    return p0 + log1p(exp(p1 - p0));
+    return p0 + m_log1p(m_exp(p1 - p0));
 }
 VLR_DEV_NOINLINE double ln_one_minus_exp(double p) {
-    if (p < -0.693) return log1p(-exp(p));
-    return log(-expm1(p));
+    if (p < -0.693) return m_log1p(-m_exp(p));
+    return m_log(-m_expm1(p));
 }
 // streaming ln_sum_exp accumulator (differs from the reference's max-first two-pass form by rounding only)
 struct Lse {
-    double m, s; // max so far, sum of exp(x - m)
+    double m, s; // max so far, sum of m_exp(x - m)
     int n;
     VLR_DEV void init() {
         m = neg_inf();
@@ -182,20 +206,20 @@ struct Lse {
             return;
         }
         if (x > m) {
-            s = (m == neg_inf()) ? 1.0 : s * exp(m - x) + 1.0;
+            s = (m == neg_inf()) ? 1.0 : s * m_exp(m - x) + 1.0;
             m = x;
         } else {
-            s += exp(x - m);
+            s += m_exp(x - m);
         }
     }
     VLR_DEV double value() const {
         if (m == neg_inf() || m != m || m == INFINITY) return m;
-        return m + log1p(s - 1.0);
+        return m + m_log1p(s - 1.0);
     }
 };
 
 VLR_DEV int kass_raftery(double m1, double m2) {
-    // BayesFactor::new(m1, m2) = exp(m1 - m2) compared with 1, 3, 20, 150; evaluated in log space.
+    // BayesFactor::new(m1, m2) = m_exp(m1 - m2) compared with 1, 3, 20, 150; evaluated in log space.
     double d = m1 - m2;
     if (d <= 0.0) return 0;
     if (d <= LN_3) return 1;
@@ -279,7 +303,7 @@ VLR_DEV int lfc_invert_cmp(int cmp) {
     }
 }
 VLR_DEV Range lfc_infer_bounds(int cmp, double value, double vaf) {
-    double proj = vaf / exp2(value);
+    double proj = vaf / m_exp2(value);
     if (proj < 0.0 || proj > 1.0) return range_empty();
     switch (cmp) {
     case VLR_CMP_EQ: return Range{proj, proj, false, false};

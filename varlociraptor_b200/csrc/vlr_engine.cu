@@ -33,7 +33,6 @@ using namespace vlrcore;
 
 namespace {
 
-constexpr int WARPS_PER_CTA = 8;
 constexpr int THREADS = WARPS_PER_CTA * 32;
 constexpr int NBUF = 3;
 
@@ -51,13 +50,11 @@ struct KernelParams {
     int64_t be_stride; // doubles per warp
 };
 
-constexpr int SM_READS = 256; // 8 KB of coefficients per warp: covers 100 reads/sample x 2 samples (config 2)
 
 // Shared memory per CTA: [WARPS_PER_CTA x Ctx (uniform per-warp state)] [WARPS_PER_CTA x coefficient arena].
 #define VLR_DEFINE_KERNEL(NS)                                                                                     \
-    __global__ void __launch_bounds__(THREADS, 2) vlr_call_kernel_##NS(const __grid_constant__ KernelParams p) {  \
-        extern __shared__ __align__(16) unsigned char vlr_smem[];                                                 \
-        const int w = threadIdx.x >> 5;                                                                           \
+    __global__ void __launch_bounds__(THREADS, VLR_MIN_CTAS) vlr_call_kernel_##NS(const __grid_constant__ KernelParams p) {  \
+                const int w = threadIdx.x >> 5;                                                                           \
         const int gw = blockIdx.x * WARPS_PER_CTA + w;                                                            \
         NS::Ctx& c = *reinterpret_cast<NS::Ctx*>(vlr_smem + (size_t)w * p.ctx_stride);                            \
         double* coef_sm = reinterpret_cast<double*>(vlr_smem + (size_t)WARPS_PER_CTA * p.ctx_stride) +            \

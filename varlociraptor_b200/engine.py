@@ -16,7 +16,8 @@ import numpy as np
 from . import abi
 from .batch import CallResults, LocusBatch
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libvlr_engine.so")
+_LIB_PATH = os.environ.get("VLR_ENGINE_LIB",  # developer override for tuning experiments (another CUDA build)
+                           os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libvlr_engine.so"))
 _lib = None
 
 
