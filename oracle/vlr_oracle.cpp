@@ -32,6 +32,7 @@
 // Build: see oracle/Makefile (g++ -O2 -ffp-contract=off: Rust never contracts a*b+c).
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -1509,12 +1510,18 @@ int32_t vlr_oracle_call_batch(const vlr_scenario_t* sc, const vlr_batch_t* batch
     if (n_threads == 1) {
         work(0, batch->n_loci);
     } else {
+        // dynamic chunks: per-locus cost varies by orders of magnitude, a static split would idle most threads
+        std::atomic<int64_t> next(0);
+        const int64_t n = batch->n_loci, chunk = 8;
         std::vector<std::thread> th;
-        int64_t n = batch->n_loci;
-        for (int t = 0; t < n_threads; ++t) {
-            int64_t lo = n * t / n_threads, hi = n * (t + 1) / n_threads;
-            th.emplace_back(work, lo, hi);
-        }
+        for (int t = 0; t < n_threads; ++t)
+            th.emplace_back([&]() {
+                for (;;) {
+                    int64_t lo = next.fetch_add(chunk);
+                    if (lo >= n) break;
+                    work(lo, std::min(n, lo + chunk));
+                }
+            });
         for (auto& t : th) t.join();
     }
     return VLR_OK;

@@ -1,0 +1,172 @@
+"""Host logic of the operator API mirror (varlociraptor_b200/calling.py) without a GPU: the engine is replaced by
+the test-only host emulation, everything else (lock-step reading, candidate filter, batching, ordering, formatting
+of the final-record fields) is the product code."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tests import emu
+from varlociraptor_b200 import Scenario, calling, obs_codec
+from varlociraptor_b200.batch import LocusBatch
+
+REF_FLAME = "/root/reference/tests/resources/flamegraph_profiling"
+
+
+class EmuEngine:
+    def __init__(self, flat):
+        self.flat = flat
+        self.calls = 0
+
+    def call_batch(self, batch, afd_capacity=0, out=None):
+        self.calls += 1
+        return emu.call_batch(self.flat, batch, afd_capacity=afd_capacity)
+
+
+def _records_from_batch(batch: LocusBatch):
+    """Re-encode a one-sample LocusBatch into the record dicts `parse_observation_vcf` produces."""
+    def enc_probs(vals):
+        body = bytearray(np.uint64(len(vals)).tobytes())
+        for v in vals:
+            body += np.uint32(1).tobytes() + np.float32(v).tobytes()
+        return body
+
+    def enc_enum(vals):
+        body = bytearray(np.uint64(len(vals)).tobytes())
+        for v in vals:
+            body += np.uint32(int(v)).tobytes()
+        return body
+
+    def enc_bits(bits):
+        n = len(bits)
+        blocks = np.packbits(np.asarray(bits, dtype=np.uint8), bitorder="little").tobytes()
+        return bytearray(b"\x01" + np.uint64(len(blocks)).tobytes() + blocks + np.uint64(n).tobytes())
+
+    def ints(body):
+        if len(body) % 2:
+            body.append(0)
+        return np.frombuffer(bytes(body), dtype="<u2").astype(np.int64).tolist()
+    recs = []
+    for i in range(batch.n_loci):
+        lo, hi = batch.read_offsets[i], batch.read_offsets[i + 1]
+        f = batch.read_flags[lo:hi]
+        info = {tag: ints(enc_probs(batch.columns[col][lo:hi])) for tag, col in obs_codec._PROB_TAGS.items()}
+        info["STRAND"] = ints(enc_enum(f & 3))
+        info["READ_ORIENTATION"] = ints(enc_enum((f >> 2) & 15))
+        info["READ_POSITION"] = ints(enc_enum(np.where(f & (1 << 6), 0, 1)))
+        info["ALT_LOCUS"] = ints(enc_enum((f >> 10) & 3))
+        info["SOFTCLIPPED"] = ints(enc_bits((f >> 7) & 1))
+        info["PAIRED"] = ints(enc_bits((f >> 8) & 1))
+        info["IS_MAX_MAPQ"] = ints(enc_bits((f >> 9) & 1))
+        recs.append({"chrom": "1", "pos": 100 + i, "ref": "A", "alt": "G", "info": info, "flags": set()})
+    return recs
+
+
+@pytest.fixture(scope="module")
+def tn_records():
+    from varlociraptor_b200 import synth
+    _, b = synth.tumor_normal(12, seed=3, depth=20)
+    normal = LocusBatch(1, b.read_offsets[0::2][:13] * 0, {}, np.zeros(0, np.uint32), np.zeros(0, np.uint32)) \
+        if False else None
+    # split the two-sample batch into two one-sample batches
+    def one(s):
+        starts = b.read_offsets[s:-1:2]
+        ends = b.read_offsets[s + 1::2]
+        idx = np.concatenate([np.arange(a, e) for a, e in zip(starts, ends)])
+        offs = np.concatenate([[0], np.cumsum(ends - starts)])
+        return LocusBatch(1, offs, {k: v[idx] for k, v in b.columns.items()}, b.read_flags[idx], b.locus_flags)
+    return _records_from_batch(one(0)), _records_from_batch(one(1)), b
+
+
+def test_call_generic_orders_batches_and_formats(tn_records):
+    normal, tumor, b = tn_records
+    sc = Scenario.tumor_normal(0.75)
+    flat = sc.flatten()
+    eng = EmuEngine(flat)
+    writer = calling.call_generic(sc, {"tumor": tumor, "normal": normal}, engine=eng, batch_size=5)
+    assert eng.calls == 3  # 12 records in batches of 5
+    assert [c.pos for c in writer.calls] == [100 + i for i in range(12)]
+    want = emu.call_batch(flat, b, afd_capacity=128)
+    for i, c in enumerate(writer.calls):
+        for e, name in enumerate(flat.event_names):
+            assert c.event_probs[name] == want.log_posteriors[i, e] or \
+                (np.isnan(c.event_probs[name]) and np.isnan(want.log_posteriors[i, e]))
+        assert set(c.info_fields()) == {"PROB_ABSENT", "PROB_GERMLINE_HET", "PROB_GERMLINE_HOM",
+                                        "PROB_SOMATIC_NORMAL", "PROB_SOMATIC_TUMOR", "PROB_ARTIFACT"}
+        assert all(v >= 0 for v in c.info_fields().values())
+        assert c.sample_info[1].allelefreq_estimate == want.map_vaf[i, 1]
+        assert c.sample_info[0].depth == 20
+    lines = writer.lines()
+    assert len(lines) == 12 and lines[0].split("\t")[8] == "DP:AF:SB:ROB:RPB:SCB:HE:ALB:AFD"
+
+
+def test_candidate_filter_and_missing_sample(tn_records):
+    normal, tumor, _ = tn_records
+
+    class EveryOther(calling.CandidateFilter):
+        def filter(self, work_item, sample_names):  # noqa: A003
+            assert work_item.pileups.n_samples == 2 and sample_names == ["normal", "tumor"]
+            return work_item.index % 2 == 0
+    sc = Scenario.tumor_normal(0.75)
+    w = calling.call_generic(sc, {"tumor": tumor, "normal": normal}, engine=EmuEngine(sc.flatten()),
+                             candidate_filter=EveryOther())
+    assert [c.pos for c in w.calls] == [100, 102, 104, 106, 108, 110]
+    # a sample without observations is legal: zero coverage (calling.rs:605-607)
+    sc2 = Scenario.tumor_normal(0.75)
+    w2 = calling.call_generic(sc2, {"tumor": tumor}, engine=EmuEngine(sc2.flatten()))
+    assert len(w2.calls) == 12 and w2.calls[0].sample_info[0].depth == 0
+
+
+def test_errors_mirror_the_reference(tn_records):
+    normal, tumor, _ = tn_records
+    sc = Scenario.tumor_normal(0.75)
+    with pytest.raises(ValueError, match="invalid observation sample name"):
+        calling.call_generic(sc, {"tumour": tumor}, engine=EmuEngine(sc.flatten()))
+    with pytest.raises(ValueError, match="different numbers of records"):
+        calling.call_generic(sc, {"tumor": tumor, "normal": normal[:-1]}, engine=EmuEngine(sc.flatten()))
+    shifted = [dict(r, pos=r["pos"] + 1) for r in normal]
+    with pytest.raises(ValueError, match="inconsistent observations"):
+        calling.call_generic(sc, {"tumor": tumor, "normal": shifted}, engine=EmuEngine(sc.flatten()))
+
+
+def test_engine_is_required_without_gpu():
+    """The product path has no CPU fallback: constructing the default engine without a device must fail loudly."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from varlociraptor_b200.engine import EngineError
+    with pytest.raises(EngineError):
+        calling.call_generic(Scenario.tumor_normal(0.75), {"tumor": [], "normal": []})
+
+
+def test_golden_text_fields_with_emulated_engine(golden_dir):
+    """Final-record text fields (PROB_*, AF, DP, AFD) against what the reference printed (calls.vcf), for the
+    records not affected by the version drift of the bias selection (see test_oracle_golden.py)."""
+    exp = json.load(open(os.path.join(golden_dir, "flamegraph_expected.json")))
+    b = LocusBatch.load(os.path.join(golden_dir, "flamegraph_obs.npz"))
+    recs = _records_from_batch(b)
+    for r, e in zip(recs, exp["records"]):
+        r["pos"], r["ref"], r["alt"] = e["pos"], "CG", "<METH>"
+    sc = Scenario.from_yaml(exp["scenario_yaml"])
+    w = calling.call_generic(sc, {"normal": recs}, engine=EmuEngine(sc.flatten()))
+    n = 0
+    for c, e in zip(w.calls, exp["records"]):
+        if e["pos"] in (10471, 10489, 10542):
+            continue
+        info = c.info_fields()
+        for tag, text in e["info"].items():
+            got = info[tag]
+            if text == "inf":
+                assert np.isinf(got)
+            else:
+                assert abs(float("%g" % got) - float(text)) <= 10 ** (np.floor(np.log10(max(abs(float(text)), 1e-9))) - 4)
+        f = c.format_fields(0)
+        assert f["AF"] == "%g" % e["AF"] and int(f["DP"]) == e["DP"]
+        got_afd = [tuple(map(float, kv.split("="))) for kv in f["AFD"].split(",")]
+        assert len(got_afd) == len(e["AFD"])
+        for (gv, gp), (wv, wp) in zip(got_afd, e["AFD"]):
+            assert gv == wv and abs(gp - wp) <= 0.0101
+        assert f["SB"] == "." and f["ALB"] == "."
+        n += 1
+    assert n == 8

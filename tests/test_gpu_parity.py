@@ -184,3 +184,33 @@ def test_chunked_host_path_is_order_preserving(engine_mod):
     assert max_abs_delta(o.log_posteriors[~ke], g.log_posteriors[idx][~ke]) <= TOL
     total = np.logaddexp.reduce(g.log_posteriors, axis=1)
     assert np.nanmax(np.abs(total)) < 1e-9  # size-independent property: posteriors sum to one
+
+
+def test_call_generic_reproduces_reference_text_fields(engine_mod, golden_dir):
+    """The operator API end to end on the GPU: scenario + observation records in, final-record text fields out,
+    compared with what the reference wrote to calls.vcf (records outside the documented version drift)."""
+    from tests.test_calling_host import _records_from_batch
+    from varlociraptor_b200 import calling
+    exp = json.load(open(os.path.join(golden_dir, "flamegraph_expected.json")))
+    b = LocusBatch.load(os.path.join(golden_dir, "flamegraph_obs.npz"))
+    recs = _records_from_batch(b)
+    for r, e in zip(recs, exp["records"]):
+        r["pos"], r["ref"], r["alt"] = e["pos"], "CG", "<METH>"
+    w = calling.call_generic(Scenario.from_yaml(exp["scenario_yaml"]), {"normal": recs})
+    n = 0
+    for c, e in zip(w.calls, exp["records"]):
+        if e["pos"] in (10471, 10489, 10542):
+            continue
+        info = c.info_fields()
+        for tag, text in e["info"].items():
+            if text == "inf":
+                assert np.isinf(info[tag])
+            else:
+                assert abs(float("%g" % info[tag]) - float(text)) <= 10 ** (np.floor(np.log10(max(abs(float(text)), 1e-9))) - 4)
+        f = c.format_fields(0)
+        assert f["AF"] == "%g" % e["AF"] and int(f["DP"]) == e["DP"]
+        got = [tuple(map(float, kv.split("="))) for kv in f["AFD"].split(",")]
+        assert [g[0] for g in got] == [x[0] for x in e["AFD"]]
+        assert max(abs(g[1] - x[1]) for g, x in zip(got, e["AFD"])) <= 0.0101
+        n += 1
+    assert n == 8

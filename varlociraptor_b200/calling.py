@@ -1,0 +1,275 @@
+"""Host-side mirror of the reference's operator API for `call variants`, over the CUDA engine.
+
+Same names and argument meaning as src/calling/variants/calling.rs:
+
+  * `call_generic(scenario, observations, omit_*..., output, log_each_record, call_processor, candidate_filter,
+    propagate_info_fields, full_prior)`  (calling.rs:1022-1116)
+  * `CallProcessor.setup / process_call / finalize`  (calling.rs:964-976), `CallWriter` (calling.rs:978-1006)
+  * `CandidateFilter.filter(work_item, sample_names) -> bool`  (calling.rs:1008-1011), `DefaultCandidateFilter`
+  * `Call` with the fields `Call::write_final_record` emits (src/calling/variants/mod.rs:178-576): `PROB_<EVENT>` as
+    PHRED f32, `AF` f32, `AFD` "vaf=phred" text, the bias labels SB/ROB/RPB/SCB/HE/ALB, `DP`, `HINTS`.
+
+Differences by design: records are processed in batches (`batch_size` loci per engine call) instead of one by one;
+calls are still delivered to the processor in input order, and the candidate filter still sees every work item with
+its pileups before it is packed. Observation input here is the text form of the observation BCF (`bcftools view`);
+binary BCF I/O stays with the host application (out of scope).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, Iterable, Iterator, List, Optional, Sequence
+
+import numpy as np
+
+from . import abi, obs_codec
+from .batch import CallResults, LocusBatch
+from .scenario import Scenario
+
+_PHRED = -10.0 / math.log(10.0)
+
+
+def event_tag_name(event: str) -> str:
+    """src/utils/mod.rs `event_tag_name`: PROB_<EVENT upper-cased>."""
+    return "PROB_" + event.upper()
+
+
+@dataclass
+class SampleCall:
+    """`SampleInfo` of a called record (src/calling/variants/mod.rs:578-600)."""
+    allelefreq_estimate: float
+    artifact: str            # abi.ARTIFACT_CONFIG_NAMES entry, "none" if the MAP is not an artifact
+    vaf_dist: Optional[List[tuple]]  # [(vaf, ln posterior density)] ascending, None for artifact MAPs
+    depth: int               # DP = round(sum(exp(prob_mapping)))
+
+
+@dataclass
+class Call:
+    chrom: str
+    pos: int                 # 1-based
+    ref: str
+    alt: str
+    event_probs: Dict[str, float] = field(default_factory=dict)  # event name (+ "artifact") -> ln posterior
+    sample_info: List[Optional[SampleCall]] = field(default_factory=list)
+    hints: List[str] = field(default_factory=list)
+    status: int = 0
+
+    def info_fields(self) -> Dict[str, np.float32]:
+        """PROB_* INFO values exactly as written: PHRED, absolute value, f32 (mod.rs:459-466)."""
+        return {event_tag_name(e): np.float32(abs(_PHRED * p)) for e, p in self.event_probs.items()}
+
+    def format_fields(self, sample: int) -> Dict[str, str]:
+        si = self.sample_info[sample]
+        if si is None:
+            return {"DP": ".", "AF": ".", "AFD": "."}
+        labels = {"SB": ".", "ROB": ".", "RPB": ".", "SCB": ".", "HE": ".", "ALB": "."}
+        a = si.artifact
+        if a == "SB_FWD":
+            labels["SB"] = "+"
+        elif a == "SB_REV":
+            labels["SB"] = "-"
+        elif a == "ROB_F1R2":
+            labels["ROB"] = ">"
+        elif a == "ROB_F2R1":
+            labels["ROB"] = "<"
+        elif a == "RPB":
+            labels["RPB"] = "^"
+        elif a == "SCB":
+            labels["SCB"] = "$"
+        elif a == "HE":
+            labels["HE"] = "*"
+        elif a == "ALB":
+            labels["ALB"] = "*"
+        afd = "." if si.vaf_dist is None else ",".join(
+            "%.3f=%.2f" % (v, _PHRED * p) for v, p in si.vaf_dist)  # mod.rs:546-556
+        out = {"DP": str(si.depth), "AF": "%g" % np.float32(si.allelefreq_estimate), "AFD": afd}
+        out.update(labels)
+        return out
+
+
+@dataclass
+class WorkItem:
+    """What a CandidateFilter may look at (calling.rs:943-962): the record and its per-sample pileups (as a
+    one-locus LocusBatch)."""
+    index: int
+    chrom: str
+    pos: int
+    ref: str
+    alt: str
+    pileups: LocusBatch
+    locus_flags: int
+
+
+class CandidateFilter:
+    def filter(self, work_item: WorkItem, sample_names: Sequence[str]) -> bool:  # noqa: A003
+        raise NotImplementedError
+
+
+class DefaultCandidateFilter(CandidateFilter):
+    def filter(self, work_item, sample_names):  # noqa: A003
+        return True
+
+
+class CallProcessor:
+    def setup(self, caller: "Caller") -> None:
+        pass
+
+    def process_call(self, call: Call, sample_names: Sequence[str]) -> None:
+        raise NotImplementedError
+
+    def finalize(self) -> None:
+        pass
+
+
+class CallWriter(CallProcessor):
+    """Collects calls; `lines()` renders the INFO/FORMAT columns the way the final BCF shows them in text."""
+
+    def __init__(self):
+        self.calls: List[Call] = []
+        self.sample_names: List[str] = []
+
+    def setup(self, caller):
+        self.sample_names = list(caller.sample_names)
+
+    def process_call(self, call, sample_names):
+        self.calls.append(call)
+
+    def lines(self) -> List[str]:
+        out = []
+        for c in self.calls:
+            info = ";".join("%s=%s" % (k, "inf" if np.isinf(v) else "%g" % v) for k, v in c.info_fields().items())
+            keys = ["DP", "AF", "SB", "ROB", "RPB", "SCB", "HE", "ALB", "AFD"]
+            fmt = []
+            for s in range(len(c.sample_info)):
+                f = c.format_fields(s)
+                fmt.append(":".join(f.get(k, ".") for k in keys))
+            out.append("\t".join([c.chrom, str(c.pos), ".", c.ref, c.alt, ".", ".", info, ":".join(keys)] + fmt))
+        return out
+
+
+class Caller:
+    """`Caller` (calling.rs:56-130, 320-455) over the CUDA engine."""
+
+    def __init__(self, scenario: Scenario, observations: Dict[str, Iterable[dict]], call_processor: CallProcessor,
+                 candidate_filter: CandidateFilter, omit: Dict[str, bool], full_prior: bool = False,
+                 batch_size: int = 65536, afd_capacity: int = 128, device: int = 0, engine=None):
+        scenario.full_prior = full_prior
+        self.scenario = scenario
+        self.flat = scenario.flatten()
+        self.sample_names = list(self.flat.sample_names)
+        for name in observations:
+            if name not in self.sample_names:  # errors::Error::InvalidObservationSampleName
+                raise ValueError("invalid observation sample name: %s" % name)
+        self.observations = observations
+        self.call_processor = call_processor
+        self.candidate_filter = candidate_filter
+        self.omit = omit
+        self.batch_size = batch_size
+        self.afd_capacity = afd_capacity
+        if engine is None:
+            from .engine import PosteriorEngine
+            engine = PosteriorEngine(self.flat, device=device)
+        self.engine = engine
+
+    def _records(self) -> Iterator[List[Optional[dict]]]:
+        """One record per sample in lock-step (calling.rs:353-398): same chrom/pos/alleles required."""
+        its = [iter(self.observations[n]) if n in self.observations else None for n in self.sample_names]
+        while True:
+            recs: List[Optional[dict]] = []
+            eof = 0
+            for it in its:
+                if it is None:
+                    recs.append(None)
+                    continue
+                r = next(it, None)
+                if r is None:
+                    eof += 1
+                recs.append(r)
+            active = sum(1 for it in its if it is not None)
+            if eof == active:
+                return
+            if eof:
+                raise ValueError("observation files have different numbers of records")  # calling.rs:369-376
+            first = next(r for r in recs if r is not None)
+            for r in recs:
+                if r is not None and (r["chrom"], r["pos"], r["ref"], r["alt"]) != \
+                        (first["chrom"], first["pos"], first["ref"], first["alt"]):
+                    raise ValueError("inconsistent observations: records differ at %s:%d" % (first["chrom"], first["pos"]))
+            yield recs
+
+    def call(self) -> None:
+        self.call_processor.setup(self)
+        pending: List[tuple] = []
+        index = 0
+        for recs in self._records():
+            one = obs_codec.batch_from_records([[r] for r in recs], **self.omit)
+            first = next(r for r in recs if r is not None)
+            item = WorkItem(index, first["chrom"], first["pos"], first["ref"], first["alt"], one,
+                            int(one.locus_flags[0]))
+            index += 1
+            if not self.candidate_filter.filter(item, self.sample_names):
+                continue
+            pending.append((item, one))
+            if len(pending) >= self.batch_size:
+                self._flush(pending)
+                pending = []
+        if pending:
+            self._flush(pending)
+        self.call_processor.finalize()
+
+    def _flush(self, pending):
+        batch = LocusBatch.concat([b for _, b in pending])
+        res: CallResults = self.engine.call_batch(batch, afd_capacity=self.afd_capacity)
+        S = len(self.sample_names)
+        names = self.flat.event_names
+        for i, (item, one) in enumerate(pending):
+            call = Call(item.chrom, item.pos, item.ref, item.alt, status=int(res.status[i]))
+            for e, name in enumerate(names):
+                call.event_probs[name] = float(res.log_posteriors[i, e])
+            call.event_probs["artifact"] = float(res.log_posteriors[i, len(names)])
+            if res.status[i] & abi.ST_SINGLETON_ADJUSTED:
+                call.hints.append("adjusted-singleton-evidence")
+            if res.status[i] & abi.ST_FILTERED_NONSTANDARD:
+                call.hints.append("filtered-non-standard-alignments")
+            no_map = bool(res.status[i] & abi.ST_NO_MAP)
+            for s in range(S):
+                if no_map:
+                    call.sample_info.append(None)
+                    continue
+                lo, hi = one.read_offsets[s], one.read_offsets[s + 1]
+                keep = np.ones(hi - lo, dtype=bool)
+                if item.locus_flags & abi.LF_FILTER_NONSTANDARD:
+                    o = (one.read_flags[lo:hi] >> abi.RF_ORIENT_SHIFT) & 15
+                    keep = (o == 0) | (o == 1) | (o == 8)
+                depth = int(round(float(np.exp(one.columns["prob_mapping"][lo:hi][keep].astype(np.float64)).sum())))
+                cfg = int(res.map_config[i])
+                dist = None
+                if cfg == 0 and res.afd_count is not None:
+                    v, p = res.afd(i, s)
+                    dist = list(zip(v.tolist(), p.tolist()))
+                call.sample_info.append(SampleCall(float(res.map_vaf[i, s]), abi.ARTIFACT_CONFIG_NAMES[cfg], dist, depth))
+            self.call_processor.process_call(call, self.sample_names)
+
+
+def call_generic(scenario: Scenario, observations: Dict[str, Iterable[dict]], omit_strand_bias: bool = False,
+                 omit_read_orientation_bias: bool = False, omit_read_position_bias: bool = False,
+                 omit_softclip_bias: bool = False, omit_homopolymer_artifact_detection: bool = False,
+                 omit_alt_locus_bias: bool = False, output=None, log_each_record: bool = False,
+                 call_processor: Optional[CallProcessor] = None, candidate_filter: Optional[CandidateFilter] = None,
+                 propagate_info_fields: Sequence[str] = (), full_prior: bool = False, **engine_kwargs) -> CallProcessor:
+    """`call_generic` (calling.rs:1022-1116). `observations` maps sample name -> records of its observation file
+    (`obs_codec.parse_observation_vcf(path)`); a sample without an entry has zero coverage (calling.rs:605-607)."""
+    omit = dict(omit_strand_bias=omit_strand_bias, omit_read_orientation_bias=omit_read_orientation_bias,
+                omit_read_position_bias=omit_read_position_bias, omit_softclip_bias=omit_softclip_bias,
+                omit_homopolymer_artifact_detection=omit_homopolymer_artifact_detection,
+                omit_alt_locus_bias=omit_alt_locus_bias)
+    cp = call_processor or CallWriter()
+    cf = candidate_filter or DefaultCandidateFilter()
+    Caller(scenario, observations, cp, cf, omit, full_prior=full_prior, **engine_kwargs).call()
+    return cp
+
+
+def call_tumor_normal(tumor_records, normal_records, purity: float = 1.0, **kwargs) -> CallProcessor:
+    """`call variants tumor-normal` (src/cli.rs:1114-1196): the fixed two-sample scenario with tumor purity."""
+    return call_generic(Scenario.tumor_normal(purity=purity), {"tumor": tumor_records, "normal": normal_records},
+                        **kwargs)
