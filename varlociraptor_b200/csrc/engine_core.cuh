@@ -137,19 +137,26 @@ struct Adaptive {
 // Along a leaf-level integration only sample t's VAF changes. Everything else is hoisted: the prior factors and the
 // pileup likelihoods of the samples that do not see t (GenericLikelihood::compute, generic.rs:511-551, hits its
 // per-sample cache for them at every point), and for the (at most two) samples that do, their pileup constants.
-constexpr int NB = 4; // abscissae per batch (short batches are padded): ONE instantiation keeps the hot code small
 struct LeafDep {
     const double2* co; // coefficient arena of the sample (shared or global memory)
     double ksum, rho, iota, fixed_vaf, fixed_by;
     int n, s;
-    bool vaf_is_x, by_is_x, has_by;
+    bool vaf_is_x, by_is_x, has_by, vaf_is_parent, by_is_parent;
 };
 struct LeafFast {
     LeafDep dep[2];
-    int n_dep;
-    double lh_const, prior_const;
+    int n_dep, n_tasks, parent, t;
     bool prior_per_point; // the prior has to be evaluated per point (non-uniform priors, or a universe with holes)
-    bool uniform, t_ploidy0, coef_in_sm;
+    bool uniform, t_ploidy0, coef_in_sm, record;
+};
+// One of the (up to MT) leaf integrations a warp advances concurrently: they differ in the VAF of the parent sample
+// (the abscissae of the enclosing integration's current batch).
+struct MultiTask {
+    Adaptive st;
+    double parent_x, lh_const, prior_const, best_f, best_x;
+    double xs[8], fs[8];
+    int n, k, slot_base;
+    bool have_best, active, overflow;
 };
 
 // One instance per warp, in SHARED memory: every lane sees the same (uniform) state, so a single copy replaces
@@ -196,8 +203,11 @@ struct Ctx {
     // adaptive integration state per nesting level (at most one Range level per sample) and the leaf fast path
     Adaptive ad[MAXS];
     double xs[MAXS][8], fs[MAXS][8];
-    double lh[NB];
     LeafFast leaf;
+    MultiTask mt[MT];
+    double slot_x[MSLOTS], slot_f[MSLOTS];
+    int slot_task[MSLOTS];
+    int slot_slow[MSLOTS];
     // per-event accumulators and end-of-locus scratch
     Lse ev_plain[MAXE], ev_twin[MAXE];
     double joint_u[2 * MAXE];
@@ -1200,11 +1210,9 @@ VLR_DEV_NOINLINE double integrate_simpson(Ctx& c_, const vlr_node_t& node, int o
 
 // ln_trapezoidal_integrate_grid_exp over the n visited points of `level` (rust-bio): rank sort with
 // lanes over points, then lanes over intervals and one warp-wide log-sum-exp.
-VLR_DEV_NOINLINE double grid_trapezoid(Ctx& c_, int level, int n) {
+VLR_DEV_NOINLINE double grid_trapezoid(Ctx& c_, const double* gx, const double* gf, int n) {
     Ctx& c = warp_ctx(c_);
     const int lane = lane_id();
-    double* gx = c.ws->grid_x[level];
-    double* gf = c.ws->grid_f[level];
     double* sx = c.ws->sort_x;
     double* sf = c.ws->sort_f;
     warp_sync();
@@ -1243,7 +1251,10 @@ VLR_DEV_NOINLINE double grid_trapezoid(Ctx& c_, int level, int n) {
     return tmax + m_log(ssum);
 }
 
-// Generic adaptive integration: every point goes through subdensity()/joint() like in the reference.
+VLR_DEV_NOINLINE bool try_child_batch(Ctx& c_, const vlr_node_t& node, int od, int k, const double* xs, double* fs);
+
+// Generic adaptive integration: every point goes through subdensity()/joint() like in the reference, unless the
+// whole batch can be handed to the concurrent leaf integrator (try_child_batch).
 VLR_DEV_NOINLINE double integrate_adaptive_generic(Ctx& c_, const vlr_node_t& node, int od, double a, double b, double res,
                                                    int level) {
     Ctx& c = warp_ctx(c_);
@@ -1257,11 +1268,14 @@ VLR_DEV_NOINLINE double integrate_adaptive_generic(Ctx& c_, const vlr_node_t& no
     double* fs = c.fs[level];
     for (;;) {
         const int k = st.points(xs);
+        const bool batched = try_child_batch(c, node, od, k, xs, fs);
         for (int i = 0; i < k; ++i) {
-            c.ops[od + 1] = c.ops[od];
-            ops_push(c.ops[od + 1], node.sample, xs[i], false);
-            double f = subdensity(c, node, od + 1, level + 1);
-            fs[i] = f;
+            if (!batched) {
+                c.ops[od + 1] = c.ops[od];
+                ops_push(c.ops[od + 1], node.sample, xs[i], false);
+                fs[i] = subdensity(c, node, od + 1, level + 1);
+            }
+            const double f = fs[i];
             if (n < GRID_CAP) {
                 gx[n] = xs[i]; // every lane stores the same value: no divergence
                 gf[n] = f;
@@ -1273,145 +1287,130 @@ VLR_DEV_NOINLINE double integrate_adaptive_generic(Ctx& c_, const vlr_node_t& no
         if (!st.consume(xs, fs, overflow)) break;
     }
     if (overflow) c.status |= VLR_ST_GRID_OVERFLOW;
-    return grid_trapezoid(c, level, n);
+    return grid_trapezoid(c, gx, gf, n);
 }
 
 // ---- leaf fast path -----------------------------------------------------------------------------------------
-// The NB abscissae of a batch are evaluated TOGETHER: one pass over the reads with NB independent product chains, NB
-// interleaved shuffle reductions and one log per point distributed over lanes - the instruction-level parallelism a
-// single-point evaluation lacks. The pieces are separate out-of-line functions and their uniform state lives in
-// shared memory (Ctx::leaf, ::ad, ::xs, ::fs) so that the per-point code stays small enough for the instruction
-// caches and the per-lane stack frames stay small enough for L1 (both were measured bottlenecks, profiles/).
+// Lanes = evaluations. A warp advances up to MT leaf-level integrations of one locus at the same time (the abscissae
+// of the enclosing integration's batch, i.e. different VAFs of the parent sample) and, per step, all abscissae the
+// adaptive searches ask for: every (task, abscissa) pair is a SLOT, the 32 lanes are split evenly over the slots
+// (G = 32 / next_pow2(#slots) lanes per slot striding over the reads), so one instruction stream serves up to 32
+// evaluations. The reads loop is a dozen instructions that stay in the L0 instruction cache; the coefficient loads
+// are shared-memory broadcasts. (The first versions evaluated one point per warp and were instruction-fetch bound:
+// profiles/README.md.)
 
-// Product over the reads for the NB points: per read x_r = xu - u_r X1, y_r = Yp + u_r X1 with u_r = 1 - s_r
-// (u_r = 0, i.e. prob_sample_alt = 0, reproduces the scalar xu / Yp exactly), term = alpha x_r + beta y_r + gamma.
+// ln-likelihood of the dependent pileups for the slots [base, base + m) -> c.slot_f / c.slot_slow
 template <bool SM>
-VLR_DEV bool leaf_products(const LeafDep& d, const double* xu, const double* Yp, const double* X1, double* acc_out,
-                           int* ex_out) {
-    double acc[NB];
-    int ex[NB];
+VLR_DEV void multi_eval_impl(Ctx& c, int base, int m) {
+    const int lane = lane_id();
+    int p2 = 1;
+    while (p2 < m) p2 <<= 1;
+    const int G = LANES / p2 > 0 ? LANES / p2 : 1; // lanes per slot
+    const int slot_in = lane / G, sub = lane - slot_in * G;
+    const bool valid = slot_in < m;
+    const int slot = base + (valid ? slot_in : 0);
+    const double x = c.slot_x[slot];
+    const MultiTask& task = c.mt[c.slot_task[slot]];
+    double lnl = 0.0;
     bool slow = false;
-#pragma unroll
-    for (int b = 0; b < NB; ++b) {
-        acc[b] = 1.0;
-        ex[b] = 0;
-    }
-    int k = 0;
-    const double2* co = d.co;
+    const int n_dep = c.leaf.n_dep;
+    for (int di = 0; di < n_dep; ++di) {
+        const LeafDep& d = c.leaf.dep[di];
+        const int n = d.n;
+        if (n == 0) continue; // empty fold = ln 1
+        const double rho = d.rho, iota = d.iota;
+        const double vaf = d.vaf_is_x ? x : (d.vaf_is_parent ? task.parent_x : d.fixed_vaf);
+        const double vby = d.has_by ? (d.by_is_x ? x : (d.by_is_parent ? task.parent_x : d.fixed_by)) : 0.0;
+        const bool p1 = vaf == 1.0, s1 = vby == 1.0, sec = iota != 0.0;
+        // x = rho xp + iota xs with xp = (vaf == 1 ? 1 : vaf s_r), y = 1 - x without cancellation; see sample_likelihood
+        const double X1 = (p1 ? 0.0 : rho * vaf) + ((sec && !s1) ? iota * vby : 0.0);
+        const double X0 = (p1 ? rho : 0.0) + ((sec && s1) ? iota : 0.0);
+        const double Yp = (p1 ? 0.0 : rho * (1.0 - vaf)) + ((sec && !s1) ? iota * (1.0 - vby) : 0.0);
+        const double xu = X1 + X0;
+        const double2* co = d.co;
 #ifndef VLR_HOST_EMU
-    if (SM) co = reinterpret_cast<const double2*>(vlr_smem + (__cvta_generic_to_shared(d.co) - __cvta_generic_to_shared(vlr_smem)));
+        if (SM) co = reinterpret_cast<const double2*>(vlr_smem + (__cvta_generic_to_shared(d.co) - __cvta_generic_to_shared(vlr_smem)));
 #endif
-    const int n = d.n;
+        double acc = 1.0;
+        int ex = 0, k = 0;
+        const int nn = valid ? n : 0;
 #pragma unroll 1
-    for (int r = lane_id(); r < n; r += LANES) {
-        const double2 ab = co[2 * r];
-        const double2 gu = co[2 * r + 1];
-#pragma unroll
-        for (int b = 0; b < NB; ++b) {
-            const double xr = fma(-gu.y, X1[b], xu[b]);
-            const double yr = fma(gu.y, X1[b], Yp[b]);
-            acc[b] *= fma(ab.x, xr, fma(ab.y, yr, gu.x));
-        }
-        if (++k == 4) { // <= 4 factors between exponent pulls; a tiny (< 1e-60) or zero factor takes the careful path
-            k = 0;
-#pragma unroll
-            for (int b = 0; b < NB; ++b) {
-                slow = slow || !(acc[b] >= 1e-240);
-                const int hi = d_hi(acc[b]);
-                ex[b] += ((hi >> 20) & 0x7ff) - 1023;
-                acc[b] = d_make((hi & 0x800fffff) | (1023 << 20), d_lo(acc[b]));
+        for (int r = sub; r < nn; r += G) {
+            const double2 ab = co[2 * r];
+            const double2 gu = co[2 * r + 1];
+            // per read x_r = xu - u_r X1, y_r = Yp + u_r X1 with u_r = 1 - s_r (u_r = 0 reproduces xu / Yp exactly)
+            const double xr = fma(-gu.y, X1, xu);
+            const double yr = fma(gu.y, X1, Yp);
+            acc *= fma(ab.x, xr, fma(ab.y, yr, gu.x));
+            if (++k == 4) { // <= 4 factors between exponent pulls; a tiny (< 1e-60) or zero factor -> careful path
+                k = 0;
+                slow = slow || !(acc >= 1e-240);
+                const int hi = d_hi(acc);
+                ex += ((hi >> 20) & 0x7ff) - 1023;
+                acc = d_make((hi & 0x800fffff) | (1023 << 20), d_lo(acc));
             }
         }
-    }
-#pragma unroll
-    for (int b = 0; b < NB; ++b) {
-        slow = slow || !(acc[b] >= 1e-240);
-        const int hi = d_hi(acc[b]);
-        ex_out[b] = ex[b] + ((hi >> 20) & 0x7ff) - 1023;
-        acc_out[b] = d_make((hi & 0x800fffff) | (1023 << 20), d_lo(acc[b]));
-    }
-    return slow;
-}
-
-// c.lh[b] += ln-likelihood of dependent pileup `which` at the NB points x[] (x points into shared memory)
-template <bool SM>
-VLR_DEV void leaf_dep_likelihood_impl(Ctx& c, int which, const double* x) {
-    const LeafDep& d = c.leaf.dep[which];
-    if (d.n == 0) return; // empty fold = ln 1
-    const double ksum = d.ksum;
-    if (ksum != ksum) {
-        for (int b = 0; b < NB; ++b) c.lh[b] = NAN;
-        return;
-    }
-    double xu[NB], Yp[NB], X1[NB];
-    {
-        const double rho = d.rho, iota = d.iota, fv = d.fixed_vaf, fb = d.fixed_by;
-        const bool vx = d.vaf_is_x, bx = d.by_is_x, hb = d.has_by, sec = iota != 0.0;
-#pragma unroll
-        for (int b = 0; b < NB; ++b) { // x = rho xp + iota xs with xp = (vaf == 1 ? 1 : vaf s_r); see sample_likelihood
-            const double xb = x[b];
-            const double vaf = vx ? xb : fv;
-            const double vby = hb ? (bx ? xb : fb) : 0.0;
-            const bool p1 = vaf == 1.0, s1 = vby == 1.0;
-            X1[b] = (p1 ? 0.0 : rho * vaf) + ((sec && !s1) ? iota * vby : 0.0);
-            const double X0 = (p1 ? rho : 0.0) + ((sec && s1) ? iota : 0.0);
-            Yp[b] = (p1 ? 0.0 : rho * (1.0 - vaf)) + ((sec && !s1) ? iota * (1.0 - vby) : 0.0);
-            xu[b] = X1[b] + X0;
+        {
+            slow = slow || !(acc >= 1e-240);
+            const int hi = d_hi(acc);
+            ex += ((hi >> 20) & 0x7ff) - 1023;
+            acc = d_make((hi & 0x800fffff) | (1023 << 20), d_lo(acc));
         }
-    }
-    double acc[NB];
-    int ex[NB];
-    const bool slow = leaf_products<SM>(d, xu, Yp, X1, acc, ex);
-    if (w_any(slow)) { // zero / denormal-range factors: the careful single-point evaluation handles them
-        for (int b = 0; b < NB; ++b) {
-            const double vaf = d.vaf_is_x ? x[b] : d.fixed_vaf;
-            const double vby = d.has_by ? (d.by_is_x ? x[b] : d.fixed_by) : 0.0;
-            c.lh[b] += sample_likelihood_call(c, d.s, vaf, vby);
+#ifndef VLR_HOST_EMU
+        for (int o = G >> 1; o > 0; o >>= 1) { // butterfly inside the slot's lane group
+            acc *= __shfl_xor_sync(FULL, acc, o);
+            ex += __shfl_xor_sync(FULL, ex, o);
+            slow = slow || (__shfl_xor_sync(FULL, slow ? 1 : 0, o) != 0);
         }
-        return;
-    }
-#ifdef VLR_HOST_EMU
-    for (int b = 0; b < NB; ++b) c.lh[b] += (m_log(acc[b]) + (double)ex[b] * LN_2) + ksum;
-#else
-    // interleaved butterflies: NB independent shuffle chains
-#pragma unroll
-    for (int o = LANES / 2; o > 0; o >>= 1) {
-#pragma unroll
-        for (int b = 0; b < NB; ++b) {
-            acc[b] *= __shfl_xor_sync(FULL, acc[b], o);
-            ex[b] += __shfl_xor_sync(FULL, ex[b], o);
-        }
-    }
-    // one log per point: lane b takes point b, then lanes 0..NB-1 add into the shared accumulators
-    const int lane = lane_id();
-    double mine = acc[0];
-    int mex = ex[0];
-#pragma unroll
-    for (int b = 1; b < NB; ++b)
-        if (lane == b) {
-            mine = acc[b];
-            mex = ex[b];
-        }
-    const double l = (m_log(mine) + (double)mex * LN_2) + ksum;
-    if (lane < NB) c.lh[lane] += l;
-    warp_sync();
 #endif
+        lnl += (m_log(acc) + (double)ex * LN_2) + d.ksum; // a NaN ksum (invalid inputs) propagates
+    }
+    if (valid && sub == 0) {
+        c.slot_f[slot] = lnl;
+        c.slot_slow[slot] = slow ? 1 : 0;
+    }
+    warp_sync();
 }
-VLR_DEV_NOINLINE void leaf_dep_likelihood_sm(Ctx& c_, int which, const double* x) {
-    leaf_dep_likelihood_impl<true>(warp_ctx(c_), which, x);
-}
-VLR_DEV_NOINLINE void leaf_dep_likelihood_gl(Ctx& c_, int which, const double* x) {
-    leaf_dep_likelihood_impl<false>(warp_ctx(c_), which, x);
+VLR_DEV_NOINLINE void multi_eval_sm(Ctx& c_, int base, int m) { multi_eval_impl<true>(warp_ctx(c_), base, m); }
+VLR_DEV_NOINLINE void multi_eval_gl(Ctx& c_, int base, int m) { multi_eval_impl<false>(warp_ctx(c_), base, m); }
+
+// careful re-evaluation of the slots whose fast product met a zero / denormal-range factor (rare)
+VLR_DEV_NOINLINE void multi_eval_slow(Ctx& c_, int total) {
+    Ctx& c = warp_ctx(c_);
+    for (int slot = 0; slot < total; ++slot) {
+        if (!c.slot_slow[slot]) continue;
+        const double x = c.slot_x[slot];
+        const MultiTask& task = c.mt[c.slot_task[slot]];
+        double lnl = 0.0;
+        for (int di = 0; di < c.leaf.n_dep; ++di) {
+            const LeafDep& d = c.leaf.dep[di];
+            const double vaf = d.vaf_is_x ? x : (d.vaf_is_parent ? task.parent_x : d.fixed_vaf);
+            const double vby = d.has_by ? (d.by_is_x ? x : (d.by_is_parent ? task.parent_x : d.fixed_by)) : 0.0;
+            lnl += sample_likelihood_call(c, d.s, vaf, vby);
+        }
+        c.slot_f[slot] = lnl;
+        c.slot_slow[slot] = 0;
+    }
+    warp_sync();
 }
 
-// Decides whether the fast path can serve the integration of `node` (a leaf) and hoists its constants into c.leaf.
-VLR_DEV_NOINLINE bool leaf_setup(Ctx& c_, const vlr_node_t& node, int od, double a, double b) {
+// Materialises the operands of (task, x) at c.ops[od + 1] (parent sample at the task's abscissa, leaf sample at x).
+VLR_DEV void multi_ops(Ctx& c, int od, int task, double x) {
+    c.ops[od + 1] = c.ops[od];
+    if (c.leaf.parent >= 0) ops_push(c.ops[od + 1], c.leaf.parent, c.mt[task].parent_x, false);
+    ops_push(c.ops[od + 1], c.leaf.t, x, false);
+}
+
+// Decides whether the fast path can serve the leaf integration(s) of `node` over [a, b] and hoists the constants.
+// parent >= 0: n_tasks integrations that differ in the VAF of sample `parent` (parent_xs); parent < 0: one.
+VLR_DEV_NOINLINE bool leaf_setup(Ctx& c_, const vlr_node_t& node, int od, double a, double b, double res, int parent,
+                                 int n_tasks, const double* parent_xs) {
     Ctx& c = warp_ctx(c_);
     const DevScenario* sc = c.sc;
     const int S = sc->S;
     const int t = node.sample;
     LeafFast& L = c.leaf;
-    if (c.ops[od].lfc_mask != 0) return false;
+    if (c.ops[od].lfc_mask != 0 || n_tasks > MT) return false;
     int n_dep = 0;
     for (int s = 0; s < S; ++s) {
         const int by = sc->samples[s].contamination_by;
@@ -1432,27 +1431,21 @@ VLR_DEV_NOINLINE bool leaf_setup(Ctx& c_, const vlr_node_t& node, int od, double
         }
         d.vaf_is_x = s == t;
         d.by_is_x = by == t;
+        d.vaf_is_parent = s == parent;
+        d.by_is_parent = by >= 0 && by == parent;
         d.fixed_vaf = c.ops[od].vaf[s];
         d.fixed_by = by >= 0 ? c.ops[od].vaf[by] : 0.0;
     }
     L.n_dep = n_dep;
+    L.n_tasks = n_tasks;
+    L.parent = parent;
+    L.t = t;
     L.coef_in_sm = c.coef_in_sm != 0;
     L.uniform = sc->all_uniform != 0;
     L.t_ploidy0 = sc->samples[t].ploidy == 0;
-    double lh_const = 0.0, prior_const = 0.0;
-    const Ops& base = c.ops[od];
-    for (int s = 0; s < S; ++s) {
-        const int by = sc->samples[s].contamination_by;
-        if (s == t || by == t) continue;
-        lh_const += cached_sample_likelihood(c, s, base.vaf[s], by >= 0 ? base.vaf[by] : 0.0);
-    }
+    L.record = c.be != nullptr && c.art.id == 0;
     bool per_point = true;
-    if (L.uniform) { // flat prior inside every sample's universe (prior.rs:385-406)
-        for (int s = 0; s < S; ++s) {
-            if (s == t) continue;
-            const double v = base.vaf[s];
-            if ((sc->samples[s].ploidy == 0 && v != 0.0) || !universe_contains(c, s, v)) prior_const = neg_inf();
-        }
+    if (L.uniform) {
         // one Range spectrum of t's universe covering [a, b] covers every abscissa of this integration
         const vlr_sample_t& sm = sc->samples[t];
         for (int i = 0; i < sm.n_universe; ++i) {
@@ -1462,109 +1455,229 @@ VLR_DEV_NOINLINE bool leaf_setup(Ctx& c_, const vlr_node_t& node, int od, double
             if (range_contains(r, a) && range_contains(r, b) && !(L.t_ploidy0 && b != 0.0)) per_point = false;
         }
     }
-    L.lh_const = lh_const;
-    L.prior_const = prior_const;
     L.prior_per_point = per_point;
+    for (int k = 0; k < n_tasks; ++k) {
+        MultiTask& m = c.mt[k];
+        m.parent_x = parent >= 0 ? parent_xs[k] : 0.0;
+        double lh_const = 0.0, prior_const = 0.0;
+        for (int s = 0; s < S; ++s) { // samples that do not see t: loop constants (generic.rs:511-551 cache hits)
+            const int by = sc->samples[s].contamination_by;
+            if (s == t || by == t) continue;
+            const double v = s == parent ? m.parent_x : c.ops[od].vaf[s];
+            const double vb = by >= 0 ? (by == parent ? m.parent_x : c.ops[od].vaf[by]) : 0.0;
+            lh_const += cached_sample_likelihood(c, s, v, vb);
+        }
+        if (L.uniform) { // flat prior inside every sample's universe (prior.rs:385-406)
+            for (int s = 0; s < S; ++s) {
+                if (s == t) continue;
+                const double v = s == parent ? m.parent_x : c.ops[od].vaf[s];
+                if ((sc->samples[s].ploidy == 0 && v != 0.0) || !universe_contains(c, s, v)) prior_const = neg_inf();
+            }
+        }
+        m.lh_const = lh_const;
+        m.prior_const = prior_const;
+        m.st.init(a, b, res);
+        m.n = 0;
+        m.k = 0;
+        m.slot_base = 0;
+        m.have_best = false;
+        m.best_f = m.best_x = 0.0;
+        m.active = true;
+        m.overflow = false;
+    }
     return true;
 }
 
-// prior per abscissa when it is not a loop constant (non-uniform priors, universes with holes)
-VLR_DEV_NOINLINE double leaf_prior_point(Ctx& c_, int t, int od, double x) {
+// prior of (task, x) when it is not a loop constant (non-uniform priors, universes with holes)
+VLR_DEV_NOINLINE double multi_prior_point(Ctx& c_, int od, int task, double x) {
     Ctx& c = warp_ctx(c_);
     if (c.leaf.uniform) {
-        if ((c.leaf.t_ploidy0 && x != 0.0) || !universe_contains(c, t, x)) return neg_inf();
-        return c.leaf.prior_const;
+        if ((c.leaf.t_ploidy0 && x != 0.0) || !universe_contains(c, c.leaf.t, x)) return neg_inf();
+        return c.mt[task].prior_const;
     }
-    c.ops[od + 1] = c.ops[od];
-    ops_push(c.ops[od + 1], t, x, false);
+    multi_ops(c, od, task, x);
     return prior_compute(c, c.ops[od + 1]);
 }
 
-// base-event log for the AFD (the fast-path twin of the recording in joint())
-VLR_DEV_NOINLINE void leaf_record(Ctx& c_, int t, int od, double x, double f) {
+// Per-task bookkeeping runs with LANES = TASKS: lane k owns task k (its state is c.mt[k] in shared memory), so the
+// adaptive state machines of all tasks advance in one pass instead of one after the other.
+#ifdef VLR_HOST_EMU
+#define VLR_FOR_EACH_TASK(k, T) for (int k = 0; k < (T); ++k)
+#else
+#define VLR_FOR_EACH_TASK(k, T) for (int k = lane_id(); k < (T); k += LANES)
+#endif
+
+// prior per slot when it is not a loop constant: added into c.slot_f (uniform code: it uses the operand stack)
+VLR_DEV_NOINLINE void multi_prior_slots(Ctx& c_, int od, int total) {
     Ctx& c = warp_ctx(c_);
+    for (int slot = 0; slot < total; ++slot) c.slot_f[slot] += multi_prior_point(c, od, c.slot_task[slot], c.slot_x[slot]);
+    warp_sync();
+}
+
+// Runs the c.leaf.n_tasks prepared leaf integrations to completion; integrals -> out[task].
+VLR_DEV_NOINLINE void leaf_multi_run(Ctx& c_, int od, double* out) {
+    Ctx& c = warp_ctx(c_);
+    const int T = c.leaf.n_tasks;
     const int S = c.sc->S;
-    if (c.n_rec < (uint32_t)BE_CAP) {
-        double* e = c.be + (int64_t)c.n_rec * (2 + S);
-        e[0] = f; // every lane stores the same values
-        e[1] = d_make(0, (int)(c.ops[od].disc_mask & ~(1u << t)));
-        for (int s = 0; s < S; ++s) e[2 + s] = s == t ? x : c.ops[od].vaf[s];
-        c.n_rec++;
-    } else {
-        c.status |= VLR_ST_BASE_EVENTS_OVERFLOW;
+    const int t = c.leaf.t;
+    const bool in_sm = c.leaf.coef_in_sm, per_point = c.leaf.prior_per_point, record = c.leaf.record;
+    unsigned disc = c.ops[od].disc_mask & ~(1u << t);
+    if (c.leaf.parent >= 0) disc &= ~(1u << c.leaf.parent);
+    for (;;) {
+        // ---- every active task asks its adaptive search for the next batch; slots = exclusive scan over tasks
+        int my_k = 0;
+        VLR_FOR_EACH_TASK(k, T) {
+            MultiTask& m = c.mt[k];
+            m.k = m.active ? m.st.points(m.xs) : 0;
+#ifndef VLR_HOST_EMU
+            my_k = m.k;
+#endif
+        }
+        int total;
+#ifdef VLR_HOST_EMU
+        total = 0;
+        for (int k = 0; k < T; ++k) {
+            c.mt[k].slot_base = total;
+            total += c.mt[k].k;
+        }
+        (void)my_k;
+#else
+        {
+            int incl = my_k; // inclusive scan over the first 8 lanes (T <= MT = 8)
+#pragma unroll
+            for (int o = 1; o < MT; o <<= 1) {
+                int v = __shfl_up_sync(FULL, incl, o);
+                if (lane_id() >= o) incl += v;
+            }
+            total = __shfl_sync(FULL, incl, MT - 1);
+            if (lane_id() < T) c.mt[lane_id()].slot_base = incl - my_k;
+        }
+#endif
+        if (total == 0) break;
+        VLR_FOR_EACH_TASK(k, T) {
+            const MultiTask& m = c.mt[k];
+            for (int i = 0; i < m.k; ++i) {
+                c.slot_x[m.slot_base + i] = m.xs[i];
+                c.slot_task[m.slot_base + i] = k;
+            }
+        }
+        warp_sync();
+        // ---- all slots in parallel, 32 at a time
+        for (int base = 0; base < total; base += LANES) {
+            const int m = total - base < LANES ? total - base : LANES;
+            if (in_sm) multi_eval_sm(c, base, m);
+            else multi_eval_gl(c, base, m);
+        }
+        {
+            bool any_slow = false;
+            for (int sidx = lane_id(); sidx < total; sidx += LANES) any_slow = any_slow || c.slot_slow[sidx] != 0;
+            if (w_any(any_slow)) multi_eval_slow(c, total);
+        }
+        if (per_point) multi_prior_slots(c, od, total);
+        // ---- consume: lane k takes the values of task k in visit order
+        const uint32_t rec0 = c.n_rec;
+        unsigned flags = 0;
+        VLR_FOR_EACH_TASK(k, T) {
+            MultiTask& m = c.mt[k];
+            if (m.active) {
+                double* gx = c.ws->mgrid_x[k];
+                double* gf = c.ws->mgrid_f[k];
+                const double base_prior = per_point ? 0.0 : m.prior_const;
+                for (int i = 0; i < m.k; ++i) {
+                    const double x = m.xs[i];
+                    const double f = base_prior + (m.lh_const + c.slot_f[m.slot_base + i]);
+                    m.fs[i] = f;
+                    if (f != f) flags |= VLR_ST_NAN;
+                    if (record) { // base-event log for the AFD (the fast-path twin of the recording in joint())
+                        const uint32_t at = rec0 + (uint32_t)(m.slot_base + i);
+                        if (at < (uint32_t)BE_CAP) {
+                            double* e = c.be + (int64_t)at * (2 + S);
+                            e[0] = f;
+                            e[1] = d_make(0, (int)disc);
+                            for (int s = 0; s < S; ++s)
+                                e[2 + s] = s == t ? x : (s == c.leaf.parent ? m.parent_x : c.ops[od].vaf[s]);
+                        } else {
+                            flags |= VLR_ST_BASE_EVENTS_OVERFLOW;
+                        }
+                    }
+                    if (!m.have_best || f > m.best_f) { // first maximum in visit order
+                        m.have_best = true;
+                        m.best_f = f;
+                        m.best_x = x;
+                    }
+                    if (m.n < GRID_CAP) {
+                        gx[m.n] = x;
+                        gf[m.n] = f;
+                        m.n++;
+                    } else {
+                        m.overflow = true;
+                    }
+                }
+                m.active = m.st.consume(m.xs, m.fs, m.overflow);
+            }
+        }
+        flags = w_or_u(flags);
+        if (flags) c.status |= flags;
+        c.n_base += (uint32_t)total;
+        if (record) {
+            const uint32_t nr = rec0 + (uint32_t)total;
+            c.n_rec = nr < (uint32_t)BE_CAP ? nr : (uint32_t)BE_CAP;
+        }
+        warp_sync();
+    }
+    // ---- per task: MAP bookkeeping of joint() (first maximum over tasks in order), then the trapezoid
+    for (int k = 0; k < T; ++k) {
+        MultiTask& m = c.mt[k];
+        const int slot = c.cur_slot;
+        if (m.have_best && (!c.map_set[slot] || m.best_f > c.map_joint[slot])) {
+            c.map_set[slot] = 1;
+            c.map_joint[slot] = m.best_f;
+            c.map_cfg[slot] = c.art.id;
+            c.map_disc[slot] = disc;
+            for (int s = 0; s < S; ++s)
+                c.map_vaf[slot][s] = s == t ? m.best_x : (s == c.leaf.parent ? m.parent_x : c.ops[od].vaf[s]);
+        }
+        if (m.overflow) c.status |= VLR_ST_GRID_OVERFLOW;
+        out[k] = grid_trapezoid(c, c.ws->mgrid_x[k], c.ws->mgrid_f[k], m.n);
     }
 }
 
 VLR_DEV_NOINLINE double integrate_adaptive_leaf(Ctx& c_, const vlr_node_t& node, int od, double a, double b, double res,
                                                 int level) {
     Ctx& c = warp_ctx(c_);
-    if (!leaf_setup(c, node, od, a, b)) return integrate_adaptive_generic(c, node, od, a, b, res, level);
-    const int t = node.sample;
-    double* gx = c.ws->grid_x[level];
-    double* gf = c.ws->grid_f[level];
-    double* xs = c.xs[level];
-    double* fs = c.fs[level];
-    Adaptive& st = c.ad[level];
-    st.init(a, b, res);
-    int n = 0;
-    bool overflow = false, have_best = false;
-    double best_f = 0.0, best_x = 0.0;
-    const bool record = c.be != nullptr && c.art.id == 0;
-    const bool per_point = c.leaf.prior_per_point;
-    const bool in_sm = c.leaf.coef_in_sm, two = c.leaf.n_dep > 1;
-    const double lh_const = c.leaf.lh_const, prior_const = c.leaf.prior_const;
-    for (;;) {
-        const int k = st.points(xs);
-        // batches of exactly NB (short batches are padded with a repeated abscissa)
-        if (k == 2) xs[2] = xs[3] = xs[1];
-        else if (k == 3) xs[3] = xs[2];
-        else xs[7] = xs[6];
-        for (int off = 0; off < k; off += NB) {
-            c.lh[0] = c.lh[1] = c.lh[2] = c.lh[3] = lh_const;
-            if (in_sm) {
-                leaf_dep_likelihood_sm(c, 0, xs + off);
-                if (two) leaf_dep_likelihood_sm(c, 1, xs + off);
-            } else {
-                leaf_dep_likelihood_gl(c, 0, xs + off);
-                if (two) leaf_dep_likelihood_gl(c, 1, xs + off);
-            }
-            const int m = (k - off) < NB ? (k - off) : NB;
-            for (int i = 0; i < m; ++i) {
-                const double x = xs[off + i];
-                const double f = (per_point ? leaf_prior_point(c, t, od, x) : prior_const) + c.lh[i];
-                fs[off + i] = f;
-                if (f != f) c.status |= VLR_ST_NAN;
-                if (record) leaf_record(c, t, od, x, f);
-                if (!have_best || f > best_f) { // first maximum in visit order, merged into the MAP slot at the end
-                    have_best = true;
-                    best_f = f;
-                    best_x = x;
-                }
-                if (n < GRID_CAP) {
-                    gx[n] = x;
-                    gf[n] = f;
-                    n++;
-                } else {
-                    overflow = true;
-                }
-            }
-        }
-        c.n_base += (uint32_t)k;
-        if (!st.consume(xs, fs, overflow)) break;
-    }
-    {
-        const int S = c.sc->S;
-        const int slot = c.cur_slot;
-        if (have_best && (!c.map_set[slot] || best_f > c.map_joint[slot])) { // joint()'s MAP bookkeeping, batched
-            c.map_set[slot] = 1;
-            c.map_joint[slot] = best_f;
-            c.map_cfg[slot] = c.art.id;
-            c.map_disc[slot] = c.ops[od].disc_mask & ~(1u << t);
-            for (int s = 0; s < S; ++s) c.map_vaf[slot][s] = s == t ? best_x : c.ops[od].vaf[s];
-        }
-    }
-    if (overflow) c.status |= VLR_ST_GRID_OVERFLOW;
-    return grid_trapezoid(c, level, n);
+    if (!leaf_setup(c, node, od, a, b, res, -1, 1, nullptr)) return integrate_adaptive_generic(c, node, od, a, b, res, level);
+    double* out = c.fs[level]; // scratch of this level
+    leaf_multi_run(c, od, out);
+    return out[0];
+}
+
+// The batch of an enclosing integration, when every point leads straight into a fast-path leaf integration of the
+// single child: decides as density() would for the child (generic.rs:331-395) and runs the k integrations together.
+// Returns false if the batch has to go through subdensity() point by point.
+VLR_DEV_NOINLINE bool try_child_batch(Ctx& c_, const vlr_node_t& node, int od, int k, const double* xs, double* fs) {
+    Ctx& c = warp_ctx(c_);
+    const DevScenario* sc = c.sc;
+    if (node.n_children != 1) return false;
+    const vlr_node_t& child = sc->nodes[node.first_child];
+    if (child.kind != VLR_NODE_RANGE || child.n_children != 0) return false;
+    if (c.ops[od].lfc_mask != 0 || sc->n_lfc_nodes != 0) return false;
+    const int cs = child.sample;
+    if (cs == node.sample) return false;
+    const int n_obs = c.n_obs[cs];
+    Range vafs{child.start, child.end, child.left_exclusive != 0, child.right_exclusive != 0};
+    if (range_is_empty(vafs) || range_is_singleton(vafs)) return false;
+    if (c.clear_ref[cs] && vafs.start > 0.0) return false;
+    const double res = sc->samples[cs].resolution;
+    const double min_vaf = range_observable_min(vafs, n_obs), max_vaf = range_observable_max(vafs, n_obs);
+    if (!(min_vaf <= max_vaf) || (max_vaf - min_vaf) < res || n_obs < 5) return false;
+    // operands of the children: the parent's event is pushed per task (continuous => not discrete)
+    c.ops[od + 1] = c.ops[od];
+    ops_push(c.ops[od + 1], node.sample, xs[0], false);
+    if (!leaf_setup(c, child, od + 1, min_vaf, max_vaf, res, node.sample, k, xs)) return false;
+    leaf_multi_run(c, od + 1, fs);
+    for (int i = 0; i < k; ++i)
+        if (fs[i] != fs[i]) c.status |= VLR_ST_NAN;
+    return true;
 }
 
 VLR_DEV bool iupac_contains(int mask, int base) {

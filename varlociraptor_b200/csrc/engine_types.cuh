@@ -29,7 +29,7 @@ constexpr int WS_LEVELS = VLR_MAX_SAMPLES; // nested integration levels with scr
 #define VLR_MIN_CTAS 2
 #endif
 constexpr int WARPS_PER_CTA = VLR_WARPS_PER_CTA;
-constexpr int SM_READS = 256; // shared-memory coefficient arena per warp, in reads (8 KB): 2 x 100 reads fit
+constexpr int SM_READS = 208; // shared-memory coefficient arena per warp, in reads (6.5 KB): 2 x 100 reads fit
 #ifndef VLR_HOST_EMU
 extern __shared__ __align__(16) unsigned char vlr_smem[];
 #endif
@@ -151,9 +151,14 @@ struct DevResults {
 // Per-warp scratch in global memory (private to the warp, so it lives in L1/L2).
 constexpr int BE_CAP = 4096; // recorded base events per locus (only when an AFD is requested)
 
+constexpr int MT = 8;      // leaf integrations a warp advances concurrently (an outer batch has at most 7 abscissae)
+constexpr int MSLOTS = 56; // (task, abscissa) slots of one step: at most 7 tasks x 7 points (+ padding)
+
 struct WarpWs {
     double grid_x[WS_LEVELS][GRID_CAP];
     double grid_f[WS_LEVELS][GRID_CAP];
+    double mgrid_x[MT][GRID_CAP]; // grids of the concurrent leaf integrations
+    double mgrid_f[MT][GRID_CAP];
     double sort_x[GRID_CAP];
     double sort_f[GRID_CAP];
     double afd_x[AFD_TMP];
