@@ -1,0 +1,60 @@
+"""C++ host mirror (host/vlr_caller.hpp): compiled here with g++ against a recording mock engine (no GPU)."""
+import os
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cpp_caller_with_mock_engine(tmp_path):
+    exe = str(tmp_path / "test_caller_mock")
+    src = os.path.join(ROOT, "tests", "host", "test_caller_mock.cpp")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-o", exe, src])
+    out = subprocess.check_output([exe], text=True)
+    assert "host caller mock test: ok" in out
+
+
+import numpy as np
+import pytest
+
+
+@pytest.mark.gpu
+def test_cpp_call_generic_on_gpu_matches_oracle(tmp_path):
+    """The C++ `call_generic` over the real engine library == oracle on the same records."""
+    from oracle import oracle
+    from varlociraptor_b200 import build as vbuild, synth
+    lib = vbuild.build()
+    sc, b = synth.tumor_normal(10, seed=41, depth=24)
+    flat = sc.flatten()
+    for name, arr in (("samples", flat._samples), ("events", flat._events), ("nodes", flat._nodes),
+                      ("set_vafs", flat._set_vafs), ("spectra", flat._spectra)):
+        n = {"samples": flat.c.n_samples, "events": flat.c.n_events, "nodes": flat.c.n_nodes,
+             "set_vafs": flat.c.n_set_vafs, "spectra": flat.c.n_spectra}[name]
+        raw = bytes(arr)
+        (tmp_path / (name + ".bin")).write_bytes(raw[: len(raw) // len(arr) * n])
+    from varlociraptor_b200 import abi
+    for s, name in enumerate(["normal", "tumor"]):
+        out = []
+        for i in range(b.n_loci):
+            lo, hi = b.read_offsets[i * 2 + s], b.read_offsets[i * 2 + s + 1]
+            out.append(np.array([hi - lo], dtype=np.float32))
+            for k in abi.BATCH_F32_COLUMNS:
+                out.append(b.columns[k][lo:hi])
+            out.append(b.read_flags[lo:hi].astype(np.float32))
+        (tmp_path / (name + ".bin")).write_bytes(np.concatenate(out).astype(np.float32).tobytes())
+    exe = str(tmp_path / "test_caller_gpu")
+    libdir = os.path.dirname(lib)
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-o", exe, os.path.join(ROOT, "tests", "host", "test_caller_gpu.cpp"),
+                           "-L" + libdir, "-lvlr_engine", "-Wl,-rpath," + libdir])
+    text = subprocess.check_output([exe, str(tmp_path)], text=True)
+    want = oracle.call_batch(flat, b, afd_capacity=128)
+    lines = [ln.split() for ln in text.splitlines() if ln.startswith("CALL")]
+    assert len(lines) == b.n_loci
+    E = flat.n_events
+    for i, t in enumerate(lines):
+        assert int(t[1]) == i and int(t[2]) == int(want.status[i])
+        got = np.array([float(x) for x in t[3:3 + E + 1]])
+        ref = want.log_posteriors[i]
+        same = (got == ref) | (np.abs(got - ref) <= 1e-9)
+        assert same.all(), (i, got, ref)
+        assert float(t[3 + E + 1]) == want.map_vaf[i, 0] and float(t[3 + E + 3]) == want.map_vaf[i, 1]
+        assert int(t[3 + E + 2]) == want.afd_count[i, 0] and int(t[3 + E + 4]) == want.afd_count[i, 1]

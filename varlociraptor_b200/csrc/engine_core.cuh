@@ -67,7 +67,7 @@ struct Adaptive {
         stop = false;
     }
     // fills xs[0..k) and returns k (2, 3 or 7)
-    VLR_DEV int points(double* xs) const {
+    VLR_DEV_NOINLINE int points(double* xs) const {
         if (phase == 0) {
             xs[0] = minp;
             xs[1] = maxp;
@@ -93,7 +93,7 @@ struct Adaptive {
         return 7;
     }
     // takes the values of the batch; returns false when the integration grid is complete
-    VLR_DEV bool consume(const double* xs, const double* fs, bool overflow) {
+    VLR_DEV_NOINLINE bool consume(const double* xs, const double* fs, bool overflow) {
         if (phase == 2) return false;
         if (phase == 0) {
             f_left = fs[0];
@@ -650,9 +650,8 @@ struct PileupArgs {
     double xu, Yp, X1, X0, Y0, vaf, vaf_by, rho, iota;
     bool p1, s1;
 };
-template <int MODE>
-VLR_DEV void pileup_product(const double2* __restrict__ co, int n, const PileupArgs& a, double& acc_out, int& ex_out,
-                            bool& zero_out, bool& overshoot_out) {
+VLR_DEV void pileup_product(const double2* __restrict__ co, int n, const int MODE, const PileupArgs& a, double& acc_out,
+                            int& ex_out, bool& zero_out, bool& overshoot_out) {
     double acc = 1.0;
     int ex = 0, k = 0;
     bool zero = false, overshoot = false;
@@ -735,20 +734,8 @@ VLR_DEV double sample_likelihood(Ctx& c, int s, double vaf, double vaf_by) {
     int ex;
     bool zero, overshoot;
     const int mode = c.s_one[s] ? 0 : (c.s_gt1[s] ? 2 : 1);
-#ifndef VLR_HOST_EMU
-    if (c.coef_in_sm) { // the common case: coefficients in this warp's shared-memory arena -> LDS.128
-        const double2* co = reinterpret_cast<const double2*>(warp_coef_sm()) + (size_t)c.coef_off[s] * 2;
-        if (mode == 0) pileup_product<0>(co, n, a, acc, ex, zero, overshoot);
-        else if (mode == 1) pileup_product<1>(co, n, a, acc, ex, zero, overshoot);
-        else pileup_product<2>(co, n, a, acc, ex, zero, overshoot);
-    } else
-#endif
-    {
-        const double2* co = reinterpret_cast<const double2*>(c.coef) + (size_t)c.coef_off[s] * 2;
-        if (mode == 0) pileup_product<0>(co, n, a, acc, ex, zero, overshoot);
-        else if (mode == 1) pileup_product<1>(co, n, a, acc, ex, zero, overshoot);
-        else pileup_product<2>(co, n, a, acc, ex, zero, overshoot);
-    }
+    // careful, rarely-hot path: one generic-pointer loop (shared or global arena) keeps the code small
+    pileup_product(reinterpret_cast<const double2*>(c.coef) + (size_t)c.coef_off[s] * 2, n, mode, a, acc, ex, zero, overshoot);
     acc = w_mul_d(acc); // 32 mantissas in [1,2): < 2^32
     ex = w_sum_i(ex);
     if (mode == 2 && w_any(overshoot)) c.status |= VLR_ST_OVERSHOOT;
@@ -1216,38 +1203,46 @@ VLR_DEV_NOINLINE double grid_trapezoid(Ctx& c_, const double* gx, const double* 
     double* sx = c.ws->sort_x;
     double* sf = c.ws->sort_f;
     warp_sync();
+#pragma unroll 1
     for (int a = lane; a < n; a += LANES) {
-        double xi = gx[a];
+        const double xi = gx[a];
         int rank = 0;
+#pragma unroll 1
         for (int j = 0; j < n; ++j) {
-            double xj = gx[j];
+            const double xj = gx[j];
             rank += (xj < xi) || (xj == xi && j < a);
         }
         sx[rank] = xi;
         sf[rank] = gf[a];
     }
     warp_sync();
+    // interval terms ln((f_i + f_{i+1}) / 2 * dx): computed in both passes (max, then sum) - two short loops are
+    // smaller and spill less than one loop with a per-lane array
     double tmax = neg_inf();
-    double tloc[(GRID_CAP + LANES - 1) / LANES];
-    int q = 0;
-    for (int a = lane; a + 1 < n; a += LANES, ++q) {
-        double dx = sx[a + 1] - sx[a];
+#pragma unroll 1
+    for (int a = lane; a + 1 < n; a += LANES) {
+        const double dx = sx[a + 1] - sx[a];
         double t = (dx > 0.0) ? ln_add_exp(sf[a], sf[a + 1]) + m_log(dx) - LN_2 : neg_inf();
         if (t != t) t = INFINITY; // poison through the max
-        tloc[q] = t;
         tmax = fmax(tmax, t);
     }
     tmax = w_max_d(tmax);
-    warp_sync();
     if (tmax == neg_inf()) return neg_inf();
     if (tmax == INFINITY) {
         c.status |= VLR_ST_NAN;
         return NAN;
     }
     double ssum = 0.0;
-    for (int a = 0; a < q; ++a)
-        if (tloc[a] != neg_inf()) ssum += m_exp(tloc[a] - tmax);
+#pragma unroll 1
+    for (int a = lane; a + 1 < n; a += LANES) {
+        const double dx = sx[a + 1] - sx[a];
+        if (dx > 0.0) {
+            const double t = ln_add_exp(sf[a], sf[a + 1]) + m_log(dx) - LN_2;
+            if (t != neg_inf()) ssum += m_exp(t - tmax);
+        }
+    }
     ssum = w_sum_d(ssum);
+    warp_sync();
     return tmax + m_log(ssum);
 }
 

@@ -261,7 +261,7 @@ VLR_DEV bool range_no_overlap(const Range& a, const Range& o) { // formula.rs:11
     return (a.end < o.start || a.start > o.end) || (a.end <= o.start && (a.rex || o.lex)) ||
            (a.start >= o.end && (a.lex || o.rex));
 }
-VLR_DEV Range range_intersect(const Range& a, const Range& o) {
+VLR_DEV_NOINLINE Range range_intersect(const Range& a, const Range& o) {
     if (range_no_overlap(a, o)) return range_empty();
     Range r;
     r.start = fmax(a.start, o.start);
@@ -270,7 +270,7 @@ VLR_DEV Range range_intersect(const Range& a, const Range& o) {
     r.rex = a.end < o.end ? a.rex : (a.end > o.end ? o.rex : (a.rex || o.rex));
     return r;
 }
-VLR_DEV double range_observable_max(const Range& r, int n) { // formula.rs:1202-1224
+VLR_DEV_NOINLINE double range_observable_max(const Range& r, int n) { // formula.rs:1202-1224
     if (n < 10 || !((double)n * (r.end - r.start) > 1.0)) return r.end;
     double c = (double)n * r.end;
     if (r.rex && fmod(c, 1.0) == 0.0) c -= 1.0;
@@ -278,7 +278,7 @@ VLR_DEV double range_observable_max(const Range& r, int n) { // formula.rs:1202-
     if (c == 0.0) return r.end;
     return c / (double)n;
 }
-VLR_DEV double range_observable_min(const Range& r, int n) { // formula.rs:1172-1200
+VLR_DEV_NOINLINE double range_observable_min(const Range& r, int n) { // formula.rs:1172-1200
     double min_vaf;
     if (n < 10 || !((double)n * (r.end - r.start) > 1.0)) {
         min_vaf = r.start;
@@ -307,7 +307,7 @@ VLR_DEV int lfc_invert_cmp(int cmp) {
     default: return cmp;
     }
 }
-VLR_DEV Range lfc_infer_bounds(int cmp, double value, double vaf) {
+VLR_DEV_NOINLINE Range lfc_infer_bounds(int cmp, double value, double vaf) {
     double proj = vaf / m_exp2(value);
     if (proj < 0.0 || proj > 1.0) return range_empty();
     switch (cmp) {
