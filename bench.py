@@ -275,6 +275,13 @@ def main():
         peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
         abytes = algorithmic_bytes(batch, E)
         achieved = abytes / (kernel_ms * 1e-3) / 1e9
+        traffic = None  # DRAM bytes per launch from the committed ncu capture of this workload, scaled by loci
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))
+            if args.config == 2:
+                traffic = int(tr["dram_bytes_per_locus"] * batch.n_loci)
+        except (OSError, KeyError, ValueError):
+            pass
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -287,10 +294,12 @@ def main():
                     "launches_per_step": int(e2e_launches)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "vlr_call_kernel", "kernel_ms": kernel_ms,
+                         "traffic": traffic, "kernel": "vlr_call_kernel", "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": int(abytes), "peak_source": peak_src,
-                         "note": "the path is fp64-issue bound, not HBM bound (DESIGN.md §4): %.0f joint evaluations "
-                                 "per locus on average" % joint_evals},
+                         "note": "the path is instruction-issue bound, not HBM bound (DESIGN.md §4): %.0f joint "
+                                 "evaluations (each a product over the reads of a pileup) per locus on average; "
+                                 "traffic = measured DRAM bytes (profiles/traffic_r1.json), dominated by stack-spill "
+                                 "write-backs, not by the %.1f GB of algorithmic bytes" % (joint_evals, abytes / 1e9)},
             "clocks": clocks,
             "checks": {"loci_with_error_status": n_bad, "max_abs_log_sum_of_posteriors": sum_err},
         }

@@ -2,6 +2,7 @@
 // test (raw C structs), feeds two samples' records through call_generic and prints the calls as lines of numbers.
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <fstream>
 #include <iostream>
 #include <iterator>

@@ -241,15 +241,15 @@ struct Read {
 VLR_DEV Read load_read(const DevBatch* b, int64_t row) {
     int64_t i = row - b->read_base;
     Read r;
-    r.pm = (double)b->pm[i];
-    r.pa = (double)b->pa[i];
-    r.pr = (double)b->pr[i];
-    r.pmiss = (double)b->pmiss[i];
-    r.psa = (double)b->psa[i];
-    r.pdo = (double)b->pdo[i];
-    r.phb = (double)b->phb[i];
-    r.f = b->rflags[i];
-    float ha = b->hart ? b->hart[i] : NAN, hv = b->hvar ? b->hvar[i] : NAN;
+    r.pm = (double)ldin(b->pm + i);
+    r.pa = (double)ldin(b->pa + i);
+    r.pr = (double)ldin(b->pr + i);
+    r.pmiss = (double)ldin(b->pmiss + i);
+    r.psa = (double)ldin(b->psa + i);
+    r.pdo = (double)ldin(b->pdo + i);
+    r.phb = (double)ldin(b->phb + i);
+    r.f = ldin(b->rflags + i);
+    float ha = b->hart ? ldin(b->hart + i) : NAN, hv = b->hvar ? ldin(b->hvar + i) : NAN;
     r.has_hart = !(ha != ha);
     r.has_hvar = !(hv != hv);
     r.hart = r.has_hart ? (double)ha : 0.0;
@@ -309,11 +309,11 @@ VLR_DEV_NOINLINE void locus_prepass(Ctx& c_, BiasPlan& plan) {
         double r_all = 0.0, r_major = 0.0, r_rate = 0.0;
         for (int64_t row = lo + lane_id(); row < hi; row += LANES) {
             int64_t i = row - b->read_base;
-            uint32_t f = b->rflags[i];
+            uint32_t f = ldin(b->rflags + i);
             if (!rd_kept(lf, f)) continue;
-            double pm = (double)b->pm[i], pa = (double)b->pa[i], pr = (double)b->pr[i];
-            double phb = (double)b->phb[i];
-            float psa = b->psa[i];
+            double pm = (double)ldin(b->pm + i), pa = (double)ldin(b->pa + i), pr = (double)ldin(b->pr + i);
+            double phb = (double)ldin(b->phb + i);
+            float psa = ldin(b->psa + i);
             int kr_ref = kass_raftery(pr, pa), kr_alt = kass_raftery(pa, pr);
             bool strong_ref = kr_ref >= 3, strong_alt = kr_alt >= 3;
             int strand = rd_strand(f), orient = rd_orient(f), al = rd_altlocus(f);

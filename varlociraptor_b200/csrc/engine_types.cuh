@@ -109,6 +109,15 @@ VLR_DEV double d_make(int hi, int lo) { return __hiloint2double(hi, lo); }
 
 VLR_DEV double neg_inf() { return -INFINITY; }
 
+// Streaming loads for the batch columns: every input byte is consumed within microseconds of its first touch, so it
+// is marked evict-first and does not push the warps' stack / scratch lines out of L2 (measured: 203 GB of DRAM traffic
+// per 1M-locus launch with plain loads, almost all of it re-fetched / written-back spill lines).
+#ifdef VLR_HOST_EMU
+template <class T> VLR_DEV T ldin(const T* p) { return *p; }
+#else
+template <class T> VLR_DEV T ldin(const T* p) { return __ldcs(p); }
+#endif
+
 // ------------------------------------------------------------------------------------------------ device views
 struct DevScenario {
     int S, E, n_nodes, n_set_vafs, n_spectra, full_prior, all_uniform, n_lfc_nodes;
