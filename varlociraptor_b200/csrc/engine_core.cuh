@@ -226,9 +226,9 @@ constexpr int CTX_STRIDE = (int)((sizeof(Ctx) + 15) & ~(size_t)15);
 #ifdef VLR_HOST_EMU
 VLR_DEV Ctx& warp_ctx(Ctx& c) { return c; }
 #else
-VLR_DEV Ctx& warp_ctx(Ctx&) { return *reinterpret_cast<Ctx*>(vlr_smem + (threadIdx.x >> 5) * CTX_STRIDE); }
+VLR_DEV Ctx& warp_ctx(Ctx&) { return *reinterpret_cast<Ctx*>(vlr_smem + group_in_cta() * CTX_STRIDE); }
 VLR_DEV double* warp_coef_sm() {
-    return reinterpret_cast<double*>(vlr_smem + WARPS_PER_CTA * CTX_STRIDE) + (threadIdx.x >> 5) * (SM_READS * 4);
+    return reinterpret_cast<double*>(vlr_smem + WARPS_PER_CTA * CTX_STRIDE) + group_in_cta() * (SM_READS * 4);
 }
 #endif
 
@@ -563,7 +563,7 @@ VLR_DEV_NOINLINE void read_coefficients(Ctx& c_, int s) {
         int pos = base;
         int n_kept = kept ? 1 : 0;
 #else
-        unsigned m = __ballot_sync(FULL, kept);
+        unsigned m = w_ballot(kept);
         int pos = base + __popc(m & ((1u << lane_id()) - 1u));
         int n_kept = __popc(m);
 #endif
@@ -1541,10 +1541,10 @@ VLR_DEV_NOINLINE void leaf_multi_run(Ctx& c_, int od, double* out) {
             int incl = my_k; // inclusive scan over the first 8 lanes (T <= MT = 8)
 #pragma unroll
             for (int o = 1; o < MT; o <<= 1) {
-                int v = __shfl_up_sync(FULL, incl, o);
+                int v = __shfl_up_sync(FULL, incl, o, LANES);
                 if (lane_id() >= o) incl += v;
             }
-            total = __shfl_sync(FULL, incl, MT - 1);
+            total = __shfl_sync(FULL, incl, MT - 1, LANES);
             if (lane_id() < T) c.mt[lane_id()].slot_base = incl - my_k;
         }
 #endif
@@ -1859,7 +1859,7 @@ VLR_DEV_NOINLINE void afd_pass(Ctx& c_, int best_scen, int map_slot, double marg
 #ifdef VLR_HOST_EMU
             int pos = cnt, tot = ok ? 1 : 0;
 #else
-            unsigned m = __ballot_sync(FULL, ok);
+            unsigned m = w_ballot(ok);
             int pos = cnt + __popc(m & ((1u << lane_id()) - 1u)), tot = __popc(m);
 #endif
             if (ok) {

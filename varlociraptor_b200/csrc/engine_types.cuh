@@ -77,31 +77,42 @@ VLR_DEV double d_make(int hi, int lo) {
     return x;
 }
 #else
-constexpr int LANES = 32;
-constexpr unsigned FULL = 0xffffffffu;
-VLR_DEV int lane_id() { return (int)(threadIdx.x & 31); }
-VLR_DEV void warp_sync() { __syncwarp(); }
+// A "logical warp" of LANES lanes (32, or 16 = two loci share one physical warp's instruction stream: the kernel is
+// instruction-fetch bound, so halving the streams per locus is worth more than the lanes). All collectives below are
+// restricted to the logical warp through its member mask.
+#ifndef VLR_LANES
+#define VLR_LANES 32
+#endif
+constexpr int LANES = VLR_LANES;
+VLR_DEV int lane_id() { return (int)(threadIdx.x & (LANES - 1)); }
+VLR_DEV int group_in_cta() { return (int)(threadIdx.x / LANES); }
+VLR_DEV unsigned group_shift() { return (threadIdx.x & 31u) & ~(unsigned)(LANES - 1); }
+VLR_DEV unsigned gmask() { return LANES == 32 ? 0xffffffffu : (((1u << (LANES & 31)) - 1u) << group_shift()); }
+#define FULL (vlrcore::gmask())
+VLR_DEV void warp_sync() { __syncwarp(FULL); }
 VLR_DEV int w_sum_i(int v) { return __reduce_add_sync(FULL, v); }
 VLR_DEV unsigned w_or_u(unsigned v) { return __reduce_or_sync(FULL, v); }
 VLR_DEV int w_max_i(int v) { return __reduce_max_sync(FULL, v); }
 // xor butterflies: a+b == b+a bitwise, so every lane ends with the identical value (needed for uniform control flow)
 VLR_DEV double w_sum_d(double v) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    for (int o = LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
     return v;
 }
 VLR_DEV double w_mul_d(double v) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v *= __shfl_xor_sync(FULL, v, o);
+    for (int o = LANES / 2; o > 0; o >>= 1) v *= __shfl_xor_sync(FULL, v, o);
     return v;
 }
 VLR_DEV double w_max_d(double v) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
+    for (int o = LANES / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
     return v;
 }
 VLR_DEV bool w_any(bool p) { return __any_sync(FULL, p) != 0; }
-VLR_DEV double w_bcast_d(double v, int src) { return __shfl_sync(FULL, v, src); }
+VLR_DEV double w_bcast_d(double v, int src) { return __shfl_sync(FULL, v, src, LANES); }
+// ballot of the logical warp with bit i = lane i of the logical warp
+VLR_DEV unsigned w_ballot(bool p) { return __ballot_sync(FULL, p) >> group_shift(); }
 VLR_DEV int d_hi(double x) { return __double2hiint(x); }
 VLR_DEV int d_lo(double x) { return __double2loint(x); }
 VLR_DEV double d_make(int hi, int lo) { return __hiloint2double(hi, lo); }

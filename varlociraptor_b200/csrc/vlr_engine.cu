@@ -33,7 +33,7 @@ using namespace vlrcore;
 
 namespace {
 
-constexpr int THREADS = WARPS_PER_CTA * 32;
+constexpr int THREADS = WARPS_PER_CTA * LANES; // WARPS_PER_CTA counts logical warps (engine_types.cuh)
 constexpr int NBUF = 3;
 
 struct KernelParams {
@@ -54,7 +54,7 @@ struct KernelParams {
 // Shared memory per CTA: [WARPS_PER_CTA x Ctx (uniform per-warp state)] [WARPS_PER_CTA x coefficient arena].
 #define VLR_DEFINE_KERNEL(NS)                                                                                     \
     __global__ void __launch_bounds__(THREADS, VLR_MIN_CTAS) vlr_call_kernel_##NS(const __grid_constant__ KernelParams p) {  \
-                const int w = threadIdx.x >> 5;                                                                           \
+                const int w = group_in_cta();                                                                             \
         const int gw = blockIdx.x * WARPS_PER_CTA + w;                                                            \
         NS::Ctx& c = *reinterpret_cast<NS::Ctx*>(vlr_smem + (size_t)w * p.ctx_stride);                            \
         double* coef_sm = reinterpret_cast<double*>(vlr_smem + (size_t)WARPS_PER_CTA * p.ctx_stride) +            \
@@ -64,11 +64,11 @@ struct KernelParams {
         double* be = p.be ? p.be + (int64_t)gw * p.be_stride : nullptr;                                           \
         for (;;) {                                                                                                \
             unsigned long long t = 0;                                                                             \
-            if ((threadIdx.x & 31) == 0) t = atomicAdd(p.ticket, 1ULL);                                           \
-            t = __shfl_sync(0xffffffffu, t, 0);                                                                   \
+            if (lane_id() == 0) t = atomicAdd(p.ticket, 1ULL);                                                    \
+            t = __shfl_sync(FULL, t, 0, LANES);                                                                   \
             if ((int64_t)t >= p.b.n_loci) break;                                                                  \
             NS::process_locus(&p.sc, &p.b, &p.r, ws, coef, coef_sm, p.sm_reads, be, p.coef_cap, (int64_t)t, c);   \
-            __syncwarp();                                                                                         \
+            warp_sync();                                                                                          \
         }                                                                                                         \
     }
 VLR_DEFINE_KERNEL(vlr_small)
