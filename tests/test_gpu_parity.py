@@ -172,13 +172,13 @@ def test_workspace_overflow_is_reported_not_silent(engine_mod):
 
 
 def test_chunked_host_path_is_order_preserving(engine_mod):
-    """More reads than one transfer chunk (2M reads): results come back in input order across chunks."""
-    sc, b = synth.tumor_normal(12000, seed=123, depth=100)  # 2.4M reads -> 2 chunks
+    """More loci than one transfer chunk (65536 loci / 16M reads): results come back in input order across chunks."""
+    sc, b = synth.tumor_normal(70000, seed=123, depth=20)  # 2 chunks
     flat = sc.flatten()
     eng = engine_mod.PosteriorEngine(flat)
     g = eng.call_batch(b)
     assert eng.launches >= 2
-    idx = np.r_[0:50, 10450:10500, 11950:12000]
+    idx = np.r_[0:50, 65500:65560, 69950:70000]
     o = oracle.call_batch(flat, b.select(idx), n_threads=os.cpu_count() or 1)
     ke = o.knife_edge()
     assert max_abs_delta(o.log_posteriors[~ke], g.log_posteriors[idx][~ke]) <= TOL

@@ -398,9 +398,10 @@ vlr_status_t vlr_call_batch(vlr_ctx_t* ctx, const vlr_batch_t* batch, vlr_result
     if (L == 0) return VLR_OK;
     const int64_t* off = batch->read_offsets;
     if (off[L * S] != batch->n_reads) return ctx->fail(VLR_ERR_INVALID_ARGUMENT, "read_offsets[n_loci*S] != n_reads");
-    // chunking: ~2M reads per chunk keeps copies >= tens of MB (PCIe-efficient) while 3 slots stay far below HBM size
-    const int64_t target_reads = 2 << 20;
-    const int64_t max_loci_chunk = 1 << 17;
+    // chunking: a chunk must hold many more loci than the 2368 resident warps (dynamic load balance inside the kernel)
+    // and tens of MB of columns (PCIe efficiency); 3 slots of <= 16M reads (512 MB) stay far below the HBM size
+    const int64_t target_reads = 16 << 20;
+    const int64_t max_loci_chunk = 1 << 16;
     const int cap = results->afd_capacity;
     const float* cols[7] = {batch->prob_mapping, batch->prob_ref,         batch->prob_alt,     batch->prob_missed_allele,
                             batch->prob_sample_alt, batch->prob_double_overlap, batch->prob_hit_base};
