@@ -51,22 +51,53 @@ def workload_name(cfg, loci):
             5: "cfg5: %d synthetic SNV loci, tumor-normal, reads/locus/sample log-uniform 10..2000"}[cfg] % loci
 
 
-def make_batch(cfg, loci, seed):
+def make_batch(cfg, loci, seed, pinned=False):
+    """Synthetic batch of `loci` loci, generated in slabs (bounded transient memory). With pinned=True the columns are
+    written straight into page-locked arrays (vlr_host_alloc), so a rank holds one copy of its 6.4 GB shard."""
     from varlociraptor_b200 import synth
-    # generate in slabs to bound peak host memory
     from varlociraptor_b200.batch import LocusBatch
-    slabs = []
+    slab = 125_000 if cfg != 5 else 20_000
+    parts = []
     scenario = None
     done = 0
-    slab = 125_000 if cfg != 5 else 20_000
     k = 0
+    out = None
+    row = 0
     while done < loci:
         n = min(slab, loci - done)
         scenario, b = synth.config(cfg, n, seed=seed * 1000 + k)
-        slabs.append(b)
+        if pinned and cfg != 5:
+            S = b.n_samples
+            if out is None:  # fixed depth: total sizes are known after the first slab
+                from varlociraptor_b200 import engine
+                total_reads = b.n_reads // n * loci
+                out = LocusBatch.__new__(LocusBatch)
+                out.n_samples, out.n_loci, out.n_reads = S, loci, total_reads
+                out.read_offsets = engine.pinned_empty(loci * S + 1, np.int64)
+                out.read_offsets[0] = 0
+                out.columns = {c: engine.pinned_empty(total_reads, np.float32) for c in b.columns}
+                out.read_flags = engine.pinned_empty(total_reads, np.uint32)
+                out.locus_flags = engine.pinned_empty(loci, np.uint32)
+                out.prob_homopolymer_artifact = out.prob_homopolymer_variant = None
+                out.locus_heterozygosity_phred = out.locus_semr_phred = None
+            out.read_offsets[done * S + 1:(done + n) * S + 1] = b.read_offsets[1:] + row
+            for c in b.columns:
+                out.columns[c][row:row + b.n_reads] = b.columns[c]
+            out.read_flags[row:row + b.n_reads] = b.read_flags
+            out.locus_flags[done:done + n] = b.locus_flags
+            row += b.n_reads
+        else:
+            parts.append(b)
         done += n
         k += 1
-    return scenario, (slabs[0] if len(slabs) == 1 else LocusBatch.concat(slabs))
+    if out is not None:
+        assert row == out.n_reads
+        return scenario, out
+    batch = parts[0] if len(parts) == 1 else LocusBatch.concat(parts)
+    if pinned:
+        from varlociraptor_b200 import engine
+        batch = engine.pin_batch(batch)
+    return scenario, batch
 
 
 def algorithmic_bytes(batch, n_events):
@@ -186,7 +217,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(device))
     from varlociraptor_b200 import engine
-    scenario, batch = make_batch(args.config, args.loci, seed=20260100 + args.config + 17 * rank)
+    scenario, batch = make_batch(args.config, args.loci, seed=20260100 + args.config + 17 * rank, pinned=True)
     flat = scenario.flatten()
     S, E = flat.n_samples, flat.n_events
     eng = engine.PosteriorEngine(flat, device=local_rank)
@@ -194,7 +225,7 @@ def main():
     eng.reserve(max_reads)
     dbatch = engine.DeviceBatch(batch, device)
     dres = engine.DeviceResults(batch.n_loci, S, E, 0, device)
-    pinned = engine.pin_batch(batch)
+    pinned = batch  # already page-locked
     pres = engine.pinned_results(batch.n_loci, S, E, 0)
     gather_buf = None
     if world > 1:
