@@ -67,7 +67,7 @@ struct Adaptive {
         stop = false;
     }
     // fills xs[0..k) and returns k (2, 3 or 7)
-    VLR_DEV_NOINLINE int points(double* xs) const {
+    VLR_DEV int points(double* xs) const {
         if (phase == 0) {
             xs[0] = minp;
             xs[1] = maxp;
@@ -93,7 +93,7 @@ struct Adaptive {
         return 7;
     }
     // takes the values of the batch; returns false when the integration grid is complete
-    VLR_DEV_NOINLINE bool consume(const double* xs, const double* fs, bool overflow) {
+    VLR_DEV bool consume(const double* xs, const double* fs, bool overflow) {
         if (phase == 2) return false;
         if (phase == 0) {
             f_left = fs[0];
@@ -1358,7 +1358,7 @@ VLR_DEV void multi_eval_impl(Ctx& c, int base, int m) {
             slow = slow || (__shfl_xor_sync(FULL, slow ? 1 : 0, o) != 0);
         }
 #endif
-        lnl += (m_log(acc) + (double)ex * LN_2) + d.ksum; // a NaN ksum (invalid inputs) propagates
+        lnl += (log(acc) + (double)ex * LN_2) + d.ksum; // a NaN ksum (invalid inputs) propagates
     }
     if (valid && sub == 0) {
         c.slot_f[slot] = lnl;
@@ -1366,7 +1366,9 @@ VLR_DEV void multi_eval_impl(Ctx& c, int base, int m) {
     }
     warp_sync();
 }
-VLR_DEV_NOINLINE void multi_eval_sm(Ctx& c_, int base, int m) { multi_eval_impl<true>(warp_ctx(c_), base, m); }
+// the shared-memory variant is inlined into the step loop (measured: +18 % over an out-of-line call); the
+// global-memory variant (loci deeper than the shared arena) stays out of line to keep the hot function small
+VLR_DEV void multi_eval_sm(Ctx& c_, int base, int m) { multi_eval_impl<true>(warp_ctx(c_), base, m); }
 VLR_DEV_NOINLINE void multi_eval_gl(Ctx& c_, int base, int m) { multi_eval_impl<false>(warp_ctx(c_), base, m); }
 
 // careful re-evaluation of the slots whose fast product met a zero / denormal-range factor (rare)
@@ -1509,11 +1511,45 @@ VLR_DEV_NOINLINE void multi_prior_slots(Ctx& c_, int od, int total) {
     warp_sync();
 }
 
+// base-event log for the AFD (the fast-path twin of the recording in joint()); called by the lane that owns the task
+VLR_DEV_NOINLINE unsigned multi_record(Ctx& c_, int od, double parent_x, double x, double f, uint32_t at, unsigned disc) {
+    Ctx& c = warp_ctx(c_);
+    const int S = c.sc->S;
+    const int t = c.leaf.t;
+    if (at >= (uint32_t)BE_CAP) return VLR_ST_BASE_EVENTS_OVERFLOW;
+    double* e = c.be + (int64_t)at * (2 + S);
+    e[0] = f;
+    e[1] = d_make(0, (int)disc);
+    for (int s = 0; s < S; ++s) e[2 + s] = s == t ? x : (s == c.leaf.parent ? parent_x : c.ops[od].vaf[s]);
+    return 0u;
+}
+
+// per task: MAP bookkeeping of joint() (first maximum over tasks in order), then the trapezoid over its grid
+VLR_DEV_NOINLINE void leaf_multi_finish(Ctx& c_, int od, unsigned disc, double* out) {
+    Ctx& c = warp_ctx(c_);
+    const int T = c.leaf.n_tasks;
+    const int S = c.sc->S;
+    const int t = c.leaf.t;
+    for (int k = 0; k < T; ++k) {
+        MultiTask& m = c.mt[k];
+        const int slot = c.cur_slot;
+        if (m.have_best && (!c.map_set[slot] || m.best_f > c.map_joint[slot])) {
+            c.map_set[slot] = 1;
+            c.map_joint[slot] = m.best_f;
+            c.map_cfg[slot] = c.art.id;
+            c.map_disc[slot] = disc;
+            for (int s = 0; s < S; ++s)
+                c.map_vaf[slot][s] = s == t ? m.best_x : (s == c.leaf.parent ? m.parent_x : c.ops[od].vaf[s]);
+        }
+        if (m.overflow) c.status |= VLR_ST_GRID_OVERFLOW;
+        out[k] = grid_trapezoid(c, c.ws->mgrid_x[k], c.ws->mgrid_f[k], m.n);
+    }
+}
+
 // Runs the c.leaf.n_tasks prepared leaf integrations to completion; integrals -> out[task].
 VLR_DEV_NOINLINE void leaf_multi_run(Ctx& c_, int od, double* out) {
     Ctx& c = warp_ctx(c_);
     const int T = c.leaf.n_tasks;
-    const int S = c.sc->S;
     const int t = c.leaf.t;
     const bool in_sm = c.leaf.coef_in_sm, per_point = c.leaf.prior_per_point, record = c.leaf.record;
     unsigned disc = c.ops[od].disc_mask & ~(1u << t);
@@ -1583,18 +1619,7 @@ VLR_DEV_NOINLINE void leaf_multi_run(Ctx& c_, int od, double* out) {
                     const double f = base_prior + (m.lh_const + c.slot_f[m.slot_base + i]);
                     m.fs[i] = f;
                     if (f != f) flags |= VLR_ST_NAN;
-                    if (record) { // base-event log for the AFD (the fast-path twin of the recording in joint())
-                        const uint32_t at = rec0 + (uint32_t)(m.slot_base + i);
-                        if (at < (uint32_t)BE_CAP) {
-                            double* e = c.be + (int64_t)at * (2 + S);
-                            e[0] = f;
-                            e[1] = d_make(0, (int)disc);
-                            for (int s = 0; s < S; ++s)
-                                e[2 + s] = s == t ? x : (s == c.leaf.parent ? m.parent_x : c.ops[od].vaf[s]);
-                        } else {
-                            flags |= VLR_ST_BASE_EVENTS_OVERFLOW;
-                        }
-                    }
+                    if (record) flags |= multi_record(c, od, m.parent_x, x, f, rec0 + (uint32_t)(m.slot_base + i), disc);
                     if (!m.have_best || f > m.best_f) { // first maximum in visit order
                         m.have_best = true;
                         m.best_f = f;
@@ -1620,21 +1645,7 @@ VLR_DEV_NOINLINE void leaf_multi_run(Ctx& c_, int od, double* out) {
         }
         warp_sync();
     }
-    // ---- per task: MAP bookkeeping of joint() (first maximum over tasks in order), then the trapezoid
-    for (int k = 0; k < T; ++k) {
-        MultiTask& m = c.mt[k];
-        const int slot = c.cur_slot;
-        if (m.have_best && (!c.map_set[slot] || m.best_f > c.map_joint[slot])) {
-            c.map_set[slot] = 1;
-            c.map_joint[slot] = m.best_f;
-            c.map_cfg[slot] = c.art.id;
-            c.map_disc[slot] = disc;
-            for (int s = 0; s < S; ++s)
-                c.map_vaf[slot][s] = s == t ? m.best_x : (s == c.leaf.parent ? m.parent_x : c.ops[od].vaf[s]);
-        }
-        if (m.overflow) c.status |= VLR_ST_GRID_OVERFLOW;
-        out[k] = grid_trapezoid(c, c.ws->mgrid_x[k], c.ws->mgrid_f[k], m.n);
-    }
+    leaf_multi_finish(c, od, disc, out);
 }
 
 VLR_DEV_NOINLINE double integrate_adaptive_leaf(Ctx& c_, const vlr_node_t& node, int od, double a, double b, double res,
