@@ -144,7 +144,8 @@ struct LeafDep {
     bool vaf_is_x, by_is_x, has_by, vaf_is_parent, by_is_parent;
 };
 struct LeafFast {
-    LeafDep dep[2];
+    LeafDep dep[3]; // [0..1]: the pileups that see the leaf sample; [2]: the parent sample's pileup (setup only)
+    int dep_lo, dep_hi; // the descriptors multi_eval walks
     int n_dep, n_tasks, parent, t;
     bool prior_per_point; // the prior has to be evaluated per point (non-uniform priors, or a universe with holes)
     bool uniform, t_ploidy0, coef_in_sm, record;
@@ -1308,8 +1309,8 @@ VLR_DEV void multi_eval_impl(Ctx& c, int base, int m) {
     const MultiTask& task = c.mt[c.slot_task[slot]];
     double lnl = 0.0;
     bool slow = false;
-    const int n_dep = c.leaf.n_dep;
-    for (int di = 0; di < n_dep; ++di) {
+    const int dep_hi = c.leaf.dep_hi;
+    for (int di = c.leaf.dep_lo; di < dep_hi; ++di) {
         const LeafDep& d = c.leaf.dep[di];
         const int n = d.n;
         if (n == 0) continue; // empty fold = ln 1
@@ -1379,7 +1380,7 @@ VLR_DEV_NOINLINE void multi_eval_slow(Ctx& c_, int total) {
         const double x = c.slot_x[slot];
         const MultiTask& task = c.mt[c.slot_task[slot]];
         double lnl = 0.0;
-        for (int di = 0; di < c.leaf.n_dep; ++di) {
+        for (int di = c.leaf.dep_lo; di < c.leaf.dep_hi; ++di) {
             const LeafDep& d = c.leaf.dep[di];
             const double vaf = d.vaf_is_x ? x : (d.vaf_is_parent ? task.parent_x : d.fixed_vaf);
             const double vby = d.has_by ? (d.by_is_x ? x : (d.by_is_parent ? task.parent_x : d.fixed_by)) : 0.0;
@@ -1453,16 +1454,61 @@ VLR_DEV_NOINLINE bool leaf_setup(Ctx& c_, const vlr_node_t& node, int od, double
         }
     }
     L.prior_per_point = per_point;
+    // ---- loop constants per task: likelihoods of the samples that do not see t (generic.rs:511-551 cache hits).
+    // Only the parent sample's differs between tasks: its n_tasks pileup likelihoods are evaluated together, one
+    // slot per task, with the same slot machinery as the leaf evaluations.
+    double lh_shared = 0.0;
+    bool parent_by_slots = false;
+    for (int s = 0; s < S; ++s) {
+        const int by = sc->samples[s].contamination_by;
+        if (s == t || by == t) continue;
+        if (s == parent && n_tasks > 1 && !c.s_gt1[s] && by != parent) {
+            LeafDep& d = L.dep[2];
+            d.s = s;
+            d.co = reinterpret_cast<const double2*>(c.coef) + (size_t)c.coef_off[s] * 2;
+            d.ksum = c.ksum[s];
+            d.n = c.n_obs[s];
+            d.rho = 1.0;
+            d.iota = 0.0;
+            d.has_by = by >= 0;
+            if (by >= 0) {
+                d.rho = 1.0 - sc->samples[s].contamination_fraction;
+                d.iota = 1.0 - d.rho;
+            }
+            d.vaf_is_x = true; // the slot abscissa is the parent's VAF here
+            d.by_is_x = false;
+            d.vaf_is_parent = false;
+            d.by_is_parent = false;
+            d.fixed_vaf = 0.0;
+            d.fixed_by = by >= 0 ? c.ops[od].vaf[by] : 0.0;
+            parent_by_slots = true;
+        } else if (s != parent) {
+            if (by >= 0 && by == parent) return false; // a non-dependent sample contaminated by the parent: generic path
+            lh_shared += cached_sample_likelihood(c, s, c.ops[od].vaf[s], by >= 0 ? c.ops[od].vaf[by] : 0.0);
+        }
+    }
+    for (int k = 0; k < n_tasks; ++k) {
+        c.mt[k].parent_x = parent >= 0 ? parent_xs[k] : 0.0;
+        c.slot_x[k] = c.mt[k].parent_x;
+        c.slot_task[k] = k;
+    }
+    if (parent_by_slots) {
+        L.dep_lo = 2;
+        L.dep_hi = 3;
+        warp_sync();
+        for (int base = 0; base < n_tasks; base += LANES)
+            multi_eval_gl(c, base, n_tasks - base < LANES ? n_tasks - base : LANES);
+        bool any_slow = false;
+        for (int k = lane_id(); k < n_tasks; k += LANES) any_slow = any_slow || c.slot_slow[k] != 0;
+        if (w_any(any_slow)) multi_eval_slow(c, n_tasks);
+    }
     for (int k = 0; k < n_tasks; ++k) {
         MultiTask& m = c.mt[k];
-        m.parent_x = parent >= 0 ? parent_xs[k] : 0.0;
-        double lh_const = 0.0, prior_const = 0.0;
-        for (int s = 0; s < S; ++s) { // samples that do not see t: loop constants (generic.rs:511-551 cache hits)
-            const int by = sc->samples[s].contamination_by;
-            if (s == t || by == t) continue;
-            const double v = s == parent ? m.parent_x : c.ops[od].vaf[s];
-            const double vb = by >= 0 ? (by == parent ? m.parent_x : c.ops[od].vaf[by]) : 0.0;
-            lh_const += cached_sample_likelihood(c, s, v, vb);
+        double lh_const = lh_shared, prior_const = 0.0;
+        if (parent_by_slots) lh_const += c.slot_f[k];
+        else if (parent >= 0 && parent != t && sc->samples[parent].contamination_by != t) {
+            const int by = sc->samples[parent].contamination_by;
+            lh_const += cached_sample_likelihood(c, parent, m.parent_x, by >= 0 ? (by == parent ? m.parent_x : c.ops[od].vaf[by]) : 0.0);
         }
         if (L.uniform) { // flat prior inside every sample's universe (prior.rs:385-406)
             for (int s = 0; s < S; ++s) {
@@ -1482,6 +1528,9 @@ VLR_DEV_NOINLINE bool leaf_setup(Ctx& c_, const vlr_node_t& node, int od, double
         m.active = true;
         m.overflow = false;
     }
+    L.dep_lo = 0;
+    L.dep_hi = n_dep;
+    warp_sync();
     return true;
 }
 
