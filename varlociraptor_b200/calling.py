@@ -29,6 +29,40 @@ from .scenario import Scenario
 _PHRED = -10.0 / math.log(10.0)
 
 
+def _kass_raftery_letter(m1: float, m2: float) -> str:
+    """`bayes_factor_to_letter` (src/utils/mod.rs:158-167) of BayesFactor::new(m1, m2) = exp(m1 - m2)."""
+    with np.errstate(over="ignore", invalid="ignore"):
+        k = float(np.exp(np.float64(m1) - np.float64(m2)))
+    if k <= 1.0:
+        return "E" if k == 1.0 or abs(k - 1.0) <= 2.220446049250313e-16 else "N"
+    if k <= 3.0:
+        return "B"
+    if k <= 20.0:
+        return "P"
+    if k <= 150.0:
+        return "S"
+    return "V"
+
+
+def simple_observations(prob_alt, prob_ref, is_max_mapq, alt_allele: bool) -> str:
+    """`fmt_simple_obs` (src/calling/variants/mod.rs:337-376): generalized CIGAR of Kass-Raftery letters of the reads
+    favouring the alt (or the ref / a third) allele, upper case iff the read has the maximum MAPQ; most common
+    first, 'E' entries last."""
+    from collections import Counter
+    items = []
+    for pa, pr, mq in zip(prob_alt, prob_ref, is_max_mapq):
+        keep = (pa > pr) if alt_allele else (pa <= pr)
+        if not keep:
+            continue
+        letter = _kass_raftery_letter(pa, pr) if alt_allele else _kass_raftery_letter(pr, pa)
+        items.append(letter.upper() if mq else letter.lower())
+    if not items:
+        return "."
+    common = Counter(items).most_common()
+    common.sort(key=lambda kv: 1 if kv[0].endswith("E") else 0)  # stable: keeps the count order
+    return "".join("%d%s" % (n, it) for it, n in common)
+
+
 def event_tag_name(event: str) -> str:
     """src/utils/mod.rs `event_tag_name`: PROB_<EVENT upper-cased>."""
     return "PROB_" + event.upper()
@@ -41,6 +75,8 @@ class SampleCall:
     artifact: str            # abi.ARTIFACT_CONFIG_NAMES entry, "none" if the MAP is not an artifact
     vaf_dist: Optional[List[tuple]]  # [(vaf, ln posterior density)] ascending, None for artifact MAPs
     depth: int               # DP = round(sum(exp(prob_mapping)))
+    saobs: str = "."         # SAOBS / SROBS: simplified observation summaries (mod.rs:337-379)
+    srobs: str = "."
 
 
 @dataclass
@@ -82,7 +118,8 @@ class Call:
             labels["ALB"] = "*"
         afd = "." if si.vaf_dist is None else ",".join(
             "%.3f=%.2f" % (v, _PHRED * p) for v, p in si.vaf_dist)  # mod.rs:546-556
-        out = {"DP": str(si.depth), "AF": "%g" % np.float32(si.allelefreq_estimate), "AFD": afd}
+        out = {"DP": str(si.depth), "AF": "%g" % np.float32(si.allelefreq_estimate), "AFD": afd,
+               "SAOBS": si.saobs, "SROBS": si.srobs}
         out.update(labels)
         return out
 
@@ -138,7 +175,7 @@ class CallWriter(CallProcessor):
         out = []
         for c in self.calls:
             info = ";".join("%s=%s" % (k, "inf" if np.isinf(v) else "%g" % v) for k, v in c.info_fields().items())
-            keys = ["DP", "AF", "SB", "ROB", "RPB", "SCB", "HE", "ALB", "AFD"]
+            keys = ["DP", "AF", "SAOBS", "SROBS", "SB", "ROB", "RPB", "SCB", "HE", "ALB", "AFD"]
             fmt = []
             for s in range(len(c.sample_info)):
                 f = c.format_fields(s)
@@ -242,12 +279,17 @@ class Caller:
                     o = (one.read_flags[lo:hi] >> abi.RF_ORIENT_SHIFT) & 15
                     keep = (o == 0) | (o == 1) | (o == 8)
                 depth = int(round(float(np.exp(one.columns["prob_mapping"][lo:hi][keep].astype(np.float64)).sum())))
+                pa = one.columns["prob_alt"][lo:hi][keep].astype(np.float64)
+                pr = one.columns["prob_ref"][lo:hi][keep].astype(np.float64)
+                mq = (one.read_flags[lo:hi][keep] & abi.RF_MAX_MAPQ) != 0
                 cfg = int(res.map_config[i])
                 dist = None
                 if cfg == 0 and res.afd_count is not None:
                     v, p = res.afd(i, s)
                     dist = list(zip(v.tolist(), p.tolist()))
-                call.sample_info.append(SampleCall(float(res.map_vaf[i, s]), abi.ARTIFACT_CONFIG_NAMES[cfg], dist, depth))
+                call.sample_info.append(SampleCall(float(res.map_vaf[i, s]), abi.ARTIFACT_CONFIG_NAMES[cfg], dist, depth,
+                                                   simple_observations(pa, pr, mq, True),
+                                                   simple_observations(pa, pr, mq, False)))
             self.call_processor.process_call(call, self.sample_names)
 
 

@@ -32,6 +32,7 @@ using namespace vlrcore;
 constexpr int MAXS = VLR_VAR_MAXS;
 constexpr int MAXE = VLR_VAR_MAXE;
 constexpr int MAXD = VLR_VAR_MAXD;
+constexpr int PRIOR_CACHE = 32;
 
 // ------------------------------------------------------------------------------------------------ per-locus state
 struct Ops { // generic.rs LikelihoodOperands
@@ -216,6 +217,10 @@ struct Ctx {
     int scen_u[2 * MAXE];
     uint8_t art_u[2 * MAXE];
     double prior_absent; // Prior of the all-zero event (absent-only mode), NaN = not computed yet
+    // prior cache for all-discrete VAF vectors (prior.rs:718-736 keeps an LRU(1000) keyed by the VAF vector; the
+    // prior does not depend on the artifact config, so the 27 combinations of a trio are computed once per locus)
+    double pc_key[PRIOR_CACHE][MAXS], pc_val[PRIOR_CACHE];
+    int pc_n;
     uint32_t n_base;
     uint32_t n_pileup_evals;
 };
@@ -1006,7 +1011,27 @@ VLR_DEV_NOINLINE double prior_full(Ctx& c_, const Ops& ev) {
 }
 
 // Prior::compute (prior.rs:718-761)
+VLR_DEV_NOINLINE double prior_compute_uncached(Ctx& c_, const Ops& ev);
 VLR_DEV_NOINLINE double prior_compute(Ctx& c_, const Ops& ev) {
+    Ctx& c = warp_ctx(c_);
+    const int S = c.sc->S;
+    const bool discrete = (ev.disc_mask & ((1u << S) - 1u)) == ((1u << S) - 1u);
+    if (!discrete) return prior_compute_uncached(c, ev);
+    for (int i = 0; i < c.pc_n; ++i) {
+        bool same = true;
+        for (int s = 0; s < S; ++s) same = same && (c.pc_key[i][s] == ev.vaf[s]);
+        if (same) return c.pc_val[i];
+    }
+    const double p = prior_compute_uncached(c, ev);
+    if (c.pc_n < PRIOR_CACHE) {
+        const int i = c.pc_n;
+        for (int s = 0; s < S; ++s) c.pc_key[i][s] = ev.vaf[s];
+        c.pc_val[i] = p;
+        c.pc_n = i + 1;
+    }
+    return p;
+}
+VLR_DEV_NOINLINE double prior_compute_uncached(Ctx& c_, const Ops& ev) {
     Ctx& c = warp_ctx(c_);
     const DevScenario* sc = c.sc;
     if (!sc->full_prior && !sc->all_uniform) {
@@ -2019,6 +2044,7 @@ VLR_DEV void process_locus(const DevScenario* sc, const DevBatch* b, const DevRe
         if (!(h != h)) c.semr_override = (double)h * phred_to_ln;
     }
     c.prior_absent = NAN;
+    c.pc_n = 0;
     c.n_base = 0;
     c.n_pileup_evals = 0;
     for (int i = 0; i < 2 * E; ++i) c.map_set[i] = 0;
