@@ -162,7 +162,11 @@ struct MultiTask {
 };
 
 // One instance per warp, in SHARED memory: every lane sees the same (uniform) state, so a single copy replaces
-// 32 per-lane local-memory copies. Writes are either "all lanes store the identical value" or lane-0 + warp_sync().
+// 32 per-lane local-memory copies. Uniform state is updated by ALL lanes storing the identical value (each lane's own
+// store precedes its own load, so no lane can observe a stale value), lane-owned state (Ctx::mt[k] by lane k, slot
+// arrays) is published with warp_sync() before other lanes read it, and the warp collectives at the end of every
+// reads loop keep the lanes converged between those points. compute-sanitizer racecheck reports these same-value
+// stores as "warp level programming" hazards (profiles/README.md); memcheck and synccheck are clean.
 struct Ctx {
     const DevScenario* sc;
     const DevBatch* b;
@@ -1112,12 +1116,12 @@ VLR_DEV double joint(Ctx& c, int od) {
     // rust-bio Model::joint_prob records every base event; only artifact-free ones can enter an AFD (calling.rs:912)
     if (c.be != nullptr && c.art.id == 0) {
         if (c.n_rec < (uint32_t)BE_CAP) {
-            if (lane_id() == 0) {
-                double* e = c.be + (int64_t)c.n_rec * (2 + S);
-                e[0] = j;
-                e[1] = d_make((int)ops.lfc_mask, (int)ops.disc_mask);
-                for (int s = 0; s < S; ++s) e[2 + s] = ops.vaf[s];
-            }
+            // every lane stores the same record (no lane-divergent block in front of the uniform counter update)
+            double* e = c.be + (int64_t)c.n_rec * (2 + S);
+            e[0] = j;
+            e[1] = d_make((int)ops.lfc_mask, (int)ops.disc_mask);
+            for (int s = 0; s < S; ++s) e[2 + s] = ops.vaf[s];
+            warp_sync();
             c.n_rec++;
         } else {
             c.status |= VLR_ST_BASE_EVENTS_OVERFLOW;
