@@ -7,7 +7,7 @@ import numpy as np
 
 from oracle import oracle
 from tests import emu
-from tests.util import batch_from_reads, max_abs_delta, read
+from tests.util import batch_from_reads, max_abs_delta, pair_as_tumor_normal, read
 from varlociraptor_b200 import LocusBatch, Scenario, abi, synth
 
 TOL = 1e-9
@@ -161,3 +161,14 @@ events:
     full = Scenario.from_yaml(synth.SIMPLE_PEDIGREE_YAML, full_prior=True).flatten()
     _, b3 = synth.pedigree(60, seed=32, depth=30)
     _compare(oracle.call_batch(full, b3), emu.call_batch(full, b3))
+
+
+def test_config1_real_pileups_paired_as_tumor_normal(golden_dir):
+    """BASELINE config 1 (plumbing): ~100 tumor-normal loci built by pairing the real-data pileups embedded in the
+    reference's testcases (depth 2..2991, indels with prob_sample_alt < 0, homopolymer columns, f16/f32 quantised)."""
+    single = LocusBatch.load(os.path.join(golden_dir, "real_pileups.npz"))
+    n = single.n_loci
+    pairs = [(i, j) for i in range(n) for j in range(n) if i != j and (i + 2 * j) % 3 != 0][:40]
+    b = pair_as_tumor_normal(single, pairs)
+    flat = Scenario.tumor_normal(0.8).flatten()
+    _compare(oracle.call_batch(flat, b, afd_capacity=128, n_threads=4), emu.call_batch(flat, b, afd_capacity=128))

@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle
-from tests.util import batch_from_reads, max_abs_delta, read
+from tests.util import batch_from_reads, max_abs_delta, pair_as_tumor_normal, read
 from varlociraptor_b200 import LocusBatch, Scenario, abi, synth
 
 pytestmark = pytest.mark.gpu
@@ -214,3 +214,17 @@ def test_call_generic_reproduces_reference_text_fields(engine_mod, golden_dir):
         assert max(abs(g[1] - x[1]) for g, x in zip(got, e["AFD"])) <= 0.0101
         n += 1
     assert n == 8
+
+
+def test_config1_real_pileups_paired_as_tumor_normal(engine_mod, golden_dir):
+    """BASELINE config 1 (plumbing): ~100 tumor-normal loci built by pairing the real-data pileups embedded in the
+    reference's testcases (depth 2..2991, indels with prob_sample_alt < 0, homopolymer columns, f16/f32 quantised)."""
+    single = LocusBatch.load(os.path.join(golden_dir, "real_pileups.npz"))
+    n = single.n_loci
+    pairs = [(i, j) for i in range(n) for j in range(n) if i != j]
+    b = pair_as_tumor_normal(single, pairs)
+    assert b.n_loci >= 100
+    flat = Scenario.tumor_normal(0.8).flatten()
+    o = oracle.call_batch(flat, b, afd_capacity=128, n_threads=os.cpu_count() or 1)
+    g = engine_mod.PosteriorEngine(flat).call_batch(b, afd_capacity=128)
+    _compare(o, g, max_knife_fraction=0.1)

@@ -71,3 +71,26 @@ def max_abs_delta(a, b):
 
 def phred(lp):
     return -10.0 * np.asarray(lp, dtype=np.float64) / math.log(10.0)
+
+
+def pair_as_tumor_normal(single: LocusBatch, pairs):
+    """Two-sample (normal, tumor) batch from a one-sample batch: locus k = (normal = single[i], tumor = single[j])
+    for (i, j) in pairs; the locus flags are the tumor record's."""
+    cols = {k: [] for k in abi.BATCH_F32_COLUMNS}
+    flags, lflags, harts, hvars = [], [], [], []
+    offs = [0]
+    has_h = single.prob_homopolymer_artifact is not None
+    for i, j in pairs:
+        for s in (i, j):
+            lo, hi = int(single.read_offsets[s]), int(single.read_offsets[s + 1])
+            for k in cols:
+                cols[k].append(single.columns[k][lo:hi])
+            flags.append(single.read_flags[lo:hi])
+            if has_h:
+                harts.append(single.prob_homopolymer_artifact[lo:hi])
+                hvars.append(single.prob_homopolymer_variant[lo:hi])
+            offs.append(offs[-1] + hi - lo)
+        lflags.append(single.locus_flags[j])
+    cat = np.concatenate
+    return LocusBatch(2, np.array(offs, dtype=np.int64), {k: cat(v) for k, v in cols.items()}, cat(flags),
+                      np.array(lflags, dtype=np.uint32), cat(harts) if has_h else None, cat(hvars) if has_h else None)
