@@ -1246,14 +1246,20 @@ VLR_DEV_NOINLINE double grid_trapezoid(Ctx& c_, const double* gx, const double* 
         sf[rank] = gf[a];
     }
     warp_sync();
-    // interval terms ln((f_i + f_{i+1}) / 2 * dx): computed in both passes (max, then sum) - two short loops are
-    // smaller and spill less than one loop with a per-lane array
+    // interval terms ln((f_i + f_{i+1}) / 2 * dx), kept in registers for the sum pass (n <= GRID_CAP = 4 x 32 lanes)
+    constexpr int PER = (GRID_CAP + LANES - 1) / LANES;
+    double tl[PER];
     double tmax = neg_inf();
-#pragma unroll 1
-    for (int a = lane; a + 1 < n; a += LANES) {
-        const double dx = sx[a + 1] - sx[a];
-        double t = (dx > 0.0) ? ln_add_exp(sf[a], sf[a + 1]) + m_log(dx) - LN_2 : neg_inf();
-        if (t != t) t = INFINITY; // poison through the max
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+        const int a = lane + q * LANES;
+        double t = neg_inf();
+        if (a + 1 < n) {
+            const double dx = sx[a + 1] - sx[a];
+            if (dx > 0.0) t = ln_add_exp(sf[a], sf[a + 1]) + m_log(dx) - LN_2;
+            if (t != t) t = INFINITY; // poison through the max
+        }
+        tl[q] = t;
         tmax = fmax(tmax, t);
     }
     tmax = w_max_d(tmax);
@@ -1263,14 +1269,9 @@ VLR_DEV_NOINLINE double grid_trapezoid(Ctx& c_, const double* gx, const double* 
         return NAN;
     }
     double ssum = 0.0;
-#pragma unroll 1
-    for (int a = lane; a + 1 < n; a += LANES) {
-        const double dx = sx[a + 1] - sx[a];
-        if (dx > 0.0) {
-            const double t = ln_add_exp(sf[a], sf[a + 1]) + m_log(dx) - LN_2;
-            if (t != neg_inf()) ssum += m_exp(t - tmax);
-        }
-    }
+#pragma unroll
+    for (int q = 0; q < PER; ++q)
+        if (tl[q] != neg_inf()) ssum += m_exp(tl[q] - tmax);
     ssum = w_sum_d(ssum);
     warp_sync();
     return tmax + m_log(ssum);
