@@ -7,7 +7,7 @@ import numpy as np
 
 from oracle import oracle
 from tests import emu
-from tests.util import batch_from_reads, max_abs_delta, pair_as_tumor_normal, read
+from tests.util import FOUR_SAMPLE_YAML, batch_from_reads, four_sample_batch, max_abs_delta, pair_as_tumor_normal, read
 from varlociraptor_b200 import LocusBatch, Scenario, abi, synth
 
 TOL = 1e-9
@@ -171,4 +171,10 @@ def test_config1_real_pileups_paired_as_tumor_normal(golden_dir):
     pairs = [(i, j) for i in range(n) for j in range(n) if i != j and (i + 2 * j) % 3 != 0][:40]
     b = pair_as_tumor_normal(single, pairs)
     flat = Scenario.tumor_normal(0.8).flatten()
+    _compare(oracle.call_batch(flat, b, afd_capacity=128, n_threads=4), emu.call_batch(flat, b, afd_capacity=128))
+
+
+def test_four_samples_nested_ranges():
+    flat = Scenario.from_yaml(FOUR_SAMPLE_YAML).flatten()
+    b = four_sample_batch(12, seed=51)
     _compare(oracle.call_batch(flat, b, afd_capacity=128, n_threads=4), emu.call_batch(flat, b, afd_capacity=128))

@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle
-from tests.util import batch_from_reads, max_abs_delta, pair_as_tumor_normal, read
+from tests.util import FOUR_SAMPLE_YAML, batch_from_reads, four_sample_batch, max_abs_delta, pair_as_tumor_normal, read
 from varlociraptor_b200 import LocusBatch, Scenario, abi, synth
 
 pytestmark = pytest.mark.gpu
@@ -225,6 +225,15 @@ def test_config1_real_pileups_paired_as_tumor_normal(engine_mod, golden_dir):
     b = pair_as_tumor_normal(single, pairs)
     assert b.n_loci >= 100
     flat = Scenario.tumor_normal(0.8).flatten()
+    o = oracle.call_batch(flat, b, afd_capacity=128, n_threads=os.cpu_count() or 1)
+    g = engine_mod.PosteriorEngine(flat).call_batch(b, afd_capacity=128)
+    _compare(o, g, max_knife_fraction=0.1)
+
+
+def test_four_samples_full_capacity_variant(engine_mod):
+    """> 3 samples: served by the full-capacity kernel variant (vlr_call_kernel_vlr_full)."""
+    flat = Scenario.from_yaml(FOUR_SAMPLE_YAML).flatten()
+    b = four_sample_batch(60, seed=51)
     o = oracle.call_batch(flat, b, afd_capacity=128, n_threads=os.cpu_count() or 1)
     g = engine_mod.PosteriorEngine(flat).call_batch(b, afd_capacity=128)
     _compare(o, g, max_knife_fraction=0.1)

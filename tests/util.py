@@ -94,3 +94,45 @@ def pair_as_tumor_normal(single: LocusBatch, pairs):
     cat = np.concatenate
     return LocusBatch(2, np.array(offs, dtype=np.int64), {k: cat(v) for k, v in cols.items()}, cat(flags),
                       np.array(lflags, dtype=np.uint32), cat(harts) if has_h else None, cat(hvars) if has_h else None)
+
+
+FOUR_SAMPLE_YAML = """
+samples:
+  a:
+    universe: "0.0 | 0.5 | 1.0"
+  b:
+    universe: "0.0 | 0.5 | 1.0"
+  c:
+    universe: "[0.0,1.0]"
+    resolution: 0.1
+  d:
+    universe: "[0.0,1.0]"
+    resolution: 0.1
+    contamination:
+      by: c
+      fraction: 0.3
+events:
+  e1: "a:0.5 & b:0.0 & c:]0.0,1.0] & d:]0.0,1.0]"
+  e2: "a:0.0 & b:0.0 & c:]0.0,0.5[ & d:0.0"
+  e3: "a:1.0 & c:0.0"
+  e4: "a:0.0 & b:0.5 & c:0.0 & d:]0.0,1.0]"
+"""
+
+
+def four_sample_batch(n_loci, seed, depth=14):
+    """Four-sample loci (exercise the full-capacity engine variant: > 3 samples)."""
+    from varlociraptor_b200 import synth
+    _, b1 = synth.tumor_normal(n_loci, seed=seed, depth=depth)
+    _, b2 = synth.tumor_normal(n_loci, seed=seed + 1, depth=depth)
+    cols = {k: [] for k in abi.BATCH_F32_COLUMNS}
+    flags, offs = [], [0]
+    for i in range(n_loci):
+        for b in (b1, b2):
+            for s in range(2):
+                lo, hi = int(b.read_offsets[2 * i + s]), int(b.read_offsets[2 * i + s + 1])
+                for k in cols:
+                    cols[k].append(b.columns[k][lo:hi])
+                flags.append(b.read_flags[lo:hi])
+                offs.append(offs[-1] + hi - lo)
+    return LocusBatch(4, np.array(offs, dtype=np.int64), {k: np.concatenate(v) for k, v in cols.items()},
+                      np.concatenate(flags), b1.locus_flags)
