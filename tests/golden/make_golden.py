@@ -8,6 +8,7 @@ Outputs (committed):
                             decoded into the SoA batch layout (inputs of `call variants`)
   flamegraph_expected.json  what the reference printed for them (calls.vcf): PROB_* (PHRED f32),
                             AF, AFD text, DP, SAOBS/SROBS, plus the scenario
+  raw_info_records.json     verbatim INFO integer arrays of three reference records (codec round trip)
   real_pileups.npz/.json    single-sample observation-format-15 pileups embedded in
                             tests/resources/testcases/*/candidates.vcf (inputs only) with their scenario text
 """
@@ -88,6 +89,21 @@ def real_pileups():
                    "testcases": meta}, f, indent=1)
 
 
+def raw_info_records():
+    """Verbatim INFO integer arrays of a few reference records (bit-exact decode -> encode round trip test)."""
+    recs = obs_codec.parse_observation_vcf(os.path.join(REF, "flamegraph_profiling", "normal.vcf"))[:2]
+    extra = obs_codec.parse_observation_vcf(os.path.join(REF, "testcases", "test_false_negative_indel_call",
+                                                         "candidates.vcf"))
+    extra = [r for r in extra if "PROB_MAPPING" in r["info"]][:1]
+    out = [{"chrom": r["chrom"], "pos": r["pos"], "ref": r["ref"], "alt": r["alt"],
+            "info": {k: v for k, v in r["info"].items() if isinstance(v, list)}} for r in recs + extra]
+    with open(os.path.join(HERE, "raw_info_records.json"), "w") as f:
+        json.dump({"source": "raw INFO integer arrays of tests/resources/flamegraph_profiling/normal.vcf (2 records) "
+                             "and testcases/test_false_negative_indel_call/candidates.vcf (1 record)",
+                   "records": out}, f)
+
+
 if __name__ == "__main__":
     flamegraph()
     real_pileups()
+    raw_info_records()

@@ -87,3 +87,17 @@ def test_batch_slice_select_concat():
     assert all(np.array_equal(c.columns[k], b.columns[k], equal_nan=True) for k in abi.BATCH_F32_COLUMNS)
     s = b.select([9, 0])
     assert np.array_equal(s.slice(1, 2).columns["prob_alt"], b.slice(0, 1).columns["prob_alt"])
+
+
+def test_codec_encode_reproduces_the_reference_files_bit_for_bit(golden_dir):
+    """decode -> encode of records taken verbatim from the reference's observation files gives back the identical
+    INFO integer arrays (every tag the engine's batch layout carries)."""
+    raw = json.load(open(os.path.join(golden_dir, "raw_info_records.json")))
+    n_tags = 0
+    for rec in raw["records"]:
+        cols, flags, hart, hvar = obs_codec.decode_record(rec["info"])
+        back = obs_codec.encode_record(cols, flags, hart, hvar)
+        for tag, ints in back.items():
+            assert ints == rec["info"][tag], (rec["pos"], tag)
+            n_tags += 1
+    assert n_tags >= 3 * 14

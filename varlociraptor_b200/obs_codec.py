@@ -251,3 +251,88 @@ def batch_from_records(per_sample_records: List[List[dict]], **omit) -> LocusBat
     return LocusBatch(S, np.array(offsets, dtype=np.int64), {k: cat(v, np.float32) for k, v in cols.items()},
                       cat(flags, np.uint32), np.array(lflags, dtype=np.uint32),
                       cat(harts, np.float32) if any_h else None, cat(hvars, np.float32) if any_h else None)
+
+
+# ----------------------------------------------------------------------------- encoding (write_observations mirror)
+def _to_ints(body: bytearray) -> List[int]:
+    """bincode bytes -> the u16-as-integer INFO array (preprocessing/mod.rs:978-1000: zero-pad to even length)."""
+    if len(body) % 2:
+        body = body + b"\x00"
+    return np.frombuffer(bytes(body), dtype="<u2").astype(np.int64).tolist()
+
+
+def encode_mini_logprobs(values: Sequence[float]) -> List[int]:
+    """Vec<MiniLogProb> with `MiniLogProb::new` (src/utils/mod.rs:458-466): f16 if < -10 and the f16 projection keeps
+    the integer floor, else f32."""
+    body = bytearray(np.uint64(len(values)).tobytes())
+    with np.errstate(over="ignore", invalid="ignore"):
+        for v in np.asarray(values, dtype=np.float64):
+            h = np.float16(v)
+            if v < -10.0 and np.floor(np.float64(h)) == np.floor(v):
+                body += np.uint32(0).tobytes() + h.tobytes()
+            else:
+                body += np.uint32(1).tobytes() + np.float32(v).tobytes()
+    return _to_ints(body)
+
+
+def encode_optional_mini_logprobs(values: Sequence[float]) -> List[int]:
+    """Vec<Option<MiniLogProb>>; NaN -> None."""
+    body = bytearray(np.uint64(len(values)).tobytes())
+    with np.errstate(over="ignore", invalid="ignore"):
+        for v in np.asarray(values, dtype=np.float64):
+            if np.isnan(v):
+                body += b"\x00"
+                continue
+            body += b"\x01"
+            h = np.float16(v)
+            if v < -10.0 and np.floor(np.float64(h)) == np.floor(v):
+                body += np.uint32(0).tobytes() + h.tobytes()
+            else:
+                body += np.uint32(1).tobytes() + np.float32(v).tobytes()
+    return _to_ints(body)
+
+
+def encode_enum(values: Sequence[int]) -> List[int]:
+    body = bytearray(np.uint64(len(values)).tobytes())
+    for v in values:
+        body += np.uint32(int(v)).tobytes()
+    return _to_ints(body)
+
+
+def encode_bitvec(bits: Sequence[bool]) -> List[int]:
+    """bv::BitVec<u8>: Option<Box<[u8]>> blocks + u64 bit length (an empty vector has no block storage)."""
+    bits = np.asarray(bits, dtype=np.uint8)
+    n = len(bits)
+    if n == 0:
+        return _to_ints(bytearray(b"\x00" + np.uint64(0).tobytes()))
+    blocks = np.packbits(bits, bitorder="little").tobytes()
+    return _to_ints(bytearray(b"\x01" + np.uint64(len(blocks)).tobytes() + blocks + np.uint64(n).tobytes()))
+
+
+def encode_optional_i8(has: Sequence[bool], values: Sequence[int]) -> List[int]:
+    body = bytearray(np.uint64(len(has)).tobytes())
+    for h, v in zip(has, values):
+        body += (b"\x01" + np.int8(v).tobytes()) if h else b"\x00"
+    return _to_ints(body)
+
+
+def encode_record(cols: Dict[str, np.ndarray], flags: np.ndarray, hart: Optional[np.ndarray] = None,
+                  hvar: Optional[np.ndarray] = None) -> Dict[str, List[int]]:
+    """SoA columns of one pileup -> the INFO arrays `write_observations` emits (preprocessing/mod.rs:921-1038).
+    FRAGMENT_ID and THIRD_ALLELE_EVIDENCE are not carried by the engine's batch layout and are not produced."""
+    flags = np.asarray(flags, dtype=np.uint32)
+    info = {tag: encode_mini_logprobs(cols[dst]) for tag, dst in _PROB_TAGS.items()}
+    info["STRAND"] = encode_enum((flags >> abi.RF_STRAND_SHIFT) & 3)
+    info["READ_ORIENTATION"] = encode_enum((flags >> abi.RF_ORIENT_SHIFT) & 15)
+    info["READ_POSITION"] = encode_enum(np.where(flags & abi.RF_READPOS_MAJOR, 0, 1))
+    info["ALT_LOCUS"] = encode_enum((flags >> abi.RF_ALTLOCUS_SHIFT) & 3)
+    info["SOFTCLIPPED"] = encode_bitvec((flags & abi.RF_SOFTCLIPPED) != 0)
+    info["PAIRED"] = encode_bitvec((flags & abi.RF_PAIRED) != 0)
+    info["IS_MAX_MAPQ"] = encode_bitvec((flags & abi.RF_MAX_MAPQ) != 0)
+    if hart is not None and np.any(~np.isnan(hart)):  # only written if any read has homopolymer info (:1018-1035)
+        info["PROB_HOMOPOLYMER_ARTIFACT_OBSERVABLE"] = encode_optional_mini_logprobs(hart)
+        info["PROB_HOMOPOLYMER_VARIANT_OBSERVABLE"] = encode_optional_mini_logprobs(hvar)
+        has = (flags & abi.RF_HAS_HOMOPOLYMER_LEN) != 0
+        val = ((flags >> abi.RF_HOMOPOLYMER_LEN_SHIFT) & 0xff).astype(np.uint8).view(np.int8)
+        info["HOMOPOLYMER_INDEL_LEN"] = encode_optional_i8(has, val)
+    return info
