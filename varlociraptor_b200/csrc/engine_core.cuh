@@ -150,6 +150,7 @@ struct LeafFast {
     int n_dep, n_tasks, parent, t;
     bool prior_per_point; // the prior has to be evaluated per point (non-uniform priors, or a universe with holes)
     bool uniform, t_ploidy0, coef_in_sm, record;
+    bool parent_disc; // the parent sample's event is discrete (Set node) rather than an integration abscissa
 };
 // One of the (up to MT) leaf integrations a warp advances concurrently: they differ in the VAF of the parent sample
 // (the abscissae of the enclosing integration's current batch).
@@ -158,6 +159,7 @@ struct MultiTask {
     double parent_x, lh_const, prior_const, best_f, best_x;
     double xs[8], fs[8];
     int n, k, slot_base;
+    int event_slot;   // MAP slot the task's base events belong to (2 * event + artifact config ? 1 : 0)
     bool have_best, active, overflow;
 };
 
@@ -1425,14 +1427,15 @@ VLR_DEV_NOINLINE void multi_eval_slow(Ctx& c_, int total) {
 // Materialises the operands of (task, x) at c.ops[od + 1] (parent sample at the task's abscissa, leaf sample at x).
 VLR_DEV void multi_ops(Ctx& c, int od, int task, double x) {
     c.ops[od + 1] = c.ops[od];
-    if (c.leaf.parent >= 0) ops_push(c.ops[od + 1], c.leaf.parent, c.mt[task].parent_x, false);
+    if (c.leaf.parent >= 0) ops_push(c.ops[od + 1], c.leaf.parent, c.mt[task].parent_x, c.leaf.parent_disc);
     ops_push(c.ops[od + 1], c.leaf.t, x, false);
 }
 
 // Decides whether the fast path can serve the leaf integration(s) of `node` over [a, b] and hoists the constants.
 // parent >= 0: n_tasks integrations that differ in the VAF of sample `parent` (parent_xs); parent < 0: one.
 VLR_DEV_NOINLINE bool leaf_setup(Ctx& c_, const vlr_node_t& node, int od, double a, double b, double res, int parent,
-                                 int n_tasks, const double* parent_xs) {
+                                 int n_tasks, const double* parent_xs, const int* event_slots = nullptr,
+                                 bool parent_disc = false) {
     Ctx& c = warp_ctx(c_);
     const DevScenario* sc = c.sc;
     const int S = sc->S;
@@ -1466,6 +1469,7 @@ VLR_DEV_NOINLINE bool leaf_setup(Ctx& c_, const vlr_node_t& node, int od, double
     }
     L.n_dep = n_dep;
     L.n_tasks = n_tasks;
+    L.parent_disc = parent_disc;
     L.parent = parent;
     L.t = t;
     L.coef_in_sm = c.coef_in_sm != 0;
@@ -1549,6 +1553,7 @@ VLR_DEV_NOINLINE bool leaf_setup(Ctx& c_, const vlr_node_t& node, int od, double
         }
         m.lh_const = lh_const;
         m.prior_const = prior_const;
+        m.event_slot = event_slots ? event_slots[k] : c.cur_slot;
         m.st.init(a, b, res);
         m.n = 0;
         m.k = 0;
@@ -1611,7 +1616,7 @@ VLR_DEV_NOINLINE void leaf_multi_finish(Ctx& c_, int od, unsigned disc, double* 
     const int t = c.leaf.t;
     for (int k = 0; k < T; ++k) {
         MultiTask& m = c.mt[k];
-        const int slot = c.cur_slot;
+        const int slot = m.event_slot;
         if (m.have_best && (!c.map_set[slot] || m.best_f > c.map_joint[slot])) {
             c.map_set[slot] = 1;
             c.map_joint[slot] = m.best_f;
@@ -1632,7 +1637,10 @@ VLR_DEV_NOINLINE void leaf_multi_run(Ctx& c_, int od, double* out) {
     const int t = c.leaf.t;
     const bool in_sm = c.leaf.coef_in_sm, per_point = c.leaf.prior_per_point, record = c.leaf.record;
     unsigned disc = c.ops[od].disc_mask & ~(1u << t);
-    if (c.leaf.parent >= 0) disc &= ~(1u << c.leaf.parent);
+    if (c.leaf.parent >= 0) {
+        if (c.leaf.parent_disc) disc |= 1u << c.leaf.parent;
+        else disc &= ~(1u << c.leaf.parent);
+    }
     for (;;) {
         // ---- every active task asks its adaptive search for the next batch; slots = exclusive scan over tasks
         int my_k = 0;
@@ -2017,6 +2025,90 @@ VLR_DEV_NOINLINE void afd_pass(Ctx& c_, int best_scen, int map_slot, double marg
     }
 }
 
+// Events of the shape  parent:{one VAF} -> leaf:Range  (tumor-normal: somatic_tumor, germline_het, germline_hom) are
+// independent leaf integrations that differ only in the parent's VAF: they run as ONE concurrent group instead of
+// one after the other. Mirrors, per event, exactly what density() does for the Set root (generic.rs:294-317: clear-ref
+// shortcut, single-VAF push as a discrete event) and for the Range child (:331-395). `done` marks the events handled
+// here; the caller walks the remaining ones through density().
+VLR_DEV_NOINLINE void run_grouped_chain_events(Ctx& c_, bool twin, double ln_event_prior, unsigned& done) {
+    Ctx& c = warp_ctx(c_);
+    const DevScenario* sc = c.sc;
+    const int E = sc->E;
+    done = 0;
+    if (sc->n_lfc_nodes != 0) return;
+    int ev_idx[MT];
+    int slots[MT];
+    double* xs = c.xs[0];
+    int n = 0, parent = -1, child_ni = -1;
+    for (int e = 0; e < E && n < MT - 1; ++e) {
+        const vlr_event_t& ev = sc->events[e];
+        if (twin && !ev.has_artifact_twin) continue;
+        if (ev.n_roots != 1) continue;
+        const vlr_node_t& root = sc->nodes[ev.first_root];
+        if (root.kind != VLR_NODE_SET || root.n_vafs != 1 || root.n_children != 1) continue;
+        const vlr_node_t& child = sc->nodes[root.first_child];
+        if (child.kind != VLR_NODE_RANGE || child.n_children != 0 || child.sample == root.sample) continue;
+        if (n > 0) { // same parent sample and the same leaf integration as the group's first event
+            const vlr_node_t& c0 = sc->nodes[child_ni];
+            if (root.sample != parent || child.sample != c0.sample || child.start != c0.start || child.end != c0.end ||
+                child.left_exclusive != c0.left_exclusive || child.right_exclusive != c0.right_exclusive)
+                continue;
+        } else {
+            parent = root.sample;
+            child_ni = root.first_child;
+        }
+        ev_idx[n] = e;
+        n++;
+    }
+    if (n < 2) return;
+    // the leaf integration as density() would set it up for the Range child (identical for every member)
+    const vlr_node_t& child = sc->nodes[child_ni];
+    const int cs = child.sample;
+    const int n_obs = c.n_obs[cs];
+    Range vafs{child.start, child.end, child.left_exclusive != 0, child.right_exclusive != 0};
+    if (range_is_empty(vafs) || range_is_singleton(vafs)) return;
+    if (c.clear_ref[cs] && vafs.start > 0.0) return;
+    const double res = sc->samples[cs].resolution;
+    const double min_vaf = range_observable_min(vafs, n_obs), max_vaf = range_observable_max(vafs, n_obs);
+    if (!(min_vaf <= max_vaf) || (max_vaf - min_vaf) < res || n_obs < 5) return;
+    // members cut by the Set node's clear-ref shortcut contribute ln 0 without any evaluation
+    int m = 0;
+    int live[MT];
+    for (int i = 0; i < n; ++i) {
+        const int e = ev_idx[i];
+        const double v = sc->set_vafs[sc->nodes[sc->events[e].first_root].vaf_offset];
+        done |= 1u << e;
+        if (c.clear_ref[parent] && v > 0.0) {
+            if (twin) c.ev_twin[e].add(ln_event_prior + neg_inf());
+            else c.ev_plain[e].add(ln_event_prior + neg_inf());
+            continue;
+        }
+        live[m] = e;
+        xs[m] = v;
+        slots[m] = 2 * e + (twin ? 1 : 0);
+        m++;
+    }
+    if (m == 0) return;
+    Ops& base = c.ops[0];
+    for (int s = 0; s < MAXS; ++s) base.vaf[s] = 0.0;
+    base.set_mask = base.disc_mask = base.lfc_mask = 0;
+    c.ops[1] = base;
+    ops_push(c.ops[1], parent, xs[0], true);
+    c.cur_slot = slots[0];
+    if (!leaf_setup(c, child, 1, min_vaf, max_vaf, res, parent, m, xs, slots, true)) {
+        for (int i = 0; i < m; ++i) done &= ~(1u << live[i]); // generic path for the live members
+        return;
+    }
+    double* out = c.fs[0];
+    leaf_multi_run(c, 1, out);
+    for (int i = 0; i < m; ++i) {
+        const double d = out[i];
+        if (d != d) c.status |= VLR_ST_NAN;
+        if (twin) c.ev_twin[live[i]].add(ln_event_prior + d);
+        else c.ev_plain[live[i]].add(ln_event_prior + d);
+    }
+}
+
 // `coef_sm` (capacity sm_reads) is the warp's shared-memory coefficient arena, `coef` (capacity coef_cap) the global
 // one used when the locus has more kept reads than fit in shared memory.
 VLR_DEV void process_locus(const DevScenario* sc, const DevBatch* b, const DevResults* res, WarpWs* ws, double* coef,
@@ -2089,9 +2181,12 @@ VLR_DEV void process_locus(const DevScenario* sc, const DevBatch* b, const DevRe
             c.lc_n[s] = 0;
             read_coefficients(c, s);
         }
+        unsigned grouped = 0;
+        run_grouped_chain_events(c, ci > 0, ci == 0 ? LN_05 : twin_prior, grouped);
         for (int e = 0; e < E; ++e) {
             const vlr_event_t& ev = sc->events[e];
             if (ci > 0 && !ev.has_artifact_twin) continue;
+            if (grouped & (1u << e)) continue;
             c.cur_slot = 2 * e + (ci > 0 ? 1 : 0);
             for (int r = 0; r < ev.n_roots; ++r) {
                 Ops& ops = c.ops[0];
