@@ -270,7 +270,7 @@ def main():
     clocks = sampler.stop()
     ms_total = ev0.elapsed_time(ev1)
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
-    launches = args.steps  # one vlr_call_kernel per step (the ticket reset is a memset, not a kernel)
+    launches = args.steps * eng.launches  # kernels of one device-entry call (vlr_last_launch_count) x timed steps
 
     # end to end through the host-buffer entry of the C-ABI
     for _ in range(1):

@@ -10,6 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "libvlr_engine_emu.so")
 _SRC = [os.path.join(_HERE, "emu_driver.cpp"),
         os.path.join(_HERE, "..", "..", "varlociraptor_b200", "csrc", "engine_core.cuh"),
+        os.path.join(_HERE, "..", "..", "varlociraptor_b200", "csrc", "engine_wave.cuh"),
         os.path.join(_HERE, "..", "..", "varlociraptor_b200", "csrc", "scenario_prep.h"),
         os.path.join(_HERE, "..", "..", "varlociraptor_b200", "csrc", "engine_types.cuh"),
         os.path.join(_HERE, "..", "..", "include", "vlr_engine.h")]
@@ -24,13 +25,33 @@ def build(force=False):
     return _LIB
 
 
-def call_batch(flat_scenario, batch, afd_capacity=0) -> CallResults:
+def _load():
     global _lib
     if _lib is None:
         build()
         _lib = C.CDLL(_LIB)
-        _lib.vlr_emu_call_batch.restype = C.c_int32
-        _lib.vlr_emu_call_batch.argtypes = [C.POINTER(abi.Scenario), C.POINTER(abi.Batch), C.POINTER(abi.Results)]
+        for fn in (_lib.vlr_emu_call_batch, _lib.vlr_emu_wave_call_batch):
+            fn.restype = C.c_int32
+            fn.argtypes = [C.POINTER(abi.Scenario), C.POINTER(abi.Batch), C.POINTER(abi.Results)]
+    return _lib
+
+
+def wave_call_batch(flat_scenario, batch, afd_capacity=0):
+    """The wavefront pipeline run sequentially on the host. Returns (results, number of loci deferred to the generic
+    engine); raises LookupError when the scenario does not have the two-level chain shape."""
+    lib = _load()
+    out = CallResults(batch.n_loci, batch.n_samples, flat_scenario.n_events, afd_capacity)
+    cb, cr = batch.as_c(), out.as_c()
+    rc = lib.vlr_emu_wave_call_batch(C.byref(flat_scenario.c), C.byref(cb), C.byref(cr))
+    if rc == -100:
+        raise LookupError("scenario is not served by the wavefront pipeline")
+    if rc < 0:
+        raise RuntimeError("emu failed with status %d" % -rc)
+    return out, rc
+
+
+def call_batch(flat_scenario, batch, afd_capacity=0) -> CallResults:
+    _load()
     out = CallResults(batch.n_loci, batch.n_samples, flat_scenario.n_events, afd_capacity)
     cb, cr = batch.as_c(), out.as_c()
     rc = _lib.vlr_emu_call_batch(C.byref(flat_scenario.c), C.byref(cb), C.byref(cr))

@@ -7,6 +7,12 @@
 #include <cstring>
 #include <vector>
 
+#define VLR_VARIANT vlr_small
+#define VLR_VAR_MAXS 3
+#define VLR_VAR_MAXE 8
+#define VLR_VAR_MAXD 6
+#define VLR_VAR_WAVE 1
+#include "../../varlociraptor_b200/csrc/engine_core.cuh"
 #define VLR_VARIANT vlr_full
 #define VLR_VAR_MAXS VLR_MAX_SAMPLES
 #define VLR_VAR_MAXE VLR_MAX_EVENTS
@@ -14,14 +20,7 @@
 #include "../../varlociraptor_b200/csrc/engine_core.cuh"
 #include "../../varlociraptor_b200/csrc/scenario_prep.h"
 
-extern "C" int32_t vlr_emu_call_batch(const vlr_scenario_t* sc, const vlr_batch_t* batch, vlr_results_t* results) {
-    using namespace vlrcore;
-    using namespace vlr_full;
-    ScenarioPrep prep;
-    if (!prep.build(sc)) return VLR_ERR_INVALID_ARGUMENT;
-    DevScenario ds = prep.view(sc->samples, sc->events, sc->nodes, sc->set_vafs, sc->spectra, prep.lfc_nodes.data(),
-                               prep.lfc_ordinal.data());
-    DevBatch db;
+static void emu_views(const vlr_batch_t* batch, vlr_results_t* results, vlrcore::DevBatch& db, vlrcore::DevResults& dr) {
     db.n_loci = batch->n_loci;
     db.read_base = 0;
     db.read_offsets = batch->read_offsets;
@@ -38,7 +37,6 @@ extern "C" int32_t vlr_emu_call_batch(const vlr_scenario_t* sc, const vlr_batch_
     db.lflags = batch->locus_flags;
     db.het_phred = batch->locus_heterozygosity_phred;
     db.semr_phred = batch->locus_semr_phred;
-    DevResults dr;
     dr.log_post = results->log_posteriors;
     dr.log_marginal = results->log_marginal;
     dr.map_vaf = results->map_vaf;
@@ -50,6 +48,18 @@ extern "C" int32_t vlr_emu_call_batch(const vlr_scenario_t* sc, const vlr_batch_
     dr.afd_count = results->afd_count;
     dr.afd_vaf = results->afd_vaf;
     dr.afd_logp = results->afd_logp;
+}
+
+extern "C" int32_t vlr_emu_call_batch(const vlr_scenario_t* sc, const vlr_batch_t* batch, vlr_results_t* results) {
+    using namespace vlrcore;
+    using namespace vlr_full;
+    ScenarioPrep prep;
+    if (!prep.build(sc)) return VLR_ERR_INVALID_ARGUMENT;
+    DevScenario ds = prep.view(sc->samples, sc->events, sc->nodes, sc->set_vafs, sc->spectra, prep.lfc_nodes.data(),
+                               prep.lfc_ordinal.data());
+    DevBatch db;
+    DevResults dr;
+    emu_views(batch, results, db, dr);
     int64_t max_reads = 1;
     const int S = sc->n_samples;
     for (int64_t i = 0; i < batch->n_loci; ++i) {
@@ -64,4 +74,88 @@ extern "C" int32_t vlr_emu_call_batch(const vlr_scenario_t* sc, const vlr_batch_
     delete c;
     delete ws;
     return VLR_OK;
+}
+
+// The wavefront pipeline (engine_wave.cuh), run sequentially: prep per locus, rounds of tasks, lc advance, finish, and
+// the generic engine for deferred loci — the same device functions the CUDA kernels call, one "thread" at a time.
+// Returns the number of deferred loci (>= 0) or a negative status; -100 = scenario not eligible.
+extern "C" int32_t vlr_emu_wave_call_batch(const vlr_scenario_t* sc, const vlr_batch_t* batch, vlr_results_t* results) {
+    using namespace vlrcore;
+    using namespace vlr_small;
+    ScenarioPrep prep;
+    if (!prep.build(sc)) return -VLR_ERR_INVALID_ARGUMENT;
+    const WavePlan wp = prep.wave_plan();
+    if (!wp.eligible) return -100;
+    DevScenario ds = prep.view(sc->samples, sc->events, sc->nodes, sc->set_vafs, sc->spectra, prep.lfc_nodes.data(),
+                               prep.lfc_ordinal.data());
+    DevBatch db;
+    DevResults dr;
+    emu_views(batch, results, db, dr);
+    const int S = sc->n_samples;
+    const int64_t L = batch->n_loci;
+    int64_t max_reads = 1;
+    for (int64_t i = 0; i < L; ++i) {
+        int64_t n = batch->read_offsets[(i + 1) * S] - batch->read_offsets[i * S];
+        if (n > max_reads) max_reads = n;
+    }
+    const bool want_be = results->afd_capacity > 0;
+    WaveCounters cnt;
+    std::memset(&cnt, 0, sizeof cnt);
+    const int lc_cap = (int)L * 4 + 16; // some loci overflow on purpose (-> deferred)
+    std::vector<WaveLocus> loci((size_t)L);
+    std::vector<WaveLC> lcs((size_t)lc_cap);
+    std::vector<double> og_x((size_t)lc_cap * W_OGRID), og_f((size_t)lc_cap * W_OGRID);
+    const int64_t coef_cap = batch->n_reads * 4 + 64;
+    std::vector<double> coef((size_t)coef_cap * 4);
+    std::vector<WaveTask> tasks0((size_t)lc_cap * W_MAXT), tasks1((size_t)lc_cap * W_MAXT);
+    std::vector<int> list0((size_t)lc_cap), list1((size_t)lc_cap), deferred((size_t)L + 1);
+    std::vector<double> gx(W_GCAP), gf(W_GCAP);
+    std::vector<short> gn(W_GCAP);
+    std::vector<double> be(want_be ? (size_t)L * BE_CAP * 4 : 4);
+    std::vector<unsigned> be_n((size_t)L + 1);
+    WaveBufs wb;
+    wb.cnt = &cnt;
+    wb.loci = loci.data();
+    wb.lcs = lcs.data();
+    wb.og_x = og_x.data();
+    wb.og_f = og_f.data();
+    wb.coef = coef.data();
+    wb.tasks[0] = tasks0.data();
+    wb.tasks[1] = tasks1.data();
+    wb.list[0] = list0.data();
+    wb.list[1] = list1.data();
+    wb.deferred = deferred.data();
+    wb.gx = gx.data();
+    wb.gf = gf.data();
+    wb.gn = gn.data();
+    wb.be = want_be ? be.data() : nullptr;
+    wb.be_n = be_n.data();
+    wb.coef_cap = coef_cap;
+    wb.lc_cap = lc_cap;
+    wb.g_stride = 1;
+    WarpWs* ws = new WarpWs;
+    Ctx* c = new Ctx;
+    for (int64_t i = 0; i < L; ++i) wave_prep_locus(&ds, &db, wp, wb, i, (int)i, want_be, *c);
+    for (int round = 0; round < wp.max_rounds; ++round) {
+        const int n_list = (int)cnt.list_n[round];
+        const int* list = wb.list[round & 1];
+        for (int k = 0; k < n_list; ++k) {
+            WaveLC& lc = lcs[list[k]];
+            for (int t = 0; t < lc.task_count; ++t) {
+                WaveTask& task = wb.tasks[round & 1][lc.task_base + t];
+                wave_task_run(&ds, wp, lc, task, reinterpret_cast<const double2*>(wb.coef + lc.coefT * 4),
+                              reinterpret_cast<const double2*>(wb.coef + lc.coefP * 4), wb.gx, wb.gf, wb.gn, 1,
+                              want_be ? wb.be + (size_t)lc.li * BE_CAP * 4 : nullptr, &wb.be_n[lc.li]);
+            }
+        }
+        for (int k = 0; k < n_list; ++k) wave_lc_advance(wp, wb, list[k], round);
+    }
+    for (int64_t i = 0; i < L; ++i) wave_finish_locus(&ds, &db, &dr, wp, wb, ws, i, (int)i, *c);
+    std::vector<double> coef2((size_t)max_reads * 4);
+    std::vector<double> be2((size_t)BE_CAP * (2 + S));
+    for (unsigned k = 0; k < cnt.n_deferred; ++k)
+        process_locus(&ds, &db, &dr, ws, coef2.data(), nullptr, 0, be2.data(), (int)max_reads, deferred[k], *c);
+    delete c;
+    delete ws;
+    return (int32_t)cnt.n_deferred;
 }

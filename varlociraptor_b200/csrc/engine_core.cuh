@@ -803,13 +803,13 @@ VLR_DEV bool prior_het(const Ctx& c, double& out) { // prior.rs:263-270
     out = m_log(m_exp(m_log(h)) * vtf(c));
     return true;
 }
-VLR_DEV_NOINLINE bool universe_contains(const Ctx& c, int s, double v) {
-    const vlr_sample_t& sm = c.sc->samples[s];
+VLR_DEV_NOINLINE bool universe_contains_sc(const DevScenario* sc, int s, double v) {
+    const vlr_sample_t& sm = sc->samples[s];
     for (int i = 0; i < sm.n_universe; ++i) {
-        const vlr_spectrum_t& sp = c.sc->spectra[sm.universe_offset + i];
+        const vlr_spectrum_t& sp = sc->spectra[sm.universe_offset + i];
         if (sp.kind == VLR_SPECTRUM_SET) {
             for (int j = 0; j < sp.n_vafs; ++j)
-                if (c.sc->set_vafs[sp.vaf_offset + j] == v) return true;
+                if (sc->set_vafs[sp.vaf_offset + j] == v) return true;
         } else {
             Range r{sp.start, sp.end, sp.left_exclusive != 0, sp.right_exclusive != 0};
             if (range_contains(r, v)) return true;
@@ -817,6 +817,7 @@ VLR_DEV_NOINLINE bool universe_contains(const Ctx& c, int s, double v) {
     }
     return false;
 }
+VLR_DEV bool universe_contains(const Ctx& c, int s, double v) { return universe_contains_sc(c.sc, s, v); }
 VLR_DEV double prob_somatic_mutation(double rate, double somatic_vaf) { // prior.rs:440-456
     if (relative_eq(somatic_vaf, 0.0)) return ln_one_minus_exp(rate);
     return rate;
@@ -2109,6 +2110,98 @@ VLR_DEV_NOINLINE void run_grouped_chain_events(Ctx& c_, bool twin, double ln_eve
     }
 }
 
+// End of a locus (calling.rs:760-937 after the joint probabilities are known): marginal, posteriors, artifact
+// probability, best event, MAP and AFD from the per-event accumulators and MAP slots in the Ctx. Shared by the
+// generic warp-per-locus engine and the wavefront pipeline (engine_wave.cuh).
+VLR_DEV_NOINLINE void locus_tail(Ctx& c_, int n_twins) {
+    Ctx& c = warp_ctx(c_);
+    const DevScenario* sc = c.sc;
+    const DevResults* res = c.res;
+    const int S = sc->S, E = sc->E;
+    const int64_t locus = c.locus;
+    Lse* ev_plain = c.ev_plain;
+    Lse* ev_twin = c.ev_twin;
+    // marginal over the event universe, in universe order [e plain, e twin]...
+    double* joint_u = c.joint_u;
+    int* scen_u = c.scen_u;
+    uint8_t* art_u = c.art_u;
+    int nu = 0;
+    Lse marg;
+    marg.init();
+    for (int e = 0; e < E; ++e) {
+        joint_u[nu] = ev_plain[e].value();
+        scen_u[nu] = e;
+        art_u[nu] = 0;
+        marg.add(joint_u[nu]);
+        nu++;
+        if (sc->events[e].has_artifact_twin && n_twins > 0) {
+            joint_u[nu] = ev_twin[e].value();
+            scen_u[nu] = e;
+            art_u[nu] = 1;
+            marg.add(joint_u[nu]);
+            nu++;
+        }
+    }
+    const double marginal = marg.value();
+    if (marginal == neg_inf()) c.status |= VLR_ST_MARGINAL_ZERO;
+    if (marginal != marginal) c.status |= VLR_ST_NAN;
+
+    int best = 0;
+    {
+        double bestv = joint_u[0] - marginal;
+        for (int i = 1; i < nu; ++i) {
+            double v = joint_u[i] - marginal;
+            if (v >= bestv) { // itertools minmax_by_key: the last maximum wins (calling.rs:762-769)
+                bestv = v;
+                best = i;
+            }
+        }
+    }
+    Lse art;
+    art.init();
+    double* lp = res->log_post + locus * (int64_t)(E + 1);
+    double* my_lp = c.my_lp;
+    for (int i = 0; i < nu; ++i) {
+        double post = joint_u[i] - marginal;
+        if (art_u[i]) art.add(post);
+        else my_lp[scen_u[i]] = post;
+    }
+    const double prob_artifact = art.value();
+    my_lp[E] = prob_artifact;
+    bool is_artifact = true;
+    for (int e = 0; e < E; ++e)
+        if (!(my_lp[e] < prob_artifact)) is_artifact = false;
+    if (is_artifact) c.status |= VLR_ST_IS_ARTIFACT;
+
+    // MAP (calling.rs:844-890): events of a valid scenario are disjoint (grammar/mod.rs:238-272 rejects overlaps),
+    // so the base events contained in the best event are the ones its own tree produced.
+    const int best_scen = scen_u[best];
+    int map_slot = -1;
+    {
+        int sp = 2 * best_scen, st = 2 * best_scen + 1;
+        if (c.map_set[sp]) map_slot = sp;
+        if (is_artifact && c.map_set[st] && (map_slot < 0 || c.map_joint[st] > c.map_joint[sp])) map_slot = st;
+    }
+    if (map_slot < 0) c.status |= VLR_ST_NO_MAP;
+
+    if (lane_id() == 0) {
+        for (int e = 0; e <= E; ++e) lp[e] = my_lp[e];
+        if (res->log_marginal) res->log_marginal[locus] = marginal;
+        if (res->best_event) res->best_event[locus] = 2 * best_scen + (art_u[best] ? 1 : 0);
+        if (res->n_base_events) res->n_base_events[locus] = c.n_base;
+        for (int s = 0; s < S; ++s) {
+            double v = NAN;
+            if (map_slot >= 0) v = c.map_cfg[map_slot] != 0 ? 0.0 : c.map_vaf[map_slot][s];
+            res->map_vaf[locus * S + s] = v;
+        }
+        if (res->map_config) res->map_config[locus] = map_slot >= 0 ? c.map_cfg[map_slot] : 0;
+        if (res->afd_capacity > 0)
+            for (int s = 0; s < S; ++s) res->afd_count[locus * S + s] = 0;
+    }
+    if (res->afd_capacity > 0) afd_pass(c, best_scen, map_slot, marginal);
+    if (lane_id() == 0) res->status[locus] = c.status;
+}
+
 // `coef_sm` (capacity sm_reads) is the warp's shared-memory coefficient arena, `coef` (capacity coef_cap) the global
 // one used when the locus has more kept reads than fit in shared memory.
 VLR_DEV void process_locus(const DevScenario* sc, const DevBatch* b, const DevResults* res, WarpWs* ws, double* coef,
@@ -2199,89 +2292,16 @@ VLR_DEV void process_locus(const DevScenario* sc, const DevBatch* b, const DevRe
         }
     }
 
-    // marginal over the event universe, in universe order [e plain, e twin]...
-    double* joint_u = c.joint_u;
-    int* scen_u = c.scen_u;
-    uint8_t* art_u = c.art_u;
-    int nu = 0;
-    Lse marg;
-    marg.init();
-    for (int e = 0; e < E; ++e) {
-        joint_u[nu] = ev_plain[e].value();
-        scen_u[nu] = e;
-        art_u[nu] = 0;
-        marg.add(joint_u[nu]);
-        nu++;
-        if (sc->events[e].has_artifact_twin && plan.n_twins > 0) {
-            joint_u[nu] = ev_twin[e].value();
-            scen_u[nu] = e;
-            art_u[nu] = 1;
-            marg.add(joint_u[nu]);
-            nu++;
-        }
-    }
-    const double marginal = marg.value();
-    if (marginal == neg_inf()) c.status |= VLR_ST_MARGINAL_ZERO;
-    if (marginal != marginal) c.status |= VLR_ST_NAN;
-
-    int best = 0;
-    {
-        double bestv = joint_u[0] - marginal;
-        for (int i = 1; i < nu; ++i) {
-            double v = joint_u[i] - marginal;
-            if (v >= bestv) { // itertools minmax_by_key: the last maximum wins (calling.rs:762-769)
-                bestv = v;
-                best = i;
-            }
-        }
-    }
-    Lse art;
-    art.init();
-    double* lp = res->log_post + locus * (int64_t)(E + 1);
-    double* my_lp = c.my_lp;
-    for (int i = 0; i < nu; ++i) {
-        double post = joint_u[i] - marginal;
-        if (art_u[i]) art.add(post);
-        else my_lp[scen_u[i]] = post;
-    }
-    const double prob_artifact = art.value();
-    my_lp[E] = prob_artifact;
-    bool is_artifact = true;
-    for (int e = 0; e < E; ++e)
-        if (!(my_lp[e] < prob_artifact)) is_artifact = false;
-    if (is_artifact) c.status |= VLR_ST_IS_ARTIFACT;
-
-    // MAP (calling.rs:844-890): events of a valid scenario are disjoint (grammar/mod.rs:238-272 rejects overlaps),
-    // so the base events contained in the best event are the ones its own tree produced.
-    const int best_scen = scen_u[best];
-    int map_slot = -1;
-    {
-        int sp = 2 * best_scen, st = 2 * best_scen + 1;
-        if (c.map_set[sp]) map_slot = sp;
-        if (is_artifact && c.map_set[st] && (map_slot < 0 || c.map_joint[st] > c.map_joint[sp])) map_slot = st;
-    }
-    if (map_slot < 0) c.status |= VLR_ST_NO_MAP;
-
-    if (lane_id() == 0) {
-        for (int e = 0; e <= E; ++e) lp[e] = my_lp[e];
-        if (res->log_marginal) res->log_marginal[locus] = marginal;
-        if (res->best_event) res->best_event[locus] = 2 * best_scen + (art_u[best] ? 1 : 0);
-        if (res->n_base_events) res->n_base_events[locus] = c.n_base;
-        for (int s = 0; s < S; ++s) {
-            double v = NAN;
-            if (map_slot >= 0) v = c.map_cfg[map_slot] != 0 ? 0.0 : c.map_vaf[map_slot][s];
-            res->map_vaf[locus * S + s] = v;
-        }
-        if (res->map_config) res->map_config[locus] = map_slot >= 0 ? c.map_cfg[map_slot] : 0;
-        if (res->afd_capacity > 0)
-            for (int s = 0; s < S; ++s) res->afd_count[locus * S + s] = 0;
-    }
-    if (res->afd_capacity > 0) afd_pass(c, best_scen, map_slot, marginal);
-    if (lane_id() == 0) res->status[locus] = c.status;
+    locus_tail(c, plan.n_twins);
 }
 
 
+#ifdef VLR_VAR_WAVE
+#include "engine_wave.cuh"
+#endif
+
 } // namespace VLR_VARIANT
+#undef VLR_VAR_WAVE
 #undef VLR_VARIANT
 #undef VLR_VAR_MAXS
 #undef VLR_VAR_MAXE

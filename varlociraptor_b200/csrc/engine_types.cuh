@@ -185,6 +185,19 @@ struct WarpWs {
     double afd_p[AFD_TMP];
 };
 
+// ------------------------------------------------------------------------------------------------ wavefront plan
+// Scenario-level description of the "two-level chain" shape the wavefront pipeline (engine_wave.cuh) serves: every event
+// is  root(sample P: one VAF | Range) -> leaf(sample T: one VAF | Range)  (tumor-normal: P = normal, T = tumor), flat
+// priors, no log2-fold-change / variant nodes. Built on the host (scenario_prep.h), passed to the kernels by value.
+constexpr int WAVE_MAXE = 8;
+struct WavePlan {
+    int eligible;
+    int P, T;        // root (parent) sample and leaf sample
+    int outer_event; // the event whose root is a Range (nested integration), or -1
+    int max_rounds;  // task rounds that complete every locus: 1 + outer iterations + 1
+    int root_node[WAVE_MAXE], child_node[WAVE_MAXE];
+};
+
 // ------------------------------------------------------------------------------------------------ math
 // Out-of-line fp64 transcendentals: CUDA inlines ~50-100 instructions per call site, and with dozens of call sites
 // the kernel outgrows the instruction caches (ncu: stall_no_instruction dominated the first versions). One copy each.

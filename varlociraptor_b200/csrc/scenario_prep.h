@@ -2,6 +2,7 @@
 // the test-only host emulation): LFC node ordinals, tree depth, the all-uniform flag (prior.rs:107-109).
 #pragma once
 #include <cmath>
+#include <cstring>
 #include <vector>
 
 #include "engine_types.cuh"
@@ -79,6 +80,59 @@ struct ScenarioPrep {
             if (!(sm.resolution > 0.0)) return fail("resolution must be positive");
         }
         return true;
+    }
+
+    // Does the scenario have the two-level chain shape of the wavefront pipeline (engine_types.cuh WavePlan)?
+    WavePlan wave_plan() const {
+        WavePlan wp;
+        std::memset(&wp, 0, sizeof wp);
+        wp.outer_event = -1;
+        wp.max_rounds = 1;
+        const vlr_scenario_t* sc = src;
+        if (!sc || sc->n_samples != 2 || sc->n_events > WAVE_MAXE || !all_uniform || !lfc_nodes.empty()) return wp;
+        int P = -1, n_leaf_tasks = 0;
+        for (int e = 0; e < sc->n_events; ++e) {
+            const vlr_event_t& ev = sc->events[e];
+            if (ev.n_roots != 1) return wp;
+            const vlr_node_t& root = sc->nodes[ev.first_root];
+            if (root.n_children != 1) return wp;
+            const vlr_node_t& child = sc->nodes[root.first_child];
+            if (child.n_children != 0) return wp;
+            const vlr_node_t* both[2] = {&root, &child};
+            for (const vlr_node_t* n : both) {
+                if (n->kind == VLR_NODE_SET) {
+                    if (n->n_vafs != 1) return wp;
+                } else if (n->kind == VLR_NODE_RANGE) {
+                    if (!(n->start < n->end)) return wp; // empty or singleton ranges take the generic path
+                } else {
+                    return wp;
+                }
+            }
+            if (P < 0) P = root.sample;
+            if (root.sample != P || child.sample != 1 - P) return wp;
+            if (root.kind == VLR_NODE_RANGE) {
+                if (wp.outer_event >= 0 || child.kind != VLR_NODE_RANGE) return wp;
+                wp.outer_event = e;
+                const double res = sc->samples[P].resolution, w0 = root.end - root.start;
+                int iters = 1;
+                if (w0 > res) iters = (int)std::ceil(std::log(w0 / res) / std::log(4.0 / 3.0)) + 2;
+                if (iters > 60) return wp;
+                wp.max_rounds = 1 + iters + 1;
+                n_leaf_tasks += 2;
+            } else if (child.kind == VLR_NODE_RANGE) {
+                n_leaf_tasks += 1;
+            }
+            wp.root_node[e] = ev.first_root;
+            wp.child_node[e] = root.first_child;
+        }
+        if (P < 0 || n_leaf_tasks > 8) return wp;
+        const int T = 1 - P;
+        if (sc->samples[P].contamination_by >= 0) return wp;
+        if (sc->samples[T].contamination_by >= 0 && sc->samples[T].contamination_by != P) return wp;
+        wp.P = P;
+        wp.T = T;
+        wp.eligible = 1;
+        return wp;
     }
 
     bool fail(const char* msg) {

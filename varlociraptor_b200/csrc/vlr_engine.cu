@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -21,6 +22,7 @@
 #define VLR_VAR_MAXS 3
 #define VLR_VAR_MAXE 8
 #define VLR_VAR_MAXD 6
+#define VLR_VAR_WAVE 1 // + the wavefront pipeline (engine_wave.cuh) for two-level chain scenarios (tumor-normal)
 #include "engine_core.cuh"
 #define VLR_VARIANT vlr_full
 #define VLR_VAR_MAXS VLR_MAX_SAMPLES
@@ -44,6 +46,8 @@ struct KernelParams {
     double* coef;
     double* be;
     unsigned long long* ticket;
+    const int* locus_list;          // optional: the loci to process (deferred by the wavefront pipeline) ...
+    const unsigned* locus_list_n;   // ... and their number (device counter)
     int coef_cap;      // reads per warp in the global arena
     int sm_reads;      // reads per warp in the shared-memory arena
     int ctx_stride;    // bytes of shared memory per warp for the Ctx
@@ -66,13 +70,113 @@ struct KernelParams {
             unsigned long long t = 0;                                                                             \
             if (lane_id() == 0) t = atomicAdd(p.ticket, 1ULL);                                                    \
             t = __shfl_sync(FULL, t, 0, LANES);                                                                   \
-            if ((int64_t)t >= p.b.n_loci) break;                                                                  \
-            NS::process_locus(&p.sc, &p.b, &p.r, ws, coef, coef_sm, p.sm_reads, be, p.coef_cap, (int64_t)t, c);   \
+            int64_t locus = (int64_t)t;                                                                           \
+            if (p.locus_list) {                                                                                   \
+                if (t >= (unsigned long long)*p.locus_list_n) break;                                              \
+                locus = p.locus_list[t];                                                                          \
+            } else if ((int64_t)t >= p.b.n_loci) break;                                                           \
+            NS::process_locus(&p.sc, &p.b, &p.r, ws, coef, coef_sm, p.sm_reads, be, p.coef_cap, locus, c);        \
             warp_sync();                                                                                          \
         }                                                                                                         \
     }
 VLR_DEFINE_KERNEL(vlr_small)
 VLR_DEFINE_KERNEL(vlr_full)
+
+// ---- wavefront pipeline kernels (engine_wave.cuh) ------------------------------------------------------------------
+struct WaveParams {
+    DevScenario sc;
+    DevBatch b;
+    DevResults r;
+    WavePlan wp;
+    vlr_small::WaveBufs wb;
+    WarpWs* ws;       // per warp of the prep/finish grid (AFD scratch)
+    int64_t sub_lo;   // first locus of the sub-chunk
+    int n_sub;        // loci in the sub-chunk
+    int want_be;      // AFD requested: log base events
+};
+constexpr int WAVE_ROUND_THREADS = vlr_small::W_GROUP * vlr_small::W_MAXT; // 256
+constexpr size_t WAVE_ROUND_SMEM = (size_t)vlr_small::W_GROUP * vlr_small::W_SLOT_READS * 4 * sizeof(double);
+
+__global__ void __launch_bounds__(THREADS, 2) vlr_wave_prep_kernel(const __grid_constant__ WaveParams p) {
+    using namespace vlr_small;
+    Ctx& c = *reinterpret_cast<Ctx*>(vlr_smem + (size_t)group_in_cta() * CTX_STRIDE);
+    for (;;) {
+        unsigned long long t = 0;
+        if (lane_id() == 0) t = atomicAdd(&p.wb.cnt->ticket[0], 1ULL);
+        t = __shfl_sync(FULL, t, 0, LANES);
+        if (t >= (unsigned long long)p.n_sub) break;
+        wave_prep_locus(&p.sc, &p.b, p.wp, p.wb, p.sub_lo + (int64_t)t, (int)t, p.want_be != 0, c);
+        warp_sync();
+    }
+}
+
+// One CTA per group of W_GROUP lcs of the round's list: the leaf sample's coefficients are staged in shared memory (one
+// slot per lc), every thread runs one task (tasks of an lc sit in neighbouring lanes: their coefficient loads are
+// shared-memory broadcasts), then one thread per lc advances the lc and emits the next round's tasks.
+__global__ void __launch_bounds__(WAVE_ROUND_THREADS, 2) vlr_wave_round_kernel(const __grid_constant__ WaveParams p, int round) {
+    using namespace vlr_small;
+    __shared__ int s_lc[W_GROUP], s_off[W_GROUP + 1];
+    const WaveBufs& wb = p.wb;
+    const int n_list = (int)wb.cnt->list_n[round];
+    const int* list = wb.list[round & 1];
+    WaveTask* tasks = wb.tasks[round & 1];
+    const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gtid = (int)(blockIdx.x * blockDim.x) + tid;
+    double* slots = reinterpret_cast<double*>(vlr_smem);
+    for (int g0 = (int)blockIdx.x * W_GROUP; g0 < n_list; g0 += (int)gridDim.x * W_GROUP) {
+        __syncthreads();
+        if (tid < W_GROUP) s_lc[tid] = g0 + tid < n_list ? list[g0 + tid] : -1;
+        __syncthreads();
+        if (tid == 0) {
+            int acc = 0;
+            for (int g = 0; g < W_GROUP; ++g) {
+                s_off[g] = acc;
+                if (s_lc[g] >= 0) acc += wb.lcs[s_lc[g]].task_count;
+            }
+            s_off[W_GROUP] = acc;
+        }
+        for (int g = warp; g < W_GROUP; g += WAVE_ROUND_THREADS / 32) {
+            const int lci = s_lc[g];
+            if (lci < 0) continue;
+            const WaveLC& L = wb.lcs[lci];
+            const int nT = L.nT;
+            if (nT > W_SLOT_READS) continue; // deep pileup: read from the arena (L2)
+            const double2* src = reinterpret_cast<const double2*>(wb.coef + L.coefT * 4);
+            double2* dst = reinterpret_cast<double2*>(slots + (size_t)g * W_SLOT_READS * 4);
+            for (int i = lane; i < nT * 2; i += 32) dst[i] = src[i];
+        }
+        __syncthreads();
+        const int total = s_off[W_GROUP];
+        if (tid < total) {
+            int g = 0;
+            while (s_off[g + 1] <= tid) ++g;
+            const int lci = s_lc[g];
+            const WaveLC& L = wb.lcs[lci];
+            WaveTask& t = tasks[L.task_base + (tid - s_off[g])];
+            const double2* coT = L.nT <= W_SLOT_READS ? reinterpret_cast<const double2*>(slots + (size_t)g * W_SLOT_READS * 4)
+                                                      : reinterpret_cast<const double2*>(wb.coef + L.coefT * 4);
+            const double2* coP = reinterpret_cast<const double2*>(wb.coef + L.coefP * 4);
+            wave_task_run(&p.sc, p.wp, L, t, coT, coP, wb.gx + gtid, wb.gf + gtid, wb.gn + gtid, wb.g_stride,
+                          p.want_be ? wb.be + (size_t)L.li * BE_CAP * 4 : nullptr, wb.be_n + L.li);
+        }
+        __syncthreads();
+        if (tid < W_GROUP && s_lc[tid] >= 0) wave_lc_advance(p.wp, wb, s_lc[tid], round);
+    }
+}
+
+__global__ void __launch_bounds__(THREADS, 2) vlr_wave_finish_kernel(const __grid_constant__ WaveParams p) {
+    using namespace vlr_small;
+    Ctx& c = *reinterpret_cast<Ctx*>(vlr_smem + (size_t)group_in_cta() * CTX_STRIDE);
+    WarpWs* ws = p.ws + (blockIdx.x * WARPS_PER_CTA + group_in_cta());
+    for (;;) {
+        unsigned long long t = 0;
+        if (lane_id() == 0) t = atomicAdd(&p.wb.cnt->ticket[1], 1ULL);
+        t = __shfl_sync(FULL, t, 0, LANES);
+        if (t >= (unsigned long long)p.n_sub) break;
+        wave_finish_locus(&p.sc, &p.b, &p.r, p.wp, p.wb, ws, p.sub_lo + (int64_t)t, (int)t, c);
+        warp_sync();
+    }
+}
 
 inline int align16(size_t x) { return (int)((x + 15) & ~(size_t)15); }
 
@@ -109,6 +213,8 @@ struct Slot { // one in-flight chunk of vlr_call_batch
     DevBuf ws, coef, be, ticket;
     int coef_cap = 0;
     bool be_ready = false;
+    // wavefront pipeline workspace (one sub-chunk of loci at a time)
+    DevBuf w_cnt, w_loci, w_lcs, w_ogx, w_ogf, w_coef, w_tasks[2], w_list[2], w_deferred, w_gx, w_gf, w_gn, w_be, w_ben;
 };
 
 } // namespace
@@ -120,6 +226,10 @@ struct vlr_ctx {
     int grid = 0;
     int S = 0, E = 0;
     bool small = false;   // which engine variant serves this scenario
+    bool wave = false;    // two-level chain scenario: the wavefront pipeline serves it (deferring loci it cannot)
+    WavePlan wplan;
+    int wave_grid_prep = 0, wave_grid_round = 0;
+    size_t wave_smem_prep = 0;
     int ctx_stride = 0;
     size_t smem_bytes = 0;
     ScenarioPrep prep;
@@ -161,7 +271,90 @@ vlr_status_t ensure_workspace(vlr_ctx* ctx, Slot& sl, int64_t max_reads, bool wa
     return VLR_OK;
 }
 
-vlr_status_t launch(vlr_ctx* ctx, Slot& sl, const DevBatch& b, const DevResults& r, cudaStream_t stream) {
+// Wavefront pipeline over the batch, one sub-chunk of loci after the other on `stream`: prep -> rounds -> finish ->
+// generic engine for the deferred loci. `avg_reads` (reads per locus of the batch, rounded up) sizes the coefficient
+// arena; loci that do not fit are deferred, never dropped.
+vlr_status_t launch_wave(vlr_ctx* ctx, Slot& sl, const DevBatch& b, const DevResults& r, int64_t avg_reads, cudaStream_t stream) {
+    using namespace vlr_small;
+    const bool want_be = r.afd_capacity > 0;
+    const int n_sub_cap = want_be ? 8192 : 65536;
+    const int lc_cap = n_sub_cap * 3;
+    if (avg_reads < 16) avg_reads = 16;
+    const int64_t coef_cap = (int64_t)n_sub_cap * avg_reads * 3 + (1 << 20);
+    const int g_stride = ctx->wave_grid_round * WAVE_ROUND_THREADS;
+    CK(sl.w_cnt.ensure(sizeof(WaveCounters)));
+    CK(sl.w_loci.ensure(sizeof(WaveLocus) * (size_t)n_sub_cap));
+    CK(sl.w_lcs.ensure(sizeof(WaveLC) * (size_t)lc_cap));
+    CK(sl.w_ogx.ensure(sizeof(double) * (size_t)lc_cap * W_OGRID));
+    CK(sl.w_ogf.ensure(sizeof(double) * (size_t)lc_cap * W_OGRID));
+    CK(sl.w_coef.ensure(sizeof(double) * 4 * (size_t)coef_cap));
+    for (int i = 0; i < 2; ++i) {
+        CK(sl.w_tasks[i].ensure(sizeof(WaveTask) * (size_t)lc_cap * W_MAXT));
+        CK(sl.w_list[i].ensure(sizeof(int) * (size_t)lc_cap));
+    }
+    CK(sl.w_deferred.ensure(sizeof(int) * (size_t)n_sub_cap));
+    CK(sl.w_gx.ensure(sizeof(double) * (size_t)W_GCAP * g_stride));
+    CK(sl.w_gf.ensure(sizeof(double) * (size_t)W_GCAP * g_stride));
+    CK(sl.w_gn.ensure(sizeof(short) * (size_t)W_GCAP * g_stride));
+    CK(sl.w_ben.ensure(sizeof(unsigned) * (size_t)n_sub_cap));
+    if (want_be) CK(sl.w_be.ensure(sizeof(double) * 4 * (size_t)BE_CAP * n_sub_cap));
+    WaveParams p;
+    p.sc = ctx->dsc;
+    p.b = b;
+    p.r = r;
+    p.wp = ctx->wplan;
+    p.wb.cnt = (WaveCounters*)sl.w_cnt.p;
+    p.wb.loci = (WaveLocus*)sl.w_loci.p;
+    p.wb.lcs = (WaveLC*)sl.w_lcs.p;
+    p.wb.og_x = (double*)sl.w_ogx.p;
+    p.wb.og_f = (double*)sl.w_ogf.p;
+    p.wb.coef = (double*)sl.w_coef.p;
+    p.wb.tasks[0] = (WaveTask*)sl.w_tasks[0].p;
+    p.wb.tasks[1] = (WaveTask*)sl.w_tasks[1].p;
+    p.wb.list[0] = (int*)sl.w_list[0].p;
+    p.wb.list[1] = (int*)sl.w_list[1].p;
+    p.wb.deferred = (int*)sl.w_deferred.p;
+    p.wb.gx = (double*)sl.w_gx.p;
+    p.wb.gf = (double*)sl.w_gf.p;
+    p.wb.gn = (short*)sl.w_gn.p;
+    p.wb.be = want_be ? (double*)sl.w_be.p : nullptr;
+    p.wb.be_n = (unsigned*)sl.w_ben.p;
+    p.wb.coef_cap = coef_cap;
+    p.wb.lc_cap = lc_cap;
+    p.wb.g_stride = g_stride;
+    p.ws = (WarpWs*)sl.ws.p;
+    p.want_be = want_be ? 1 : 0;
+    KernelParams gp; // generic engine over the deferred loci
+    gp.sc = ctx->dsc;
+    gp.b = b;
+    gp.r = r;
+    gp.ws = (WarpWs*)sl.ws.p;
+    gp.coef = (double*)sl.coef.p;
+    gp.be = want_be ? (double*)sl.be.p : nullptr;
+    gp.ticket = &p.wb.cnt->ticket[2];
+    gp.locus_list = p.wb.deferred;
+    gp.locus_list_n = &p.wb.cnt->n_deferred;
+    gp.coef_cap = sl.coef_cap;
+    gp.sm_reads = SM_READS;
+    gp.ctx_stride = ctx->ctx_stride;
+    gp.be_stride = (int64_t)BE_CAP * (2 + ctx->S);
+    for (int64_t lo = 0; lo < b.n_loci; lo += n_sub_cap) {
+        p.sub_lo = lo;
+        p.n_sub = (int)std::min<int64_t>(n_sub_cap, b.n_loci - lo);
+        CK(cudaMemsetAsync(sl.w_cnt.p, 0, sizeof(WaveCounters), stream));
+        vlr_wave_prep_kernel<<<ctx->wave_grid_prep, THREADS, ctx->wave_smem_prep, stream>>>(p);
+        for (int round = 0; round < ctx->wplan.max_rounds; ++round)
+            vlr_wave_round_kernel<<<ctx->wave_grid_round, WAVE_ROUND_THREADS, WAVE_ROUND_SMEM, stream>>>(p, round);
+        vlr_wave_finish_kernel<<<ctx->wave_grid_prep, THREADS, ctx->wave_smem_prep, stream>>>(p);
+        vlr_call_kernel_vlr_small<<<ctx->grid, THREADS, ctx->smem_bytes, stream>>>(gp);
+        CK(cudaGetLastError());
+        ctx->launches += 3 + ctx->wplan.max_rounds;
+    }
+    return VLR_OK;
+}
+
+vlr_status_t launch(vlr_ctx* ctx, Slot& sl, const DevBatch& b, const DevResults& r, cudaStream_t stream, int64_t avg_reads = 0) {
+    if (ctx->wave && b.n_loci > 0) return launch_wave(ctx, sl, b, r, avg_reads, stream);
     KernelParams p;
     p.sc = ctx->dsc;
     p.b = b;
@@ -170,6 +363,8 @@ vlr_status_t launch(vlr_ctx* ctx, Slot& sl, const DevBatch& b, const DevResults&
     p.coef = (double*)sl.coef.p;
     p.be = r.afd_capacity > 0 ? (double*)sl.be.p : nullptr;
     p.ticket = (unsigned long long*)sl.ticket.p;
+    p.locus_list = nullptr;
+    p.locus_list_n = nullptr;
     p.coef_cap = sl.coef_cap;
     p.sm_reads = SM_READS;
     p.ctx_stride = ctx->ctx_stride;
@@ -307,6 +502,23 @@ vlr_status_t vlr_ctx_create(const vlr_scenario_t* scenario, int32_t device, vlr_
     if (per_sm < 1) per_sm = 1;
     ctx->ctas_per_sm = per_sm;
     ctx->grid = per_sm * ctx->n_sms;
+    ctx->wplan = ctx->prep.wave_plan();
+    const char* wave_env = getenv("VLR_WAVE"); // VLR_WAVE=0: generic engine only (A/B measurements, debugging)
+    ctx->wave = ctx->small && ctx->wplan.eligible && ctx->wplan.max_rounds <= vlr_small::W_MAXROUNDS &&
+                !(wave_env && wave_env[0] == '0');
+    if (ctx->wave) {
+        ctx->wave_smem_prep = (size_t)WARPS_PER_CTA * (size_t)ctx->ctx_stride;
+        CKB(cudaFuncSetAttribute(vlr_wave_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->wave_smem_prep));
+        CKB(cudaFuncSetAttribute(vlr_wave_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->wave_smem_prep));
+        CKB(cudaFuncSetAttribute(vlr_wave_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WAVE_ROUND_SMEM));
+        int n1 = 0, n2 = 0;
+        CKB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n1, vlr_wave_prep_kernel, THREADS, ctx->wave_smem_prep));
+        CKB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n2, vlr_wave_round_kernel, WAVE_ROUND_THREADS, WAVE_ROUND_SMEM));
+        ctx->wave_grid_prep = std::max(1, n1) * ctx->n_sms;
+        ctx->wave_grid_round = std::max(1, n2) * ctx->n_sms;
+        // the finish kernel indexes the per-warp scratch (WarpWs) of the generic workspace: same number of warps or fewer
+        if (ctx->wave_grid_prep > ctx->grid) ctx->wave_grid_prep = ctx->grid;
+    }
     CKB(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     for (int i = 0; i < NBUF; ++i) CKB(cudaStreamCreateWithFlags(&ctx->slots[i].stream, cudaStreamNonBlocking));
 #undef CKB
@@ -326,7 +538,9 @@ void vlr_ctx_destroy(vlr_ctx_t* ctx) {
         for (auto& c : s.cols) c.release();
         DevBuf* all[] = {&s.rflags, &s.hart, &s.hvar, &s.lflags, &s.het, &s.semr, &s.log_post, &s.log_marginal,
                          &s.map_vaf, &s.map_config, &s.best_event, &s.status, &s.n_base, &s.afd_count, &s.afd_vaf,
-                         &s.afd_logp, &s.ws, &s.coef, &s.be, &s.ticket};
+                         &s.afd_logp, &s.ws, &s.coef, &s.be, &s.ticket, &s.w_cnt, &s.w_loci, &s.w_lcs, &s.w_ogx,
+                         &s.w_ogf, &s.w_coef, &s.w_tasks[0], &s.w_tasks[1], &s.w_list[0], &s.w_list[1], &s.w_deferred,
+                         &s.w_gx, &s.w_gf, &s.w_gn, &s.w_be, &s.w_ben};
         for (DevBuf* b : all) b->release();
     };
     if (ctx->stream) {
@@ -385,7 +599,8 @@ vlr_status_t vlr_call_batch_device(vlr_ctx_t* ctx, const vlr_batch_t* batch, vlr
     r.afd_count = results->afd_count;
     r.afd_vaf = results->afd_vaf;
     r.afd_logp = results->afd_logp;
-    return launch(ctx, ctx->dev_slot, b, r, stream);
+    const int64_t avg_reads = batch->n_loci > 0 ? (batch->n_reads + batch->n_loci - 1) / batch->n_loci : 0;
+    return launch(ctx, ctx->dev_slot, b, r, stream, avg_reads);
 }
 
 vlr_status_t vlr_call_batch(vlr_ctx_t* ctx, const vlr_batch_t* batch, vlr_results_t* results) {
@@ -487,10 +702,8 @@ vlr_status_t vlr_call_batch(vlr_ctx_t* ctx, const vlr_batch_t* batch, vlr_result
         r.afd_count = (int32_t*)sl.afd_count.p;
         r.afd_vaf = (double*)sl.afd_vaf.p;
         r.afd_logp = (double*)sl.afd_logp.p;
-        int64_t saved = ctx->launches;
-        st = launch(ctx, sl, b, r, s);
+        st = launch(ctx, sl, b, r, s, nl > 0 ? (nr + nl - 1) / nl : 0);
         if (st != VLR_OK) break;
-        ctx->launches = saved + 1;
         // D2H
         CK(cudaMemcpyAsync(results->log_posteriors + lo * (E + 1), r.log_post, sizeof(double) * (size_t)(nl * (E + 1)), cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(results->map_vaf + lo * S, r.map_vaf, sizeof(double) * (size_t)(nl * S), cudaMemcpyDeviceToHost, s));
