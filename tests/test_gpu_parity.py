@@ -152,11 +152,22 @@ def test_device_pointer_entry_matches_host_entry(engine_mod):
     assert np.array_equal(host.afd_logp[host.afd_count > 0], dev.afd_logp[dev.afd_count > 0], equal_nan=True)
 
 
-def test_workspace_overflow_is_reported_not_silent(engine_mod):
+def test_workspace_overflow_is_reported_not_silent(engine_mod, monkeypatch):
     import torch
     sc, b = synth.tumor_normal(4, seed=5, depth=3000)  # 6000 reads/locus > default reserve of 4096
     flat = sc.flatten()
+    # the wavefront pipeline sizes its coefficient arena from the batch and never needs the reserve; the generic
+    # engine (VLR_WAVE=0, and every scenario the pipeline does not serve) does
+    wave = engine_mod.PosteriorEngine(flat)
+    dbw = engine_mod.DeviceBatch(b)
+    drw = engine_mod.DeviceResults(b.n_loci, 2, flat.n_events)
+    wave.call_batch_device(dbw, drw)
+    torch.cuda.synchronize()
+    assert not np.any(drw.to_host().status & abi.ST_WORKSPACE_OVERFLOW)
+    assert max_abs_delta(oracle.call_batch(flat, b).log_posteriors, drw.to_host().log_posteriors) <= TOL
+    monkeypatch.setenv("VLR_WAVE", "0")
     eng = engine_mod.PosteriorEngine(flat)
+    monkeypatch.delenv("VLR_WAVE")
     db = engine_mod.DeviceBatch(b)
     dr = engine_mod.DeviceResults(b.n_loci, 2, flat.n_events)
     eng.call_batch_device(db, dr)
@@ -237,3 +248,36 @@ def test_four_samples_full_capacity_variant(engine_mod):
     o = oracle.call_batch(flat, b, afd_capacity=128, n_threads=os.cpu_count() or 1)
     g = engine_mod.PosteriorEngine(flat).call_batch(b, afd_capacity=128)
     _compare(o, g, max_knife_fraction=0.1)
+
+
+def test_wavefront_pipeline_equals_generic_engine(engine_mod, monkeypatch):
+    """Tumor-normal scenarios run the wavefront pipeline (engine_wave.cuh); VLR_WAVE=0 forces the generic warp-per-locus
+    engine. Same loci, both against the oracle and against each other, with and without AFD, several sub-chunks."""
+    sc, b = synth.tumor_normal(20000, seed=4242, depth=40)
+    flat = sc.flatten()
+    wave = engine_mod.PosteriorEngine(flat)
+    monkeypatch.setenv("VLR_WAVE", "0")
+    generic = engine_mod.PosteriorEngine(flat)
+    monkeypatch.delenv("VLR_WAVE")
+    for afd in (0, 48):
+        gw = wave.call_batch(b, afd_capacity=afd)
+        gg = generic.call_batch(b, afd_capacity=afd)
+        assert wave.launches > generic.launches
+        assert np.array_equal(gw.status, gg.status)
+        assert np.array_equal(gw.best_event, gg.best_event)
+        same_grid = gw.n_base_events == gg.n_base_events
+        assert same_grid.mean() > 0.995  # different product order: knife-edge loci may take another grid
+        assert max_abs_delta(gw.log_posteriors[same_grid], gg.log_posteriors[same_grid]) <= TOL
+        assert max_abs_delta(gw.map_vaf[same_grid], gg.map_vaf[same_grid]) == 0.0
+        if afd:
+            assert np.array_equal(gw.afd_count[same_grid], gg.afd_count[same_grid])
+    idx = np.r_[0:300, 19700:20000]
+    o = oracle.call_batch(flat, b.select(idx), afd_capacity=48, n_threads=os.cpu_count() or 1)
+    ke = o.knife_edge()
+    gw = wave.call_batch(b, afd_capacity=48)
+    assert max_abs_delta(o.log_posteriors[~ke], gw.log_posteriors[idx][~ke]) <= TOL
+    assert np.array_equal(o.n_base_events[~ke], gw.n_base_events[idx][~ke])
+    valid = np.arange(48)[None, None, :] < o.afd_count[:, :, None]
+    valid &= (~ke)[:, None, None]
+    assert np.array_equal(o.afd_count[~ke], gw.afd_count[idx][~ke])
+    assert max_abs_delta(o.afd_logp[valid], gw.afd_logp[idx][valid]) <= TOL
