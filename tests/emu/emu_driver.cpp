@@ -109,8 +109,7 @@ extern "C" int32_t vlr_emu_wave_call_batch(const vlr_scenario_t* sc, const vlr_b
     std::vector<double> coef((size_t)coef_cap * 4);
     std::vector<WaveTask> tasks0((size_t)lc_cap * W_MAXT), tasks1((size_t)lc_cap * W_MAXT);
     std::vector<int> list0((size_t)lc_cap), list1((size_t)lc_cap), deferred((size_t)L + 1);
-    std::vector<double> gx(W_GCAP), gf(W_GCAP);
-    std::vector<short> gn(W_GCAP);
+    std::vector<double> gx((size_t)W_GCAP * W_MAXT), gf((size_t)W_GCAP * W_MAXT), scratch(3 * W_GCAP);
     std::vector<double> be(want_be ? (size_t)L * BE_CAP * 4 : 4);
     std::vector<unsigned> be_n((size_t)L + 1);
     WaveBufs wb;
@@ -127,12 +126,10 @@ extern "C" int32_t vlr_emu_wave_call_batch(const vlr_scenario_t* sc, const vlr_b
     wb.deferred = deferred.data();
     wb.gx = gx.data();
     wb.gf = gf.data();
-    wb.gn = gn.data();
     wb.be = want_be ? be.data() : nullptr;
     wb.be_n = be_n.data();
     wb.coef_cap = coef_cap;
     wb.lc_cap = lc_cap;
-    wb.g_stride = 1;
     WarpWs* ws = new WarpWs;
     Ctx* c = new Ctx;
     for (int64_t i = 0; i < L; ++i) wave_prep_locus(&ds, &db, wp, wb, i, (int)i, want_be, *c);
@@ -143,12 +140,13 @@ extern "C" int32_t vlr_emu_wave_call_batch(const vlr_scenario_t* sc, const vlr_b
             WaveLC& lc = lcs[list[k]];
             for (int t = 0; t < lc.task_count; ++t) {
                 WaveTask& task = wb.tasks[round & 1][lc.task_base + t];
-                wave_task_run(&ds, wp, lc, task, reinterpret_cast<const double2*>(wb.coef + lc.coefT * 4),
-                              reinterpret_cast<const double2*>(wb.coef + lc.coefP * 4), wb.gx, wb.gf, wb.gn, 1,
-                              want_be ? wb.be + (size_t)lc.li * BE_CAP * 4 : nullptr, &wb.be_n[lc.li]);
+                const WSplit one{0, 1, 1u};
+                const double lh = wave_task_parent(lc, task, reinterpret_cast<const double2*>(wb.coef + lc.coefP * 4), false, one);
+                wave_task_run(&ds, wp, lc, task, reinterpret_cast<const double2*>(wb.coef + lc.coefT * 4), false, lh,
+                              wb.gx + (size_t)t * W_GCAP, wb.gf + (size_t)t * W_GCAP, one);
             }
+            wave_lc_advance(wp, wb, list[k], round, wb.gx, wb.gf, W_GCAP, scratch.data(), want_be);
         }
-        for (int k = 0; k < n_list; ++k) wave_lc_advance(wp, wb, list[k], round);
     }
     for (int64_t i = 0; i < L; ++i) wave_finish_locus(&ds, &db, &dr, wp, wb, ws, i, (int)i, *c);
     std::vector<double> coef2((size_t)max_reads * 4);

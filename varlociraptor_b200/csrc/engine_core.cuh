@@ -319,6 +319,7 @@ VLR_DEV_NOINLINE void locus_prepass(Ctx& c_, BiasPlan& plan) {
         int e1 = 0, e2 = 0, e3 = 0, e4 = 0, e5 = 0, e6 = 0, e7 = 0, e8 = 0, e9 = 0;
         int n_snot0 = 0, n_sgt0 = 0;
         double r_all = 0.0, r_major = 0.0, r_rate = 0.0;
+        double memo_pm = NAN, memo_w = 0.0, memo_pmh = NAN, memo_wh = 0.0;
         for (int64_t row = lo + lane_id(); row < hi; row += LANES) {
             int64_t i = row - b->read_base;
             uint32_t f = ldin(b->rflags + i);
@@ -344,8 +345,12 @@ VLR_DEV_NOINLINE void locus_prepass(Ctx& c_, BiasPlan& plan) {
                 g_alt_support++;
                 g_alt_row = row;
             }
-            double w = m_exp(pm);
             if (strong_ref) {
+                if (pm != memo_pm) { // exp of a repeated argument (MAPQ takes a handful of values): same bits
+                    memo_pm = pm;
+                    memo_w = m_exp(pm);
+                }
+                const double w = memo_w;
                 if (strand != 2) g_sb_all += w;
                 if (strand == 0) g_sb_fwd += w;
                 bool std_or = orient == 0 || orient == 1;
@@ -355,7 +360,12 @@ VLR_DEV_NOINLINE void locus_prepass(Ctx& c_, BiasPlan& plan) {
                 g_nm_ref += !maxq;
                 r_all += w;
                 if (major) r_major += w;
-                r_rate += m_exp(pm + phb);
+                const double pmh = pm + phb;
+                if (pmh != memo_pmh) {
+                    memo_pmh = pmh;
+                    memo_wh = m_exp(pmh);
+                }
+                r_rate += memo_wh;
             }
             g_uncertain += !(orient == 0 || orient == 1);
             if (strong_alt) {
@@ -562,6 +572,12 @@ VLR_DEV_NOINLINE void read_coefficients(Ctx& c_, int s) {
     double ksum = 0.0;
     bool dead = false, bad = false;
     int base = 0; // kept reads before this chunk of LANES rows
+    // Transcendentals dominate this function (profiles/: exp/log/log1p were 2/3 of the prep kernel's instructions), and
+    // most of their arguments repeat: the strand rate is a per-locus constant, MAPQ and prob_hit_base take a handful of
+    // values. Same function of the same argument = same bits, so one-entry per-lane memos and the exact special values
+    // (exp(0) = 1, exp(-inf) = 0, ln(1 - e^-inf) = -0) change nothing numerically.
+    const double ln_rate_fwd = m_log(a.forward_rate), ln_rate_rev = m_log(1.0 - a.forward_rate);
+    double memo_pm = NAN, memo_pmis = 0.0, memo_phb = NAN, memo_l1m_phb = 0.0, memo_pdo = NAN, memo_l1m_pdo = 0.0;
     for (int64_t row0 = lo; row0 < hi; row0 += LANES) {
         int64_t row = row0 + lane_id();
         bool valid = row < hi;
@@ -592,15 +608,25 @@ VLR_DEV_NOINLINE void read_coefficients(Ctx& c_, int s) {
             else if (a.id == 8) sb_alt = strand == 1 ? 0.0 : neg_inf();
             else if (strand == 2) sb_alt = r.pdo;
             else {
-                double rate = strand == 0 ? a.forward_rate : 1.0 - a.forward_rate;
-                sb_alt = m_log(rate) + ln_one_minus_exp(r.pdo);
+                if (r.pdo != memo_pdo) {
+                    memo_pdo = r.pdo;
+                    memo_l1m_pdo = r.pdo == neg_inf() ? -0.0 : ln_one_minus_exp(r.pdo);
+                }
+                sb_alt = (strand == 0 ? ln_rate_fwd : ln_rate_rev) + memo_l1m_pdo;
             }
             // read orientation bias (read_orientation_bias.rs:17-29)
             double rob_alt = LN_05;
             if (a.id == 5) rob_alt = orient == 0 ? 0.0 : (orient == 1 ? neg_inf() : LN_05);
             else if (a.id == 6) rob_alt = orient == 1 ? 0.0 : (orient == 0 ? neg_inf() : LN_05);
             // read position bias (read_position_bias.rs:17-61)
-            double rpb_any = major ? r.phb : (r.phb != 0.0 ? ln_one_minus_exp(r.phb) : 0.0);
+            double rpb_any = r.phb;
+            if (!major) {
+                if (r.phb != memo_phb) {
+                    memo_phb = r.phb;
+                    memo_l1m_phb = r.phb != 0.0 ? ln_one_minus_exp(r.phb) : 0.0;
+                }
+                rpb_any = memo_l1m_phb;
+            }
             double rpb_alt = a.id == 4 ? (major ? 0.0 : neg_inf()) : rpb_any;
             // softclip bias (softclip_bias.rs:14-24)
             double scb_alt = a.id == 3 ? (softclip ? 0.0 : neg_inf()) : 0.0;
@@ -620,7 +646,11 @@ VLR_DEV_NOINLINE void read_coefficients(Ctx& c_, int s) {
             double bA = sb_alt + rob_alt + rpb_alt + scb_alt + he + alb_alt;
             double bR = LN_05 + LN_05 + rpb_any + 0.0 + he + alb_ref;
             double bAny = LN_05 + LN_05 + rpb_any + 0.0 + 0.0 + LN_05;
-            double pmis = ln_one_minus_exp(r.pm); // read_observation.rs:283-286
+            if (r.pm != memo_pm) {
+                memo_pm = r.pm;
+                memo_pmis = ln_one_minus_exp(r.pm);
+            }
+            const double pmis = memo_pmis; // read_observation.rs:283-286
             double lnA = r.pm + (bA + pa);
             double lnR = r.pm + (pr + bR);
             double lnC = pmis + r.pmiss + bAny;
@@ -631,16 +661,16 @@ VLR_DEV_NOINLINE void read_coefficients(Ctx& c_, int s) {
             } else if (K == neg_inf()) {
                 dead = true;
             } else {
-                al_ = m_exp(lnA - K);
-                be_ = m_exp(lnR - K);
-                ga_ = m_exp(lnC - K);
+                al_ = lnA == K ? 1.0 : (lnA == neg_inf() ? 0.0 : m_exp(lnA - K));
+                be_ = lnR == K ? 1.0 : (lnR == neg_inf() ? 0.0 : m_exp(lnR - K));
+                ga_ = lnC == K ? 1.0 : (lnC == neg_inf() ? 0.0 : m_exp(lnC - K));
                 ksum += K;
             }
             double* o = out + (int64_t)pos * 4;
             o[0] = al_;
             o[1] = be_;
             o[2] = ga_;
-            o[3] = -m_expm1(r.psa); // u_r = 1 - s_r, s_r = e^{prob_sample_alt}: exactly 0 when prob_sample_alt = 0
+            o[3] = r.psa == 0.0 ? -0.0 : -m_expm1(r.psa); // u_r = 1 - s_r, s_r = e^{prob_sample_alt}: 0 when prob_sample_alt = 0
         }
         base += n_kept;
     }

@@ -30,6 +30,7 @@ constexpr int W_MAXT = 8;        // tasks an lc can have in one round
 constexpr int W_MAXROUNDS = 64;
 constexpr int W_GROUP = 32;      // lcs per CTA group (= shared-memory coefficient slots)
 constexpr int W_SLOT_READS = 104; // reads per shared-memory coefficient slot (3.3 KB); deeper pileups are read from L2
+constexpr int W_SLOT_STRIDE = W_SLOT_READS * 4 + 2; // doubles between slots: 16 bytes of skew against bank conflicts
 
 #ifdef VLR_HOST_EMU
 VLR_DEV unsigned wa_add_u32(unsigned* p, unsigned v) {
@@ -86,6 +87,7 @@ struct WaveTask {
     double parent_x, a, b; // in
     double value, best_f, best_x; // out
     uint32_t n_evals, status;
+    int n_grid, pad2;
 };
 
 struct WaveBufs {
@@ -98,14 +100,12 @@ struct WaveBufs {
     WaveTask* tasks[2];
     int* list[2];
     int* deferred; // absolute locus indices
-    double* gx;    // per-thread leaf grids: [W_GCAP][g_stride]
+    double* gx;    // per-thread leaf grid rows: [threads][W_GCAP]
     double* gf;
-    short* gn;
     double* be;      // base-event log per locus of the sub-chunk (AFD only): [n_sub][BE_CAP][2 + S]
     unsigned* be_n;  // [n_sub]
     int64_t coef_cap; // reads
     int lc_cap;
-    int g_stride;
 };
 
 // ---------------------------------------------------------------------------------------------- pileup evaluation
@@ -131,11 +131,25 @@ VLR_DEV void wave_pull(double& acc, int& ex, unsigned& slow, unsigned bit) {
     acc = d_make((hi & 0x800fffff) | (1023 << 20), d_lo(acc));
 }
 
-// ln-likelihood of one pileup at NP abscissae at once (one thread): product over the reads of
-// alpha x + beta y + gamma as mantissa + binary exponent, one log per abscissa.
+// How the lanes of a task split the reads of a pileup: H = 1, 2, 4 or 8 neighbouring lanes (h = position inside the
+// group, mask = the group's lanes) each take every H-th block of 4 reads and combine their partial products with an
+// xor butterfly (bitwise identical on all H lanes, which keeps their control flow identical). (The text above says
+// "block of 4 reads" loosely: lane h takes reads h, h + H, ...; see wave_eval.)
+struct WSplit {
+    int h, H;
+    unsigned mask;
+};
+
+// ln-likelihood of one pileup at NP abscissae at once: product over the reads of alpha x + beta y + gamma as mantissa
+// + binary exponent, one log per abscissa.
 // M0: every read has prob_sample_alt = 0 (u_r = 0), the per-read x/y corrections vanish.
-template <bool M0, int NP>
-VLR_DEV void wave_eval(const double2* __restrict__ co, int n, double ksum, const WArgs* a, double* lnl, unsigned& slowmask) {
+// SM: `co` points into the CTA's dynamic shared memory (LDS instead of generic loads).
+template <bool M0, int NP, bool SM>
+VLR_DEV void wave_eval(const double2* __restrict__ co, int n, double ksum, const WArgs* a, double* lnl, unsigned& slowmask,
+                       const WSplit sp) {
+#ifndef VLR_HOST_EMU
+    if (SM) co = reinterpret_cast<const double2*>(vlr_smem + (__cvta_generic_to_shared(co) - __cvta_generic_to_shared(vlr_smem)));
+#endif
     double acc[NP];
     int ex[NP];
 #pragma unroll
@@ -144,37 +158,59 @@ VLR_DEV void wave_eval(const double2* __restrict__ co, int n, double ksum, const
         ex[i] = 0;
     }
     unsigned slow = 0;
-    auto step = [&](int r) {
+    auto term = [&](int r, int i) -> double {
         const double2 ab = co[2 * r];
         const double2 gu = co[2 * r + 1];
+        if (M0) return fma(ab.x, a[i].xu, fma(ab.y, a[i].Yp, gu.x));
+        const double xr = fma(-gu.y, a[i].X1, a[i].xu);
+        const double yr = fma(gu.y, a[i].X1, a[i].Yp);
+        return fma(ab.x, xr, fma(ab.y, yr, gu.x));
+    };
+    auto step = [&](int r) {
+#pragma unroll
+        for (int i = 0; i < NP; ++i) acc[i] *= term(r, i);
+    };
+    // lane h takes the reads h, h + H, h + 2H, ...: neighbouring lanes touch neighbouring 32-byte records, and the
+    // slots of neighbouring lcs are skewed by 16 bytes (W_SLOT_STRIDE), so the 128-bit loads of a quarter warp fall
+    // into different bank groups (the first version, block-split and unskewed, ran ~7-way bank conflicts).
+    // Four reads per block, their 4 x NP terms independent and multiplied as a tree: enough instruction-level
+    // parallelism for one warp to keep the fp64 pipe busy (a serial acc *= t chain stalls on the pipe latency).
+    const int H = sp.H;
+    int r = sp.h;
+#pragma unroll 1
+    for (; r + 3 * H < n; r += 4 * H) { // 4 factors (each <= 3) between exponent pulls
+        double t0[NP], t1[NP], t2[NP], t3[NP];
 #pragma unroll
         for (int i = 0; i < NP; ++i) {
-            double t;
-            if (M0) {
-                t = fma(ab.x, a[i].xu, fma(ab.y, a[i].Yp, gu.x));
-            } else {
-                const double xr = fma(-gu.y, a[i].X1, a[i].xu);
-                const double yr = fma(gu.y, a[i].X1, a[i].Yp);
-                t = fma(ab.x, xr, fma(ab.y, yr, gu.x));
-            }
-            acc[i] *= t;
+            t0[i] = term(r, i);
+            t1[i] = term(r + H, i);
+            t2[i] = term(r + 2 * H, i);
+            t3[i] = term(r + 3 * H, i);
         }
-    };
-    int r = 0;
-#pragma unroll 1
-    for (; r + 4 <= n; r += 4) { // 4 factors (each <= 3) between exponent pulls
-        step(r);
-        step(r + 1);
-        step(r + 2);
-        step(r + 3);
 #pragma unroll
-        for (int i = 0; i < NP; ++i) wave_pull(acc[i], ex[i], slow, 1u << i);
+        for (int i = 0; i < NP; ++i) {
+            acc[i] *= (t0[i] * t1[i]) * (t2[i] * t3[i]);
+            wave_pull(acc[i], ex[i], slow, 1u << i);
+        }
     }
 #pragma unroll 1
-    for (; r < n; ++r) step(r);
+    for (; r < n; r += H) step(r);
+#pragma unroll
+    for (int i = 0; i < NP; ++i) wave_pull(acc[i], ex[i], slow, 1u << i);
+#ifndef VLR_HOST_EMU
+#pragma unroll 1
+    for (int o = sp.H >> 1; o > 0; o >>= 1) {
+        slow |= __shfl_xor_sync(sp.mask, slow, o);
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            acc[i] *= __shfl_xor_sync(sp.mask, acc[i], o);
+            ex[i] += __shfl_xor_sync(sp.mask, ex[i], o);
+        }
+    }
+#endif
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
-        wave_pull(acc[i], ex[i], slow, 1u << i);
+        wave_pull(acc[i], ex[i], slow, 1u << i); // <= 8 mantissas in [1,2): < 2^8
         lnl[i] = (log(acc[i]) + (double)ex[i] * LN_2) + ksum; // a NaN ksum (invalid inputs) propagates
     }
     slowmask = slow;
@@ -219,17 +255,18 @@ VLR_DEV_NOINLINE double wave_eval_careful(const double2* co, int n, double ksum,
     return (log(acc) + (double)ex * LN_2) + ksum;
 }
 
-template <int NP>
-VLR_DEV void wave_pileup(const double2* co, int n, double ksum, bool m0, const WArgs* a, int nvalid, double* lnl) {
+template <int NP, bool SM>
+VLR_DEV void wave_pileup(const double2* co, int n, double ksum, bool m0, const WArgs* a, int nvalid, double* lnl,
+                         const WSplit sp) {
     if (n == 0) { // empty fold = ln 1
 #pragma unroll
         for (int i = 0; i < NP; ++i) lnl[i] = 0.0;
         return;
     }
     unsigned slow;
-    if (m0) wave_eval<true, NP>(co, n, ksum, a, lnl, slow);
-    else wave_eval<false, NP>(co, n, ksum, a, lnl, slow);
-    if (slow) {
+    if (m0) wave_eval<true, NP, SM>(co, n, ksum, a, lnl, slow, sp);
+    else wave_eval<false, NP, SM>(co, n, ksum, a, lnl, slow, sp);
+    if (slow) { // every lane of the task re-evaluates the whole pileup (identical values, no exchange needed)
 #pragma unroll
         for (int i = 0; i < NP; ++i)
             if (i < nvalid && ((slow >> i) & 1u)) lnl[i] = wave_eval_careful(co, n, ksum, a[i]);
@@ -243,10 +280,23 @@ VLR_DEV bool wave_prior_ok(const DevScenario* sc, int s, double v) {
 
 // ---------------------------------------------------------------------------------------------- leaf task (thread)
 // One adaptive integration of the leaf sample's allele frequency over [a, b] with the parent sample fixed at
-// parent_x: utils/adaptive_integration.rs:25-141 driven exactly like integrate_adaptive_leaf / leaf_multi_run, with the
-// visited points kept in a per-thread linked list in x order (so the closing trapezoid needs no sort).
+// parent_x: utils/adaptive_integration.rs:25-141 driven exactly like integrate_adaptive_leaf / leaf_multi_run. The
+// whole search state lives in registers; the visited points are appended, in visit order, to the thread's grid row
+// (gx, gf) and integrated afterwards by wave_fin_coop.
+// The H lanes of a task (WSplit) run these functions in lockstep on identical values; lane h = 0 writes.
+//
+// Pileup ln-likelihood of the parent sample at the task's parent_x: a constant of the leaf integration
+// (GenericLikelihood::compute, generic.rs:511-551, hits its per-sample cache for it at every point).
+VLR_DEV double wave_task_parent(const WaveLC& lc, const WaveTask& t, const double2* coP, const bool p_in_sm, const WSplit sp) {
+    const WArgs ap = wave_args(1.0, 0.0, t.parent_x, 0.0);
+    double lh;
+    if (p_in_sm) wave_pileup<1, true>(coP, lc.nP, lc.ksumP, lc.m0P != 0, &ap, 1, &lh, sp);
+    else wave_pileup<1, false>(coP, lc.nP, lc.ksumP, lc.m0P != 0, &ap, 1, &lh, sp);
+    return lh;
+}
+
 VLR_DEV void wave_task_run(const DevScenario* sc, const WavePlan& wp, const WaveLC& lc, WaveTask& t, const double2* coT,
-                           const double2* coP, double* gx, double* gf, short* gn, const int gs, double* be, unsigned* be_n) {
+                           const bool t_in_sm, const double lh_const, double* gx, double* gf, const WSplit sp) {
     const int P = wp.P, T = wp.T;
     const vlr_sample_t& smT = sc->samples[T];
     double rhoT = 1.0, iotaT = 0.0;
@@ -256,23 +306,18 @@ VLR_DEV void wave_task_run(const DevScenario* sc, const WavePlan& wp, const Wave
     }
     const double px = t.parent_x;
     const double vby = smT.contamination_by >= 0 ? px : 0.0;
-    const int nT = lc.nT;
+    const int nT = lc.nT; // (locals: the lc lives in global memory and the grid stores below may alias it)
     const double ksumT = lc.ksumT;
     const bool m0T = lc.m0T != 0;
     uint32_t status = 0;
     const double prior_const = wave_prior_ok(sc, P, px) ? 0.0 : neg_inf();
-    double lh_const;
-    {
-        const WArgs ap = wave_args(1.0, 0.0, px, 0.0);
-        wave_pileup<1>(coP, lc.nP, lc.ksumP, lc.m0P != 0, &ap, 1, &lh_const);
-    }
     const double a = t.a, b = t.b, res = smT.resolution;
     int n = 0;
     uint32_t n_evals = 0;
     bool overflow = false, have_best = false, any_nan = false;
     double best_f = 0.0, best_x = 0.0;
 
-    auto insert = [&](double x, double f, int hint) -> int {
+    auto visit = [&](double x, double f) {
         n_evals++;
         if (f != f) any_nan = true;
         if (!have_best || f > best_f) { // first maximum in visit order (calling.rs:851-870 via joint())
@@ -282,171 +327,145 @@ VLR_DEV void wave_task_run(const DevScenario* sc, const WavePlan& wp, const Wave
         }
         if (n >= W_GCAP) {
             overflow = true;
-            return hint;
+            return;
         }
-        const int idx = n++;
-        gx[idx * gs] = x;
-        gf[idx * gs] = f;
-        if (idx == 0) {
-            gn[0] = -1;
-            return 0;
+        if (sp.h == 0) {
+            gx[n] = x;
+            gf[n] = f;
         }
-        int cur = hint;
-        for (;;) { // equal abscissae keep visit order, like the rank sort of grid_trapezoid
-            const int nx = gn[cur * gs];
-            if (nx < 0 || !(gx[nx * gs] <= x)) break;
-            cur = nx;
-        }
-        gn[idx * gs] = gn[cur * gs];
-        gn[cur * gs] = (short)idx;
-        return idx;
+        n++;
     };
-    auto eval3 = [&](double x0, double x1, double x2, int nvalid, double* f) {
+
+    // One loop, one evaluation site (small code: every lane of the warp, whatever its phase, meets in the same pileup
+    // loop). Steps: 0 [min, max]; 1 [middle, m1, m2] while the bracket is wider than the resolution; 2, 3 the 3 + 3
+    // points around the optimum (adaptive_integration.rs:108-131). The midpoint of the arm abandoned by the first
+    // iteration (:96-106) is bitwise that iteration's m1 or m2 — the reference's HashMap deduplicates it — so its
+    // value is remembered instead of evaluated again (it still counts as a visit, like in the generic engine).
+    double left = a, right = b, f_left = 0.0, f_right = 0.0, middle = 0.0, first_middle = 0.0;
+    double f_first_m1 = 0.0, f_first_m2 = 0.0;
+    double x4 = 0.0, x5 = 0.0, x6 = 0.0;
+    bool have_middle = false;
+    int step = 0;
+    while (step < 4) {
+        double x0, x1, x2;
+        int nvalid = 3;
+        if (step == 0) {
+            x0 = a;
+            x1 = x2 = b;
+            nvalid = 2;
+        } else if (step == 1) {
+            middle = (right + left) / 2.0;
+            x0 = middle;
+            x1 = (middle + left) / 2.0;
+            x2 = (right + middle) / 2.0;
+        } else if (step == 2) {
+            const bool upper = middle < first_middle;
+            visit(upper ? (b + first_middle) / 2.0 : (first_middle + a) / 2.0, upper ? f_first_m2 : f_first_m1);
+            const double lo = fmax(middle - (res * 3.0), a);
+            const double slo = (middle - lo) / 3.0; // itertools-num linspace(lo, middle, 4).take(3)
+            x0 = lo + slo * 0.0;
+            x1 = lo + slo * 1.0;
+            x2 = lo + slo * 2.0;
+            const double hi = fmin(middle + (res * 3.0), b);
+            const double shi = (hi - middle) / 3.0; // linspace(middle, hi, 4).skip(1)
+            x4 = middle + shi * 1.0;
+            x5 = middle + shi * 2.0;
+            x6 = middle + shi * 3.0;
+        } else {
+            x0 = x4;
+            x1 = x5;
+            x2 = x6;
+        }
         WArgs w[3];
         w[0] = wave_args(rhoT, iotaT, x0, vby);
         w[1] = wave_args(rhoT, iotaT, x1, vby);
         w[2] = wave_args(rhoT, iotaT, x2, vby);
         double lnl[3];
-        wave_pileup<3>(coT, nT, ksumT, m0T, w, nvalid, lnl);
-#pragma unroll
-        for (int i = 0; i < 3; ++i) f[i] = prior_const + (lh_const + lnl[i]);
-    };
-
-    double left = a, right = b, f_left, f_right, middle = 0.0, first_middle = 0.0;
-    bool have_middle = false;
-    int il, ir;
-    double f[3];
-    eval3(a, b, b, 2, f);
-    il = insert(a, f[0], 0);
-    ir = insert(b, f[1], il);
-    f_left = f[0];
-    f_right = f[1];
-    // while (((right - left) >= res && left < right) || middle.is_none())   (adaptive_integration.rs:52)
-    while (!overflow && ((((right - left) >= res) && left < right) || !have_middle)) {
-        middle = (right + left) / 2.0;
-        const double m1 = (middle + left) / 2.0, m2 = (right + middle) / 2.0;
-        eval3(middle, m1, m2, 3, f);
-        const int im = insert(middle, f[0], il);
-        const int i1 = insert(m1, f[1], il);
-        const int i2 = insert(m2, f[2], im);
-        if (!have_middle) first_middle = middle;
-        have_middle = true;
-        const double f_m1 = f[1], f_m2 = f[2];
-        int idx = 0;
-        double fb = f_left;
-        if (f_m1 > fb) {
-            idx = 1;
-            fb = f_m1;
-        }
-        if (f_m2 > fb) {
-            idx = 2;
-            fb = f_m2;
-        }
-        if (f_right > fb) idx = 3;
-        // neighbours of the argmax in [left, m1, m2, right] become the new bounds (the middle is not a candidate)
-        const double nl = idx <= 1 ? left : (idx == 2 ? m1 : m2), nfl = idx <= 1 ? f_left : (idx == 2 ? f_m1 : f_m2);
-        const double nr = idx == 0 ? m1 : (idx == 1 ? m2 : right), nfr = idx == 0 ? f_m1 : (idx == 1 ? f_m2 : f_right);
-        const int nil = idx <= 1 ? il : (idx == 2 ? i1 : i2), nir = idx == 0 ? i1 : (idx == 1 ? i2 : ir);
-        left = nl;
-        f_left = nfl;
-        right = nr;
-        f_right = nfr;
-        il = nil;
-        ir = nir;
-    }
-    (void)ir;
-    { // the abandoned arm's midpoint and 3 + 3 points around the optimum (adaptive_integration.rs:96-131)
-        const double x0 = (middle < first_middle) ? (b + first_middle) / 2.0 : (first_middle + a) / 2.0;
-        const double lo = fmax(middle - (res * 3.0), a);
-        const double slo = (middle - lo) / 3.0;
-        const double x1 = lo + slo * 0.0, x2 = lo + slo * 1.0, x3 = lo + slo * 2.0;
-        const double hi = fmin(middle + (res * 3.0), b);
-        const double shi = (hi - middle) / 3.0;
-        const double x4 = middle + shi * 1.0, x5 = middle + shi * 2.0, x6 = middle + shi * 3.0;
-        eval3(x0, x1, x2, 3, f);
-        insert(x0, f[0], 0);
-        int h = insert(x1, f[1], 0);
-        h = insert(x2, f[2], h);
-        eval3(x3, x4, x5, 3, f);
-        h = insert(x3, f[0], h);
-        h = insert(x4, f[1], h);
-        h = insert(x5, f[2], h);
-        eval3(x6, x6, x6, 1, f);
-        insert(x6, f[0], h);
-    }
-    // ln_trapezoidal_integrate_grid_exp over the visited points in x order (rust-bio), summed in linear
-    // space relative to the maximum: ln( sum_i (e^{f_i} + e^{f_i+1}) / 2 * (x_i+1 - x_i) )
-    double value;
-    if (any_nan) {
-        status |= VLR_ST_NAN;
-        value = NAN;
-    } else if (best_f == neg_inf()) {
-        value = neg_inf();
-    } else {
-        double xp = gx[0], ep = exp(gf[0] - best_f), sum = 0.0;
-        for (int nx = gn[0]; nx >= 0; nx = gn[nx * gs]) {
-            const double xc = gx[nx * gs], ec = exp(gf[nx * gs] - best_f);
-            sum += (ep + ec) * (xc - xp);
-            xp = xc;
-            ep = ec;
-        }
-        value = best_f + log(sum * 0.5);
-    }
-    if (overflow) status |= VLR_ST_GRID_OVERFLOW;
-    if (be != nullptr && lc.ci == 0) { // base events of the artifact-free config feed the AFD (calling.rs:891-928)
-        const unsigned base = wa_add_u32(be_n, (unsigned)n);
-        const double disc = d_make(0, (int)((t.parent_disc ? 1u : 0u) << P));
-        for (int i = 0; i < n; ++i) {
-            const unsigned at = base + (unsigned)i;
-            if (at >= (unsigned)BE_CAP) {
-                status |= VLR_ST_BASE_EVENTS_OVERFLOW;
-                break;
+        if (t_in_sm) wave_pileup<3, true>(coT, nT, ksumT, m0T, w, nvalid, lnl, sp);
+        else wave_pileup<3, false>(coT, nT, ksumT, m0T, w, nvalid, lnl, sp);
+        const double f0 = prior_const + (lh_const + lnl[0]), f1 = prior_const + (lh_const + lnl[1]),
+                     f2 = prior_const + (lh_const + lnl[2]);
+        visit(x0, f0);
+        visit(x1, f1);
+        if (nvalid > 2) visit(x2, f2);
+        if (step == 0) {
+            f_left = f0;
+            f_right = f1;
+        } else if (step == 1) {
+            if (!have_middle) {
+                first_middle = middle;
+                f_first_m1 = f1;
+                f_first_m2 = f2;
             }
-            double* e = be + (size_t)at * 4;
-            e[0] = gf[i * gs];
-            e[1] = disc;
-            e[2 + P] = px;
-            e[2 + T] = gx[i * gs];
+            have_middle = true;
+            const double m1 = x1, m2 = x2, f_m1 = f1, f_m2 = f2;
+            int idx = 0;
+            double fb = f_left;
+            if (f_m1 > fb) {
+                idx = 1;
+                fb = f_m1;
+            }
+            if (f_m2 > fb) {
+                idx = 2;
+                fb = f_m2;
+            }
+            if (f_right > fb) idx = 3;
+            // neighbours of the argmax in [left, m1, m2, right] become the new bounds (the middle is not a candidate)
+            const double nl = idx <= 1 ? left : (idx == 2 ? m1 : m2), nfl = idx <= 1 ? f_left : (idx == 2 ? f_m1 : f_m2);
+            const double nr = idx == 0 ? m1 : (idx == 1 ? m2 : right), nfr = idx == 0 ? f_m1 : (idx == 1 ? f_m2 : f_right);
+            left = nl;
+            f_left = nfl;
+            right = nr;
+            f_right = nfr;
+        }
+        if (step <= 1) {
+            // while (((right - left) >= res && left < right) || middle.is_none())   (adaptive_integration.rs:52)
+            step = (!overflow && ((((right - left) >= res) && left < right) || !have_middle)) ? 1 : 2;
+        } else {
+            step++;
         }
     }
-    t.value = value;
+    if (any_nan) status |= VLR_ST_NAN;
+    if (overflow) status |= VLR_ST_GRID_OVERFLOW;
+    if (sp.h != 0) return;
+    t.value = neg_inf(); // set by wave_fin_coop
     t.best_f = best_f;
     t.best_x = best_x;
     t.n_evals = n_evals;
+    t.n_grid = n;
     t.status = status;
 }
 
-// ---------------------------------------------------------------------------------------------- lc advance (thread)
-// trapezoid over an outer grid (<= W_OGRID points, in place): stable insertion sort by x, then the same sum as above
-VLR_DEV_NOINLINE double wave_outer_trapezoid(double* x, double* f, int n, uint32_t& status) {
-    bool any_nan = false;
-    double fmx = neg_inf();
-    for (int i = 0; i < n; ++i) {
-        if (f[i] != f[i]) any_nan = true;
-        if (f[i] > fmx) fmx = f[i];
-    }
-    if (any_nan) {
-        status |= VLR_ST_NAN;
-        return NAN;
-    }
+// ---------------------------------------------------------------------------------------------- closing trapezoid (warp)
+// ln_trapezoidal_integrate_grid_exp over n visited points in any order (rust-bio): rank sort by (x, visit
+// order) into the scratch arrays (shared memory on the device), lanes over points, then lanes over intervals, summed in
+// linear space relative to the maximum: ln( sum_i (e^{f_i} + e^{f_i+1}) / 2 * (x_i+1 - x_i) ). scratch: 3 x W_GCAP doubles.
+// Equal abscissae keep visit order (zero-width intervals contribute nothing), like grid_trapezoid of the generic engine.
+VLR_DEV_NOINLINE double wave_fin_coop(const double* x, const double* f, int n, double fmx, bool any_nan, double* scratch) {
+    if (any_nan) return NAN;
     if (n < 2 || fmx == neg_inf()) return neg_inf();
-    for (int i = 1; i < n; ++i) {
-        const double xi = x[i], fi = f[i];
-        int j = i - 1;
-        while (j >= 0 && x[j] > xi) {
-            x[j + 1] = x[j];
-            f[j + 1] = f[j];
-            --j;
+    double* ux = scratch;               // unsorted abscissae
+    double* sx = scratch + W_GCAP;      // sorted abscissae
+    double* sf = scratch + 2 * W_GCAP;  // e^{f - max} in x order
+    warp_sync();
+    for (int a = lane_id(); a < n; a += LANES) ux[a] = x[a];
+    warp_sync();
+    for (int a = lane_id(); a < n; a += LANES) {
+        const double xi = ux[a];
+        int rank = 0;
+#pragma unroll 4
+        for (int j = 0; j < n; ++j) {
+            const double xj = ux[j];
+            rank += (xj < xi) || (xj == xi && j < a);
         }
-        x[j + 1] = xi;
-        f[j + 1] = fi;
+        sx[rank] = xi;
+        sf[rank] = m_exp(f[a] - fmx);
     }
-    double sum = 0.0, ep = m_exp(f[0] - fmx);
-    for (int i = 1; i < n; ++i) {
-        const double ec = m_exp(f[i] - fmx);
-        sum += (ep + ec) * (x[i] - x[i - 1]);
-        ep = ec;
-    }
+    warp_sync();
+    double sum = 0.0;
+    for (int a = lane_id(); a + 1 < n; a += LANES) sum += (sf[a] + sf[a + 1]) * (sx[a + 1] - sx[a]);
+    sum = w_sum_d(sum);
+    warp_sync();
     return fmx + m_log(sum * 0.5);
 }
 
@@ -462,72 +481,140 @@ VLR_DEV void wave_emit_task(WaveTask& t, int lc, int event, double px, bool disc
     t.best_f = neg_inf();
     t.best_x = 0.0;
     t.n_evals = 0;
+    t.n_grid = 0;
     t.status = 0;
 }
 
-// After the tasks of round `round` of an lc are complete: MAP bookkeeping in visit order (calling.rs:851-870), event
-// densities, and the next step of the enclosing integration (integrate_adaptive_generic over the root Range).
-VLR_DEV_NOINLINE void wave_lc_advance(const WavePlan& wp, const WaveBufs& wb, int lci, int round) {
+// ---------------------------------------------------------------------------------------------- lc advance (warp)
+// After the tasks of round `round` of an lc ran (task i of the lc used grid row rows + i * row_stride): integrate each
+// task's grid, MAP bookkeeping in visit order (calling.rs:851-870), event densities, base-event log for the AFD, and the
+// next step of the enclosing integration (integrate_adaptive_generic over the root Range). Control flow is warp-uniform
+// (every lane reads the same records); lane 0 alone writes.
+VLR_DEV_NOINLINE void wave_lc_advance(const WavePlan& wp, const WaveBufs& wb, int lci, int round, const double* rows_x,
+                                      const double* rows_f, int row_stride, double* scratch, bool want_be) {
     WaveLC& lc = wb.lcs[lci];
-    const WaveTask* tasks = wb.tasks[round & 1] + lc.task_base;
+    WaveTask* tasks = wb.tasks[round & 1] + lc.task_base;
     const int cnt = lc.task_count;
+    const int P = wp.P, T = wp.T;
+    const bool l0 = lane_id() == 0;
+    uint32_t status = lc.status, n_base = lc.n_base;
     double ofs[8];
     int no = 0;
     for (int i = 0; i < cnt; ++i) {
-        const WaveTask& t = tasks[i];
+        const WaveTask t = tasks[i];
         const int e = t.event;
-        lc.status |= t.status;
-        lc.n_base += t.n_evals;
-        if (t.n_evals > 0 && (!lc.map_set[e] || t.best_f > lc.map_joint[e])) {
+        const double* gx = rows_x + (size_t)i * row_stride;
+        const double* gf = rows_f + (size_t)i * row_stride;
+        const double value = wave_fin_coop(gx, gf, t.n_grid, t.best_f, (t.status & VLR_ST_NAN) != 0, scratch);
+        status |= t.status;
+        n_base += t.n_evals;
+        if (want_be && lc.ci == 0) { // base events of the artifact-free config feed the AFD (calling.rs:891-928)
+            unsigned base = 0;
+            if (l0) base = wa_add_u32(&wb.be_n[lc.li], (unsigned)t.n_grid);
+#ifndef VLR_HOST_EMU
+            base = __shfl_sync(FULL, base, 0, LANES);
+#endif
+            double* be = wb.be + (size_t)lc.li * BE_CAP * 4;
+            const double disc = d_make(0, (int)((t.parent_disc ? 1u : 0u) << P));
+            if (base + (unsigned)t.n_grid > (unsigned)BE_CAP) status |= VLR_ST_BASE_EVENTS_OVERFLOW;
+            for (int k = lane_id(); k < t.n_grid; k += LANES) {
+                const unsigned at = base + (unsigned)k;
+                if (at >= (unsigned)BE_CAP) break;
+                double* r = be + (size_t)at * 4;
+                r[0] = gf[k];
+                r[1] = disc;
+                r[2 + P] = t.parent_x;
+                r[2 + T] = gx[k];
+            }
+        }
+        if (l0 && t.n_evals > 0 && (!lc.map_set[e] || t.best_f > lc.map_joint[e])) {
             lc.map_set[e] = 1;
             lc.map_joint[e] = t.best_f;
             lc.map_vp[e] = t.parent_x;
             lc.map_vt[e] = t.best_x;
             lc.map_disc[e] = t.parent_disc ? 1 : 0;
         }
+        warp_sync();
         if (e == wp.outer_event) {
-            if (no < 8) ofs[no] = t.value;
+            if (no < 8) ofs[no] = value;
             no++;
-        } else {
-            lc.dens[e] = t.value;
+        } else if (l0) {
+            lc.dens[e] = value;
         }
     }
-    lc.task_count = 0;
-    if (!lc.outer_pending) return;
+    if (!lc.outer_pending) {
+        if (l0) {
+            lc.status = status;
+            lc.n_base = n_base;
+            lc.task_count = 0;
+        }
+        return;
+    }
     double* ox = wb.og_x + (size_t)lci * W_OGRID;
     double* of = wb.og_f + (size_t)lci * W_OGRID;
+    int outer_n = lc.outer_n, outer_overflow = lc.outer_overflow;
     for (int i = 0; i < no && i < 8; ++i) {
-        if (ofs[i] != ofs[i]) lc.status |= VLR_ST_NAN;
-        if (lc.outer_n < W_OGRID) {
-            ox[lc.outer_n] = lc.outer_xs[i];
-            of[lc.outer_n] = ofs[i];
-            lc.outer_n++;
+        if (ofs[i] != ofs[i]) status |= VLR_ST_NAN;
+        if (outer_n < W_OGRID) {
+            if (l0) {
+                ox[outer_n] = lc.outer_xs[i];
+                of[outer_n] = ofs[i];
+            }
+            outer_n++;
         } else {
-            lc.outer_overflow = 1;
+            outer_overflow = 1;
         }
     }
+    warp_sync();
     Adaptive st = lc.outer;
-    const bool more = st.consume(lc.outer_xs, ofs, lc.outer_overflow != 0);
+    double oxs[8];
+    for (int i = 0; i < 8; ++i) oxs[i] = lc.outer_xs[i];
+    const double lta = lc.ta, ltb = lc.tb;
+    warp_sync(); // every lane has read the lc before lane 0 updates it
+    const bool more = st.consume(oxs, ofs, outer_overflow != 0);
     if (more && round + 1 < W_MAXROUNDS) {
         double xs[8];
         const int k = st.points(xs);
-        lc.outer = st;
-        const unsigned tb = wa_add_u32(&wb.cnt->task_n[round + 1], (unsigned)k);
-        WaveTask* nt = wb.tasks[(round + 1) & 1] + tb;
-        for (int i = 0; i < k; ++i) {
-            lc.outer_xs[i] = xs[i];
-            wave_emit_task(nt[i], lci, wp.outer_event, xs[i], false, lc.ta, lc.tb);
+        if (l0) {
+            lc.outer = st;
+            const unsigned tb = wa_add_u32(&wb.cnt->task_n[round + 1], (unsigned)k);
+            WaveTask* nt = wb.tasks[(round + 1) & 1] + tb;
+            for (int i = 0; i < k; ++i) {
+                lc.outer_xs[i] = xs[i];
+                wave_emit_task(nt[i], lci, wp.outer_event, xs[i], false, lta, ltb);
+            }
+            lc.task_base = (int)tb;
+            lc.task_count = k;
+            const unsigned li = wa_add_u32(&wb.cnt->list_n[round + 1], 1u);
+            wb.list[(round + 1) & 1][li] = lci;
+            lc.outer_n = outer_n;
+            lc.outer_overflow = outer_overflow;
+            lc.status = status;
+            lc.n_base = n_base;
         }
-        lc.task_base = (int)tb;
-        lc.task_count = k;
-        const unsigned li = wa_add_u32(&wb.cnt->list_n[round + 1], 1u);
-        wb.list[(round + 1) & 1][li] = lci;
     } else {
-        lc.outer = st;
-        lc.outer_pending = 0;
-        if (lc.outer_overflow || more) lc.status |= VLR_ST_GRID_OVERFLOW;
-        lc.dens[wp.outer_event] = wave_outer_trapezoid(ox, of, lc.outer_n, lc.status);
+        if (outer_overflow || more) status |= VLR_ST_GRID_OVERFLOW;
+        bool any_nan = false;
+        double fmx = neg_inf();
+        for (int i = 0; i < outer_n; ++i) {
+            const double v = of[i];
+            if (v != v) any_nan = true;
+            if (v > fmx) fmx = v;
+        }
+        if (any_nan) status |= VLR_ST_NAN;
+        const double d = wave_fin_coop(ox, of, outer_n, fmx, any_nan, scratch);
+        if (l0) {
+            lc.outer = st;
+            lc.outer_pending = 0;
+            lc.outer_n = outer_n;
+            lc.outer_overflow = outer_overflow;
+            lc.dens[wp.outer_event] = d;
+            lc.status = status;
+            lc.n_base = n_base;
+            lc.task_count = 0;
+        }
     }
+    warp_sync();
 }
 
 // ---------------------------------------------------------------------------------------------- prep (warp per locus)

@@ -7,6 +7,7 @@
 // Host: vlr_call_batch() streams a host batch through NBUF slots (chunk of loci -> H2D -> kernel -> D2H, one CUDA
 // stream per slot) so copies overlap compute; vlr_call_batch_device() launches on device-resident buffers.
 // There is no CPU fallback: without a usable CUDA device vlr_ctx_create() fails with VLR_ERR_NO_DEVICE.
+#include <cuda_pipeline.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -93,9 +94,10 @@ struct WaveParams {
     int64_t sub_lo;   // first locus of the sub-chunk
     int n_sub;        // loci in the sub-chunk
     int want_be;      // AFD requested: log base events
+    int debug;        // VLR_WAVE_DEBUG=1: CTA 0 prints per-phase cycle counts of its first group
 };
 constexpr int WAVE_ROUND_THREADS = vlr_small::W_GROUP * vlr_small::W_MAXT; // 256
-constexpr size_t WAVE_ROUND_SMEM = (size_t)vlr_small::W_GROUP * vlr_small::W_SLOT_READS * 4 * sizeof(double);
+constexpr size_t WAVE_ROUND_SMEM = (size_t)vlr_small::W_GROUP * vlr_small::W_SLOT_STRIDE * sizeof(double);
 
 __global__ void __launch_bounds__(THREADS, 2) vlr_wave_prep_kernel(const __grid_constant__ WaveParams p) {
     using namespace vlr_small;
@@ -110,9 +112,10 @@ __global__ void __launch_bounds__(THREADS, 2) vlr_wave_prep_kernel(const __grid_
     }
 }
 
-// One CTA per group of W_GROUP lcs of the round's list: the leaf sample's coefficients are staged in shared memory (one
-// slot per lc), every thread runs one task (tasks of an lc sit in neighbouring lanes: their coefficient loads are
-// shared-memory broadcasts), then one thread per lc advances the lc and emits the next round's tasks.
+// One CTA per group of lcs of the round's list: the leaf sample's coefficients are staged in shared memory (one slot per
+// lc, cp.async), H = 1..8 neighbouring lanes run one task (tasks of an lc sit in neighbouring lanes: their coefficient
+// loads are shared-memory broadcasts), then the warps close the lcs of the group: trapezoids over the task grids, MAP
+// bookkeeping, the next round's tasks.
 __global__ void __launch_bounds__(WAVE_ROUND_THREADS, 2) vlr_wave_round_kernel(const __grid_constant__ WaveParams p, int round) {
     using namespace vlr_small;
     __shared__ int s_lc[W_GROUP], s_off[W_GROUP + 1];
@@ -121,46 +124,97 @@ __global__ void __launch_bounds__(WAVE_ROUND_THREADS, 2) vlr_wave_round_kernel(c
     const int* list = wb.list[round & 1];
     WaveTask* tasks = wb.tasks[round & 1];
     const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int gtid = (int)(blockIdx.x * blockDim.x) + tid;
     double* slots = reinterpret_cast<double*>(vlr_smem);
-    for (int g0 = (int)blockIdx.x * W_GROUP; g0 < n_list; g0 += (int)gridDim.x * W_GROUP) {
+    // full groups while the list is long; in the straggler rounds every CTA takes a short group and more lanes per task
+    int G = (n_list + (int)gridDim.x - 1) / (int)gridDim.x;
+    G = G < 1 ? 1 : (G > W_GROUP ? W_GROUP : G);
+    for (int g0 = (int)blockIdx.x * G; g0 < n_list; g0 += (int)gridDim.x * G) {
+        long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0;
         __syncthreads();
-        if (tid < W_GROUP) s_lc[tid] = g0 + tid < n_list ? list[g0 + tid] : -1;
-        __syncthreads();
-        if (tid == 0) {
-            int acc = 0;
-            for (int g = 0; g < W_GROUP; ++g) {
-                s_off[g] = acc;
-                if (s_lc[g] >= 0) acc += wb.lcs[s_lc[g]].task_count;
+        if (p.debug) tk0 = clock64();
+        if (tid < W_GROUP) { // warp 0: the group's lcs and the exclusive scan of their task counts
+            const int lci = (tid < G && g0 + tid < n_list) ? list[g0 + tid] : -1;
+            const int cnt = lci >= 0 ? wb.lcs[lci].task_count : 0;
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
             }
-            s_off[W_GROUP] = acc;
+            s_lc[tid] = lci;
+            s_off[tid] = incl - cnt;
+            if (tid == W_GROUP - 1) s_off[W_GROUP] = incl;
         }
-        for (int g = warp; g < W_GROUP; g += WAVE_ROUND_THREADS / 32) {
+        __syncthreads();
+        // thread -> task: H = 1..8 neighbouring lanes per task (as many as fit the CTA)
+        const int total = s_off[W_GROUP];
+        int H = 1;
+        while (H < 8 && total * H * 2 <= WAVE_ROUND_THREADS) H <<= 1;
+        const int q = tid / H;
+        const bool active = q < total;
+        int g_mine = 0;
+        if (active)
+            while (s_off[g_mine + 1] <= q) ++g_mine;
+        WSplit sp;
+        sp.H = H;
+        sp.h = tid & (H - 1);
+        sp.mask = ((1u << H) - 1u) << (lane & ~(H - 1));
+        // ---- the parent sample's coefficients -> slots; every task evaluates its parent pileup once
+        auto stage = [&](bool parent) {
+            for (int g = warp; g < G; g += WAVE_ROUND_THREADS / 32) {
+                const int lci = s_lc[g];
+                if (lci < 0) continue;
+                const WaveLC& L = wb.lcs[lci];
+                const int nr = parent ? L.nP : L.nT;
+                if (nr > W_SLOT_READS) continue; // deep pileup: read from the arena (L2)
+                const double2* src = reinterpret_cast<const double2*>(wb.coef + (parent ? L.coefP : L.coefT) * 4);
+                double2* dst = reinterpret_cast<double2*>(slots + (size_t)g * W_SLOT_STRIDE);
+                for (int i = lane; i < nr * 2; i += 32) __pipeline_memcpy_async(dst + i, src + i, sizeof(double2));
+            }
+            __pipeline_commit();
+            __pipeline_wait_prior(0);
+            __syncthreads();
+        };
+        stage(true);
+        double lh_const = 0.0;
+        if (active) {
+            const WaveLC& L = wb.lcs[s_lc[g_mine]];
+            const bool in_sm = L.nP <= W_SLOT_READS;
+            const double2* coP = in_sm ? reinterpret_cast<const double2*>(slots + (size_t)g_mine * W_SLOT_STRIDE)
+                                       : reinterpret_cast<const double2*>(wb.coef + L.coefP * 4);
+            lh_const = wave_task_parent(L, tasks[L.task_base + (q - s_off[g_mine])], coP, in_sm, sp);
+        }
+        __syncthreads();
+        // ---- the leaf sample's coefficients -> slots; the adaptive integrations
+        stage(false);
+        if (p.debug) tk1 = clock64();
+        if (active) {
+            const WaveLC& L = wb.lcs[s_lc[g_mine]];
+            WaveTask& t = tasks[L.task_base + (q - s_off[g_mine])];
+            const bool in_sm = L.nT <= W_SLOT_READS;
+            const double2* coT = in_sm ? reinterpret_cast<const double2*>(slots + (size_t)g_mine * W_SLOT_STRIDE)
+                                       : reinterpret_cast<const double2*>(wb.coef + L.coefT * 4);
+            const size_t row = (size_t)(blockIdx.x * blockDim.x) + (size_t)q;
+            wave_task_run(&p.sc, p.wp, L, t, coT, in_sm, lh_const, wb.gx + row * W_GCAP, wb.gf + row * W_GCAP, sp);
+        }
+        __syncthreads();
+        if (p.debug) tk2 = clock64();
+        // the coefficient slots are dead now: each warp takes 3 x W_GCAP doubles of them as sort scratch and closes the
+        // lcs g = warp, warp + 8, ... of the group
+        double* scratch = slots + (size_t)warp * 3 * W_GCAP;
+        for (int g = warp; g < G; g += WAVE_ROUND_THREADS / 32) {
             const int lci = s_lc[g];
             if (lci < 0) continue;
-            const WaveLC& L = wb.lcs[lci];
-            const int nT = L.nT;
-            if (nT > W_SLOT_READS) continue; // deep pileup: read from the arena (L2)
-            const double2* src = reinterpret_cast<const double2*>(wb.coef + L.coefT * 4);
-            double2* dst = reinterpret_cast<double2*>(slots + (size_t)g * W_SLOT_READS * 4);
-            for (int i = lane; i < nT * 2; i += 32) dst[i] = src[i];
+            const size_t row0 = (size_t)(blockIdx.x * blockDim.x) + (size_t)s_off[g];
+            wave_lc_advance(p.wp, wb, lci, round, wb.gx + row0 * W_GCAP, wb.gf + row0 * W_GCAP, W_GCAP, scratch, p.want_be != 0);
         }
-        __syncthreads();
-        const int total = s_off[W_GROUP];
-        if (tid < total) {
-            int g = 0;
-            while (s_off[g + 1] <= tid) ++g;
-            const int lci = s_lc[g];
-            const WaveLC& L = wb.lcs[lci];
-            WaveTask& t = tasks[L.task_base + (tid - s_off[g])];
-            const double2* coT = L.nT <= W_SLOT_READS ? reinterpret_cast<const double2*>(slots + (size_t)g * W_SLOT_READS * 4)
-                                                      : reinterpret_cast<const double2*>(wb.coef + L.coefT * 4);
-            const double2* coP = reinterpret_cast<const double2*>(wb.coef + L.coefP * 4);
-            wave_task_run(&p.sc, p.wp, L, t, coT, coP, wb.gx + gtid, wb.gf + gtid, wb.gn + gtid, wb.g_stride,
-                          p.want_be ? wb.be + (size_t)L.li * BE_CAP * 4 : nullptr, wb.be_n + L.li);
+        if (p.debug) {
+            __syncthreads();
+            tk3 = clock64();
+            if (blockIdx.x == 0 && tid == 0 && g0 == 0)
+                printf("round %d: n_list %d, G %d, H %d, group tasks %d: stage+parent %lld, tasks %lld, advance %lld cycles\n",
+                       round, n_list, G, H, total, tk1 - tk0, tk2 - tk1, tk3 - tk2);
         }
-        __syncthreads();
-        if (tid < W_GROUP && s_lc[tid] >= 0) wave_lc_advance(p.wp, wb, s_lc[tid], round);
     }
 }
 
@@ -214,7 +268,7 @@ struct Slot { // one in-flight chunk of vlr_call_batch
     int coef_cap = 0;
     bool be_ready = false;
     // wavefront pipeline workspace (one sub-chunk of loci at a time)
-    DevBuf w_cnt, w_loci, w_lcs, w_ogx, w_ogf, w_coef, w_tasks[2], w_list[2], w_deferred, w_gx, w_gf, w_gn, w_be, w_ben;
+    DevBuf w_cnt, w_loci, w_lcs, w_ogx, w_ogf, w_coef, w_tasks[2], w_list[2], w_deferred, w_gx, w_gf, w_be, w_ben;
 };
 
 } // namespace
@@ -295,7 +349,6 @@ vlr_status_t launch_wave(vlr_ctx* ctx, Slot& sl, const DevBatch& b, const DevRes
     CK(sl.w_deferred.ensure(sizeof(int) * (size_t)n_sub_cap));
     CK(sl.w_gx.ensure(sizeof(double) * (size_t)W_GCAP * g_stride));
     CK(sl.w_gf.ensure(sizeof(double) * (size_t)W_GCAP * g_stride));
-    CK(sl.w_gn.ensure(sizeof(short) * (size_t)W_GCAP * g_stride));
     CK(sl.w_ben.ensure(sizeof(unsigned) * (size_t)n_sub_cap));
     if (want_be) CK(sl.w_be.ensure(sizeof(double) * 4 * (size_t)BE_CAP * n_sub_cap));
     WaveParams p;
@@ -316,14 +369,16 @@ vlr_status_t launch_wave(vlr_ctx* ctx, Slot& sl, const DevBatch& b, const DevRes
     p.wb.deferred = (int*)sl.w_deferred.p;
     p.wb.gx = (double*)sl.w_gx.p;
     p.wb.gf = (double*)sl.w_gf.p;
-    p.wb.gn = (short*)sl.w_gn.p;
     p.wb.be = want_be ? (double*)sl.w_be.p : nullptr;
     p.wb.be_n = (unsigned*)sl.w_ben.p;
     p.wb.coef_cap = coef_cap;
     p.wb.lc_cap = lc_cap;
-    p.wb.g_stride = g_stride;
     p.ws = (WarpWs*)sl.ws.p;
     p.want_be = want_be ? 1 : 0;
+    {
+        const char* dbg = getenv("VLR_WAVE_DEBUG");
+        p.debug = dbg && dbg[0] == '1';
+    }
     KernelParams gp; // generic engine over the deferred loci
     gp.sc = ctx->dsc;
     gp.b = b;
@@ -540,7 +595,7 @@ void vlr_ctx_destroy(vlr_ctx_t* ctx) {
                          &s.map_vaf, &s.map_config, &s.best_event, &s.status, &s.n_base, &s.afd_count, &s.afd_vaf,
                          &s.afd_logp, &s.ws, &s.coef, &s.be, &s.ticket, &s.w_cnt, &s.w_loci, &s.w_lcs, &s.w_ogx,
                          &s.w_ogf, &s.w_coef, &s.w_tasks[0], &s.w_tasks[1], &s.w_list[0], &s.w_list[1], &s.w_deferred,
-                         &s.w_gx, &s.w_gf, &s.w_gn, &s.w_be, &s.w_ben};
+                         &s.w_gx, &s.w_gf, &s.w_be, &s.w_ben};
         for (DevBuf* b : all) b->release();
     };
     if (ctx->stream) {
