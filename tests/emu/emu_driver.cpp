@@ -145,7 +145,7 @@ extern "C" int32_t vlr_emu_wave_call_batch(const vlr_scenario_t* sc, const vlr_b
                 wave_task_run(&ds, wp, lc, task, reinterpret_cast<const double2*>(wb.coef + lc.coefT * 4), false, lh,
                               wb.gx + (size_t)t * W_GCAP, wb.gf + (size_t)t * W_GCAP, one);
             }
-            wave_lc_advance(wp, wb, list[k], round, wb.gx, wb.gf, W_GCAP, scratch.data(), want_be);
+            wave_lc_advance(wp, wb, list[k], round, wb.gx, wb.gf, W_GCAP, scratch.data(), want_be, WGroup{0, 1, 1u});
         }
     }
     for (int64_t i = 0; i < L; ++i) wave_finish_locus(&ds, &db, &dr, wp, wb, ws, i, (int)i, *c);

@@ -436,21 +436,40 @@ VLR_DEV void wave_task_run(const DevScenario* sc, const WavePlan& wp, const Wave
     t.status = status;
 }
 
-// ---------------------------------------------------------------------------------------------- closing trapezoid (warp)
+// A cooperating lane group (the whole warp, or an 8-lane quarter of it so that one warp closes four lcs at a time
+// and their global-memory latencies overlap; a single lane in the host emulation).
+struct WGroup {
+    int lane, n;
+    unsigned mask;
+};
+#ifdef VLR_HOST_EMU
+VLR_DEV void grp_sync(const WGroup&) {}
+VLR_DEV double grp_sum_d(double v, const WGroup&) { return v; }
+VLR_DEV unsigned grp_bcast_u(unsigned v, const WGroup&) { return v; }
+#else
+VLR_DEV void grp_sync(const WGroup& g) { __syncwarp(g.mask); }
+VLR_DEV double grp_sum_d(double v, const WGroup& g) { // xor butterfly: identical bits in every lane of the group
+    for (int o = g.n >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(g.mask, v, o);
+    return v;
+}
+VLR_DEV unsigned grp_bcast_u(unsigned v, const WGroup& g) { return __shfl_sync(g.mask, v, 0, g.n); }
+#endif
+
+// ---------------------------------------------------------------------------------------------- closing trapezoid (lane group)
 // ln_trapezoidal_integrate_grid_exp over n visited points in any order (rust-bio): rank sort by (x, visit
 // order) into the scratch arrays (shared memory on the device), lanes over points, then lanes over intervals, summed in
 // linear space relative to the maximum: ln( sum_i (e^{f_i} + e^{f_i+1}) / 2 * (x_i+1 - x_i) ). scratch: 3 x W_GCAP doubles.
 // Equal abscissae keep visit order (zero-width intervals contribute nothing), like grid_trapezoid of the generic engine.
-VLR_DEV_NOINLINE double wave_fin_coop(const double* x, const double* f, int n, double fmx, bool any_nan, double* scratch) {
+VLR_DEV_NOINLINE double wave_fin_coop(const double* x, const double* f, int n, double fmx, bool any_nan, double* scratch, const WGroup grp) {
     if (any_nan) return NAN;
     if (n < 2 || fmx == neg_inf()) return neg_inf();
     double* ux = scratch;               // unsorted abscissae
     double* sx = scratch + W_GCAP;      // sorted abscissae
     double* sf = scratch + 2 * W_GCAP;  // e^{f - max} in x order
-    warp_sync();
-    for (int a = lane_id(); a < n; a += LANES) ux[a] = x[a];
-    warp_sync();
-    for (int a = lane_id(); a < n; a += LANES) {
+    grp_sync(grp);
+    for (int a = grp.lane; a < n; a += grp.n) ux[a] = x[a];
+    grp_sync(grp);
+    for (int a = grp.lane; a < n; a += grp.n) {
         const double xi = ux[a];
         int rank = 0;
 #pragma unroll 4
@@ -461,11 +480,11 @@ VLR_DEV_NOINLINE double wave_fin_coop(const double* x, const double* f, int n, d
         sx[rank] = xi;
         sf[rank] = m_exp(f[a] - fmx);
     }
-    warp_sync();
+    grp_sync(grp);
     double sum = 0.0;
-    for (int a = lane_id(); a + 1 < n; a += LANES) sum += (sf[a] + sf[a + 1]) * (sx[a + 1] - sx[a]);
-    sum = w_sum_d(sum);
-    warp_sync();
+    for (int a = grp.lane; a + 1 < n; a += grp.n) sum += (sf[a] + sf[a + 1]) * (sx[a + 1] - sx[a]);
+    sum = grp_sum_d(sum, grp);
+    grp_sync(grp);
     return fmx + m_log(sum * 0.5);
 }
 
@@ -491,12 +510,12 @@ VLR_DEV void wave_emit_task(WaveTask& t, int lc, int event, double px, bool disc
 // next step of the enclosing integration (integrate_adaptive_generic over the root Range). Control flow is warp-uniform
 // (every lane reads the same records); lane 0 alone writes.
 VLR_DEV_NOINLINE void wave_lc_advance(const WavePlan& wp, const WaveBufs& wb, int lci, int round, const double* rows_x,
-                                      const double* rows_f, int row_stride, double* scratch, bool want_be) {
+                                      const double* rows_f, int row_stride, double* scratch, bool want_be, const WGroup grp) {
     WaveLC& lc = wb.lcs[lci];
     WaveTask* tasks = wb.tasks[round & 1] + lc.task_base;
     const int cnt = lc.task_count;
     const int P = wp.P, T = wp.T;
-    const bool l0 = lane_id() == 0;
+    const bool l0 = grp.lane == 0;
     uint32_t status = lc.status, n_base = lc.n_base;
     double ofs[8];
     int no = 0;
@@ -505,19 +524,17 @@ VLR_DEV_NOINLINE void wave_lc_advance(const WavePlan& wp, const WaveBufs& wb, in
         const int e = t.event;
         const double* gx = rows_x + (size_t)i * row_stride;
         const double* gf = rows_f + (size_t)i * row_stride;
-        const double value = wave_fin_coop(gx, gf, t.n_grid, t.best_f, (t.status & VLR_ST_NAN) != 0, scratch);
+        const double value = wave_fin_coop(gx, gf, t.n_grid, t.best_f, (t.status & VLR_ST_NAN) != 0, scratch, grp);
         status |= t.status;
         n_base += t.n_evals;
         if (want_be && lc.ci == 0) { // base events of the artifact-free config feed the AFD (calling.rs:891-928)
             unsigned base = 0;
             if (l0) base = wa_add_u32(&wb.be_n[lc.li], (unsigned)t.n_grid);
-#ifndef VLR_HOST_EMU
-            base = __shfl_sync(FULL, base, 0, LANES);
-#endif
+            base = grp_bcast_u(base, grp);
             double* be = wb.be + (size_t)lc.li * BE_CAP * 4;
             const double disc = d_make(0, (int)((t.parent_disc ? 1u : 0u) << P));
             if (base + (unsigned)t.n_grid > (unsigned)BE_CAP) status |= VLR_ST_BASE_EVENTS_OVERFLOW;
-            for (int k = lane_id(); k < t.n_grid; k += LANES) {
+            for (int k = grp.lane; k < t.n_grid; k += grp.n) {
                 const unsigned at = base + (unsigned)k;
                 if (at >= (unsigned)BE_CAP) break;
                 double* r = be + (size_t)at * 4;
@@ -534,7 +551,7 @@ VLR_DEV_NOINLINE void wave_lc_advance(const WavePlan& wp, const WaveBufs& wb, in
             lc.map_vt[e] = t.best_x;
             lc.map_disc[e] = t.parent_disc ? 1 : 0;
         }
-        warp_sync();
+        grp_sync(grp);
         if (e == wp.outer_event) {
             if (no < 8) ofs[no] = value;
             no++;
@@ -565,12 +582,12 @@ VLR_DEV_NOINLINE void wave_lc_advance(const WavePlan& wp, const WaveBufs& wb, in
             outer_overflow = 1;
         }
     }
-    warp_sync();
+    grp_sync(grp);
     Adaptive st = lc.outer;
     double oxs[8];
     for (int i = 0; i < 8; ++i) oxs[i] = lc.outer_xs[i];
     const double lta = lc.ta, ltb = lc.tb;
-    warp_sync(); // every lane has read the lc before lane 0 updates it
+    grp_sync(grp); // every lane has read the lc before lane 0 updates it
     const bool more = st.consume(oxs, ofs, outer_overflow != 0);
     if (more && round + 1 < W_MAXROUNDS) {
         double xs[8];
@@ -602,7 +619,7 @@ VLR_DEV_NOINLINE void wave_lc_advance(const WavePlan& wp, const WaveBufs& wb, in
             if (v > fmx) fmx = v;
         }
         if (any_nan) status |= VLR_ST_NAN;
-        const double d = wave_fin_coop(ox, of, outer_n, fmx, any_nan, scratch);
+        const double d = wave_fin_coop(ox, of, outer_n, fmx, any_nan, scratch, grp);
         if (l0) {
             lc.outer = st;
             lc.outer_pending = 0;
@@ -614,7 +631,7 @@ VLR_DEV_NOINLINE void wave_lc_advance(const WavePlan& wp, const WaveBufs& wb, in
             lc.task_count = 0;
         }
     }
-    warp_sync();
+    grp_sync(grp);
 }
 
 // ---------------------------------------------------------------------------------------------- prep (warp per locus)

@@ -199,14 +199,21 @@ __global__ void __launch_bounds__(WAVE_ROUND_THREADS, 2) vlr_wave_round_kernel(c
         }
         __syncthreads();
         if (p.debug) tk2 = clock64();
-        // the coefficient slots are dead now: each warp takes 3 x W_GCAP doubles of them as sort scratch and closes the
-        // lcs g = warp, warp + 8, ... of the group
-        double* scratch = slots + (size_t)warp * 3 * W_GCAP;
-        for (int g = warp; g < G; g += WAVE_ROUND_THREADS / 32) {
-            const int lci = s_lc[g];
-            if (lci < 0) continue;
-            const size_t row0 = (size_t)(blockIdx.x * blockDim.x) + (size_t)s_off[g];
-            wave_lc_advance(p.wp, wb, lci, round, wb.gx + row0 * W_GCAP, wb.gf + row0 * W_GCAP, W_GCAP, scratch, p.want_be != 0);
+        // the coefficient slots are dead now: every 8-lane group takes 3 x W_GCAP doubles of them as sort scratch and
+        // closes one lc of the group (32 lcs at a time per CTA: their global-memory latencies overlap)
+        {
+            const int gi = tid >> 3;
+            WGroup grp;
+            grp.lane = tid & 7;
+            grp.n = 8;
+            grp.mask = 0xffu << (lane & ~7);
+            double* scratch = slots + (size_t)gi * 3 * W_GCAP;
+            const int lci = gi < G ? s_lc[gi] : -1;
+            if (lci >= 0) {
+                const size_t row0 = (size_t)(blockIdx.x * blockDim.x) + (size_t)s_off[gi];
+                wave_lc_advance(p.wp, wb, lci, round, wb.gx + row0 * W_GCAP, wb.gf + row0 * W_GCAP, W_GCAP, scratch,
+                                p.want_be != 0, grp);
+            }
         }
         if (p.debug) {
             __syncthreads();
