@@ -248,6 +248,10 @@ vlr_status_t vlr_ctx_reserve(vlr_ctx_t* ctx, int64_t max_reads_per_locus);
 void* vlr_host_alloc(size_t bytes);
 void vlr_host_free(void* p);
 
+/* Measured fp64 FMA throughput of `device` in TFLOP/s (2 flops per FMA): a register-resident DFMA microbenchmark,
+ * the denominator of the fp64 roofline this path is bound by (HBM is not the bound here). */
+vlr_status_t vlr_measure_fp64_peak(int32_t device, double* tflops);
+
 /* Number of kernels the last vlr_call_batch* launched (for bench accounting). */
 int64_t vlr_last_launch_count(const vlr_ctx_t* ctx);
 /* The context's stream (cudaStream_t) so callers can time with CUDA events. */

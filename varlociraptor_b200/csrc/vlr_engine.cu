@@ -239,6 +239,24 @@ __global__ void __launch_bounds__(THREADS, 2) vlr_wave_finish_kernel(const __gri
     }
 }
 
+// fp64 peak microbenchmark: 8 independent FMA chains per thread, register resident
+__global__ void __launch_bounds__(256) vlr_fp64_peak_kernel(double* out, int iters) {
+    double a0 = 1.0 + threadIdx.x * 1e-9, a1 = a0 + 1e-3, a2 = a0 + 2e-3, a3 = a0 + 3e-3, a4 = a0 + 4e-3, a5 = a0 + 5e-3,
+           a6 = a0 + 6e-3, a7 = a0 + 7e-3;
+    const double m = 0.999999999, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c);
+        a1 = fma(a1, m, c);
+        a2 = fma(a2, m, c);
+        a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c);
+        a5 = fma(a5, m, c);
+        a6 = fma(a6, m, c);
+        a7 = fma(a7, m, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
 inline int align16(size_t x) { return (int)((x + 15) & ~(size_t)15); }
 
 #define CK(call)                                                                      \
@@ -478,6 +496,41 @@ const char* vlr_status_string(vlr_status_t st) {
 const char* vlr_last_error(const vlr_ctx_t* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 int64_t vlr_last_launch_count(const vlr_ctx_t* ctx) { return ctx ? ctx->launches : 0; }
 void* vlr_ctx_stream(const vlr_ctx_t* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+vlr_status_t vlr_measure_fp64_peak(int32_t device, double* tflops) {
+    if (!tflops) return VLR_ERR_INVALID_ARGUMENT;
+    *tflops = 0.0;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        return VLR_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= n_dev || cudaSetDevice(device) != cudaSuccess) return VLR_ERR_INVALID_ARGUMENT;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return VLR_ERR_CUDA;
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
+    double* out = nullptr;
+    if (cudaMalloc(&out, sizeof(double) * (size_t)blocks * threads) != cudaSuccess) return VLR_ERR_OUT_OF_MEMORY;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) { // first repetition warms up
+        cudaEventRecord(e0);
+        vlr_fp64_peak_kernel<<<blocks, threads>>>(out, iters);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) break;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    if (cudaGetLastError() != cudaSuccess || best > 1e29f) return VLR_ERR_CUDA;
+    *tflops = 2.0 * 8.0 * (double)iters * (double)blocks * threads / ((double)best * 1e-3) / 1e12;
+    return VLR_OK;
+}
 
 void* vlr_host_alloc(size_t bytes) {
     void* p = nullptr;

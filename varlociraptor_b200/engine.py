@@ -55,6 +55,8 @@ def lib():
         l.vlr_last_error.argtypes = [C.c_void_p]
         l.vlr_status_string.restype = C.c_char_p
         l.vlr_status_string.argtypes = [C.c_int32]
+        l.vlr_measure_fp64_peak.restype = C.c_int32
+        l.vlr_measure_fp64_peak.argtypes = [C.c_int32, C.POINTER(C.c_double)]
         if l.vlr_abi_version() != abi.VLR_ABI_VERSION:
             raise EngineError("ABI version mismatch between abi.py and libvlr_engine.so")
         _lib = l
@@ -63,7 +65,16 @@ def lib():
 
 EXPORTED_SYMBOLS = ["vlr_ctx_create", "vlr_ctx_destroy", "vlr_call_batch", "vlr_call_batch_device", "vlr_ctx_reserve",
                     "vlr_host_alloc", "vlr_host_free", "vlr_last_launch_count", "vlr_ctx_stream", "vlr_last_error",
-                    "vlr_status_string", "vlr_abi_version"]
+                    "vlr_status_string", "vlr_abi_version", "vlr_measure_fp64_peak"]
+
+
+def measure_fp64_peak(device: int = 0) -> float:
+    """Measured fp64 FMA throughput of the device in TFLOP/s (register-resident DFMA microbenchmark)."""
+    out = C.c_double(0.0)
+    rc = lib().vlr_measure_fp64_peak(device, C.byref(out))
+    if rc != 0:
+        raise EngineError("vlr_measure_fp64_peak failed: %s" % lib().vlr_status_string(rc).decode())
+    return float(out.value)
 
 
 def pinned_empty(shape, dtype) -> np.ndarray:
