@@ -215,6 +215,8 @@ def main():
     torch.cuda.set_device(local_rank)
     device = "cuda:%d" % local_rank
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version banner there)
         dist.init_process_group("nccl", device_id=torch.device(device))
     from varlociraptor_b200 import engine
     scenario, batch = make_batch(args.config, args.loci, seed=20260100 + args.config + 17 * rank, pinned=True)
