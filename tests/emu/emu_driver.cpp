@@ -57,6 +57,9 @@ extern "C" int32_t vlr_emu_call_batch(const vlr_scenario_t* sc, const vlr_batch_
     if (!prep.build(sc)) return VLR_ERR_INVALID_ARGUMENT;
     DevScenario ds = prep.view(sc->samples, sc->events, sc->nodes, sc->set_vafs, sc->spectra, prep.lfc_nodes.data(),
                                prep.lfc_ordinal.data());
+    std::vector<PriorTabEntry> ptab(PRIOR_TAB_N);
+    std::memset(ptab.data(), 0, sizeof(PriorTabEntry) * PRIOR_TAB_N);
+    ds.prior_tab = ptab.data();
     DevBatch db;
     DevResults dr;
     emu_views(batch, results, db, dr);

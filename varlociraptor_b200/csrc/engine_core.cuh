@@ -854,6 +854,13 @@ VLR_DEV double prob_somatic_mutation(double rate, double somatic_vaf) { // prior
 }
 VLR_DEV double binomial_coeff(unsigned n, unsigned k) { // statrs factorial::binomial
     if (k > n) return 0.0;
+    if (n <= 30) { // floor(0.5 + exp(ln n! - ln k! - ln (n-k)!)) is the exact integer for small n: compute it exactly
+        // (ploidies are 1..4 in practice; the log/exp form below was 57 % of the pedigree kernel's instructions)
+        if (k > n - k) k = n - k;
+        unsigned long long r = 1;
+        for (unsigned i = 1; i <= k; ++i) r = r * (unsigned long long)(n - k + i) / (unsigned long long)i;
+        return (double)r;
+    }
     double fn = 1.0, fk = 1.0, fnk = 1.0;
     for (unsigned i = 2; i <= n; ++i) fn *= (double)i;
     for (unsigned i = 2; i <= k; ++i) fk *= (double)i;
@@ -890,6 +897,7 @@ VLR_DEV_NOINLINE double prob_mendelian_alt_counts(Ctx& c, unsigned sp0, unsigned
     Lse acc;
     acc.init();
     bool valid = false;
+    const double ln_rate = m_log(rate);
     for (int i = 0; i < n0; ++i)
         for (int j = 0; j < n1; ++j) {
             unsigned p1 = c0[i], p2 = c1[j];
@@ -901,7 +909,7 @@ VLR_DEV_NOINLINE double prob_mendelian_alt_counts(Ctx& c, unsigned sp0, unsigned
                     if (a1 + a2 <= ta) {
                         double p = prob_select(sp0, sa0, a1, p1 - a1) + prob_select(sp1, sa1, a2, p2 - a2);
                         int missing = (int)ta - (int)(a1 + a2);
-                        acc.add(p + m_log(rate) * (double)missing);
+                        acc.add(p + ln_rate * (double)missing);
                     }
         }
     if (!valid) {
@@ -1049,6 +1057,103 @@ VLR_DEV_NOINLINE double prior_full(Ctx& c_, const Ops& ev) {
 
 // Prior::compute (prior.rs:718-761)
 VLR_DEV_NOINLINE double prior_compute_uncached(Ctx& c_, const Ops& ev);
+
+// All-discrete VAF vector, no per-record prior overrides: look the prior up in the context's table, computing and
+// publishing it on a miss. Lane 0 talks to the table and broadcasts, so the warp's control flow stays uniform.
+#ifdef VLR_PTAB_DEBUG
+static long g_ptab_hits = 0, g_ptab_miss = 0;
+struct PtabReport { ~PtabReport() { fprintf(stderr, "ptab hits %ld miss %ld\n", g_ptab_hits, g_ptab_miss); } } static g_ptab_report;
+#endif
+VLR_DEV_NOINLINE double prior_tab_compute(Ctx& c_, const Ops& ev) {
+    Ctx& c = warp_ctx(c_);
+    const DevScenario* sc = c.sc;
+    PriorTabEntry* tab = sc->prior_tab;
+    if (tab == nullptr || !(c.het_override != c.het_override) || !(c.semr_override != c.semr_override))
+        return prior_compute_uncached(c, ev);
+    const int S = sc->S;
+    unsigned h = 2166136261u ^ (unsigned)c.vartype;
+    for (int s = 0; s < S; ++s) {
+        h = (h ^ (unsigned)d_lo(ev.vaf[s])) * 16777619u;
+        h = (h ^ (unsigned)d_hi(ev.vaf[s])) * 16777619u;
+    }
+    h ^= h >> 16; // murmur3 finaliser: the VAFs' low mantissa bits are all zero, FNV alone leaves the low hash bits equal
+    h *= 0x85ebca6bu;
+    h ^= h >> 13;
+    h *= 0xc2b2ae35u;
+    h ^= h >> 16;
+    // ---- probe (lane 0): found -> value; else the first empty slot (or none)
+    int found = 0, slot = -1;
+    double value = 0.0;
+    unsigned side = 0;
+    if (lane_id() == 0) {
+        for (int k = 0; k < 8; ++k) {
+            PriorTabEntry* e = tab + ((h + (unsigned)k) & (PRIOR_TAB_N - 1));
+#ifdef VLR_HOST_EMU
+            const unsigned st = e->state;
+#else
+            unsigned st; // acquire: the entry's fields are read after (and only if) the state says "readable"
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(st) : "l"(&e->state) : "memory");
+#endif
+            if (st == 2u) {
+                bool same = e->vartype == c.vartype;
+                for (int s = 0; s < S; ++s) same = same && (e->vaf[s] == ev.vaf[s]);
+                if (same) {
+                    found = 1;
+                    value = e->value;
+                    side = e->side_status;
+                    break;
+                }
+            } else if (st == 0u) {
+                slot = (int)((h + (unsigned)k) & (PRIOR_TAB_N - 1));
+                break;
+            } // st == 1: someone is writing it; keep probing (worst case we compute without publishing)
+        }
+    }
+#ifndef VLR_HOST_EMU
+    found = __shfl_sync(FULL, found, 0, LANES);
+    slot = __shfl_sync(FULL, slot, 0, LANES);
+    value = __shfl_sync(FULL, value, 0, LANES);
+    side = __shfl_sync(FULL, side, 0, LANES);
+#endif
+    if (found) {
+#ifdef VLR_PTAB_DEBUG
+        g_ptab_hits++;
+#endif
+        c.status |= side;
+        return value;
+    }
+#ifdef VLR_PTAB_DEBUG
+    g_ptab_miss++;
+#endif
+    const uint32_t s0 = c.status;
+    c.status = 0;
+    const double p = prior_compute_uncached(c, ev);
+    side = c.status;
+    c.status = s0 | side;
+    if (slot >= 0 && lane_id() == 0) {
+        PriorTabEntry* e = tab + slot;
+#ifdef VLR_HOST_EMU
+        const bool won = e->state == 0u;
+        if (won) e->state = 1u;
+#else
+        const bool won = atomicCAS(&e->state, 0u, 1u) == 0u;
+#endif
+        if (won) {
+            e->vartype = c.vartype;
+            e->side_status = side;
+            for (int s = 0; s < S; ++s) e->vaf[s] = ev.vaf[s];
+            e->value = p;
+#ifdef VLR_HOST_EMU
+            e->state = 2u;
+#else
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&e->state), "r"(2u) : "memory");
+#endif
+        }
+    }
+    warp_sync();
+    return p;
+}
+
 VLR_DEV_NOINLINE double prior_compute(Ctx& c_, const Ops& ev) {
     Ctx& c = warp_ctx(c_);
     const int S = c.sc->S;
@@ -1059,7 +1164,7 @@ VLR_DEV_NOINLINE double prior_compute(Ctx& c_, const Ops& ev) {
         for (int s = 0; s < S; ++s) same = same && (c.pc_key[i][s] == ev.vaf[s]);
         if (same) return c.pc_val[i];
     }
-    const double p = prior_compute_uncached(c, ev);
+    const double p = prior_tab_compute(c, ev);
     if (c.pc_n < PRIOR_CACHE) {
         const int i = c.pc_n;
         for (int s = 0; s < S; ++s) c.pc_key[i][s] = ev.vaf[s];

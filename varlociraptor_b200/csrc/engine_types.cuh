@@ -130,7 +130,20 @@ template <class T> VLR_DEV T ldin(const T* p) { return __ldcs(p); }
 #endif
 
 // ------------------------------------------------------------------------------------------------ device views
+// Context-level memo of Prior::compute for all-discrete VAF vectors (prior.rs:718-736 keeps an LRU(1000) per contig):
+// the value depends only on the scenario, the variant type and the VAF vector, so it is shared by all loci of a context.
+// Open addressing; an entry goes 0 (empty) -> 1 (being written by the warp that won the CAS) -> 2 (readable).
+constexpr int PRIOR_TAB_N = 1024; // power of two
+struct PriorTabEntry {
+    unsigned state;
+    unsigned side_status; // status bits the computation raised (they must reach every locus that uses the entry)
+    int vartype, pad;
+    double vaf[VLR_MAX_SAMPLES];
+    double value;
+};
+
 struct DevScenario {
+    PriorTabEntry* prior_tab; // NULL = no table
     int S, E, n_nodes, n_set_vafs, n_spectra, full_prior, all_uniform, n_lfc_nodes;
     const vlr_sample_t* samples;
     const vlr_event_t* events;

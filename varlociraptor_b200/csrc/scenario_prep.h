@@ -144,6 +144,7 @@ struct ScenarioPrep {
                      const double* set_vafs, const vlr_spectrum_t* spectra, const int* lfc_nodes_p,
                      const int* lfc_ordinal_p) const {
         DevScenario d;
+        d.prior_tab = nullptr;
         d.S = src->n_samples;
         d.E = src->n_events;
         d.n_nodes = src->n_nodes;

@@ -313,7 +313,7 @@ struct vlr_ctx {
     size_t smem_bytes = 0;
     ScenarioPrep prep;
     DevScenario dsc;
-    DevBuf d_samples, d_events, d_nodes, d_set_vafs, d_spectra, d_lfc_nodes, d_lfc_ordinal;
+    DevBuf d_samples, d_events, d_nodes, d_set_vafs, d_spectra, d_lfc_nodes, d_lfc_ordinal, d_prior_tab;
     cudaStream_t stream = nullptr; // the context's own stream (device-pointer entry)
     Slot dev_slot;                 // workspace of the device-pointer entry
     Slot slots[NBUF];
@@ -599,6 +599,9 @@ vlr_status_t vlr_ctx_create(const vlr_scenario_t* scenario, int32_t device, vlr_
                               (const vlr_node_t*)ctx->d_nodes.p, (const double*)ctx->d_set_vafs.p,
                               (const vlr_spectrum_t*)ctx->d_spectra.p, (const int*)ctx->d_lfc_nodes.p,
                               (const int*)ctx->d_lfc_ordinal.p);
+    CKB(ctx->d_prior_tab.ensure(sizeof(PriorTabEntry) * PRIOR_TAB_N));
+    CKB(cudaMemset(ctx->d_prior_tab.p, 0, sizeof(PriorTabEntry) * PRIOR_TAB_N));
+    ctx->dsc.prior_tab = (PriorTabEntry*)ctx->d_prior_tab.p;
     // The tree walk recurses once per tree level (density -> subdensity -> density); frames hold an Ops copy and the
     // integration state. Size the per-thread stack from the scenario's depth.
     size_t stack = 4096 + (size_t)(ctx->prep.max_depth + 2) * 1024;
@@ -665,7 +668,7 @@ void vlr_ctx_destroy(vlr_ctx_t* ctx) {
     free_slot(ctx->dev_slot);
     for (auto& s : ctx->slots) free_slot(s);
     DevBuf* sc[] = {&ctx->d_samples, &ctx->d_events, &ctx->d_nodes, &ctx->d_set_vafs, &ctx->d_spectra,
-                    &ctx->d_lfc_nodes, &ctx->d_lfc_ordinal};
+                    &ctx->d_lfc_nodes, &ctx->d_lfc_ordinal, &ctx->d_prior_tab};
     for (DevBuf* b : sc) b->release();
     delete ctx;
 }
