@@ -11,5 +11,5 @@ rows=list(csv.reader(open('gpurun_out/launches_wave.csv')))
 hdr=[i for i,r in enumerate(rows) if r and r[0]=='ID'][0]
 cols=rows[hdr]
 ki=cols.index('Kernel Name'); vi=cols.index('Metric Value')
-print(" ".join("%s:%s"%(r[ki][19:24], r[vi]) for r in rows[hdr+1+13:] if len(r)>vi))
+print(" ".join("%s:%s"%(r[ki][19:24], r[vi]) for r in rows[hdr+1+15:] if len(r)>vi))
 PY

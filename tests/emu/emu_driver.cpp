@@ -3,6 +3,7 @@
 // TEST INFRASTRUCTURE ONLY. It exists so the warp-uniform control flow of the CUDA engine (tree walk, adaptive
 // integration, prior, bias selection, MAP/AFD bookkeeping) can be compared with the oracle in the GPU-less build
 // container. It is never linked into or loaded by the product library (libvlr_engine.so), which has no CPU path.
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -135,7 +136,10 @@ extern "C" int32_t vlr_emu_wave_call_batch(const vlr_scenario_t* sc, const vlr_b
     wb.lc_cap = lc_cap;
     WarpWs* ws = new WarpWs;
     Ctx* c = new Ctx;
-    for (int64_t i = 0; i < L; ++i) wave_prep_locus(&ds, &db, wp, wb, i, (int)i, want_be, *c);
+    for (int64_t i = 0; i < L; ++i) wave_pre_locus(&ds, &db, wp, wb, i, (int)i, want_be, *c);
+    const int n_lc = (int)std::min<unsigned>(cnt.n_lc, (unsigned)lc_cap);
+    for (int k = 0; k < n_lc; ++k) wave_lc_init(&ds, wp, wb, k);
+    for (int k = 0; k < n_lc; ++k) wave_lc_coef(&ds, &db, wp, wb, k, 0, want_be, *c);
     for (int round = 0; round < wp.max_rounds; ++round) {
         const int n_list = (int)cnt.list_n[round];
         const int* list = wb.list[round & 1];

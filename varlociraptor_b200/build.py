@@ -23,7 +23,8 @@ def is_stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if force or is_stale():
         nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+        extra = os.environ.get("VLR_NVCC_EXTRA", "").split()  # tuning experiments (-D...), never set in the product build
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
         subprocess.check_call(cmd, cwd=CSRC)
     return LIB
 

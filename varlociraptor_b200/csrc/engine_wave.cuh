@@ -49,7 +49,7 @@ VLR_DEV unsigned long long wa_add_u64(unsigned long long* p, unsigned long long 
 #endif
 
 struct WaveCounters {
-    unsigned long long ticket[4]; // prep, finish, deferred (generic kernel), spare
+    unsigned long long ticket[4]; // pre, finish, deferred (generic kernel), coefficients
     unsigned long long coef_used; // reads allocated in the coefficient arena
     unsigned int n_lc, n_deferred;
     unsigned int list_n[W_MAXROUNDS + 2];
@@ -60,6 +60,16 @@ struct WaveLocus {
     int lc_base, n_cfg; // n_cfg = 0: deferred to the generic engine
     int n_twins;
     uint32_t status;
+    // what the per-lc kernels need from the pre-pass
+    uint32_t lf;
+    int coef_total, has_alt_loci;
+    int n_obs[2], s_one[2], coef_off[2];
+    int surviving[NCFG];
+    int64_t coef_base, singleton_row;
+    double forward_rate;
+    double pa, pb;                    // limits of the outer (root Range) integration
+    double ev_a[MAXE], ev_b[MAXE];    // limits of the leaf integration per event
+    int8_t ev_kind[MAXE];             // 0 pruned, 1 leaf task under a discrete parent, 2 point, 3 outer
 };
 
 struct WaveLC { // one (locus, artifact config)
@@ -634,24 +644,22 @@ VLR_DEV_NOINLINE void wave_lc_advance(const WavePlan& wp, const WaveBufs& wb, in
     grp_sync(grp);
 }
 
-// ---------------------------------------------------------------------------------------------- prep (warp per locus)
-// calling.rs:586-626 + bias/*.rs (locus_prepass), per config likelihood.rs hoisting (read_coefficients), then per event
-// what GenericPosterior::density (generic.rs:191-422) decides before any integration starts.
-VLR_DEV void wave_prep_locus(const DevScenario* sc, const DevBatch* b, const WavePlan& wp, const WaveBufs& wb, int64_t locus,
-                             int li, bool want_be, Ctx& c) {
+// ---------------------------------------------------------------------------------------------- prep
+// Three kernels, so that each one's code fits the instruction caches (a single warp-per-locus prep kernel spent most of
+// its cycles waiting for instruction fetch: 43 KB of text, 16 warps per SM in different phases):
+//   wave_pre_locus  warp per locus : calling.rs:586-626 + bias/*.rs (locus_prepass); per event what
+//                                    GenericPosterior::density (generic.rs:191-422) decides before any integration
+//                                    starts; lc and coefficient-arena allocation
+//   wave_lc_init    thread per lc  : the lc record and its round-0 tasks (cold scalar code, 32 lcs per instruction)
+//   wave_lc_coef    warp per lc    : likelihood.rs hoisting (read_coefficients) for both samples, point events
+VLR_DEV void wave_pre_locus(const DevScenario* sc, const DevBatch* b, const WavePlan& wp, const WaveBufs& wb, int64_t locus,
+                            int li, bool want_be, Ctx& c) {
     const int E = sc->E, P = wp.P, T = wp.T;
     c.sc = sc;
     c.b = b;
-    c.res = nullptr;
-    c.ws = nullptr;
-    c.be = nullptr;
-    c.n_rec = 0;
     c.locus = locus;
     c.status = 0;
     c.lf = b->lflags[locus];
-    c.vartype = (c.lf >> VLR_LF_VARTYPE_SHIFT) & 3;
-    c.n_base = 0;
-    c.n_pileup_evals = 0;
     BiasPlan plan;
     locus_prepass(c, plan);
     WaveLocus& wl = wb.loci[li];
@@ -712,7 +720,9 @@ VLR_DEV void wave_prep_locus(const DevScenario* sc, const DevBatch* b, const Wav
     const int coef_total = c.coef_total;
     int lc_base = 0;
     int64_t coef_base = 0;
+    bool allocated = false;
     if (!defer) {
+        allocated = true;
         unsigned lb = 0;
         unsigned long long cb = 0;
         if (lane_id() == 0) {
@@ -727,68 +737,168 @@ VLR_DEV void wave_prep_locus(const DevScenario* sc, const DevBatch* b, const Wav
         coef_base = (int64_t)cb;
         if ((int64_t)lb + n_cfg > (int64_t)wb.lc_cap || coef_base + (int64_t)n_cfg * coef_total > wb.coef_cap) defer = true;
     }
+    if (lane_id() != 0) return;
     if (defer) {
-        if (lane_id() == 0) {
-            const unsigned d = wa_add_u32(&wb.cnt->n_deferred, 1u);
-            wb.deferred[d] = (int)locus;
-            wl.lc_base = 0;
-            wl.n_cfg = 0;
-            wl.n_twins = 0;
-            wl.status = 0;
-        }
+        if (allocated) // lcs were allocated before a table or the arena ran out: mark the ones inside the table as dead
+            for (int ci = 0; ci < n_cfg; ++ci)
+                if ((int64_t)lc_base + ci < (int64_t)wb.lc_cap) wb.lcs[lc_base + ci].li = -1;
+        const unsigned d = wa_add_u32(&wb.cnt->n_deferred, 1u);
+        wb.deferred[d] = (int)locus;
+        wl.lc_base = 0;
+        wl.n_cfg = 0;
+        wl.n_twins = 0;
+        wl.status = 0;
         return;
     }
-    if (lane_id() == 0) {
-        wl.lc_base = lc_base;
-        wl.n_cfg = n_cfg;
-        wl.n_twins = plan.n_twins;
-        wl.status = c.status; // hints of the pre-pass (singleton adjustment, filtered alignments)
-        if (want_be) wb.be_n[li] = 0;
+    wl.lc_base = lc_base;
+    wl.n_cfg = n_cfg;
+    wl.n_twins = plan.n_twins;
+    wl.status = c.status; // hints of the pre-pass (singleton adjustment, filtered alignments)
+    wl.lf = c.lf;
+    wl.coef_base = coef_base;
+    wl.coef_total = coef_total;
+    wl.singleton_row = c.singleton_row;
+    wl.forward_rate = plan.forward_rate;
+    wl.has_alt_loci = plan.has_alt_loci ? 1 : 0;
+    for (int k = 0; k < NCFG; ++k) wl.surviving[k] = k < plan.n_surviving ? plan.surviving[k] : 0;
+    for (int s = 0; s < 2; ++s) {
+        wl.n_obs[s] = c.n_obs[s];
+        wl.s_one[s] = c.s_one[s];
+        wl.coef_off[s] = c.coef_off[s];
+    }
+    wl.pa = pa;
+    wl.pb = pb;
+    for (int e = 0; e < MAXE; ++e) {
+        wl.ev_kind[e] = e < E ? (int8_t)ev_kind[e] : 0;
+        wl.ev_a[e] = e < E ? ev_a[e] : 0.0;
+        wl.ev_b[e] = e < E ? ev_b[e] : 0.0;
+    }
+    if (want_be) wb.be_n[li] = 0;
+    for (int ci = 0; ci < n_cfg; ++ci) { // so that the per-lc kernels find their locus
+        WaveLC& lc = wb.lcs[lc_base + ci];
+        lc.li = li;
+        lc.ci = ci;
+    }
+}
+
+// One thread per lc: everything of the lc record that does not need the reads, and the round-0 tasks.
+VLR_DEV void wave_lc_init(const DevScenario* sc, const WavePlan& wp, const WaveBufs& wb, int lci) {
+    WaveLC& lc = wb.lcs[lci];
+    if (lc.li < 0) return; // dead (its locus was deferred after allocation)
+    const WaveLocus& wl = wb.loci[lc.li];
+    const int E = sc->E, P = wp.P, T = wp.T;
+    const int ci = lc.ci;
+    lc.art_id = ci == 0 ? 0 : wl.surviving[ci - 1];
+    lc.nP = wl.n_obs[P];
+    lc.nT = wl.n_obs[T];
+    lc.m0P = wl.s_one[P];
+    lc.m0T = wl.s_one[T];
+    lc.status = 0;
+    lc.n_base = 0;
+    lc.coefP = wl.coef_base + (int64_t)ci * wl.coef_total + wl.coef_off[P];
+    lc.coefT = wl.coef_base + (int64_t)ci * wl.coef_total + wl.coef_off[T];
+    lc.ksumP = lc.ksumT = 0.0; // wave_lc_coef
+    lc.outer_pending = 0;
+    lc.outer_n = 0;
+    lc.outer_overflow = 0;
+    lc.ta = lc.tb = 0.0;
+    int n_tasks = 0;
+    for (int e = 0; e < MAXE; ++e) {
+        lc.dens[e] = neg_inf();
+        lc.map_set[e] = 0;
+        lc.map_joint[e] = lc.map_vp[e] = lc.map_vt[e] = 0.0;
+        lc.map_disc[e] = 3;
+        if (e >= E || (ci > 0 && !sc->events[e].has_artifact_twin)) continue;
+        if (wl.ev_kind[e] == 1) n_tasks += 1;
+        if (wl.ev_kind[e] == 3) n_tasks += 2;
+    }
+    lc.task_base = 0;
+    lc.task_count = 0;
+    if (n_tasks == 0) return;
+    const unsigned tb = wa_add_u32(&wb.cnt->task_n[0], (unsigned)n_tasks);
+    WaveTask* nt = wb.tasks[0] + tb;
+    int k = 0;
+    for (int e = 0; e < E; ++e) {
+        if (ci > 0 && !sc->events[e].has_artifact_twin) continue;
+        if (wl.ev_kind[e] == 1) {
+            const double v = sc->set_vafs[sc->nodes[wp.root_node[e]].vaf_offset];
+            wave_emit_task(nt[k++], lci, e, v, true, wl.ev_a[e], wl.ev_b[e]);
+        } else if (wl.ev_kind[e] == 3) {
+            Adaptive st;
+            st.init(wl.pa, wl.pb, sc->samples[P].resolution);
+            double xs[8];
+            const int np = st.points(xs); // [min, max]
+            for (int i = 0; i < np; ++i) {
+                lc.outer_xs[i] = xs[i];
+                wave_emit_task(nt[k++], lci, e, xs[i], false, wl.ev_a[e], wl.ev_b[e]);
+            }
+            lc.outer = st;
+            lc.outer_pending = 1;
+            lc.ta = wl.ev_a[e];
+            lc.tb = wl.ev_b[e];
+        }
+    }
+    lc.task_base = (int)tb;
+    lc.task_count = k;
+    const unsigned at = wa_add_u32(&wb.cnt->list_n[0], 1u);
+    wb.list[0][at] = lci;
+}
+
+// One warp per lc: the per-read coefficients of both samples under the lc's artifact config, and the point events
+// (both nodes a single VAF, e.g. the absent event): one joint evaluation each, like joint() of the generic engine.
+VLR_DEV void wave_lc_coef(const DevScenario* sc, const DevBatch* b, const WavePlan& wp, const WaveBufs& wb, int lci,
+                          int64_t sub_lo, bool want_be, Ctx& c) {
+    WaveLC& lc = wb.lcs[lci];
+    const int li = lc.li, ci = lc.ci;
+    if (li < 0) return; // dead
+    const WaveLocus& wl = wb.loci[li];
+    const int E = sc->E, P = wp.P, T = wp.T;
+    c.sc = sc;
+    c.b = b;
+    c.locus = sub_lo + li;
+    c.status = 0;
+    c.lf = wl.lf;
+    c.singleton_row = wl.singleton_row;
+    c.n_pileup_evals = 0;
+    c.art.id = ci == 0 ? 0 : wl.surviving[ci - 1];
+    c.art.forward_rate = wl.forward_rate;
+    c.art.has_alt_loci = wl.has_alt_loci != 0;
+    c.coef = wb.coef + (wl.coef_base + (int64_t)ci * wl.coef_total) * 4;
+    c.coef_in_sm = 0;
+    c.coef_cap = wl.coef_total;
+    c.coef_total = wl.coef_total;
+    for (int s = 0; s < 2; ++s) {
+        c.n_obs[s] = wl.n_obs[s];
+        c.s_one[s] = wl.s_one[s];
+        c.s_gt1[s] = 0;
+        c.coef_off[s] = wl.coef_off[s];
     }
     warp_sync();
+    for (int s = 0; s < 2; ++s) read_coefficients(c, s);
     double* be = want_be ? wb.be + (size_t)li * BE_CAP * 4 : nullptr;
-    for (int ci = 0; ci < n_cfg; ++ci) {
-        c.status = 0;
-        c.art.id = ci == 0 ? 0 : plan.surviving[ci - 1];
-        c.art.forward_rate = plan.forward_rate;
-        c.art.has_alt_loci = plan.has_alt_loci;
-        c.coef = wb.coef + (coef_base + (int64_t)ci * coef_total) * 4;
-        c.coef_in_sm = 0;
-        c.coef_cap = coef_total;
-        for (int s = 0; s < 2; ++s) read_coefficients(c, s);
-        const int lci = lc_base + ci;
-        WaveLC& lc = wb.lcs[lci];
-        uint32_t n_base = 0;
-        // point events (both nodes a single VAF, e.g. the absent event): one joint evaluation here (generic.rs joint())
-        double dens[MAXE], mj[MAXE], mvp[MAXE], mvt[MAXE];
-        int mset[MAXE];
-        int n_tasks = 0;
-        for (int e = 0; e < E; ++e) {
-            dens[e] = neg_inf();
-            mset[e] = 0;
-            mj[e] = mvp[e] = mvt[e] = 0.0;
-            if (ci > 0 && !sc->events[e].has_artifact_twin) continue;
-            if (ev_kind[e] == 1) n_tasks += 1;
-            if (ev_kind[e] == 3) n_tasks += 2;
-            if (ev_kind[e] != 2) continue;
-            const double v = sc->set_vafs[sc->nodes[wp.root_node[e]].vaf_offset];
-            const double w = sc->set_vafs[sc->nodes[wp.child_node[e]].vaf_offset];
-            const double prior = (wave_prior_ok(sc, P, v) && wave_prior_ok(sc, T, w)) ? 0.0 : neg_inf();
-            double lh = 0.0;
-            for (int s = 0; s < 2; ++s) { // sample-index order (generic.rs:511-551)
-                const double vs = s == P ? v : w;
-                const double by = sc->samples[s].contamination_by >= 0 ? v : 0.0;
-                lh += sample_likelihood_call(c, s, vs, by);
-            }
-            const double j = prior + lh;
-            if (j != j) c.status |= VLR_ST_NAN;
-            n_base++;
-            dens[e] = j;
-            mset[e] = 1;
-            mj[e] = j;
-            mvp[e] = v;
-            mvt[e] = w;
-            if (be != nullptr && ci == 0 && lane_id() == 0) {
+    uint32_t n_base = 0;
+    for (int e = 0; e < E; ++e) {
+        if (wl.ev_kind[e] != 2 || (ci > 0 && !sc->events[e].has_artifact_twin)) continue;
+        const double v = sc->set_vafs[sc->nodes[wp.root_node[e]].vaf_offset];
+        const double w = sc->set_vafs[sc->nodes[wp.child_node[e]].vaf_offset];
+        const double prior = (wave_prior_ok(sc, P, v) && wave_prior_ok(sc, T, w)) ? 0.0 : neg_inf();
+        double lh = 0.0;
+        for (int s = 0; s < 2; ++s) { // sample-index order (generic.rs:511-551)
+            const double vs = s == P ? v : w;
+            const double by = sc->samples[s].contamination_by >= 0 ? v : 0.0;
+            lh += sample_likelihood_call(c, s, vs, by);
+        }
+        const double j = prior + lh;
+        if (j != j) c.status |= VLR_ST_NAN;
+        n_base++;
+        if (lane_id() == 0) {
+            lc.dens[e] = j;
+            lc.map_set[e] = 1;
+            lc.map_joint[e] = j;
+            lc.map_vp[e] = v;
+            lc.map_vt[e] = w;
+            lc.map_disc[e] = 3;
+            if (be != nullptr && ci == 0) {
                 const unsigned at = wa_add_u32(&wb.be_n[li], 1u);
                 if (at < (unsigned)BE_CAP) {
                     double* r = be + (size_t)at * 4;
@@ -801,64 +911,15 @@ VLR_DEV void wave_prep_locus(const DevScenario* sc, const DevBatch* b, const Wav
                 }
             }
         }
-        if (lane_id() == 0) {
-            lc.li = li;
-            lc.ci = ci;
-            lc.art_id = c.art.id;
-            lc.nP = c.n_obs[P];
-            lc.nT = c.n_obs[T];
-            lc.m0P = c.s_one[P];
-            lc.m0T = c.s_one[T];
-            lc.status = c.status;
-            lc.n_base = n_base;
-            lc.coefP = coef_base + (int64_t)ci * coef_total + c.coef_off[P];
-            lc.coefT = coef_base + (int64_t)ci * coef_total + c.coef_off[T];
-            lc.ksumP = c.ksum[P];
-            lc.ksumT = c.ksum[T];
-            lc.outer_pending = 0;
-            lc.outer_n = 0;
-            lc.outer_overflow = 0;
-            lc.ta = lc.tb = 0.0;
-            for (int e = 0; e < MAXE; ++e) {
-                lc.dens[e] = e < E ? dens[e] : neg_inf();
-                lc.map_set[e] = e < E ? (uint8_t)mset[e] : 0;
-                lc.map_joint[e] = e < E ? mj[e] : 0.0;
-                lc.map_vp[e] = e < E ? mvp[e] : 0.0;
-                lc.map_vt[e] = e < E ? mvt[e] : 0.0;
-                lc.map_disc[e] = 3;
-            }
-            lc.task_base = 0;
-            lc.task_count = 0;
-            if (n_tasks > 0) {
-                const unsigned tb = wa_add_u32(&wb.cnt->task_n[0], (unsigned)n_tasks);
-                WaveTask* nt = wb.tasks[0] + tb;
-                int k = 0;
-                for (int e = 0; e < E; ++e) {
-                    if (ci > 0 && !sc->events[e].has_artifact_twin) continue;
-                    if (ev_kind[e] == 1) {
-                        const double v = sc->set_vafs[sc->nodes[wp.root_node[e]].vaf_offset];
-                        wave_emit_task(nt[k++], lci, e, v, true, ev_a[e], ev_b[e]);
-                    } else if (ev_kind[e] == 3) {
-                        lc.outer.init(pa, pb, smP.resolution);
-                        double xs[8];
-                        const int np = lc.outer.points(xs); // [min, max]
-                        for (int i = 0; i < np; ++i) {
-                            lc.outer_xs[i] = xs[i];
-                            wave_emit_task(nt[k++], lci, e, xs[i], false, ev_a[e], ev_b[e]);
-                        }
-                        lc.outer_pending = 1;
-                        lc.ta = ev_a[e];
-                        lc.tb = ev_b[e];
-                    }
-                }
-                lc.task_base = (int)tb;
-                lc.task_count = k;
-                const unsigned at = wa_add_u32(&wb.cnt->list_n[0], 1u);
-                wb.list[0][at] = lci;
-            }
-        }
         warp_sync();
     }
+    if (lane_id() == 0) {
+        lc.ksumP = c.ksum[P];
+        lc.ksumT = c.ksum[T];
+        lc.status |= c.status;
+        lc.n_base += n_base;
+    }
+    warp_sync();
 }
 
 // ---------------------------------------------------------------------------------------------- finish (warp per locus)

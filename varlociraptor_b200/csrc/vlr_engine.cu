@@ -99,7 +99,11 @@ struct WaveParams {
 constexpr int WAVE_ROUND_THREADS = vlr_small::W_GROUP * vlr_small::W_MAXT; // 256
 constexpr size_t WAVE_ROUND_SMEM = (size_t)vlr_small::W_GROUP * vlr_small::W_SLOT_STRIDE * sizeof(double);
 
-__global__ void __launch_bounds__(THREADS, 2) vlr_wave_prep_kernel(const __grid_constant__ WaveParams p) {
+#ifndef VLR_PREP_MIN_CTAS
+#define VLR_PREP_MIN_CTAS 3
+#endif
+// prep, split in three so that each kernel's text fits the instruction caches (engine_wave.cuh "prep")
+__global__ void __launch_bounds__(THREADS, VLR_PREP_MIN_CTAS) vlr_wave_pre_kernel(const __grid_constant__ WaveParams p) {
     using namespace vlr_small;
     Ctx& c = *reinterpret_cast<Ctx*>(vlr_smem + (size_t)group_in_cta() * CTX_STRIDE);
     for (;;) {
@@ -107,7 +111,28 @@ __global__ void __launch_bounds__(THREADS, 2) vlr_wave_prep_kernel(const __grid_
         if (lane_id() == 0) t = atomicAdd(&p.wb.cnt->ticket[0], 1ULL);
         t = __shfl_sync(FULL, t, 0, LANES);
         if (t >= (unsigned long long)p.n_sub) break;
-        wave_prep_locus(&p.sc, &p.b, p.wp, p.wb, p.sub_lo + (int64_t)t, (int)t, p.want_be != 0, c);
+        wave_pre_locus(&p.sc, &p.b, p.wp, p.wb, p.sub_lo + (int64_t)t, (int)t, p.want_be != 0, c);
+        warp_sync();
+    }
+}
+
+__global__ void __launch_bounds__(256) vlr_wave_lcinit_kernel(const __grid_constant__ WaveParams p) {
+    using namespace vlr_small;
+    const int n_lc = (int)min(p.wb.cnt->n_lc, (unsigned)p.wb.lc_cap);
+    for (int k = (int)(blockIdx.x * blockDim.x + threadIdx.x); k < n_lc; k += (int)(gridDim.x * blockDim.x))
+        wave_lc_init(&p.sc, p.wp, p.wb, k);
+}
+
+__global__ void __launch_bounds__(THREADS, VLR_PREP_MIN_CTAS) vlr_wave_coef_kernel(const __grid_constant__ WaveParams p) {
+    using namespace vlr_small;
+    Ctx& c = *reinterpret_cast<Ctx*>(vlr_smem + (size_t)group_in_cta() * CTX_STRIDE);
+    const unsigned long long n_lc = min(p.wb.cnt->n_lc, (unsigned)p.wb.lc_cap);
+    for (;;) {
+        unsigned long long t = 0;
+        if (lane_id() == 0) t = atomicAdd(&p.wb.cnt->ticket[3], 1ULL);
+        t = __shfl_sync(FULL, t, 0, LANES);
+        if (t >= n_lc) break;
+        wave_lc_coef(&p.sc, &p.b, p.wp, p.wb, (int)t, p.sub_lo, p.want_be != 0, c);
         warp_sync();
     }
 }
@@ -307,7 +332,7 @@ struct vlr_ctx {
     bool small = false;   // which engine variant serves this scenario
     bool wave = false;    // two-level chain scenario: the wavefront pipeline serves it (deferring loci it cannot)
     WavePlan wplan;
-    int wave_grid_prep = 0, wave_grid_round = 0;
+    int wave_grid_prep = 0, wave_grid_round = 0, wave_grid_finish = 0;
     size_t wave_smem_prep = 0;
     int ctx_stride = 0;
     size_t smem_bytes = 0;
@@ -422,13 +447,15 @@ vlr_status_t launch_wave(vlr_ctx* ctx, Slot& sl, const DevBatch& b, const DevRes
         p.sub_lo = lo;
         p.n_sub = (int)std::min<int64_t>(n_sub_cap, b.n_loci - lo);
         CK(cudaMemsetAsync(sl.w_cnt.p, 0, sizeof(WaveCounters), stream));
-        vlr_wave_prep_kernel<<<ctx->wave_grid_prep, THREADS, ctx->wave_smem_prep, stream>>>(p);
+        vlr_wave_pre_kernel<<<ctx->wave_grid_prep, THREADS, ctx->wave_smem_prep, stream>>>(p);
+        vlr_wave_lcinit_kernel<<<ctx->n_sms * 4, 256, 0, stream>>>(p);
+        vlr_wave_coef_kernel<<<ctx->wave_grid_prep, THREADS, ctx->wave_smem_prep, stream>>>(p);
         for (int round = 0; round < ctx->wplan.max_rounds; ++round)
             vlr_wave_round_kernel<<<ctx->wave_grid_round, WAVE_ROUND_THREADS, WAVE_ROUND_SMEM, stream>>>(p, round);
-        vlr_wave_finish_kernel<<<ctx->wave_grid_prep, THREADS, ctx->wave_smem_prep, stream>>>(p);
+        vlr_wave_finish_kernel<<<ctx->wave_grid_finish, THREADS, ctx->wave_smem_prep, stream>>>(p);
         vlr_call_kernel_vlr_small<<<ctx->grid, THREADS, ctx->smem_bytes, stream>>>(gp);
         CK(cudaGetLastError());
-        ctx->launches += 3 + ctx->wplan.max_rounds;
+        ctx->launches += 5 + ctx->wplan.max_rounds;
     }
     return VLR_OK;
 }
@@ -626,16 +653,19 @@ vlr_status_t vlr_ctx_create(const vlr_scenario_t* scenario, int32_t device, vlr_
                 !(wave_env && wave_env[0] == '0');
     if (ctx->wave) {
         ctx->wave_smem_prep = (size_t)WARPS_PER_CTA * (size_t)ctx->ctx_stride;
-        CKB(cudaFuncSetAttribute(vlr_wave_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->wave_smem_prep));
+        CKB(cudaFuncSetAttribute(vlr_wave_pre_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->wave_smem_prep));
+        CKB(cudaFuncSetAttribute(vlr_wave_coef_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->wave_smem_prep));
         CKB(cudaFuncSetAttribute(vlr_wave_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->wave_smem_prep));
         CKB(cudaFuncSetAttribute(vlr_wave_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WAVE_ROUND_SMEM));
         int n1 = 0, n2 = 0;
-        CKB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n1, vlr_wave_prep_kernel, THREADS, ctx->wave_smem_prep));
+        CKB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n1, vlr_wave_coef_kernel, THREADS, ctx->wave_smem_prep));
         CKB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n2, vlr_wave_round_kernel, WAVE_ROUND_THREADS, WAVE_ROUND_SMEM));
         ctx->wave_grid_prep = std::max(1, n1) * ctx->n_sms;
         ctx->wave_grid_round = std::max(1, n2) * ctx->n_sms;
         // the finish kernel indexes the per-warp scratch (WarpWs) of the generic workspace: same number of warps or fewer
-        if (ctx->wave_grid_prep > ctx->grid) ctx->wave_grid_prep = ctx->grid;
+        int n3 = 0;
+        CKB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n3, vlr_wave_finish_kernel, THREADS, ctx->wave_smem_prep));
+        ctx->wave_grid_finish = std::min(std::max(1, n3) * ctx->n_sms, ctx->grid);
     }
     CKB(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     for (int i = 0; i < NBUF; ++i) CKB(cudaStreamCreateWithFlags(&ctx->slots[i].stream, cudaStreamNonBlocking));
