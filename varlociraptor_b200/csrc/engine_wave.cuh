@@ -28,7 +28,10 @@ constexpr int W_OGRID = 96;      // points of an outer (root Range) integration 
 constexpr int W_GCAP = GRID_CAP; // points of a leaf integration grid (same capacity as the generic engine)
 constexpr int W_MAXT = 8;        // tasks an lc can have in one round
 constexpr int W_MAXROUNDS = 64;
-constexpr int W_GROUP = 32;      // lcs per CTA group (= shared-memory coefficient slots)
+#ifndef VLR_WAVE_GROUP
+#define VLR_WAVE_GROUP 16 // measured: 4 CTAs x 16 lcs per SM overlap their stage / task / advance phases best (vs 2 x 32)
+#endif
+constexpr int W_GROUP = VLR_WAVE_GROUP; // lcs per CTA group (= shared-memory coefficient slots), <= 32
 constexpr int W_SLOT_READS = 104; // reads per shared-memory coefficient slot (3.3 KB); deeper pileups are read from L2
 constexpr int W_SLOT_STRIDE = W_SLOT_READS * 4 + 2; // doubles between slots: 16 bytes of skew against bank conflicts
 

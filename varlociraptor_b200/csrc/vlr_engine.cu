@@ -96,7 +96,7 @@ struct WaveParams {
     int want_be;      // AFD requested: log base events
     int debug;        // VLR_WAVE_DEBUG=1: CTA 0 prints per-phase cycle counts of its first group
 };
-constexpr int WAVE_ROUND_THREADS = vlr_small::W_GROUP * vlr_small::W_MAXT; // 256
+constexpr int WAVE_ROUND_THREADS = vlr_small::W_GROUP * vlr_small::W_MAXT; // 128
 constexpr size_t WAVE_ROUND_SMEM = (size_t)vlr_small::W_GROUP * vlr_small::W_SLOT_STRIDE * sizeof(double);
 
 #ifndef VLR_PREP_MIN_CTAS
@@ -141,7 +141,10 @@ __global__ void __launch_bounds__(THREADS, VLR_PREP_MIN_CTAS) vlr_wave_coef_kern
 // lc, cp.async), H = 1..8 neighbouring lanes run one task (tasks of an lc sit in neighbouring lanes: their coefficient
 // loads are shared-memory broadcasts), then the warps close the lcs of the group: trapezoids over the task grids, MAP
 // bookkeeping, the next round's tasks.
-__global__ void __launch_bounds__(WAVE_ROUND_THREADS, 2) vlr_wave_round_kernel(const __grid_constant__ WaveParams p, int round) {
+#ifndef VLR_ROUND_MIN_CTAS
+#define VLR_ROUND_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(WAVE_ROUND_THREADS, VLR_ROUND_MIN_CTAS) vlr_wave_round_kernel(const __grid_constant__ WaveParams p, int round) {
     using namespace vlr_small;
     __shared__ int s_lc[W_GROUP], s_off[W_GROUP + 1];
     const WaveBufs& wb = p.wb;
@@ -157,7 +160,7 @@ __global__ void __launch_bounds__(WAVE_ROUND_THREADS, 2) vlr_wave_round_kernel(c
         long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0;
         __syncthreads();
         if (p.debug) tk0 = clock64();
-        if (tid < W_GROUP) { // warp 0: the group's lcs and the exclusive scan of their task counts
+        if (tid < 32) { // warp 0: the group's lcs and the exclusive scan of their task counts
             const int lci = (tid < G && g0 + tid < n_list) ? list[g0 + tid] : -1;
             const int cnt = lci >= 0 ? wb.lcs[lci].task_count : 0;
             int incl = cnt;
@@ -166,9 +169,11 @@ __global__ void __launch_bounds__(WAVE_ROUND_THREADS, 2) vlr_wave_round_kernel(c
                 const int v = __shfl_up_sync(0xffffffffu, incl, o);
                 if (lane >= o) incl += v;
             }
-            s_lc[tid] = lci;
-            s_off[tid] = incl - cnt;
-            if (tid == W_GROUP - 1) s_off[W_GROUP] = incl;
+            if (tid < W_GROUP) {
+                s_lc[tid] = lci;
+                s_off[tid] = incl - cnt;
+                if (tid == W_GROUP - 1) s_off[W_GROUP] = incl;
+            }
         }
         __syncthreads();
         // thread -> task: H = 1..8 neighbouring lanes per task (as many as fit the CTA)
