@@ -476,11 +476,15 @@ VLR_DEV unsigned grp_bcast_u(unsigned v, const WGroup& g) { return __shfl_sync(g
 VLR_DEV_NOINLINE double wave_fin_coop(const double* x, const double* f, int n, double fmx, bool any_nan, double* scratch, const WGroup grp) {
     if (any_nan) return NAN;
     if (n < 2 || fmx == neg_inf()) return neg_inf();
-    double* ux = scratch;               // unsorted abscissae
-    double* sx = scratch + W_GCAP;      // sorted abscissae
-    double* sf = scratch + 2 * W_GCAP;  // e^{f - max} in x order
+    double* ux = scratch;          // abscissae in visit order
+    double* ue = scratch + W_GCAP; // e^{f - max} in visit order
+    short* inv = reinterpret_cast<short*>(scratch + 2 * W_GCAP); // inv[rank] = visit index
     grp_sync(grp);
-    for (int a = grp.lane; a < n; a += grp.n) ux[a] = x[a];
+    for (int a = grp.lane; a < n; a += grp.n) { // both rows in flight together; the exp is off the sort's critical path
+        const double xa = x[a], fa = f[a];
+        ux[a] = xa;
+        ue[a] = m_exp(fa - fmx);
+    }
     grp_sync(grp);
     for (int a = grp.lane; a < n; a += grp.n) {
         const double xi = ux[a];
@@ -490,12 +494,14 @@ VLR_DEV_NOINLINE double wave_fin_coop(const double* x, const double* f, int n, d
             const double xj = ux[j];
             rank += (xj < xi) || (xj == xi && j < a);
         }
-        sx[rank] = xi;
-        sf[rank] = m_exp(f[a] - fmx);
+        inv[rank] = (short)a;
     }
     grp_sync(grp);
     double sum = 0.0;
-    for (int a = grp.lane; a + 1 < n; a += grp.n) sum += (sf[a] + sf[a + 1]) * (sx[a + 1] - sx[a]);
+    for (int p = grp.lane; p + 1 < n; p += grp.n) {
+        const int i0 = inv[p], i1 = inv[p + 1];
+        sum += (ue[i0] + ue[i1]) * (ux[i1] - ux[i0]);
+    }
     sum = grp_sum_d(sum, grp);
     grp_sync(grp);
     return fmx + m_log(sum * 0.5);
@@ -532,8 +538,10 @@ VLR_DEV_NOINLINE void wave_lc_advance(const WavePlan& wp, const WaveBufs& wb, in
     uint32_t status = lc.status, n_base = lc.n_base;
     double ofs[8];
     int no = 0;
+    WaveTask tnext = tasks[0];
     for (int i = 0; i < cnt; ++i) {
-        const WaveTask t = tasks[i];
+        const WaveTask t = tnext;
+        if (i + 1 < cnt) tnext = tasks[i + 1]; // in flight while task i's grid is integrated
         const int e = t.event;
         const double* gx = rows_x + (size_t)i * row_stride;
         const double* gf = rows_f + (size_t)i * row_stride;
