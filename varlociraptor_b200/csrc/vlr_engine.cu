@@ -386,10 +386,18 @@ vlr_status_t ensure_workspace(vlr_ctx* ctx, Slot& sl, int64_t max_reads, bool wa
 vlr_status_t launch_wave(vlr_ctx* ctx, Slot& sl, const DevBatch& b, const DevResults& r, int64_t avg_reads, cudaStream_t stream) {
     using namespace vlr_small;
     const bool want_be = r.afd_capacity > 0;
-    const int n_sub_cap = want_be ? 8192 : 65536;
-    const int lc_cap = n_sub_cap * 3;
+    // sub-chunk: <= 65536 loci (8192 with an AFD: the base-event log is 128 KB per locus) and <= ~16M reads, so that
+    // deep batches keep the workspace bounded; arena and lc table sized for 6 artifact configs per locus on average
+    // (config 2 has 2.2, the depth-skewed config 5 ~4); what does not fit is deferred to the generic engine, never lost
     if (avg_reads < 16) avg_reads = 16;
-    const int64_t coef_cap = (int64_t)n_sub_cap * avg_reads * 3 + (1 << 20);
+    int n_sub_cap = want_be ? 8192 : 65536;
+    n_sub_cap = (int)std::min<int64_t>(n_sub_cap, std::max<int64_t>(4096, ((int64_t)1 << 24) / avg_reads));
+    if (const char* e = getenv("VLR_WAVE_SUB")) { // tuning knob: loci per sub-chunk
+        const int v = atoi(e);
+        if (v >= 256 && v <= (1 << 20)) n_sub_cap = want_be ? std::min(v, 8192) : v;
+    }
+    const int lc_cap = n_sub_cap * 6;
+    const int64_t coef_cap = (int64_t)n_sub_cap * avg_reads * 6 + (1 << 20);
     const int g_stride = ctx->wave_grid_round * WAVE_ROUND_THREADS;
     CK(sl.w_cnt.ensure(sizeof(WaveCounters)));
     CK(sl.w_loci.ensure(sizeof(WaveLocus) * (size_t)n_sub_cap));
