@@ -137,16 +137,21 @@ __global__ void __launch_bounds__(THREADS, VLR_PREP_MIN_CTAS) vlr_wave_coef_kern
     }
 }
 
-// One CTA per group of lcs of the round's list: the leaf sample's coefficients are staged in shared memory (one slot per
-// lc, cp.async), H = 1..8 neighbouring lanes run one task (tasks of an lc sit in neighbouring lanes: their coefficient
-// loads are shared-memory broadcasts), then the warps close the lcs of the group: trapezoids over the task grids, MAP
+// One CTA per group of lcs of the round's list. A group is processed in passes: pass 0 takes all lcs whose pileups fit
+// a coefficient slot (<= W_SLOT_READS reads) together; every deeper lc then gets a pass of its own with the whole slot
+// region as one big slot and up to 32 lanes per task, so a 2000-read pileup next to 10-read ones (config 5) neither
+// idles the other lanes nor falls back to global-memory coefficient loads. A pass: cp.async the parent sample's
+// coefficients into shared memory, every task evaluates its parent pileup; cp.async the leaf sample's coefficients,
+// H = 1..32 neighbouring lanes run one task (tasks of an lc sit in neighbouring lanes: their coefficient loads are
+// shared-memory broadcasts); then 8-lane groups close the lcs of the pass: trapezoids over the task grids, MAP
 // bookkeeping, the next round's tasks.
 #ifndef VLR_ROUND_MIN_CTAS
 #define VLR_ROUND_MIN_CTAS 4
 #endif
+constexpr int WAVE_BIG_READS = vlr_small::W_GROUP * vlr_small::W_SLOT_STRIDE / 4; // reads the whole slot region holds
 __global__ void __launch_bounds__(WAVE_ROUND_THREADS, VLR_ROUND_MIN_CTAS) vlr_wave_round_kernel(const __grid_constant__ WaveParams p, int round) {
     using namespace vlr_small;
-    __shared__ int s_lc[W_GROUP], s_off[W_GROUP + 1];
+    __shared__ int s_lc[W_GROUP], s_cnt[W_GROUP], s_deep[W_GROUP], s_h[W_GROUP], s_off[W_GROUP + 1], s_ndeep;
     const WaveBufs& wb = p.wb;
     const int n_list = (int)wb.cnt->list_n[round];
     const int* list = wb.list[round & 1];
@@ -160,97 +165,155 @@ __global__ void __launch_bounds__(WAVE_ROUND_THREADS, VLR_ROUND_MIN_CTAS) vlr_wa
         long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0;
         __syncthreads();
         if (p.debug) tk0 = clock64();
-        if (tid < 32) { // warp 0: the group's lcs and the exclusive scan of their task counts
+        if (tid < 32) { // warp 0: the group's lcs, their task counts, which of them are deep
             const int lci = (tid < G && g0 + tid < n_list) ? list[g0 + tid] : -1;
-            const int cnt = lci >= 0 ? wb.lcs[lci].task_count : 0;
-            int incl = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += v;
+            int cnt = 0;
+            bool deep = false;
+            if (lci >= 0) {
+                const WaveLC& L = wb.lcs[lci];
+                cnt = L.task_count;
+                deep = L.nT > W_SLOT_READS || L.nP > W_SLOT_READS;
             }
+            const unsigned dm = __ballot_sync(0xffffffffu, deep);
             if (tid < W_GROUP) {
                 s_lc[tid] = lci;
-                s_off[tid] = incl - cnt;
-                if (tid == W_GROUP - 1) s_off[W_GROUP] = incl;
+                s_cnt[tid] = cnt;
+                if (deep) s_deep[__popc(dm & ((1u << tid) - 1u))] = tid;
             }
+            if (tid == 0) s_ndeep = __popc(dm);
         }
         __syncthreads();
-        // thread -> task: H = 1..8 neighbouring lanes per task (as many as fit the CTA)
-        const int total = s_off[W_GROUP];
-        int H = 1;
-        while (H < 8 && total * H * 2 <= WAVE_ROUND_THREADS) H <<= 1;
-        const int q = tid / H;
-        const bool active = q < total;
-        int g_mine = 0;
-        if (active)
-            while (s_off[g_mine + 1] <= q) ++g_mine;
-        WSplit sp;
-        sp.H = H;
-        sp.h = tid & (H - 1);
-        sp.mask = ((1u << H) - 1u) << (lane & ~(H - 1));
-        // ---- the parent sample's coefficients -> slots; every task evaluates its parent pileup once
-        auto stage = [&](bool parent) {
-            for (int g = warp; g < G; g += WAVE_ROUND_THREADS / 32) {
-                const int lci = s_lc[g];
-                if (lci < 0) continue;
-                const WaveLC& L = wb.lcs[lci];
-                const int nr = parent ? L.nP : L.nT;
-                if (nr > W_SLOT_READS) continue; // deep pileup: read from the arena (L2)
-                const double2* src = reinterpret_cast<const double2*>(wb.coef + (parent ? L.coefP : L.coefT) * 4);
-                double2* dst = reinterpret_cast<double2*>(slots + (size_t)g * W_SLOT_STRIDE);
-                for (int i = lane; i < nr * 2; i += 32) __pipeline_memcpy_async(dst + i, src + i, sizeof(double2));
-            }
-            __pipeline_commit();
-            __pipeline_wait_prior(0);
+        const int n_deep = s_ndeep;
+        for (int pass = 0; pass <= n_deep; ++pass) {
+            const int g_deep = pass > 0 ? s_deep[pass - 1] : -1;
+            // members of the pass and the exclusive scan of their task counts (warp 0)
             __syncthreads();
-        };
-        stage(true);
-        double lh_const = 0.0;
-        if (active) {
-            const WaveLC& L = wb.lcs[s_lc[g_mine]];
-            const bool in_sm = L.nP <= W_SLOT_READS;
-            const double2* coP = in_sm ? reinterpret_cast<const double2*>(slots + (size_t)g_mine * W_SLOT_STRIDE)
-                                       : reinterpret_cast<const double2*>(wb.coef + L.coefP * 4);
-            lh_const = wave_task_parent(L, tasks[L.task_base + (q - s_off[g_mine])], coP, in_sm, sp);
-        }
-        __syncthreads();
-        // ---- the leaf sample's coefficients -> slots; the adaptive integrations
-        stage(false);
-        if (p.debug) tk1 = clock64();
-        if (active) {
-            const WaveLC& L = wb.lcs[s_lc[g_mine]];
-            WaveTask& t = tasks[L.task_base + (q - s_off[g_mine])];
-            const bool in_sm = L.nT <= W_SLOT_READS;
-            const double2* coT = in_sm ? reinterpret_cast<const double2*>(slots + (size_t)g_mine * W_SLOT_STRIDE)
-                                       : reinterpret_cast<const double2*>(wb.coef + L.coefT * 4);
-            const size_t row = (size_t)(blockIdx.x * blockDim.x) + (size_t)q;
-            wave_task_run(&p.sc, p.wp, L, t, coT, in_sm, lh_const, wb.gx + row * W_GCAP, wb.gf + row * W_GCAP, sp);
-        }
-        __syncthreads();
-        if (p.debug) tk2 = clock64();
-        // the coefficient slots are dead now: every 8-lane group takes 3 x W_GCAP doubles of them as sort scratch and
-        // closes one lc of the group (32 lcs at a time per CTA: their global-memory latencies overlap)
-        {
-            const int gi = tid >> 3;
-            WGroup grp;
-            grp.lane = tid & 7;
-            grp.n = 8;
-            grp.mask = 0xffu << (lane & ~7);
-            double* scratch = slots + (size_t)gi * 3 * W_GCAP;
-            const int lci = gi < G ? s_lc[gi] : -1;
-            if (lci >= 0) {
-                const size_t row0 = (size_t)(blockIdx.x * blockDim.x) + (size_t)s_off[gi];
-                wave_lc_advance(p.wp, wb, lci, round, wb.gx + row0 * W_GCAP, wb.gf + row0 * W_GCAP, W_GCAP, scratch,
-                                p.want_be != 0, grp);
+            if (tid < 32) {
+                bool member = false;
+                if (tid < W_GROUP && s_lc[tid] >= 0) {
+                    if (pass == 0) {
+                        bool deep = false;
+                        for (int k = 0; k < n_deep; ++k) deep = deep || s_deep[k] == tid;
+                        member = !deep;
+                    } else {
+                        member = tid == g_deep;
+                    }
+                }
+                // lanes per task: a function of the lc alone (its task count; in a deep pass the lc has the CTA to
+                // itself), never of the group it happens to share a CTA with, so results are bitwise reproducible
+                // whatever order the atomics built the round's list in. Thread ranges are padded to even sizes so that
+                // the lane pairs of a task stay aligned for the xor butterflies.
+                int hh = 1;
+                if (member) {
+                    if (pass == 0) hh = s_cnt[tid] <= 1 ? 8 : (s_cnt[tid] <= 2 ? 4 : (s_cnt[tid] <= 4 ? 2 : 1)); // <= 8 threads per lc
+                    else
+                        while (hh < 32 && s_cnt[tid] * hh * 2 <= WAVE_ROUND_THREADS) hh <<= 1;
+                }
+                const int cnt = member ? ((s_cnt[tid] * hh + 1) & ~1) : 0;
+                int incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                if (tid < W_GROUP) {
+                    s_off[tid] = incl - cnt;
+                    s_h[tid] = hh;
+                    if (tid == W_GROUP - 1) s_off[W_GROUP] = incl;
+                }
             }
-        }
-        if (p.debug) {
             __syncthreads();
-            tk3 = clock64();
-            if (blockIdx.x == 0 && tid == 0 && g0 == 0)
-                printf("round %d: n_list %d, G %d, H %d, group tasks %d: stage+parent %lld, tasks %lld, advance %lld cycles\n",
-                       round, n_list, G, H, total, tk1 - tk0, tk2 - tk1, tk3 - tk2);
+            const int total = s_off[W_GROUP]; // threads of the pass
+            if (total == 0) continue; // (uniform: every thread reads the same shared value)
+            const int slot_reads = pass == 0 ? W_SLOT_READS : WAVE_BIG_READS;
+            int g_mine = 0, q = 0; // my lc of the group and my task of that lc
+            bool active = tid < total;
+            WSplit sp;
+            sp.H = 1;
+            sp.h = 0;
+            sp.mask = 1u << lane;
+            if (active) {
+                while (s_off[g_mine + 1] <= tid) ++g_mine; // (non-members have empty ranges and are skipped)
+                const int H = s_h[g_mine], local = tid - s_off[g_mine];
+                q = local / H;
+                active = q < s_cnt[g_mine]; // (padding lanes idle)
+                sp.H = H;
+                sp.h = local & (H - 1);
+                sp.mask = H == 32 ? 0xffffffffu : (((1u << H) - 1u) << (lane & ~(H - 1)));
+            }
+            auto slot_of = [&](int g) { return slots + (pass == 0 ? (size_t)g * W_SLOT_STRIDE : (size_t)0); };
+            auto stage = [&](bool parent) {
+                for (int g = warp; g < G; g += WAVE_ROUND_THREADS / 32) {
+                    if (s_off[g + 1] == s_off[g]) continue; // not a member of this pass (or no tasks)
+                    const WaveLC& L = wb.lcs[s_lc[g]];
+                    const int nr = parent ? L.nP : L.nT;
+                    if (nr > slot_reads) continue; // does not even fit the whole region: read from the arena (L2)
+                    const double2* src = reinterpret_cast<const double2*>(wb.coef + (parent ? L.coefP : L.coefT) * 4);
+                    double2* dst = reinterpret_cast<double2*>(slot_of(g));
+                    if (pass == 0) {
+                        for (int i = lane; i < nr * 2; i += 32) __pipeline_memcpy_async(dst + i, src + i, sizeof(double2));
+                    }
+                }
+                if (pass > 0) { // one lc, all warps copy
+                    const WaveLC& L = wb.lcs[s_lc[g_deep]];
+                    const int nr = parent ? L.nP : L.nT;
+                    if (nr <= slot_reads) {
+                        const double2* src = reinterpret_cast<const double2*>(wb.coef + (parent ? L.coefP : L.coefT) * 4);
+                        double2* dst = reinterpret_cast<double2*>(slots);
+                        for (int i = tid; i < nr * 2; i += WAVE_ROUND_THREADS) __pipeline_memcpy_async(dst + i, src + i, sizeof(double2));
+                    }
+                }
+                __pipeline_commit();
+                __pipeline_wait_prior(0);
+                __syncthreads();
+            };
+            // ---- the parent sample's coefficients -> slots; every task evaluates its parent pileup once
+            stage(true);
+            double lh_const = 0.0;
+            if (active) {
+                const WaveLC& L = wb.lcs[s_lc[g_mine]];
+                const bool in_sm = L.nP <= slot_reads;
+                const double2* coP = in_sm ? reinterpret_cast<const double2*>(slot_of(g_mine))
+                                           : reinterpret_cast<const double2*>(wb.coef + L.coefP * 4);
+                lh_const = wave_task_parent(L, tasks[L.task_base + q], coP, in_sm, sp);
+            }
+            __syncthreads();
+            // ---- the leaf sample's coefficients -> slots; the adaptive integrations
+            stage(false);
+            if (p.debug) tk1 = clock64();
+            if (active) {
+                const WaveLC& L = wb.lcs[s_lc[g_mine]];
+                WaveTask& t = tasks[L.task_base + q];
+                const bool in_sm = L.nT <= slot_reads;
+                const double2* coT = in_sm ? reinterpret_cast<const double2*>(slot_of(g_mine))
+                                           : reinterpret_cast<const double2*>(wb.coef + L.coefT * 4);
+                const size_t row = (size_t)(blockIdx.x * blockDim.x) + (size_t)(s_off[g_mine] + q);
+                wave_task_run(&p.sc, p.wp, L, t, coT, in_sm, lh_const, wb.gx + row * W_GCAP, wb.gf + row * W_GCAP, sp);
+            }
+            __syncthreads();
+            if (p.debug) tk2 = clock64();
+            // the coefficient slots are dead now: every 8-lane group takes 3 x W_GCAP doubles of them as sort scratch
+            // and closes one lc of the pass (their global-memory latencies overlap)
+            {
+                const int gi = tid >> 3;
+                WGroup grp;
+                grp.lane = tid & 7;
+                grp.n = 8;
+                grp.mask = 0xffu << (lane & ~7);
+                double* scratch = slots + (size_t)gi * 3 * W_GCAP;
+                if (gi < G && s_off[gi + 1] > s_off[gi]) {
+                    const size_t row0 = (size_t)(blockIdx.x * blockDim.x) + (size_t)s_off[gi];
+                    wave_lc_advance(p.wp, wb, s_lc[gi], round, wb.gx + row0 * W_GCAP, wb.gf + row0 * W_GCAP, W_GCAP, scratch,
+                                    p.want_be != 0, grp);
+                }
+            }
+            if (p.debug) {
+                __syncthreads();
+                tk3 = clock64();
+                if (blockIdx.x == 0 && tid == 0 && g0 == 0)
+                    printf("round %d pass %d: n_list %d, G %d, threads %d: stage+parent %lld, tasks %lld, advance %lld cycles\n",
+                           round, pass, n_list, G, total, tk1 - tk0, tk2 - tk1, tk3 - tk2);
+            }
         }
     }
 }
