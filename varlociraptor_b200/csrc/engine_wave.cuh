@@ -941,49 +941,51 @@ VLR_DEV void wave_finish_locus(const DevScenario* sc, const DevBatch* b, const D
     const WaveLocus& wl = wb.loci[li];
     if (wl.n_cfg == 0) return; // deferred: the generic engine writes this locus
     const int E = sc->E, P = wp.P, T = wp.T;
-    c.sc = sc;
-    c.b = b;
-    c.res = res;
-    c.ws = ws;
-    c.locus = locus;
-    c.status = wl.status;
-    c.be = nullptr;
-    c.n_rec = 0;
-    if (res->afd_capacity > 0) {
-        c.be = wb.be + (size_t)li * BE_CAP * 4;
-        const unsigned n = wb.be_n[li];
-        c.n_rec = n < (unsigned)BE_CAP ? n : (unsigned)BE_CAP;
-    }
-    for (int i = 0; i < 2 * E; ++i) c.map_set[i] = 0;
-    for (int e = 0; e < E; ++e) {
-        c.ev_plain[e].init();
-        c.ev_twin[e].init();
-    }
-    const double twin_prior = wl.n_twins > 0 ? LN_05 + m_log(1.0 / (double)wl.n_twins) : neg_inf();
-    uint32_t n_base = 0;
-    for (int ci = 0; ci < wl.n_cfg; ++ci) {
-        const WaveLC& lc = wb.lcs[wl.lc_base + ci];
-        c.status |= lc.status;
-        if (lc.outer_pending || lc.task_count != 0) c.status |= VLR_ST_GRID_OVERFLOW; // round budget exceeded
-        n_base += lc.n_base;
+    if (lane_id() == 0) { // one lane fills the warp's context (shared memory), the warp reads it after the sync
+        c.sc = sc;
+        c.b = b;
+        c.res = res;
+        c.ws = ws;
+        c.locus = locus;
+        c.status = wl.status;
+        c.be = nullptr;
+        c.n_rec = 0;
+        if (res->afd_capacity > 0) {
+            c.be = wb.be + (size_t)li * BE_CAP * 4;
+            const unsigned n = wb.be_n[li];
+            c.n_rec = n < (unsigned)BE_CAP ? n : (unsigned)BE_CAP;
+        }
+        for (int i = 0; i < 2 * E; ++i) c.map_set[i] = 0;
         for (int e = 0; e < E; ++e) {
-            if (ci > 0 && !sc->events[e].has_artifact_twin) continue;
-            const double d = lc.dens[e];
-            if (d != d) c.status |= VLR_ST_NAN;
-            if (ci == 0) c.ev_plain[e].add(LN_05 + d);
-            else c.ev_twin[e].add(twin_prior + d);
-            const int slot = 2 * e + (ci > 0 ? 1 : 0);
-            if (lc.map_set[e] && (!c.map_set[slot] || lc.map_joint[e] > c.map_joint[slot])) {
-                c.map_set[slot] = 1;
-                c.map_joint[slot] = lc.map_joint[e];
-                c.map_cfg[slot] = lc.art_id;
-                c.map_disc[slot] = ((uint32_t)(lc.map_disc[e] & 1u) << P) | ((uint32_t)((lc.map_disc[e] >> 1) & 1u) << T);
-                c.map_vaf[slot][P] = lc.map_vp[e];
-                c.map_vaf[slot][T] = lc.map_vt[e];
+            c.ev_plain[e].init();
+            c.ev_twin[e].init();
+        }
+        const double twin_prior = wl.n_twins > 0 ? LN_05 + m_log(1.0 / (double)wl.n_twins) : neg_inf();
+        uint32_t n_base = 0;
+        for (int ci = 0; ci < wl.n_cfg; ++ci) {
+            const WaveLC& lc = wb.lcs[wl.lc_base + ci];
+            c.status |= lc.status;
+            if (lc.outer_pending || lc.task_count != 0) c.status |= VLR_ST_GRID_OVERFLOW; // round budget exceeded
+            n_base += lc.n_base;
+            for (int e = 0; e < E; ++e) {
+                if (ci > 0 && !sc->events[e].has_artifact_twin) continue;
+                const double d = lc.dens[e];
+                if (d != d) c.status |= VLR_ST_NAN;
+                if (ci == 0) c.ev_plain[e].add(LN_05 + d);
+                else c.ev_twin[e].add(twin_prior + d);
+                const int slot = 2 * e + (ci > 0 ? 1 : 0);
+                if (lc.map_set[e] && (!c.map_set[slot] || lc.map_joint[e] > c.map_joint[slot])) {
+                    c.map_set[slot] = 1;
+                    c.map_joint[slot] = lc.map_joint[e];
+                    c.map_cfg[slot] = lc.art_id;
+                    c.map_disc[slot] = ((uint32_t)(lc.map_disc[e] & 1u) << P) | ((uint32_t)((lc.map_disc[e] >> 1) & 1u) << T);
+                    c.map_vaf[slot][P] = lc.map_vp[e];
+                    c.map_vaf[slot][T] = lc.map_vt[e];
+                }
             }
         }
+        c.n_base = n_base;
     }
-    c.n_base = n_base;
     warp_sync();
     locus_tail(c, wl.n_twins);
 }
