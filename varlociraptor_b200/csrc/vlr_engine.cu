@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(WAVE_ROUND_THREADS, VLR_ROUND_MIN_CTAS) vlr_wa
         long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0;
         __syncthreads();
         if (p.debug) tk0 = clock64();
-        if (tid < 32) { // warp 0: the group's lcs, their task counts, which of them are deep
+        if (tid < 32) { // warp 0: the group's lcs, their task counts, which of them are deep; thread ranges of pass 0
             const int lci = (tid < G && g0 + tid < n_list) ? list[g0 + tid] : -1;
             int cnt = 0;
             bool deep = false;
@@ -175,9 +175,24 @@ __global__ void __launch_bounds__(WAVE_ROUND_THREADS, VLR_ROUND_MIN_CTAS) vlr_wa
                 deep = L.nT > W_SLOT_READS || L.nP > W_SLOT_READS;
             }
             const unsigned dm = __ballot_sync(0xffffffffu, deep);
+            // lanes per task: a function of the lc alone (its task count; in a deep pass the lc has the CTA to itself),
+            // never of the group it happens to share a CTA with, so results are bitwise reproducible whatever order the
+            // atomics built the round's list in. Thread ranges are padded to even sizes so that the lane pairs of a task
+            // stay aligned for the xor butterflies.
+            const int hh = cnt <= 1 ? 8 : (cnt <= 2 ? 4 : (cnt <= 4 ? 2 : 1)); // <= 8 threads per lc
+            const int thr = (lci >= 0 && !deep) ? ((cnt * hh + 1) & ~1) : 0;
+            int incl = thr;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
             if (tid < W_GROUP) {
                 s_lc[tid] = lci;
                 s_cnt[tid] = cnt;
+                s_off[tid] = incl - thr;
+                s_h[tid] = hh;
+                if (tid == W_GROUP - 1) s_off[W_GROUP] = incl;
                 if (deep) s_deep[__popc(dm & ((1u << tid) - 1u))] = tid;
             }
             if (tid == 0) s_ndeep = __popc(dm);
@@ -186,43 +201,28 @@ __global__ void __launch_bounds__(WAVE_ROUND_THREADS, VLR_ROUND_MIN_CTAS) vlr_wa
         const int n_deep = s_ndeep;
         for (int pass = 0; pass <= n_deep; ++pass) {
             const int g_deep = pass > 0 ? s_deep[pass - 1] : -1;
-            // members of the pass and the exclusive scan of their task counts (warp 0)
-            __syncthreads();
-            if (tid < 32) {
-                bool member = false;
-                if (tid < W_GROUP && s_lc[tid] >= 0) {
-                    if (pass == 0) {
-                        bool deep = false;
-                        for (int k = 0; k < n_deep; ++k) deep = deep || s_deep[k] == tid;
-                        member = !deep;
-                    } else {
-                        member = tid == g_deep;
+            if (pass > 0) { // a deep lc alone: as many lanes per task as fit the CTA
+                __syncthreads();
+                if (tid < 32) {
+                    const bool member = tid == g_deep;
+                    int hh = 1;
+                    if (member)
+                        while (hh < 32 && s_cnt[tid] * hh * 2 <= WAVE_ROUND_THREADS) hh <<= 1;
+                    const int thr = member ? ((s_cnt[tid] * hh + 1) & ~1) : 0;
+                    int incl = thr;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += v;
+                    }
+                    if (tid < W_GROUP) {
+                        s_off[tid] = incl - thr;
+                        s_h[tid] = hh;
+                        if (tid == W_GROUP - 1) s_off[W_GROUP] = incl;
                     }
                 }
-                // lanes per task: a function of the lc alone (its task count; in a deep pass the lc has the CTA to
-                // itself), never of the group it happens to share a CTA with, so results are bitwise reproducible
-                // whatever order the atomics built the round's list in. Thread ranges are padded to even sizes so that
-                // the lane pairs of a task stay aligned for the xor butterflies.
-                int hh = 1;
-                if (member) {
-                    if (pass == 0) hh = s_cnt[tid] <= 1 ? 8 : (s_cnt[tid] <= 2 ? 4 : (s_cnt[tid] <= 4 ? 2 : 1)); // <= 8 threads per lc
-                    else
-                        while (hh < 32 && s_cnt[tid] * hh * 2 <= WAVE_ROUND_THREADS) hh <<= 1;
-                }
-                const int cnt = member ? ((s_cnt[tid] * hh + 1) & ~1) : 0;
-                int incl = cnt;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += v;
-                }
-                if (tid < W_GROUP) {
-                    s_off[tid] = incl - cnt;
-                    s_h[tid] = hh;
-                    if (tid == W_GROUP - 1) s_off[W_GROUP] = incl;
-                }
+                __syncthreads();
             }
-            __syncthreads();
             const int total = s_off[W_GROUP]; // threads of the pass
             if (total == 0) continue; // (uniform: every thread reads the same shared value)
             const int slot_reads = pass == 0 ? W_SLOT_READS : WAVE_BIG_READS;
