@@ -112,7 +112,7 @@ extern "C" int32_t vlr_emu_wave_call_batch(const vlr_scenario_t* sc, const vlr_b
     const int64_t coef_cap = batch->n_reads * 4 + 64;
     std::vector<double> coef((size_t)coef_cap * 4);
     std::vector<WaveTask> tasks0((size_t)lc_cap * W_MAXT), tasks1((size_t)lc_cap * W_MAXT);
-    std::vector<int> list0((size_t)lc_cap), list1((size_t)lc_cap), deferred((size_t)L + 1);
+    std::vector<int> list0((size_t)lc_cap), list1((size_t)lc_cap), dlist0((size_t)lc_cap), dlist1((size_t)lc_cap), deferred((size_t)L + 1);
     std::vector<double> gx((size_t)W_GCAP * W_MAXT), gf((size_t)W_GCAP * W_MAXT), scratch(3 * W_GCAP);
     std::vector<double> be(want_be ? (size_t)L * BE_CAP * 4 : 4);
     std::vector<unsigned> be_n((size_t)L + 1);
@@ -127,6 +127,8 @@ extern "C" int32_t vlr_emu_wave_call_batch(const vlr_scenario_t* sc, const vlr_b
     wb.tasks[1] = tasks1.data();
     wb.list[0] = list0.data();
     wb.list[1] = list1.data();
+    wb.dlist[0] = dlist0.data();
+    wb.dlist[1] = dlist1.data();
     wb.deferred = deferred.data();
     wb.gx = gx.data();
     wb.gf = gf.data();
@@ -141,18 +143,20 @@ extern "C" int32_t vlr_emu_wave_call_batch(const vlr_scenario_t* sc, const vlr_b
     for (int k = 0; k < n_lc; ++k) wave_lc_init(&ds, wp, wb, k);
     for (int k = 0; k < n_lc; ++k) wave_lc_coef(&ds, &db, wp, wb, k, 0, want_be, *c);
     for (int round = 0; round < wp.max_rounds; ++round) {
-        const int n_list = (int)cnt.list_n[round];
-        const int* list = wb.list[round & 1];
-        for (int k = 0; k < n_list; ++k) {
-            WaveLC& lc = lcs[list[k]];
-            for (int t = 0; t < lc.task_count; ++t) {
-                WaveTask& task = wb.tasks[round & 1][lc.task_base + t];
-                const WSplit one{0, 1, 1u};
-                const double lh = wave_task_parent(lc, task, reinterpret_cast<const double2*>(wb.coef + lc.coefP * 4), false, one);
-                wave_task_run(&ds, wp, lc, task, reinterpret_cast<const double2*>(wb.coef + lc.coefT * 4), false, lh,
-                              wb.gx + (size_t)t * W_GCAP, wb.gf + (size_t)t * W_GCAP, one);
+        for (int which = 0; which < 2; ++which) { // shallow list, then deep list
+            const int n_list = (int)(which == 0 ? cnt.list_n[round] : cnt.dlist_n[round]);
+            const int* list = which == 0 ? wb.list[round & 1] : wb.dlist[round & 1];
+            for (int k = 0; k < n_list; ++k) {
+                WaveLC& lc = lcs[list[k]];
+                for (int t = 0; t < lc.task_count; ++t) {
+                    WaveTask& task = wb.tasks[round & 1][lc.task_base + t];
+                    const WSplit one{0, 1, 1u};
+                    const double lh = wave_task_parent(lc, task, reinterpret_cast<const double2*>(wb.coef + lc.coefP * 4), false, one);
+                    wave_task_run(&ds, wp, lc, task, reinterpret_cast<const double2*>(wb.coef + lc.coefT * 4), false, lh,
+                                  wb.gx + (size_t)t * W_GCAP, wb.gf + (size_t)t * W_GCAP, one);
+                }
+                wave_lc_advance(wp, wb, list[k], round, wb.gx, wb.gf, W_GCAP, scratch.data(), want_be, WGroup{0, 1, 1u});
             }
-            wave_lc_advance(wp, wb, list[k], round, wb.gx, wb.gf, W_GCAP, scratch.data(), want_be, WGroup{0, 1, 1u});
         }
     }
     for (int64_t i = 0; i < L; ++i) wave_finish_locus(&ds, &db, &dr, wp, wb, ws, i, (int)i, *c);

@@ -55,7 +55,8 @@ struct WaveCounters {
     unsigned long long ticket[4]; // pre, finish, deferred (generic kernel), coefficients
     unsigned long long coef_used; // reads allocated in the coefficient arena
     unsigned int n_lc, n_deferred;
-    unsigned int list_n[W_MAXROUNDS + 2];
+    unsigned int list_n[W_MAXROUNDS + 2];  // lcs of the round whose pileups fit a coefficient slot
+    unsigned int dlist_n[W_MAXROUNDS + 2]; // lcs of the round with a deeper pileup
     unsigned int task_n[W_MAXROUNDS + 2];
 };
 
@@ -112,6 +113,7 @@ struct WaveBufs {
     double* coef; // arena, 4 doubles per read
     WaveTask* tasks[2];
     int* list[2];
+    int* dlist[2];
     int* deferred; // absolute locus indices
     double* gx;    // per-thread leaf grid rows: [threads][W_GCAP]
     double* gf;
@@ -507,6 +509,18 @@ VLR_DEV_NOINLINE double wave_fin_coop(const double* x, const double* f, int n, d
     return fmx + m_log(sum * 0.5);
 }
 
+// The round's lcs come in two lists: pileups that fit a shared-memory coefficient slot go to the warp-per-4-lcs round
+// kernel, deeper ones to the CTA-per-group kernel (passes, big slot, up to 32 lanes per task).
+VLR_DEV void wave_list_append(const WaveBufs& wb, int round, int lci, int nP, int nT) {
+    if (nP > W_SLOT_READS || nT > W_SLOT_READS) {
+        const unsigned at = wa_add_u32(&wb.cnt->dlist_n[round], 1u);
+        wb.dlist[round & 1][at] = lci;
+    } else {
+        const unsigned at = wa_add_u32(&wb.cnt->list_n[round], 1u);
+        wb.list[round & 1][at] = lci;
+    }
+}
+
 VLR_DEV void wave_emit_task(WaveTask& t, int lc, int event, double px, bool disc, double a, double b) {
     t.lc = lc;
     t.event = (short)event;
@@ -623,8 +637,7 @@ VLR_DEV_NOINLINE void wave_lc_advance(const WavePlan& wp, const WaveBufs& wb, in
             }
             lc.task_base = (int)tb;
             lc.task_count = k;
-            const unsigned li = wa_add_u32(&wb.cnt->list_n[round + 1], 1u);
-            wb.list[(round + 1) & 1][li] = lci;
+            wave_list_append(wb, round + 1, lci, lc.nP, lc.nT);
             lc.outer_n = outer_n;
             lc.outer_overflow = outer_overflow;
             lc.status = status;
@@ -851,8 +864,7 @@ VLR_DEV void wave_lc_init(const DevScenario* sc, const WavePlan& wp, const WaveB
     }
     lc.task_base = (int)tb;
     lc.task_count = k;
-    const unsigned at = wa_add_u32(&wb.cnt->list_n[0], 1u);
-    wb.list[0][at] = lci;
+    wave_list_append(wb, 0, lci, lc.nP, lc.nT);
 }
 
 // One warp per lc: the per-read coefficients of both samples under the lc's artifact config, and the point events

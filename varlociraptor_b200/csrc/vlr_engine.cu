@@ -153,8 +153,8 @@ __global__ void __launch_bounds__(WAVE_ROUND_THREADS, VLR_ROUND_MIN_CTAS) vlr_wa
     using namespace vlr_small;
     __shared__ int s_lc[W_GROUP], s_cnt[W_GROUP], s_deep[W_GROUP], s_h[W_GROUP], s_off[W_GROUP + 1], s_ndeep;
     const WaveBufs& wb = p.wb;
-    const int n_list = (int)wb.cnt->list_n[round];
-    const int* list = wb.list[round & 1];
+    const int n_list = (int)wb.cnt->dlist_n[round]; // the round's lcs with a pileup deeper than a slot
+    const int* list = wb.dlist[round & 1];
     WaveTask* tasks = wb.tasks[round & 1];
     const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double* slots = reinterpret_cast<double*>(vlr_smem);
@@ -318,6 +318,72 @@ __global__ void __launch_bounds__(WAVE_ROUND_THREADS, VLR_ROUND_MIN_CTAS) vlr_wa
     }
 }
 
+// The round kernel of the common case (every pileup of the lc fits a slot): no CTA-wide phases at all. A warp owns
+// four coefficient slots and takes four lcs of the round's list at a time; the 8 lanes of an octet own one lc through
+// all of its phases — cp.async its parent coefficients into the octet's slot, the lc's tasks (H = 8 / #tasks lanes each)
+// evaluate their parent pileup, cp.async the leaf coefficients, run the adaptive integrations, then close the lc
+// (trapezoids in the slot, MAP, next round's tasks) as the same 8-lane group. Only __syncwarp between the phases: the
+// 16 warps of an SM drift apart and overlap each other's copy, compute and bookkeeping phases (the CTA-phase kernel
+// lost ~1/3 of its issue slots to barrier waits).
+__global__ void __launch_bounds__(WAVE_ROUND_THREADS, VLR_ROUND_MIN_CTAS) vlr_wave_round_warp_kernel(const __grid_constant__ WaveParams p, int round) {
+    using namespace vlr_small;
+    const WaveBufs& wb = p.wb;
+    const int n_list = (int)wb.cnt->list_n[round];
+    const int* list = wb.list[round & 1];
+    WaveTask* tasks = wb.tasks[round & 1];
+    const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int oct = lane >> 3, l8 = lane & 7;
+    constexpr int WARPS = WAVE_ROUND_THREADS / 32;
+    static_assert(W_GROUP == 4 * WARPS, "one slot per octet");
+    double* slot = reinterpret_cast<double*>(vlr_smem) + (size_t)(4 * warp + oct) * W_SLOT_STRIDE;
+    const size_t row0 = (size_t)(blockIdx.x * blockDim.x) + (size_t)(warp * 32 + oct * 8); // task rows of my octet
+    WGroup grp;
+    grp.lane = l8;
+    grp.n = 8;
+    grp.mask = 0xffu << (oct * 8);
+    const int warp_g = (int)blockIdx.x * WARPS + warp, n_warps = (int)gridDim.x * WARPS;
+    for (int g0 = warp_g * 4; g0 < n_list; g0 += n_warps * 4) {
+        const int lci = g0 + oct < n_list ? list[g0 + oct] : -1;
+        int cnt = 0, nP = 0, nT = 0, task_base = 0;
+        const double2 *srcP = nullptr, *srcT = nullptr;
+        if (lci >= 0) {
+            const WaveLC& L = wb.lcs[lci];
+            cnt = L.task_count;
+            nP = L.nP;
+            nT = L.nT;
+            task_base = L.task_base;
+            srcP = reinterpret_cast<const double2*>(wb.coef + L.coefP * 4);
+            srcT = reinterpret_cast<const double2*>(wb.coef + L.coefT * 4);
+        }
+        // lanes per task: a function of the lc alone (bitwise reproducible results), <= 8 threads per lc
+        const int H = cnt <= 1 ? 8 : (cnt <= 2 ? 4 : (cnt <= 4 ? 2 : 1));
+        const int q = l8 / H;
+        const bool active = lci >= 0 && q < cnt;
+        WSplit sp;
+        sp.H = H;
+        sp.h = l8 & (H - 1);
+        sp.mask = ((1u << H) - 1u) << (lane & ~(H - 1));
+        __syncwarp(); // the previous lcs' scratch use of the slots is over
+        for (int i = l8; i < nP * 2; i += 8) __pipeline_memcpy_async(reinterpret_cast<double2*>(slot) + i, srcP + i, sizeof(double2));
+        __pipeline_commit();
+        __pipeline_wait_prior(0);
+        __syncwarp();
+        double lh_const = 0.0;
+        if (active) lh_const = wave_task_parent(wb.lcs[lci], tasks[task_base + q], reinterpret_cast<const double2*>(slot), true, sp);
+        __syncwarp();
+        for (int i = l8; i < nT * 2; i += 8) __pipeline_memcpy_async(reinterpret_cast<double2*>(slot) + i, srcT + i, sizeof(double2));
+        __pipeline_commit();
+        __pipeline_wait_prior(0);
+        __syncwarp();
+        if (active)
+            wave_task_run(&p.sc, p.wp, wb.lcs[lci], tasks[task_base + q], reinterpret_cast<const double2*>(slot), true, lh_const,
+                          wb.gx + (row0 + q) * W_GCAP, wb.gf + (row0 + q) * W_GCAP, sp);
+        __syncwarp();
+        if (lci >= 0)
+            wave_lc_advance(p.wp, wb, lci, round, wb.gx + row0 * W_GCAP, wb.gf + row0 * W_GCAP, W_GCAP, slot, p.want_be != 0, grp);
+    }
+}
+
 __global__ void __launch_bounds__(THREADS, 2) vlr_wave_finish_kernel(const __grid_constant__ WaveParams p) {
     using namespace vlr_small;
     Ctx& c = *reinterpret_cast<Ctx*>(vlr_smem + (size_t)group_in_cta() * CTX_STRIDE);
@@ -386,7 +452,7 @@ struct Slot { // one in-flight chunk of vlr_call_batch
     int coef_cap = 0;
     bool be_ready = false;
     // wavefront pipeline workspace (one sub-chunk of loci at a time)
-    DevBuf w_cnt, w_loci, w_lcs, w_ogx, w_ogf, w_coef, w_tasks[2], w_list[2], w_deferred, w_gx, w_gf, w_be, w_ben;
+    DevBuf w_cnt, w_loci, w_lcs, w_ogx, w_ogf, w_coef, w_tasks[2], w_list[2], w_dlist[2], w_deferred, w_gx, w_gf, w_be, w_ben;
 };
 
 } // namespace
@@ -471,6 +537,7 @@ vlr_status_t launch_wave(vlr_ctx* ctx, Slot& sl, const DevBatch& b, const DevRes
     for (int i = 0; i < 2; ++i) {
         CK(sl.w_tasks[i].ensure(sizeof(WaveTask) * (size_t)lc_cap * W_MAXT));
         CK(sl.w_list[i].ensure(sizeof(int) * (size_t)lc_cap));
+        CK(sl.w_dlist[i].ensure(sizeof(int) * (size_t)lc_cap));
     }
     CK(sl.w_deferred.ensure(sizeof(int) * (size_t)n_sub_cap));
     CK(sl.w_gx.ensure(sizeof(double) * (size_t)W_GCAP * g_stride));
@@ -492,6 +559,8 @@ vlr_status_t launch_wave(vlr_ctx* ctx, Slot& sl, const DevBatch& b, const DevRes
     p.wb.tasks[1] = (WaveTask*)sl.w_tasks[1].p;
     p.wb.list[0] = (int*)sl.w_list[0].p;
     p.wb.list[1] = (int*)sl.w_list[1].p;
+    p.wb.dlist[0] = (int*)sl.w_dlist[0].p;
+    p.wb.dlist[1] = (int*)sl.w_dlist[1].p;
     p.wb.deferred = (int*)sl.w_deferred.p;
     p.wb.gx = (double*)sl.w_gx.p;
     p.wb.gf = (double*)sl.w_gf.p;
@@ -526,12 +595,14 @@ vlr_status_t launch_wave(vlr_ctx* ctx, Slot& sl, const DevBatch& b, const DevRes
         vlr_wave_pre_kernel<<<ctx->wave_grid_prep, THREADS, ctx->wave_smem_prep, stream>>>(p);
         vlr_wave_lcinit_kernel<<<ctx->n_sms * 4, 256, 0, stream>>>(p);
         vlr_wave_coef_kernel<<<ctx->wave_grid_prep, THREADS, ctx->wave_smem_prep, stream>>>(p);
-        for (int round = 0; round < ctx->wplan.max_rounds; ++round)
+        for (int round = 0; round < ctx->wplan.max_rounds; ++round) {
+            vlr_wave_round_warp_kernel<<<ctx->wave_grid_round, WAVE_ROUND_THREADS, WAVE_ROUND_SMEM, stream>>>(p, round);
             vlr_wave_round_kernel<<<ctx->wave_grid_round, WAVE_ROUND_THREADS, WAVE_ROUND_SMEM, stream>>>(p, round);
+        }
         vlr_wave_finish_kernel<<<ctx->wave_grid_finish, THREADS, ctx->wave_smem_prep, stream>>>(p);
         vlr_call_kernel_vlr_small<<<ctx->grid, THREADS, ctx->smem_bytes, stream>>>(gp);
         CK(cudaGetLastError());
-        ctx->launches += 5 + ctx->wplan.max_rounds;
+        ctx->launches += 5 + 2 * ctx->wplan.max_rounds;
     }
     return VLR_OK;
 }
@@ -733,6 +804,7 @@ vlr_status_t vlr_ctx_create(const vlr_scenario_t* scenario, int32_t device, vlr_
         CKB(cudaFuncSetAttribute(vlr_wave_coef_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->wave_smem_prep));
         CKB(cudaFuncSetAttribute(vlr_wave_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->wave_smem_prep));
         CKB(cudaFuncSetAttribute(vlr_wave_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WAVE_ROUND_SMEM));
+        CKB(cudaFuncSetAttribute(vlr_wave_round_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WAVE_ROUND_SMEM));
         int n1 = 0, n2 = 0;
         CKB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n1, vlr_wave_coef_kernel, THREADS, ctx->wave_smem_prep));
         CKB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n2, vlr_wave_round_kernel, WAVE_ROUND_THREADS, WAVE_ROUND_SMEM));
@@ -763,7 +835,7 @@ void vlr_ctx_destroy(vlr_ctx_t* ctx) {
         DevBuf* all[] = {&s.rflags, &s.hart, &s.hvar, &s.lflags, &s.het, &s.semr, &s.log_post, &s.log_marginal,
                          &s.map_vaf, &s.map_config, &s.best_event, &s.status, &s.n_base, &s.afd_count, &s.afd_vaf,
                          &s.afd_logp, &s.ws, &s.coef, &s.be, &s.ticket, &s.w_cnt, &s.w_loci, &s.w_lcs, &s.w_ogx,
-                         &s.w_ogf, &s.w_coef, &s.w_tasks[0], &s.w_tasks[1], &s.w_list[0], &s.w_list[1], &s.w_deferred,
+                         &s.w_ogf, &s.w_coef, &s.w_tasks[0], &s.w_tasks[1], &s.w_list[0], &s.w_list[1], &s.w_dlist[0], &s.w_dlist[1], &s.w_deferred,
                          &s.w_gx, &s.w_gf, &s.w_be, &s.w_ben};
         for (DevBuf* b : all) b->release();
     };
