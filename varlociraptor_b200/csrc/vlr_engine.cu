@@ -475,6 +475,9 @@ struct vlr_ctx {
     DevBuf d_samples, d_events, d_nodes, d_set_vafs, d_spectra, d_lfc_nodes, d_lfc_ordinal, d_prior_tab;
     cudaStream_t stream = nullptr; // the context's own stream (device-pointer entry)
     Slot dev_slot;                 // workspace of the device-pointer entry
+    Slot dev_slot2;                // second half of a large wavefront batch runs concurrently on its own stream
+    cudaStream_t aux[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     Slot slots[NBUF];
     int64_t reserve_reads = 4096;
     int64_t launches = 0;
@@ -512,7 +515,8 @@ vlr_status_t ensure_workspace(vlr_ctx* ctx, Slot& sl, int64_t max_reads, bool wa
 // Wavefront pipeline over the batch, one sub-chunk of loci after the other on `stream`: prep -> rounds -> finish ->
 // generic engine for the deferred loci. `avg_reads` (reads per locus of the batch, rounded up) sizes the coefficient
 // arena; loci that do not fit are deferred, never dropped.
-vlr_status_t launch_wave(vlr_ctx* ctx, Slot& sl, const DevBatch& b, const DevResults& r, int64_t avg_reads, cudaStream_t stream) {
+vlr_status_t launch_wave(vlr_ctx* ctx, Slot& sl, const DevBatch& b, const DevResults& r, int64_t avg_reads, cudaStream_t stream,
+                         int64_t locus_begin, int64_t locus_end) {
     using namespace vlr_small;
     const bool want_be = r.afd_capacity > 0;
     // sub-chunk: <= 65536 loci (8192 with an AFD: the base-event log is 128 KB per locus) and <= ~16M reads, so that
@@ -588,9 +592,9 @@ vlr_status_t launch_wave(vlr_ctx* ctx, Slot& sl, const DevBatch& b, const DevRes
     gp.sm_reads = SM_READS;
     gp.ctx_stride = ctx->ctx_stride;
     gp.be_stride = (int64_t)BE_CAP * (2 + ctx->S);
-    for (int64_t lo = 0; lo < b.n_loci; lo += n_sub_cap) {
+    for (int64_t lo = locus_begin; lo < locus_end; lo += n_sub_cap) {
         p.sub_lo = lo;
-        p.n_sub = (int)std::min<int64_t>(n_sub_cap, b.n_loci - lo);
+        p.n_sub = (int)std::min<int64_t>(n_sub_cap, locus_end - lo);
         CK(cudaMemsetAsync(sl.w_cnt.p, 0, sizeof(WaveCounters), stream));
         vlr_wave_pre_kernel<<<ctx->wave_grid_prep, THREADS, ctx->wave_smem_prep, stream>>>(p);
         vlr_wave_lcinit_kernel<<<ctx->n_sms * 4, 256, 0, stream>>>(p);
@@ -608,7 +612,7 @@ vlr_status_t launch_wave(vlr_ctx* ctx, Slot& sl, const DevBatch& b, const DevRes
 }
 
 vlr_status_t launch(vlr_ctx* ctx, Slot& sl, const DevBatch& b, const DevResults& r, cudaStream_t stream, int64_t avg_reads = 0) {
-    if (ctx->wave && b.n_loci > 0) return launch_wave(ctx, sl, b, r, avg_reads, stream);
+    if (ctx->wave && b.n_loci > 0) return launch_wave(ctx, sl, b, r, avg_reads, stream, 0, b.n_loci);
     KernelParams p;
     p.sc = ctx->dsc;
     p.b = b;
@@ -816,6 +820,11 @@ vlr_status_t vlr_ctx_create(const vlr_scenario_t* scenario, int32_t device, vlr_
         ctx->wave_grid_finish = std::min(std::max(1, n3) * ctx->n_sms, ctx->grid);
     }
     CKB(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CKB(cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking));
+        CKB(cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming));
+    }
+    CKB(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     for (int i = 0; i < NBUF; ++i) CKB(cudaStreamCreateWithFlags(&ctx->slots[i].stream, cudaStreamNonBlocking));
 #undef CKB
     *out = ctx;
@@ -844,6 +853,12 @@ void vlr_ctx_destroy(vlr_ctx_t* ctx) {
         cudaStreamDestroy(ctx->stream);
     }
     free_slot(ctx->dev_slot);
+    free_slot(ctx->dev_slot2);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->aux[i]) cudaStreamDestroy(ctx->aux[i]);
+        if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     for (auto& s : ctx->slots) free_slot(s);
     DevBuf* sc[] = {&ctx->d_samples, &ctx->d_events, &ctx->d_nodes, &ctx->d_set_vafs, &ctx->d_spectra,
                     &ctx->d_lfc_nodes, &ctx->d_lfc_ordinal, &ctx->d_prior_tab};
@@ -896,6 +911,24 @@ vlr_status_t vlr_call_batch_device(vlr_ctx_t* ctx, const vlr_batch_t* batch, vlr
     r.afd_vaf = results->afd_vaf;
     r.afd_logp = results->afd_logp;
     const int64_t avg_reads = batch->n_loci > 0 ? (batch->n_reads + batch->n_loci - 1) / batch->n_loci : 0;
+    if (ctx->wave && batch->n_loci >= (1 << 17)) {
+        // large batch on the wavefront pipeline: its two halves run on two internal streams (own workspaces), forked
+        // from and joined to the caller's stream, so that one half's kernels fill the grid tails and the straggler
+        // rounds of the other (the host entry gets the same effect from its three chunk streams)
+        st = ensure_workspace(ctx, ctx->dev_slot2, ctx->reserve_reads, results->afd_capacity > 0);
+        if (st != VLR_OK) return st;
+        CK(cudaEventRecord(ctx->ev_fork, stream));
+        const int64_t mid = batch->n_loci / 2;
+        Slot* slots2[2] = {&ctx->dev_slot, &ctx->dev_slot2};
+        for (int i = 0; i < 2; ++i) {
+            CK(cudaStreamWaitEvent(ctx->aux[i], ctx->ev_fork, 0));
+            st = launch_wave(ctx, *slots2[i], b, r, avg_reads, ctx->aux[i], i == 0 ? 0 : mid, i == 0 ? mid : batch->n_loci);
+            if (st != VLR_OK) return st;
+            CK(cudaEventRecord(ctx->ev_join[i], ctx->aux[i]));
+            CK(cudaStreamWaitEvent(stream, ctx->ev_join[i], 0));
+        }
+        return VLR_OK;
+    }
     return launch(ctx, ctx->dev_slot, b, r, stream, avg_reads);
 }
 
