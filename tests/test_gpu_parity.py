@@ -281,3 +281,25 @@ def test_wavefront_pipeline_equals_generic_engine(engine_mod, monkeypatch):
     valid &= (~ke)[:, None, None]
     assert np.array_equal(o.afd_count[~ke], gw.afd_count[idx][~ke])
     assert max_abs_delta(o.afd_logp[valid], gw.afd_logp[idx][valid]) <= TOL
+
+
+def test_large_device_batch_runs_on_internal_streams(engine_mod):
+    """>= 131072 loci through the device entry: the wavefront pipeline splits the batch over internal streams (forked
+    from / joined to the caller's stream). Bitwise the same results as the chunked host entry, in input order."""
+    import torch
+    sc, b = synth.tumor_normal(140000, seed=777, depth=12)
+    flat = sc.flatten()
+    eng = engine_mod.PosteriorEngine(flat)
+    host = eng.call_batch(b)
+    db = engine_mod.DeviceBatch(b)
+    dr = engine_mod.DeviceResults(b.n_loci, 2, flat.n_events)
+    s = torch.cuda.Stream()
+    eng.call_batch_device(db, dr, s.cuda_stream)
+    s.synchronize()
+    dev = dr.to_host()
+    assert np.array_equal(host.log_posteriors, dev.log_posteriors, equal_nan=True)
+    assert np.array_equal(host.map_vaf, dev.map_vaf, equal_nan=True)
+    assert np.array_equal(host.status, dev.status)
+    assert np.array_equal(host.n_base_events, dev.n_base_events)
+    total = np.logaddexp.reduce(dev.log_posteriors, axis=1)
+    assert np.nanmax(np.abs(total)) < 1e-9

@@ -475,9 +475,11 @@ struct vlr_ctx {
     DevBuf d_samples, d_events, d_nodes, d_set_vafs, d_spectra, d_lfc_nodes, d_lfc_ordinal, d_prior_tab;
     cudaStream_t stream = nullptr; // the context's own stream (device-pointer entry)
     Slot dev_slot;                 // workspace of the device-pointer entry
-    Slot dev_slot2;                // second half of a large wavefront batch runs concurrently on its own stream
-    cudaStream_t aux[2] = {nullptr, nullptr};
-    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    static constexpr int MAX_AUX = 4;
+    Slot dev_slot_aux[MAX_AUX - 1]; // parts of a large wavefront batch run concurrently on internal streams
+    cudaStream_t aux[MAX_AUX] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[MAX_AUX] = {nullptr, nullptr, nullptr, nullptr};
+    int n_aux = 3; // measured on 512k config-2 loci: 1 stream 4.05, 2: 4.43, 3: 4.48, 4: 4.51 M loci/s
     Slot slots[NBUF];
     int64_t reserve_reads = 4096;
     int64_t launches = 0;
@@ -820,7 +822,8 @@ vlr_status_t vlr_ctx_create(const vlr_scenario_t* scenario, int32_t device, vlr_
         ctx->wave_grid_finish = std::min(std::max(1, n3) * ctx->n_sms, ctx->grid);
     }
     CKB(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
+    if (const char* e = getenv("VLR_WAVE_STREAMS")) ctx->n_aux = std::max(1, std::min((int)vlr_ctx::MAX_AUX, atoi(e)));
+    for (int i = 0; i < vlr_ctx::MAX_AUX; ++i) {
         CKB(cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking));
         CKB(cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming));
     }
@@ -853,8 +856,8 @@ void vlr_ctx_destroy(vlr_ctx_t* ctx) {
         cudaStreamDestroy(ctx->stream);
     }
     free_slot(ctx->dev_slot);
-    free_slot(ctx->dev_slot2);
-    for (int i = 0; i < 2; ++i) {
+    for (auto& sa : ctx->dev_slot_aux) free_slot(sa);
+    for (int i = 0; i < vlr_ctx::MAX_AUX; ++i) {
         if (ctx->aux[i]) cudaStreamDestroy(ctx->aux[i]);
         if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
     }
@@ -911,18 +914,21 @@ vlr_status_t vlr_call_batch_device(vlr_ctx_t* ctx, const vlr_batch_t* batch, vlr
     r.afd_vaf = results->afd_vaf;
     r.afd_logp = results->afd_logp;
     const int64_t avg_reads = batch->n_loci > 0 ? (batch->n_reads + batch->n_loci - 1) / batch->n_loci : 0;
-    if (ctx->wave && batch->n_loci >= (1 << 17)) {
-        // large batch on the wavefront pipeline: its two halves run on two internal streams (own workspaces), forked
-        // from and joined to the caller's stream, so that one half's kernels fill the grid tails and the straggler
-        // rounds of the other (the host entry gets the same effect from its three chunk streams)
-        st = ensure_workspace(ctx, ctx->dev_slot2, ctx->reserve_reads, results->afd_capacity > 0);
-        if (st != VLR_OK) return st;
+    if (ctx->wave && ctx->n_aux > 1 && batch->n_loci >= (1 << 17)) {
+        // large batch on the wavefront pipeline: its parts run on internal streams (own workspaces), forked from and
+        // joined to the caller's stream, so that one part's kernels fill the grid tails and the straggler rounds of
+        // the others (the host entry gets the same effect from its three chunk streams)
+        const int ns = ctx->n_aux;
         CK(cudaEventRecord(ctx->ev_fork, stream));
-        const int64_t mid = batch->n_loci / 2;
-        Slot* slots2[2] = {&ctx->dev_slot, &ctx->dev_slot2};
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < ns; ++i) {
+            Slot& sl = i == 0 ? ctx->dev_slot : ctx->dev_slot_aux[i - 1];
+            if (i > 0) {
+                st = ensure_workspace(ctx, sl, ctx->reserve_reads, results->afd_capacity > 0);
+                if (st != VLR_OK) return st;
+            }
+            const int64_t lo = batch->n_loci * i / ns, hi = batch->n_loci * (i + 1) / ns;
             CK(cudaStreamWaitEvent(ctx->aux[i], ctx->ev_fork, 0));
-            st = launch_wave(ctx, *slots2[i], b, r, avg_reads, ctx->aux[i], i == 0 ? 0 : mid, i == 0 ? mid : batch->n_loci);
+            st = launch_wave(ctx, sl, b, r, avg_reads, ctx->aux[i], lo, hi);
             if (st != VLR_OK) return st;
             CK(cudaEventRecord(ctx->ev_join[i], ctx->aux[i]));
             CK(cudaStreamWaitEvent(stream, ctx->ev_join[i], 0));
