@@ -1060,10 +1060,6 @@ VLR_DEV_NOINLINE double prior_compute_uncached(Ctx& c_, const Ops& ev);
 
 // All-discrete VAF vector, no per-record prior overrides: look the prior up in the context's table, computing and
 // publishing it on a miss. Lane 0 talks to the table and broadcasts, so the warp's control flow stays uniform.
-#ifdef VLR_PTAB_DEBUG
-static long g_ptab_hits = 0, g_ptab_miss = 0;
-struct PtabReport { ~PtabReport() { fprintf(stderr, "ptab hits %ld miss %ld\n", g_ptab_hits, g_ptab_miss); } } static g_ptab_report;
-#endif
 VLR_DEV_NOINLINE double prior_tab_compute(Ctx& c_, const Ops& ev) {
     Ctx& c = warp_ctx(c_);
     const DevScenario* sc = c.sc;
@@ -1116,15 +1112,9 @@ VLR_DEV_NOINLINE double prior_tab_compute(Ctx& c_, const Ops& ev) {
     side = __shfl_sync(FULL, side, 0, LANES);
 #endif
     if (found) {
-#ifdef VLR_PTAB_DEBUG
-        g_ptab_hits++;
-#endif
         c.status |= side;
         return value;
     }
-#ifdef VLR_PTAB_DEBUG
-    g_ptab_miss++;
-#endif
     const uint32_t s0 = c.status;
     c.status = 0;
     const double p = prior_compute_uncached(c, ev);
