@@ -13,9 +13,14 @@ trees without it. It mirrors
   * `VAFTree::new` incl. `add_missing_samples` and `VAFTree::absent` (src/grammar/vaftree.rs:18-40,168-305);
   * the tumor-normal scenario of `call variants tumor-normal` (src/cli.rs:1151-1173).
 
-Known divergence (documented in DESIGN.md): the reference additionally runs a BDD
-simplification (`boolean_expression::Expr::simplify_via_bdd`, formula.rs:710-714, crate not
-vendored); formulas here are kept structurally as written after negation/merging.
+`Formula::simplify` (formula.rs:710-714) goes through `boolean_expression::Expr::simplify_via_bdd`
+(crate `boolean_expression 0.4`, Cargo.toml; not vendored). After `apply_negations` every literal is
+positive, so the formula is a monotone function of its distinct terminals, and the reference panics on
+any negative literal that survives (`to_normalized_formula`, formula.rs:553-555): whenever the reference
+works at all, the BDD round trip returns a positive, irredundant sum of products, and for a monotone
+function that cover is unique - the set of its prime implicants. `Scenario._simplify` computes exactly
+that set (distribution with absorption); pinned by the reference's own normalisation tests
+(formula.rs:1621-1735, tests/test_scenario_normalize.py).
 """
 from __future__ import annotations
 
@@ -61,15 +66,48 @@ class VAFRange:
                 or (self.end <= o.start and (self.right_exclusive or o.left_exclusive))
                 or (self.start >= o.end and (self.left_exclusive or o.right_exclusive)))
 
-    def intersect(self, o: "VAFRange") -> "VAFRange":
+    def is_complete(self) -> bool:
+        return self.start == 0.0 and self.end == 1.0 and not self.left_exclusive and not self.right_exclusive
+
+    def overlap(self, o: "VAFRange") -> str:
+        """VAFRange::overlap (formula.rs:1137-1170): how `self` lies relative to `o`."""
+        if self == o:
+            return "equal"
         if self.no_overlap(o):
-            return VAFRange(0.0, 0.0, True, True)
-        start, end = max(self.start, o.start), min(self.end, o.end)
-        lex = self.left_exclusive if self.start > o.start else (
-            o.left_exclusive if self.start < o.start else (self.left_exclusive or o.left_exclusive))
-        rex = self.right_exclusive if self.end < o.end else (
-            o.right_exclusive if self.end > o.end else (self.right_exclusive or o.right_exclusive))
-        return VAFRange(start, end, lex, rex)
+            return "none"
+        start_right = (self.start >= o.start) if (self.left_exclusive and not o.left_exclusive) \
+            else (self.start > o.start)
+        end_left = (self.end <= o.end) if (self.right_exclusive and not o.right_exclusive) \
+            else (self.end < o.end)
+        if start_right:
+            return "contained" if end_left else "start"
+        return "end" if end_left else "contains"
+
+    def intersect(self, o: "VAFRange") -> "VAFRange":
+        """`&a & &b` (formula.rs:1264-1282)."""
+        ov = self.overlap(o)
+        if ov in ("contained", "equal"):
+            return self
+        if ov == "contains":
+            return o
+        if ov == "start":
+            return VAFRange(self.start, o.end, self.left_exclusive, o.right_exclusive)
+        if ov == "end":
+            return VAFRange(o.start, self.end, o.left_exclusive, self.right_exclusive)
+        return VAFRange(0.0, 0.0, True, True)
+
+    def union(self, o: "VAFRange") -> Optional["VAFRange"]:
+        """First component of `&a | &b` (formula.rs:1284-1302); None when the ranges do not overlap."""
+        ov = self.overlap(o)
+        if ov == "contained":
+            return o
+        if ov in ("contains", "equal"):
+            return self
+        if ov == "start":
+            return VAFRange(o.start, self.end, o.left_exclusive, self.right_exclusive)
+        if ov == "end":
+            return VAFRange(self.start, o.end, self.left_exclusive, o.right_exclusive)
+        return None
 
     def split_at(self, vaf: float):
         """formula.rs:1105-1135; returns (left, right) spectra or None."""
@@ -319,7 +357,7 @@ class Species:
     heterozygosity: Optional[float] = None
     germline_mutation_rate: Optional[float] = None
     somatic_effective_mutation_rate: Optional[float] = None
-    ploidy: Optional[int] = None
+    ploidy: Union[None, int, dict] = None
     vtf_indel: float = 0.0125
     vtf_mnv: float = 0.001
     vtf_sv: float = 0.01
@@ -366,6 +404,7 @@ class Scenario:
         for k, f in self.event_formulas.items():  # events are registered as expressions (mod.rs:155-162)
             self.expressions.setdefault(k, f)
         self.full_prior = full_prior
+        self.contig = "all"  # the reference's tests normalise on "all" (formula.rs:1663)
         self._keepalive = None
 
     # -- construction helpers
@@ -377,9 +416,7 @@ class Scenario:
         if doc.get("species"):
             d = doc["species"]
             vtf = d.get("variant-type-fractions", {}) or {}
-            ploidy = d.get("ploidy")
-            if isinstance(ploidy, dict):
-                raise NotImplementedError("per-contig/sex ploidy maps are resolved by the host")
+            ploidy = d.get("ploidy")  # u32 | {contig: u32} | {sex: u32 | {contig: u32}} (mod.rs:288-342)
             sp = Species(_opt_float(d.get("heterozygosity")), _opt_float(d.get("germline-mutation-rate")),
                          _opt_float(d.get("somatic-effective-mutation-rate")), ploidy,
                          float(vtf.get("indel", 0.0125)), float(vtf.get("mnv", 0.001)), float(vtf.get("sv", 0.01)))
@@ -429,11 +466,42 @@ class Scenario:
     def idx(self, name: str) -> int:
         return self.sample_names.index(name)
 
+    @staticmethod
+    def _contig_ploidy(definition, contig: str) -> int:
+        """PloidyDefinition::contig_ploidy (mod.rs:296-312)."""
+        if isinstance(definition, dict):
+            if contig in definition:
+                return int(definition[contig])
+            if "all" not in definition:
+                raise ValueError("ploidy definition for contig %s not found" % contig)
+            return int(definition["all"])
+        return int(definition)
+
     def ploidy(self, name: str) -> Optional[int]:
+        """Sample::contig_ploidy (mod.rs:581-593) on `self.contig`."""
         s = self.samples[name]
         if s.ploidy is not None:
-            return s.ploidy
-        return self.species.ploidy if self.species else None
+            return self._contig_ploidy(s.ploidy, self.contig)
+        if self.species is None or self.species.ploidy is None:
+            return None
+        d = self.species.ploidy
+        if isinstance(d, dict) and (any(isinstance(v, dict) for v in d.values()) or set(d) <= {"male", "female"}):
+            # SexPloidyDefinition::Specific (mod.rs:321-342)
+            if s.sex is None:
+                raise ValueError("sex specific ploidy definition found but no sex specified in sample")
+            if s.sex not in d:
+                raise ValueError("ploidy definition for %s not found" % s.sex)
+            return self._contig_ploidy(d[s.sex], self.contig)
+        return self._contig_ploidy(d, self.contig)
+
+    def for_contig(self, contig: str) -> "Scenario":
+        """The scenario as `Caller::configure_model` sees it on `contig` (calling.rs:632-718): universes,
+        and with them the event trees, follow the contig's ploidy."""
+        import copy
+        sc = copy.copy(self)
+        sc.contig = contig
+        sc._keepalive = None
+        return sc
 
     def somatic_rate(self, name: str) -> Optional[float]:
         s = self.samples[name]
@@ -623,7 +691,8 @@ class Scenario:
                         merged = cur if all(cur.contains(v) for v in o) else None
                     elif isinstance(cur, frozenset) and isinstance(o, VAFRange):
                         merged = o if all(o.contains(v) for v in cur) else None
-                    # Range|Range unions are left unmerged here (reference merges overlapping ranges)
+                    elif isinstance(cur, VAFRange) and isinstance(o, VAFRange):
+                        merged = cur.union(o)  # None when they do not overlap (formula.rs:157-160)
                     if merged is not None:
                         cur = merged
                     else:
@@ -638,16 +707,14 @@ class Scenario:
         # derived Ord: Conjunction < Disjunction < Negation < Terminal; LFC terminals first (formula.rs:455-471)
         if isinstance(f, L2FC):
             return (0, 3, f.sample_a, f.sample_b)
-        if isinstance(f, And):
-            return (1, 0, "", "")
-        if isinstance(f, Or):
-            return (1, 1, "", "")
+        if isinstance(f, (And, Or)):  # Vec<Formula> compares lexicographically
+            return (1, 0 if isinstance(f, And) else 1, tuple(Scenario._sort_key(o) for o in f.operands), "")
         if isinstance(f, Atom):
             v = f.vafs
             sub = (0, tuple(sorted(v))) if isinstance(v, frozenset) else (1, (v.start, v.end))
             return (1, 2, f.sample, sub)
         if isinstance(f, Variant):
-            return (1, 3, f.refbase, f.altbase)
+            return (1, 3, (f.positive, f.refbase, f.altbase), "")
         return (1, 4, "", "")
 
     @staticmethod
@@ -658,9 +725,59 @@ class Scenario:
             return type(f)(tuple(ops))
         return f
 
+    @staticmethod
+    def _absorb(cubes):
+        """Drop every cube that is a superset of another one (x | x & y = x)."""
+        out = []
+        for c in sorted(set(cubes), key=len):
+            if not any(k <= c for k in out):
+                out.append(c)
+        return out
+
+    @classmethod
+    def _prime_implicants(cls, f):
+        """Cubes (frozensets of terminals) of the minimal positive DNF of the negation-free formula `f`."""
+        if isinstance(f, Const):
+            return [frozenset()] if f.value else []
+        if isinstance(f, Atom):  # From<Formula> for Expr (formula.rs:369-379): empty -> false, complete -> true
+            if spectrum_is_empty(f.vafs):
+                return []
+            if isinstance(f.vafs, VAFRange) and f.vafs.is_complete():
+                return [frozenset()]
+            return [frozenset([f])]
+        if isinstance(f, (Variant, L2FC)):
+            return [frozenset([f])]
+        if isinstance(f, Or):
+            cubes = []
+            for o in f.operands:
+                cubes.extend(cls._prime_implicants(o))
+            return cls._absorb(cubes)
+        if isinstance(f, And):
+            cubes = [frozenset()]
+            for o in f.operands:
+                sub = cls._prime_implicants(o)
+                cubes = cls._absorb([a | b for a in cubes for b in sub])
+            return cubes
+        raise TypeError("negations and expressions must be resolved before simplification: %r" % (f,))
+
+    @classmethod
+    def _simplify(cls, f):
+        """Formula::simplify (formula.rs:710-714), see the module docstring."""
+        cubes = cls._prime_implicants(f)
+        if not cubes:
+            return Const(False)
+        if any(len(c) == 0 for c in cubes):
+            return Const(True)
+        terms = []
+        for c in cubes:
+            lits = sorted(c, key=cls._sort_key)
+            terms.append(lits[0] if len(lits) == 1 else And(tuple(lits)))
+        return terms[0] if len(terms) == 1 else Or(tuple(terms))
+
     def normalize(self, f):
-        g = self._flatten(self._apply_negations(self._expand(f)))
-        g = self._flatten(self._merge_atoms(g))
+        """Formula::normalize (formula.rs:473-485)."""
+        g = self._simplify(self._apply_negations(self._expand(f)))
+        g = self._simplify(self._flatten(self._merge_atoms(g)))
         if isinstance(g, Or):  # strip_false
             keep = [o for o in g.operands if not (isinstance(o, Const) and not o.value)
                     and not (isinstance(o, And) and any(isinstance(x, Const) and not x.value for x in o.operands))]
