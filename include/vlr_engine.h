@@ -252,6 +252,41 @@ void vlr_host_free(void* p);
  * the denominator of the fp64 roofline this path is bound by (HBM is not the bound here). */
 vlr_status_t vlr_measure_fp64_peak(int32_t device, double* tflops);
 
+/* ---- contamination estimator (src/estimation/contamination.rs), SURVEY.md §8(f)-4 --------------------------------
+ * The second Bayesian model `estimate contamination` runs over the calls of the `denovo`/`other` scenario
+ * (contamination.rs:436-449): events = expected maximum somatic VAF x contamination grid, likelihood = sum over the
+ * kept VariantObservations of the observation's allele frequency distribution, interpolated at the VAF the event
+ * predicts (Likelihood::compute :163-186, VariantObservation::pdf :84-115), marginal = ln_sum_exp over the rows of
+ * a Simpson rule over the contamination grid (Marginal::compute :213-240). The host keeps what the reference does per
+ * call (VariantObservation::new :44-82: P(denovo) >= 0.95 and an AFD present) and the output tables. */
+typedef struct {
+    int64_t n_obs;
+    const double* prob_denovo;       /* [n_obs] ln P(denovo) */
+    const double* max_posterior_vaf; /* [n_obs] MAP allele frequency of the sample */
+    const int64_t* afd_offsets;      /* [n_obs+1] rows of afd_vaf/afd_logp per observation */
+    const double* afd_vaf;           /* ascending within an observation (BTreeMap order) */
+    const double* afd_logp;          /* ln posterior density */
+    int32_t n_grid;                  /* contamination grid points per row, odd, >= 3 (reference: 101) */
+    int32_t n_max_vafs;              /* rows, <= 8 (reference: 4); n_grid * n_max_vafs <= 1024 */
+    const double* expected_max_somatic_vaf; /* [n_max_vafs] (reference: 0.25, 0.5, 0.75, 1.0) */
+    const double* ln_prior;          /* [n_grid] Prior::prob (contamination.rs:137-147) at linspace(0, 1, n_grid) */
+} vlr_contamination_input_t;
+
+typedef struct {
+    double* ln_posterior;  /* [n_max_vafs][n_grid] joint - marginal (ModelInstance::event_posteriors) */
+    double* ln_likelihood; /* [n_max_vafs][n_grid], optional (NULL) */
+    double* ln_marginal;   /* [1] */
+    double* max_vaf;       /* [1] VAFDist::max_vaf (contamination.rs:249-258), optional (NULL) */
+} vlr_contamination_output_t;
+
+/* Host buffers in, host buffers out, on `device`. n_obs = 0 is valid (likelihood ln_one everywhere). */
+vlr_status_t vlr_contamination_posterior(int32_t device, const vlr_contamination_input_t* in,
+                                         vlr_contamination_output_t* out);
+/* Same with every pointer a DEVICE pointer on `device` (e.g. AFDs packed from device-resident results);
+ * asynchronous on `cuda_stream` except for the scratch allocation; the caller synchronises. */
+vlr_status_t vlr_contamination_posterior_device(int32_t device, const vlr_contamination_input_t* in,
+                                                vlr_contamination_output_t* out, void* cuda_stream);
+
 /* Number of kernels the last vlr_call_batch* launched (for bench accounting). */
 int64_t vlr_last_launch_count(const vlr_ctx_t* ctx);
 /* The context's stream (cudaStream_t) so callers can time with CUDA events. */

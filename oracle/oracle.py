@@ -47,7 +47,32 @@ def lib():
         _lib.vlr_oracle_pileup_likelihood.restype = C.c_double
         _lib.vlr_oracle_pileup_likelihood.argtypes = [C.POINTER(abi.Batch), C.c_int64, C.c_int64, C.c_double,
                                                       C.c_double, C.c_double, C.c_int32]
+        _lib.vlr_oracle_contamination_posterior.restype = C.c_int32
+        _lib.vlr_oracle_contamination_posterior.argtypes = [C.POINTER(abi.ContaminationInput),
+                                                            C.POINTER(abi.ContaminationOutput)]
     return _lib
+
+
+def contamination_posterior(prob_denovo, max_posterior_vaf, afd_offsets, afd_vaf, afd_logp, ln_prior,
+                            expected_max_somatic_vafs=(0.25, 0.5, 0.75, 1.0)):
+    """estimation/contamination.rs' model on CSR-packed observations: (ln_posterior[rows][n_grid], ln_likelihood,
+    ln_marginal, max_vaf)."""
+    f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)  # noqa: E731
+    prob_denovo, mpv, vaf, logp, ln_prior = map(f64, (prob_denovo, max_posterior_vaf, afd_vaf, afd_logp, ln_prior))
+    offsets = np.ascontiguousarray(afd_offsets, dtype=np.int64)
+    emsv = f64(expected_max_somatic_vafs)
+    post = np.empty((len(emsv), len(ln_prior)))
+    lik = np.empty_like(post)
+    marginal, max_vaf = np.zeros(1), np.zeros(1)
+    cin = abi.ContaminationInput(len(prob_denovo), abi.ptr(prob_denovo, C.c_double), abi.ptr(mpv, C.c_double),
+                                 abi.ptr(offsets, C.c_int64), abi.ptr(vaf, C.c_double), abi.ptr(logp, C.c_double),
+                                 len(ln_prior), len(emsv), abi.ptr(emsv, C.c_double), abi.ptr(ln_prior, C.c_double))
+    cout = abi.ContaminationOutput(abi.ptr(post, C.c_double), abi.ptr(lik, C.c_double), abi.ptr(marginal, C.c_double),
+                                   abi.ptr(max_vaf, C.c_double))
+    rc = lib().vlr_oracle_contamination_posterior(C.byref(cin), C.byref(cout))
+    if rc != 0:
+        raise RuntimeError("oracle contamination model failed with status %d" % rc)
+    return post, lik, float(marginal[0]), float(max_vaf[0])
 
 
 class OracleOutput(CallResults):

@@ -11,7 +11,9 @@
 //   src/variants/model/bias/*.rs              (six artifact models)
 //   src/utils/adaptive_integration.rs         (unimodal adaptive ln-integration)
 //   src/utils/log2_fold_change.rs, src/grammar/formula.rs:1057-1263 (VAFRange),
-//   src/grammar/vaftree.rs:42-165 (contains), src/calling/variants/calling.rs:720-937
+//   src/grammar/vaftree.rs:42-165 (contains), src/calling/variants/calling.rs:720-937,
+//   src/estimation/contamination.rs:84-271 (the contamination estimator's model; no golden vector in the reference:
+//   parity unpinned, checked against a pure-Python restatement in tests/test_contamination.py)
 // and of the rust-bio 2.0 (`bio::stats`) semantics those files call (crate absent from
 // /root/reference; restated from its published algorithm):
 //   LogProb::{ln_sum_exp, ln_add_exp, ln_one_minus_exp, cap_numerical_overshoot,
@@ -1569,6 +1571,65 @@ double vlr_oracle_pileup_likelihood(const vlr_batch_t* batch, int64_t lo, int64_
         }
     }
     return lh;
+}
+
+// ---- estimation/contamination.rs: the contamination estimator's model, sequentially, in the reference's order ----
+// Same contract as vlr_contamination_posterior (include/vlr_engine.h).
+int32_t vlr_oracle_contamination_posterior(const vlr_contamination_input_t* in, vlr_contamination_output_t* out) {
+    if (!in || !out || !out->ln_posterior || !out->ln_marginal || in->n_grid < 3 || in->n_grid % 2 == 0)
+        return VLR_ERR_INVALID_ARGUMENT;
+    const int n = in->n_grid, rows = in->n_max_vafs;
+    // VariantObservation.vaf_dist: BTreeMap<AlleleFreq, LogProb> (contamination.rs:38)
+    std::vector<std::map<double, double>> dist((size_t)in->n_obs);
+    double max_vaf = 0.0; // VAFDist::new (contamination.rs:249-258)
+    for (int64_t o = 0; o < in->n_obs; ++o) {
+        for (int64_t j = in->afd_offsets[o]; j < in->afd_offsets[o + 1]; ++j) dist[o][in->afd_vaf[j]] = in->afd_logp[j];
+        if (in->max_posterior_vaf[o] > max_vaf) max_vaf = in->max_posterior_vaf[o];
+    }
+    auto pdf = [&](int64_t o, double vaf) -> double { // VariantObservation::pdf (contamination.rs:84-115)
+        const auto& d = dist[o];
+        auto sup = d.lower_bound(vaf); // range(vaf..).next()
+        if (sup != d.end() && sup->first == vaf) return sup->second;
+        if (sup == d.begin() || sup == d.end()) return NEG_INF; // no infimum / no supremum / empty
+        auto inf = std::prev(sup); // range(..vaf).last()
+        return ln_add_exp(inf->second, std::log((std::exp(sup->second) - std::exp(inf->second)) / (sup->first - inf->first)) +
+                                           std::log(vaf - inf->first));
+    };
+    Diag diag;
+    auto likelihood = [&](double contamination, double emsv) -> double { // Likelihood::compute (contamination.rs:163-186)
+        const double purity = 1.0 - contamination;
+        double sum = 0.0;
+        for (int64_t o = 0; o < in->n_obs; ++o) {
+            if (purity == 0.0) {
+                sum += ln_one_minus_exp(in->prob_denovo[o], diag);
+                continue;
+            }
+            const double quantile = in->max_posterior_vaf[o] / max_vaf; // get_expected_vaf (contamination.rs:263-271)
+            sum += pdf(o, emsv * purity * quantile);
+        }
+        return sum;
+    };
+    std::vector<double> joint((size_t)rows * n), row_integrals;
+    for (int k = 0; k < rows; ++k) { // Marginal::compute (contamination.rs:213-240)
+        const double emsv = in->expected_max_somatic_vaf[k];
+        auto density = [&](int i, double contamination) {
+            const double lik = likelihood(contamination, emsv);
+            if (out->ln_likelihood) out->ln_likelihood[k * n + i] = lik;
+            joint[(size_t)k * n + i] = in->ln_prior[i] + lik; // Model::joint_prob: prior + likelihood
+            return joint[(size_t)k * n + i];
+        };
+        // rust-bio ln_simpsons_integrate_exp(density, 0.0, 1.0, n): interior points first, then both ends
+        std::vector<double> probs;
+        for (int i = 1; i < n - 1; ++i) probs.push_back(density(i, linspace_at(0.0, 1.0, n, i)) + std::log((double)(2 + (i % 2) * 2)));
+        probs.push_back(density(0, 0.0));
+        probs.push_back(density(n - 1, 1.0));
+        row_integrals.push_back(ln_sum_exp(probs) + std::log(1.0 - 0.0) - std::log((double)(n - 1)) - std::log(3.0));
+    }
+    const double marginal = ln_sum_exp(row_integrals);
+    for (size_t e = 0; e < joint.size(); ++e) out->ln_posterior[e] = joint[e] - marginal; // event_posteriors
+    *out->ln_marginal = marginal;
+    if (out->max_vaf) *out->max_vaf = max_vaf;
+    return VLR_OK;
 }
 
 int32_t vlr_oracle_abi_version(void) { return VLR_ABI_VERSION; }

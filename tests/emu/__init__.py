@@ -13,6 +13,7 @@ _SRC = [os.path.join(_HERE, "emu_driver.cpp"),
         os.path.join(_HERE, "..", "..", "varlociraptor_b200", "csrc", "engine_wave.cuh"),
         os.path.join(_HERE, "..", "..", "varlociraptor_b200", "csrc", "scenario_prep.h"),
         os.path.join(_HERE, "..", "..", "varlociraptor_b200", "csrc", "engine_types.cuh"),
+        os.path.join(_HERE, "..", "..", "varlociraptor_b200", "csrc", "contamination.cuh"),
         os.path.join(_HERE, "..", "..", "include", "vlr_engine.h")]
 _lib = None
 
@@ -33,6 +34,9 @@ def _load():
         for fn in (_lib.vlr_emu_call_batch, _lib.vlr_emu_wave_call_batch):
             fn.restype = C.c_int32
             fn.argtypes = [C.POINTER(abi.Scenario), C.POINTER(abi.Batch), C.POINTER(abi.Results)]
+        _lib.vlr_emu_contamination_posterior.restype = C.c_int32
+        _lib.vlr_emu_contamination_posterior.argtypes = [C.POINTER(abi.ContaminationInput),
+                                                         C.POINTER(abi.ContaminationOutput), C.c_int64]
     return _lib
 
 
@@ -58,3 +62,26 @@ def call_batch(flat_scenario, batch, afd_capacity=0) -> CallResults:
     if rc != 0:
         raise RuntimeError("emu failed with status %d" % rc)
     return out
+
+
+def contamination_posterior(observations, prior_estimate=None, device=0, chunk=37):
+    """`varlociraptor_b200.contamination.contamination_posterior` with the device functions of csrc/contamination.cuh
+    run on the host (chunked partial sums like the kernels)."""
+    import numpy as np
+    from varlociraptor_b200 import contamination as ct
+    lib = _load()
+    prob_denovo, mpv, offsets, vaf, logp = ct.pack_observations(observations)
+    emsv = np.asarray(ct.EXPECTED_MAX_SOMATIC_VAFS, dtype=np.float64)
+    ln_prior = ct.Prior(prior_estimate).table(ct.N_GRID)
+    post = np.empty((len(emsv), ct.N_GRID))
+    lik = np.empty_like(post)
+    marginal, max_vaf = np.zeros(1), np.zeros(1)
+    cin = abi.ContaminationInput(len(observations), abi.ptr(prob_denovo, C.c_double), abi.ptr(mpv, C.c_double),
+                                 abi.ptr(offsets, C.c_int64), abi.ptr(vaf, C.c_double), abi.ptr(logp, C.c_double),
+                                 ct.N_GRID, len(emsv), abi.ptr(emsv, C.c_double), abi.ptr(ln_prior, C.c_double))
+    cout = abi.ContaminationOutput(abi.ptr(post, C.c_double), abi.ptr(lik, C.c_double), abi.ptr(marginal, C.c_double),
+                                   abi.ptr(max_vaf, C.c_double))
+    rc = lib.vlr_emu_contamination_posterior(C.byref(cin), C.byref(cout), chunk)
+    if rc != 0:
+        raise RuntimeError("emu contamination model failed with status %d" % rc)
+    return ct.ContaminationPosterior(post, lik, float(marginal[0]), float(max_vaf[0]), tuple(emsv.tolist()))

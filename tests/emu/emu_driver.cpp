@@ -20,6 +20,7 @@
 #define VLR_VAR_MAXD VLR_MAX_TREE_DEPTH
 #include "../../varlociraptor_b200/csrc/engine_core.cuh"
 #include "../../varlociraptor_b200/csrc/scenario_prep.h"
+#include "../../varlociraptor_b200/csrc/contamination.cuh"
 
 static void emu_views(const vlr_batch_t* batch, vlr_results_t* results, vlrcore::DevBatch& db, vlrcore::DevResults& dr) {
     db.n_loci = batch->n_loci;
@@ -167,4 +168,39 @@ extern "C" int32_t vlr_emu_wave_call_batch(const vlr_scenario_t* sc, const vlr_b
     delete c;
     delete ws;
     return (int32_t)cnt.n_deferred;
+}
+
+// The contamination model's device functions (csrc/contamination.cuh) driven the way the two kernels drive them:
+// per event a partial sum per chunk of `chunk` observations, combined in chunk order, then the Simpson rows.
+extern "C" int32_t vlr_emu_contamination_posterior(const vlr_contamination_input_t* in, vlr_contamination_output_t* out,
+                                                    int64_t chunk) {
+    using namespace vlrcontam;
+    const int n_events = in->n_grid * in->n_max_vafs;
+    if (n_events > CONTAM_MAX_EVENTS || in->n_max_vafs > CONTAM_MAX_ROWS || chunk < 1) return VLR_ERR_INVALID_ARGUMENT;
+    double max_vaf = 0.0;
+    for (int64_t o = 0; o < in->n_obs; ++o) max_vaf = fmax(max_vaf, in->max_posterior_vaf[o]);
+    std::vector<double> joint((size_t)n_events), scratch((size_t)n_events), rows((size_t)in->n_max_vafs);
+    for (int e = 0; e < n_events; ++e) {
+        const int k = e / in->n_grid, gi = e % in->n_grid;
+        const double purity = 1.0 - grid_contamination(gi, in->n_grid);
+        double lik = 0.0;
+        for (int64_t o0 = 0; o0 < in->n_obs; o0 += chunk) {
+            double sum = 0.0;
+            for (int64_t o = o0; o < std::min(in->n_obs, o0 + chunk); ++o) {
+                const int64_t base = in->afd_offsets[o];
+                sum += obs_term(in->prob_denovo[o], in->max_posterior_vaf[o], max_vaf, in->expected_max_somatic_vaf[k],
+                                purity, in->afd_vaf + base, in->afd_logp + base, (int)(in->afd_offsets[o + 1] - base));
+            }
+            lik += sum;
+        }
+        if (out->ln_likelihood) out->ln_likelihood[e] = lik;
+        joint[e] = in->ln_prior[gi] + lik;
+    }
+    for (int k = 0; k < in->n_max_vafs; ++k)
+        rows[k] = simpson_row(joint.data() + (size_t)k * in->n_grid, in->n_grid, scratch.data() + (size_t)k * in->n_grid);
+    const double marginal = ln_sum_exp_slice(rows.data(), in->n_max_vafs);
+    for (int e = 0; e < n_events; ++e) out->ln_posterior[e] = joint[e] - marginal;
+    *out->ln_marginal = marginal;
+    if (out->max_vaf) *out->max_vaf = max_vaf;
+    return VLR_OK;
 }

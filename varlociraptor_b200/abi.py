@@ -137,6 +137,18 @@ BATCH_F32_COLUMNS = ["prob_mapping", "prob_ref", "prob_alt", "prob_missed_allele
 BATCH_OPTIONAL_F32_COLUMNS = ["prob_homopolymer_artifact", "prob_homopolymer_variant"]
 
 
+class ContaminationInput(C.Structure):  # vlr_contamination_input_t
+    _fields_ = [
+        ("n_obs", C.c_int64), ("prob_denovo", _f64p), ("max_posterior_vaf", _f64p), ("afd_offsets", _i64p),
+        ("afd_vaf", _f64p), ("afd_logp", _f64p), ("n_grid", C.c_int32), ("n_max_vafs", C.c_int32),
+        ("expected_max_somatic_vaf", _f64p), ("ln_prior", _f64p),
+    ]
+
+
+class ContaminationOutput(C.Structure):  # vlr_contamination_output_t
+    _fields_ = [("ln_posterior", _f64p), ("ln_likelihood", _f64p), ("ln_marginal", _f64p), ("max_vaf", _f64p)]
+
+
 def ptr(arr, ctype):
     """Pointer to a C-contiguous numpy array (or NULL for None)."""
     if arr is None:

@@ -31,6 +31,7 @@
 #define VLR_VAR_MAXD VLR_MAX_TREE_DEPTH
 #include "engine_core.cuh"
 #include "scenario_prep.h"
+#include "contamination.cuh"
 
 using namespace vlrcore;
 
@@ -710,6 +711,134 @@ vlr_status_t vlr_measure_fp64_peak(int32_t device, double* tflops) {
     if (cudaGetLastError() != cudaSuccess || best > 1e29f) return VLR_ERR_CUDA;
     *tflops = 2.0 * 8.0 * (double)iters * (double)blocks * threads / ((double)best * 1e-3) / 1e12;
     return VLR_OK;
+}
+
+// ---- contamination estimator (contamination.cuh) ----
+static vlr_status_t contamination_launch(int n_sms, const vlr_contamination_input_t* in, vlr_contamination_output_t* out,
+                                         double* d_scratch, size_t scratch_doubles, cudaStream_t s) {
+    using namespace vlrcontam;
+    const int n_events = in->n_grid * in->n_max_vafs;
+    const int gx = (n_events + CONTAM_THREADS - 1) / CONTAM_THREADS;
+    // chunks of observations: enough CTAs for ~4 per SM, at least 32 observations each
+    int64_t n_chunks = std::max<int64_t>(1, std::min<int64_t>((in->n_obs + 31) / 32, (int64_t)(4 * n_sms) / gx));
+    const int64_t chunk = std::max<int64_t>(1, (in->n_obs + n_chunks - 1) / n_chunks);
+    n_chunks = std::max<int64_t>(1, (in->n_obs + chunk - 1) / chunk);
+    if ((size_t)(1 + n_chunks * n_events) > scratch_doubles) return VLR_ERR_INVALID_ARGUMENT;
+    double* d_maxvaf = d_scratch;
+    double* d_partial = d_scratch + 1;
+    vlr_contam_maxvaf_kernel<<<1, 1024, 0, s>>>(in->max_posterior_vaf, in->n_obs, d_maxvaf, out->max_vaf);
+    Obs o{in->n_obs, in->prob_denovo, in->max_posterior_vaf, in->afd_offsets, in->afd_vaf, in->afd_logp};
+    vlr_contam_likelihood_kernel<<<dim3(gx, (unsigned)n_chunks), CONTAM_THREADS, 0, s>>>(
+        o, in->expected_max_somatic_vaf, in->n_max_vafs, in->n_grid, d_maxvaf, chunk, d_partial);
+    vlr_contam_finish_kernel<<<1, CONTAM_MAX_EVENTS, 0, s>>>(d_partial, (int)n_chunks, in->ln_prior, in->n_max_vafs,
+                                                            in->n_grid, out->ln_posterior, out->ln_likelihood,
+                                                            out->ln_marginal);
+    return cudaGetLastError() == cudaSuccess ? VLR_OK : VLR_ERR_CUDA;
+}
+
+static bool contamination_args_ok(const vlr_contamination_input_t* in, const vlr_contamination_output_t* out) {
+    if (!in || !out || !out->ln_posterior || !out->ln_marginal) return false;
+    if (in->n_obs < 0 || in->n_grid < 3 || in->n_grid % 2 == 0 || in->n_max_vafs < 1 ||
+        in->n_max_vafs > vlrcontam::CONTAM_MAX_ROWS || in->n_grid * in->n_max_vafs > vlrcontam::CONTAM_MAX_EVENTS)
+        return false;
+    if (!in->expected_max_somatic_vaf || !in->ln_prior) return false;
+    if (in->n_obs > 0 && (!in->prob_denovo || !in->max_posterior_vaf || !in->afd_offsets)) return false;
+    return true;
+}
+
+static vlr_status_t contamination_device_ok(int32_t device, int* n_sms) {
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        return VLR_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= n_dev || cudaSetDevice(device) != cudaSuccess) return VLR_ERR_INVALID_ARGUMENT;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return VLR_ERR_CUDA;
+    if (prop.major < 10) return VLR_ERR_UNSUPPORTED;
+    *n_sms = prop.multiProcessorCount;
+    return VLR_OK;
+}
+
+vlr_status_t vlr_contamination_posterior_device(int32_t device, const vlr_contamination_input_t* in,
+                                                vlr_contamination_output_t* out, void* cuda_stream) {
+    if (!contamination_args_ok(in, out)) return VLR_ERR_INVALID_ARGUMENT;
+    int n_sms = 0;
+    vlr_status_t st = contamination_device_ok(device, &n_sms);
+    if (st != VLR_OK) return st;
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    const size_t scratch = 1 + (size_t)(4 * n_sms + 1) * (size_t)(in->n_grid * in->n_max_vafs);
+    double* d_scratch = nullptr;
+    if (cudaMallocAsync(&d_scratch, scratch * sizeof(double), s) != cudaSuccess) {
+        cudaGetLastError();
+        return VLR_ERR_OUT_OF_MEMORY;
+    }
+    st = contamination_launch(n_sms, in, out, d_scratch, scratch, s);
+    cudaFreeAsync(d_scratch, s); // stream-ordered: released after the finishing kernel
+    return st;
+}
+
+vlr_status_t vlr_contamination_posterior(int32_t device, const vlr_contamination_input_t* in,
+                                         vlr_contamination_output_t* out) {
+    if (!contamination_args_ok(in, out)) return VLR_ERR_INVALID_ARGUMENT;
+    int n_sms = 0;
+    vlr_status_t st = contamination_device_ok(device, &n_sms);
+    if (st != VLR_OK) return st;
+    const int64_t n = in->n_obs, n_pts = n > 0 ? in->afd_offsets[n] : 0;
+    if (n_pts < 0 || (n_pts > 0 && (!in->afd_vaf || !in->afd_logp))) return VLR_ERR_INVALID_ARGUMENT;
+    const int n_events = in->n_grid * in->n_max_vafs;
+    const size_t scratch = 1 + (size_t)(4 * n_sms + 1) * (size_t)n_events;
+    // one device block: [prob_denovo n][mpv n][afd_vaf P][afd_logp P][emsv R][prior G][post E][lik E][marginal][maxvaf]
+    // [scratch] then the offsets (int64)
+    const size_t n_d = 2 * (size_t)n + 2 * (size_t)n_pts + in->n_max_vafs + in->n_grid + 2 * (size_t)n_events + 2 + scratch;
+    double* d = nullptr;
+    int64_t* d_off = nullptr;
+    cudaStream_t s = nullptr;
+    cudaError_t e = cudaSuccess;
+    auto done = [&](vlr_status_t r) {
+        if (s) cudaStreamDestroy(s);
+        cudaFree(d);
+        cudaFree(d_off);
+        if (r != VLR_OK) cudaGetLastError();
+        return r;
+    };
+    if (cudaMalloc(&d, n_d * sizeof(double)) != cudaSuccess || cudaMalloc(&d_off, ((size_t)n + 1) * sizeof(int64_t)) != cudaSuccess)
+        return done(VLR_ERR_OUT_OF_MEMORY);
+    if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return done(VLR_ERR_CUDA);
+    double* p = d;
+    auto put = [&](const double* src, size_t count) -> double* {
+        double* at = p;
+        p += count;
+        if (count && e == cudaSuccess) e = cudaMemcpyAsync(at, src, count * sizeof(double), cudaMemcpyHostToDevice, s);
+        return at;
+    };
+    vlr_contamination_input_t din = *in;
+    din.prob_denovo = put(in->prob_denovo, (size_t)n);
+    din.max_posterior_vaf = put(in->max_posterior_vaf, (size_t)n);
+    din.afd_vaf = put(in->afd_vaf, (size_t)n_pts);
+    din.afd_logp = put(in->afd_logp, (size_t)n_pts);
+    din.expected_max_somatic_vaf = put(in->expected_max_somatic_vaf, (size_t)in->n_max_vafs);
+    din.ln_prior = put(in->ln_prior, (size_t)in->n_grid);
+    vlr_contamination_output_t dout;
+    dout.ln_posterior = p;
+    dout.ln_likelihood = p + n_events;
+    dout.ln_marginal = p + 2 * n_events;
+    dout.max_vaf = p + 2 * n_events + 1;
+    double* d_scratch = p + 2 * n_events + 2;
+    if (n > 0 && e == cudaSuccess)
+        e = cudaMemcpyAsync(d_off, in->afd_offsets, ((size_t)n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s);
+    din.afd_offsets = d_off;
+    if (e != cudaSuccess) return done(VLR_ERR_CUDA);
+    st = contamination_launch(n_sms, &din, &dout, d_scratch, scratch, s);
+    if (st != VLR_OK) return done(st);
+    e = cudaMemcpyAsync(out->ln_posterior, dout.ln_posterior, n_events * sizeof(double), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess && out->ln_likelihood)
+        e = cudaMemcpyAsync(out->ln_likelihood, dout.ln_likelihood, n_events * sizeof(double), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out->ln_marginal, dout.ln_marginal, sizeof(double), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess && out->max_vaf)
+        e = cudaMemcpyAsync(out->max_vaf, dout.max_vaf, sizeof(double), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    return done(e == cudaSuccess ? VLR_OK : VLR_ERR_CUDA);
 }
 
 void* vlr_host_alloc(size_t bytes) {

@@ -57,6 +57,12 @@ def lib():
         l.vlr_status_string.argtypes = [C.c_int32]
         l.vlr_measure_fp64_peak.restype = C.c_int32
         l.vlr_measure_fp64_peak.argtypes = [C.c_int32, C.POINTER(C.c_double)]
+        l.vlr_contamination_posterior.restype = C.c_int32
+        l.vlr_contamination_posterior.argtypes = [C.c_int32, C.POINTER(abi.ContaminationInput),
+                                                  C.POINTER(abi.ContaminationOutput)]
+        l.vlr_contamination_posterior_device.restype = C.c_int32
+        l.vlr_contamination_posterior_device.argtypes = [C.c_int32, C.POINTER(abi.ContaminationInput),
+                                                         C.POINTER(abi.ContaminationOutput), C.c_void_p]
         if l.vlr_abi_version() != abi.VLR_ABI_VERSION:
             raise EngineError("ABI version mismatch between abi.py and libvlr_engine.so")
         _lib = l
@@ -65,7 +71,8 @@ def lib():
 
 EXPORTED_SYMBOLS = ["vlr_ctx_create", "vlr_ctx_destroy", "vlr_call_batch", "vlr_call_batch_device", "vlr_ctx_reserve",
                     "vlr_host_alloc", "vlr_host_free", "vlr_last_launch_count", "vlr_ctx_stream", "vlr_last_error",
-                    "vlr_status_string", "vlr_abi_version", "vlr_measure_fp64_peak"]
+                    "vlr_status_string", "vlr_abi_version", "vlr_measure_fp64_peak", "vlr_contamination_posterior",
+                    "vlr_contamination_posterior_device"]
 
 
 def measure_fp64_peak(device: int = 0) -> float:
