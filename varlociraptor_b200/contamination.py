@@ -53,14 +53,26 @@ class PriorEstimate:
     n_observed_cells: int
 
 
-@dataclass
 class VariantObservation:
-    """contamination.rs:35-42"""
-    prob_denovo: float
-    vaf_dist: List[Tuple[float, float]]  # ascending VAF (BTreeMap), ln posterior density
-    max_posterior_vaf: float
-    chrom: str
-    pos: int
+    """contamination.rs:35-42. The AFD (`vaf_dist`, a BTreeMap upstream) is kept as two ascending numpy columns so that
+    packing 10^5 observations for the device is a concatenation, not a Python loop over points."""
+    __slots__ = ("prob_denovo", "vafs", "densities", "max_posterior_vaf", "chrom", "pos")
+
+    def __init__(self, prob_denovo: float, vaf_dist, max_posterior_vaf: float, chrom: str, pos: int):
+        self.prob_denovo = float(prob_denovo)
+        self.max_posterior_vaf = float(max_posterior_vaf)
+        self.chrom, self.pos = chrom, pos
+        self.vaf_dist = vaf_dist
+
+    @property
+    def vaf_dist(self) -> List[Tuple[float, float]]:
+        """[(vaf, ln posterior density)] in ascending VAF order."""
+        return list(zip(self.vafs.tolist(), self.densities.tolist()))
+
+    @vaf_dist.setter
+    def vaf_dist(self, pairs) -> None:
+        a = np.asarray(list(pairs), dtype=np.float64).reshape(-1, 2)
+        self.vafs, self.densities = np.ascontiguousarray(a[:, 0]), np.ascontiguousarray(a[:, 1])
 
     @classmethod
     def new(cls, call: Call, sample_names: Sequence[str]) -> Optional["VariantObservation"]:
@@ -131,15 +143,9 @@ def pack_observations(observations: Sequence[VariantObservation]):
     """CSR columns of `vlr_contamination_input_t`."""
     n = len(observations)
     offsets = np.zeros(n + 1, dtype=np.int64)
-    for i, o in enumerate(observations):
-        offsets[i + 1] = offsets[i] + len(o.vaf_dist)
-    vaf = np.empty(int(offsets[-1]), dtype=np.float64)
-    logp = np.empty(int(offsets[-1]), dtype=np.float64)
-    for i, o in enumerate(observations):
-        if o.vaf_dist:
-            v, p = zip(*o.vaf_dist)
-            vaf[offsets[i]:offsets[i + 1]] = v
-            logp[offsets[i]:offsets[i + 1]] = p
+    np.cumsum([len(o.vafs) for o in observations], out=offsets[1:])
+    vaf = np.concatenate([o.vafs for o in observations]) if n else np.empty(0, dtype=np.float64)
+    logp = np.concatenate([o.densities for o in observations]) if n else np.empty(0, dtype=np.float64)
     prob_denovo = np.array([o.prob_denovo for o in observations], dtype=np.float64)
     mpv = np.array([o.max_posterior_vaf for o in observations], dtype=np.float64)
     return prob_denovo, mpv, offsets, vaf, logp
