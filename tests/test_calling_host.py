@@ -174,3 +174,31 @@ def test_golden_text_fields_with_emulated_engine(golden_dir):
             assert sorted(re.findall(r"\d+[A-Za-z]", f[key])) == sorted(re.findall(r"\d+[A-Za-z]", e[key])), (key, f[key], e[key])
         n += 1
     assert n == 8
+
+
+def test_haplotype_groups_reuse_the_first_members_result(tn_records):
+    """calling.rs:569-580, 726-741: records sharing INFO/EVENT (or a breakend MATEID pair) are computed once."""
+    tumor, normal, _ = tn_records
+    import copy
+    tumor, normal = copy.deepcopy(tumor), copy.deepcopy(normal)
+    for recs in (tumor, normal):
+        recs[2]["info"]["EVENT"] = "ev1"
+        recs[7]["info"]["EVENT"] = "ev1"        # reuses record 2's result although its own reads differ
+        recs[4]["id"], recs[4]["info"]["MATEID"] = "bnd_b", "bnd_a"
+        recs[9]["id"], recs[9]["info"]["MATEID"] = "bnd_a", "bnd_b"
+    assert calling.haplotype_identifier(tumor[4]) == calling.haplotype_identifier(tumor[9]) == "bnd_a-bnd_b"
+    sc = Scenario.tumor_normal(0.75)
+    eng = EmuEngine(sc.flatten())
+    seen = []
+    orig = eng.call_batch
+    eng.call_batch = lambda batch, afd_capacity=0, out=None: (seen.append(batch.n_loci), orig(batch, afd_capacity))[1]
+    w = calling.call_generic(sc, {"tumor": tumor, "normal": normal}, engine=eng, batch_size=5)
+    assert [c.pos for c in w.calls] == [r["pos"] for r in tumor]          # input order kept
+    assert sum(seen) == len(tumor) - 2                                     # two records were never packed
+    assert w.calls[7].event_probs == w.calls[2].event_probs and w.calls[7].sample_info == w.calls[2].sample_info
+    assert w.calls[9].event_probs == w.calls[4].event_probs
+    ref = calling.call_generic(sc, {"tumor": tn_records[0], "normal": tn_records[1]}, engine=EmuEngine(sc.flatten()))
+    assert ref.calls[7].event_probs != w.calls[7].event_probs              # it really is the group's result
+    assert ref.calls[3].event_probs == w.calls[3].event_probs
+    with pytest.raises(ValueError, match="without record ID"):
+        calling.haplotype_identifier({"info": {"MATEID": "x"}, "id": "."})

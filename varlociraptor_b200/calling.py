@@ -135,6 +135,23 @@ class WorkItem:
     alt: str
     pileups: LocusBatch
     locus_flags: int
+    haplotype: Optional[str] = None  # EVENT / breakend group: later members reuse the first member's result
+
+
+def haplotype_identifier(record: dict) -> Optional[str]:
+    """`HaplotypeIdentifier::from` (src/variants/model/mod.rs:87-133): INFO/EVENT, else the sorted pair of record id and
+    INFO/MATEID joined by '-' (breakend mates); a MATEID without a record id is an error upstream too."""
+    info = record.get("info", {})
+    event = info.get("EVENT")
+    if event is not None:
+        return str(event).split(",")[0]
+    mateid = info.get("MATEID")
+    if mateid is not None:
+        recid = record.get("id", ".")
+        if recid in (".", "", None):
+            raise ValueError("breakend with MATEID but without record ID")  # errors::Error::BreakendMateidWithoutRecid
+        return "-".join(sorted([str(recid), str(mateid).split(",")[0]]))
+    return None
 
 
 class CandidateFilter:
@@ -207,6 +224,7 @@ class Caller:
             from .engine import PosteriorEngine
             engine = PosteriorEngine(self.flat, device=device)
         self.engine = engine
+        self._haplotype_results: Dict[str, Optional[Call]] = {}
 
     def _records(self) -> Iterator[List[Optional[dict]]]:
         """One record per sample in lock-step (calling.rs:353-398): same chrom/pos/alleles required."""
@@ -242,7 +260,7 @@ class Caller:
             one = obs_codec.batch_from_records([[r] for r in recs], **self.omit)
             first = next(r for r in recs if r is not None)
             item = WorkItem(index, first["chrom"], first["pos"], first["ref"], first["alt"], one,
-                            int(one.locus_flags[0]))
+                            int(one.locus_flags[0]), haplotype_identifier(first))
             index += 1
             if not self.candidate_filter.filter(item, self.sample_names):
                 continue
@@ -255,11 +273,31 @@ class Caller:
         self.call_processor.finalize()
 
     def _flush(self, pending):
-        batch = LocusBatch.concat([b for _, b in pending])
-        res: CallResults = self.engine.call_batch(batch, afd_capacity=self.afd_capacity)
+        # Breakend / haplotype groups (calling.rs:569-580, 726-741, 820-839): only the first member of a group is
+        # computed; the others take its event probabilities and sample infos. Upstream drops the stored result after
+        # the member with the last record index; groups are keyed here for the whole run, which is the same as long
+        # as an identifier is not reused by a later, unrelated group.
+        computed = []
+        for k, (item, _) in enumerate(pending):
+            if item.haplotype is None or item.haplotype not in self._haplotype_results:
+                computed.append(k)
+                if item.haplotype is not None:
+                    self._haplotype_results[item.haplotype] = None  # claimed by this record, filled below
+        slot = {k: i for i, k in enumerate(computed)}
+        res: Optional[CallResults] = None
+        if computed:
+            batch = LocusBatch.concat([pending[k][1] for k in computed])
+            res = self.engine.call_batch(batch, afd_capacity=self.afd_capacity)
         S = len(self.sample_names)
         names = self.flat.event_names
-        for i, (item, one) in enumerate(pending):
+        for k, (item, one) in enumerate(pending):
+            if k not in slot:
+                first = self._haplotype_results[item.haplotype]
+                call = Call(item.chrom, item.pos, item.ref, item.alt, dict(first.event_probs), list(first.sample_info),
+                            status=first.status)
+                self.call_processor.process_call(call, self.sample_names)
+                continue
+            i = slot[k]
             call = Call(item.chrom, item.pos, item.ref, item.alt, status=int(res.status[i]))
             for e, name in enumerate(names):
                 call.event_probs[name] = float(res.log_posteriors[i, e])
@@ -290,6 +328,8 @@ class Caller:
                 call.sample_info.append(SampleCall(float(res.map_vaf[i, s]), abi.ARTIFACT_CONFIG_NAMES[cfg], dist, depth,
                                                    simple_observations(pa, pr, mq, True),
                                                    simple_observations(pa, pr, mq, False)))
+            if item.haplotype is not None:
+                self._haplotype_results[item.haplotype] = call
             self.call_processor.process_call(call, self.sample_names)
 
 

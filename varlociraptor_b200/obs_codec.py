@@ -161,7 +161,8 @@ def parse_observation_vcf(path: str) -> List[dict]:
                         info[k] = v
                 else:
                     flags.add(kv)
-            out.append({"chrom": t[0], "pos": int(t[1]), "ref": t[3], "alt": t[4], "info": info, "flags": flags})
+            out.append({"chrom": t[0], "pos": int(t[1]), "id": t[2], "ref": t[3], "alt": t[4], "info": info,
+                        "flags": flags})
     return out
 
 
