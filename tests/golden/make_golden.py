@@ -7,7 +7,8 @@ Outputs (committed):
   flamegraph_obs.npz        the 11 preprocessed loci of tests/resources/flamegraph_profiling/normal.vcf
                             decoded into the SoA batch layout (inputs of `call variants`)
   flamegraph_expected.json  what the reference printed for them (calls.vcf): PROB_* (PHRED f32),
-                            AF, AFD text, DP, SAOBS/SROBS, plus the scenario
+                            AF, AFD text, DP, SAOBS/SROBS/OBS/OOBS, the raw
+                            THIRD_ALLELE_EVIDENCE INFO arrays, plus the scenario
   raw_info_records.json     verbatim INFO integer arrays of three reference records (codec round trip)
   real_pileups.npz/.json    single-sample observation-format-15 pileups embedded in
                             tests/resources/testcases/*/candidates.vcf (inputs only) with their scenario text
@@ -43,10 +44,12 @@ def flamegraph():
             expected.append({"chrom": t[0], "pos": int(t[1]), "info": {k: v for k, v in info.items()
                                                                        if k.startswith("PROB_")},
                              "DP": int(fmt["DP"]), "AF": float(fmt["AF"]), "SAOBS": fmt["SAOBS"],
-                             "SROBS": fmt["SROBS"], "AFD": afd})
+                             "SROBS": fmt["SROBS"], "OBS": fmt["OBS"], "OOBS": fmt["OOBS"], "AFD": afd})
     with open(os.path.join(d, "scenario.yaml")) as f:
         scenario = f.read()
     assert [r["pos"] for r in recs] == [e["pos"] for e in expected]
+    for r, e in zip(recs, expected):  # output-only column the SoA batch does not carry (feeds FORMAT/OBS)
+        e["THIRD_ALLELE_EVIDENCE"] = r["info"]["THIRD_ALLELE_EVIDENCE"]
     with open(os.path.join(HERE, "flamegraph_expected.json"), "w") as f:
         json.dump({"source": "tests/resources/flamegraph_profiling/{normal.vcf,calls.vcf,scenario.yaml}",
                    "scenario_yaml": scenario, "records": expected}, f, indent=1)

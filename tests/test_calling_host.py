@@ -98,7 +98,7 @@ def test_call_generic_orders_batches_and_formats(tn_records):
         assert c.sample_info[1].allelefreq_estimate == want.map_vaf[i, 1]
         assert c.sample_info[0].depth == 20
     lines = writer.lines()
-    assert len(lines) == 12 and lines[0].split("\t")[8] == "DP:AF:SAOBS:SROBS:SB:ROB:RPB:SCB:HE:ALB:AFD"
+    assert len(lines) == 12 and lines[0].split("\t")[8] == "DP:AF:SAOBS:SROBS:OBS:OOBS:SB:ROB:RPB:SCB:HE:ALB:AFD"
 
 
 def test_candidate_filter_and_missing_sample(tn_records):
@@ -148,6 +148,7 @@ def test_golden_text_fields_with_emulated_engine(golden_dir):
     recs = _records_from_batch(b)
     for r, e in zip(recs, exp["records"]):
         r["pos"], r["ref"], r["alt"] = e["pos"], "CG", "<METH>"
+        r["info"]["THIRD_ALLELE_EVIDENCE"] = e["THIRD_ALLELE_EVIDENCE"]
     sc = Scenario.from_yaml(exp["scenario_yaml"])
     w = calling.call_generic(sc, {"normal": recs}, engine=EmuEngine(sc.flatten()))
     n = 0
@@ -170,8 +171,10 @@ def test_golden_text_fields_with_emulated_engine(golden_dir):
         assert f["SB"] == "." and f["ALB"] == "."
         # SAOBS / SROBS: same (count, letter) entries; entries with equal counts come out of a hash map upstream
         import re
-        for key in ("SAOBS", "SROBS"):
-            assert sorted(re.findall(r"\d+[A-Za-z]", f[key])) == sorted(re.findall(r"\d+[A-Za-z]", e[key])), (key, f[key], e[key])
+        PAT = {"SAOBS": r"\d+[A-Za-z]", "SROBS": r"\d+[A-Za-z]", "OBS": r"\d+[A-Za-z]{1,2}(?:\d+|\.)[ps][#*.][*+.-][><*!][\^*][$.][*.]"}
+        assert f["OOBS"] == e["OOBS"]
+        for key in ("SAOBS", "SROBS", "OBS"):
+            assert sorted(re.findall(PAT[key], f[key])) == sorted(re.findall(PAT[key], e[key])), (key, f[key], e[key])
         n += 1
     assert n == 8
 

@@ -63,6 +63,38 @@ def simple_observations(prob_alt, prob_ref, is_max_mapq, alt_allele: bool) -> st
     return "".join("%d%s" % (n, it) for it, n in common)
 
 
+def read_observation_summary(prob_alt, prob_ref, read_flags, third_allele=None) -> str:
+    """FORMAT/OBS (src/calling/variants/mod.rs:277-333): generalized CIGAR over one code per read -
+    max Bayes factor (`A`/`R` + Kass-Raftery letter or `E`, upper case iff maximum MAPQ), third-allele edit distance
+    or '.', p(aired)/s(ingle), alt locus (#, *, .), strand (*, -, +, .), read orientation (>, <, *, !), read position
+    (^, *), softclip ($, .), homopolymer error (*, .); most common first, then `E...` codes, then `N...` codes."""
+    from collections import Counter
+    items = []
+    has3, val3 = third_allele if third_allele is not None else (None, None)
+    for k, (pa, pr, f) in enumerate(zip(prob_alt, prob_ref, read_flags)):
+        f = int(f)
+        if pa > pr:      # bf_alt > bf_ref  <=>  prob_alt > prob_ref (exp is monotone; equal -> Equal)
+            score = "A" + _kass_raftery_letter(pa, pr)
+        elif pr > pa:
+            score = "R" + _kass_raftery_letter(pr, pa)
+        else:
+            score = "E"
+        score = score.upper() if f & abi.RF_MAX_MAPQ else score.lower()
+        third = str(int(val3[k])) if has3 is not None and k < len(has3) and has3[k] else "."
+        altlocus = "#*."[(f >> abi.RF_ALTLOCUS_SHIFT) & 3]
+        strand = "+-*."[(f >> abi.RF_STRAND_SHIFT) & 3]          # Forward, Reverse, Both, None
+        orient = {0: ">", 1: "<", 8: "*"}.get((f >> abi.RF_ORIENT_SHIFT) & 15, "!")
+        hom = bool(f & abi.RF_HAS_HOMOPOLYMER_LEN) and ((f >> abi.RF_HOMOPOLYMER_LEN_SHIFT) & 0xff) != 0
+        items.append("%s%s%s%s%s%s%s%s%s" % (score, third, "p" if f & abi.RF_PAIRED else "s", altlocus, strand, orient,
+                                               "^" if f & abi.RF_READPOS_MAJOR else "*",
+                                               "$" if f & abi.RF_SOFTCLIPPED else ".", "*" if hom else "."))
+    if not items:
+        return "."
+    common = Counter(items).most_common()
+    common.sort(key=lambda kv: 2 if kv[0].startswith("N") else (1 if kv[0].startswith("E") else 0))  # stable
+    return "".join("%d%s" % (n, it) for it, n in common)
+
+
 def event_tag_name(event: str) -> str:
     """src/utils/mod.rs `event_tag_name`: PROB_<EVENT upper-cased>."""
     return "PROB_" + event.upper()
@@ -77,6 +109,8 @@ class SampleCall:
     depth: int               # DP = round(sum(exp(prob_mapping)))
     saobs: str = "."         # SAOBS / SROBS: simplified observation summaries (mod.rs:337-379)
     srobs: str = "."
+    obs: str = "."           # OBS: full per-read codes (mod.rs:277-333)
+    oobs: int = 0            # OOBS: reads dropped by remove_nonstandard_alignments (pileup.rs:26-43, mod.rs:382)
 
 
 @dataclass
@@ -97,7 +131,7 @@ class Call:
     def format_fields(self, sample: int) -> Dict[str, str]:
         si = self.sample_info[sample]
         if si is None:
-            return {"DP": ".", "AF": ".", "AFD": "."}
+            return {"DP": ".", "AF": ".", "AFD": ".", "OBS": ".", "OOBS": "."}
         labels = {"SB": ".", "ROB": ".", "RPB": ".", "SCB": ".", "HE": ".", "ALB": "."}
         a = si.artifact
         if a == "SB_FWD":
@@ -119,7 +153,7 @@ class Call:
         afd = "." if si.vaf_dist is None else ",".join(
             "%.3f=%.2f" % (v, _PHRED * p) for v, p in si.vaf_dist)  # mod.rs:546-556
         out = {"DP": str(si.depth), "AF": "%g" % np.float32(si.allelefreq_estimate), "AFD": afd,
-               "SAOBS": si.saobs, "SROBS": si.srobs}
+               "SAOBS": si.saobs, "SROBS": si.srobs, "OBS": si.obs, "OOBS": str(si.oobs)}
         out.update(labels)
         return out
 
@@ -136,6 +170,7 @@ class WorkItem:
     pileups: LocusBatch
     locus_flags: int
     haplotype: Optional[str] = None  # EVENT / breakend group: later members reuse the first member's result
+    third_allele_evidence: Optional[list] = None  # per sample (is_some, value) arrays or None; output only (OBS)
 
 
 def haplotype_identifier(record: dict) -> Optional[str]:
@@ -192,7 +227,7 @@ class CallWriter(CallProcessor):
         out = []
         for c in self.calls:
             info = ";".join("%s=%s" % (k, "inf" if np.isinf(v) else "%g" % v) for k, v in c.info_fields().items())
-            keys = ["DP", "AF", "SAOBS", "SROBS", "SB", "ROB", "RPB", "SCB", "HE", "ALB", "AFD"]
+            keys = ["DP", "AF", "SAOBS", "SROBS", "OBS", "OOBS", "SB", "ROB", "RPB", "SCB", "HE", "ALB", "AFD"]
             fmt = []
             for s in range(len(c.sample_info)):
                 f = c.format_fields(s)
@@ -260,7 +295,9 @@ class Caller:
             one = obs_codec.batch_from_records([[r] for r in recs], **self.omit)
             first = next(r for r in recs if r is not None)
             item = WorkItem(index, first["chrom"], first["pos"], first["ref"], first["alt"], one,
-                            int(one.locus_flags[0]), haplotype_identifier(first))
+                            int(one.locus_flags[0]), haplotype_identifier(first),
+                            [obs_codec.decode_optional_u32(r["info"]["THIRD_ALLELE_EVIDENCE"])
+                             if r is not None and "THIRD_ALLELE_EVIDENCE" in r["info"] else None for r in recs])
             index += 1
             if not self.candidate_filter.filter(item, self.sample_names):
                 continue
@@ -319,7 +356,11 @@ class Caller:
                 depth = int(round(float(np.exp(one.columns["prob_mapping"][lo:hi][keep].astype(np.float64)).sum())))
                 pa = one.columns["prob_alt"][lo:hi][keep].astype(np.float64)
                 pr = one.columns["prob_ref"][lo:hi][keep].astype(np.float64)
-                mq = (one.read_flags[lo:hi][keep] & abi.RF_MAX_MAPQ) != 0
+                rf = one.read_flags[lo:hi][keep]
+                mq = (rf & abi.RF_MAX_MAPQ) != 0
+                third = item.third_allele_evidence[s] if item.third_allele_evidence else None
+                if third is not None:
+                    third = (third[0][keep], third[1][keep])
                 cfg = int(res.map_config[i])
                 dist = None
                 if cfg == 0 and res.afd_count is not None:
@@ -327,7 +368,9 @@ class Caller:
                     dist = list(zip(v.tolist(), p.tolist()))
                 call.sample_info.append(SampleCall(float(res.map_vaf[i, s]), abi.ARTIFACT_CONFIG_NAMES[cfg], dist, depth,
                                                    simple_observations(pa, pr, mq, True),
-                                                   simple_observations(pa, pr, mq, False)))
+                                                   simple_observations(pa, pr, mq, False),
+                                                   read_observation_summary(pa, pr, rf, third),
+                                                   int((~keep).sum())))
             if item.haplotype is not None:
                 self._haplotype_results[item.haplotype] = call
             self.call_processor.process_call(call, self.sample_names)

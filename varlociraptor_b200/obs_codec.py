@@ -99,6 +99,19 @@ def decode_optional_i8(ints: Sequence[int]) -> Tuple[np.ndarray, np.ndarray]:
     return has, val
 
 
+def decode_optional_u32(ints: Sequence[int]) -> Tuple[np.ndarray, np.ndarray]:
+    """Vec<Option<u32>> (THIRD_ALLELE_EVIDENCE, preprocessing/mod.rs:818-1038) -> (is_some, value)."""
+    r = _Reader(ints)
+    n = r.u64()
+    has = np.zeros(n, dtype=bool)
+    val = np.zeros(n, dtype=np.uint32)
+    for k in range(n):
+        if r.u8():
+            has[k] = True
+            val[k] = r.u32()
+    return has, val
+
+
 def decode_bitvec(ints: Sequence[int]) -> np.ndarray:
     r = _Reader(ints)
     blocks = b""

@@ -772,6 +772,7 @@ class Scenario:
         for c in cubes:
             lits = sorted(c, key=cls._sort_key)
             terms.append(lits[0] if len(lits) == 1 else And(tuple(lits)))
+        terms.sort(key=cls._sort_key)  # cubes come out of sets: fix the order
         return terms[0] if len(terms) == 1 else Or(tuple(terms))
 
     def normalize(self, f):
