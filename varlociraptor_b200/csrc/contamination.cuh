@@ -55,8 +55,7 @@ VLR_DEV double obs_term(double prob_denovo, double mpv, double max_vaf, double e
     return obs_pdf(vaf, logp, n, emsv * purity * quantile);
 }
 
-constexpr int CONTAM_THREADS = 128;
-constexpr int CONTAM_TILE_PTS = 2048; // AFD points staged per tile (32 KB of shared memory)
+constexpr int CONTAM_MAX_THREADS = 512; // events per CTA column (blockDim.x is chosen by the launcher)
 constexpr int CONTAM_TILE_OBS = 128;
 
 #ifndef VLR_HOST_EMU
@@ -81,10 +80,13 @@ vlr_contam_maxvaf_kernel(const double* __restrict__ mpv, int64_t n_obs, double* 
     }
 }
 
-// grid = (ceil(n_events / CONTAM_THREADS), n_chunks); partial[chunk][event]
-__global__ void __launch_bounds__(CONTAM_THREADS)
+// grid = (ceil(n_events / blockDim.x), n_chunks); partial[chunk][event]. CONTAM_TILE_PTS = AFD points staged per tile
+// (16 B each of shared memory).
+template <int CONTAM_TILE_PTS>
+__global__ void __launch_bounds__(CONTAM_MAX_THREADS)
 vlr_contam_likelihood_kernel(Obs in, const double* __restrict__ emsv, int n_emsv, int n_grid,
                              const double* __restrict__ max_vaf_p, int64_t chunk, double* __restrict__ partial) {
+    const int CONTAM_THREADS = blockDim.x;
     __shared__ double s_vaf[CONTAM_TILE_PTS], s_lp[CONTAM_TILE_PTS];
     __shared__ double s_pd[CONTAM_TILE_OBS], s_mpv[CONTAM_TILE_OBS];
     __shared__ int s_off[CONTAM_TILE_OBS + 1];

@@ -714,13 +714,31 @@ vlr_status_t vlr_measure_fp64_peak(int32_t device, double* tflops) {
 }
 
 // ---- contamination estimator (contamination.cuh) ----
+// Launch geometry of the likelihood kernel: events per CTA column, AFD points per shared-memory tile, CTA rows per SM.
+// VLR_CONTAM_GEOM="threads,tile,rows_per_sm" overrides it for measurements (tile: 1024 or 2048).
+struct ContamGeom {
+    int threads, tile, rows_per_sm;
+};
+static ContamGeom contamination_geometry(int n_events) {
+    ContamGeom g{416, 1024, 4}; // measured best of five (profiles/README.md): one column holds all 404 events
+    if (const char* e = getenv("VLR_CONTAM_GEOM")) {
+        int t = 0, tile = 0, r = 0;
+        if (sscanf(e, "%d,%d,%d", &t, &tile, &r) == 3 && t >= 32 && t <= vlrcontam::CONTAM_MAX_THREADS && t % 32 == 0 &&
+            (tile == 1024 || tile == 2048) && r >= 1 && r <= 32)
+            g = ContamGeom{t, tile, r};
+    }
+    if (g.threads > ((n_events + 31) & ~31)) g.threads = (n_events + 31) & ~31;
+    return g;
+}
+
 static vlr_status_t contamination_launch(int n_sms, const vlr_contamination_input_t* in, vlr_contamination_output_t* out,
                                          double* d_scratch, size_t scratch_doubles, cudaStream_t s) {
     using namespace vlrcontam;
     const int n_events = in->n_grid * in->n_max_vafs;
-    const int gx = (n_events + CONTAM_THREADS - 1) / CONTAM_THREADS;
-    // chunks of observations: enough CTAs for ~4 per SM, at least 32 observations each
-    int64_t n_chunks = std::max<int64_t>(1, std::min<int64_t>((in->n_obs + 31) / 32, (int64_t)(4 * n_sms) / gx));
+    const ContamGeom g = contamination_geometry(n_events);
+    const int gx = (n_events + g.threads - 1) / g.threads;
+    // chunks of observations: g.rows_per_sm CTA rows per SM, at least 32 observations each
+    int64_t n_chunks = std::max<int64_t>(1, std::min<int64_t>((in->n_obs + 31) / 32, (int64_t)g.rows_per_sm * n_sms));
     const int64_t chunk = std::max<int64_t>(1, (in->n_obs + n_chunks - 1) / n_chunks);
     n_chunks = std::max<int64_t>(1, (in->n_obs + chunk - 1) / chunk);
     if ((size_t)(1 + n_chunks * n_events) > scratch_doubles) return VLR_ERR_INVALID_ARGUMENT;
@@ -728,13 +746,20 @@ static vlr_status_t contamination_launch(int n_sms, const vlr_contamination_inpu
     double* d_partial = d_scratch + 1;
     vlr_contam_maxvaf_kernel<<<1, 1024, 0, s>>>(in->max_posterior_vaf, in->n_obs, d_maxvaf, out->max_vaf);
     Obs o{in->n_obs, in->prob_denovo, in->max_posterior_vaf, in->afd_offsets, in->afd_vaf, in->afd_logp};
-    vlr_contam_likelihood_kernel<<<dim3(gx, (unsigned)n_chunks), CONTAM_THREADS, 0, s>>>(
-        o, in->expected_max_somatic_vaf, in->n_max_vafs, in->n_grid, d_maxvaf, chunk, d_partial);
+    const dim3 grid(gx, (unsigned)n_chunks);
+    if (g.tile == 1024)
+        vlr_contam_likelihood_kernel<1024><<<grid, g.threads, 0, s>>>(o, in->expected_max_somatic_vaf, in->n_max_vafs,
+                                                                     in->n_grid, d_maxvaf, chunk, d_partial);
+    else
+        vlr_contam_likelihood_kernel<2048><<<grid, g.threads, 0, s>>>(o, in->expected_max_somatic_vaf, in->n_max_vafs,
+                                                                     in->n_grid, d_maxvaf, chunk, d_partial);
     vlr_contam_finish_kernel<<<1, CONTAM_MAX_EVENTS, 0, s>>>(d_partial, (int)n_chunks, in->ln_prior, in->n_max_vafs,
                                                             in->n_grid, out->ln_posterior, out->ln_likelihood,
                                                             out->ln_marginal);
     return cudaGetLastError() == cudaSuccess ? VLR_OK : VLR_ERR_CUDA;
 }
+
+constexpr int CONTAM_MAX_ROWS_PER_SM = 32; // bound of ContamGeom::rows_per_sm, sizes the partial-sum scratch
 
 static bool contamination_args_ok(const vlr_contamination_input_t* in, const vlr_contamination_output_t* out) {
     if (!in || !out || !out->ln_posterior || !out->ln_marginal) return false;
@@ -767,7 +792,7 @@ vlr_status_t vlr_contamination_posterior_device(int32_t device, const vlr_contam
     vlr_status_t st = contamination_device_ok(device, &n_sms);
     if (st != VLR_OK) return st;
     cudaStream_t s = (cudaStream_t)cuda_stream;
-    const size_t scratch = 1 + (size_t)(4 * n_sms + 1) * (size_t)(in->n_grid * in->n_max_vafs);
+    const size_t scratch = 1 + (size_t)(CONTAM_MAX_ROWS_PER_SM * n_sms + 1) * (size_t)(in->n_grid * in->n_max_vafs);
     double* d_scratch = nullptr;
     if (cudaMallocAsync(&d_scratch, scratch * sizeof(double), s) != cudaSuccess) {
         cudaGetLastError();
@@ -787,7 +812,7 @@ vlr_status_t vlr_contamination_posterior(int32_t device, const vlr_contamination
     const int64_t n = in->n_obs, n_pts = n > 0 ? in->afd_offsets[n] : 0;
     if (n_pts < 0 || (n_pts > 0 && (!in->afd_vaf || !in->afd_logp))) return VLR_ERR_INVALID_ARGUMENT;
     const int n_events = in->n_grid * in->n_max_vafs;
-    const size_t scratch = 1 + (size_t)(4 * n_sms + 1) * (size_t)n_events;
+    const size_t scratch = 1 + (size_t)(CONTAM_MAX_ROWS_PER_SM * n_sms + 1) * (size_t)n_events;
     // one device block: [prob_denovo n][mpv n][afd_vaf P][afd_logp P][emsv R][prior G][post E][lik E][marginal][maxvaf]
     // [scratch] then the offsets (int64)
     const size_t n_d = 2 * (size_t)n + 2 * (size_t)n_pts + in->n_max_vafs + in->n_grid + 2 * (size_t)n_events + 2 + scratch;
