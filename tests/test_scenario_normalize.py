@@ -1,6 +1,8 @@
 """Formula::normalize (src/grammar/formula.rs:473-485) against the reference's own normalisation tests
 (formula.rs:1621-1735), re-expressed on varlociraptor_b200.scenario, plus the effects of the BDD
 simplification step (formula.rs:710-714) on the VAF trees the engine receives."""
+import os
+
 import pytest
 
 from varlociraptor_b200 import abi
@@ -157,3 +159,50 @@ def test_ploidy_follows_contig_and_sex():  # grammar/mod.rs:288-342, 581-593
     assert y.ploidy("tumor") == 0 and y.universe("tumor") == [frozenset([0.0])]
     with pytest.raises(ValueError):
         Scenario.from_yaml(MERGE_ATOMS_YAML.replace("        all: 2\n", "")).ploidy("normal")
+
+
+def test_universe_follows_contig():  # UniverseDefinition::Map (grammar/mod.rs:508-520, 651-654)
+    sc = Scenario.from_yaml("""
+samples:
+  a:
+    universe: "[0.0,1.0]"
+  b:
+    universe:
+      all: "[0.0,1.0]"
+      Y: "0.0 | 1.0"
+events:
+  both: "a:]0.0,1.0] & !b:0.0"
+  not_half: "!b:0.5"
+""")
+    assert sc.universe("b") == [VAFRange(0.0, 1.0, False, False)]
+    assert _norm(sc, "not_half") == Or((Atom("b", VAFRange(0.0, 0.5, False, True)),
+                                        Atom("b", VAFRange(0.5, 1.0, True, False))))
+    # upstream quirk, mirrored: splitting [0,1] at its own inclusive start keeps the singleton {0} on the left
+    # (`split_at`'s emptiness test looks at the wrong bounds, formula.rs:1120-1131), so !b:0.0 still contains b:0.0
+    a = Atom("a", VAFRange(0.0, 1.0, True, False))
+    assert _norm(sc, "both") == Or((And((a, Atom("b", frozenset([0.0])))), And((a, Atom("b", VAFRange(0.0, 1.0, True, False))))))
+    y = sc.for_contig("Y")
+    assert y.universe("b") == [frozenset([0.0]), frozenset([1.0])]
+    assert _norm(y, "both") == And((a, Atom("b", frozenset([1.0]))))
+    assert _norm(y, "not_half") == Atom("b", frozenset([0.0, 1.0]))  # set differences, merged by the disjunction
+    assert y.flatten().c.samples[1].uniform_prior == 1
+    with pytest.raises(ValueError):
+        Scenario.from_yaml('samples:\n  a:\n    universe:\n      X: "0.0"\nevents:\n  e: "a:0.0"\n').universe("a")
+
+
+REFERENCE_RESOURCES = "/root/reference/tests/resources"
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE_RESOURCES), reason="reference checkout not present (GPU box)")
+def test_every_scenario_of_the_reference_test_suite_normalises_and_flattens():
+    """All scenario files under the reference's tests/resources go through parse -> normalize -> VAF trees -> C-ABI
+    structs; events of one scenario must stay pairwise distinct after normalisation."""
+    import glob
+    files = sorted(glob.glob(os.path.join(REFERENCE_RESOURCES, "**", "*scenario*.y*ml"), recursive=True))
+    assert len(files) >= 100
+    for path in files:
+        sc = Scenario.from_yaml(open(path).read())
+        flat = sc.flatten()
+        assert flat.n_events == len(sc.events) + (0 if "absent" in sc.events else 1), path
+        normal = [repr(sc.normalize(f)) for f in sc.event_formulas.values()]
+        assert len(set(normal)) == len(normal), path

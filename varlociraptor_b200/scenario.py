@@ -343,7 +343,7 @@ class Inheritance:
 @dataclass
 class SampleDef:
     resolution: float = 0.01
-    universe: Optional[List[Spectrum]] = None
+    universe: Union[None, List[Spectrum], Dict[str, List[Spectrum]]] = None  # per contig when a dict
     contamination: Optional[Contamination] = None
     somatic_effective_mutation_rate: Optional[float] = None
     germline_mutation_rate: Optional[float] = None
@@ -426,8 +426,9 @@ class Scenario:
             s = SampleDef()
             if "resolution" in d:
                 s.resolution = float(d["resolution"])
-            if "universe" in d:
-                s.universe = parse_universe(d["universe"])
+            if "universe" in d:  # UniverseDefinition::{Simple, Map} (mod.rs:651-654)
+                u = d["universe"]
+                s.universe = {c: parse_universe(t) for c, t in u.items()} if isinstance(u, dict) else parse_universe(u)
             if "contamination" in d:
                 s.contamination = Contamination(d["contamination"]["by"], float(d["contamination"]["fraction"]))
             s.somatic_effective_mutation_rate = _opt_float(d.get("somatic-effective-mutation-rate"))
@@ -517,6 +518,12 @@ class Scenario:
 
     def universe(self, name: str) -> List[Spectrum]:
         s = self.samples[name]
+        if isinstance(s.universe, dict):  # per-contig universes fall back to "all" (mod.rs:511-519)
+            if self.contig in s.universe:
+                return list(s.universe[self.contig])
+            if "all" not in s.universe:
+                raise ValueError("universe definition for contig %s not found" % self.contig)
+            return list(s.universe["all"])
         if s.universe is not None:
             return list(s.universe)
         ploidy = self.ploidy(name)
