@@ -13,8 +13,43 @@ def test_cpp_caller_with_mock_engine(tmp_path):
     assert "host caller mock test: ok" in out
 
 
+def test_cpp_contamination_estimator_with_mock_model(tmp_path):
+    """host/vlr_contamination.hpp: selection, CSR packing, prior, table and filter against a mock of the C-ABI entry."""
+    exe = str(tmp_path / "test_contamination_mock")
+    src = os.path.join(ROOT, "tests", "host", "test_contamination_mock.cpp")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-o", exe, src])
+    assert "host contamination mock test: ok" in subprocess.check_output([exe], text=True)
+
+
+def _build_contamination_link(tmp_path):
+    from varlociraptor_b200 import build as vbuild
+    lib = vbuild.build()
+    exe = str(tmp_path / "test_contamination_link")
+    src = os.path.join(ROOT, "tests", "host", "test_contamination_link.cpp")
+    libdir = os.path.dirname(lib)
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-o", exe, src, "-L" + libdir,
+                           "-lvlr_engine", "-Wl,-rpath," + libdir])
+    return exe
+
+
+def test_cpp_contamination_estimator_refuses_without_device(tmp_path):
+    """The real library behind the C++ estimator: no device, no result (there is no CPU path)."""
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("GPU present")
+    out = subprocess.check_output([_build_contamination_link(tmp_path)], text=True)
+    assert "refused: vlr_contamination_posterior failed with status 5" in out
+
+
 import numpy as np
 import pytest
+
+
+@pytest.mark.gpu
+def test_cpp_contamination_estimator_on_gpu(tmp_path):
+    out = subprocess.check_output([_build_contamination_link(tmp_path)], text=True)
+    assert "posterior integrates to 1.0000000" in out or "posterior integrates to 0.9999999" in out
 
 
 @pytest.mark.gpu
