@@ -192,6 +192,36 @@ VLR_DEV void wave_eval(const double2* __restrict__ co, int n, double ksum, const
     // parallelism for one warp to keep the fp64 pipe busy (a serial acc *= t chain stalls on the pipe latency).
     const int H = sp.H;
     int r = sp.h;
+#ifdef VLR_PULL8
+    // Tuning experiment (never set in the product build; A/B with scripts/ab_lib.py): 8 factors between exponent pulls.
+    // A pull is an exact power-of-two rescaling, so skipping every other one leaves every bit of the result unchanged
+    // (mantissa < 2 times 8 factors <= 3 stays far from overflow; a product below 1e-240 still takes the careful path).
+#pragma unroll 1
+    for (; r + 7 * H < n; r += 8 * H) {
+        double t0[NP], t1[NP], t2[NP], t3[NP];
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            t0[i] = term(r, i);
+            t1[i] = term(r + H, i);
+            t2[i] = term(r + 2 * H, i);
+            t3[i] = term(r + 3 * H, i);
+        }
+#pragma unroll
+        for (int i = 0; i < NP; ++i) acc[i] *= (t0[i] * t1[i]) * (t2[i] * t3[i]);
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            t0[i] = term(r + 4 * H, i);
+            t1[i] = term(r + 5 * H, i);
+            t2[i] = term(r + 6 * H, i);
+            t3[i] = term(r + 7 * H, i);
+        }
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            acc[i] *= (t0[i] * t1[i]) * (t2[i] * t3[i]);
+            wave_pull(acc[i], ex[i], slow, 1u << i);
+        }
+    }
+#endif
 #pragma unroll 1
     for (; r + 3 * H < n; r += 4 * H) { // 4 factors (each <= 3) between exponent pulls
         double t0[NP], t1[NP], t2[NP], t3[NP];
