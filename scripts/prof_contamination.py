@@ -5,8 +5,6 @@ import os
 import sys
 import time
 
-import numpy as np
-
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 from oracle import oracle  # noqa: E402
 from tests.test_contamination import make_observations  # noqa: E402

@@ -1,6 +1,5 @@
 """The C-ABI library loads without a GPU and exports every entry point include/vlr_engine.h declares; entry points
 that need a device fail loudly (no CPU fallback) when there is none."""
-import ctypes as C
 import os
 import re
 

@@ -7,9 +7,7 @@ oracle through the host emulation, and the CUDA path (`-m gpu`) against the orac
 Tolerance: 1e-9 absolute on ln posteriors / ln marginal (sums over <= 4096 observations; the chunked device sum and the
 reference's sequential sum differ by rounding only), identical -inf / NaN positions, identical max_vaf."""
 import bisect
-import io
 import math
-import os
 
 import numpy as np
 import pytest
@@ -274,7 +272,6 @@ def test_gpu_contamination_matches_oracle(n):
 
 @pytest.mark.gpu
 def test_gpu_contamination_nan_positions_and_bad_arguments():
-    import ctypes as C
     from varlociraptor_b200 import engine
     obs = make_observations(12, seed=5, with_full_vaf=False)
     want_lik = oracle_posterior(obs)[1]

@@ -30,7 +30,6 @@ from .scenario import Scenario
 
 EXPECTED_MAX_SOMATIC_VAFS = (0.25, 0.5, 0.75, 1.0)  # Marginal::compute (contamination.rs:222)
 N_GRID = 101                                        # ln_simpsons_integrate_exp(density, 0.0, 1.0, 101) (:233)
-LN_095 = math.log(0.95)
 
 CONTAMINATION_SCENARIO = """
 samples:
