@@ -205,3 +205,26 @@ def test_haplotype_groups_reuse_the_first_members_result(tn_records):
     assert ref.calls[3].event_probs == w.calls[3].event_probs
     with pytest.raises(ValueError, match="without record ID"):
         calling.haplotype_identifier({"info": {"MATEID": "x"}, "id": "."})
+
+
+def test_missing_data_record(tn_records):
+    """mod.rs:424-466, 559-571: a record without any read in any sample is written with missing probabilities,
+    DP 0 and the hint `missing-data`; its neighbours are unaffected."""
+    import copy
+    tumor, normal, b = tn_records
+    tumor, normal = copy.deepcopy(tumor), copy.deepcopy(normal)
+    empty = _records_from_batch(LocusBatch(1, np.zeros(2, np.int64), {k: v[:0] for k, v in b.columns.items()},
+                                           b.read_flags[:0], b.locus_flags[:1]))[0]
+    for recs in (tumor, normal):
+        recs[5]["info"] = copy.deepcopy(empty["info"])
+    sc = Scenario.tumor_normal(0.75)
+    w = calling.call_generic(sc, {"tumor": tumor, "normal": normal}, engine=EmuEngine(sc.flatten()))
+    ref = calling.call_generic(sc, {"tumor": tn_records[0], "normal": tn_records[1]}, engine=EmuEngine(sc.flatten()))
+    c = w.calls[5]
+    assert c.is_missing_data and c.all_hints()[-1] == "missing-data"
+    assert all(np.isnan(v) for v in c.info_fields().values())
+    assert c.format_fields(0)["DP"] == "0" and c.format_fields(1)["AF"] == "." and c.format_fields(0)["OBS"] == "."
+    line = w.lines()[5].split("\t")
+    assert "PROB_ABSENT=." in line[7] and line[7].endswith("HINTS=missing-data") and line[9].startswith("0:.:")
+    assert not w.calls[4].is_missing_data and w.calls[4].event_probs == ref.calls[4].event_probs
+    assert w.lines()[4] == ref.lines()[4] and w.lines()[6] == ref.lines()[6]

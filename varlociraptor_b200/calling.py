@@ -111,6 +111,7 @@ class SampleCall:
     srobs: str = "."
     obs: str = "."           # OBS: full per-read codes (mod.rs:277-333)
     oobs: int = 0            # OOBS: reads dropped by remove_nonstandard_alignments (pileup.rs:26-43, mod.rs:382)
+    n_reads: int = -1        # reads left in the pileup (Pileup::is_empty decides `missing-data`); -1 = not recorded
 
 
 @dataclass
@@ -124,12 +125,26 @@ class Call:
     hints: List[str] = field(default_factory=list)
     status: int = 0
 
+    @property
+    def is_missing_data(self) -> bool:
+        """mod.rs:424-431: no sample has a read left (after the non-standard alignment filter): the record is written
+        with missing PROB_* / AF, DP 0 and the hint `missing-data`."""
+        return all(si is None or si.n_reads == 0 for si in self.sample_info)
+
+    def all_hints(self) -> List[str]:
+        return self.hints + (["missing-data"] if self.is_missing_data else [])
+
     def info_fields(self) -> Dict[str, np.float32]:
-        """PROB_* INFO values exactly as written: PHRED, absolute value, f32 (mod.rs:459-466)."""
+        """PROB_* INFO values exactly as written: PHRED, absolute value, f32 (mod.rs:447-466); NaN = missing value."""
+        if self.is_missing_data:
+            return {event_tag_name(e): np.float32(np.nan) for e in self.event_probs}
         return {event_tag_name(e): np.float32(abs(_PHRED * p)) for e, p in self.event_probs.items()}
 
     def format_fields(self, sample: int) -> Dict[str, str]:
         si = self.sample_info[sample]
+        if self.is_missing_data:  # mod.rs:559-571
+            return {"DP": "0", "AF": ".", "SAOBS": ".", "SROBS": ".", "OBS": ".", "OOBS": ".", "SB": ".", "ROB": ".",
+                    "RPB": ".", "AFD": "."}
         if si is None:
             return {"DP": ".", "AF": ".", "AFD": ".", "OBS": ".", "OOBS": "."}
         labels = {"SB": ".", "ROB": ".", "RPB": ".", "SCB": ".", "HE": ".", "ALB": "."}
@@ -226,7 +241,10 @@ class CallWriter(CallProcessor):
     def lines(self) -> List[str]:
         out = []
         for c in self.calls:
-            info = ";".join("%s=%s" % (k, "inf" if np.isinf(v) else "%g" % v) for k, v in c.info_fields().items())
+            info = ";".join("%s=%s" % (k, "." if np.isnan(v) else ("inf" if np.isinf(v) else "%g" % v))
+                            for k, v in c.info_fields().items())
+            if c.all_hints():
+                info += ";HINTS=" + ",".join(c.all_hints())
             keys = ["DP", "AF", "SAOBS", "SROBS", "OBS", "OOBS", "SB", "ROB", "RPB", "SCB", "HE", "ALB", "AFD"]
             fmt = []
             for s in range(len(c.sample_info)):
@@ -370,7 +388,7 @@ class Caller:
                                                    simple_observations(pa, pr, mq, True),
                                                    simple_observations(pa, pr, mq, False),
                                                    read_observation_summary(pa, pr, rf, third),
-                                                   int((~keep).sum())))
+                                                   int((~keep).sum()), int(keep.sum())))
             if item.haplotype is not None:
                 self._haplotype_results[item.haplotype] = call
             self.call_processor.process_call(call, self.sample_names)
