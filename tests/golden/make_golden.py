@@ -10,6 +10,7 @@ Outputs (committed):
                             AF, AFD text, DP, SAOBS/SROBS/OBS/OOBS, the raw
                             THIRD_ALLELE_EVIDENCE INFO arrays, plus the scenario
   raw_info_records.json     verbatim INFO integer arrays of three reference records (codec round trip)
+  prior_scenarios.json      the six scenario files of tests/resources/prior/scenarios, verbatim
   real_pileups.npz/.json    single-sample observation-format-15 pileups embedded in
                             tests/resources/testcases/*/candidates.vcf (inputs only) with their scenario text
 """
@@ -54,6 +55,17 @@ def flamegraph():
         json.dump({"source": "tests/resources/flamegraph_profiling/{normal.vcf,calls.vcf,scenario.yaml}",
                    "scenario_yaml": scenario, "records": expected}, f, indent=1)
     print("flamegraph: %d loci, %d reads" % (batch.n_loci, batch.n_reads))
+
+
+def prior_scenarios():
+    """The six scenario files of tests/resources/prior/scenarios (every prior branch: population, Mendelian with
+    sex/contig ploidy maps, clonal and subclonal inheritance, somatic rates), verbatim, keyed by file name."""
+    d = os.path.join(REF, "prior", "scenarios")
+    out = {name[:-len(".scenario.yaml")]: open(os.path.join(d, name)).read() for name in sorted(os.listdir(d))
+           if name.endswith(".scenario.yaml")}
+    with open(os.path.join(HERE, "prior_scenarios.json"), "w") as f:
+        json.dump({"source": "tests/resources/prior/scenarios/*.scenario.yaml", "scenarios": out}, f, indent=1)
+    print("prior scenarios: %s" % ", ".join(out))
 
 
 def real_pileups():
@@ -108,5 +120,6 @@ def raw_info_records():
 
 if __name__ == "__main__":
     flamegraph()
+    prior_scenarios()
     real_pileups()
     raw_info_records()

@@ -1,0 +1,50 @@
+"""The reference's six prior scenarios (tests/resources/prior/scenarios, committed verbatim in
+tests/golden/prior_scenarios.json): population heterozygosity, Mendelian inheritance with sex- and contig-specific
+ploidy, clonal / subclonal inheritance and somatic mutation rates (src/variants/model/prior.rs:298-678). Upstream
+only plots them; here every one goes through scenario front-end -> flattened trees -> engine (host emulation of the
+kernel source) and is compared with the oracle, on autosomes and on the sex chromosomes where ploidies differ."""
+import json
+import os
+
+import pytest
+
+from oracle import oracle
+from tests import emu
+from tests.test_emu_parity import _compare
+from tests.util import four_sample_batch
+from varlociraptor_b200 import Scenario, synth
+
+CASES = [("population", "all"), ("tumor-normal", "all"), ("tumor-relapse", "all"), ("tumor-normal-relapse", "all"),
+         ("simple-pedigree", "all"), ("pedigree", "all"), ("pedigree", "X"), ("pedigree", "Y")]
+
+
+def _batch(n_samples, n_loci, seed):
+    if n_samples == 2:
+        return synth.tumor_normal(n_loci, seed=seed, depth=30)[1]
+    if n_samples == 3:
+        return synth.pedigree(n_loci, seed=seed, depth=30)[1]
+    return four_sample_batch(n_loci, seed=seed, depth=16)
+
+
+@pytest.mark.parametrize("name,contig", CASES)
+def test_prior_scenario_engine_matches_oracle(golden_dir, name, contig):
+    text = json.load(open(os.path.join(golden_dir, "prior_scenarios.json")))["scenarios"][name]
+    for full_prior in (False, True):
+        sc = Scenario.from_yaml(text, full_prior=full_prior).for_contig(contig)
+        flat = sc.flatten()
+        b = _batch(flat.n_samples, 16, seed=70 + len(name))
+        # AFDs only where the nested integrations stay below the engine's base-event log (4096 per locus, reported as
+        # VLR_ST_BASE_EVENTS_OVERFLOW otherwise): the relapse scenarios integrate two full ranges inside each other
+        afd = 0 if "relapse" in name else 64
+        want = oracle.call_batch(flat, b, afd_capacity=afd, n_threads=4)
+        _compare(want, emu.call_batch(flat, b, afd_capacity=afd))
+        assert not (want.status & (1 << 1 | 1 << 2 | 1 << 3)).any()  # no NaN / overshoot / positive prior
+
+
+def test_ploidies_of_the_pedigree_on_sex_chromosomes(golden_dir):
+    text = json.load(open(os.path.join(golden_dir, "prior_scenarios.json")))["scenarios"]["pedigree"]
+    sc = Scenario.from_yaml(text)
+    assert [sc.for_contig("X").ploidy(n) for n in ("mother", "father", "child", "sibling")] == [2, 1, 1, 2]
+    assert [sc.for_contig("Y").ploidy(n) for n in ("mother", "father", "child", "sibling")] == [0, 1, 1, 0]
+    y = sc.for_contig("Y")
+    assert y.universe("mother") == [frozenset([0.0])] and y.universe("father") == [frozenset([0.0, 1.0])]
