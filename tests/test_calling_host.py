@@ -228,3 +228,42 @@ def test_missing_data_record(tn_records):
     assert "PROB_ABSENT=." in line[7] and line[7].endswith("HINTS=missing-data") and line[9].startswith("0:.:")
     assert not w.calls[4].is_missing_data and w.calls[4].event_probs == ref.calls[4].event_probs
     assert w.lines()[4] == ref.lines()[4] and w.lines()[6] == ref.lines()[6]
+
+
+def test_model_is_reconfigured_per_contig(golden_dir):
+    """calling.rs:632-718: ploidy (hence universes, trees and prior) follows the contig of the record."""
+    from tests.test_prior_scenarios import _batch
+    text = json.load(open(os.path.join(golden_dir, "prior_scenarios.json")))["scenarios"]["pedigree"]
+    sc = Scenario.from_yaml(text)
+    assert sc.is_contig_dependent() and not Scenario.tumor_normal(0.75).is_contig_dependent()
+    b = _batch(4, 9, seed=3)
+    names = sc.sample_names
+
+    def one(s):
+        starts, ends = b.read_offsets[s:-1:4], b.read_offsets[s + 1::4]
+        idx = np.concatenate([np.arange(a, e) for a, e in zip(starts, ends)])
+        offs = np.concatenate([[0], np.cumsum(ends - starts)])
+        return LocusBatch(1, offs, {k: v[idx] for k, v in b.columns.items()}, b.read_flags[idx], b.locus_flags)
+    records = {n: _records_from_batch(one(s)) for s, n in enumerate(names)}
+    contigs = ["1", "1", "2", "X", "X", "Y", "1", "X", "2"]
+    for recs in records.values():
+        for r, c in zip(recs, contigs):
+            r["chrom"] = c
+    built = []
+
+    def factory(flat):
+        built.append(flat)
+        return EmuEngine(flat)
+    w = calling.call_generic(sc, records, engine_factory=factory)
+    assert [c.chrom for c in w.calls] == contigs
+    assert len(built) == 3  # autosomes ("all", "1", "2" share one model), X, Y
+    for contig in ("1", "X", "Y"):
+        flat = sc.for_contig(contig).flatten()
+        want = emu.call_batch(flat, b, afd_capacity=128)
+        for i, c in enumerate(w.calls):
+            if c.chrom == contig:
+                assert [c.event_probs[e] for e in flat.event_names] == want.log_posteriors[i, :-1].tolist()
+    x, a = [c for c in w.calls if c.chrom == "X"][0], [c for c in w.calls if c.chrom == "1"][0]
+    father = names.index("father")
+    assert x.sample_info[father].allelefreq_estimate in (0.0, 1.0)          # haploid on X
+    assert a.sample_info[father].allelefreq_estimate in (0.0, 0.5, 1.0)

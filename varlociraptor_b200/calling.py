@@ -259,7 +259,11 @@ class Caller:
 
     def __init__(self, scenario: Scenario, observations: Dict[str, Iterable[dict]], call_processor: CallProcessor,
                  candidate_filter: CandidateFilter, omit: Dict[str, bool], full_prior: bool = False,
-                 batch_size: int = 65536, afd_capacity: int = 128, device: int = 0, engine=None):
+                 batch_size: int = 65536, afd_capacity: int = 128, device: int = 0, engine=None,
+                 engine_factory=None):
+        """`engine`: a ready engine for `scenario.flatten()` (tests). `engine_factory(flat_scenario)`: how to build one
+        per configured model; default = the CUDA `PosteriorEngine`. A scenario whose ploidies or universes depend on
+        the contig gets one model per contig, like `configure_model` upstream (calling.rs:632-718)."""
         scenario.full_prior = full_prior
         self.scenario = scenario
         self.flat = scenario.flatten()
@@ -273,11 +277,32 @@ class Caller:
         self.omit = omit
         self.batch_size = batch_size
         self.afd_capacity = afd_capacity
+        if engine_factory is None:
+            def engine_factory(flat):
+                from .engine import PosteriorEngine
+                return PosteriorEngine(flat, device=device)
+        self._engine_factory = engine_factory
+        self._per_contig = engine is None and scenario.is_contig_dependent()
+        self._models: Dict[str, tuple] = {}
+        self._contig = scenario.contig
         if engine is None:
-            from .engine import PosteriorEngine
-            engine = PosteriorEngine(self.flat, device=device)
+            engine = engine_factory(self.flat)
         self.engine = engine
+        self._models[scenario.contig] = (self.flat, engine)
+        self._model_by_signature = {scenario.contig_signature(): (self.flat, engine)}
         self._haplotype_results: Dict[str, Optional[Call]] = {}
+
+    def _configure_model(self, contig: str) -> None:
+        """calling.rs:632-718: the event universe follows the contig (ploidy- and contig-specific universes)."""
+        if contig not in self._models:
+            sc = self.scenario.for_contig(contig)
+            key = sc.contig_signature()
+            if key not in self._model_by_signature:  # contigs with the same ploidies and universes share a model
+                flat = sc.flatten()
+                self._model_by_signature[key] = (flat, self._engine_factory(flat))
+            self._models[contig] = self._model_by_signature[key]
+        self.flat, self.engine = self._models[contig]
+        self._contig = contig
 
     def _records(self) -> Iterator[List[Optional[dict]]]:
         """One record per sample in lock-step (calling.rs:353-398): same chrom/pos/alleles required."""
@@ -312,6 +337,11 @@ class Caller:
         for recs in self._records():
             one = obs_codec.batch_from_records([[r] for r in recs], **self.omit)
             first = next(r for r in recs if r is not None)
+            if self._per_contig and first["chrom"] != self._contig:
+                if pending:  # records of the previous contig are called with its model
+                    self._flush(pending)
+                    pending = []
+                self._configure_model(first["chrom"])
             item = WorkItem(index, first["chrom"], first["pos"], first["ref"], first["alt"], one,
                             int(one.locus_flags[0]), haplotype_identifier(first),
                             [obs_codec.decode_optional_u32(r["info"]["THIRD_ALLELE_EVIDENCE"])

@@ -495,6 +495,17 @@ class Scenario:
             return self._contig_ploidy(d[s.sex], self.contig)
         return self._contig_ploidy(d, self.contig)
 
+    def is_contig_dependent(self) -> bool:
+        """True if some ploidy or universe is given per contig (PloidyDefinition::Map, UniverseDefinition::Map)."""
+        sp = self.species.ploidy if self.species else None
+        if isinstance(sp, dict) and (set(sp) - {"male", "female"} or any(isinstance(v, dict) for v in sp.values())):
+            return True
+        return any(isinstance(s.ploidy, dict) or isinstance(s.universe, dict) for s in self.samples.values())
+
+    def contig_signature(self) -> tuple:
+        """What of the scenario depends on the contig: per sample its universe and ploidy on `self.contig`."""
+        return tuple((n, repr(self.universe(n)), self.ploidy(n)) for n in self.sample_names)
+
     def for_contig(self, contig: str) -> "Scenario":
         """The scenario as `Caller::configure_model` sees it on `contig` (calling.rs:632-718): universes,
         and with them the event trees, follow the contig's ploidy."""
