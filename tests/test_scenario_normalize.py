@@ -202,7 +202,40 @@ def test_every_scenario_of_the_reference_test_suite_normalises_and_flattens():
     assert len(files) >= 100
     for path in files:
         sc = Scenario.from_yaml(open(path).read())
+        if os.path.basename(os.path.dirname(path)) == "test_overlapping_events":  # testcase_should_panic! upstream
+            with pytest.raises(ValueError, match="not disjunct"):
+                sc.flatten()
+            continue
         flat = sc.flatten()
         assert flat.n_events == len(sc.events) + (0 if "absent" in sc.events else 1), path
         normal = [repr(sc.normalize(f)) for f in sc.event_formulas.values()]
         assert len(set(normal)) == len(normal), path
+
+
+def test_overlapping_events_are_rejected():
+    """Scenario::validate (grammar/mod.rs:223-278); the reference's `testcase_should_panic!(test_overlapping_events)`
+    (tests/lib.rs:160): `germline` contains `germline_het` and `germline_hom`, `somatic` contains its two parts."""
+    sc = Scenario.from_yaml("""
+samples:
+  tumor:
+    contamination:
+      by: normal
+      fraction: 0.25
+    resolution: 0.01
+    universe: "[0.0,1.0]"
+  normal:
+    resolution: 0.1
+    universe: "[0.0,0.5[ | 0.5 | 1.0"
+events:
+  somatic: "tumor:]0.0,1.0] & normal:[0.0,0.5["
+  somatic_tumor:  "tumor:]0.0,1.0] & normal:0.0"
+  germline: "normal:0.5 | normal:1.0"
+  germline_het:   "tumor:[0.0,1.0] & normal:0.5"
+""")
+    with pytest.raises(ValueError, match="the following events are not disjunct") as err:
+        sc.flatten()
+    assert "['germline'] | ['germline_het']) = ['germline']" in str(err.value)
+    # containment that needs interval reasoning inside a conjunction (`somatic` covers `somatic_tumor`) is not found:
+    # atoms are only merged at the top level of a disjunction, upstream as well (formula.rs:636-706)
+    assert "somatic" not in str(err.value)
+    Scenario.tumor_normal(0.75).validate()  # the CLI's own scenario is disjunct

@@ -870,8 +870,34 @@ class Scenario:
             node = TreeNode(abi.NODE_SET, sample=s, vafs=frozenset([0.0]), children=[node] if node else [])
         return [node]
 
+    def validate(self) -> None:
+        """Scenario::validate (grammar/mod.rs:223-278): two events are rejected when their disjunction normalises to
+        one of the scenario's events, i.e. when one contains the other ("the following events are not disjunct")."""
+        by_formula: Dict[str, List[str]] = {}
+        normal = {}
+        for name, f in self.event_formulas.items():
+            if name == "absent":
+                continue
+            g = self.normalize(f)
+            normal[repr(g)] = g
+            by_formula.setdefault(repr(g), []).append(name)
+        keys = sorted(normal)
+        overlapping = []
+        for i, k1 in enumerate(keys):
+            for k2 in keys[i + 1:]:
+                e1, e2 = normal[k1], normal[k2]
+                if any(isinstance(e, Const) and not e.value for e in (e1, e2)):
+                    continue  # a terminal `false` overlaps with nothing
+                d = repr(self.normalize(Or((e1, e2))))
+                if d in normal:
+                    overlapping.append("(%s | %s) = %s" % (by_formula[k1], by_formula[k2], by_formula[d]))
+        if overlapping:
+            raise ValueError("the following events are not disjunct: " + ", ".join(overlapping))
+
     def event_trees(self) -> List[Tuple[str, List[TreeNode]]]:
-        """[absent] + scenario events (calling.rs:655-687); scenario events in name order."""
+        """[absent] + scenario events (calling.rs:655-687); scenario events in name order. Validates the events like
+        `Scenario::vaftrees` does (grammar/mod.rs:206-221)."""
+        self.validate()
         out = [("absent", self.absent_tree())]
         for name, f in self.event_formulas.items():
             if name == "absent":
