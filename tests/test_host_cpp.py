@@ -21,6 +21,64 @@ def test_cpp_contamination_estimator_with_mock_model(tmp_path):
     assert "host contamination mock test: ok" in subprocess.check_output([exe], text=True)
 
 
+def _bits(a, dtype):
+    import numpy as np
+    return ["%08x" % x for x in np.asarray(a, dtype=dtype).view(np.uint32).tolist()]
+
+
+def test_cpp_observation_decoder_matches_the_python_codec(tmp_path, golden_dir):
+    """host/vlr_obs_codec.hpp against varlociraptor_b200.obs_codec on the reference's own records (verbatim INFO arrays
+    of two methylation records and one indel record), a synthetic record with homopolymer columns, and a truncated
+    array."""
+    import json
+    import numpy as np
+    from varlociraptor_b200 import abi, obs_codec
+    from varlociraptor_b200.batch import mini_logprob
+    exe = str(tmp_path / "test_obs_codec")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-o", exe,
+                           os.path.join(ROOT, "tests", "host", "test_obs_codec.cpp")])
+    infos = [r["info"] for r in json.load(open(os.path.join(golden_dir, "raw_info_records.json")))["records"]]
+    rng = np.random.Generator(np.random.PCG64(3))
+    n = 37
+    cols = {k: mini_logprob(-rng.exponential(8.0, n)) for k in abi.BATCH_F32_COLUMNS}
+    cols["prob_double_overlap"][::3] = -np.inf
+    flags = (rng.integers(0, 4, n) << abi.RF_STRAND_SHIFT) | (rng.choice([0, 1, 8, 5], n) << abi.RF_ORIENT_SHIFT) | \
+        (rng.integers(0, 3, n) << abi.RF_ALTLOCUS_SHIFT) | (rng.integers(0, 2, n) * abi.RF_SOFTCLIPPED) | \
+        (rng.integers(0, 2, n) * abi.RF_PAIRED) | (rng.integers(0, 2, n) * abi.RF_MAX_MAPQ) | \
+        (rng.integers(0, 2, n) * abi.RF_READPOS_MAJOR)
+    hl = rng.integers(-3, 4, n)
+    has = rng.random(n) < 0.7
+    flags = flags.astype(np.uint32) | np.where(has, abi.RF_HAS_HOMOPOLYMER_LEN | ((hl & 0xff) << abi.RF_HOMOPOLYMER_LEN_SHIFT), 0).astype(np.uint32)
+    hart = np.where(has, mini_logprob(-rng.exponential(3.0, n)), np.nan).astype(np.float32)
+    hvar = np.where(has, mini_logprob(-rng.exponential(3.0, n)), np.nan).astype(np.float32)
+    infos.append(obs_codec.encode_record(cols, flags, hart, hvar))
+    broken = dict(infos[0])
+    broken["PROB_ALT"] = broken["PROB_ALT"][:-3]
+    infos.append(broken)
+    path = tmp_path / "records.txt"
+    with open(path, "w") as f:
+        for info in infos:
+            for tag, vals in info.items():
+                if isinstance(vals, list):
+                    f.write(tag + " " + " ".join(str(v) for v in vals) + "\n")
+            f.write("--\n")
+    blocks = subprocess.check_output([exe, str(path)], text=True).strip().split("--\n")
+    blocks = [b for b in (x.strip() for x in blocks) if b]
+    assert len(blocks) == len(infos)
+    for info, block in zip(infos[:-1], blocks):
+        got = {ln.split()[0]: ln.split()[1:] for ln in block.splitlines()}
+        want_cols, want_flags, want_hart, want_hvar = obs_codec.decode_record(info)
+        for k in abi.BATCH_F32_COLUMNS:
+            assert got[k] == _bits(want_cols[k], np.float32), k
+        assert got["read_flags"] == _bits(want_flags, np.uint32)
+        assert got["hart"] == ([] if want_hart is None else _bits(want_hart, np.float32))
+        assert got["hvar"] == ([] if want_hvar is None else _bits(want_hvar, np.float32))
+        if "THIRD_ALLELE_EVIDENCE" in info:
+            h, v = obs_codec.decode_optional_u32(info["THIRD_ALLELE_EVIDENCE"])
+            assert got["third"] == [str(int(x)) if y else "." for x, y in zip(v, h)]
+    assert blocks[-1].startswith("ERROR truncated observation INFO array")
+
+
 def _build_contamination_link(tmp_path):
     from varlociraptor_b200 import build as vbuild
     lib = vbuild.build()
