@@ -9,9 +9,9 @@
 //   preprocess_record's per-record flags  calling.rs:513-566   -> locus_flags_for()
 //
 // The reference is Rust; its toolchain is not available in the build image, so this header is the compiled-language
-// host a maintainer can diff against calling.rs. Observation *decoding* (BCF via htslib) stays with the application:
-// a record arrives here as already decoded per-read columns (`ObservationRecord`), exactly what
-// `read_observations` (preprocessing/mod.rs:818-919) yields before it builds `ReadObservation` structs.
+// host a maintainer can diff against calling.rs. BCF access (htslib) stays with the application: a record arrives here
+// as per-read columns (`ObservationRecord`), exactly what `read_observations` (preprocessing/mod.rs:818-919) yields
+// before it builds `ReadObservation` structs; vlr_obs_codec.hpp decodes the INFO integer arrays into them.
 //
 // Errors: like anyhow::Result in the reference, configuration / input problems throw std::runtime_error with the
 // reference's message; model-invariant violations arrive as status bits per call (the reference panics there).
