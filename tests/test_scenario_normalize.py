@@ -239,3 +239,57 @@ events:
     # atoms are only merged at the top level of a disjunction, upstream as well (formula.rs:636-706)
     assert "somatic" not in str(err.value)
     Scenario.tumor_normal(0.75).validate()  # the CLI's own scenario is disjunct
+
+
+# ------------------------------------------------------------------------------------------ property: meaning is preserved
+def _holds(f, vafs):
+    """Truth of a (normalised or raw) formula at one VAF assignment {sample: vaf}."""
+    from varlociraptor_b200.scenario import Not, spectrum_contains
+    if isinstance(f, Const):
+        return f.value
+    if isinstance(f, Atom):
+        return spectrum_contains(f.vafs, vafs[f.sample])
+    if isinstance(f, And):
+        return all(_holds(o, vafs) for o in f.operands)
+    if isinstance(f, Or):
+        return any(_holds(o, vafs) for o in f.operands)
+    if isinstance(f, Not):
+        return not _holds(f.operand, vafs)
+    raise TypeError(f)
+
+
+def test_normalisation_preserves_the_meaning_of_random_formulas():
+    """expand -> negations -> simplify -> merge atoms -> simplify must not change which VAF assignments satisfy an
+    event. Random formulas over two samples with discrete universes (negation against a range universe is excluded:
+    upstream's `split_at` keeps an inclusive boundary point on the wrong side, mirrored and tested above)."""
+    from hypothesis import given, settings, strategies as st
+    from varlociraptor_b200.scenario import Not
+    sc = Scenario.from_yaml("""
+samples:
+  a:
+    universe: "0.0 | 0.25 | 0.5 | 0.75 | 1.0"
+  b:
+    universe: "{0.0,0.5} | 1.0"
+events:
+  e: "a:0.5"
+""")
+    points = [0.0, 0.25, 0.5, 0.75, 1.0]
+    spectra = st.one_of(
+        st.frozensets(st.sampled_from(points), min_size=1, max_size=3),
+        st.builds(lambda lo, hi, le, re: VAFRange(min(lo, hi), max(lo, hi), le, re), st.sampled_from(points),
+                  st.sampled_from(points), st.booleans(), st.booleans()).filter(lambda r: r.start < r.end))
+    atoms = st.builds(Atom, st.sampled_from(["a", "b"]), spectra)
+    set_atoms = st.builds(Atom, st.sampled_from(["a", "b"]), st.frozensets(st.sampled_from(points), min_size=1, max_size=3))
+    formulas = st.recursive(st.one_of(atoms, st.builds(Not, set_atoms)),
+                            lambda inner: st.one_of(st.builds(lambda xs: And(tuple(xs)), st.lists(inner, min_size=2, max_size=3)),
+                                                    st.builds(lambda xs: Or(tuple(xs)), st.lists(inner, min_size=2, max_size=3))),
+                            max_leaves=8)
+
+    @settings(max_examples=300, deadline=None)
+    @given(formulas)
+    def check(f):
+        g = sc.normalize(f)
+        for va in points:
+            for vb in (0.0, 0.5, 1.0):  # b's universe
+                assert _holds(f, {"a": va, "b": vb}) == _holds(g, {"a": va, "b": vb}), (f, g, va, vb)
+    check()
