@@ -19,8 +19,8 @@ ncu --set full --clock-control none --import-source on -k regex:vlr_wave_coef_ke
 # read here with: ncu -i gpurun_out/X.ncu-rep --page raw --csv   /   --page source --csv --print-source sass
 # contamination estimator: launch list and one full capture of the likelihood kernel (second launch =
 # the 100 000-observation call; the first is the 10-observation warm-up)
-python scripts/prof_contamination.py 100000 2>&1 | tail -1
+python tests/tools/prof_contamination.py 100000 2>&1 | tail -1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 30 --csv --log-file gpurun_out/launches_contam.csv \
-    python scripts/prof_contamination.py 100000 > /dev/null 2>&1
+    python tests/tools/prof_contamination.py 100000 > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:vlr_contam_likelihood_kernel -s 1 -c 1 \
-    -o gpurun_out/ncu_contam -f python scripts/prof_contamination.py 100000 > gpurun_out/ncu_contam.log 2>&1
+    -o gpurun_out/ncu_contam -f python tests/tools/prof_contamination.py 100000 > gpurun_out/ncu_contam.log 2>&1

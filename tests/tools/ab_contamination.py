@@ -6,7 +6,7 @@ import sys
 
 import numpy as np
 
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 from tests.test_contamination import assert_same, make_observations, oracle_posterior  # noqa: E402
 from varlociraptor_b200 import contamination as ct  # noqa: E402
 

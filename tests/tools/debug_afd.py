@@ -1,6 +1,6 @@
 import os, sys
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import oracle
 from varlociraptor_b200 import synth, engine
 sc, b = synth.tumor_normal(1500, seed=synth.SEED_BASE + 2)

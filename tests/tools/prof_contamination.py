@@ -5,7 +5,7 @@ import os
 import sys
 import time
 
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 from oracle import oracle  # noqa: E402
 from tests.test_contamination import make_observations  # noqa: E402
 from varlociraptor_b200 import contamination as ct  # noqa: E402
