@@ -267,3 +267,33 @@ def test_model_is_reconfigured_per_contig(golden_dir):
     father = names.index("father")
     assert x.sample_info[father].allelefreq_estimate in (0.0, 1.0)          # haploid on X
     assert a.sample_info[father].allelefreq_estimate in (0.0, 0.5, 1.0)
+
+
+def test_read_observation_summary_codes():
+    """FORMAT/OBS (mod.rs:277-333): one nine-part code per read, counted; most common first, `E` then `N` codes last."""
+    from varlociraptor_b200 import abi
+    ln = np.log
+
+    def flags(strand, orient, altlocus, major=False, soft=False, paired=False, maxq=False, hlen=None):
+        f = (strand << abi.RF_STRAND_SHIFT) | (orient << abi.RF_ORIENT_SHIFT) | (altlocus << abi.RF_ALTLOCUS_SHIFT)
+        f |= (abi.RF_READPOS_MAJOR if major else 0) | (abi.RF_SOFTCLIPPED if soft else 0)
+        f |= (abi.RF_PAIRED if paired else 0) | (abi.RF_MAX_MAPQ if maxq else 0)
+        if hlen is not None:
+            f |= abi.RF_HAS_HOMOPOLYMER_LEN | ((hlen & 0xff) << abi.RF_HOMOPOLYMER_LEN_SHIFT)
+        return f
+    pa = np.array([ln(0.9), ln(0.9), ln(0.5), ln(0.02), ln(0.5), ln(0.4)])
+    pr = np.array([ln(0.001), ln(0.001), ln(0.5), ln(0.9), ln(0.5), ln(0.6)])
+    rf = np.array([flags(0, 0, 2, paired=True, maxq=True), flags(0, 0, 2, paired=True, maxq=True),
+                   flags(3, 8, 2), flags(1, 1, 0, major=True, soft=True, maxq=True, hlen=-2),
+                   flags(3, 8, 2), flags(2, 5, 1, hlen=0)], dtype=np.uint32)
+    third = (np.array([False, False, False, True, False, False]), np.array([0, 0, 0, 3, 0, 0], dtype=np.uint32))
+    got = calling.read_observation_summary(pa, pr, rf, third)
+    # two very strong alt reads (max MAPQ -> upper case), one strong ref read with third-allele distance 3, major read
+    # position, softclip and a homopolymer error, one barely-ref read on both strands in a non-standard orientation,
+    # two reads with equal evidence
+    # (the `E`-codes-last rule is case sensitive upstream: a lower-case `e` of a read below the maximum MAPQ sorts by count)
+    assert got == "2AV.p.+>*..2e.s..**..1RS3s#-<^$*1rb.s**!*.."
+    upper = calling.read_observation_summary(pa[2:5], pr[2:5], rf[2:5] | abi.RF_MAX_MAPQ)
+    assert upper == "1RS.s#-<^$*2E.s..**.."  # ... an upper-case `E` goes last despite its higher count
+    assert calling.read_observation_summary(pa[:0], pr[:0], rf[:0]) == "."
+    assert calling.read_observation_summary(pa[:1], pr[:1], rf[:1]) == "1AV.p.+>*.."
