@@ -67,3 +67,61 @@ def test_random_scenario(seed):
     assert np.array_equal(want.n_base_events[ok], got.n_base_events[ok])
     no_map = np.uint32(1 << 7)  # differs only where an event contains `absent` (true nodes), see above
     assert np.array_equal(want.status[ok] & ~no_map, got.status[ok] & ~no_map)
+
+
+def random_prior_scenario(seed):
+    """Species / sample prior settings at random: ploidy 1-3, heterozygosity, germline and somatic rates, Mendelian,
+    clonal and subclonal inheritance, contamination (src/variants/model/prior.rs:298-678)."""
+    rng = random.Random(seed)
+    names = ["a", "b", "c"][:rng.choice([2, 3])]
+    ploidy = rng.choice([1, 2, 2, 2, 3])
+    text = "species:\n  heterozygosity: %g\n  ploidy: %d\n" % (rng.choice([1e-3, 1e-2, 5e-4]), ploidy)
+    if rng.random() < 0.5:
+        text += "  germline-mutation-rate: %g\n" % rng.choice([1e-3, 1e-4])
+    if rng.random() < 0.3:
+        text += "  somatic-effective-mutation-rate: %g\n" % rng.choice([1e-6, 1e-5])
+    text += "samples:\n"
+    somatic = {}
+    for i, n in enumerate(names):
+        text += "  %s:\n    resolution: %s\n" % (n, rng.choice([0.1, 0.05]))
+        somatic[n] = rng.random() < 0.4
+        if somatic[n]:
+            text += "    somatic-effective-mutation-rate: %g\n" % rng.choice([1e-6, 1e-4, 1e-10])
+        if i > 0 and rng.random() < 0.6:
+            r = rng.random()
+            if len(names) == 3 and i == 2 and r < 0.4:
+                text += "    inheritance:\n      mendelian:\n        from:\n          - a\n          - b\n"
+            elif r < 0.7:
+                text += "    inheritance:\n      clonal:\n        from: %s\n        somatic: %s\n" % (
+                    names[rng.randrange(i)], rng.choice(["true", "false"]))
+            else:
+                text += "    inheritance:\n      subclonal:\n        from: %s\n" % names[rng.randrange(i)]
+        if i > 0 and rng.random() < 0.25:
+            text += "    contamination:\n      by: a\n      fraction: %s\n" % rng.choice([0.1, 0.3])
+    points = [k / ploidy for k in range(ploidy + 1)]
+    events = ['  het: "a:%s"' % points[1]]
+    if ploidy >= 2:
+        events.append('  hom: "a:%s"' % points[-1])
+    if somatic[names[-1]]:
+        events.append('  som: "a:0.0 & %s:]0.0,%s["' % (names[-1], points[1]))
+    return text + "events:\n" + "\n".join(events) + "\n", len(names)
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_random_prior_configuration(seed):
+    """Everything must agree here (events are disjoint), MAP allele frequencies included. Loci whose prior raises an
+    invariant violation (status bits NaN / overshoot / prior > 0: the reference panics, e.g. Mendelian inheritance
+    with mismatching ploidies, prior.rs:672-676) only need the same status. 1500 configurations were explored."""
+    text, n_samples = random_prior_scenario(seed)
+    gen = synth.tumor_normal if n_samples == 2 else synth.pedigree
+    b = gen(5, seed=seed, depth=16)[1]
+    for full_prior in (False, True):
+        flat = Scenario.from_yaml(text, full_prior=full_prior).flatten()
+        want = oracle.call_batch(flat, b, n_threads=4)
+        got = emu.call_batch(flat, b)
+        assert np.array_equal(want.status, got.status)
+        ok = ~want.knife_edge() & ((want.status & 0xe) == 0)
+        assert max_abs_delta(want.log_posteriors[ok], got.log_posteriors[ok]) <= 1e-9
+        assert np.array_equal(want.best_event[ok], got.best_event[ok])
+        assert np.array_equal(want.n_base_events[ok], got.n_base_events[ok])
+        assert np.array_equal(want.map_vaf[ok], got.map_vaf[ok], equal_nan=True)
