@@ -178,3 +178,30 @@ def test_four_samples_nested_ranges():
     flat = Scenario.from_yaml(FOUR_SAMPLE_YAML).flatten()
     b = four_sample_batch(12, seed=51)
     _compare(oracle.call_batch(flat, b, afd_capacity=128, n_threads=4), emu.call_batch(flat, b, afd_capacity=128))
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.xfail(strict=True, reason="known engine bug (DESIGN.md §7): MAP candidates are not checked for containment "
+                                       "in the best event; found by fuzzing read-level inputs")
+def test_map_must_be_contained_in_the_best_event():
+    """calling.rs:861-864 skips base events that are not contained in the strongest event. With fewer than 10 reads the
+    integration limits are the range bounds themselves even when they are exclusive (formula.rs:1172-1224), so for
+    `tumor:]0.0,1.0]` the point 0.0 is evaluated, can have the highest joint (two reference reads) and is still not a
+    valid MAP: the reference reports the next best contained point (0.1), the engine today reports 0.0. Posteriors, best
+    event and the AFD are unaffected."""
+    import math
+    hi, lo = math.log1p(-1e-3), math.log(1e-3 / 3)
+
+    def r(alt, k):
+        return read(prob_mapping=math.log1p(-1e-6), prob_alt=hi if alt else lo, prob_ref=lo if alt else hi,
+                    strand=abi.STRAND_FORWARD if k % 2 else abi.STRAND_REVERSE,
+                    orientation=abi.ORIENT_F1R2 if k % 2 else abi.ORIENT_F2R1, prob_double_overlap=-math.inf)
+    b = batch_from_reads([[[r(k % 2 == 0, k // 2) for k in range(40)], [r(False, 0), r(False, 1)]]])
+    flat = Scenario.tumor_normal(0.75).flatten()
+    want = oracle.call_batch(flat, b, afd_capacity=64)
+    assert want.map_vaf.tolist() == [[0.5, 0.1]] and want.best_event.tolist() == [2]  # germline_het
+    for got in (emu.call_batch(flat, b, afd_capacity=64), emu.wave_call_batch(flat, b, afd_capacity=64)[0]):
+        assert max_abs_delta(want.log_posteriors, got.log_posteriors) <= TOL
+        assert np.array_equal(want.map_vaf, got.map_vaf)
