@@ -1,6 +1,7 @@
 """Read-level fuzzer: random pileups (depths 0-40, every strand / orientation / read-position / softclip / alt-locus /
-homopolymer combination, MAPQ 0, equal evidence, missing bias checks) under the tumor-normal scenario; the host
-emulations of both engines against the oracle. Usage: python tests/tools/fuzz_reads.py FIRST_SEED LAST_SEED [show].
+homopolymer combination, MAPQ 0, equal evidence, missing bias checks) under the tumor-normal scenario (or a pedigree, the contamination scenario, one sample, a log2-fold-change
+scenario); the host
+emulations of both engines against the oracle. Usage: python tests/tools/fuzz_reads.py FIRST_SEED LAST_SEED [tn|pedigree|contamination|single|l2fc] [show].
 Found the MAP containment bug; the other differences seen in 300 seeds were exact ties between events
 or between grid points of pileups with 0-2 reads."""
 import math
@@ -35,12 +36,12 @@ def rand_read(rng, alt_bias, indel):
         kw.update(hlen=rng.choice([-2,-1,0,1,2]), hart=q(-rng.uniform(0,5)), hvar=q(-rng.uniform(0,5)))
     if kw["strand"]==abi.STRAND_BOTH and kw["prob_double_overlap"]==-math.inf: kw["prob_double_overlap"]=q(math.log(0.5))
     return read(**kw)
-def gen(seed):
+def gen(seed, n_samples=2):
     rng=random.Random(seed); loci=[]; lflags=[]
     for _ in range(6):
         indel = rng.random()<0.3
         piles=[]
-        for s in range(2):
+        for s in range(n_samples):
             depth=rng.choice([0,1,2,5,12,12,25,40])
             ab = rng.choice([0.0,0.0,0.1,0.5,1.0])
             # artifact-like: alt reads concentrated on one strand/orientation
@@ -55,13 +56,55 @@ def gen(seed):
                 if rng.random()<0.15: f &= ~bit
         lflags.append(f)
     return batch_from_reads(loci, lflags)
-flatTN = Scenario.tumor_normal(0.75).flatten()
+SCENARIOS = {
+    "tn": (Scenario.tumor_normal(0.75), 2),
+    "pedigree": (Scenario.from_yaml(synth.SIMPLE_PEDIGREE_YAML), 3),
+    "contamination": (Scenario.from_yaml("""
+samples:
+  sample:
+    resolution: 0.05
+    universe: "[0.0,1.0]"
+  contaminant:
+    resolution: 0.05
+    universe: "[0.0,1.0]"
+events:
+  denovo:  "sample:]0.0,1.0] & contaminant:0.0"
+  other: "sample:[0.0,1.0] & contaminant:]0.0,1.0]"
+"""), 2),
+    "single": (Scenario.from_yaml("""
+samples:
+  s:
+    resolution: 0.02
+    universe: "[0.0,1.0]"
+events:
+  low: "s:]0.0,0.3["
+  high: "s:[0.3,1.0]"
+"""), 1),
+    "l2fc": (Scenario.from_yaml("""
+samples:
+  a:
+    resolution: 0.1
+    universe: "[0.0,1.0]"
+  b:
+    resolution: 0.1
+    universe: "[0.0,1.0]"
+events:
+  up: "l2fc(a,b) > 1.0 & a:]0.0,1.0]"
+  notup: "l2fc(a,b) <= 1.0 & a:]0.0,1.0]"
+"""), 2),
+}
+which = [a for a in sys.argv[3:] if a in SCENARIOS]
+scenario, n_samples = SCENARIOS[which[0] if which else "tn"]
+flatTN = scenario.flatten()
+_gen = gen
+gen = lambda seed: _gen(seed, n_samples)  # noqa: E731
 bad=[]; n=0
 for seed in range(int(sys.argv[1]), int(sys.argv[2])):
     b=gen(seed)
     want=oracle.call_batch(flatTN,b,afd_capacity=64,n_threads=4)
     for name,fn in (("generic", lambda: emu.call_batch(flatTN,b,afd_capacity=64)), ("wave", lambda: emu.wave_call_batch(flatTN,b,afd_capacity=64)[0])):
         try: got=fn()
+        except LookupError: continue  # scenario not served by the wavefront pipeline
         except Exception as e: bad.append((seed,name,repr(e))); continue
         ok=~want.knife_edge(); why=[]
         if not np.array_equal(want.status[ok], got.status[ok]): why.append("status %s %s"%(want.status[ok],got.status[ok]))
@@ -81,12 +124,13 @@ for seed in range(int(sys.argv[1]), int(sys.argv[2])):
 other=[x for x in bad if "known containment bug" not in x[2] or ";" in x[2]]
 print("compared",n,"differences",len(bad),"of which not the known MAP containment bug:",len(other))
 for b_ in other[:15]: print(b_)
-if len(sys.argv)>3:
+if 'show' in sys.argv:
     seed=int(sys.argv[1]); b=gen(seed)
     want=oracle.call_batch(flatTN,b,afd_capacity=64,n_threads=1); got=emu.call_batch(flatTN,b,afd_capacity=64)
     for i in range(b.n_loci):
-        if not np.array_equal(want.map_vaf[i], got.map_vaf[i], equal_nan=True) or want.best_event[i]!=got.best_event[i]:
-            print("locus", i, "flags %x"%b.locus_flags[i], "depths", b.read_offsets[2*i+1]-b.read_offsets[2*i], b.read_offsets[2*i+2]-b.read_offsets[2*i+1])
+        if not np.array_equal(want.map_vaf[i], got.map_vaf[i], equal_nan=True) or want.best_event[i]!=got.best_event[i] or want.map_config[i]!=got.map_config[i]:
+            S_=b.n_samples
+            print("locus", i, "flags %x"%b.locus_flags[i], "depths", [int(b.read_offsets[S_*i+s+1]-b.read_offsets[S_*i+s]) for s in range(S_)])
             print(" oracle map", want.map_vaf[i], "cfg", want.map_config[i], "best", want.best_event[i], "status %x"%want.status[i], "knife", want.knife_edge()[i], want.margin_bias[i], want.margin_adaptive[i])
             print(" emu    map", got.map_vaf[i], "cfg", got.map_config[i], "best", got.best_event[i], "status %x"%got.status[i])
             print(" post", want.log_posteriors[i], got.log_posteriors[i])
