@@ -52,13 +52,21 @@ def python_posterior(obs, prior_estimate=None):
             return -math.inf
         if b == -math.inf:
             return a
+        if math.isnan(a) or math.isnan(b):
+            return math.nan
         return a + math.log1p(math.exp(b - a))
 
     def ln_sum_exp(ps):
-        pmax = max(ps)
-        imax = ps.index(pmax)
+        pmax, imax = ps[0], 0
+        for i, p in enumerate(ps):  # first maximum; a NaN never wins a `>` comparison but poisons the sum
+            if p > pmax:
+                pmax, imax = p, i
         if pmax == -math.inf:
             return -math.inf
+        if any(math.isnan(p) for p in ps):
+            return math.nan
+        if pmax == math.inf:
+            return math.inf
         return pmax + math.log1p(sum(math.exp(p - pmax) for i, p in enumerate(ps) if i != imax and p != -math.inf))
 
     def pdf(o, x):
@@ -69,7 +77,8 @@ def python_posterior(obs, prior_estimate=None):
         if j == 0 or j == len(keys):
             return -math.inf
         (iv, ip), (sv, sp) = o.vaf_dist[j - 1], o.vaf_dist[j]
-        return ln_add_exp(ip, math.log((math.exp(sp) - math.exp(ip)) / (sv - iv)) + math.log(x - iv))
+        with np.errstate(all="ignore"):  # ln of a negative slope is NaN, of zero -inf (f64::ln), not an exception
+            return ln_add_exp(ip, float(np.log(np.float64(math.exp(sp) - math.exp(ip)) / (sv - iv)) + np.log(x - iv)))
 
     max_vaf = max([0.0] + [o.max_posterior_vaf for o in obs])
     prior = ct.Prior(prior_estimate)
@@ -83,14 +92,16 @@ def python_posterior(obs, prior_estimate=None):
             for o in obs:
                 if purity == 0.0:
                     p = o.prob_denovo
-                    lik += math.log1p(-math.exp(p)) if p < -0.693 else math.log(-math.expm1(p))
+                    with np.errstate(all="ignore"):  # P(denovo) = 1: ln(0) = -inf
+                        lik += math.log1p(-math.exp(p)) if p < -0.693 else float(np.log(np.float64(-math.expm1(p))))
                 else:
                     lik += pdf(o, emsv * purity * (o.max_posterior_vaf / max_vaf))
             joint[k, i] = prior.prob(c) + lik
         probs = [joint[k, i] + math.log(2 + (i % 2) * 2) for i in range(1, 100)] + [joint[k, 0], joint[k, 100]]
         rows.append(ln_sum_exp(probs) + math.log(1.0) - math.log(100.0) - math.log(3.0))
     marginal = ln_sum_exp(rows)
-    return joint - marginal, marginal, max_vaf
+    with np.errstate(invalid="ignore"):  # -inf - -inf = NaN, as upstream
+        return joint - marginal, marginal, max_vaf
 
 
 def assert_same(got_post, got_marg, want_post, want_marg, tol=TOL):
@@ -281,3 +292,32 @@ def test_gpu_contamination_nan_positions_and_bad_arguments():
         ct.contamination_posterior(obs, device=0, n_grid=100)  # Simpson needs an odd grid (rust-bio asserts)
     with pytest.raises(engine.EngineError):
         ct.contamination_posterior(obs, device=99)
+
+
+def test_random_small_inputs_agree_everywhere():
+    """Random tiny observation sets (non-monotone AFDs, -inf densities, P(denovo) = 1, repeated MAP VAFs, expected VAFs
+    that hit AFD points exactly or fall outside the support): oracle, pure-Python restatement and the device functions
+    agree on every value, including where -inf and NaN appear."""
+    rng = np.random.Generator(np.random.PCG64(99))
+    grid = np.round(np.linspace(0.0, 1.0, 21), 2)
+    for case in range(60):
+        obs = []
+        for i in range(int(rng.integers(1, 6))):
+            k = int(rng.integers(1, 7))
+            vafs = np.sort(rng.choice(grid, size=k, replace=False))
+            logp = np.round(rng.normal(-2.0, 3.0, k), 3)
+            logp[rng.random(k) < 0.15] = -np.inf
+            prob_denovo = 0.0 if rng.random() < 0.1 else float(np.log(rng.uniform(0.95, 1.0)))
+            obs.append(ct.VariantObservation(prob_denovo, list(zip(vafs.tolist(), logp.tolist())),
+                                             float(rng.choice(grid[1:])), "1", i))
+        prior = ct.PriorEstimate(float(rng.uniform(0, 1)), int(rng.integers(1, 40))) if rng.random() < 0.5 else None
+        post, lik, marg, max_vaf = oracle_posterior(obs, prior)
+        p_post, p_marg, p_max = python_posterior(obs, prior)
+        got = emu.contamination_posterior(obs, prior, chunk=int(rng.integers(1, 4)))
+        assert max_vaf == p_max == got.max_vaf
+        for a, b in ((post, p_post), (post, got.ln_posterior)):
+            assert np.array_equal(np.isnan(a), np.isnan(b)), case
+            assert np.array_equal(np.isneginf(a), np.isneginf(b)) and np.array_equal(np.isposinf(a), np.isposinf(b)), case
+            fin = np.isfinite(a)
+            assert not fin.any() or np.max(np.abs(a[fin] - b[fin])) <= 1e-9, case
+        assert np.array_equal(np.isnan(lik), np.isnan(got.ln_likelihood)), case
