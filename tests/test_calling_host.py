@@ -297,3 +297,36 @@ def test_read_observation_summary_codes():
     assert upper == "1RS.s#-<^$*2E.s..**.."  # ... an upper-case `E` goes last despite its higher count
     assert calling.read_observation_summary(pa[:0], pr[:0], rf[:0]) == "."
     assert calling.read_observation_summary(pa[:1], pr[:1], rf[:1]) == "1AV.p.+>*.."
+
+
+def test_batching_groups_and_filters_do_not_change_what_is_delivered(tn_records):
+    """Property: whatever the batch size, calls arrive in input order with the same content; haplotype groups and a
+    candidate filter interact with batching only through which records are computed."""
+    import copy
+    import random
+    tumor0, normal0, _ = tn_records
+    sc = Scenario.tumor_normal(0.75)
+
+    class EveryThird(calling.CandidateFilter):
+        def filter(self, work_item, sample_names):  # noqa: A003
+            return work_item.index % 3 != 1
+
+    def run(batch_size, groups, use_filter):
+        tumor, normal = copy.deepcopy(tumor0), copy.deepcopy(normal0)
+        for name, members in groups.items():
+            for i in members:
+                tumor[i]["info"]["EVENT"] = normal[i]["info"]["EVENT"] = name
+        w = calling.call_generic(sc, {"tumor": tumor, "normal": normal}, engine=EmuEngine(sc.flatten()),
+                                 batch_size=batch_size, candidate_filter=EveryThird() if use_filter else None)
+        return [(c.pos, tuple(sorted(c.event_probs.items())), repr(c.sample_info)) for c in w.calls]
+
+    rng = random.Random(5)
+    for trial in range(6):
+        idx = list(range(len(tumor0)))
+        rng.shuffle(idx)
+        groups = {"g1": sorted(idx[:3]), "g2": sorted(idx[3:5])} if trial % 2 else {}
+        use_filter = trial >= 3
+        want = run(10 ** 6, groups, use_filter)
+        assert [p for p, _, _ in want] == sorted(p for p, _, _ in want)
+        for batch_size in (1, 2, 5):
+            assert run(batch_size, groups, use_filter) == want
