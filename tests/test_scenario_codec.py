@@ -101,3 +101,28 @@ def test_codec_encode_reproduces_the_reference_files_bit_for_bit(golden_dir):
             assert ints == rec["info"][tag], (rec["pos"], tag)
             n_tags += 1
     assert n_tags >= 3 * 14
+
+
+def test_codec_round_trip_property():
+    """encode_record -> decode_record is the identity on MiniLogProb-representable columns and on every flag
+    combination (hypothesis), including -inf, -0.0, half-precision boundaries and empty pileups."""
+    from hypothesis import given, settings, strategies as st
+    special = st.sampled_from([0.0, -0.0, -np.inf, -10.0, -10.000001, -9.999999, -65504.0, -65520.0, -1e-8, -745.0])
+    values = st.lists(st.one_of(special, st.floats(min_value=-1e5, max_value=0.0, allow_nan=False)), max_size=12)
+
+    @settings(max_examples=150, deadline=None)
+    @given(values, st.integers(0, 2 ** 31 - 1))
+    def check(vals, seed):
+        n = len(vals)
+        rng = np.random.Generator(np.random.PCG64(seed))
+        cols = {k: mini_logprob(np.array(vals, dtype=np.float64) if i == 0 else -rng.exponential(20.0, n))
+                for i, k in enumerate(abi.BATCH_F32_COLUMNS)}
+        flags = ((rng.integers(0, 4, n) << abi.RF_STRAND_SHIFT) | (rng.integers(0, 9, n) << abi.RF_ORIENT_SHIFT)
+                 | (rng.integers(0, 3, n) << abi.RF_ALTLOCUS_SHIFT) | (rng.integers(0, 2, n) * abi.RF_READPOS_MAJOR)
+                 | (rng.integers(0, 2, n) * abi.RF_SOFTCLIPPED) | (rng.integers(0, 2, n) * abi.RF_PAIRED)
+                 | (rng.integers(0, 2, n) * abi.RF_MAX_MAPQ)).astype(np.uint32)
+        got_cols, got_flags, hart, hvar = obs_codec.decode_record(obs_codec.encode_record(cols, flags))
+        assert hart is None and hvar is None and np.array_equal(got_flags, flags)
+        for k in cols:
+            assert np.array_equal(got_cols[k].view(np.uint32), cols[k].astype(np.float32).view(np.uint32)), k
+    check()
