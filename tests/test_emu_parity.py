@@ -180,17 +180,11 @@ def test_four_samples_nested_ranges():
     _compare(oracle.call_batch(flat, b, afd_capacity=128, n_threads=4), emu.call_batch(flat, b, afd_capacity=128))
 
 
-import pytest  # noqa: E402
-
-
-@pytest.mark.xfail(strict=True, reason="known engine bug (DESIGN.md §7): MAP candidates are not checked for containment "
-                                       "in the best event; found by fuzzing read-level inputs")
 def test_map_must_be_contained_in_the_best_event():
     """calling.rs:861-864 skips base events that are not contained in the strongest event. With fewer than 10 reads the
     integration limits are the range bounds themselves even when they are exclusive (formula.rs:1172-1224), so for
     `tumor:]0.0,1.0]` the point 0.0 is evaluated, can have the highest joint (two reference reads) and is still not a
-    valid MAP: the reference reports the next best contained point (0.1), the engine today reports 0.0. Posteriors, best
-    event and the AFD are unaffected."""
+    valid MAP: the reference reports the next best contained point (0.1). Found by the read-level fuzzer."""
     import math
     hi, lo = math.log1p(-1e-3), math.log(1e-3 / 3)
 

@@ -65,8 +65,11 @@ def test_random_scenario(seed):
     assert max_abs_delta(want.log_posteriors[ok], got.log_posteriors[ok]) <= 1e-9
     assert np.array_equal(want.best_event[ok], got.best_event[ok])
     assert np.array_equal(want.n_base_events[ok], got.n_base_events[ok])
-    no_map = np.uint32(1 << 7)  # differs only where an event contains `absent` (true nodes), see above
-    assert np.array_equal(want.status[ok] & ~no_map, got.status[ok] & ~no_map)
+    assert np.array_equal(want.status[ok], got.status[ok])
+    # random events overlap: the MAP is the best base event ANY event recorded that the strongest event contains
+    # (calling.rs:851-864), which the engine reproduces by offering every base event to every event (Ctx::map_global)
+    assert np.array_equal(want.map_vaf[ok], got.map_vaf[ok], equal_nan=True)
+    assert np.array_equal(want.map_config[ok], got.map_config[ok])
 
 
 def random_prior_scenario(seed):

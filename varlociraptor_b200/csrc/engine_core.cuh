@@ -206,6 +206,15 @@ struct Ctx {
     uint32_t map_disc[2 * MAXE];
     int map_cfg[2 * MAXE];
     uint8_t map_set[2 * MAXE];
+    uint32_t map_seq[2 * MAXE]; // evaluation number of the slot's base event (ties: the earlier one wins, like the oracle's stable sort)
+    // MAP candidates are offered to every event's slots (instead of the walked event's own): set for scenarios whose
+    // events overlap, and per locus as soon as an integration's limits lie on an excluded range bound (calling.rs:861-864)
+    int map_global;
+    // second pass of a locus whose base-event log overflowed: only base events that differ from the MAP in at most
+    // one sample are logged (all an allele frequency distribution can use, calling.rs:891-928)
+    int be_filter;
+    double flt_vaf[MAXS];
+    uint32_t flt_disc;
     // operand stack of the tree walk (generic.rs clones LikelihoodOperands per branch / grid point)
     Ops ops[MAXD + 2];
     // adaptive integration state per nesting level (at most one Range level per sample) and the leaf fast path
@@ -1191,6 +1200,61 @@ VLR_DEV_NOINLINE double prior_compute_uncached(Ctx& c_, const Ops& ev) {
 // GenericLikelihood::compute (generic.rs:500-554) + Prior + rust-bio Model::joint_prob bookkeeping.
 // `od` indexes the operand stack c.ops[]. FORCE-INLINED: its one hot call site is the evaluation site of the
 // leaf-level adaptive integrator; everything else reaches it through joint_call().
+VLR_DEV_NOINLINE bool node_contains(const DevScenario* sc, int ni, const double* vaf, uint32_t& lfcs, int exclude);
+
+// `best_event.contains(map_estimates, None)` (calling.rs:861-864, vaftree.rs:42-51) for event e
+VLR_DEV_NOINLINE bool event_contains(const DevScenario* sc, int e, const double* vaf, uint32_t lfc_mask) {
+    const vlr_event_t& ev = sc->events[e];
+    for (int r = 0; r < ev.n_roots; ++r) {
+        uint32_t l = lfc_mask;
+        if (node_contains(sc, ev.first_root + r, vaf, l, -1)) return true;
+    }
+    return false;
+}
+
+// The reference keeps ONE map of base events and reports the best one the strongest event contains (calling.rs:851-864).
+// Offer a base event to the MAP slot of every event (same plain / artifact class): needed when events overlap or when a
+// point on an excluded range bound was evaluated (fewer than 10 reads, narrow ranges: formula.rs:1172-1224), which
+// belongs to another event than the one whose tree produced it.
+VLR_DEV_NOINLINE void map_offer_all(Ctx& c_, const Ops& ops, double j) {
+    Ctx& c = warp_ctx(c_);
+    const DevScenario* sc = c.sc;
+    const int S = sc->S, E = sc->E;
+    const int cls = c.art.id != 0 ? 1 : 0;
+    // Recording order of the oracle (= universe order: event, plain before twin, then evaluation order) decides between
+    // base events of equal probability (the reference: HashMap order). Two events can evaluate the SAME allele
+    // frequencies, once as a discrete and once as a continuous event (e.g. normal = 0.0 as the set value of
+    // somatic_tumor and as the excluded lower bound of somatic_normal): an exact tie upstream, so it is decided by the
+    // recording order here too, whatever the last bit of the two evaluations.
+    const uint32_t seq = ((uint32_t)c.cur_slot << 24) | (c.n_base & 0xffffffu);
+    for (int e = 0; e < E; ++e) {
+        const int slot = 2 * e + cls;
+        if (c.map_set[slot]) {
+            bool same = c.map_cfg[slot] == c.art.id;
+            for (int s = 0; s < S; ++s) same = same && c.map_vaf[slot][s] == ops.vaf[s];
+            const double cur = c.map_joint[slot];
+            const bool better = same ? seq < c.map_seq[slot] : (j > cur || (j == cur && seq < c.map_seq[slot]));
+            if (!better) continue;
+        }
+        if (!event_contains(sc, e, ops.vaf, ops.lfc_mask)) continue;
+        c.map_set[slot] = 1;
+        c.map_joint[slot] = j;
+        c.map_cfg[slot] = c.art.id;
+        c.map_disc[slot] = ops.disc_mask;
+        c.map_seq[slot] = seq;
+        for (int s = 0; s < S; ++s) c.map_vaf[slot][s] = ops.vaf[s];
+    }
+}
+
+// base-event log filter of the second pass (Ctx::be_filter)
+VLR_DEV bool be_keep(const Ctx& c, const double* vaf, uint32_t disc) {
+    if (!c.be_filter) return true;
+    int mismatches = 0;
+    for (int s = 0; s < c.sc->S; ++s)
+        mismatches += !(vaf[s] == c.flt_vaf[s] && ((disc >> s) & 1u) == ((c.flt_disc >> s) & 1u));
+    return mismatches <= 1;
+}
+
 VLR_DEV double joint(Ctx& c, int od) {
     const DevScenario* sc = c.sc;
     const int S = sc->S;
@@ -1242,7 +1306,7 @@ VLR_DEV double joint(Ctx& c, int od) {
     double j = prior + lh;
     if (j != j) c.status |= VLR_ST_NAN;
     // rust-bio Model::joint_prob records every base event; only artifact-free ones can enter an AFD (calling.rs:912)
-    if (c.be != nullptr && c.art.id == 0) {
+    if (c.be != nullptr && c.art.id == 0 && be_keep(c, ops.vaf, ops.disc_mask)) {
         if (c.n_rec < (uint32_t)BE_CAP) {
             // every lane stores the same record (no lane-divergent block in front of the uniform counter update)
             double* e = c.be + (int64_t)c.n_rec * (2 + S);
@@ -1258,11 +1322,14 @@ VLR_DEV double joint(Ctx& c, int od) {
     // bookkeeping for MAP (calling.rs:851-870): best base event per (event, plain | artifact)
     c.n_base++;
     int slot = c.cur_slot;
-    if (!c.map_set[slot] || j > c.map_joint[slot]) {
+    if (c.map_global) {
+        map_offer_all(c, ops, j);
+    } else if (!c.map_set[slot] || j > c.map_joint[slot]) {
         c.map_set[slot] = 1;
         c.map_joint[slot] = j;
         c.map_cfg[slot] = c.art.id;
         c.map_disc[slot] = ops.disc_mask;
+        c.map_seq[slot] = ((uint32_t)slot << 24) | (c.n_base & 0xffffffu);
         for (int s = 0; s < S; ++s) c.map_vaf[slot][s] = ops.vaf[s];
     }
     return j;
@@ -1322,6 +1389,12 @@ VLR_DEV bool ops_lfc_bounds(const Ctx& c, const Ops& ops, int sample, Range& out
         }
     }
     return have;
+}
+
+// Integration limits on an excluded bound of the node's range (formula.rs:1172-1224 returns the bound itself for fewer
+// than 10 reads or narrow ranges): that point is evaluated but belongs to another event -> global MAP bookkeeping.
+VLR_DEV void mark_bound_points(Ctx& c, const Range& vafs, double min_vaf, double max_vaf) {
+    if ((vafs.lex && min_vaf <= vafs.start) || (vafs.rex && max_vaf >= vafs.end)) c.map_global = 1;
 }
 
 VLR_DEV void ops_push(Ops& o, int sample, double vaf, bool discrete) {
@@ -1568,6 +1641,7 @@ VLR_DEV_NOINLINE bool leaf_setup(Ctx& c_, const vlr_node_t& node, int od, double
     const int t = node.sample;
     LeafFast& L = c.leaf;
     if (c.ops[od].lfc_mask != 0 || n_tasks > MT) return false;
+    if (c.map_global || c.be_filter) return false; // every base event goes through joint() (offers to all events / filtered log)
     int n_dep = 0;
     for (int s = 0; s < S; ++s) {
         const int by = sc->samples[s].contamination_by;
@@ -1748,6 +1822,7 @@ VLR_DEV_NOINLINE void leaf_multi_finish(Ctx& c_, int od, unsigned disc, double* 
             c.map_joint[slot] = m.best_f;
             c.map_cfg[slot] = c.art.id;
             c.map_disc[slot] = disc;
+            c.map_seq[slot] = ((uint32_t)slot << 24) | (c.n_base & 0xffffffu);
             for (int s = 0; s < S; ++s)
                 c.map_vaf[slot][s] = s == t ? m.best_x : (s == c.leaf.parent ? m.parent_x : c.ops[od].vaf[s]);
         }
@@ -1889,6 +1964,7 @@ VLR_DEV_NOINLINE bool try_child_batch(Ctx& c_, const vlr_node_t& node, int od, i
     const double res = sc->samples[cs].resolution;
     const double min_vaf = range_observable_min(vafs, n_obs), max_vaf = range_observable_max(vafs, n_obs);
     if (!(min_vaf <= max_vaf) || (max_vaf - min_vaf) < res || n_obs < 5) return false;
+    mark_bound_points(c, vafs, min_vaf, max_vaf);
     // operands of the children: the parent's event is pushed per task (continuous => not discrete)
     c.ops[od + 1] = c.ops[od];
     ops_push(c.ops[od + 1], node.sample, xs[0], false);
@@ -1978,6 +2054,7 @@ VLR_DEV_NOINLINE double density(Ctx& c_, int ni, int od, int level) {
     const double min_vaf = range_observable_min(vafs, n_obs);
     const double max_vaf = range_observable_max(vafs, n_obs);
     if (!(min_vaf <= max_vaf)) c.status |= VLR_ST_NAN; // assert in the reference
+    mark_bound_points(c, vafs, min_vaf, max_vaf);
     if ((max_vaf - min_vaf) < res) return integrate_simpson(c, node, od, min_vaf, max_vaf, 3, level);
     if (n_obs < 5) return integrate_simpson(c, node, od, min_vaf, max_vaf, 11, level);
     if (level >= MAXS) {
@@ -2197,6 +2274,8 @@ VLR_DEV_NOINLINE void run_grouped_chain_events(Ctx& c_, bool twin, double ln_eve
     const double res = sc->samples[cs].resolution;
     const double min_vaf = range_observable_min(vafs, n_obs), max_vaf = range_observable_max(vafs, n_obs);
     if (!(min_vaf <= max_vaf) || (max_vaf - min_vaf) < res || n_obs < 5) return;
+    mark_bound_points(c, vafs, min_vaf, max_vaf);
+    if (c.map_global || c.be_filter) return; // no fast path (leaf_setup): the events go through density()
     // members cut by the Set node's clear-ref shortcut contribute ln 0 without any evaluation
     int m = 0;
     int live[MT];
@@ -2238,7 +2317,9 @@ VLR_DEV_NOINLINE void run_grouped_chain_events(Ctx& c_, bool twin, double ln_eve
 // End of a locus (calling.rs:760-937 after the joint probabilities are known): marginal, posteriors, artifact
 // probability, best event, MAP and AFD from the per-event accumulators and MAP slots in the Ctx. Shared by the
 // generic warp-per-locus engine and the wavefront pipeline (engine_wave.cuh).
-VLR_DEV_NOINLINE void locus_tail(Ctx& c_, int n_twins) {
+// Returns the MAP slot (or -1). with_afd = false: everything but the allele frequency distributions (first pass of a locus
+// whose base-event log overflowed).
+VLR_DEV_NOINLINE int locus_tail(Ctx& c_, int n_twins, bool with_afd = true) {
     Ctx& c = warp_ctx(c_);
     const DevScenario* sc = c.sc;
     const DevResults* res = c.res;
@@ -2305,7 +2386,10 @@ VLR_DEV_NOINLINE void locus_tail(Ctx& c_, int n_twins) {
     {
         int sp = 2 * best_scen, st = 2 * best_scen + 1;
         if (c.map_set[sp]) map_slot = sp;
-        if (is_artifact && c.map_set[st] && (map_slot < 0 || c.map_joint[st] > c.map_joint[sp])) map_slot = st;
+        if (is_artifact && c.map_set[st] &&
+            (map_slot < 0 || c.map_joint[st] > c.map_joint[sp] ||
+             (c.map_joint[st] == c.map_joint[sp] && c.map_seq[st] < c.map_seq[sp])))
+            map_slot = st;
     }
     if (map_slot < 0) c.status |= VLR_ST_NO_MAP;
 
@@ -2323,8 +2407,9 @@ VLR_DEV_NOINLINE void locus_tail(Ctx& c_, int n_twins) {
         if (res->afd_capacity > 0)
             for (int s = 0; s < S; ++s) res->afd_count[locus * S + s] = 0;
     }
-    if (res->afd_capacity > 0) afd_pass(c, best_scen, map_slot, marginal);
+    if (res->afd_capacity > 0 && with_afd) afd_pass(c, best_scen, map_slot, marginal);
     if (lane_id() == 0) res->status[locus] = c.status;
+    return map_slot;
 }
 
 // `coef_sm` (capacity sm_reads) is the warp's shared-memory coefficient arena, `coef` (capacity coef_cap) the global
@@ -2386,38 +2471,66 @@ VLR_DEV void process_locus(const DevScenario* sc, const DevBatch* b, const DevRe
     // joint probability per universe event: plain events get ln 0.5, twins ln 0.5 + ln(1/#configs) (generic.rs:437-441)
     Lse* ev_plain = c.ev_plain;
     Lse* ev_twin = c.ev_twin;
-    for (int e = 0; e < E; ++e) {
-        ev_plain[e].init();
-        ev_twin[e].init();
-    }
     const double twin_prior = plan.n_twins > 0 ? LN_05 + m_log(1.0 / (double)plan.n_twins) : neg_inf();
-    for (int ci = 0; ci <= plan.n_surviving; ++ci) {
-        c.art.id = ci == 0 ? 0 : plan.surviving[ci - 1];
-        c.art.forward_rate = plan.forward_rate;
-        c.art.has_alt_loci = plan.has_alt_loci;
-        for (int s = 0; s < S; ++s) {
-            c.lc_n[s] = 0;
-            read_coefficients(c, s);
-        }
-        unsigned grouped = 0;
-        run_grouped_chain_events(c, ci > 0, ci == 0 ? LN_05 : twin_prior, grouped);
+    const uint32_t prepass_status = c.status;
+    c.map_global = sc->events_overlap;
+    c.be_filter = 0;
+    for (int pass = 0; pass < 2; ++pass) {
         for (int e = 0; e < E; ++e) {
-            const vlr_event_t& ev = sc->events[e];
-            if (ci > 0 && !ev.has_artifact_twin) continue;
-            if (grouped & (1u << e)) continue;
-            c.cur_slot = 2 * e + (ci > 0 ? 1 : 0);
-            for (int r = 0; r < ev.n_roots; ++r) {
-                Ops& ops = c.ops[0];
-                for (int s = 0; s < MAXS; ++s) ops.vaf[s] = 0.0;
-                ops.set_mask = ops.disc_mask = ops.lfc_mask = 0;
-                double d = density(c, ev.first_root + r, 0, 0);
-                if (ci == 0) ev_plain[e].add(LN_05 + d);
-                else ev_twin[e].add(twin_prior + d);
+            ev_plain[e].init();
+            ev_twin[e].init();
+        }
+        for (int ci = 0; ci <= plan.n_surviving; ++ci) {
+            c.art.id = ci == 0 ? 0 : plan.surviving[ci - 1];
+            c.art.forward_rate = plan.forward_rate;
+            c.art.has_alt_loci = plan.has_alt_loci;
+            for (int s = 0; s < S; ++s) {
+                c.lc_n[s] = 0;
+                read_coefficients(c, s);
+            }
+            unsigned grouped = 0;
+            run_grouped_chain_events(c, ci > 0, ci == 0 ? LN_05 : twin_prior, grouped);
+            for (int e = 0; e < E; ++e) {
+                const vlr_event_t& ev = sc->events[e];
+                if (ci > 0 && !ev.has_artifact_twin) continue;
+                if (grouped & (1u << e)) continue;
+                c.cur_slot = 2 * e + (ci > 0 ? 1 : 0);
+                for (int r = 0; r < ev.n_roots; ++r) {
+                    Ops& ops = c.ops[0];
+                    for (int s = 0; s < MAXS; ++s) ops.vaf[s] = 0.0;
+                    ops.set_mask = ops.disc_mask = ops.lfc_mask = 0;
+                    double d = density(c, ev.first_root + r, 0, 0);
+                    if (ci == 0) ev_plain[e].add(LN_05 + d);
+                    else ev_twin[e].add(twin_prior + d);
+                }
             }
         }
+        // The base-event log holds BE_CAP joint evaluations; scenarios that nest full ranges (the reference's
+        // tumor-relapse priors) record more. The reference keeps them all (rust-bio Model::compute), but an allele
+        // frequency distribution only uses those that equal the MAP in all other samples (calling.rs:891-928): take
+        // the MAP from this pass and walk the trees once more, logging only base events within one sample of the MAP.
+        const bool overflow = c.be != nullptr && (c.status & VLR_ST_BASE_EVENTS_OVERFLOW) != 0;
+        if (pass == 1 || !overflow) {
+            locus_tail(c, plan.n_twins);
+            break;
+        }
+        const int map_slot = locus_tail(c, plan.n_twins, false);
+        if (map_slot < 0 || c.map_cfg[map_slot] != 0) { // no MAP or an artifact MAP: no distribution to report
+            if (lane_id() == 0) res->status[locus] = c.status & ~(uint32_t)VLR_ST_BASE_EVENTS_OVERFLOW;
+            break;
+        }
+        for (int s = 0; s < S; ++s) c.flt_vaf[s] = c.map_vaf[map_slot][s];
+        c.flt_disc = c.map_disc[map_slot];
+        c.be_filter = 1;
+        c.n_rec = 0;
+        c.status = prepass_status;
+        c.n_base = 0;
+        c.n_pileup_evals = 0;
+        c.pc_n = 0;
+        c.prior_absent = NAN;
+        for (int i = 0; i < 2 * E; ++i) c.map_set[i] = 0;
+        warp_sync();
     }
-
-    locus_tail(c, plan.n_twins);
 }
 
 

@@ -145,6 +145,8 @@ struct PriorTabEntry {
 struct DevScenario {
     PriorTabEntry* prior_tab; // NULL = no table
     int S, E, n_nodes, n_set_vafs, n_spectra, full_prior, all_uniform, n_lfc_nodes;
+    int events_overlap; // two events may share a VAF combination (scenario_prep.h): MAP candidates are offered to every event
+    int pad_;
     const vlr_sample_t* samples;
     const vlr_event_t* events;
     const vlr_node_t* nodes;

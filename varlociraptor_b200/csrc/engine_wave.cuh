@@ -740,6 +740,12 @@ VLR_DEV void wave_pre_locus(const DevScenario* sc, const DevBatch* b, const Wave
                 defer = true;
                 continue;
             }
+            // a limit on an excluded bound (< 10 reads, narrow ranges: formula.rs:1172-1224) is evaluated but belongs to
+            // another event; the generic engine offers such points to every event's MAP slot (calling.rs:861-864)
+            if ((r.lex && mn <= r.start) || (r.rex && mx >= r.end)) {
+                defer = true;
+                continue;
+            }
             pa = mn;
             pb = mx;
         }
@@ -751,6 +757,10 @@ VLR_DEV void wave_pre_locus(const DevScenario* sc, const DevBatch* b, const Wave
             Range r{child.start, child.end, child.left_exclusive != 0, child.right_exclusive != 0};
             const double mn = range_observable_min(r, c.n_obs[T]), mx = range_observable_max(r, c.n_obs[T]);
             if (!(mn <= mx) || (mx - mn) < smT.resolution || c.n_obs[T] < 5) {
+                defer = true;
+                continue;
+            }
+            if ((r.lex && mn <= r.start) || (r.rex && mx >= r.end)) {
                 defer = true;
                 continue;
             }
@@ -983,6 +993,16 @@ VLR_DEV void wave_finish_locus(const DevScenario* sc, const DevBatch* b, const D
     const WaveLocus& wl = wb.loci[li];
     if (wl.n_cfg == 0) return; // deferred: the generic engine writes this locus
     const int E = sc->E, P = wp.P, T = wp.T;
+    if (res->afd_capacity > 0 && wb.be_n[li] > (unsigned)BE_CAP) {
+        // more base events than the log holds: the generic engine redoes the locus (its second pass logs only what the
+        // allele frequency distributions can use)
+        if (lane_id() == 0) {
+            const unsigned d = wa_add_u32(&wb.cnt->n_deferred, 1u);
+            wb.deferred[d] = (int)locus;
+        }
+        warp_sync();
+        return;
+    }
     if (lane_id() == 0) { // one lane fills the warp's context (shared memory), the warp reads it after the sync
         c.sc = sc;
         c.b = b;
@@ -1020,6 +1040,7 @@ VLR_DEV void wave_finish_locus(const DevScenario* sc, const DevBatch* b, const D
                     c.map_set[slot] = 1;
                     c.map_joint[slot] = lc.map_joint[e];
                     c.map_cfg[slot] = lc.art_id;
+                    c.map_seq[slot] = ((uint32_t)slot << 24) | (uint32_t)ci;
                     c.map_disc[slot] = ((uint32_t)(lc.map_disc[e] & 1u) << P) | ((uint32_t)((lc.map_disc[e] >> 1) & 1u) << T);
                     c.map_vaf[slot][P] = lc.map_vp[e];
                     c.map_vaf[slot][T] = lc.map_vt[e];

@@ -13,8 +13,100 @@ struct ScenarioPrep {
     std::vector<int> lfc_nodes, lfc_ordinal;
     int max_depth = 0;
     int all_uniform = 1;
+    int events_overlap = 0;
     const vlr_scenario_t* src = nullptr;
     const char* error = "";
+
+    // ---- may two events contain the same VAF combination? ----------------------------------------------------------
+    // The reference picks the MAP among ALL recorded base events that the best event's tree contains (calling.rs:851-864,
+    // vaftree.rs:42-51). For pairwise disjoint events those are the base events the best event recorded itself (plus
+    // points on excluded range bounds, which the engines detect per locus); for overlapping events (the reference's
+    // validation only rejects containment, grammar/mod.rs:223-278) the engines offer every base event to every event.
+    // Conservative test over root-to-leaf paths: per sample the Set / Range constraints of both paths must intersect;
+    // log2-fold-change, variant and true nodes are treated as no constraint.
+    struct PathSet {
+        std::vector<std::vector<int>> paths; // node indices (Set / Range nodes) along each root-to-leaf path
+        bool too_many = false;
+    };
+    void collect_paths(const vlr_scenario_t* sc, int ni, std::vector<int>& cur, PathSet& out) {
+        if (out.too_many) return;
+        const vlr_node_t& n = sc->nodes[ni];
+        if (n.kind == VLR_NODE_FALSE) return;
+        const bool constrains = n.kind == VLR_NODE_SET || n.kind == VLR_NODE_RANGE;
+        if (constrains) cur.push_back(ni);
+        if (n.n_children == 0) {
+            if (out.paths.size() >= 4096) out.too_many = true;
+            else out.paths.push_back(cur);
+        } else {
+            for (int k = 0; k < n.n_children; ++k) collect_paths(sc, n.first_child + k, cur, out);
+        }
+        if (constrains) cur.pop_back();
+    }
+    static bool h_range_contains(const vlr_node_t& r, double v) {
+        const bool l = r.left_exclusive ? (r.start < v) : (r.start <= v);
+        const bool rr = r.right_exclusive ? (r.end > v) : (r.end >= v);
+        return l && rr;
+    }
+    bool paths_overlap(const vlr_scenario_t* sc, const std::vector<int>& a, const std::vector<int>& b) const {
+        for (int s = 0; s < sc->n_samples; ++s) {
+            std::vector<const vlr_node_t*> cons;
+            for (int ni : a)
+                if (sc->nodes[ni].sample == s) cons.push_back(&sc->nodes[ni]);
+            for (int ni : b)
+                if (sc->nodes[ni].sample == s) cons.push_back(&sc->nodes[ni]);
+            if (cons.size() < 2) continue;
+            const vlr_node_t* set = nullptr;
+            for (const vlr_node_t* n : cons)
+                if (n->kind == VLR_NODE_SET) set = n;
+            bool any = false;
+            if (set) { // some value of the set satisfies every constraint
+                for (int i = 0; i < set->n_vafs && !any; ++i) {
+                    const double v = sc->set_vafs[set->vaf_offset + i];
+                    bool ok = true;
+                    for (const vlr_node_t* n : cons) {
+                        if (n->kind == VLR_NODE_SET) {
+                            bool in = false;
+                            for (int j = 0; j < n->n_vafs; ++j) in = in || sc->set_vafs[n->vaf_offset + j] == v;
+                            ok = ok && in;
+                        } else {
+                            ok = ok && h_range_contains(*n, v);
+                        }
+                    }
+                    any = ok;
+                }
+            } else { // intersection of intervals
+                double lo = -INFINITY, hi = INFINITY;
+                bool lex = false, rex = false;
+                for (const vlr_node_t* n : cons) {
+                    if (n->start > lo || (n->start == lo && n->left_exclusive)) {
+                        lex = n->start > lo ? n->left_exclusive != 0 : (lex || n->left_exclusive != 0);
+                        lo = n->start;
+                    }
+                    if (n->end < hi || (n->end == hi && n->right_exclusive)) {
+                        rex = n->end < hi ? n->right_exclusive != 0 : (rex || n->right_exclusive != 0);
+                        hi = n->end;
+                    }
+                }
+                any = lo < hi || (lo == hi && !lex && !rex);
+            }
+            if (!any) return false;
+        }
+        return true;
+    }
+    int compute_events_overlap(const vlr_scenario_t* sc) {
+        std::vector<PathSet> ps((size_t)sc->n_events);
+        for (int e = 0; e < sc->n_events; ++e) {
+            std::vector<int> cur;
+            for (int r = 0; r < sc->events[e].n_roots; ++r) collect_paths(sc, sc->events[e].first_root + r, cur, ps[e]);
+            if (ps[e].too_many) return 1;
+        }
+        for (int a = 0; a < sc->n_events; ++a)
+            for (int b = a + 1; b < sc->n_events; ++b)
+                for (const auto& pa : ps[a].paths)
+                    for (const auto& pb : ps[b].paths)
+                        if (paths_overlap(sc, pa, pb)) return 1;
+        return 0;
+    }
 
     int depth_of(const vlr_scenario_t* sc, int ni, int guard) {
         if (guard > sc->n_nodes + 1) return 1 << 20;
@@ -79,6 +171,7 @@ struct ScenarioPrep {
                 return fail("mendelian parent out of range");
             if (!(sm.resolution > 0.0)) return fail("resolution must be positive");
         }
+        events_overlap = compute_events_overlap(sc);
         return true;
     }
 
@@ -90,6 +183,7 @@ struct ScenarioPrep {
         wp.max_rounds = 1;
         const vlr_scenario_t* sc = src;
         if (!sc || sc->n_samples != 2 || sc->n_events > WAVE_MAXE || !all_uniform || !lfc_nodes.empty()) return wp;
+        if (events_overlap) return wp; // the pipeline's MAP bookkeeping is per event (see compute_events_overlap)
         int P = -1, n_leaf_tasks = 0;
         for (int e = 0; e < sc->n_events; ++e) {
             const vlr_event_t& ev = sc->events[e];
@@ -153,6 +247,8 @@ struct ScenarioPrep {
         d.full_prior = src->full_prior;
         d.all_uniform = all_uniform;
         d.n_lfc_nodes = (int)lfc_nodes.size();
+        d.events_overlap = events_overlap;
+        d.pad_ = 0;
         d.samples = samples;
         d.events = events;
         d.nodes = nodes;
