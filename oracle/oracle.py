@@ -20,7 +20,8 @@ _LIB_PATH = os.path.join(_HERE, "libvlr_oracle.so")
 
 class OracleDiag(C.Structure):
     _fields_ = [("margin_bias", C.POINTER(C.c_double)), ("margin_adaptive", C.POINTER(C.c_double)),
-                ("n_pileup_evals", C.POINTER(C.c_uint64)), ("n_read_evals", C.POINTER(C.c_uint64))]
+                ("n_pileup_evals", C.POINTER(C.c_uint64)), ("n_read_evals", C.POINTER(C.c_uint64)),
+                ("lfc_tie", C.POINTER(C.c_uint8))]
 
 
 def build(force: bool = False) -> str:
@@ -82,11 +83,19 @@ class OracleOutput(CallResults):
         self.margin_adaptive = np.full(n_loci, np.inf)
         self.n_pileup_evals = np.zeros(n_loci, dtype=np.uint64)
         self.n_read_evals = np.zeros(n_loci, dtype=np.uint64)
+        self.lfc_tie = np.zeros(n_loci, dtype=np.uint8)
 
     def knife_edge(self, bias_tol: float = 1e-9, adaptive_tol: float = 1e-7) -> np.ndarray:
         """Loci whose result hinges on a discrete decision that is within rounding noise of flipping in the
         reference algorithm itself ("knife-edge loci")."""
         return (self.margin_bias < bias_tol) | (self.margin_adaptive < adaptive_tol)
+
+    def lfc_threshold_ties(self) -> np.ndarray:
+        """Loci whose result changes when the log2-fold-change predicates that were evaluated exactly ON their
+        threshold are decided the other way. The integration limits the reference infers from a predicate
+        (generic.rs:148-174) put abscissae there, where `log2(a) - log2(b) >= v` hangs on the last bit of the
+        platform's log2: identical between this oracle and the reference (both glibc), not across libms (CUDA)."""
+        return self.lfc_tie != 0
 
 
 def call_batch(flat_scenario, batch: LocusBatch, afd_capacity: int = 0, n_threads: int = 1) -> OracleOutput:
@@ -94,7 +103,8 @@ def call_batch(flat_scenario, batch: LocusBatch, afd_capacity: int = 0, n_thread
     cb = batch.as_c()
     cr = out.as_c()
     d = OracleDiag(abi.ptr(out.margin_bias, C.c_double), abi.ptr(out.margin_adaptive, C.c_double),
-                   abi.ptr(out.n_pileup_evals, C.c_uint64), abi.ptr(out.n_read_evals, C.c_uint64))
+                   abi.ptr(out.n_pileup_evals, C.c_uint64), abi.ptr(out.n_read_evals, C.c_uint64),
+                   abi.ptr(out.lfc_tie, C.c_uint8))
     rc = lib().vlr_oracle_call_batch(C.byref(flat_scenario.c), C.byref(cb), C.byref(cr), C.byref(d), n_threads)
     if rc != 0:
         raise RuntimeError("oracle failed with status %d" % rc)

@@ -59,6 +59,7 @@ struct Diag {
     uint64_t n_pileup_evals = 0; // uncached pileup folds
     uint64_t n_read_evals = 0;   // per-read emissions
     uint32_t n_joint_calls = 0;  // joint_prob invocations (base events incl. repeats)
+    uint8_t lfc_tie = 0;         // the result depends on log2-fold-change predicates evaluated exactly on their threshold
 };
 
 inline void note_margin(Diag& d, double lhs, double rhs) {
@@ -519,12 +520,19 @@ inline LfcPred lfc_invert(LfcPred p) {
     default: return {VLR_CMP_NE, p.value};
     }
 }
-inline bool lfc_is_true(LfcPred p, double a, double b, Diag& d) {
+inline bool lfc_is_true(LfcPred p, double a, double b, Diag& d, int tie_mode = 0, bool* tie_seen = nullptr) {
     double lfc;
     if (a == 0.0 && b == 0.0) lfc = 0.0;
     else {
         lfc = std::log2(a) - std::log2(b);
         if (std::isnan(lfc)) d.status |= VLR_ST_NAN;
+    }
+    // Integration limits inferred from the predicate itself (generic.rs:148-174) put an abscissa exactly ON the
+    // threshold (b = a / 2^value), where the outcome hangs on the last bit of the platform's log2 (Engine::call_locus).
+    if (tie_seen && std::isfinite(lfc) && std::fabs(lfc - p.value) <= 1e-12 * std::max(1.0, std::fabs(p.value))) {
+        *tie_seen = true;
+        if (tie_mode == 1) return true;
+        if (tie_mode == 2) return false;
     }
     switch (p.cmp) {
     case VLR_CMP_EQ: return relative_eq(lfc, p.value);
@@ -595,6 +603,8 @@ struct Engine {
     int vartype = 0;
     double het_override = NAN, semr_override = NAN; // ln
     Diag diag;
+    int lfc_tie_mode = 0;      // 0: as computed; 1 / 2: predicates within rounding noise of their threshold hold / fail
+    bool lfc_tie_seen = false;
     // caches (generic.rs:43-53): one per sample
     std::vector<std::map<Key, double>> lh_cache;
     std::map<Key, double> prior_cache;
@@ -650,7 +660,7 @@ struct Engine {
     // GenericLikelihood::compute (generic.rs:500-554)
     double likelihood(const Operands& ops, const Artifacts& b) {
         for (auto& l : ops.lfcs) {
-            if (!lfc_is_true(l.pred, ops.ev[l.a].vaf, ops.ev[l.b].vaf, diag)) return NEG_INF;
+            if (!lfc_is_true(l.pred, ops.ev[l.a].vaf, ops.ev[l.b].vaf, diag, lfc_tie_mode, &lfc_tie_seen)) return NEG_INF;
         }
         double p = 0.0;
         for (int s = 0; s < S; ++s) {
@@ -1227,7 +1237,8 @@ struct Engine {
     }
 
     // ---------------- one locus: preprocess_record + call_record + sample_infos
-    void call_locus(const vlr_batch_t* b, int64_t locus, vlr_results_t* res) {
+    // `ol`: index of the locus in the result arrays
+    void call_locus_once(const vlr_batch_t* b, int64_t locus, vlr_results_t* res, int64_t ol) {
         diag = Diag();
         pileups.assign(S, Pileup());
         lh_cache.assign(S, {});
@@ -1404,7 +1415,7 @@ struct Engine {
                 }
             }
         }
-        double* lp = res->log_posteriors + locus * (E + 1);
+        double* lp = res->log_posteriors + ol * (E + 1);
         std::vector<double> art_post;
         for (size_t i = 0; i < ev_joint.size(); ++i) {
             double post = ev_joint[i] - marginal;
@@ -1417,9 +1428,9 @@ struct Engine {
         for (int e = 0; e < E; ++e)
             if (!(lp[e] < prob_artifact)) is_artifact = false;
         if (is_artifact) diag.status |= VLR_ST_IS_ARTIFACT;
-        if (res->log_marginal) res->log_marginal[locus] = marginal;
-        if (res->best_event) res->best_event[locus] = 2 * ev_scen[best] + (ev_art[best] ? 1 : 0);
-        if (res->n_base_events) res->n_base_events[locus] = diag.n_joint_calls;
+        if (res->log_marginal) res->log_marginal[ol] = marginal;
+        if (res->best_event) res->best_event[ol] = 2 * ev_scen[best] + (ev_art[best] ? 1 : 0);
+        if (res->n_base_events) res->n_base_events[ol] = diag.n_joint_calls;
 
         // sample_infos (calling.rs:844-937): descending posterior, stable
         std::vector<size_t> order(base_events.size());
@@ -1435,15 +1446,15 @@ struct Engine {
             map = &be;
             break;
         }
-        for (int s = 0; s < S; ++s) res->map_vaf[locus * S + s] = NAN;
-        if (res->map_config) res->map_config[locus] = 0;
+        for (int s = 0; s < S; ++s) res->map_vaf[ol * S + s] = NAN;
+        if (res->map_config) res->map_config[ol] = 0;
         if (res->afd_capacity > 0)
-            for (int s = 0; s < S; ++s) res->afd_count[locus * S + s] = 0;
+            for (int s = 0; s < S; ++s) res->afd_count[ol * S + s] = 0;
         if (!map) diag.status |= VLR_ST_NO_MAP;
         else {
-            if (res->map_config) res->map_config[locus] = map->cfg;
+            if (res->map_config) res->map_config[ol] = map->cfg;
             for (int s = 0; s < S; ++s) {
-                res->map_vaf[locus * S + s] = map->cfg != 0 ? 0.0 : map->vaf[s];
+                res->map_vaf[ol * S + s] = map->cfg != 0 ? 0.0 : map->vaf[s];
                 if (res->afd_capacity > 0 && map->cfg == 0) {
                     std::map<double, double> dist;
                     for (size_t oi : order) {
@@ -1464,15 +1475,51 @@ struct Engine {
                             diag.status |= VLR_ST_AFD_TRUNCATED;
                             break;
                         }
-                        res->afd_vaf[(locus * S + s) * res->afd_capacity + n] = kv.first;
-                        res->afd_logp[(locus * S + s) * res->afd_capacity + n] = kv.second;
+                        res->afd_vaf[(ol * S + s) * res->afd_capacity + n] = kv.first;
+                        res->afd_logp[(ol * S + s) * res->afd_capacity + n] = kv.second;
                         n++;
                     }
-                    res->afd_count[locus * S + s] = n;
+                    res->afd_count[ol * S + s] = n;
                 }
             }
         }
-        res->status[locus] = diag.status;
+        res->status[ol] = diag.status;
+    }
+
+    // A log2-fold-change predicate evaluated exactly on its threshold (the integration limits inferred from the
+    // predicate itself put abscissae there, generic.rs:148-174) is decided by the last bit of the platform's log2. If
+    // deciding those evaluations the other way changes the locus' posteriors or MAP, the locus is a knife-edge one
+    // (diagnostic `lfc_tie`); the reported result is the natural one (glibc's log2, what the reference's f64::log2 calls).
+    void call_locus(const vlr_batch_t* b, int64_t locus, vlr_results_t* res) {
+        lfc_tie_mode = 0;
+        lfc_tie_seen = false;
+        call_locus_once(b, locus, res, locus);
+        if (!lfc_tie_seen) return;
+        const Diag natural = diag;
+        const int E = sc->n_events;
+        std::vector<double> lp((size_t)2 * (E + 1)), mv((size_t)2 * S);
+        std::vector<uint32_t> st(2);
+        vlr_results_t tmp;
+        std::memset(&tmp, 0, sizeof tmp);
+        tmp.log_posteriors = lp.data();
+        tmp.map_vaf = mv.data();
+        tmp.status = st.data();
+        for (int mode = 1; mode <= 2; ++mode) {
+            lfc_tie_mode = mode;
+            call_locus_once(b, locus, &tmp, mode - 1);
+        }
+        lfc_tie_mode = 0;
+        bool same = true;
+        for (int e = 0; e <= E; ++e) {
+            const double x = lp[e], y = lp[(E + 1) + e];
+            if (!(x == y || std::fabs(x - y) <= 1e-11 || (std::isnan(x) && std::isnan(y)))) same = false;
+        }
+        for (int s2 = 0; s2 < S; ++s2) {
+            const double x = mv[s2], y = mv[S + s2];
+            if (!(x == y || (std::isnan(x) && std::isnan(y)))) same = false;
+        }
+        diag = natural;
+        diag.lfc_tie = same ? 0 : 1;
     }
 };
 
@@ -1486,6 +1533,7 @@ typedef struct {
     double* margin_adaptive; // [n_loci] min |f(best) - f(other)| over adaptive argmax decisions
     uint64_t* n_pileup_evals; // [n_loci]
     uint64_t* n_read_evals;   // [n_loci]
+    uint8_t* lfc_tie;         // [n_loci] result depends on log2-fold-change predicates evaluated on their threshold
 } vlr_oracle_diag_t;
 
 // Same contract as vlr_call_batch (include/vlr_engine.h), computed sequentially on the CPU;
@@ -1506,6 +1554,7 @@ int32_t vlr_oracle_call_batch(const vlr_scenario_t* sc, const vlr_batch_t* batch
                 if (diag->margin_adaptive) diag->margin_adaptive[i] = eng.diag.margin_adaptive;
                 if (diag->n_pileup_evals) diag->n_pileup_evals[i] = eng.diag.n_pileup_evals;
                 if (diag->n_read_evals) diag->n_read_evals[i] = eng.diag.n_read_evals;
+                if (diag->lfc_tie) diag->lfc_tie[i] = eng.diag.lfc_tie;
             }
         }
     };

@@ -1,5 +1,6 @@
-"""GPU-less check of the engine's control flow: the single-lane host build of engine_core.cuh (tests/emu, test
-infrastructure only) against the oracle. The real parity tests are tests/test_gpu_parity.py (-m gpu)."""
+"""Engine against the oracle, every test twice (fixture `engine_call`, tests/conftest.py): the single-lane host build of
+engine_core.cuh (tests/emu, test infrastructure only: the engine's control flow without a GPU) and the CUDA library
+through the C-ABI (-m gpu). More CUDA-only parity tests are in tests/test_gpu_parity.py."""
 import json
 import os
 
@@ -13,8 +14,8 @@ from varlociraptor_b200 import LocusBatch, Scenario, abi, synth
 TOL = 1e-9
 
 
-def _compare(o, g):
-    ok = ~o.knife_edge()
+def _compare(o, g, ok=None):
+    ok = ~o.knife_edge() if ok is None else ok
     assert max_abs_delta(o.log_posteriors[ok], g.log_posteriors[ok]) <= TOL
     assert max_abs_delta(o.map_vaf[ok], g.map_vaf[ok]) == 0.0
     assert np.array_equal(o.best_event[ok], g.best_event[ok])
@@ -29,29 +30,29 @@ def _compare(o, g):
         assert max_abs_delta(o.afd_logp[valid], g.afd_logp[valid]) <= TOL
 
 
-def test_tumor_normal():
+def test_tumor_normal(engine_call):
     sc, b = synth.tumor_normal(150, seed=5)
     flat = sc.flatten()
-    _compare(oracle.call_batch(flat, b, afd_capacity=96, n_threads=4), emu.call_batch(flat, b, afd_capacity=96))
+    _compare(oracle.call_batch(flat, b, afd_capacity=96, n_threads=4), engine_call(flat, b, afd_capacity=96))
 
 
-def test_pedigree_mixed_snv_indel():
+def test_pedigree_mixed_snv_indel(engine_call):
     sc, b = synth.pedigree(300, seed=6)
     flat = sc.flatten()
-    _compare(oracle.call_batch(flat, b, afd_capacity=8, n_threads=4), emu.call_batch(flat, b, afd_capacity=8))
+    _compare(oracle.call_batch(flat, b, afd_capacity=8, n_threads=4), engine_call(flat, b, afd_capacity=8))
 
 
-def test_depth_skew():
+def test_depth_skew(engine_call):
     sc, b = synth.tumor_normal(24, seed=8, depth_range=(10, 2000))
     flat = sc.flatten()
-    _compare(oracle.call_batch(flat, b, n_threads=4), emu.call_batch(flat, b))
+    _compare(oracle.call_batch(flat, b, n_threads=4), engine_call(flat, b))
 
 
-def test_golden_and_real_pileups(golden_dir):
+def test_golden_and_real_pileups(engine_call, golden_dir):
     exp = json.load(open(os.path.join(golden_dir, "flamegraph_expected.json")))
     flat = Scenario.from_yaml(exp["scenario_yaml"]).flatten()
     b = LocusBatch.load(os.path.join(golden_dir, "flamegraph_obs.npz"))
-    _compare(oracle.call_batch(flat, b, afd_capacity=64), emu.call_batch(flat, b, afd_capacity=64))
+    _compare(oracle.call_batch(flat, b, afd_capacity=64), engine_call(flat, b, afd_capacity=64))
     meta = json.load(open(os.path.join(golden_dir, "real_pileups.json")))
     allb = LocusBatch.load(os.path.join(golden_dir, "real_pileups.npz"))
     lo = 0
@@ -66,12 +67,12 @@ def test_golden_and_real_pileups(golden_dir):
         if len(sc.sample_names) != 1:
             continue
         flat = sc.flatten()
-        _compare(oracle.call_batch(flat, bb, afd_capacity=128), emu.call_batch(flat, bb, afd_capacity=128))
+        _compare(oracle.call_batch(flat, bb, afd_capacity=128), engine_call(flat, bb, afd_capacity=128))
         n += 1
     assert n >= 5
 
 
-def test_edge_cases():
+def test_edge_cases(engine_call):
     flat = Scenario.tumor_normal(0.75).flatten()
     ref = dict(prob_alt=np.log(1e-3 / 3), prob_ref=np.log1p(-1e-3), prob_mapping=np.log1p(-1e-6))
     alt = dict(prob_ref=np.log(1e-3 / 3), prob_alt=np.log1p(-1e-3), prob_mapping=np.log1p(-1e-6))
@@ -90,7 +91,7 @@ def test_edge_cases():
     ]
     b = batch_from_reads(loci)
     o = oracle.call_batch(flat, b, afd_capacity=128)
-    g = emu.call_batch(flat, b, afd_capacity=128)
+    g = engine_call(flat, b, afd_capacity=128)
     _compare(o, g)
     assert g.status[3] & abi.ST_SINGLETON_ADJUSTED
     assert g.status[7] & abi.ST_FILTERED_NONSTANDARD
@@ -111,11 +112,24 @@ events:
 """
 
 
-def test_log2_fold_change_and_variant_nodes():
+def test_log2_fold_change_and_variant_nodes(engine_call):
     sc = Scenario.from_yaml(LFC_YAML)
     flat = sc.flatten()
     _, b = synth.tumor_normal(40, seed=21, depth=30)
-    _compare(oracle.call_batch(flat, b, afd_capacity=128, n_threads=4), emu.call_batch(flat, b, afd_capacity=128))
+    o = oracle.call_batch(flat, b, afd_capacity=128, n_threads=4)
+    g = engine_call(flat, b, afd_capacity=128)
+    if engine_call.kind == "emu":  # same libm as the oracle: every decision is the same one
+        _compare(o, g)
+    else:
+        # The limits the reference infers from a predicate put abscissae exactly ON its threshold (b = a / 2), where
+        # `log2(a) - log2(b) >= 1` hangs on the last bit of log2 - glibc's for the reference and the oracle, CUDA's on
+        # the device. Loci whose result depends on such ties (almost all: OracleOutput.lfc_threshold_ties) can only be
+        # required to agree mostly; the others must agree like everywhere else.
+        ties = o.lfc_threshold_ties()
+        _compare(o, g, ok=~o.knife_edge() & ~ties)
+        same = np.array([max_abs_delta(o.log_posteriors[i], g.log_posteriors[i]) <= TOL and
+                         np.array_equal(o.map_vaf[i], g.map_vaf[i], equal_nan=True) for i in np.nonzero(ties)[0]])
+        assert same.mean() >= 0.7, "log2-fold-change loci that agree with the oracle: %g" % same.mean()
     sc2 = Scenario.from_yaml("""
 samples:
   s:
@@ -128,10 +142,10 @@ events:
     _, b2 = synth.tumor_normal(30, seed=22, depth=25)
     one = LocusBatch(1, b2.read_offsets[::2].copy(), {k: v for k, v in b2.columns.items()}, b2.read_flags,
                      b2.locus_flags)  # merge both pileups of each locus into one sample
-    _compare(oracle.call_batch(flat2, one, afd_capacity=64), emu.call_batch(flat2, one, afd_capacity=64))
+    _compare(oracle.call_batch(flat2, one, afd_capacity=64), engine_call(flat2, one, afd_capacity=64))
 
 
-def test_population_and_somatic_priors():
+def test_population_and_somatic_priors(engine_call):
     """Prior branches beyond uniform/Mendelian: somatic rate (germline odometer), clonal/subclonal inheritance."""
     sc = Scenario.from_yaml("""
 species:
@@ -157,13 +171,13 @@ events:
 """)
     flat = sc.flatten()
     _, b = synth.tumor_normal(25, seed=31, depth=40)
-    _compare(oracle.call_batch(flat, b, afd_capacity=128, n_threads=4), emu.call_batch(flat, b, afd_capacity=128))
+    _compare(oracle.call_batch(flat, b, afd_capacity=128, n_threads=4), engine_call(flat, b, afd_capacity=128))
     full = Scenario.from_yaml(synth.SIMPLE_PEDIGREE_YAML, full_prior=True).flatten()
     _, b3 = synth.pedigree(60, seed=32, depth=30)
-    _compare(oracle.call_batch(full, b3), emu.call_batch(full, b3))
+    _compare(oracle.call_batch(full, b3), engine_call(full, b3))
 
 
-def test_config1_real_pileups_paired_as_tumor_normal(golden_dir):
+def test_config1_real_pileups_paired_as_tumor_normal(engine_call, golden_dir):
     """BASELINE config 1 (plumbing): ~100 tumor-normal loci built by pairing the real-data pileups embedded in the
     reference's testcases (depth 2..2991, indels with prob_sample_alt < 0, homopolymer columns, f16/f32 quantised)."""
     single = LocusBatch.load(os.path.join(golden_dir, "real_pileups.npz"))
@@ -171,16 +185,16 @@ def test_config1_real_pileups_paired_as_tumor_normal(golden_dir):
     pairs = [(i, j) for i in range(n) for j in range(n) if i != j and (i + 2 * j) % 3 != 0][:40]
     b = pair_as_tumor_normal(single, pairs)
     flat = Scenario.tumor_normal(0.8).flatten()
-    _compare(oracle.call_batch(flat, b, afd_capacity=128, n_threads=4), emu.call_batch(flat, b, afd_capacity=128))
+    _compare(oracle.call_batch(flat, b, afd_capacity=128, n_threads=4), engine_call(flat, b, afd_capacity=128))
 
 
-def test_four_samples_nested_ranges():
+def test_four_samples_nested_ranges(engine_call):
     flat = Scenario.from_yaml(FOUR_SAMPLE_YAML).flatten()
     b = four_sample_batch(12, seed=51)
-    _compare(oracle.call_batch(flat, b, afd_capacity=128, n_threads=4), emu.call_batch(flat, b, afd_capacity=128))
+    _compare(oracle.call_batch(flat, b, afd_capacity=128, n_threads=4), engine_call(flat, b, afd_capacity=128))
 
 
-def test_map_must_be_contained_in_the_best_event():
+def test_map_must_be_contained_in_the_best_event(engine_call):
     """calling.rs:861-864 skips base events that are not contained in the strongest event. With fewer than 10 reads the
     integration limits are the range bounds themselves even when they are exclusive (formula.rs:1172-1224), so for
     `tumor:]0.0,1.0]` the point 0.0 is evaluated, can have the highest joint (two reference reads) and is still not a
@@ -196,6 +210,7 @@ def test_map_must_be_contained_in_the_best_event():
     flat = Scenario.tumor_normal(0.75).flatten()
     want = oracle.call_batch(flat, b, afd_capacity=64)
     assert want.map_vaf.tolist() == [[0.5, 0.1]] and want.best_event.tolist() == [2]  # germline_het
-    for got in (emu.call_batch(flat, b, afd_capacity=64), emu.wave_call_batch(flat, b, afd_capacity=64)[0]):
+    # (the wavefront pipeline defers this locus: an integration limit on an excluded bound)
+    for got in (engine_call(flat, b, afd_capacity=64), emu.wave_call_batch(flat, b, afd_capacity=64)[0]):
         assert max_abs_delta(want.log_posteriors, got.log_posteriors) <= TOL
         assert np.array_equal(want.map_vaf, got.map_vaf)

@@ -1,17 +1,15 @@
 """Random scenarios (2-3 samples, set and range universes, nested and/or/not formulas) through the front-end, the
 engine's host emulation and the oracle: tree shapes no hand-written test covers (many roots after the DNF step, true
 nodes, branches that re-add missing samples). Posteriors, best events, status bits and the number of joint evaluations
-must agree; MAP allele frequencies are compared only by the dedicated parity tests, because random events overlap and
-the engine's MAP selection assumes disjoint events: in a 260-seed exploration every MAP difference was
-a base event recorded by one event and contained in another, overlapping one (upstream keeps one global map of base
-events), or an event that contains `absent`."""
+must agree, and so must the MAP allele frequencies although random events overlap: upstream keeps one global map of
+base events and reports the best one the strongest event contains, whichever event evaluated it. Every test runs on
+the host emulation and (-m gpu) on the CUDA library."""
 import random
 
 import numpy as np
 import pytest
 
 from oracle import oracle
-from tests import emu
 from tests.util import max_abs_delta
 from varlociraptor_b200 import Scenario, synth
 
@@ -50,7 +48,7 @@ def random_scenario(seed):
 
 
 @pytest.mark.parametrize("seed", list(range(120)))
-def test_random_scenario(seed):
+def test_random_scenario(engine_call, seed):
     text, n_samples = random_scenario(seed)
     try:
         flat = Scenario.from_yaml(text).flatten()
@@ -60,7 +58,7 @@ def test_random_scenario(seed):
     gen = synth.tumor_normal if n_samples == 2 else synth.pedigree
     b = gen(5, seed=seed, depth=16)[1]
     want = oracle.call_batch(flat, b, n_threads=4)
-    got = emu.call_batch(flat, b)
+    got = engine_call(flat, b)
     ok = ~want.knife_edge()
     assert max_abs_delta(want.log_posteriors[ok], got.log_posteriors[ok]) <= 1e-9
     assert np.array_equal(want.best_event[ok], got.best_event[ok])
@@ -111,7 +109,7 @@ def random_prior_scenario(seed):
 
 
 @pytest.mark.parametrize("seed", range(40))
-def test_random_prior_configuration(seed):
+def test_random_prior_configuration(engine_call, seed):
     """Everything must agree here (events are disjoint), MAP allele frequencies included. Loci whose prior raises an
     invariant violation (status bits NaN / overshoot / prior > 0: the reference panics, e.g. Mendelian inheritance
     with mismatching ploidies, prior.rs:672-676) only need the same status. 1500 configurations were explored."""
@@ -121,7 +119,7 @@ def test_random_prior_configuration(seed):
     for full_prior in (False, True):
         flat = Scenario.from_yaml(text, full_prior=full_prior).flatten()
         want = oracle.call_batch(flat, b, n_threads=4)
-        got = emu.call_batch(flat, b)
+        got = engine_call(flat, b)
         assert np.array_equal(want.status, got.status)
         ok = ~want.knife_edge() & ((want.status & 0xe) == 0)
         assert max_abs_delta(want.log_posteriors[ok], got.log_posteriors[ok]) <= 1e-9

@@ -64,7 +64,7 @@ def test_pedigree_config3_sample(engine_mod):
 
 
 def test_depth_skew_config5_sample(engine_mod):
-    sc, b = synth.tumor_normal(200, seed=synth.SEED_BASE + 5, depth_range=(10, 2000))
+    sc, b = synth.tumor_normal(2000, seed=synth.SEED_BASE + 5, depth_range=(10, 2000))
     flat = sc.flatten()
     o = oracle.call_batch(flat, b, afd_capacity=0, n_threads=os.cpu_count() or 1)
     g = engine_mod.PosteriorEngine(flat).call_batch(b)

@@ -2,14 +2,13 @@
 tests/golden/prior_scenarios.json): population heterozygosity, Mendelian inheritance with sex- and contig-specific
 ploidy, clonal / subclonal inheritance and somatic mutation rates (src/variants/model/prior.rs:298-678). Upstream
 only plots them; here every one goes through scenario front-end -> flattened trees -> engine (host emulation of the
-kernel source) and is compared with the oracle, on autosomes and on the sex chromosomes where ploidies differ."""
+kernel source, and the CUDA library with -m gpu) and is compared with the oracle, on autosomes and on the sex chromosomes where ploidies differ."""
 import json
 import os
 
 import pytest
 
 from oracle import oracle
-from tests import emu
 from tests.test_emu_parity import _compare
 from tests.util import four_sample_batch
 from varlociraptor_b200 import Scenario, synth
@@ -27,7 +26,7 @@ def _batch(n_samples, n_loci, seed):
 
 
 @pytest.mark.parametrize("name,contig", CASES)
-def test_prior_scenario_engine_matches_oracle(golden_dir, name, contig):
+def test_prior_scenario_engine_matches_oracle(engine_call, golden_dir, name, contig):
     text = json.load(open(os.path.join(golden_dir, "prior_scenarios.json")))["scenarios"][name]
     for full_prior in (False, True):
         sc = Scenario.from_yaml(text, full_prior=full_prior).for_contig(contig)
@@ -37,7 +36,7 @@ def test_prior_scenario_engine_matches_oracle(golden_dir, name, contig):
         # holds (4096 per locus), so those loci take the second, filtered pass of process_locus (engine_core.cuh)
         afd = 64
         want = oracle.call_batch(flat, b, afd_capacity=afd, n_threads=4)
-        _compare(want, emu.call_batch(flat, b, afd_capacity=afd))
+        _compare(want, engine_call(flat, b, afd_capacity=afd))
         assert not (want.status & (1 << 1 | 1 << 2 | 1 << 3)).any()  # no NaN / overshoot / positive prior
 
 
