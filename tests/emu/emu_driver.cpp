@@ -135,14 +135,56 @@ extern "C" int32_t vlr_emu_wave_call_batch(const vlr_scenario_t* sc, const vlr_b
     wb.gf = gf.data();
     wb.be = want_be ? be.data() : nullptr;
     wb.be_n = be_n.data();
-    wb.coef_cap = coef_cap;
+    wb.coef_cap = coef_cap * 4;
     wb.lc_cap = lc_cap;
+    std::vector<int> rlist((size_t)lc_cap);
+    std::vector<double> rgx((size_t)W_MAXT * W_GCAP), rgm((size_t)W_MAXT * W_GCAP), rscratch(3 * W_GCAP), cscratch(R_SCRATCH);
+    std::vector<int> rge((size_t)W_MAXT * W_GCAP);
+    wb.rlist = rlist.data();
+    wb.rgx = rgx.data();
+    wb.rgm = rgm.data();
+    wb.rge = rge.data();
+    wb.rscratch = rscratch.data();
+    wb.cscratch = cscratch.data();
+    {
+        const char* e = getenv("VLR_RESIDENT");
+        wb.allow_resident = !(e && e[0] == '0');
+    }
     WarpWs* ws = new WarpWs;
     Ctx* c = new Ctx;
     for (int64_t i = 0; i < L; ++i) wave_pre_locus(&ds, &db, wp, wb, i, (int)i, want_be, *c);
     const int n_lc = (int)std::min<unsigned>(cnt.n_lc, (unsigned)lc_cap);
     for (int k = 0; k < n_lc; ++k) wave_lc_init(&ds, wp, wb, k);
-    for (int k = 0; k < n_lc; ++k) wave_lc_coef(&ds, &db, wp, wb, k, 0, want_be, *c);
+    for (int k = 0; k < n_lc; ++k) wave_lc_coef(&ds, &db, wp, wb, k, 0, want_be, *c, 0);
+    // lc-resident rounds (engine_resident.cuh): one "octet" of a single lane, the slot filled by a plain copy
+    {
+        ROct* oc = new ROct;
+        const WGroup one{0, 1, 1u};
+        const WSplit lane{0, 1, 1u};
+        for (unsigned k = 0; k < cnt.rlist_n + cnt.rlist_back_n; ++k) {
+            const int lci = k < cnt.rlist_n ? rlist[k] : rlist[lc_cap - 1 - (int)(k - cnt.rlist_n)];
+            const WaveLC& L = lcs[lci];
+            oc->lc.lci = lci;
+            oc->lc.li = L.li;
+            oc->lc.ci = L.ci;
+            oc->lc.nqPx = L.nqPx;
+            oc->lc.nqPy = L.nqPy;
+            oc->lc.nqTx = L.nqTx;
+            oc->lc.nqTy = L.nqTy;
+            oc->lc.ksumP = L.ksumP;
+            oc->lc.ksumT = L.ksumT;
+            const int nq = L.nqPx + L.nqPy + L.nqTx + L.nqTy;
+            if (nq > R_SLOT_Q) return -VLR_ERR_INVALID_ARGUMENT;
+            std::memcpy(oc->q, wb.coef + L.coefP, sizeof(double) * R_QW * (size_t)nq);
+            int n_tasks = r_first_tasks(&ds, wp, wb, lci, oc->task, one);
+            for (int round = 0; n_tasks > 0; ++round) {
+                for (int t = 0; t < n_tasks; ++t)
+                    r_task(&ds, wp, wb, *oc, t, n_tasks, wb.rgx + (size_t)t * W_GCAP, wb.rgm + (size_t)t * W_GCAP, wb.rge + (size_t)t * W_GCAP, lane);
+                n_tasks = r_advance(&ds, wp, wb, *oc, round, n_tasks, wb.rgx, wb.rgm, wb.rge, wb.rscratch, want_be, one);
+            }
+        }
+        delete oc;
+    }
     for (int round = 0; round < wp.max_rounds; ++round) {
         for (int which = 0; which < 2; ++which) { // shallow list, then deep list
             const int n_list = (int)(which == 0 ? cnt.list_n[round] : cnt.dlist_n[round]);
@@ -152,8 +194,8 @@ extern "C" int32_t vlr_emu_wave_call_batch(const vlr_scenario_t* sc, const vlr_b
                 for (int t = 0; t < lc.task_count; ++t) {
                     WaveTask& task = wb.tasks[round & 1][lc.task_base + t];
                     const WSplit one{0, 1, 1u};
-                    const double lh = wave_task_parent(lc, task, reinterpret_cast<const double2*>(wb.coef + lc.coefP * 4), false, one);
-                    wave_task_run(&ds, wp, lc, task, reinterpret_cast<const double2*>(wb.coef + lc.coefT * 4), false, lh,
+                    const double lh = wave_task_parent(lc, task, reinterpret_cast<const double2*>(wb.coef + lc.coefP), false, one);
+                    wave_task_run(&ds, wp, lc, task, reinterpret_cast<const double2*>(wb.coef + lc.coefT), false, lh,
                                   wb.gx + (size_t)t * W_GCAP, wb.gf + (size_t)t * W_GCAP, one);
                 }
                 wave_lc_advance(wp, wb, list[k], round, wb.gx, wb.gf, W_GCAP, scratch.data(), want_be, WGroup{0, 1, 1u});

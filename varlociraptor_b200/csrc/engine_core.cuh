@@ -1278,7 +1278,7 @@ VLR_DEV double joint(Ctx& c, int od) {
         double lfc;
         if (a == 0.0 && b2 == 0.0) lfc = 0.0;
         else {
-            lfc = m_log2(a) - m_log2(b2);
+            lfc = m_log2_lfc(a) - m_log2_lfc(b2);
             if (lfc != lfc) c.status |= VLR_ST_NAN;
         }
         bool t;

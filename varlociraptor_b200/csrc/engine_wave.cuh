@@ -52,9 +52,13 @@ VLR_DEV unsigned long long wa_add_u64(unsigned long long* p, unsigned long long 
 #endif
 
 struct WaveCounters {
-    unsigned long long ticket[4]; // pre, finish, deferred (generic kernel), coefficients
-    unsigned long long coef_used; // reads allocated in the coefficient arena
+    unsigned long long ticket[6]; // pre, finish, deferred (generic kernel), coefficients, resident rounds
+    unsigned long long coef_used; // doubles allocated in the coefficient arena
     unsigned int n_lc, n_deferred;
+    // lcs served by the lc-resident round kernel (engine_resident.cuh): those with an outer integration (five rounds of
+    // 5, 3, 3, 3, 7 tasks) from the front of the list, the others (one round) from its back, so that the four octets of
+    // a warp mostly work on lcs of the same shape and stay in step
+    unsigned int rlist_n, rlist_back_n;
     unsigned int list_n[W_MAXROUNDS + 2];  // lcs of the round whose pileups fit a coefficient slot
     unsigned int dlist_n[W_MAXROUNDS + 2]; // lcs of the round with a deeper pileup
     unsigned int task_n[W_MAXROUNDS + 2];
@@ -66,6 +70,8 @@ struct WaveLocus {
     uint32_t status;
     // what the per-lc kernels need from the pre-pass
     uint32_t lf;
+    int resident;   // the locus' lcs are served by the lc-resident round kernel (polynomial arena format)
+    int lc_doubles; // arena doubles per lc
     int coef_total, has_alt_loci;
     int n_obs[2], s_one[2], coef_off[2];
     int surviving[NCFG];
@@ -81,10 +87,12 @@ struct WaveLC { // one (locus, artifact config)
     int ci, art_id;
     int nP, nT;
     int m0P, m0T; // every kept read of the sample has prob_sample_alt == 0
+    int resident;               // arena holds pileup polynomials (engine_resident.cuh) instead of per-read coefficients
+    int nqPx, nqPy, nqTx, nqTy; // ... this many per group, parent pileup at coefP, leaf pileup right behind it
     int task_base, task_count;
     uint32_t status, n_base;
     int outer_pending, outer_n, outer_overflow;
-    int64_t coefP, coefT; // first read of the sample's coefficients in the arena
+    int64_t coefP, coefT; // first double of the sample's coefficients in the arena
     double ksumP, ksumT;
     double ta, tb; // leaf integration limits under the outer event
     double dens[MAXE];
@@ -92,6 +100,12 @@ struct WaveLC { // one (locus, artifact config)
     uint8_t map_set[MAXE], map_disc[MAXE]; // disc: bit 0 parent event discrete, bit 1 leaf event discrete
     Adaptive outer;
     double outer_xs[8];
+    // lc-resident rounds: m1 and m2 of the outer integration's first iteration (abscissa, integral, joint evaluations).
+    // The closing batch revisits one of them (the abandoned arm's midpoint, adaptive_integration.rs:96-106, is bitwise
+    // that m1 or m2): the reference evaluates it again and gets the same number, here it is remembered.
+    double om_x[2], om_val[2];
+    uint32_t om_nev[2];
+    int outer_skip; // the next round's first outer abscissa is om_x[outer_skip - 1] and has no task
 };
 
 struct WaveTask {
@@ -110,7 +124,7 @@ struct WaveBufs {
     WaveLC* lcs;
     double* og_x; // [lc_cap][W_OGRID]
     double* og_f;
-    double* coef; // arena, 4 doubles per read
+    double* coef; // arena: 4 doubles per read [alpha, beta, gamma, u], or 6 per polynomial for resident lcs
     WaveTask* tasks[2];
     int* list[2];
     int* dlist[2];
@@ -119,8 +133,16 @@ struct WaveBufs {
     double* gf;
     double* be;      // base-event log per locus of the sub-chunk (AFD only): [n_sub][BE_CAP][2 + S]
     unsigned* be_n;  // [n_sub]
-    int64_t coef_cap; // reads
+    int64_t coef_cap; // doubles
     int lc_cap;
+    // lc-resident round kernel (engine_resident.cuh)
+    int* rlist;        // its lcs
+    double* rgx;       // per octet and task: visited abscissae [W_GCAP] ...
+    double* rgm;       // ... mantissas ...
+    int* rge;          // ... and binary exponents of the values
+    double* rscratch;  // per octet: 3 x W_GCAP doubles (sorting grids longer than the shared-memory scratch)
+    double* cscratch;  // per warp of the coefficient kernel: R_SCRATCH doubles
+    int allow_resident;
 };
 
 // ---------------------------------------------------------------------------------------------- pileup evaluation
@@ -698,6 +720,8 @@ VLR_DEV_NOINLINE void wave_lc_advance(const WavePlan& wp, const WaveBufs& wb, in
     grp_sync(grp);
 }
 
+#include "engine_resident.cuh"
+
 // ---------------------------------------------------------------------------------------------- prep
 // Three kernels, so that each one's code fits the instruction caches (a single warp-per-locus prep kernel spent most of
 // its cycles waiting for instruction fetch: 43 KB of text, 16 warps per SM in different phases):
@@ -782,6 +806,8 @@ VLR_DEV void wave_pre_locus(const DevScenario* sc, const DevBatch* b, const Wave
     }
     const int n_cfg = 1 + plan.n_surviving;
     const int coef_total = c.coef_total;
+    const bool resident = wb.allow_resident && c.s_one[P] && c.s_one[T] && r_fits(c.n_obs[P], c.n_obs[T]);
+    const int lc_doubles = resident ? R_QW * (r_qcap(c.n_obs[P]) + r_qcap(c.n_obs[T])) : 4 * coef_total;
     int lc_base = 0;
     int64_t coef_base = 0;
     bool allocated = false;
@@ -791,7 +817,7 @@ VLR_DEV void wave_pre_locus(const DevScenario* sc, const DevBatch* b, const Wave
         unsigned long long cb = 0;
         if (lane_id() == 0) {
             lb = wa_add_u32(&wb.cnt->n_lc, (unsigned)n_cfg);
-            cb = wa_add_u64(&wb.cnt->coef_used, (unsigned long long)n_cfg * (unsigned long long)coef_total);
+            cb = wa_add_u64(&wb.cnt->coef_used, (unsigned long long)n_cfg * (unsigned long long)lc_doubles);
         }
 #ifndef VLR_HOST_EMU
         lb = __shfl_sync(FULL, lb, 0, LANES);
@@ -799,7 +825,7 @@ VLR_DEV void wave_pre_locus(const DevScenario* sc, const DevBatch* b, const Wave
 #endif
         lc_base = (int)lb;
         coef_base = (int64_t)cb;
-        if ((int64_t)lb + n_cfg > (int64_t)wb.lc_cap || coef_base + (int64_t)n_cfg * coef_total > wb.coef_cap) defer = true;
+        if ((int64_t)lb + n_cfg > (int64_t)wb.lc_cap || coef_base + (int64_t)n_cfg * lc_doubles > wb.coef_cap) defer = true;
     }
     if (lane_id() != 0) return;
     if (defer) {
@@ -821,6 +847,8 @@ VLR_DEV void wave_pre_locus(const DevScenario* sc, const DevBatch* b, const Wave
     wl.lf = c.lf;
     wl.coef_base = coef_base;
     wl.coef_total = coef_total;
+    wl.resident = resident ? 1 : 0;
+    wl.lc_doubles = lc_doubles;
     wl.singleton_row = c.singleton_row;
     wl.forward_rate = plan.forward_rate;
     wl.has_alt_loci = plan.has_alt_loci ? 1 : 0;
@@ -859,12 +887,15 @@ VLR_DEV void wave_lc_init(const DevScenario* sc, const WavePlan& wp, const WaveB
     lc.m0T = wl.s_one[T];
     lc.status = 0;
     lc.n_base = 0;
-    lc.coefP = wl.coef_base + (int64_t)ci * wl.coef_total + wl.coef_off[P];
-    lc.coefT = wl.coef_base + (int64_t)ci * wl.coef_total + wl.coef_off[T];
+    lc.resident = wl.resident;
+    lc.nqPx = lc.nqPy = lc.nqTx = lc.nqTy = 0; // wave_lc_coef
+    lc.coefP = wl.coef_base + (int64_t)ci * wl.lc_doubles + (wl.resident ? 0 : 4 * wl.coef_off[P]);
+    lc.coefT = wl.coef_base + (int64_t)ci * wl.lc_doubles + (wl.resident ? 0 : 4 * wl.coef_off[T]);
     lc.ksumP = lc.ksumT = 0.0; // wave_lc_coef
     lc.outer_pending = 0;
     lc.outer_n = 0;
     lc.outer_overflow = 0;
+    lc.outer_skip = 0;
     lc.ta = lc.tb = 0.0;
     int n_tasks = 0;
     for (int e = 0; e < MAXE; ++e) {
@@ -879,6 +910,18 @@ VLR_DEV void wave_lc_init(const DevScenario* sc, const WavePlan& wp, const WaveB
     lc.task_base = 0;
     lc.task_count = 0;
     if (n_tasks == 0) return;
+    if (wl.resident) { // its tasks live in the shared memory of the octet that takes the lc (r_first_tasks)
+        bool outer = false;
+        for (int e = 0; e < E; ++e) outer = outer || (wl.ev_kind[e] == 3 && !(ci > 0 && !sc->events[e].has_artifact_twin));
+        if (outer) {
+            const unsigned at = wa_add_u32(&wb.cnt->rlist_n, 1u);
+            wb.rlist[at] = lci;
+        } else {
+            const unsigned at = wa_add_u32(&wb.cnt->rlist_back_n, 1u);
+            wb.rlist[wb.lc_cap - 1 - (int)at] = lci;
+        }
+        return;
+    }
     const unsigned tb = wa_add_u32(&wb.cnt->task_n[0], (unsigned)n_tasks);
     WaveTask* nt = wb.tasks[0] + tb;
     int k = 0;
@@ -910,7 +953,7 @@ VLR_DEV void wave_lc_init(const DevScenario* sc, const WavePlan& wp, const WaveB
 // One warp per lc: the per-read coefficients of both samples under the lc's artifact config, and the point events
 // (both nodes a single VAF, e.g. the absent event): one joint evaluation each, like joint() of the generic engine.
 VLR_DEV void wave_lc_coef(const DevScenario* sc, const DevBatch* b, const WavePlan& wp, const WaveBufs& wb, int lci,
-                          int64_t sub_lo, bool want_be, Ctx& c) {
+                          int64_t sub_lo, bool want_be, Ctx& c, int warp_global) {
     WaveLC& lc = wb.lcs[lci];
     const int li = lc.li, ci = lc.ci;
     if (li < 0) return; // dead
@@ -926,7 +969,10 @@ VLR_DEV void wave_lc_coef(const DevScenario* sc, const DevBatch* b, const WavePl
     c.art.id = ci == 0 ? 0 : wl.surviving[ci - 1];
     c.art.forward_rate = wl.forward_rate;
     c.art.has_alt_loci = wl.has_alt_loci != 0;
-    c.coef = wb.coef + (wl.coef_base + (int64_t)ci * wl.coef_total) * 4;
+    // resident lcs: per-read coefficients into the warp's scratch (the point events below evaluate them there), then
+    // multiplied out into the arena's pileup polynomials; other lcs: per-read coefficients straight into the arena
+    double* const scratch = wb.cscratch + (size_t)warp_global * R_SCRATCH;
+    c.coef = wl.resident ? scratch : wb.coef + (wl.coef_base + (int64_t)ci * wl.lc_doubles);
     c.coef_in_sm = 0;
     c.coef_cap = wl.coef_total;
     c.coef_total = wl.coef_total;
@@ -976,11 +1022,23 @@ VLR_DEV void wave_lc_coef(const DevScenario* sc, const DevBatch* b, const WavePl
         }
         warp_sync();
     }
+    int nq[4] = {0, 0, 0, 0};
+    if (wl.resident) {
+        double* cd = scratch + 4 * (size_t)wl.coef_total;
+        double* out = wb.coef + lc.coefP;
+        r_build_pileup(scratch + 4 * (size_t)wl.coef_off[P], wl.n_obs[P], cd, out, nq[0], nq[1]);
+        out += (size_t)(nq[0] + nq[1]) * R_QW;
+        r_build_pileup(scratch + 4 * (size_t)wl.coef_off[T], wl.n_obs[T], cd, out, nq[2], nq[3]);
+    }
     if (lane_id() == 0) {
         lc.ksumP = c.ksum[P];
         lc.ksumT = c.ksum[T];
         lc.status |= c.status;
         lc.n_base += n_base;
+        lc.nqPx = nq[0];
+        lc.nqPy = nq[1];
+        lc.nqTx = nq[2];
+        lc.nqTy = nq[3];
     }
     warp_sync();
 }

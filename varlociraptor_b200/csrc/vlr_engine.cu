@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(THREADS, VLR_PREP_MIN_CTAS) vlr_wave_coef_kern
         if (lane_id() == 0) t = atomicAdd(&p.wb.cnt->ticket[3], 1ULL);
         t = __shfl_sync(FULL, t, 0, LANES);
         if (t >= n_lc) break;
-        wave_lc_coef(&p.sc, &p.b, p.wp, p.wb, (int)t, p.sub_lo, p.want_be != 0, c);
+        wave_lc_coef(&p.sc, &p.b, p.wp, p.wb, (int)t, p.sub_lo, p.want_be != 0, c, (int)(blockIdx.x * WARPS_PER_CTA) + group_in_cta());
         warp_sync();
     }
 }
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(WAVE_ROUND_THREADS, VLR_ROUND_MIN_CTAS) vlr_wa
                     const WaveLC& L = wb.lcs[s_lc[g]];
                     const int nr = parent ? L.nP : L.nT;
                     if (nr > slot_reads) continue; // does not even fit the whole region: read from the arena (L2)
-                    const double2* src = reinterpret_cast<const double2*>(wb.coef + (parent ? L.coefP : L.coefT) * 4);
+                    const double2* src = reinterpret_cast<const double2*>(wb.coef + (parent ? L.coefP : L.coefT));
                     double2* dst = reinterpret_cast<double2*>(slot_of(g));
                     if (pass == 0) {
                         for (int i = lane; i < nr * 2; i += 32) __pipeline_memcpy_async(dst + i, src + i, sizeof(double2));
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(WAVE_ROUND_THREADS, VLR_ROUND_MIN_CTAS) vlr_wa
                     const WaveLC& L = wb.lcs[s_lc[g_deep]];
                     const int nr = parent ? L.nP : L.nT;
                     if (nr <= slot_reads) {
-                        const double2* src = reinterpret_cast<const double2*>(wb.coef + (parent ? L.coefP : L.coefT) * 4);
+                        const double2* src = reinterpret_cast<const double2*>(wb.coef + (parent ? L.coefP : L.coefT));
                         double2* dst = reinterpret_cast<double2*>(slots);
                         for (int i = tid; i < nr * 2; i += WAVE_ROUND_THREADS) __pipeline_memcpy_async(dst + i, src + i, sizeof(double2));
                     }
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(WAVE_ROUND_THREADS, VLR_ROUND_MIN_CTAS) vlr_wa
                 const WaveLC& L = wb.lcs[s_lc[g_mine]];
                 const bool in_sm = L.nP <= slot_reads;
                 const double2* coP = in_sm ? reinterpret_cast<const double2*>(slot_of(g_mine))
-                                           : reinterpret_cast<const double2*>(wb.coef + L.coefP * 4);
+                                           : reinterpret_cast<const double2*>(wb.coef + L.coefP);
                 lh_const = wave_task_parent(L, tasks[L.task_base + q], coP, in_sm, sp);
             }
             __syncthreads();
@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(WAVE_ROUND_THREADS, VLR_ROUND_MIN_CTAS) vlr_wa
                 WaveTask& t = tasks[L.task_base + q];
                 const bool in_sm = L.nT <= slot_reads;
                 const double2* coT = in_sm ? reinterpret_cast<const double2*>(slot_of(g_mine))
-                                           : reinterpret_cast<const double2*>(wb.coef + L.coefT * 4);
+                                           : reinterpret_cast<const double2*>(wb.coef + L.coefT);
                 const size_t row = (size_t)(blockIdx.x * blockDim.x) + (size_t)(s_off[g_mine] + q);
                 wave_task_run(&p.sc, p.wp, L, t, coT, in_sm, lh_const, wb.gx + row * W_GCAP, wb.gf + row * W_GCAP, sp);
             }
@@ -353,8 +353,8 @@ __global__ void __launch_bounds__(WAVE_ROUND_THREADS, VLR_ROUND_MIN_CTAS) vlr_wa
             nP = L.nP;
             nT = L.nT;
             task_base = L.task_base;
-            srcP = reinterpret_cast<const double2*>(wb.coef + L.coefP * 4);
-            srcT = reinterpret_cast<const double2*>(wb.coef + L.coefT * 4);
+            srcP = reinterpret_cast<const double2*>(wb.coef + L.coefP);
+            srcT = reinterpret_cast<const double2*>(wb.coef + L.coefT);
         }
         // lanes per task: a function of the lc alone (bitwise reproducible results), <= 8 threads per lc
         const int H = cnt <= 1 ? 8 : (cnt <= 2 ? 4 : (cnt <= 4 ? 2 : 1));
@@ -382,6 +382,113 @@ __global__ void __launch_bounds__(WAVE_ROUND_THREADS, VLR_ROUND_MIN_CTAS) vlr_wa
         __syncwarp();
         if (lci >= 0)
             wave_lc_advance(p.wp, wb, lci, round, wb.gx + row0 * W_GCAP, wb.gf + row0 * W_GCAP, W_GCAP, slot, p.want_be != 0, grp);
+    }
+}
+
+// ---- the lc-resident round kernel (engine_resident.cuh) -------------------------------------------------------------
+// Persistent grid; a warp is four octets; an octet takes an lc by ticket, bulk-copies its pileup polynomials into its
+// shared-memory slot (cp.async.bulk, completion on the slot's mbarrier) and runs every round of the lc: (1) the lc's
+// tasks, H = 8 / #tasks lanes each — parent pileup, then the adaptive search of the leaf allele frequency to completion;
+// (2) the octet closes the round: trapezoids, MAP, the outer integration's next abscissae = the next round's tasks.
+// Only __syncwarp between the phases; an octet whose lc is complete takes the next one while its neighbours go on.
+constexpr int RES_THREADS = 64; // two warps = eight octets: 36 KB of shared memory, six CTAs per SM
+constexpr int RES_OCTETS = RES_THREADS / 8;
+constexpr size_t RES_SMEM = sizeof(vlr_small::ROct) * RES_OCTETS;
+#ifndef VLR_RES_MIN_CTAS
+#define VLR_RES_MIN_CTAS 6
+#endif
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(RES_THREADS, VLR_RES_MIN_CTAS) vlr_wave_resident_kernel(const __grid_constant__ WaveParams p) {
+    using namespace vlr_small;
+    const WaveBufs& wb = p.wb;
+    ROct* octs = reinterpret_cast<ROct*>(vlr_smem);
+    const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5, oct = lane >> 3, l8 = lane & 7;
+    ROct& oc = octs[warp * 4 + oct];
+    const unsigned omask = 0xffu << (oct * 8);
+    WGroup grp;
+    grp.lane = l8;
+    grp.n = 8;
+    grp.mask = omask;
+    const size_t og = (size_t)blockIdx.x * RES_OCTETS + (size_t)(warp * 4 + oct); // this octet's rows of the global scratch
+    double* const rows_x = wb.rgx + og * (W_MAXT * W_GCAP);
+    double* const rows_m = wb.rgm + og * (W_MAXT * W_GCAP);
+    int* const rows_e = wb.rge + og * (W_MAXT * W_GCAP);
+    double* const big = wb.rscratch + og * (3 * W_GCAP);
+    const unsigned n_front = wb.cnt->rlist_n, n_list = n_front + wb.cnt->rlist_back_n;
+    const unsigned bar = smem_u32(&oc.bar);
+    if (l8 == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    unsigned parity = 0;
+    bool have = false;
+    int round = 0, cnt = 0;
+    for (;;) {
+        if (!have) {
+            unsigned long long t = 0;
+            if (l8 == 0) t = atomicAdd(&wb.cnt->ticket[4], 1ULL);
+            t = __shfl_sync(omask, t, 0, 8);
+            if (t < (unsigned long long)n_list) {
+                const int lci = t < n_front ? wb.rlist[t] : wb.rlist[wb.lc_cap - 1 - (int)(t - n_front)];
+                const WaveLC& L = wb.lcs[lci];
+                const int nq = L.nqPx + L.nqPy + L.nqTx + L.nqTy;
+                __syncwarp(omask); // nobody of the octet still reads the slot
+                if (l8 == 0) {
+                    oc.lc.lci = lci;
+                    oc.lc.li = L.li;
+                    oc.lc.ci = L.ci;
+                    oc.lc.nqPx = L.nqPx;
+                    oc.lc.nqPy = L.nqPy;
+                    oc.lc.nqTx = L.nqTx;
+                    oc.lc.nqTy = L.nqTy;
+                    oc.lc.ksumP = L.ksumP;
+                    oc.lc.ksumT = L.ksumT;
+                    const unsigned bytes = (unsigned)nq * (unsigned)(R_QW * sizeof(double));
+                    // the slot was last read through the generic proxy: order those reads before the bulk write
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                     smem_u32(oc.q)),
+                                 "l"(wb.coef + L.coefP), "r"(bytes), "r"(bar)
+                                 : "memory");
+                }
+                cnt = r_first_tasks(&p.sc, p.wp, wb, lci, oc.task, grp); // while the copy is in flight
+                unsigned ok = 0;
+                while (!ok) {
+                    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                                 : "=r"(ok)
+                                 : "r"(bar), "r"(parity)
+                                 : "memory");
+                }
+                parity ^= 1u;
+                have = true;
+                round = 0;
+            }
+        }
+        if (!__any_sync(0xffffffffu, have)) break;
+        __syncwarp();
+        if (have) {
+            // lanes per task: a function of the lc's task count alone (bitwise reproducible results)
+            const int H = cnt <= 1 ? 8 : (cnt <= 2 ? 4 : (cnt <= 4 ? 2 : 1));
+            const int q = l8 / H;
+            if (q < cnt) {
+                WSplit sp;
+                sp.H = H;
+                sp.h = l8 & (H - 1);
+                sp.mask = ((1u << H) - 1u) << (lane & ~(H - 1));
+                r_task(&p.sc, p.wp, wb, oc, q, cnt, rows_x + (size_t)q * W_GCAP, rows_m + (size_t)q * W_GCAP, rows_e + (size_t)q * W_GCAP, sp);
+            }
+        }
+        __syncwarp();
+        if (have) {
+            const int next = r_advance(&p.sc, p.wp, wb, oc, round, cnt, rows_x, rows_m, rows_e, big, p.want_be != 0, grp);
+            if (next == 0) have = false;
+            cnt = next;
+            round++;
+        }
     }
 }
 
@@ -454,6 +561,7 @@ struct Slot { // one in-flight chunk of vlr_call_batch
     bool be_ready = false;
     // wavefront pipeline workspace (one sub-chunk of loci at a time)
     DevBuf w_cnt, w_loci, w_lcs, w_ogx, w_ogf, w_coef, w_tasks[2], w_list[2], w_dlist[2], w_deferred, w_gx, w_gf, w_be, w_ben;
+    DevBuf w_rlist, w_rgx, w_rgm, w_rge, w_rscratch, w_cscratch; // lc-resident round kernel
 };
 
 } // namespace
@@ -467,7 +575,8 @@ struct vlr_ctx {
     bool small = false;   // which engine variant serves this scenario
     bool wave = false;    // two-level chain scenario: the wavefront pipeline serves it (deferring loci it cannot)
     WavePlan wplan;
-    int wave_grid_prep = 0, wave_grid_round = 0, wave_grid_finish = 0;
+    int wave_grid_prep = 0, wave_grid_round = 0, wave_grid_finish = 0, wave_grid_res = 0;
+    bool resident = true; // VLR_RESIDENT=0: per-round kernels only (A/B measurements)
     size_t wave_smem_prep = 0;
     int ctx_stride = 0;
     size_t smem_bytes = 0;
@@ -533,14 +642,23 @@ vlr_status_t launch_wave(vlr_ctx* ctx, Slot& sl, const DevBatch& b, const DevRes
         if (v >= 256 && v <= (1 << 20)) n_sub_cap = want_be ? std::min(v, 8192) : v;
     }
     const int lc_cap = n_sub_cap * 6;
-    const int64_t coef_cap = (int64_t)n_sub_cap * avg_reads * 6 + (1 << 20);
+    const int64_t coef_cap = ((int64_t)n_sub_cap * avg_reads * 6 + (1 << 20)) * 4; // doubles
     const int g_stride = ctx->wave_grid_round * WAVE_ROUND_THREADS;
     CK(sl.w_cnt.ensure(sizeof(WaveCounters)));
     CK(sl.w_loci.ensure(sizeof(WaveLocus) * (size_t)n_sub_cap));
     CK(sl.w_lcs.ensure(sizeof(WaveLC) * (size_t)lc_cap));
     CK(sl.w_ogx.ensure(sizeof(double) * (size_t)lc_cap * W_OGRID));
     CK(sl.w_ogf.ensure(sizeof(double) * (size_t)lc_cap * W_OGRID));
-    CK(sl.w_coef.ensure(sizeof(double) * 4 * (size_t)coef_cap));
+    CK(sl.w_coef.ensure(sizeof(double) * (size_t)coef_cap));
+    {
+        const size_t n_oct = (size_t)ctx->wave_grid_res * RES_OCTETS;
+        CK(sl.w_rlist.ensure(sizeof(int) * (size_t)lc_cap));
+        CK(sl.w_rgx.ensure(sizeof(double) * n_oct * W_MAXT * W_GCAP));
+        CK(sl.w_rgm.ensure(sizeof(double) * n_oct * W_MAXT * W_GCAP));
+        CK(sl.w_rge.ensure(sizeof(int) * n_oct * W_MAXT * W_GCAP));
+        CK(sl.w_rscratch.ensure(sizeof(double) * n_oct * 3 * W_GCAP));
+        CK(sl.w_cscratch.ensure(sizeof(double) * (size_t)ctx->wave_grid_prep * WARPS_PER_CTA * R_SCRATCH));
+    }
     for (int i = 0; i < 2; ++i) {
         CK(sl.w_tasks[i].ensure(sizeof(WaveTask) * (size_t)lc_cap * W_MAXT));
         CK(sl.w_list[i].ensure(sizeof(int) * (size_t)lc_cap));
@@ -575,6 +693,13 @@ vlr_status_t launch_wave(vlr_ctx* ctx, Slot& sl, const DevBatch& b, const DevRes
     p.wb.be_n = (unsigned*)sl.w_ben.p;
     p.wb.coef_cap = coef_cap;
     p.wb.lc_cap = lc_cap;
+    p.wb.rlist = (int*)sl.w_rlist.p;
+    p.wb.rgx = (double*)sl.w_rgx.p;
+    p.wb.rgm = (double*)sl.w_rgm.p;
+    p.wb.rge = (int*)sl.w_rge.p;
+    p.wb.rscratch = (double*)sl.w_rscratch.p;
+    p.wb.cscratch = (double*)sl.w_cscratch.p;
+    p.wb.allow_resident = ctx->resident ? 1 : 0;
     p.ws = (WarpWs*)sl.ws.p;
     p.want_be = want_be ? 1 : 0;
     {
@@ -602,6 +727,7 @@ vlr_status_t launch_wave(vlr_ctx* ctx, Slot& sl, const DevBatch& b, const DevRes
         vlr_wave_pre_kernel<<<ctx->wave_grid_prep, THREADS, ctx->wave_smem_prep, stream>>>(p);
         vlr_wave_lcinit_kernel<<<ctx->n_sms * 4, 256, 0, stream>>>(p);
         vlr_wave_coef_kernel<<<ctx->wave_grid_prep, THREADS, ctx->wave_smem_prep, stream>>>(p);
+        if (ctx->resident) vlr_wave_resident_kernel<<<ctx->wave_grid_res, RES_THREADS, RES_SMEM, stream>>>(p);
         for (int round = 0; round < ctx->wplan.max_rounds; ++round) {
             vlr_wave_round_warp_kernel<<<ctx->wave_grid_round, WAVE_ROUND_THREADS, WAVE_ROUND_SMEM, stream>>>(p, round);
             vlr_wave_round_kernel<<<ctx->wave_grid_round, WAVE_ROUND_THREADS, WAVE_ROUND_SMEM, stream>>>(p, round);
@@ -609,7 +735,7 @@ vlr_status_t launch_wave(vlr_ctx* ctx, Slot& sl, const DevBatch& b, const DevRes
         vlr_wave_finish_kernel<<<ctx->wave_grid_finish, THREADS, ctx->wave_smem_prep, stream>>>(p);
         vlr_call_kernel_vlr_small<<<ctx->grid, THREADS, ctx->smem_bytes, stream>>>(gp);
         CK(cudaGetLastError());
-        ctx->launches += 5 + 2 * ctx->wplan.max_rounds;
+        ctx->launches += 5 + (ctx->resident ? 1 : 0) + 2 * ctx->wplan.max_rounds;
     }
     return VLR_OK;
 }
@@ -974,6 +1100,12 @@ vlr_status_t vlr_ctx_create(const vlr_scenario_t* scenario, int32_t device, vlr_
         int n3 = 0;
         CKB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n3, vlr_wave_finish_kernel, THREADS, ctx->wave_smem_prep));
         ctx->wave_grid_finish = std::min(std::max(1, n3) * ctx->n_sms, ctx->grid);
+        const char* res_env = getenv("VLR_RESIDENT");
+        ctx->resident = !(res_env && res_env[0] == '0');
+        CKB(cudaFuncSetAttribute(vlr_wave_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RES_SMEM));
+        int n4 = 0;
+        CKB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n4, vlr_wave_resident_kernel, RES_THREADS, RES_SMEM));
+        ctx->wave_grid_res = std::max(1, n4) * ctx->n_sms;
     }
     CKB(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     if (const char* e = getenv("VLR_WAVE_STREAMS")) ctx->n_aux = std::max(1, std::min((int)vlr_ctx::MAX_AUX, atoi(e)));
@@ -1002,7 +1134,8 @@ void vlr_ctx_destroy(vlr_ctx_t* ctx) {
                          &s.map_vaf, &s.map_config, &s.best_event, &s.status, &s.n_base, &s.afd_count, &s.afd_vaf,
                          &s.afd_logp, &s.ws, &s.coef, &s.be, &s.ticket, &s.w_cnt, &s.w_loci, &s.w_lcs, &s.w_ogx,
                          &s.w_ogf, &s.w_coef, &s.w_tasks[0], &s.w_tasks[1], &s.w_list[0], &s.w_list[1], &s.w_dlist[0], &s.w_dlist[1], &s.w_deferred,
-                         &s.w_gx, &s.w_gf, &s.w_be, &s.w_ben};
+                         &s.w_gx, &s.w_gf, &s.w_be, &s.w_ben, &s.w_rlist, &s.w_rgx, &s.w_rgm, &s.w_rge, &s.w_rscratch,
+                         &s.w_cscratch};
         for (DevBuf* b : all) b->release();
     };
     if (ctx->stream) {
