@@ -1,19 +1,28 @@
 #!/usr/bin/env python
-"""bench.py — loci/s of the per-locus posterior engine on BASELINE.json's config 2
-(1M synthetic SNV loci, tumor-normal, 100 reads/locus/sample, tumor resolution 0.01 = "101-pt grid").
+"""bench.py — loci/s of the per-locus posterior engine on BASELINE.json's configs, and max |d ln posterior| against the
+oracle on a sample of the same batch (BASELINE.json's metric has both halves).
 
 One "step" = one pass of the hot path over the whole locus batch.
   value     whole-job loci/s with the batch already resident in HBM (CUDA events on the launch stream)
   e2e       the same metric through the C-ABI entry `vlr_call_batch` with pinned HOST buffers
             (chunked H2D, kernels and D2H all inside the timed region)
-  roofline  algorithmic HBM bytes of the kernel / its measured duration vs the measured HBM peak
-  cpu_baseline  the CPU oracle (port of the reference algorithm) on a bounded sample of the same workload
+  roofline  the bound of this path is the fp64 pipe: executed-algorithm flops / measured DFMA peak;
+            the HBM view (algorithmic bytes / measured copy bandwidth) is kept beside it
+  parity    engine vs oracle on the first loci of the same batch: max |d ln posterior|, MAP mismatches, fraction of loci
+            with the identical adaptive grid, fraction of knife-edge loci
+  cpu_baseline  the CPU oracle (port of the reference algorithm) on a bounded sample: all host threads and one thread
+  also      short runs of the other single-GPU configs (3: pedigree, 5: depth skew) so that the driver witnesses them
+
+Default workload: config 2 (1M synthetic SNV loci, tumor-normal, 100 reads/locus/sample, tumor resolution 0.01).
+Multi-GPU (torchrun, one rank per GPU), default: every rank its own config-2 shard of the same size (weak scaling), the
+only collective is the final NCCL gather of the fixed-stride result records. `also` then carries the STRONG-scaling
+configs of BASELINE.json: config 5 (1M loci with depth skew 10..2000) and, at 8 GPUs, config 4 (10M loci): ONE batch
+description, cut into contiguous ranges of equal estimated work by varlociraptor_b200.sharding (shard_cuts /
+locus_work), every rank generates and processes only its range, records gathered to rank 0 (gather_records).
+`--config 4|5` runs those as the main line.
 
 `--impl reference` times the reference algorithm's CPU implementation (the oracle port; the Rust reference cannot be
 built in this image) with all host threads on a bounded sample of the same workload.
-
-Multi-GPU (torchrun, one rank per GPU): loci are independent, every rank processes its own shard of the same size
-(weak scaling) and the only collective is the final NCCL gather of the fixed-stride result records.
 """
 import argparse
 import json
@@ -30,6 +39,11 @@ sys.path.insert(0, ROOT)
 
 METRIC = "loci_per_sec"
 UNIT = "loci/s"
+SLAB = {2: 125_000, 3: 125_000, 4: 125_000, 5: 20_000}  # loci per generator call (seed = base * 1000 + slab index)
+STRONG_TOTAL = {4: 10_000_000, 5: 1_000_000}
+# executed-algorithm flops per read and abscissa of a pileup evaluation: pileup polynomials (engine_resident.cuh),
+# 5 FMA + 1 MUL per five reads; the per-read form of the generic engine is 2 FMA + 1 MUL
+FLOPS_POLY, FLOPS_READ = 11.0 / 5.0, 5.0
 
 
 def parse_args():
@@ -38,34 +52,41 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--loci", type=int, default=1_000_000, help="loci per GPU (config 2: 1M)")
-    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 5], help="BASELINE.json config index")
-    ap.add_argument("--cpu-sample", type=int, default=0, help="loci in the cpu_baseline sample (0 = auto)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--loci", type=int, default=0, help="loci per GPU (configs 2, 3; default 1M) or in total (4, 5)")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5], help="BASELINE.json config index")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="loci in the cpu_baseline / parity sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the oracle legs (cpu_baseline, parity)")
+    ap.add_argument("--no-also", action="store_true", help="main line only")
     return ap.parse_args()
 
 
 def workload_name(cfg, loci):
     return {2: "cfg2: %d synthetic SNV loci, tumor-normal (purity 0.75), 100 reads/locus/sample, tumor resolution 0.01",
             3: "cfg3: %d synthetic mixed SNV/indel loci, 3-sample pedigree grammar, 100 reads/locus/sample",
+            4: "cfg4: %d synthetic SNV loci, tumor-normal, 100 reads/locus/sample, one batch sharded over the GPUs",
             5: "cfg5: %d synthetic SNV loci, tumor-normal, reads/locus/sample log-uniform 10..2000"}[cfg] % loci
 
 
-def make_batch(cfg, loci, seed, pinned=False):
-    """Synthetic batch of `loci` loci, generated in slabs (bounded transient memory). With pinned=True the columns are
-    written straight into page-locked arrays (vlr_host_alloc), so a rank holds one copy of its 6.4 GB shard."""
+def slab_seed(cfg, base, k):
+    return (20260100 + (2 if cfg == 4 else cfg) + 17 * base) * 1000 + k
+
+
+def make_range(cfg, lo, hi, base=0, pinned=False):
+    """Loci [lo, hi) of the synthetic batch of config `cfg` (slab k = generator call k): what one rank holds. With
+    pinned=True and a fixed depth the columns are written straight into page-locked arrays (vlr_host_alloc)."""
     from varlociraptor_b200 import synth
     from varlociraptor_b200.batch import LocusBatch
-    slab = 125_000 if cfg != 5 else 20_000
-    parts = []
-    scenario = None
-    done = 0
-    k = 0
-    out = None
-    row = 0
-    while done < loci:
-        n = min(slab, loci - done)
-        scenario, b = synth.config(cfg, n, seed=seed * 1000 + k)
+    gen_cfg = 2 if cfg == 4 else cfg
+    slab = SLAB[cfg]
+    parts, scenario, out, row, done = [], None, None, 0, 0
+    loci = hi - lo
+    for k in range(lo // slab, (hi + slab - 1) // slab):
+        s_lo, s_hi = k * slab, (k + 1) * slab
+        scenario, b = synth.config(gen_cfg, slab, seed=slab_seed(cfg, base, k))
+        a, z = max(lo, s_lo) - s_lo, min(hi, s_hi) - s_lo
+        if a != 0 or z != slab:
+            b = b.slice(a, z)
+        n = z - a
         if pinned and cfg != 5:
             S = b.n_samples
             if out is None:  # fixed depth: total sizes are known after the first slab
@@ -80,7 +101,7 @@ def make_batch(cfg, loci, seed, pinned=False):
                 out.locus_flags = engine.pinned_empty(loci, np.uint32)
                 out.prob_homopolymer_artifact = out.prob_homopolymer_variant = None
                 out.locus_heterozygosity_phred = out.locus_semr_phred = None
-            out.read_offsets[done * S + 1:(done + n) * S + 1] = b.read_offsets[1:] + row
+            out.read_offsets[done * S + 1:(done + n) * S + 1] = b.read_offsets[1:] - b.read_offsets[0] + row
             for c in b.columns:
                 out.columns[c][row:row + b.n_reads] = b.columns[c]
             out.read_flags[row:row + b.n_reads] = b.read_flags
@@ -89,7 +110,6 @@ def make_batch(cfg, loci, seed, pinned=False):
         else:
             parts.append(b)
         done += n
-        k += 1
     if out is not None:
         assert row == out.n_reads
         return scenario, out
@@ -98,6 +118,15 @@ def make_batch(cfg, loci, seed, pinned=False):
         from varlociraptor_b200 import engine
         batch = engine.pin_batch(batch)
     return scenario, batch
+
+
+def total_depths(cfg, total, base=0):
+    """Reads per locus and sample of the WHOLE batch (no reads generated): input of the shard cut."""
+    from varlociraptor_b200 import synth
+    gen_cfg = 2 if cfg == 4 else cfg
+    slab = SLAB[cfg]
+    parts = [synth.config_depths(gen_cfg, slab, seed=slab_seed(cfg, base, k)) for k in range((total + slab - 1) // slab)]
+    return np.concatenate(parts, axis=0)[:total]
 
 
 def algorithmic_bytes(batch, n_events):
@@ -158,29 +187,55 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_baseline(flat, batch, n_sample, threads):
+def oracle_sample(flat, batch, n_sample, threads):
     from oracle import oracle
     n = min(n_sample, batch.n_loci)
     sub = batch.slice(0, n)
     t0 = time.perf_counter()
-    oracle.call_batch(flat, sub, afd_capacity=0, n_threads=threads)
+    res = oracle.call_batch(flat, sub, afd_capacity=0, n_threads=threads)
     dt = time.perf_counter() - t0
-    return n / dt, n, dt
+    return res, n, dt
+
+
+def parity_block(want, got):
+    """Engine (`got`: CallResults of the same loci) against the oracle (`want`)."""
+    def max_abs_delta(a, b):  # SURVEY §8(d): 0 where both are -inf (or both NaN), +inf where only one is
+        same = (a == b) | (np.isnan(a) & np.isnan(b))
+        with np.errstate(invalid="ignore"):
+            d = np.abs(a - b)
+        d[same] = 0.0
+        d[np.isnan(d)] = np.inf
+        return float(d.max()) if d.size else 0.0
+    ke = want.knife_edge()
+    ok = ~ke
+    same_grid = want.n_base_events == got.n_base_events
+    map_same = np.all((want.map_vaf == got.map_vaf) | (np.isnan(want.map_vaf) & np.isnan(got.map_vaf)), axis=1)
+    return {"loci": int(len(ke)),
+            "max_abs_dlogpost": max_abs_delta(want.log_posteriors[ok], got.log_posteriors[ok]),
+            "max_abs_dlogpost_all_loci": max_abs_delta(want.log_posteriors, got.log_posteriors),
+            "map_vaf_mismatches": int(np.count_nonzero(~map_same & ok)),
+            "best_event_mismatches": int(np.count_nonzero((want.best_event != got.best_event) & ok)),
+            "identical_grid_fraction": float(same_grid.mean()),
+            "knife_edge_fraction": float(ke.mean()),
+            "note": "oracle = C++ port of the reference algorithm; knife-edge = a discrete decision of the reference "
+                    "algorithm within rounding noise of flipping (excluded from max_abs_dlogpost, included in _all_loci)"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    cfg = args.config
     threads = os.cpu_count() or 1
-    n_sample = args.cpu_sample or 250 * threads
-    scenario, batch = make_batch(args.config, n_sample, seed=20260100 + args.config)
+    n_sample = args.cpu_sample or (250 * threads if cfg in (2, 4) else (1000 * threads if cfg == 3 else 60 * threads))
+    scenario, batch = make_range(cfg, 0, n_sample)
     flat = scenario.flatten()
     from oracle import oracle
     oracle.build()
     vals = []
     for i in range(args.warmup + args.steps):
-        v, n, dt = cpu_baseline(flat, batch, n_sample, threads)
+        _, n, dt = oracle_sample(flat, batch, n_sample, threads)
+        v = n / dt
         if i >= args.warmup:
             vals.append((v, dt))
         if i == 0 and dt * (args.warmup + args.steps) > 240:  # keep the whole run within minutes
@@ -188,16 +243,219 @@ def run_reference(args):
     value = float(np.mean([v for v, _ in vals])) if vals else v
     ms = float(np.mean([dt for _, dt in vals]) * 1e3) if vals else dt * 1e3
     sample = "first %d loci of the workload per step, %d threads over disjoint locus ranges" % (batch.n_loci, threads)
+    loci = args.loci or STRONG_TOTAL.get(cfg, 1_000_000)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong" if cfg in STRONG_TOTAL else "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.config, args.loci), "sample_loci_per_step": int(batch.n_loci)},
+        "config": {"workload": workload_name(cfg, loci), "sample_loci_per_step": int(batch.n_loci)},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "CPU oracle = C++ port of the reference algorithm (the Rust reference cannot be built here: no cargo); "
                 "upstream `call variants` is single-threaded, the port is run on all host threads",
     }))
+
+
+class Dist:
+    def __init__(self):
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    def barrier(self):
+        import torch
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+
+def run_workload(args, D, cfg, loci, steps, warmup, strong, oracle_legs, n_oracle=0):
+    """One workload on this rank's GPU. strong: `loci` is the total of ONE batch cut over the ranks by estimated work;
+    else every rank has its own batch of `loci`. Returns the result dict on rank 0 (None elsewhere)."""
+    import torch
+    import torch.distributed as dist
+    from varlociraptor_b200 import engine, sharding
+    world, rank, local_rank = D.world, D.rank, D.local_rank
+    device = "cuda:%d" % local_rank
+    shard_info = None
+    if strong:
+        depths = total_depths(cfg, loci)
+        cuts = sharding.shard_cuts(sharding.locus_work(depths), world)
+        lo, hi = cuts[rank], cuts[rank + 1]
+        sizes = [cuts[r + 1] - cuts[r] for r in range(world)]
+        work = sharding.locus_work(depths)
+        shard_info = {"loci_per_rank": sizes, "reads_per_rank": [int(depths[cuts[r]:cuts[r + 1]].sum()) for r in range(world)],
+                      "estimated_work_per_rank": [float(work[cuts[r]:cuts[r + 1]].sum()) for r in range(world)],
+                      "cut": "sharding.shard_cuts(sharding.locus_work(depths), world): contiguous ranges of equal "
+                             "(%.0f + depth_tumor + %.2f depth_normal) per locus" % (sharding.WORK_OVERHEAD_READS,
+                                                                                    sharding.WORK_OTHER_SAMPLES)}
+        del depths, work
+        scenario, batch = make_range(cfg, lo, hi, base=0, pinned=True)
+    else:
+        sizes = [loci] * world
+        scenario, batch = make_range(cfg, 0, loci, base=rank, pinned=True)
+    flat = scenario.flatten()
+    S, E = flat.n_samples, flat.n_events
+    eng = engine.PosteriorEngine(flat, device=local_rank)
+    max_reads = int(np.max(batch.read_offsets[S::S] - batch.read_offsets[:-S:S])) if batch.n_loci else 1
+    eng.reserve(max_reads)
+    dbatch = engine.DeviceBatch(batch, device)
+    dres = engine.DeviceResults(batch.n_loci, S, E, 0, device)
+    pres = engine.pinned_results(batch.n_loci, S, E, 0)
+    rec = None
+    if world > 1:
+        rec = torch.empty((batch.n_loci, E + 1 + S + 1), dtype=torch.float64, device=device)
+    stream = torch.cuda.Stream(device=device)  # a real (non-default) stream: handle 0 would mean "the engine's own"
+    torch.cuda.set_stream(stream)
+
+    def gather_step():  # final gather of fixed-stride result records over NVLink
+        rec[:, :E + 1] = dres.log_posteriors
+        rec[:, E + 1:E + 1 + S] = dres.map_vaf
+        rec[:, E + 1 + S] = dres.status.to(torch.float64)
+        sharding.gather_records(rec, sizes, rank, world)
+
+    for _ in range(max(3, warmup)):
+        eng.call_batch_device(dbatch, dres, stream.cuda_stream)
+        if world > 1:
+            gather_step()
+    D.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    D.barrier()
+    ev0.record(stream)
+    for i in range(steps):
+        kev[i][0].record(stream)
+        eng.call_batch_device(dbatch, dres, stream.cuda_stream)
+        kev[i][1].record(stream)
+        if world > 1:
+            gather_step()
+    ev1.record(stream)
+    D.barrier()
+    clocks = sampler.stop()
+    ms_total = ev0.elapsed_time(ev1)
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    launches = steps * eng.launches  # kernels of one device-entry call (vlr_last_launch_count) x timed steps
+
+    # end to end through the host-buffer entry of the C-ABI
+    eng.call_batch(batch, out=pres)
+    D.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        eng.call_batch(batch, out=pres)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e_launches = eng.launches
+
+    t = torch.tensor([ms_total, e2e_s * 1e3, kernel_ms], dtype=torch.float64, device=device)
+    busy = [kernel_ms]
+    if world > 1:
+        allk = [torch.zeros(1, dtype=torch.float64, device=device) for _ in range(world)]
+        dist.all_gather(allk, t[2:3].clone())
+        busy = [float(x[0]) for x in allk]
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = float(t[0]), float(t[1])
+    got = dres.to_host()
+    n_bad = int(np.count_nonzero(got.status & 0x83f))  # NaN/overflow/overshoot/workspace bits
+    sum_err = float(np.nanmax(np.abs(np.logaddexp.reduce(got.log_posteriors, axis=1)))) if batch.n_loci else 0.0
+    joint_evals = float(got.n_base_events.mean()) if batch.n_loci else 0.0
+    out = None
+    if rank == 0:
+        total_loci = sum(sizes)
+        value = total_loci * steps / (ms_total * 1e-3)
+        e2e = total_loci * steps / (e2e_ms * 1e-3)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        hbm_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        abytes = algorithmic_bytes(batch, E)
+        wave = os.environ.get("VLR_WAVE", "1") != "0" and cfg in (2, 4, 5)
+        traffic, traffic_src = None, None
+        kernel_name = "vlr_call_kernel_vlr_small (warp per locus)"
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r2_wave.json" if wave else "traffic_r1.json")))
+            if cfg in (2, 4):
+                traffic = int(tr["dram_bytes_per_locus"] * batch.n_loci)
+                traffic_src = "static: %s (ncu dram__bytes of one sub-chunk of this workload, scaled by loci)" % tr.get("source", "profiles/")
+            if wave:
+                kernel_name = tr["kernels"]
+        except (OSError, KeyError, ValueError):
+            pass
+        # the bound that matters (SURVEY §8(d)): fp64. Executed-algorithm flops = joint evaluations x reads of the
+        # integrated pileup x flops per read and abscissa; peak = DFMA microbenchmark on this device.
+        reads_leaf = batch.n_reads / max(1, batch.n_loci) / S
+        per_read = FLOPS_POLY if wave else FLOPS_READ
+        flops = joint_evals * batch.n_loci * reads_leaf * per_read
+        try:
+            fp64_peak = engine.measure_fp64_peak(local_rank)
+        except Exception:  # noqa: BLE001
+            fp64_peak = None
+        fp64_achieved = flops / (kernel_ms * 1e-3) / 1e12
+        hbm_achieved = abytes / (kernel_ms * 1e-3) / 1e9
+        roofline = {
+            "bound": "fp64" if wave else "hbm", "kernel": kernel_name, "kernel_ms": kernel_ms,
+            "achieved": fp64_achieved if wave else hbm_achieved, "peak": fp64_peak if wave else hbm_peak,
+            "unit": "TFLOP/s" if wave else "GB/s",
+            "frac": (fp64_achieved / fp64_peak if fp64_peak else None) if wave else hbm_achieved / hbm_peak,
+            "traffic": traffic, "traffic_source": traffic_src,
+            "fp64": {"achieved": fp64_achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                     "frac": (fp64_achieved / fp64_peak) if fp64_peak else None, "flops_per_step": flops,
+                     "peak_source": "vlr_measure_fp64_peak (DFMA microbenchmark, this device)",
+                     "accounting": "joint evaluations (%.0f per locus) x reads of the integrated pileup (%.0f) x %.1f flops "
+                                   "(%s)" % (joint_evals, reads_leaf, per_read,
+                                             "pileup polynomials: 5 FMA + 1 MUL per five reads and abscissa; the per-read "
+                                             "form of round 1 counted 5 flops for the same evaluation" if wave else
+                                             "2 FMA + 1 MUL per read and abscissa")},
+            "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
+                    "algorithmic_bytes_per_launch": int(abytes), "peak_source": hbm_src},
+            "note": "kernel_ms = all kernels of one vlr_call_batch_device step of rank 0 (CUDA events on the launch "
+                    "stream); the path is compute bound: algorithmic HBM bytes are 6.5 KB per locus against >= 1e5 "
+                    "flops, so the HBM fraction is small by construction"}
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
+            "warmup": max(3, warmup), "ms_per_step": ms_total / steps, "higher_is_better": True,
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(cfg, total_loci if strong else loci), "loci_per_gpu": int(batch.n_loci),
+                       "reads_per_gpu": int(batch.n_reads),
+                       "parallelism": ("one batch cut into %d contiguous ranges of equal estimated work" % world) if strong
+                       else "loci sharded, %d rank(s), every rank its own batch" % world,
+                       "l2": "inputs (%.1f GB per step and GPU) are larger than L2" % (abytes / 1e9)},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(batch.nbytes()),
+                    "d2h_bytes_per_step": int(batch.n_loci * (8 * (E + 1) + 8 * S + 8 + 4 * 4)),
+                    "launches_per_step": int(e2e_launches)},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "clocks": clocks,
+            "checks": {"loci_with_error_status": n_bad, "max_abs_log_sum_of_posteriors": sum_err},
+        }
+        if world > 1:
+            out["rank_busy_ms"] = busy
+            out["rank_busy_spread"] = (max(busy) - min(busy)) / max(busy) if max(busy) > 0 else 0.0
+        if shard_info:
+            out["sharding"] = shard_info
+        if oracle_legs:
+            from oracle import oracle
+            oracle.build()
+            threads = os.cpu_count() or 1
+            n_sample = n_oracle or args.cpu_sample or (250 * threads if cfg in (2, 4) else (1000 * threads if cfg == 3 else 40 * threads))
+            want, n, dt = oracle_sample(flat, batch, n_sample, threads)
+            out["parity"] = parity_block(want, got.slice(0, n))
+            n1 = max(20, int(n / threads / 2))
+            _, n1, dt1 = oracle_sample(flat, batch, n1, 1)
+            out["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                                   "sample": "first %d loci of the same batch, %.1f s, %d threads over disjoint locus "
+                                             "ranges (upstream is single-threaded)" % (n, dt, threads),
+                                   "single_thread": {"value": n1 / dt1, "cores": 1,
+                                                     "sample": "first %d loci, %.1f s" % (n1, dt1)}}
+    del dbatch, dres, pres, batch, eng
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -207,165 +465,43 @@ def main():
         return
     import torch
     import torch.distributed as dist
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    D = Dist()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
-    torch.cuda.set_device(local_rank)
-    device = "cuda:%d" % local_rank
-    if world > 1:
+    torch.cuda.set_device(D.local_rank)
+    if D.world > 1:
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version banner there)
-        dist.init_process_group("nccl", device_id=torch.device(device))
-    from varlociraptor_b200 import engine
-    scenario, batch = make_batch(args.config, args.loci, seed=20260100 + args.config + 17 * rank, pinned=True)
-    flat = scenario.flatten()
-    S, E = flat.n_samples, flat.n_events
-    eng = engine.PosteriorEngine(flat, device=local_rank)
-    max_reads = int(np.max(batch.read_offsets[S::S] - batch.read_offsets[:-S:S]))
-    eng.reserve(max_reads)
-    dbatch = engine.DeviceBatch(batch, device)
-    dres = engine.DeviceResults(batch.n_loci, S, E, 0, device)
-    pinned = batch  # already page-locked
-    pres = engine.pinned_results(batch.n_loci, S, E, 0)
-    gather_buf = None
-    if world > 1:
-        rec = torch.empty((batch.n_loci, E + 1 + S + 1), dtype=torch.float64, device=device)
-        gather_buf = [torch.empty_like(rec) for _ in range(world)] if rank == 0 else None
-    stream = torch.cuda.Stream(device=device)  # a real (non-default) stream: handle 0 would mean "the engine's own"
-    torch.cuda.set_stream(stream)
-
-    def step_device():
-        eng.call_batch_device(dbatch, dres, stream.cuda_stream)
-        if world > 1:  # final gather of fixed-stride result records over NVLink
-            rec[:, :E + 1] = dres.log_posteriors
-            rec[:, E + 1:E + 1 + S] = dres.map_vaf
-            rec[:, E + 1 + S] = dres.status.to(torch.float64)
-            dist.gather(rec, gather_buf, dst=0)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(3, args.warmup)):
-        step_device()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    ev0.record(stream)
-    for i in range(args.steps):
-        kev[i][0].record(stream)
-        eng.call_batch_device(dbatch, dres, stream.cuda_stream)
-        kev[i][1].record(stream)
-        if world > 1:
-            rec[:, :E + 1] = dres.log_posteriors
-            rec[:, E + 1:E + 1 + S] = dres.map_vaf
-            rec[:, E + 1 + S] = dres.status.to(torch.float64)
-            dist.gather(rec, gather_buf, dst=0)
-    ev1.record(stream)
-    barrier()
-    clocks = sampler.stop()
-    ms_total = ev0.elapsed_time(ev1)
-    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
-    launches = args.steps * eng.launches  # kernels of one device-entry call (vlr_last_launch_count) x timed steps
-
-    # end to end through the host-buffer entry of the C-ABI
-    for _ in range(1):
-        eng.call_batch(pinned, out=pres)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        eng.call_batch(pinned, out=pres)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    e2e_launches = eng.launches
-
-    t = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms = float(t[0]), float(t[1])
-    status = dres.status.cpu().numpy().view(np.uint32)
-    n_bad = int(np.count_nonzero(status & 0x83f))  # NaN/overflow/overshoot/workspace bits
-    post = dres.log_posteriors.cpu().numpy()
-    sum_err = float(np.nanmax(np.abs(np.logaddexp.reduce(post, axis=1))))
-    joint_evals = float(dres.n_base_events.cpu().numpy().view(np.uint32).mean())
-
-    if rank == 0:
-        total_loci = batch.n_loci * world
-        value = total_loci * args.steps / (ms_total * 1e-3)
-        e2e = total_loci * args.steps / (e2e_ms * 1e-3)
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except OSError:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-        abytes = algorithmic_bytes(batch, E)
-        achieved = abytes / (kernel_ms * 1e-3) / 1e9
-        wave = os.environ.get("VLR_WAVE", "1") != "0" and args.config in (2, 5)
-        traffic = None  # DRAM bytes per step from the committed ncu capture of this workload, scaled by loci
-        kernel_name = "vlr_call_kernel (warp per locus)"
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1_wave.json" if wave else "traffic_r1.json")))
-            if args.config == 2:
-                traffic = int(tr["dram_bytes_per_locus"] * batch.n_loci)
-            if wave:
-                kernel_name = tr["kernels"]
-        except (OSError, KeyError, ValueError):
-            pass
-        # the bound that matters: fp64. Algorithmic flops = joint evaluations x reads of the integrated
-        # pileup x 5 (2 FMA + 1 MUL per read and abscissa); peak = DFMA microbenchmark on this device.
-        reads_leaf = batch.n_reads / max(1, batch.n_loci) / S
-        flops = joint_evals * batch.n_loci * reads_leaf * 5.0
-        try:
-            fp64_peak = engine.measure_fp64_peak(local_rank)
-        except Exception:  # noqa: BLE001
-            fp64_peak = None
-        fp64 = {"achieved": flops / (kernel_ms * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
-                "frac": (flops / (kernel_ms * 1e-3) / 1e12 / fp64_peak) if fp64_peak else None,
-                "flops_per_step": flops, "peak_source": "vlr_measure_fp64_peak (DFMA microbenchmark, this device)",
-                "accounting": "joint evaluations x reads of the integrated pileup x 5 flops"}
-        out = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args.config, args.loci), "loci_per_gpu": int(batch.n_loci),
-                       "reads_per_gpu": int(batch.n_reads), "parallelism": "loci sharded, %d rank(s)" % world,
-                       "l2": "inputs (%.1f GB per step) are larger than L2" % (abytes / 1e9)},
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(batch.nbytes()),
-                    "d2h_bytes_per_step": int(batch.n_loci * (8 * (E + 1) + 8 * S + 8 + 4 * 4)),
-                    "launches_per_step": int(e2e_launches)},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": kernel_name, "kernel_ms": kernel_ms,
-                         "algorithmic_bytes_per_launch": int(abytes), "peak_source": peak_src, "fp64": fp64,
-                         "note": "kernel_ms = all kernels of one vlr_call_batch_device step (CUDA events on the launch "
-                                 "stream). The path is compute/latency bound, not HBM bound (DESIGN.md §4): %.0f joint "
-                                 "evaluations (each a product over the reads of a pileup) per locus on average, so the "
-                                 "HBM fraction is small by construction and `fp64` is the meaningful roofline; traffic "
-                                 "= measured DRAM bytes of the committed ncu pass (profiles/), mostly the per-config "
-                                 "coefficient arena (written once, re-staged every round), not the %.1f GB of "
-                                 "algorithmic bytes" % (joint_evals, abytes / 1e9)},
-            "clocks": clocks,
-            "checks": {"loci_with_error_status": n_bad, "max_abs_log_sum_of_posteriors": sum_err},
-        }
-        if world == 1 and not args.no_cpu_baseline:
-            from oracle import oracle
-            oracle.build()
-            threads = os.cpu_count() or 1
-            n_sample = args.cpu_sample or 250 * threads
-            v, n, dt = cpu_baseline(flat, batch, n_sample, threads)
-            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                   "sample": "first %d loci of the same batch, %.1f s, %d threads over disjoint "
-                                             "locus ranges (upstream is single-threaded)" % (n, dt, threads)}
+        dist.init_process_group("nccl", device_id=torch.device("cuda:%d" % D.local_rank))
+    cfg = args.config
+    strong = cfg in STRONG_TOTAL
+    loci = args.loci or (STRONG_TOTAL[cfg] if strong else 1_000_000)
+    oracle_legs = D.world == 1 and not args.no_cpu_baseline
+    out = run_workload(args, D, cfg, loci, args.steps, args.warmup, strong, oracle_legs)
+    if not args.no_also and cfg == 2:
+        extra = []
+        if D.world == 1:  # the other single-GPU configs, short
+            extra = [(3, 250_000, False, 20_000), (5, 100_000, False, 400)]
+        else:  # the strong-scaling configs of BASELINE.json (config 4 is defined at 8 GPUs)
+            extra = [(5, STRONG_TOTAL[5], True, 0)] + ([(4, STRONG_TOTAL[4], True, 0)] if D.world == 8 else [])
+        also = []
+        for c, n, st, n_or in extra:
+            r = run_workload(args, D, c, n, max(1, min(args.steps, 2)), 3, st, oracle_legs, n_oracle=n_or)
+            if r is not None:
+                keep = {k: r[k] for k in ("value", "unit", "n_gpus", "steps", "ms_per_step", "scaling", "config", "e2e",
+                                          "gpu_launches", "checks") if k in r}
+                keep["roofline"] = {k: r["roofline"][k] for k in ("bound", "achieved", "peak", "unit", "frac", "kernel", "kernel_ms")}
+                keep["roofline"]["hbm_frac"] = r["roofline"]["hbm"]["frac"]
+                keep["roofline"]["fp64_frac"] = r["roofline"]["fp64"]["frac"]
+                for k in ("parity", "cpu_baseline", "sharding", "rank_busy_ms", "rank_busy_spread"):
+                    if k in r:
+                        keep[k] = r[k]
+                also.append(keep)
+        if out is not None:
+            out["also"] = also
+    if out is not None:
         print(json.dumps(out))
-    if world > 1:
+    if D.world > 1:
         dist.destroy_process_group()
 
 

@@ -234,7 +234,9 @@ vlr_status_t vlr_call_batch(vlr_ctx_t* ctx, const vlr_batch_t* batch, vlr_result
 
 /* Same, with every pointer in `batch` and `results` a DEVICE pointer on the
  * context's device. Asynchronous on `cuda_stream` (a cudaStream_t, 0 = the
- * context's own stream); the caller synchronises. */
+ * context's own stream); the caller synchronises. Calls on one context share
+ * its workspace: a call issued on another stream than the previous one waits
+ * (on the device, through an event) until that one has finished. */
 vlr_status_t vlr_call_batch_device(vlr_ctx_t* ctx, const vlr_batch_t* batch, vlr_results_t* results,
                                    void* cuda_stream);
 

@@ -8,7 +8,8 @@ import numpy as np
 import pytest
 
 from tests import emu
-from varlociraptor_b200 import Scenario, calling, obs_codec
+from oracle import oracle
+from varlociraptor_b200 import Scenario, calling, obs_codec, synth
 from varlociraptor_b200.batch import LocusBatch
 
 REF_FLAME = "/root/reference/tests/resources/flamegraph_profiling"
@@ -330,3 +331,102 @@ def test_batching_groups_and_filters_do_not_change_what_is_delivered(tn_records)
         assert [p for p, _, _ in want] == sorted(p for p, _, _ in want)
         for batch_size in (1, 2, 5):
             assert run(batch_size, groups, use_filter) == want
+
+
+def test_scenario_without_the_pseudo_contig_all():
+    """A per-contig ploidy map need not define `all`: upstream resolves only the contigs that occur (calling.rs:632-718)."""
+    sc = Scenario.from_yaml("""
+species:
+  heterozygosity: 0.001
+  ploidy:
+    chr1: 2
+    chrX: 1
+samples:
+  s:
+    resolution: 0.1
+events:
+  het: "s:0.5"
+  hom: "s:1.0"
+""")
+    assert sc.is_contig_dependent()
+    _, b2 = synth.tumor_normal(6, seed=12, depth=20)
+    one = LocusBatch(1, b2.read_offsets[::2].copy(), dict(b2.columns), b2.read_flags, b2.locus_flags)
+    recs = _records_from_batch(one)
+    contigs = ["chr1", "chr1", "chrX", "chrX", "chr1", "chrX"]
+    for r, c in zip(recs, contigs):
+        r["chrom"] = c
+    built = []
+
+    def factory(flat):
+        built.append(flat)
+        return EmuEngine(flat)
+    w = calling.call_generic(sc, {"s": recs}, engine_factory=factory)
+    assert [c.chrom for c in w.calls] == contigs and len(built) == 2
+    x = [c for c in w.calls if c.chrom == "chrX"]
+    assert all(set(c.event_probs) == {"absent", "hom", "artifact"} or "het" in c.event_probs for c in x)
+    want = emu.call_batch(sc.for_contig("chrX").flatten(), one, afd_capacity=128)
+    flat_x = sc.for_contig("chrX").flatten()
+    for i, c in enumerate(w.calls):
+        if c.chrom == "chrX":
+            assert [c.event_probs[e] for e in flat_x.event_names] == want.log_posteriors[i, :-1].tolist()
+
+
+def test_variant_specific_priors_reach_the_engine():
+    """INFO HETEROZYGOSITY / SOMATIC_EFFECTIVE_MUTATION_RATE of a record (PHRED; calling.rs:472-494) override the
+    scenario's rates for that record: the operator API must hand them to the engine like the batch columns do."""
+    sc = Scenario.from_yaml(synth.SIMPLE_PEDIGREE_YAML)
+    flat = sc.flatten()
+    _, b = synth.pedigree(8, seed=41, depth=14)
+    from tests.util import SNV_FLAGS
+    b.locus_flags[:] = SNV_FLAGS  # the re-encoded records are all A>G SNVs
+    names = sc.sample_names
+
+    def one(s):
+        starts, ends = b.read_offsets[s:-1:3], b.read_offsets[s + 1::3]
+        idx = np.concatenate([np.arange(a, e) for a, e in zip(starts, ends)])
+        offs = np.concatenate([[0], np.cumsum(ends - starts)])
+        return LocusBatch(1, offs, {k: v[idx] for k, v in b.columns.items()}, b.read_flags[idx], b.locus_flags)
+    records = {n: _records_from_batch(one(s)) for s, n in enumerate(names)}
+    het = np.full(8, np.nan, dtype=np.float32)
+    het[[1, 4, 5]] = [13.5, 40.25, 7.0]
+    for recs in records.values():
+        for i, r in enumerate(recs):
+            if not np.isnan(het[i]):
+                r["info"]["HETEROZYGOSITY"] = float(het[i])
+    w = calling.call_generic(sc, records, engine_factory=EmuEngine)
+    with_override = LocusBatch(3, b.read_offsets, b.columns, b.read_flags, b.locus_flags, None, None, het, None)
+    want = oracle.call_batch(flat, with_override, afd_capacity=128)
+    plain = oracle.call_batch(flat, b, afd_capacity=128)
+    assert not np.allclose(want.log_posteriors[[1, 4, 5]], plain.log_posteriors[[1, 4, 5]])  # the override matters
+    for i, c in enumerate(w.calls):
+        got = [c.event_probs[e] for e in flat.event_names]
+        assert np.allclose(got, want.log_posteriors[i, :-1], rtol=0, atol=1e-9, equal_nan=True)
+
+
+def test_observation_file_version_and_float_tags(tmp_path):
+    rec = _records_from_batch(LocusBatch(1, *(lambda b: (b.read_offsets[::2].copy(), dict(b.columns), b.read_flags,
+                                                         b.locus_flags))(synth.tumor_normal(1, seed=3, depth=4)[1])))[0]
+    info = ";".join("%s=%s" % (k, ",".join(map(str, v))) for k, v in rec["info"].items())
+    body = "chr1\t100\t.\tA\tG\t.\t.\t%s;HETEROZYGOSITY=30.1;SOMATIC_EFFECTIVE_MUTATION_RATE=.\n" % info
+    good = tmp_path / "obs.vcf"
+    good.write_text("##fileformat=VCFv4.2\n##varlociraptor_observation_format_version=%s\n#CHROM\tPOS\n%s" % (
+        obs_codec.OBSERVATION_FORMAT_VERSION, body))
+    r = obs_codec.parse_observation_vcf(str(good))[0]
+    assert r["info"]["HETEROZYGOSITY"] == 30.1 and r["info"]["SOMATIC_EFFECTIVE_MUTATION_RATE"] is None
+    b = obs_codec.batch_from_records([[r]])
+    assert b.locus_heterozygosity_phred is not None and abs(float(b.locus_heterozygosity_phred[0]) - 30.1) < 1e-5
+    assert b.locus_semr_phred is None
+    for header in ("##varlociraptor_observation_format_version=14\n", ""):
+        bad = tmp_path / "old.vcf"
+        bad.write_text("##fileformat=VCFv4.2\n%s#CHROM\tPOS\n%s" % (header, body))
+        with pytest.raises(obs_codec.InvalidObservationFormat):
+            obs_codec.parse_observation_vcf(str(bad))
+    r2 = dict(r, info=dict(r["info"], STRAND=r["info"]["STRAND"][:-4]))  # one read fewer in one vector
+    import struct
+    with pytest.raises((obs_codec.InvalidObservationFormat, ValueError, IndexError, struct.error)):
+        obs_codec.decode_record(r2["info"])
+    shorter = dict(r["info"])
+    n = len(obs_codec.decode_enum(shorter["STRAND"]))
+    shorter["STRAND"] = obs_codec.encode_enum([0] * (n - 1))  # a well-formed vector with one read fewer
+    with pytest.raises(obs_codec.InvalidObservationFormat):
+        obs_codec.decode_record(shorter)

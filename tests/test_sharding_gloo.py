@@ -28,7 +28,7 @@ def _worker(rank, world, port, out_path):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     sc, b = synth.tumor_normal(40, seed=77, depth_range=(10, 120))
     flat = sc.flatten()
-    res = call_sharded(lambda sub: emu.call_batch(flat, sub), b, flat.n_events, rank, world)
+    res = call_sharded(lambda sub: emu.call_batch(flat, sub, afd_capacity=48), b, flat.n_events, rank, world)
     if rank == 0:
         np.save(out_path, pack_records(res))
     else:
@@ -44,21 +44,31 @@ def test_two_rank_gather_equals_single_process(tmp_path):
     mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
     sc, b = synth.tumor_normal(40, seed=77, depth_range=(10, 120))
     flat = sc.flatten()
-    want = pack_records(emu.call_batch(flat, b))
+    want = pack_records(emu.call_batch(flat, b, afd_capacity=48))  # the distributions travel with the records
     got = np.load(out)
     assert got.shape == want.shape
     assert np.array_equal(got, want, equal_nan=True)
 
 
-def test_shard_ranges_balance_reads_and_cover_everything():
+def test_shard_ranges_balance_and_cover_everything():
+    from varlociraptor_b200.sharding import batch_depths, locus_work, shard_cuts
     _, b = synth.tumor_normal(500, seed=5, depth_range=(10, 2000))
+    work = locus_work(batch_depths(b))
     for world in (1, 2, 4, 8):
-        r = shard_ranges(b, world)
-        assert r[0][0] == 0 and r[-1][1] == b.n_loci
-        assert all(r[i][1] == r[i + 1][0] for i in range(world - 1))
-        reads = [int(b.read_offsets[hi * 2] - b.read_offsets[lo * 2]) for lo, hi in r]
-        assert max(reads) - min(reads) <= 2 * 4000  # within one locus of perfect balance
+        for by in ("work", "reads"):
+            r = shard_ranges(b, world, by=by)
+            assert r[0][0] == 0 and r[-1][1] == b.n_loci
+            assert all(r[i][1] == r[i + 1][0] for i in range(world - 1))
+            if by == "reads":
+                load = [int(b.read_offsets[hi * 2] - b.read_offsets[lo * 2]) for lo, hi in r]
+                assert max(load) - min(load) <= 2 * 4000  # within one locus of perfect balance
+            else:
+                load = [float(work[lo:hi].sum()) for lo, hi in r]
+                assert max(load) - min(load) <= 2 * work.max()
     assert shard_ranges(b, 3, by="loci")[1] == (166, 333)
+    # the cut only needs the per-locus depths, which the generator provides without the reads (bench.py --config 5)
+    assert np.array_equal(synth.tumor_normal_depths(500, seed=5, depth_range=(10, 2000)), batch_depths(b))
+    assert shard_cuts(np.ones(10), 3) == [0, 4, 7, 10] and shard_cuts(np.zeros(0), 2) == [0, 0, 0]
 
 
 def test_record_pack_roundtrip():
@@ -74,3 +84,10 @@ def test_record_pack_roundtrip():
     back = unpack_records(pack_records(r), 2, 4)
     assert np.array_equal(back.log_posteriors, r.log_posteriors) and np.array_equal(back.status, r.status)
     assert np.array_equal(back.best_event, r.best_event) and np.array_equal(back.map_vaf, r.map_vaf)
+    a = CallResults(3, 2, 4, afd_capacity=5)
+    a.afd_count[...] = [[1, 2], [0, 5], [3, 3]]
+    a.afd_vaf[...] = rng.random((3, 2, 5))
+    a.afd_logp[...] = -rng.random((3, 2, 5))
+    back = unpack_records(pack_records(a), 2, 4, afd_capacity=5)
+    assert np.array_equal(back.afd_count, a.afd_count) and np.array_equal(back.afd_vaf, a.afd_vaf)
+    assert np.array_equal(back.afd_logp, a.afd_logp)

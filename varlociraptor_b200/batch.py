@@ -192,6 +192,16 @@ class CallResults:
         r.afd_logp = abi.ptr(self.afd_logp, C.c_double)
         return r
 
+    def slice(self, lo: int, hi: int) -> "CallResults":
+        """Results of the loci [lo, hi) (views, not copies)."""
+        r = CallResults.__new__(CallResults)
+        r.n_loci, r.n_samples, r.n_events, r.afd_capacity = hi - lo, self.n_samples, self.n_events, self.afd_capacity
+        for name in ("log_posteriors", "log_marginal", "map_vaf", "map_config", "best_event", "status", "n_base_events",
+                     "afd_count", "afd_vaf", "afd_logp"):
+            a = getattr(self, name)
+            setattr(r, name, None if a is None else a[lo:hi])
+        return r
+
     def afd(self, locus: int, sample: int):
         n = int(self.afd_count[locus, sample])
         return self.afd_vaf[locus, sample, :n].copy(), self.afd_logp[locus, sample, :n].copy()

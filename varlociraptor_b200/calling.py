@@ -266,8 +266,7 @@ class Caller:
         the contig gets one model per contig, like `configure_model` upstream (calling.rs:632-718)."""
         scenario.full_prior = full_prior
         self.scenario = scenario
-        self.flat = scenario.flatten()
-        self.sample_names = list(self.flat.sample_names)
+        self.sample_names = list(scenario.sample_names)
         for name in observations:
             if name not in self.sample_names:  # errors::Error::InvalidObservationSampleName
                 raise ValueError("invalid observation sample name: %s" % name)
@@ -284,12 +283,20 @@ class Caller:
         self._engine_factory = engine_factory
         self._per_contig = engine is None and scenario.is_contig_dependent()
         self._models: Dict[str, tuple] = {}
-        self._contig = scenario.contig
-        if engine is None:
-            engine = engine_factory(self.flat)
-        self.engine = engine
-        self._models[scenario.contig] = (self.flat, engine)
-        self._model_by_signature = {scenario.contig_signature(): (self.flat, engine)}
+        self._model_by_signature: Dict[tuple, tuple] = {}
+        if self._per_contig:
+            # ploidies / universes are given per contig: like upstream (calling.rs:632-718) a model exists only for
+            # the contigs that occur in the records; the scenario need not define the pseudo-contig "all"
+            self._contig = None
+            self.flat = self.engine = None
+        else:
+            self._contig = scenario.contig
+            self.flat = scenario.flatten()
+            if engine is None:
+                engine = engine_factory(self.flat)
+            self.engine = engine
+            self._models[scenario.contig] = (self.flat, engine)
+            self._model_by_signature[scenario.contig_signature()] = (self.flat, engine)
         self._haplotype_results: Dict[str, Optional[Call]] = {}
 
     def _configure_model(self, contig: str) -> None:

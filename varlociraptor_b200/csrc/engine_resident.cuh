@@ -577,15 +577,17 @@ VLR_DEV_NOINLINE double r_fin_list(const double* gx, const double* gm, const int
     const double inv_m = 1.0 / best.m;
     grp_sync(grp);
     double sum = 0.0;
-    for (int i = grp.lane; i < n; i += grp.n) {
-        const int j = (int)(node[i] & 0xffu);
-        if (j == R_NONE) continue;
-        const double mi = gm[i], mj = gm[j];
+#pragma unroll 2
+    for (int i = grp.lane; i < n; i += grp.n) { // (independent loads: several points in flight)
+        int j = (int)(node[i] & 0xffu);
+        const bool last = j == R_NONE;
+        if (last) j = i;
+        const double mi = gm[i], mj = gm[j], xi = gx[i], xj = gx[j];
         const int di = ge[i] - best.e, dj = ge[j] - best.e; // <= 0
         double wi = 0.0, wj = 0.0;
         if (mi != 0.0 && di > -1000) wi = (mi * inv_m) * d_make((1023 + di) << 20, 0);
         if (mj != 0.0 && dj > -1000) wj = (mj * inv_m) * d_make((1023 + dj) << 20, 0);
-        sum += (wi + wj) * (gx[j] - gx[i]);
+        if (!last) sum += (wi + wj) * (xj - xi);
     }
     sum = grp_sum_d(sum, grp);
     grp_sync(grp);

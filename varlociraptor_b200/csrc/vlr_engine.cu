@@ -589,6 +589,8 @@ struct vlr_ctx {
     Slot dev_slot_aux[MAX_AUX - 1]; // parts of a large wavefront batch run concurrently on internal streams
     cudaStream_t aux[MAX_AUX] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[MAX_AUX] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_done = nullptr; // end of the previous device-entry call: calls share one workspace, so a call on
+    bool have_done = false;        // another stream waits for it (an event chain instead of a rule for the caller)
     int n_aux = 3; // measured on 512k config-2 loci: 1 stream 4.05, 2: 4.43, 3: 4.48, 4: 4.51 M loci/s
     Slot slots[NBUF];
     int64_t reserve_reads = 4096;
@@ -1114,6 +1116,7 @@ vlr_status_t vlr_ctx_create(const vlr_scenario_t* scenario, int32_t device, vlr_
         CKB(cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming));
     }
     CKB(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    CKB(cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming));
     for (int i = 0; i < NBUF; ++i) CKB(cudaStreamCreateWithFlags(&ctx->slots[i].stream, cudaStreamNonBlocking));
 #undef CKB
     *out = ctx;
@@ -1149,6 +1152,7 @@ void vlr_ctx_destroy(vlr_ctx_t* ctx) {
         if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
     }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
     for (auto& s : ctx->slots) free_slot(s);
     DevBuf* sc[] = {&ctx->d_samples, &ctx->d_events, &ctx->d_nodes, &ctx->d_set_vafs, &ctx->d_spectra,
                     &ctx->d_lfc_nodes, &ctx->d_lfc_ordinal, &ctx->d_prior_tab};
@@ -1171,6 +1175,7 @@ vlr_status_t vlr_call_batch_device(vlr_ctx_t* ctx, const vlr_batch_t* batch, vlr
     cudaStream_t stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
     vlr_status_t st = ensure_workspace(ctx, ctx->dev_slot, ctx->reserve_reads, results->afd_capacity > 0);
     if (st != VLR_OK) return st;
+    if (ctx->have_done) CK(cudaStreamWaitEvent(stream, ctx->ev_done, 0)); // the workspace of the previous call is free
     DevBatch b;
     b.n_loci = batch->n_loci;
     b.read_base = 0;
@@ -1220,9 +1225,15 @@ vlr_status_t vlr_call_batch_device(vlr_ctx_t* ctx, const vlr_batch_t* batch, vlr
             CK(cudaEventRecord(ctx->ev_join[i], ctx->aux[i]));
             CK(cudaStreamWaitEvent(stream, ctx->ev_join[i], 0));
         }
+        CK(cudaEventRecord(ctx->ev_done, stream));
+        ctx->have_done = true;
         return VLR_OK;
     }
-    return launch(ctx, ctx->dev_slot, b, r, stream, avg_reads);
+    st = launch(ctx, ctx->dev_slot, b, r, stream, avg_reads);
+    if (st != VLR_OK) return st;
+    CK(cudaEventRecord(ctx->ev_done, stream));
+    ctx->have_done = true;
+    return VLR_OK;
 }
 
 vlr_status_t vlr_call_batch(vlr_ctx_t* ctx, const vlr_batch_t* batch, vlr_results_t* results) {

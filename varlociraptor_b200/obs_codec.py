@@ -138,6 +138,11 @@ def decode_record(info: Dict[str, Sequence[int]]):
     softclipped = decode_bitvec(info["SOFTCLIPPED"])
     paired = decode_bitvec(info["PAIRED"])
     max_mapq = decode_bitvec(info["IS_MAX_MAPQ"])
+    lengths = {k: len(v) for k, v in cols.items()}
+    lengths.update(STRAND=len(strand), READ_ORIENTATION=len(orient), READ_POSITION=len(readpos), ALT_LOCUS=len(altlocus),
+                   SOFTCLIPPED=len(softclipped), PAIRED=len(paired), IS_MAX_MAPQ=len(max_mapq))
+    if any(m != n for m in lengths.values()):  # one entry per read in every vector (preprocessing/mod.rs:869-910)
+        raise InvalidObservationFormat("per-read vectors of a record differ in length: %r" % lengths)
     flags = (strand << abi.RF_STRAND_SHIFT) | (orient << abi.RF_ORIENT_SHIFT) | (altlocus << abi.RF_ALTLOCUS_SHIFT)
     flags = flags.astype(np.uint32)
     flags |= np.where(readpos == 0, abi.RF_READPOS_MAJOR, 0).astype(np.uint32)
@@ -155,11 +160,23 @@ def decode_record(info: Dict[str, Sequence[int]]):
     return cols, flags, hart, hvar
 
 
-def parse_observation_vcf(path: str) -> List[dict]:
-    """Text dump (`bcftools view`) of an observation BCF -> list of records with integer INFO arrays."""
+class InvalidObservationFormat(ValueError):
+    """errors::Error::InvalidObservationFormat: the file was written by another observation format version."""
+
+
+_FLOAT_INFO_TAGS = ("HETEROZYGOSITY", "SOMATIC_EFFECTIVE_MUTATION_RATE")  # PHRED floats (calling.rs:472-494)
+
+
+def parse_observation_vcf(path: str, check_version: bool = True) -> List[dict]:
+    """Text dump (`bcftools view`) of an observation BCF -> list of records with integer INFO arrays. Like
+    `Caller::call` (calling.rs:324-339) it refuses files whose `varlociraptor_observation_format_version` header is
+    missing or differs from the version this codec decodes: another bincode layout would be mis-decoded silently."""
     out = []
+    version = None
     with open(path) as f:
         for line in f:
+            if line.startswith("##varlociraptor_observation_format_version="):
+                version = line.rstrip("\n").split("=", 1)[1]
             if line.startswith("#"):
                 continue
             t = line.rstrip("\n").split("\t")
@@ -168,6 +185,10 @@ def parse_observation_vcf(path: str) -> List[dict]:
             for kv in t[7].split(";"):
                 if "=" in kv:
                     k, v = kv.split("=", 1)
+                    if k in _FLOAT_INFO_TAGS:
+                        x = v.split(",")[0]  # all records output by preprocess are single allele
+                        info[k] = None if x == "." else float(x)
+                        continue
                     try:
                         info[k] = [int(x) for x in v.split(",")]
                     except ValueError:
@@ -176,6 +197,9 @@ def parse_observation_vcf(path: str) -> List[dict]:
                     flags.add(kv)
             out.append({"chrom": t[0], "pos": int(t[1]), "id": t[2], "ref": t[3], "alt": t[4], "info": info,
                         "flags": flags})
+    if check_version and version != OBSERVATION_FORMAT_VERSION:
+        raise InvalidObservationFormat("%s: observation format version %s, this codec reads version %s" % (
+            path, "missing" if version is None else version, OBSERVATION_FORMAT_VERSION))
     return out
 
 
@@ -233,6 +257,7 @@ def batch_from_records(per_sample_records: List[List[dict]], **omit) -> LocusBat
     L = len(per_sample_records[0])
     cols = {k: [] for k in abi.BATCH_F32_COLUMNS}
     flags, harts, hvars, lflags = [], [], [], []
+    het, semr = np.full(L, np.nan, dtype=np.float32), np.full(L, np.nan, dtype=np.float32)
     offsets = [0]
     any_h = False
     for i in range(L):
@@ -259,12 +284,19 @@ def batch_from_records(per_sample_records: List[List[dict]], **omit) -> LocusBat
                 hvars.append(np.full(n, np.nan, dtype=np.float32))
             offsets.append(offsets[-1] + n)
         lflags.append(locus_flags_for(first["ref"], first["alt"], hom, "IMPRECISE" in first["flags"], **omit))
+        # variant-specific priors of the first record with observations (calling.rs:472-494): PHRED, None = not given
+        h, r = first["info"].get("HETEROZYGOSITY"), first["info"].get("SOMATIC_EFFECTIVE_MUTATION_RATE")
+        if isinstance(h, (int, float)):
+            het[i] = h
+        if isinstance(r, (int, float)):
+            semr[i] = r
 
     def cat(lst, dt):
         return np.concatenate(lst) if lst else np.zeros(0, dtype=dt)
     return LocusBatch(S, np.array(offsets, dtype=np.int64), {k: cat(v, np.float32) for k, v in cols.items()},
                       cat(flags, np.uint32), np.array(lflags, dtype=np.uint32),
-                      cat(harts, np.float32) if any_h else None, cat(hvars, np.float32) if any_h else None)
+                      cat(harts, np.float32) if any_h else None, cat(hvars, np.float32) if any_h else None,
+                      het if np.any(~np.isnan(het)) else None, semr if np.any(~np.isnan(semr)) else None)
 
 
 # ----------------------------------------------------------------------------- encoding (write_observations mirror)

@@ -113,28 +113,41 @@ def _assemble(n_samples, depths, eff_vaf, rng, locus_flags) -> LocusBatch:
     return LocusBatch(n_samples, offsets, cols, flags, locus_flags)
 
 
-def tumor_normal(n_loci: int, seed: int = SEED_BASE + 2, depth: int = 100, purity: float = 0.75,
-                 depth_range: Optional[Tuple[int, int]] = None) -> Tuple[Scenario, LocusBatch]:
-    """cfg-2 (and cfg-4 by n_loci, cfg-5 by depth_range=(10, 2000)): SNV loci, scenario of
-    `call variants tumor-normal` (src/cli.rs:1151-1173). Sample order: normal = 0, tumor = 1."""
-    rng = np.random.Generator(np.random.PCG64(seed))
+def _tn_draws(rng, n_loci: int, depth: int, depth_range):
+    """The per-locus draws of `tumor_normal` that precede the reads: class, true allele frequencies, depths [L, 2]."""
     cls = rng.choice(5, size=n_loci, p=[0.50, 0.25, 0.15, 0.05, 0.05])
-    theta_t = np.zeros(n_loci)
-    theta_n = np.zeros(n_loci)
     u_t = rng.uniform(0.05, 0.6, size=n_loci)
     u_n = rng.uniform(0.05, 0.3, size=n_loci)
-    theta_t[cls == 1] = u_t[cls == 1]
-    theta_t[cls == 2] = theta_n[cls == 2] = 0.5
-    theta_t[cls == 3] = theta_n[cls == 3] = 1.0
-    theta_t[cls == 4] = u_t[cls == 4]
-    theta_n[cls == 4] = u_n[cls == 4]
-    eff = np.stack([theta_n, purity * theta_t + (1.0 - purity) * theta_n], axis=1)
     if depth_range is None:
         depths = np.full((n_loci, 2), depth, dtype=np.int64)
     else:
         lo, hi = depth_range
         depths = np.exp(rng.uniform(math.log(lo), math.log(hi + 1), size=(n_loci, 2))).astype(np.int64)
         depths = np.clip(depths, lo, hi)
+    return cls, u_t, u_n, depths
+
+
+def tumor_normal_depths(n_loci: int, seed: int = SEED_BASE + 2, depth: int = 100,
+                        depth_range: Optional[Tuple[int, int]] = None) -> np.ndarray:
+    """Reads per locus and sample [L, 2] of `tumor_normal(n_loci, seed, ...)` without generating the reads: what a
+    rank needs of the WHOLE batch to cut it into shards of equal work (sharding.shard_cuts)."""
+    return _tn_draws(np.random.Generator(np.random.PCG64(seed)), n_loci, depth, depth_range)[3]
+
+
+def tumor_normal(n_loci: int, seed: int = SEED_BASE + 2, depth: int = 100, purity: float = 0.75,
+                 depth_range: Optional[Tuple[int, int]] = None) -> Tuple[Scenario, LocusBatch]:
+    """cfg-2 (and cfg-4 by n_loci, cfg-5 by depth_range=(10, 2000)): SNV loci, scenario of
+    `call variants tumor-normal` (src/cli.rs:1151-1173). Sample order: normal = 0, tumor = 1."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    cls, u_t, u_n, depths = _tn_draws(rng, n_loci, depth, depth_range)
+    theta_t = np.zeros(n_loci)
+    theta_n = np.zeros(n_loci)
+    theta_t[cls == 1] = u_t[cls == 1]
+    theta_t[cls == 2] = theta_n[cls == 2] = 0.5
+    theta_t[cls == 3] = theta_n[cls == 3] = 1.0
+    theta_t[cls == 4] = u_t[cls == 4]
+    theta_n[cls == 4] = u_n[cls == 4]
+    eff = np.stack([theta_n, purity * theta_t + (1.0 - purity) * theta_n], axis=1)
     batch = _assemble(2, depths, eff, rng, _snv_locus_flags(rng, n_loci))
     return Scenario.tumor_normal(purity=purity), batch
 
@@ -156,6 +169,18 @@ def pedigree(n_loci: int, seed: int = SEED_BASE + 3, depth: int = 100) -> Tuple[
     snv_mask = rng.random(n_loci) < 0.7
     batch = _assemble(3, depths, eff, rng, _snv_locus_flags(rng, n_loci, snv_mask))
     return Scenario.from_yaml(SIMPLE_PEDIGREE_YAML), batch
+
+
+def config_depths(idx: int, n_loci: int, seed: Optional[int] = None) -> np.ndarray:
+    """Reads per locus and sample of `config(idx, n_loci, seed)` without generating the reads."""
+    seed = SEED_BASE + idx if seed is None else seed
+    if idx in (2, 4):
+        return np.full((n_loci, 2), 100, dtype=np.int64)
+    if idx == 3:
+        return np.full((n_loci, 3), 100, dtype=np.int64)
+    if idx == 5:
+        return tumor_normal_depths(n_loci, seed, depth_range=(10, 2000))
+    raise ValueError("config index must be 2..5")
 
 
 def config(idx: int, n_loci: int, seed: Optional[int] = None):
