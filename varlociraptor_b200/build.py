@@ -6,7 +6,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libvlr_engine.so")
 SOURCES = ["vlr_engine.cu"]
-DEPS = ["vlr_engine.cu", "engine_core.cuh", "engine_wave.cuh", "engine_types.cuh", "contamination.cuh", "scenario_prep.h", os.path.join("..", "..", "include", "vlr_engine.h")]
+DEPS = ["vlr_engine.cu", "engine_core.cuh", "engine_wave.cuh", "engine_resident.cuh", "engine_sets.cuh", "engine_types.cuh", "contamination.cuh", "scenario_prep.h", os.path.join("..", "..", "include", "vlr_engine.h")]
 # -fmad=false: the reference (Rust) and the oracle never contract a*b+c; grid abscissae (linspace, observable
 # limits) must round identically or adaptive grids diverge. The hot loop uses explicit fma() where fusion is wanted.
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",

@@ -2536,6 +2536,7 @@ VLR_DEV void process_locus(const DevScenario* sc, const DevBatch* b, const DevRe
 
 #ifdef VLR_VAR_WAVE
 #include "engine_wave.cuh"
+#include "engine_sets.cuh"
 #endif
 
 } // namespace VLR_VARIANT

@@ -213,6 +213,40 @@ struct WavePlan {
     int root_node[WAVE_MAXE], child_node[WAVE_MAXE];
 };
 
+// ------------------------------------------------------------------------------------------------ all-Set plan
+// Scenario-level description of an "all-Set" scenario (engine_sets.cuh): every node of every event tree is a Set node,
+// e.g. pedigrees (samples without an explicit universe have the allele frequencies their ploidy allows,
+// grammar/mod.rs:539-543). GenericPosterior::density (generic.rs:294-330) then only sums joint probabilities of
+// discrete allele frequency combinations: the trees are flattened on the host into the list of their root-to-leaf
+// combinations ("leaves", in the order density() visits them) and the distinct pileup evaluations those need ("folds").
+constexpr int SETS_MAXL = 192; // leaves of all events together
+constexpr int SETS_MAXF = 48;  // distinct (sample, allele frequency, contaminant's allele frequency) pileup evaluations
+constexpr int SETS_MAXS = 4;   // samples (the small engine variant serves <= 3)
+struct SetsFold {
+    double vaf, vaf_by;
+    int sample, pad;
+};
+struct SetsLeaf {
+    uint8_t fold[SETS_MAXS]; // pileup evaluation of each sample
+    uint8_t event;           // scenario event the leaf belongs to
+    uint8_t posmask;         // samples whose Set node on the path has only positive allele frequencies: the path is cut
+                             // when such a sample is clearly reference (generic.rs:294-299)
+    uint8_t discmask;        // samples pushed as discrete events on the path (all, unless a tree leaves a sample out)
+    uint8_t pad;
+};
+struct SetsPlan {
+    int eligible, n_folds, n_leaves, pad;
+    int ev_first[VLR_MAX_EVENTS], ev_count[VLR_MAX_EVENTS]; // leaves of event e: [ev_first, ev_first + ev_count)
+    const SetsFold* folds;
+    const SetsLeaf* leaves;
+    const double* leaf_vaf; // [n_leaves][S]
+    // prior of every leaf per variant type class (Prior::compute depends on scenario, variant type and the allele
+    // frequencies only; prior.rs:718-736 caches it per contig): filled by the first warps that need it
+    double* prior_val;      // [4][n_leaves]
+    uint32_t* prior_side;   // [4][n_leaves] status bits the computation raised
+    int* prior_state;       // [4]: 0 = not computed, 2 = readable
+};
+
 // ------------------------------------------------------------------------------------------------ math
 // Out-of-line fp64 transcendentals: CUDA inlines ~50-100 instructions per call site, and with dozens of call sites
 // the kernel outgrows the instruction caches (ncu: stall_no_instruction dominated the first versions). One copy each.

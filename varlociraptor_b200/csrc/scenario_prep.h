@@ -229,6 +229,90 @@ struct ScenarioPrep {
         return wp;
     }
 
+    // ---- all-Set scenarios (engine_sets.cuh): leaves in the order GenericPosterior::density visits them ------------
+    std::vector<SetsFold> sets_folds;
+    std::vector<SetsLeaf> sets_leaves;
+    std::vector<double> sets_leaf_vaf;
+    bool sets_ok = true;
+
+    void sets_walk(const vlr_scenario_t* sc, int ni, int event, double* vaf, unsigned posmask, unsigned discmask) {
+        if (!sets_ok) return;
+        const vlr_node_t& n = sc->nodes[ni];
+        if (n.kind != VLR_NODE_SET || n.n_vafs < 1) {
+            sets_ok = false;
+            return;
+        }
+        bool all_pos = true;
+        for (int i = 0; i < n.n_vafs; ++i)
+            if (!(sc->set_vafs[n.vaf_offset + i] > 0.0)) all_pos = false;
+        const unsigned pm = posmask | (all_pos ? 1u << n.sample : 0u);
+        const double saved = vaf[n.sample];
+        for (int i = 0; i < n.n_vafs; ++i) {
+            vaf[n.sample] = sc->set_vafs[n.vaf_offset + i];
+            const unsigned dm = discmask | (1u << n.sample);
+            if (n.n_children == 0) {
+                if ((int)sets_leaves.size() >= SETS_MAXL) {
+                    sets_ok = false;
+                    return;
+                }
+                SetsLeaf lf;
+                std::memset(&lf, 0, sizeof lf);
+                lf.event = (uint8_t)event;
+                lf.posmask = (uint8_t)pm;
+                lf.discmask = (uint8_t)dm;
+                for (int s = 0; s < sc->n_samples; ++s) {
+                    const int by = sc->samples[s].contamination_by;
+                    const double v = vaf[s], vb = by >= 0 ? vaf[by] : 0.0;
+                    int f = -1;
+                    for (size_t k = 0; k < sets_folds.size(); ++k)
+                        if (sets_folds[k].sample == s && sets_folds[k].vaf == v && sets_folds[k].vaf_by == vb) f = (int)k;
+                    if (f < 0) {
+                        if ((int)sets_folds.size() >= SETS_MAXF) {
+                            sets_ok = false;
+                            return;
+                        }
+                        f = (int)sets_folds.size();
+                        sets_folds.push_back(SetsFold{v, vb, s, 0});
+                    }
+                    lf.fold[s] = (uint8_t)f;
+                }
+                sets_leaves.push_back(lf);
+                for (int s = 0; s < sc->n_samples; ++s) sets_leaf_vaf.push_back(vaf[s]);
+            } else {
+                for (int k = 0; k < n.n_children; ++k) sets_walk(sc, n.first_child + k, event, vaf, pm, dm);
+            }
+        }
+        vaf[n.sample] = saved;
+    }
+
+    // Host part of the plan (the device pointers are filled in by the caller). Not eligible: anything but Set nodes,
+    // overlapping events (MAP candidates would have to be offered across events, engine_core.cuh map_offer_all), more
+    // than SETS_MAXS samples.
+    SetsPlan sets_plan() {
+        SetsPlan sp;
+        std::memset(&sp, 0, sizeof sp);
+        const vlr_scenario_t* sc = src;
+        sets_folds.clear();
+        sets_leaves.clear();
+        sets_leaf_vaf.clear();
+        sets_ok = true;
+        if (!sc || sc->n_samples > SETS_MAXS || sc->n_samples > 3 || events_overlap || !lfc_nodes.empty()) return sp;
+        for (int e = 0; e < sc->n_events && sets_ok; ++e) {
+            sp.ev_first[e] = (int)sets_leaves.size();
+            for (int r = 0; r < sc->events[e].n_roots && sets_ok; ++r) {
+                double vaf[VLR_MAX_SAMPLES];
+                for (int s = 0; s < VLR_MAX_SAMPLES; ++s) vaf[s] = 0.0; // an unset sample reads as 0.0 (Ops of the generic engine)
+                sets_walk(sc, sc->events[e].first_root + r, e, vaf, 0u, 0u);
+            }
+            sp.ev_count[e] = (int)sets_leaves.size() - sp.ev_first[e];
+        }
+        if (!sets_ok || sets_leaves.empty()) return sp;
+        sp.eligible = 1;
+        sp.n_folds = (int)sets_folds.size();
+        sp.n_leaves = (int)sets_leaves.size();
+        return sp;
+    }
+
     bool fail(const char* msg) {
         error = msg;
         return false;

@@ -506,6 +506,64 @@ __global__ void __launch_bounds__(THREADS, 2) vlr_wave_finish_kernel(const __gri
     }
 }
 
+// ---- all-Set pipeline kernels (engine_sets.cuh) -----------------------------------------------------------------------
+struct SetsParams {
+    DevScenario sc;
+    DevBatch b;
+    DevResults r;
+    SetsPlan sp;
+    vlr_small::SetsBufs sb;
+    WarpWs* ws;
+    int64_t sub_lo;
+    int n_sub;
+    int want_be;
+};
+constexpr size_t SETS_LC_WARP_SMEM = (size_t)vlr_small::CTX_STRIDE + sizeof(double) * (4 * vlr_small::SETS_SM_READS + SETS_MAXF);
+
+__global__ void __launch_bounds__(THREADS, VLR_PREP_MIN_CTAS) vlr_sets_pre_kernel(const __grid_constant__ SetsParams p) {
+    using namespace vlr_small;
+    Ctx& c = *reinterpret_cast<Ctx*>(vlr_smem + (size_t)group_in_cta() * CTX_STRIDE);
+    for (;;) {
+        unsigned long long t = 0;
+        if (lane_id() == 0) t = atomicAdd(&p.sb.cnt->ticket[0], 1ULL);
+        t = __shfl_sync(FULL, t, 0, LANES);
+        if (t >= (unsigned long long)p.n_sub) break;
+        sets_pre_locus(&p.sc, &p.b, p.sb, p.sub_lo + (int64_t)t, (int)t, p.want_be != 0, c);
+        warp_sync();
+    }
+}
+
+// warp per lc; shared memory per warp: [Ctx][coefficient arena: SETS_SM_READS x 4 doubles][fold values: SETS_MAXF doubles]
+__global__ void __launch_bounds__(THREADS, 2) vlr_sets_lc_kernel(const __grid_constant__ SetsParams p) {
+    using namespace vlr_small;
+    Ctx& c = *reinterpret_cast<Ctx*>(vlr_smem + (size_t)group_in_cta() * CTX_STRIDE);
+    double* arena = reinterpret_cast<double*>(vlr_smem + (size_t)WARPS_PER_CTA * CTX_STRIDE) +
+                    (size_t)group_in_cta() * (4 * SETS_SM_READS + SETS_MAXF);
+    const unsigned long long n_lc = min(p.sb.cnt->n_lc, (unsigned)p.sb.lc_cap);
+    for (;;) {
+        unsigned long long t = 0;
+        if (lane_id() == 0) t = atomicAdd(&p.sb.cnt->ticket[1], 1ULL);
+        t = __shfl_sync(FULL, t, 0, LANES);
+        if (t >= n_lc) break;
+        sets_lc(&p.sc, &p.b, p.sp, p.sb, (int)t, p.sub_lo, p.want_be != 0, c, arena, arena + 4 * SETS_SM_READS);
+        warp_sync();
+    }
+}
+
+__global__ void __launch_bounds__(THREADS, 2) vlr_sets_finish_kernel(const __grid_constant__ SetsParams p) {
+    using namespace vlr_small;
+    Ctx& c = *reinterpret_cast<Ctx*>(vlr_smem + (size_t)group_in_cta() * CTX_STRIDE);
+    WarpWs* ws = p.ws + (blockIdx.x * WARPS_PER_CTA + group_in_cta());
+    for (;;) {
+        unsigned long long t = 0;
+        if (lane_id() == 0) t = atomicAdd(&p.sb.cnt->ticket[2], 1ULL);
+        t = __shfl_sync(FULL, t, 0, LANES);
+        if (t >= (unsigned long long)p.n_sub) break;
+        sets_finish_locus(&p.sc, &p.b, &p.r, p.sp, p.sb, ws, p.sub_lo + (int64_t)t, (int)t, c);
+        warp_sync();
+    }
+}
+
 // fp64 peak microbenchmark: 8 independent FMA chains per thread, register resident
 __global__ void __launch_bounds__(256) vlr_fp64_peak_kernel(double* out, int iters) {
     double a0 = 1.0 + threadIdx.x * 1e-9, a1 = a0 + 1e-3, a2 = a0 + 2e-3, a3 = a0 + 3e-3, a4 = a0 + 4e-3, a5 = a0 + 5e-3,
@@ -562,6 +620,7 @@ struct Slot { // one in-flight chunk of vlr_call_batch
     // wavefront pipeline workspace (one sub-chunk of loci at a time)
     DevBuf w_cnt, w_loci, w_lcs, w_ogx, w_ogf, w_coef, w_tasks[2], w_list[2], w_dlist[2], w_deferred, w_gx, w_gf, w_be, w_ben;
     DevBuf w_rlist, w_rgx, w_rgm, w_rge, w_rscratch, w_cscratch; // lc-resident round kernel
+    DevBuf s_cnt, s_loci, s_lcs, s_deferred, s_be, s_ben;        // all-Set pipeline
 };
 
 } // namespace
@@ -577,6 +636,11 @@ struct vlr_ctx {
     WavePlan wplan;
     int wave_grid_prep = 0, wave_grid_round = 0, wave_grid_finish = 0, wave_grid_res = 0;
     bool resident = true; // VLR_RESIDENT=0: per-round kernels only (A/B measurements)
+    bool sets = false;    // all-Set scenario (pedigrees): the all-Set pipeline serves it (engine_sets.cuh)
+    SetsPlan splan;
+    int sets_grid_pre = 0, sets_grid_lc = 0, sets_grid_finish = 0;
+    size_t sets_smem_lc = 0;
+    DevBuf d_sets_folds, d_sets_leaves, d_sets_leaf_vaf, d_sets_prior_val, d_sets_prior_side, d_sets_prior_state;
     size_t wave_smem_prep = 0;
     int ctx_stride = 0;
     size_t smem_bytes = 0;
@@ -742,8 +806,65 @@ vlr_status_t launch_wave(vlr_ctx* ctx, Slot& sl, const DevBatch& b, const DevRes
     return VLR_OK;
 }
 
+// All-Set pipeline over the batch, one sub-chunk of loci after the other on `stream`: pre -> lc -> finish -> generic
+// engine for the deferred loci.
+vlr_status_t launch_sets(vlr_ctx* ctx, Slot& sl, const DevBatch& b, const DevResults& r, cudaStream_t stream) {
+    using namespace vlr_small;
+    const bool want_be = r.afd_capacity > 0;
+    const int n_sub_cap = 65536;
+    const int lc_cap = n_sub_cap * 4;
+    const int S = ctx->S;
+    CK(sl.s_cnt.ensure(sizeof(SetsCounters)));
+    CK(sl.s_loci.ensure(sizeof(SetsLocus) * (size_t)n_sub_cap));
+    CK(sl.s_lcs.ensure(sizeof(SetsLC) * (size_t)lc_cap));
+    CK(sl.s_deferred.ensure(sizeof(int) * (size_t)n_sub_cap));
+    CK(sl.s_ben.ensure(sizeof(unsigned) * (size_t)n_sub_cap));
+    if (want_be) CK(sl.s_be.ensure(sizeof(double) * (size_t)n_sub_cap * SETS_MAXL * (2 + S)));
+    SetsParams p;
+    p.sc = ctx->dsc;
+    p.b = b;
+    p.r = r;
+    p.sp = ctx->splan;
+    p.sb.cnt = (SetsCounters*)sl.s_cnt.p;
+    p.sb.loci = (SetsLocus*)sl.s_loci.p;
+    p.sb.lcs = (SetsLC*)sl.s_lcs.p;
+    p.sb.deferred = (int*)sl.s_deferred.p;
+    p.sb.be = want_be ? (double*)sl.s_be.p : nullptr;
+    p.sb.be_n = (unsigned*)sl.s_ben.p;
+    p.sb.lc_cap = lc_cap;
+    p.ws = (WarpWs*)sl.ws.p;
+    p.want_be = want_be ? 1 : 0;
+    KernelParams gp; // generic engine over the deferred loci
+    gp.sc = ctx->dsc;
+    gp.b = b;
+    gp.r = r;
+    gp.ws = (WarpWs*)sl.ws.p;
+    gp.coef = (double*)sl.coef.p;
+    gp.be = want_be ? (double*)sl.be.p : nullptr;
+    gp.ticket = &p.sb.cnt->ticket[3];
+    gp.locus_list = p.sb.deferred;
+    gp.locus_list_n = &p.sb.cnt->n_deferred;
+    gp.coef_cap = sl.coef_cap;
+    gp.sm_reads = SM_READS;
+    gp.ctx_stride = ctx->ctx_stride;
+    gp.be_stride = (int64_t)BE_CAP * (2 + ctx->S);
+    for (int64_t lo = 0; lo < b.n_loci; lo += n_sub_cap) {
+        p.sub_lo = lo;
+        p.n_sub = (int)std::min<int64_t>(n_sub_cap, b.n_loci - lo);
+        CK(cudaMemsetAsync(sl.s_cnt.p, 0, sizeof(SetsCounters), stream));
+        vlr_sets_pre_kernel<<<ctx->sets_grid_pre, THREADS, ctx->wave_smem_prep, stream>>>(p);
+        vlr_sets_lc_kernel<<<ctx->sets_grid_lc, THREADS, ctx->sets_smem_lc, stream>>>(p);
+        vlr_sets_finish_kernel<<<ctx->sets_grid_finish, THREADS, ctx->wave_smem_prep, stream>>>(p);
+        vlr_call_kernel_vlr_small<<<ctx->grid, THREADS, ctx->smem_bytes, stream>>>(gp);
+        CK(cudaGetLastError());
+        ctx->launches += 4;
+    }
+    return VLR_OK;
+}
+
 vlr_status_t launch(vlr_ctx* ctx, Slot& sl, const DevBatch& b, const DevResults& r, cudaStream_t stream, int64_t avg_reads = 0) {
     if (ctx->wave && b.n_loci > 0) return launch_wave(ctx, sl, b, r, avg_reads, stream, 0, b.n_loci);
+    if (ctx->sets && b.n_loci > 0) return launch_sets(ctx, sl, b, r, stream);
     KernelParams p;
     p.sc = ctx->dsc;
     p.b = b;
@@ -1109,6 +1230,40 @@ vlr_status_t vlr_ctx_create(const vlr_scenario_t* scenario, int32_t device, vlr_
         CKB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n4, vlr_wave_resident_kernel, RES_THREADS, RES_SMEM));
         ctx->wave_grid_res = std::max(1, n4) * ctx->n_sms;
     }
+    {
+        const char* sets_env = getenv("VLR_SETS"); // VLR_SETS=0: generic engine only (A/B measurements, tests)
+        ctx->splan = ctx->prep.sets_plan();
+        ctx->sets = ctx->small && !ctx->wave && ctx->splan.eligible && !(sets_env && sets_env[0] == '0');
+    }
+    if (ctx->sets) {
+        SetsPlan& sp = ctx->splan;
+        CKB(upload(ctx->d_sets_folds, ctx->prep.sets_folds.data(), sizeof(SetsFold) * ctx->prep.sets_folds.size()));
+        CKB(upload(ctx->d_sets_leaves, ctx->prep.sets_leaves.data(), sizeof(SetsLeaf) * ctx->prep.sets_leaves.size()));
+        CKB(upload(ctx->d_sets_leaf_vaf, ctx->prep.sets_leaf_vaf.data(), sizeof(double) * ctx->prep.sets_leaf_vaf.size()));
+        CKB(ctx->d_sets_prior_val.ensure(sizeof(double) * 4 * (size_t)sp.n_leaves));
+        CKB(ctx->d_sets_prior_side.ensure(sizeof(uint32_t) * 4 * (size_t)sp.n_leaves));
+        CKB(ctx->d_sets_prior_state.ensure(sizeof(int) * 4));
+        CKB(cudaMemset(ctx->d_sets_prior_state.p, 0, sizeof(int) * 4));
+        sp.folds = (const SetsFold*)ctx->d_sets_folds.p;
+        sp.leaves = (const SetsLeaf*)ctx->d_sets_leaves.p;
+        sp.leaf_vaf = (const double*)ctx->d_sets_leaf_vaf.p;
+        sp.prior_val = (double*)ctx->d_sets_prior_val.p;
+        sp.prior_side = (uint32_t*)ctx->d_sets_prior_side.p;
+        sp.prior_state = (int*)ctx->d_sets_prior_state.p;
+        ctx->wave_smem_prep = (size_t)WARPS_PER_CTA * (size_t)ctx->ctx_stride;
+        ctx->sets_smem_lc = (size_t)WARPS_PER_CTA * SETS_LC_WARP_SMEM;
+        CKB(cudaFuncSetAttribute(vlr_sets_pre_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->wave_smem_prep));
+        CKB(cudaFuncSetAttribute(vlr_sets_lc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->sets_smem_lc));
+        CKB(cudaFuncSetAttribute(vlr_sets_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->wave_smem_prep));
+        int n1 = 0, n2 = 0, n3 = 0;
+        CKB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n1, vlr_sets_pre_kernel, THREADS, ctx->wave_smem_prep));
+        CKB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n2, vlr_sets_lc_kernel, THREADS, ctx->sets_smem_lc));
+        CKB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n3, vlr_sets_finish_kernel, THREADS, ctx->wave_smem_prep));
+        ctx->sets_grid_pre = std::max(1, n1) * ctx->n_sms;
+        ctx->sets_grid_lc = std::max(1, n2) * ctx->n_sms;
+        // the finish kernel indexes the per-warp scratch (WarpWs) of the generic workspace: same number of warps or fewer
+        ctx->sets_grid_finish = std::min(std::max(1, n3) * ctx->n_sms, ctx->grid);
+    }
     CKB(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     if (const char* e = getenv("VLR_WAVE_STREAMS")) ctx->n_aux = std::max(1, std::min((int)vlr_ctx::MAX_AUX, atoi(e)));
     for (int i = 0; i < vlr_ctx::MAX_AUX; ++i) {
@@ -1138,7 +1293,7 @@ void vlr_ctx_destroy(vlr_ctx_t* ctx) {
                          &s.afd_logp, &s.ws, &s.coef, &s.be, &s.ticket, &s.w_cnt, &s.w_loci, &s.w_lcs, &s.w_ogx,
                          &s.w_ogf, &s.w_coef, &s.w_tasks[0], &s.w_tasks[1], &s.w_list[0], &s.w_list[1], &s.w_dlist[0], &s.w_dlist[1], &s.w_deferred,
                          &s.w_gx, &s.w_gf, &s.w_be, &s.w_ben, &s.w_rlist, &s.w_rgx, &s.w_rgm, &s.w_rge, &s.w_rscratch,
-                         &s.w_cscratch};
+                         &s.w_cscratch, &s.s_cnt, &s.s_loci, &s.s_lcs, &s.s_deferred, &s.s_be, &s.s_ben};
         for (DevBuf* b : all) b->release();
     };
     if (ctx->stream) {
@@ -1155,7 +1310,8 @@ void vlr_ctx_destroy(vlr_ctx_t* ctx) {
     if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
     for (auto& s : ctx->slots) free_slot(s);
     DevBuf* sc[] = {&ctx->d_samples, &ctx->d_events, &ctx->d_nodes, &ctx->d_set_vafs, &ctx->d_spectra,
-                    &ctx->d_lfc_nodes, &ctx->d_lfc_ordinal, &ctx->d_prior_tab};
+                    &ctx->d_lfc_nodes, &ctx->d_lfc_ordinal, &ctx->d_prior_tab, &ctx->d_sets_folds, &ctx->d_sets_leaves,
+                    &ctx->d_sets_leaf_vaf, &ctx->d_sets_prior_val, &ctx->d_sets_prior_side, &ctx->d_sets_prior_state};
     for (DevBuf* b : sc) b->release();
     delete ctx;
 }
