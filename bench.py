@@ -376,17 +376,22 @@ def run_workload(args, D, cfg, loci, steps, warmup, strong, oracle_legs, n_oracl
         hbm_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
         abytes = algorithmic_bytes(batch, E)
         wave = os.environ.get("VLR_WAVE", "1") != "0" and cfg in (2, 4, 5)
+        sets = os.environ.get("VLR_SETS", "1") != "0" and cfg == 3
         traffic, traffic_src = None, None
         kernel_name = "vlr_call_kernel_vlr_small (warp per locus)"
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r2_wave.json" if wave else "traffic_r1.json")))
-            if cfg in (2, 4):
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r2_wave.json" if wave else
+                                             ("traffic_r2_cfg3.json" if sets else "traffic_r1.json"))))
+            if cfg in (2, 3, 4):
                 traffic = int(tr["dram_bytes_per_locus"] * batch.n_loci)
                 traffic_src = "static: %s (ncu dram__bytes of one sub-chunk of this workload, scaled by loci)" % tr.get("source", "profiles/")
-            if wave:
+            if wave or sets:
                 kernel_name = tr["kernels"]
         except (OSError, KeyError, ValueError):
             pass
+        if cfg == 5 and wave:
+            kernel_name = ("wavefront pipeline: vlr_wave_resident_kernel for the lcs whose pileups fit a shared-memory slot, "
+                           "vlr_wave_round_kernel (CTA per group, per round) for deeper ones")
         # the bound that matters: fp64. Executed-algorithm flops = joint evaluations x reads of the
         # integrated pileup x flops per read and abscissa; peak = DFMA microbenchmark on this device.
         reads_leaf = batch.n_reads / max(1, batch.n_loci) / S
