@@ -196,9 +196,6 @@ struct Ctx {
     int s_gt1[MAXS];   // some kept read has prob_sample_alt > 0
     int coef_off[MAXS];
     double ksum[MAXS];
-    // pileup likelihood cache (generic.rs:43-53; here LC_WAYS most recent entries per sample and config)
-    double lc_k1[MAXS][LC_WAYS], lc_k2[MAXS][LC_WAYS], lc_v[MAXS][LC_WAYS];
-    int lc_n[MAXS];
     // events
     int cur_slot; // 2*event + (artifact config ? 1 : 0)
     double map_joint[2 * MAXE];
@@ -215,6 +212,22 @@ struct Ctx {
     int be_filter;
     double flt_vaf[MAXS];
     uint32_t flt_disc;
+    // per-event accumulators and end-of-locus scratch
+    Lse ev_plain[MAXE], ev_twin[MAXE];
+    double joint_u[2 * MAXE];
+    double my_lp[MAXE + 1];
+    int scen_u[2 * MAXE];
+    uint8_t art_u[2 * MAXE];
+    double prior_absent; // Prior of the all-zero event (absent-only mode), NaN = not computed yet
+    int pc_n;
+    uint32_t n_base;
+    uint32_t n_pileup_evals;
+    // ---- everything above is what the pre-pass, the coefficients, a pileup evaluation, the prior and locus_tail use:
+    // the pipelines' kernels (engine_wave.cuh, engine_sets.cuh) may give a warp only CTX_LEAN bytes of shared memory.
+    // Below: state of the generic engine's tree walk only.
+    // pileup likelihood cache (generic.rs:43-53; here LC_WAYS most recent entries per sample and config)
+    double lc_k1[MAXS][LC_WAYS], lc_k2[MAXS][LC_WAYS], lc_v[MAXS][LC_WAYS];
+    int lc_n[MAXS];
     // operand stack of the tree walk (generic.rs clones LikelihoodOperands per branch / grid point)
     Ops ops[MAXD + 2];
     // adaptive integration state per nesting level (at most one Range level per sample) and the leaf fast path
@@ -225,29 +238,24 @@ struct Ctx {
     double slot_x[MSLOTS], slot_f[MSLOTS];
     int slot_task[MSLOTS];
     int slot_slow[MSLOTS];
-    // per-event accumulators and end-of-locus scratch
-    Lse ev_plain[MAXE], ev_twin[MAXE];
-    double joint_u[2 * MAXE];
-    double my_lp[MAXE + 1];
-    int scen_u[2 * MAXE];
-    uint8_t art_u[2 * MAXE];
-    double prior_absent; // Prior of the all-zero event (absent-only mode), NaN = not computed yet
     // prior cache for all-discrete VAF vectors (prior.rs:718-736 keeps an LRU(1000) keyed by the VAF vector; the
     // prior does not depend on the artifact config, so the 27 combinations of a trio are computed once per locus)
     double pc_key[PRIOR_CACHE][MAXS], pc_val[PRIOR_CACHE];
-    int pc_n;
-    uint32_t n_base;
-    uint32_t n_pileup_evals;
 };
 
 // Shared memory of a CTA: [WARPS_PER_CTA x Ctx][WARPS_PER_CTA x SM_READS x 4 doubles]. Deriving the per-warp
 // references from the __shared__ symbol (instead of carrying generic pointers through calls) lets the compiler
 // emit LDS/STS for all of the uniform state.
 constexpr int CTX_STRIDE = (int)((sizeof(Ctx) + 15) & ~(size_t)15);
+constexpr int CTX_LEAN = (int)((offsetof(Ctx, lc_k1) + 15) & ~(size_t)15); // see the comment inside Ctx
 #ifdef VLR_HOST_EMU
 VLR_DEV Ctx& warp_ctx(Ctx& c) { return c; }
 #else
-VLR_DEV Ctx& warp_ctx(Ctx&) { return *reinterpret_cast<Ctx*>(vlr_smem + group_in_cta() * CTX_STRIDE); }
+// The same object, addressed through the __shared__ symbol (LDS/STS instead of generic accesses) wherever the kernel
+// placed it inside its dynamic shared memory.
+VLR_DEV Ctx& warp_ctx(Ctx& c) {
+    return *reinterpret_cast<Ctx*>(vlr_smem + (__cvta_generic_to_shared(&c) - __cvta_generic_to_shared(vlr_smem)));
+}
 VLR_DEV double* warp_coef_sm() {
     return reinterpret_cast<double*>(vlr_smem + WARPS_PER_CTA * CTX_STRIDE) + group_in_cta() * (SM_READS * 4);
 }

@@ -60,7 +60,7 @@ VLR_DEV_NOINLINE void sets_fill_prior(Ctx& c_, const SetsPlan& sp, int vt) {
     const int S = c.sc->S;
     const uint32_t s0 = c.status;
     for (int l = 0; l < sp.n_leaves; ++l) {
-        Ops& ev = c.ops[0];
+        Ops ev; // (a local: the kernel's shared-memory Ctx is lean, without the operand stack)
         for (int s = 0; s < MAXS; ++s) ev.vaf[s] = s < S ? sp.leaf_vaf[(size_t)l * S + s] : 0.0;
         ev.set_mask = (1u << S) - 1u;
         ev.disc_mask = sp.leaves[l].discmask;

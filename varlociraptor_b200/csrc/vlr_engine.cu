@@ -518,11 +518,11 @@ struct SetsParams {
     int n_sub;
     int want_be;
 };
-constexpr size_t SETS_LC_WARP_SMEM = (size_t)vlr_small::CTX_STRIDE + sizeof(double) * (4 * vlr_small::SETS_SM_READS + SETS_MAXF);
+constexpr size_t SETS_LC_WARP_SMEM = (size_t)vlr_small::CTX_LEAN + sizeof(double) * (4 * vlr_small::SETS_SM_READS + SETS_MAXF);
 
 __global__ void __launch_bounds__(THREADS, VLR_PREP_MIN_CTAS) vlr_sets_pre_kernel(const __grid_constant__ SetsParams p) {
     using namespace vlr_small;
-    Ctx& c = *reinterpret_cast<Ctx*>(vlr_smem + (size_t)group_in_cta() * CTX_STRIDE);
+    Ctx& c = *reinterpret_cast<Ctx*>(vlr_smem + (size_t)group_in_cta() * CTX_LEAN);
     for (;;) {
         unsigned long long t = 0;
         if (lane_id() == 0) t = atomicAdd(&p.sb.cnt->ticket[0], 1ULL);
@@ -536,8 +536,8 @@ __global__ void __launch_bounds__(THREADS, VLR_PREP_MIN_CTAS) vlr_sets_pre_kerne
 // warp per lc; shared memory per warp: [Ctx][coefficient arena: SETS_SM_READS x 4 doubles][fold values: SETS_MAXF doubles]
 __global__ void __launch_bounds__(THREADS, 2) vlr_sets_lc_kernel(const __grid_constant__ SetsParams p) {
     using namespace vlr_small;
-    Ctx& c = *reinterpret_cast<Ctx*>(vlr_smem + (size_t)group_in_cta() * CTX_STRIDE);
-    double* arena = reinterpret_cast<double*>(vlr_smem + (size_t)WARPS_PER_CTA * CTX_STRIDE) +
+    Ctx& c = *reinterpret_cast<Ctx*>(vlr_smem + (size_t)group_in_cta() * CTX_LEAN);
+    double* arena = reinterpret_cast<double*>(vlr_smem + (size_t)WARPS_PER_CTA * CTX_LEAN) +
                     (size_t)group_in_cta() * (4 * SETS_SM_READS + SETS_MAXF);
     const unsigned long long n_lc = min(p.sb.cnt->n_lc, (unsigned)p.sb.lc_cap);
     for (;;) {
@@ -552,7 +552,7 @@ __global__ void __launch_bounds__(THREADS, 2) vlr_sets_lc_kernel(const __grid_co
 
 __global__ void __launch_bounds__(THREADS, 2) vlr_sets_finish_kernel(const __grid_constant__ SetsParams p) {
     using namespace vlr_small;
-    Ctx& c = *reinterpret_cast<Ctx*>(vlr_smem + (size_t)group_in_cta() * CTX_STRIDE);
+    Ctx& c = *reinterpret_cast<Ctx*>(vlr_smem + (size_t)group_in_cta() * CTX_LEAN);
     WarpWs* ws = p.ws + (blockIdx.x * WARPS_PER_CTA + group_in_cta());
     for (;;) {
         unsigned long long t = 0;
@@ -1250,7 +1250,7 @@ vlr_status_t vlr_ctx_create(const vlr_scenario_t* scenario, int32_t device, vlr_
         sp.prior_val = (double*)ctx->d_sets_prior_val.p;
         sp.prior_side = (uint32_t*)ctx->d_sets_prior_side.p;
         sp.prior_state = (int*)ctx->d_sets_prior_state.p;
-        ctx->wave_smem_prep = (size_t)WARPS_PER_CTA * (size_t)ctx->ctx_stride;
+        ctx->wave_smem_prep = (size_t)WARPS_PER_CTA * (size_t)vlr_small::CTX_LEAN; // (pre, finish: a lean Ctx per warp)
         ctx->sets_smem_lc = (size_t)WARPS_PER_CTA * SETS_LC_WARP_SMEM;
         CKB(cudaFuncSetAttribute(vlr_sets_pre_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->wave_smem_prep));
         CKB(cudaFuncSetAttribute(vlr_sets_lc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->sets_smem_lc));
