@@ -232,6 +232,55 @@ void vlr_ctx_destroy(vlr_ctx_t* ctx);
  * run on the context's stream; returns after the results are in host memory. */
 vlr_status_t vlr_call_batch(vlr_ctx_t* ctx, const vlr_batch_t* batch, vlr_results_t* results);
 
+/* ---- packed batch: the same columns, losslessly encoded for the host -> device link ------------------------------
+ * vlr_call_batch() moves 32 bytes per read over PCIe, which bounds the end-to-end rate of the all-Set pipeline
+ * (pedigrees) and, from ~8 M loci/s on, of the tumor-normal pipeline. Most observation columns hold few distinct
+ * values: prob_mapping is a function of MAPQ, prob_hit_base of the read length, prob_double_overlap is mostly ln 0,
+ * prob_sample_alt is ln 1 for SNVs, SNV base-quality emissions come from <= 94 quality values; on disk the reference
+ * shrinks them value by value (MiniLogProb, utils/mod.rs:448-474: f16 where that keeps the integer part). A packed
+ * column keeps the exact f32 BIT PATTERNS (so results are bitwise those of vlr_call_batch) in the smallest of:
+ *   F32     4 bytes per read, as in vlr_batch_t
+ *   F16     2 bytes per read: every value is exactly representable as IEEE half
+ *   DICT16  2 bytes per read: code into a dictionary of <= 65536 bit patterns
+ *   DICT8   1 byte per read:  code into a dictionary of <= 256 bit patterns
+ *   CONST   0 bytes per read: every row holds dict[0]
+ * The engine widens the chunk on the device (vlr_unpack_kernel: one pass, HBM-bound) in front of the pre-pass. */
+enum { VLR_ENC_F32 = 0, VLR_ENC_F16 = 1, VLR_ENC_DICT16 = 2, VLR_ENC_DICT8 = 3, VLR_ENC_CONST = 4 };
+enum {
+    VLR_COL_PROB_MAPPING = 0, VLR_COL_PROB_REF = 1, VLR_COL_PROB_ALT = 2, VLR_COL_PROB_MISSED_ALLELE = 3,
+    VLR_COL_PROB_SAMPLE_ALT = 4, VLR_COL_PROB_DOUBLE_OVERLAP = 5, VLR_COL_PROB_HIT_BASE = 6, VLR_COL_READ_FLAGS = 7,
+    VLR_N_PACKED_COLUMNS = 8
+};
+typedef struct {
+    int32_t encoding;     /* VLR_ENC_* */
+    int32_t n_dict;       /* DICT16 / DICT8: entries of `dict`; CONST: 1; else 0 */
+    const void* data;     /* [n_reads] float / uint32 (F32), uint16 half bits (F16), uint16 (DICT16), uint8 (DICT8); NULL (CONST) */
+    const uint32_t* dict; /* [n_dict] bit patterns of the f32 values (of the flag words for VLR_COL_READ_FLAGS) */
+} vlr_column_t;
+typedef struct {
+    int64_t n_loci;
+    int64_t n_reads;
+    const int64_t* read_offsets;                 /* as in vlr_batch_t */
+    vlr_column_t columns[VLR_N_PACKED_COLUMNS];  /* VLR_COL_*; read_flags: F32 means plain uint32 words, F16 is invalid */
+    const float* prob_homopolymer_artifact;      /* optional, plain (indel records only) */
+    const float* prob_homopolymer_variant;
+    const uint32_t* locus_flags;
+    const float* locus_heterozygosity_phred;
+    const float* locus_semr_phred;
+} vlr_packed_batch_t;
+
+/* Encodes `batch` (host buffers) column by column into the smallest lossless encoding; the packed arrays are
+ * page-locked (vlr_host_alloc) and owned by `*out` until vlr_packed_batch_free(). Pointers of `batch` that need no
+ * encoding (read_offsets, locus columns, homopolymer columns) are borrowed, not copied: they must outlive `*out`.
+ * `n_threads` <= 0: all host threads. This is host work a producer does while it decodes observation records
+ * (obs_codec): one hash lookup per value. */
+vlr_status_t vlr_pack_batch(const vlr_batch_t* batch, int32_t n_threads, vlr_packed_batch_t** out);
+void vlr_packed_batch_free(vlr_packed_batch_t* packed);
+/* Bytes vlr_call_batch_packed() moves host -> device for `packed`. */
+int64_t vlr_packed_batch_bytes(const vlr_packed_batch_t* packed, int32_t n_samples);
+/* vlr_call_batch() on a packed batch: same chunking, same results bit for bit. */
+vlr_status_t vlr_call_batch_packed(vlr_ctx_t* ctx, const vlr_packed_batch_t* packed, vlr_results_t* results);
+
 /* Same, with every pointer in `batch` and `results` a DEVICE pointer on the
  * context's device. Asynchronous on `cuda_stream` (a cudaStream_t, 0 = the
  * context's own stream); the caller synchronises. Calls on one context share

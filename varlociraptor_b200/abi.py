@@ -123,6 +123,27 @@ class Batch(C.Structure):
     ]
 
 
+# packed batch (vlr_packed_batch_t): lossless per-column encodings for the host -> device link
+ENC_F32, ENC_F16, ENC_DICT16, ENC_DICT8, ENC_CONST = 0, 1, 2, 3, 4
+ENC_NAMES = ["f32", "f16", "dict16", "dict8", "const"]
+ENC_BYTES = [4, 2, 2, 1, 0]
+PACKED_COLUMNS = ["prob_mapping", "prob_ref", "prob_alt", "prob_missed_allele", "prob_sample_alt",
+                  "prob_double_overlap", "prob_hit_base", "read_flags"]
+
+
+class Column(C.Structure):  # vlr_column_t
+    _fields_ = [("encoding", C.c_int32), ("n_dict", C.c_int32), ("data", C.c_void_p), ("dict", _u32p)]
+
+
+class PackedBatch(C.Structure):  # vlr_packed_batch_t
+    _fields_ = [
+        ("n_loci", C.c_int64), ("n_reads", C.c_int64), ("read_offsets", _i64p),
+        ("columns", Column * 8),
+        ("prob_homopolymer_artifact", _f32p), ("prob_homopolymer_variant", _f32p),
+        ("locus_flags", _u32p), ("locus_heterozygosity_phred", _f32p), ("locus_semr_phred", _f32p),
+    ]
+
+
 class Results(C.Structure):
     _fields_ = [
         ("log_posteriors", _f64p), ("log_marginal", _f64p), ("map_vaf", _f64p), ("map_config", _i32p),

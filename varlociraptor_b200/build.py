@@ -10,7 +10,7 @@ DEPS = ["vlr_engine.cu", "engine_core.cuh", "engine_wave.cuh", "engine_resident.
 # -fmad=false: the reference (Rust) and the oracle never contract a*b+c; grid abscissae (linspace, observable
 # limits) must round identically or adaptive grids diverge. The hot loop uses explicit fma() where fusion is wanted.
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
-              "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-shared", "-cudart", "shared"]
 
 
 def is_stale() -> bool:

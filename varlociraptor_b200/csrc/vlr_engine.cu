@@ -7,6 +7,7 @@
 // Host: vlr_call_batch() streams a host batch through NBUF slots (chunk of loci -> H2D -> kernel -> D2H, one CUDA
 // stream per slot) so copies overlap compute; vlr_call_batch_device() launches on device-resident buffers.
 // There is no CPU fallback: without a usable CUDA device vlr_ctx_create() fails with VLR_ERR_NO_DEVICE.
+#include <cuda_fp16.h>
 #include <cuda_pipeline.h>
 #include <cuda_runtime.h>
 
@@ -14,7 +15,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <new>
 #include <string>
+#include <thread>
+#include <utility>
 #include <vector>
 
 // The engine core is instantiated twice by inclusion: a small variant (<= 3 samples, <= 8 events, tree depth <= 6:
@@ -590,6 +594,62 @@ inline int align16(size_t x) { return (int)((x + 15) & ~(size_t)15); }
         if (_e != cudaSuccess) return ctx->fail_cuda(_e, #call, __LINE__);            \
     } while (0)
 
+// ---- packed batch (include/vlr_engine.h: vlr_packed_batch_t) --------------------------------------------------------
+// Widens the encoded columns of one chunk to the f32 / u32 columns the pipelines read: blockIdx.y = column, four rows
+// per thread (one 4- or 8-byte load, one 16-byte store, both coalesced). HBM-bound: <= 9 bytes in, 32 bytes out per read.
+struct UnpackParams {
+    const void* src[VLR_N_PACKED_COLUMNS];
+    const uint32_t* dict[VLR_N_PACKED_COLUMNS];
+    uint32_t* dst[VLR_N_PACKED_COLUMNS];
+    int enc[VLR_N_PACKED_COLUMNS];
+    int n_dict[VLR_N_PACKED_COLUMNS];
+    int64_t n;
+};
+
+__global__ void __launch_bounds__(256) vlr_unpack_kernel(const __grid_constant__ UnpackParams p) {
+    __shared__ uint32_t sdict[256];
+    const int c = (int)blockIdx.y;
+    const int enc = p.enc[c];
+    if (enc == VLR_ENC_F32) return; // copied straight into place
+    uint32_t* __restrict__ dst = p.dst[c];
+    const int64_t n = p.n, n4 = n >> 2;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (enc == VLR_ENC_DICT8) {
+        for (int i = (int)threadIdx.x; i < 256; i += (int)blockDim.x) sdict[i] = i < p.n_dict[c] ? p.dict[c][i] : 0u;
+        __syncthreads();
+        const uchar4* __restrict__ s4 = reinterpret_cast<const uchar4*>(p.src[c]);
+        for (int64_t i = t0; i < n4; i += stride) {
+            const uchar4 k = s4[i];
+            reinterpret_cast<uint4*>(dst)[i] = make_uint4(sdict[k.x], sdict[k.y], sdict[k.z], sdict[k.w]);
+        }
+        const uint8_t* __restrict__ s1 = reinterpret_cast<const uint8_t*>(p.src[c]);
+        for (int64_t i = (n4 << 2) + t0; i < n; i += stride) dst[i] = sdict[s1[i]];
+    } else if (enc == VLR_ENC_DICT16) {
+        const uint32_t* __restrict__ d = p.dict[c];
+        const ushort4* __restrict__ s4 = reinterpret_cast<const ushort4*>(p.src[c]);
+        for (int64_t i = t0; i < n4; i += stride) {
+            const ushort4 k = s4[i];
+            reinterpret_cast<uint4*>(dst)[i] = make_uint4(__ldg(d + k.x), __ldg(d + k.y), __ldg(d + k.z), __ldg(d + k.w));
+        }
+        const uint16_t* __restrict__ s1 = reinterpret_cast<const uint16_t*>(p.src[c]);
+        for (int64_t i = (n4 << 2) + t0; i < n; i += stride) dst[i] = __ldg(d + s1[i]);
+    } else if (enc == VLR_ENC_F16) {
+        const ushort4* __restrict__ s4 = reinterpret_cast<const ushort4*>(p.src[c]);
+        auto widen = [](unsigned short h) { return __float_as_uint(__half2float(__ushort_as_half(h))); };
+        for (int64_t i = t0; i < n4; i += stride) {
+            const ushort4 k = s4[i];
+            reinterpret_cast<uint4*>(dst)[i] = make_uint4(widen(k.x), widen(k.y), widen(k.z), widen(k.w));
+        }
+        const uint16_t* __restrict__ s1 = reinterpret_cast<const uint16_t*>(p.src[c]);
+        for (int64_t i = (n4 << 2) + t0; i < n; i += stride) dst[i] = widen(s1[i]);
+    } else { // VLR_ENC_CONST
+        const uint32_t v = p.dict[c][0];
+        for (int64_t i = t0; i < n4; i += stride) reinterpret_cast<uint4*>(dst)[i] = make_uint4(v, v, v, v);
+        for (int64_t i = (n4 << 2) + t0; i < n; i += stride) dst[i] = v;
+    }
+}
+
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
@@ -613,6 +673,7 @@ struct DevBuf {
 struct Slot { // one in-flight chunk of vlr_call_batch
     cudaStream_t stream = nullptr;
     DevBuf offsets, cols[7], rflags, hart, hvar, lflags, het, semr;
+    DevBuf pk[VLR_N_PACKED_COLUMNS], pk_dict[VLR_N_PACKED_COLUMNS]; // packed chunk (vlr_call_batch_packed) and its dictionaries
     DevBuf log_post, log_marginal, map_vaf, map_config, best_event, status, n_base, afd_count, afd_vaf, afd_logp;
     DevBuf ws, coef, be, ticket;
     int coef_cap = 0;
@@ -1288,6 +1349,8 @@ void vlr_ctx_destroy(vlr_ctx_t* ctx) {
         }
         s.offsets.release();
         for (auto& c : s.cols) c.release();
+        for (auto& c : s.pk) c.release();
+        for (auto& c : s.pk_dict) c.release();
         DevBuf* all[] = {&s.rflags, &s.hart, &s.hvar, &s.lflags, &s.het, &s.semr, &s.log_post, &s.log_marginal,
                          &s.map_vaf, &s.map_config, &s.best_event, &s.status, &s.n_base, &s.afd_count, &s.afd_vaf,
                          &s.afd_logp, &s.ws, &s.coef, &s.be, &s.ticket, &s.w_cnt, &s.w_loci, &s.w_lcs, &s.w_ogx,
@@ -1392,11 +1455,10 @@ vlr_status_t vlr_call_batch_device(vlr_ctx_t* ctx, const vlr_batch_t* batch, vlr
     return VLR_OK;
 }
 
-vlr_status_t vlr_call_batch(vlr_ctx_t* ctx, const vlr_batch_t* batch, vlr_results_t* results) {
-    if (!ctx) return VLR_ERR_INVALID_ARGUMENT;
-    if (!batch_valid(batch) || !results_valid(results)) return ctx->fail(VLR_ERR_INVALID_ARGUMENT, "invalid batch or results");
+static vlr_status_t call_batch_host(vlr_ctx_t* ctx, const vlr_packed_batch_t* batch, vlr_results_t* results) {
     CK(cudaSetDevice(ctx->device));
     ctx->launches = 0;
+    int64_t unpack_launches = 0;
     const int S = ctx->S, E = ctx->E;
     const int64_t L = batch->n_loci;
     if (L == 0) return VLR_OK;
@@ -1407,8 +1469,9 @@ vlr_status_t vlr_call_batch(vlr_ctx_t* ctx, const vlr_batch_t* batch, vlr_result
     const int64_t target_reads = 16 << 20;
     const int64_t max_loci_chunk = 1 << 16;
     const int cap = results->afd_capacity;
-    const float* cols[7] = {batch->prob_mapping, batch->prob_ref,         batch->prob_alt,     batch->prob_missed_allele,
-                            batch->prob_sample_alt, batch->prob_double_overlap, batch->prob_hit_base};
+    static const size_t enc_bytes[5] = {4, 2, 2, 1, 0}; // VLR_ENC_*: bytes per read on the link
+    bool any_packed = false;
+    for (int c = 0; c < VLR_N_PACKED_COLUMNS; ++c) any_packed = any_packed || batch->columns[c].encoding != VLR_ENC_F32;
     int64_t lo = 0;
     int k = 0;
     vlr_status_t st = VLR_OK;
@@ -1431,12 +1494,43 @@ vlr_status_t vlr_call_batch(vlr_ctx_t* ctx, const vlr_batch_t* batch, vlr_result
         if (st != VLR_OK) break;
         CK(sl.offsets.ensure(sizeof(int64_t) * (size_t)(nl * S + 1)));
         CK(cudaMemcpyAsync(sl.offsets.p, off + lo * S, sizeof(int64_t) * (size_t)(nl * S + 1), cudaMemcpyHostToDevice, s));
-        for (int c = 0; c < 7; ++c) {
-            CK(sl.cols[c].ensure(sizeof(float) * (size_t)std::max<int64_t>(nr, 1)));
-            if (nr) CK(cudaMemcpyAsync(sl.cols[c].p, cols[c] + r0, sizeof(float) * (size_t)nr, cudaMemcpyHostToDevice, s));
+        // columns: plain ones go straight into place, encoded ones into the slot's staging buffers (with their
+        // dictionaries the first time the slot is used in this call) and are widened on the device
+        UnpackParams up;
+        up.n = nr;
+        for (int c = 0; c < VLR_N_PACKED_COLUMNS; ++c) {
+            const vlr_column_t& col = batch->columns[c];
+            DevBuf& dstb = c == VLR_COL_READ_FLAGS ? sl.rflags : sl.cols[c];
+            CK(dstb.ensure(sizeof(uint32_t) * (size_t)std::max<int64_t>(nr, 4)));
+            up.enc[c] = col.encoding;
+            up.n_dict[c] = col.n_dict;
+            up.dst[c] = (uint32_t*)dstb.p;
+            up.src[c] = nullptr;
+            up.dict[c] = nullptr;
+            const size_t w = enc_bytes[col.encoding];
+            if (col.encoding == VLR_ENC_F32) {
+                if (nr) CK(cudaMemcpyAsync(dstb.p, (const char*)col.data + 4 * (size_t)r0, 4 * (size_t)nr, cudaMemcpyHostToDevice, s));
+                continue;
+            }
+            if (w) {
+                CK(sl.pk[c].ensure(w * (size_t)std::max<int64_t>(nr, 4)));
+                if (nr) CK(cudaMemcpyAsync(sl.pk[c].p, (const char*)col.data + w * (size_t)r0, w * (size_t)nr, cudaMemcpyHostToDevice, s));
+                up.src[c] = sl.pk[c].p;
+            }
+            if (col.n_dict > 0) {
+                if (k < NBUF) {
+                    CK(sl.pk_dict[c].ensure(sizeof(uint32_t) * (size_t)col.n_dict));
+                    CK(cudaMemcpyAsync(sl.pk_dict[c].p, col.dict, sizeof(uint32_t) * (size_t)col.n_dict, cudaMemcpyHostToDevice, s));
+                }
+                up.dict[c] = (const uint32_t*)sl.pk_dict[c].p;
+            }
         }
-        CK(sl.rflags.ensure(sizeof(uint32_t) * (size_t)std::max<int64_t>(nr, 1)));
-        if (nr) CK(cudaMemcpyAsync(sl.rflags.p, batch->read_flags + r0, sizeof(uint32_t) * (size_t)nr, cudaMemcpyHostToDevice, s));
+        if (any_packed && nr) {
+            const int bx = (int)std::min<int64_t>((nr / 4 + 255) / 256 + 1, (int64_t)ctx->n_sms * 8);
+            vlr_unpack_kernel<<<dim3(bx, VLR_N_PACKED_COLUMNS), 256, 0, s>>>(up);
+            CK(cudaGetLastError());
+            unpack_launches++;
+        }
         auto opt_up = [&](DevBuf& buf, const float* src, int64_t first, int64_t n) -> cudaError_t {
             if (!src) return cudaSuccess;
             cudaError_t e = buf.ensure(sizeof(float) * (size_t)std::max<int64_t>(n, 1));
@@ -1509,11 +1603,304 @@ vlr_status_t vlr_call_batch(vlr_ctx_t* ctx, const vlr_batch_t* batch, vlr_result
         lo = hi;
         ++k;
     }
+    ctx->launches += unpack_launches;
     for (int i = 0; i < NBUF; ++i) {
         cudaError_t e = cudaStreamSynchronize(ctx->slots[i].stream);
         if (e != cudaSuccess && st == VLR_OK) st = ctx->fail_cuda(e, "cudaStreamSynchronize", __LINE__);
     }
     return st;
+}
+
+
+static bool packed_valid(const vlr_packed_batch_t* b) {
+    if (!b || b->n_loci < 0 || b->n_reads < 0) return false;
+    if (b->n_loci == 0) return true;
+    if (!b->read_offsets || !b->locus_flags) return false;
+    for (int c = 0; c < VLR_N_PACKED_COLUMNS; ++c) {
+        const vlr_column_t& col = b->columns[c];
+        switch (col.encoding) {
+        case VLR_ENC_F32: if (b->n_reads > 0 && !col.data) return false; break;
+        case VLR_ENC_F16: if (c == VLR_COL_READ_FLAGS || (b->n_reads > 0 && !col.data)) return false; break;
+        case VLR_ENC_DICT16: if (col.n_dict < 1 || col.n_dict > 65536 || !col.dict || (b->n_reads > 0 && !col.data)) return false; break;
+        case VLR_ENC_DICT8: if (col.n_dict < 1 || col.n_dict > 256 || !col.dict || (b->n_reads > 0 && !col.data)) return false; break;
+        case VLR_ENC_CONST: if (col.n_dict != 1 || !col.dict) return false; break;
+        default: return false;
+        }
+    }
+    return true;
+}
+
+vlr_status_t vlr_call_batch(vlr_ctx_t* ctx, const vlr_batch_t* batch, vlr_results_t* results) {
+    if (!ctx) return VLR_ERR_INVALID_ARGUMENT;
+    if (!batch_valid(batch) || !results_valid(results)) return ctx->fail(VLR_ERR_INVALID_ARGUMENT, "invalid batch or results");
+    vlr_packed_batch_t pk; // the plain batch as a packed one whose columns are all F32: one code path
+    memset(&pk, 0, sizeof pk);
+    pk.n_loci = batch->n_loci;
+    pk.n_reads = batch->n_reads;
+    pk.read_offsets = batch->read_offsets;
+    const void* cols[VLR_N_PACKED_COLUMNS] = {batch->prob_mapping, batch->prob_ref, batch->prob_alt, batch->prob_missed_allele,
+                                              batch->prob_sample_alt, batch->prob_double_overlap, batch->prob_hit_base, batch->read_flags};
+    for (int c = 0; c < VLR_N_PACKED_COLUMNS; ++c) {
+        pk.columns[c].encoding = VLR_ENC_F32;
+        pk.columns[c].data = cols[c];
+    }
+    pk.prob_homopolymer_artifact = batch->prob_homopolymer_artifact;
+    pk.prob_homopolymer_variant = batch->prob_homopolymer_variant;
+    pk.locus_flags = batch->locus_flags;
+    pk.locus_heterozygosity_phred = batch->locus_heterozygosity_phred;
+    pk.locus_semr_phred = batch->locus_semr_phred;
+    return call_batch_host(ctx, &pk, results);
+}
+
+// ---- vlr_pack_batch: host-side encoder of the packed batch -----------------------------------------------------------
+} // extern "C"
+namespace {
+
+struct PackedOwner { // what vlr_pack_batch hands out: the public struct first, then what it owns
+    vlr_packed_batch_t pub;
+    std::vector<std::pair<void*, bool>> bufs; // (pointer, page-locked?)
+};
+
+// open addressing over 32-bit patterns; slot value = pattern + 1 as 64 bits (0 = empty)
+struct PatternSet {
+    static constexpr uint32_t CAP = 1u << 18, MASK = CAP - 1;
+    std::vector<uint64_t> slot;
+    std::vector<uint32_t> code; // same index as slot: dictionary position (filled by number())
+    uint32_t n = 0;
+    PatternSet() : slot(CAP, 0) {}
+    static uint32_t hash(uint32_t v) {
+        v *= 0x9E3779B1u;
+        return (v ^ (v >> 15)) & MASK;
+    }
+    // false: more than 65536 distinct patterns (no dictionary)
+    bool insert(uint32_t v) {
+        uint32_t h = hash(v);
+        const uint64_t key = (uint64_t)v + 1;
+        for (;;) {
+            const uint64_t s = slot[h];
+            if (s == key) return true;
+            if (s == 0) {
+                if (n >= 65536) return false;
+                slot[h] = key;
+                ++n;
+                return true;
+            }
+            h = (h + 1) & MASK;
+        }
+    }
+    uint32_t find(uint32_t v) const {
+        uint32_t h = hash(v);
+        const uint64_t key = (uint64_t)v + 1;
+        while (slot[h] != key) h = (h + 1) & MASK;
+        return code[h];
+    }
+    std::vector<uint32_t> values() const {
+        std::vector<uint32_t> out;
+        out.reserve(n);
+        for (uint64_t s : slot)
+            if (s) out.push_back((uint32_t)(s - 1));
+        return out;
+    }
+    void number(const std::vector<uint32_t>& sorted) {
+        code.assign(CAP, 0);
+        for (uint32_t i = 0; i < (uint32_t)sorted.size(); ++i) {
+            uint32_t h = hash(sorted[i]);
+            const uint64_t key = (uint64_t)sorted[i] + 1;
+            while (slot[h] != key) h = (h + 1) & MASK;
+            code[h] = i;
+        }
+    }
+};
+
+// the f32 pattern is exactly representable as an IEEE half (normal, subnormal, zero, inf; NaNs are left to F32/dictionary)
+inline bool half_exact(uint32_t b) {
+    const uint32_t e = (b >> 23) & 0xffu, m = b & 0x7fffffu;
+    if (e == 0xffu) return m == 0;           // inf
+    if (e == 0) return m == 0;               // zero (f32 subnormals are below the half range)
+    const int ue = (int)e - 127;
+    if (ue > 15) return false;
+    if (ue >= -14) return (m & 0x1fffu) == 0; // normal half: 10 mantissa bits
+    if (ue < -24) return false;
+    const int drop = 13 + (-14 - ue);         // subnormal half: fewer bits
+    return (m & ((1u << drop) - 1u)) == 0;
+}
+inline uint16_t to_half_exact(uint32_t b) { // only for patterns half_exact() accepted
+    const uint32_t sgn = (b >> 16) & 0x8000u, e = (b >> 23) & 0xffu, m = b & 0x7fffffu;
+    if (e == 0xffu) return (uint16_t)(sgn | 0x7c00u);
+    if (e == 0) return (uint16_t)sgn;
+    const int ue = (int)e - 127;
+    if (ue >= -14) return (uint16_t)(sgn | ((uint32_t)(ue + 15) << 10) | (m >> 13));
+    const uint32_t full = m | 0x800000u;
+    return (uint16_t)(sgn | (full >> (13 + (-14 - ue))));
+}
+
+template <class F>
+void parallel_ranges(int64_t n, int threads, F f) {
+    if (threads <= 1 || n < (1 << 16)) {
+        f(0, (int64_t)0, n);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (int t = 0; t < threads; ++t) th.emplace_back(f, t, n * t / threads, n * (t + 1) / threads);
+    for (auto& x : th) x.join();
+}
+
+} // namespace
+extern "C" {
+
+vlr_status_t vlr_pack_batch(const vlr_batch_t* batch, int32_t n_threads, vlr_packed_batch_t** out) {
+    if (!out || !batch_valid(batch)) return VLR_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    int threads = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    if (threads < 1) threads = 1;
+    if (threads > 64) threads = 64;
+    PackedOwner* own = new (std::nothrow) PackedOwner();
+    if (!own) return VLR_ERR_OUT_OF_MEMORY;
+    vlr_packed_batch_t& pk = own->pub;
+    memset(&pk, 0, sizeof pk);
+    pk.n_loci = batch->n_loci;
+    pk.n_reads = batch->n_reads;
+    pk.read_offsets = batch->read_offsets;
+    pk.prob_homopolymer_artifact = batch->prob_homopolymer_artifact;
+    pk.prob_homopolymer_variant = batch->prob_homopolymer_variant;
+    pk.locus_flags = batch->locus_flags;
+    pk.locus_heterozygosity_phred = batch->locus_heterozygosity_phred;
+    pk.locus_semr_phred = batch->locus_semr_phred;
+    const uint32_t* cols[VLR_N_PACKED_COLUMNS] = {
+        (const uint32_t*)batch->prob_mapping,    (const uint32_t*)batch->prob_ref,
+        (const uint32_t*)batch->prob_alt,        (const uint32_t*)batch->prob_missed_allele,
+        (const uint32_t*)batch->prob_sample_alt, (const uint32_t*)batch->prob_double_overlap,
+        (const uint32_t*)batch->prob_hit_base,   batch->read_flags};
+    const int64_t n = batch->n_reads;
+    auto pinned = [&](size_t bytes) -> void* { // page-locked when a device is there (plain memory still works, staged)
+        void* p = vlr_host_alloc(bytes ? bytes : 1);
+        const bool locked = p != nullptr;
+        if (!p) p = malloc(bytes ? bytes : 1);
+        if (p) own->bufs.emplace_back(p, locked);
+        return p;
+    };
+    vlr_status_t st = VLR_OK;
+    for (int c = 0; c < VLR_N_PACKED_COLUMNS && st == VLR_OK; ++c) {
+        vlr_column_t& col = pk.columns[c];
+        const uint32_t* src = cols[c];
+        col.encoding = VLR_ENC_F32;
+        col.data = src;
+        if (n == 0) continue;
+        // pass 1: distinct patterns per thread (one-entry memo: neighbouring reads repeat), half-exactness
+        std::vector<PatternSet> sets((size_t)threads);
+        std::vector<char> overflow((size_t)threads, 0), all_half((size_t)threads, 1);
+        parallel_ranges(n, threads, [&](int t, int64_t lo, int64_t hi) {
+            PatternSet& ps = sets[(size_t)t];
+            bool ok = true, half = c != VLR_COL_READ_FLAGS;
+            uint32_t last = ~src[lo];
+            for (int64_t i = lo; i < hi && (ok || half); ++i) {
+                const uint32_t v = src[i];
+                if (v == last) continue;
+                last = v;
+                if (ok && !ps.insert(v)) ok = false;
+                if (half && !half_exact(v)) half = false;
+            }
+            overflow[(size_t)t] = ok ? 0 : 1;
+            all_half[(size_t)t] = half ? 1 : 0;
+        });
+        bool dict_ok = true, half_ok = c != VLR_COL_READ_FLAGS;
+        for (int t = 0; t < threads; ++t) {
+            dict_ok = dict_ok && !overflow[(size_t)t];
+            half_ok = half_ok && all_half[(size_t)t];
+        }
+        PatternSet& all = sets[0];
+        for (int t = 1; t < threads && dict_ok; ++t)
+            for (uint32_t v : sets[(size_t)t].values())
+                if (!all.insert(v)) {
+                    dict_ok = false;
+                    break;
+                }
+        std::vector<uint32_t> dict;
+        if (dict_ok) {
+            dict = all.values();
+            std::sort(dict.begin(), dict.end());
+            all.number(dict);
+        }
+        int enc = VLR_ENC_F32;
+        if (dict_ok && dict.size() == 1) enc = VLR_ENC_CONST;
+        else if (dict_ok && dict.size() <= 256) enc = VLR_ENC_DICT8;
+        else if (half_ok) enc = VLR_ENC_F16;
+        else if (dict_ok) enc = VLR_ENC_DICT16;
+        if (enc == VLR_ENC_F32) continue;
+        col.encoding = enc;
+        if (enc != VLR_ENC_F16) {
+            uint32_t* d = (uint32_t*)pinned(sizeof(uint32_t) * dict.size());
+            if (!d) {
+                st = VLR_ERR_OUT_OF_MEMORY;
+                break;
+            }
+            memcpy(d, dict.data(), sizeof(uint32_t) * dict.size());
+            col.dict = d;
+            col.n_dict = (int32_t)dict.size();
+        }
+        if (enc == VLR_ENC_CONST) {
+            col.data = nullptr;
+            continue;
+        }
+        const size_t w = enc == VLR_ENC_DICT8 ? 1 : 2;
+        void* data = pinned(w * (size_t)n);
+        if (!data) {
+            st = VLR_ERR_OUT_OF_MEMORY;
+            break;
+        }
+        col.data = data;
+        // pass 2: codes
+        parallel_ranges(n, threads, [&](int, int64_t lo, int64_t hi) {
+            uint32_t last = ~src[lo], code = 0;
+            for (int64_t i = lo; i < hi; ++i) {
+                const uint32_t v = src[i];
+                if (v != last) {
+                    last = v;
+                    code = enc == VLR_ENC_F16 ? (uint32_t)to_half_exact(v) : all.find(v);
+                }
+                if (w == 1) ((uint8_t*)data)[i] = (uint8_t)code;
+                else ((uint16_t*)data)[i] = (uint16_t)code;
+            }
+        });
+    }
+    if (st != VLR_OK) {
+        vlr_packed_batch_free(&own->pub);
+        return st;
+    }
+    *out = &own->pub;
+    return VLR_OK;
+}
+
+void vlr_packed_batch_free(vlr_packed_batch_t* packed) {
+    if (!packed) return;
+    PackedOwner* own = reinterpret_cast<PackedOwner*>(packed); // `pub` is the first member
+    for (auto& b : own->bufs) {
+        if (b.second) vlr_host_free(b.first);
+        else free(b.first);
+    }
+    delete own;
+}
+
+int64_t vlr_packed_batch_bytes(const vlr_packed_batch_t* pk, int32_t n_samples) {
+    if (!pk) return 0;
+    static const int64_t w[5] = {4, 2, 2, 1, 0};
+    int64_t bytes = 8 * (pk->n_loci * n_samples + 1) + 4 * pk->n_loci;
+    for (int c = 0; c < VLR_N_PACKED_COLUMNS; ++c) {
+        const vlr_column_t& col = pk->columns[c];
+        if (col.encoding < 0 || col.encoding > 4) return -1;
+        bytes += w[col.encoding] * pk->n_reads + 4 * (int64_t)col.n_dict;
+    }
+    if (pk->prob_homopolymer_artifact) bytes += 4 * pk->n_reads;
+    if (pk->prob_homopolymer_variant) bytes += 4 * pk->n_reads;
+    if (pk->locus_heterozygosity_phred) bytes += 4 * pk->n_loci;
+    if (pk->locus_semr_phred) bytes += 4 * pk->n_loci;
+    return bytes;
+}
+
+vlr_status_t vlr_call_batch_packed(vlr_ctx_t* ctx, const vlr_packed_batch_t* packed, vlr_results_t* results) {
+    if (!ctx) return VLR_ERR_INVALID_ARGUMENT;
+    if (!packed_valid(packed) || !results_valid(results)) return ctx->fail(VLR_ERR_INVALID_ARGUMENT, "invalid packed batch or results");
+    return call_batch_host(ctx, packed, results);
 }
 
 } // extern "C"
