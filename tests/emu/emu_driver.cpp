@@ -137,8 +137,10 @@ extern "C" int32_t vlr_emu_wave_call_batch(const vlr_scenario_t* sc, const vlr_b
     wb.be_n = be_n.data();
     wb.coef_cap = coef_cap * 4;
     wb.lc_cap = lc_cap;
-    std::vector<int> rlist((size_t)lc_cap);
-    std::vector<double> rgx((size_t)W_MAXT * W_GCAP), rgm((size_t)W_MAXT * W_GCAP), rscratch(3 * W_GCAP), cscratch(R_SCRATCH);
+    std::vector<int> rlist((size_t)lc_cap * R_CLASSES);
+    std::vector<double> rgx((size_t)W_MAXT * W_GCAP), rgm((size_t)W_MAXT * W_GCAP), rscratch(3 * W_GCAP);
+    const int cs_reads = (int)std::min<int64_t>(R_MAXREADS, std::max<int64_t>(max_reads, 256));
+    std::vector<double> cscratch((size_t)6 * cs_reads);
     std::vector<int> rge((size_t)W_MAXT * W_GCAP);
     wb.rlist = rlist.data();
     wb.rgx = rgx.data();
@@ -146,6 +148,7 @@ extern "C" int32_t vlr_emu_wave_call_batch(const vlr_scenario_t* sc, const vlr_b
     wb.rge = rge.data();
     wb.rscratch = rscratch.data();
     wb.cscratch = cscratch.data();
+    wb.cscratch_reads = cs_reads;
     {
         const char* e = getenv("VLR_RESIDENT");
         wb.allow_resident = !(e && e[0] == '0');
@@ -154,33 +157,48 @@ extern "C" int32_t vlr_emu_wave_call_batch(const vlr_scenario_t* sc, const vlr_b
     Ctx* c = new Ctx;
     for (int64_t i = 0; i < L; ++i) wave_pre_locus(&ds, &db, wp, wb, i, (int)i, want_be, *c);
     const int n_lc = (int)std::min<unsigned>(cnt.n_lc, (unsigned)lc_cap);
-    for (int k = 0; k < n_lc; ++k) wave_lc_init(&ds, wp, wb, k);
+    std::fill(rlist.begin(), rlist.end(), -1);
+    unsigned key_off[R_CLASSES][W_KEYS];
+    for (int cl = 0; cl < R_CLASSES; ++cl) wave_key_offsets(cnt.rkey_n[cl], key_off[cl]);
+    for (int k = 0; k < n_lc; ++k) {
+        const int id = wave_lc_init(&ds, wp, wb, k);
+        if (id < 0) continue;
+        const unsigned at = key_off[id / W_KEYS][id % W_KEYS] + wa_add_u32(&cnt.rkey_cur[id / W_KEYS][id % W_KEYS], 1u);
+        rlist[(size_t)(id / W_KEYS) * lc_cap + at] = k;
+    }
     for (int k = 0; k < n_lc; ++k) wave_lc_coef(&ds, &db, wp, wb, k, 0, want_be, *c, 0);
-    // lc-resident rounds (engine_resident.cuh): one "octet" of a single lane, the slot filled by a plain copy
+    // lc-resident rounds (engine_resident.cuh): one group of a single lane per size class, the slot filled by a plain copy
     {
         ROct* oc = new ROct;
+        std::vector<double> slot((size_t)R_SLOT_QL * R_QW);
+        oc->q = slot.data();
         const WGroup one{0, 1, 1u};
         const WSplit lane{0, 1, 1u};
-        for (unsigned k = 0; k < cnt.rlist_n + cnt.rlist_back_n; ++k) {
-            const int lci = k < cnt.rlist_n ? rlist[k] : rlist[lc_cap - 1 - (int)(k - cnt.rlist_n)];
-            const WaveLC& L = lcs[lci];
-            oc->lc.lci = lci;
-            oc->lc.li = L.li;
-            oc->lc.ci = L.ci;
-            oc->lc.nqPx = L.nqPx;
-            oc->lc.nqPy = L.nqPy;
-            oc->lc.nqTx = L.nqTx;
-            oc->lc.nqTy = L.nqTy;
-            oc->lc.ksumP = L.ksumP;
-            oc->lc.ksumT = L.ksumT;
-            const int nq = L.nqPx + L.nqPy + L.nqTx + L.nqTy;
-            if (nq > R_SLOT_Q) return -VLR_ERR_INVALID_ARGUMENT;
-            std::memcpy(oc->q, wb.coef + L.coefP, sizeof(double) * R_QW * (size_t)nq);
-            int n_tasks = r_first_tasks(&ds, wp, wb, lci, oc->task, one);
-            for (int round = 0; n_tasks > 0; ++round) {
-                for (int t = 0; t < n_tasks; ++t)
-                    r_task(&ds, wp, wb, *oc, t, n_tasks, wb.rgx + (size_t)t * W_GCAP, wb.rgm + (size_t)t * W_GCAP, wb.rge + (size_t)t * W_GCAP, lane);
-                n_tasks = r_advance(&ds, wp, wb, *oc, round, n_tasks, wb.rgx, wb.rgm, wb.rge, wb.rscratch, want_be, one);
+        for (int cls = 1; cls <= R_CLASSES; ++cls) {
+            const int* rl = rlist.data() + (size_t)(cls - 1) * lc_cap;
+            const unsigned n_all = cnt.rlist_total[cls - 1];
+            for (unsigned k = 0; k < n_all; ++k) {
+                const int lci = rl[k];
+                if (lci < 0) return -VLR_ERR_INVALID_ARGUMENT; // the key counts of the pre-pass and the placement disagree
+                const WaveLC& L = lcs[lci];
+                oc->lc.lci = lci;
+                oc->lc.li = L.li;
+                oc->lc.ci = L.ci;
+                oc->lc.nqPx = L.nqPx;
+                oc->lc.nqPy = L.nqPy;
+                oc->lc.nqTx = L.nqTx;
+                oc->lc.nqTy = L.nqTy;
+                oc->lc.ksumP = L.ksumP;
+                oc->lc.ksumT = L.ksumT;
+                const int nq = L.nqPx + L.nqPy + L.nqTx + L.nqTy;
+                if (nq > r_slot_q(cls)) return -VLR_ERR_INVALID_ARGUMENT;
+                std::memcpy(oc->q, wb.coef + L.coefP, sizeof(double) * R_QW * (size_t)nq);
+                int n_tasks = r_first_tasks(&ds, wp, wb, lci, oc->task, one);
+                for (int round = 0; n_tasks > 0; ++round) {
+                    for (int t = 0; t < n_tasks; ++t)
+                        r_task(&ds, wp, wb, *oc, t, n_tasks, wb.rgx + (size_t)t * W_GCAP, wb.rgm + (size_t)t * W_GCAP, wb.rge + (size_t)t * W_GCAP, lane, 1u);
+                    n_tasks = r_advance(&ds, wp, wb, *oc, round, n_tasks, wb.rgx, wb.rgm, wb.rge, wb.rscratch, want_be, one);
+                }
             }
         }
         delete oc;

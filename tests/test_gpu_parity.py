@@ -31,7 +31,15 @@ def _compare(o, g, afd=True, max_knife_fraction=0.02):
     ok = ~ke
     assert max_abs_delta(o.log_posteriors[ok], g.log_posteriors[ok]) <= TOL
     assert max_abs_delta(o.log_marginal[ok], g.log_marginal[ok]) <= TOL * 10  # marginal ~ -1e3: relative 1e-14
-    assert max_abs_delta(o.map_vaf[ok], g.map_vaf[ok]) == 0.0
+    # MAP allele frequencies are visited abscissae: identical, except where two visited abscissae are one ulp apart (a
+    # closing linspace point next to a dyadic bracket point: lo + k * step rounds differently from (l + r) / 2) and carry
+    # the same likelihood to the last bits - then the order of the factors in the pileup product decides which of the
+    # two is "the first maximum" (config 5, locus 297: 0x1.aa00000000000p-8 vs 0x1.aa00000000001p-8)
+    with np.errstate(invalid="ignore"):
+        d_map = np.abs(o.map_vaf[ok] - g.map_vaf[ok])
+    same = (o.map_vaf[ok] == g.map_vaf[ok]) | (np.isnan(o.map_vaf[ok]) & np.isnan(g.map_vaf[ok]))
+    assert np.all(same | (d_map <= 2 * np.spacing(np.abs(o.map_vaf[ok]))))
+    assert np.count_nonzero(~same) <= max(1, int(2e-3 * same.size))
     assert np.array_equal(o.best_event[ok], g.best_event[ok])
     assert np.array_equal(o.map_config[ok], g.map_config[ok])
     assert np.array_equal(o.status[ok], g.status[ok])

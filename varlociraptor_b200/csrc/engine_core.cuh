@@ -191,6 +191,7 @@ struct Ctx {
     Art art;
     // per sample
     int n_obs[MAXS];
+    int n_notref[MAXS]; // kept reads that do not favour the reference (prob_ref <= prob_alt)
     int clear_ref[MAXS];
     int s_one[MAXS];   // every kept read has prob_sample_alt == 0
     int s_gt1[MAXS];   // some kept read has prob_sample_alt > 0
@@ -426,7 +427,8 @@ VLR_DEV_NOINLINE void locus_prepass(Ctx& c_, BiasPlan& plan) {
         bool any_strong_alt = w_sum_i(n_strong_alt) > 0;
         bool has_ins = w_sum_i(n_ins) > 0, has_del = w_sum_i(n_del) > 0;
         if (!(!any_strong_alt || (has_ins && has_del))) he_informative = false;
-        all_ref[s] = w_sum_i(n_notref) == 0;
+        c.n_notref[s] = w_sum_i(n_notref);
+        all_ref[s] = c.n_notref[s] == 0;
         uq_salt[s] = w_sum_i(n_uq);
         ev_cnt[s][0] = 0;
         ev_cnt[s][1] = w_sum_i(e1);

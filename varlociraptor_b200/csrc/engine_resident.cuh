@@ -24,17 +24,27 @@
 constexpr int R_DEG = 5;          // reads per polynomial
 constexpr int R_QW = R_DEG + 1;   // coefficients (doubles) per polynomial: 48 bytes = 3 x 16
 constexpr int R_SLOT_Q = 48;      // polynomials per octet slot (parent and leaf pileup of one lc): 2304 bytes
-constexpr int R_POOL_N = 400;     // sorted-list nodes per octet, shared by the tasks of a round: one 32-bit word each,
+constexpr int R_SLOT_QM = 208;    // ... of a warp's slot, medium class (~1000 reads): 9984 bytes
+constexpr int R_SLOT_QL = 832;    // ... of a warp's slot, large class (~4100 reads): 39936 bytes
+constexpr int R_CLASSES = 3;      // 1: an octet per lc; 2, 3: a warp per lc (deep pileups, depth skew)
+constexpr int R_POOL_N = 400;     // sorted-list nodes per lc, shared by the tasks of a round: one 32-bit word each,
                                   // (24-bit key << 8) | next node (a task visits ~60 points at resolution 0.01)
 constexpr int R_POOL_D = R_POOL_N / 2; // ... as doubles: 1600 bytes
 constexpr int R_SORT = 64;        // points of the OUTER grid sorted in the (then idle) pool (larger: global scratch)
 constexpr int R_NONE = 255;       // end of a sorted list
 constexpr int R_ZERO_E = -(1 << 29);
-constexpr int R_MAXREADS = R_DEG * R_SLOT_Q;  // no resident lc has more kept reads (r_fits)
-constexpr int R_SCRATCH = 6 * R_MAXREADS;     // coefficient kernel, per warp: 4 doubles per read + (c, d) pairs of a pileup
+constexpr int R_MAXREADS = R_DEG * R_SLOT_QL; // no resident lc has more kept reads (r_class)
+// coefficient kernel, per warp: 4 doubles per read + (c, d) pairs of a pileup = 6 doubles per read of the deepest
+// resident lc the workspace allows (WaveBufs::cscratch_reads <= R_MAXREADS)
 // upper bound of the polynomials of a pileup of n reads (two groups, each rounded up)
 VLR_DEV int r_qcap(int n) { return n / R_DEG + 2; }
-VLR_DEV bool r_fits(int nP, int nT) { return r_qcap(nP) + r_qcap(nT) <= R_SLOT_Q; }
+VLR_DEV int r_slot_q(int cls) { return cls == 1 ? R_SLOT_Q : (cls == 2 ? R_SLOT_QM : R_SLOT_QL); }
+// size class of an lc whose pileups hold nP and nT kept reads (0: not resident, the per-round kernels serve it)
+VLR_DEV int r_class(int nP, int nT, int scratch_reads) {
+    if (nP + nT > scratch_reads) return 0;
+    const int q = r_qcap(nP) + r_qcap(nT);
+    return q <= R_SLOT_Q ? 1 : (q <= R_SLOT_QM ? 2 : (q <= R_SLOT_QL ? 3 : 0));
+}
 
 struct MV { // value = m * 2^e with m in [1, 2), or exactly zero (m = 0, e = R_ZERO_E); a NaN m is a NaN value
     double m;
@@ -279,14 +289,15 @@ struct RLc { // what the rounds need from the lc record, read once
     double ksumP, ksumT;
 };
 
-struct alignas(16) ROct { // (128-bit loads of the polynomials, 16-byte bulk copies)
-    double q[R_SLOT_Q * R_QW];
+struct alignas(16) ROct { // per lc group (octet or warp) in shared memory; the slot of polynomials follows it
     double pool[R_POOL_D]; // during the tasks: list nodes (unsigned[R_POOL_N]), split evenly over the round's tasks;
                            // closing the outer integration: sort scratch (R_SORT abscissae, weights, ranks)
     RTask task[W_MAXT];
     RLc lc;
     unsigned long long bar; // mbarrier of the slot's bulk copy
+    double* q;              // the slot: r_slot_q(class) polynomials (128-bit loads, 16-byte bulk copies)
 };
+static_assert(sizeof(ROct) % 16 == 0, "the slot behind the record must stay 16-byte aligned");
 
 // ---- a task's points in abscissa order: singly linked list of 32-bit nodes, node index = visit index
 // node = (key << 8) | next; key = the upper 24 bits of the abscissa rounded to float (abscissae are allele frequencies
@@ -344,8 +355,11 @@ VLR_DEV_NOINLINE void r_link3(unsigned* node, const double* gx, int from, int cn
 // iteration's [m1, middle, m2] at the bracket's left end, the closing points at a node left behind by the bracket
 // and at the last middle. The closing trapezoid then needs no sort: each point knows its right neighbour (r_fin_list).
 // All H lanes perform the same stores (a lane reads back what it wrote).
+// `wmask`: the lanes of the WARP that run a task of this round (all of them are in here together). They meet again at
+// the top of every step, so the evaluation of a step runs once for all tasks of the warp however differently their
+// list walks went; a lane whose search is over waits there for the others.
 VLR_DEV void r_task_run(const DevScenario* sc, const WavePlan& wp, const ROct& oc, RTask& t, const bool dead, double a, double b,
-                        double* gx, double* gm, int* ge, unsigned* node, int cap, const WSplit sp) {
+                        double* gx, double* gm, int* ge, unsigned* node, int cap, const WSplit sp, const unsigned wmask) {
     const int T = wp.T;
     const vlr_sample_t& smT = sc->samples[T];
     double rhoT = 1.0, iotaT = 0.0;
@@ -396,7 +410,14 @@ VLR_DEV void r_task_run(const DevScenario* sc, const WavePlan& wp, const ROct& o
     // starts (the left end only moves up and the final middle lies above it, so the node stays below middle - 3 res)
     int i_lo = 0;
     int step = 0;
-    while (step < 4) {
+    for (;;) {
+#ifdef VLR_HOST_EMU
+        if (step >= 4) break;
+#else
+        __syncwarp(wmask);
+        if (!__any_sync(wmask, step < 4)) break;
+        if (step >= 4) continue;
+#endif
         double xs[3];
         int nvalid = 3;
         if (step == 0) {
@@ -673,7 +694,7 @@ VLR_DEV int r_first_tasks(const DevScenario* sc, const WavePlan& wp, const WaveB
 // Phase 1 of a round, per task (H lanes): the parent pileup at the task's parent_x (a constant of the leaf integration:
 // GenericLikelihood::compute, generic.rs:511-551, hits its per-sample cache for it at every point), then the search.
 VLR_DEV void r_task(const DevScenario* sc, const WavePlan& wp, const WaveBufs& wb, ROct& oc, int q, int cnt, double* gx, double* gm,
-                    int* ge, const WSplit sp) {
+                    int* ge, const WSplit sp, const unsigned wmask) {
     RTask& t = oc.task[q];
     const WaveLocus& wl = wb.loci[oc.lc.li];
     const double px = t.parent_x;
@@ -697,7 +718,7 @@ VLR_DEV void r_task(const DevScenario* sc, const WavePlan& wp, const WaveBufs& w
     const double b = t.parent_disc ? wl.ev_b[t.event] : wb.lcs[oc.lc.lci].tb;
     const int cap = R_POOL_N / cnt; // the task's share of the octet's list pool
     unsigned* node = reinterpret_cast<unsigned*>(oc.pool) + (size_t)q * cap;
-    r_task_run(sc, wp, oc, t, dead, a, b, gx, gm, ge, node, cap < W_GCAP ? cap : W_GCAP, sp);
+    r_task_run(sc, wp, oc, t, dead, a, b, gx, gm, ge, node, cap < W_GCAP ? cap : W_GCAP, sp, wmask);
 }
 
 // Phase 2 of a round (the whole group): integrate each task's grid, MAP bookkeeping in visit order (calling.rs:851-870),

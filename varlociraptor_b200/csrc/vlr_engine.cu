@@ -123,9 +123,29 @@ __global__ void __launch_bounds__(THREADS, VLR_PREP_MIN_CTAS) vlr_wave_pre_kerne
 
 __global__ void __launch_bounds__(256) vlr_wave_lcinit_kernel(const __grid_constant__ WaveParams p) {
     using namespace vlr_small;
+    __shared__ unsigned key_n[R_CLASSES * W_KEYS], key_off[R_CLASSES * W_KEYS];
+    for (int i = (int)threadIdx.x; i < R_CLASSES * W_KEYS; i += (int)blockDim.x) key_n[i] = p.wb.cnt->rkey_n[i / W_KEYS][i % W_KEYS];
+    __syncthreads();
+    if (threadIdx.x < R_CLASSES) wave_key_offsets(key_n + threadIdx.x * W_KEYS, key_off + threadIdx.x * W_KEYS);
+    __syncthreads();
     const int n_lc = (int)min(p.wb.cnt->n_lc, (unsigned)p.wb.lc_cap);
-    for (int k = (int)(blockIdx.x * blockDim.x + threadIdx.x); k < n_lc; k += (int)(gridDim.x * blockDim.x))
-        wave_lc_init(&p.sc, p.wp, p.wb, k);
+    const int lane = (int)(threadIdx.x & 31);
+    for (int k0 = (int)(blockIdx.x * blockDim.x + (threadIdx.x & ~31u)); k0 < n_lc; k0 += (int)(gridDim.x * blockDim.x)) {
+        const int k = k0 + lane;
+        const int id = k < n_lc ? wave_lc_init(&p.sc, p.wp, p.wb, k) : -1;
+        // the warp's resident lcs go into their key's block of the class's list: the lcs of one key as one run, in lc
+        // order (one atomic per warp and key)
+        __syncwarp();
+        const unsigned m = __match_any_sync(0xffffffffu, id);
+        if (id >= 0) {
+            const int leader = __ffs(m) - 1;
+            unsigned base = 0;
+            if (lane == leader) base = atomicAdd(&p.wb.cnt->rkey_cur[id / W_KEYS][id % W_KEYS], (unsigned)__popc(m));
+            base = __shfl_sync(m, base, leader);
+            const unsigned at = key_off[id] + base + (unsigned)__popc(m & ((1u << lane) - 1u));
+            if (at < (unsigned)p.wb.lc_cap) p.wb.rlist[(size_t)(id / W_KEYS) * p.wb.lc_cap + at] = k;
+        }
+    }
 }
 
 __global__ void __launch_bounds__(THREADS, VLR_PREP_MIN_CTAS) vlr_wave_coef_kernel(const __grid_constant__ WaveParams p) {
@@ -389,58 +409,67 @@ __global__ void __launch_bounds__(WAVE_ROUND_THREADS, VLR_ROUND_MIN_CTAS) vlr_wa
     }
 }
 
-// ---- the lc-resident round kernel (engine_resident.cuh) -------------------------------------------------------------
-// Persistent grid; a warp is four octets; an octet takes an lc by ticket, bulk-copies its pileup polynomials into its
-// shared-memory slot (cp.async.bulk, completion on the slot's mbarrier) and runs every round of the lc: (1) the lc's
-// tasks, H = 8 / #tasks lanes each — parent pileup, then the adaptive search of the leaf allele frequency to completion;
-// (2) the octet closes the round: trapezoids, MAP, the outer integration's next abscissae = the next round's tasks.
-// Only __syncwarp between the phases; an octet whose lc is complete takes the next one while its neighbours go on.
-constexpr int RES_THREADS = 64; // two warps = eight octets: 36 KB of shared memory, six CTAs per SM
-constexpr int RES_OCTETS = RES_THREADS / 8;
-constexpr size_t RES_SMEM = sizeof(vlr_small::ROct) * RES_OCTETS;
+// ---- the lc-resident round kernels (engine_resident.cuh) ------------------------------------------------------------
+// Persistent grid; a group of G lanes takes an lc by ticket, bulk-copies its pileup polynomials into its shared-memory
+// slot (cp.async.bulk, completion on the slot's mbarrier) and runs every round of the lc: (1) the lc's tasks,
+// H = G / #tasks lanes each — parent pileup, then the adaptive search of the leaf allele frequency to completion;
+// (2) the group closes the round: trapezoids, MAP, the outer integration's next abscissae = the next round's tasks.
+// Only __syncwarp between the phases; a group whose lc is complete takes the next one while its neighbours go on.
+// G = 8 (an octet per lc, four lcs per warp) serves lcs of size class 1 (both pileups in 48 polynomials = 240 reads);
+// G = 32 (a warp per lc) the deeper classes 2 and 3 (up to ~1000 and ~4100 reads: config 5's depth skew), where the
+// evaluation itself (reads / H polynomial blocks per lane) outweighs the bookkeeping.
+constexpr int RES_THREADS = 64; // two warps: eight octets (36 KB of shared memory, six CTAs per SM) or two warp groups
 #ifndef VLR_RES_MIN_CTAS
 #define VLR_RES_MIN_CTAS 6
 #endif
+constexpr size_t res_smem(int G, int slot_q) {
+    return (size_t)(RES_THREADS / G) * (sizeof(vlr_small::ROct) + (size_t)slot_q * vlr_small::R_QW * sizeof(double));
+}
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
-__global__ void __launch_bounds__(RES_THREADS, VLR_RES_MIN_CTAS) vlr_wave_resident_kernel(const __grid_constant__ WaveParams p) {
+template <int G>
+__device__ __forceinline__ void wave_resident_body(const WaveParams& p, const int cls, const int slot_q) {
     using namespace vlr_small;
     const WaveBufs& wb = p.wb;
-    ROct* octs = reinterpret_cast<ROct*>(vlr_smem);
-    const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5, oct = lane >> 3, l8 = lane & 7;
-    ROct& oc = octs[warp * 4 + oct];
-    const unsigned omask = 0xffu << (oct * 8);
+    constexpr int GROUPS = RES_THREADS / G; // per CTA
+    const size_t gstride = sizeof(ROct) + (size_t)slot_q * R_QW * sizeof(double);
+    const int tid = (int)threadIdx.x, lane = tid & 31, gi = tid / G, lg = tid % G;
+    ROct& oc = *reinterpret_cast<ROct*>(vlr_smem + (size_t)gi * gstride);
+    const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
     WGroup grp;
-    grp.lane = l8;
-    grp.n = 8;
-    grp.mask = omask;
-    const size_t og = (size_t)blockIdx.x * RES_OCTETS + (size_t)(warp * 4 + oct); // this octet's rows of the global scratch
+    grp.lane = lg;
+    grp.n = G;
+    grp.mask = gmask;
+    const size_t og = (size_t)blockIdx.x * GROUPS + (size_t)gi; // this group's rows of the global scratch
     double* const rows_x = wb.rgx + og * (W_MAXT * W_GCAP);
     double* const rows_m = wb.rgm + og * (W_MAXT * W_GCAP);
     int* const rows_e = wb.rge + og * (W_MAXT * W_GCAP);
     double* const big = wb.rscratch + og * (3 * W_GCAP);
-    const unsigned n_front = wb.cnt->rlist_n, n_list = n_front + wb.cnt->rlist_back_n;
+    const int* rlist = wb.rlist + (size_t)(cls - 1) * wb.lc_cap;
+    const unsigned n_list = min(wb.cnt->rlist_total[cls - 1], (unsigned)wb.lc_cap);
     const unsigned bar = smem_u32(&oc.bar);
-    if (l8 == 0) {
+    if (lg == 0) {
+        oc.q = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(&oc) + sizeof(ROct));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
     unsigned parity = 0;
-    bool have = false;
+    bool have = false, more = true; // more: the list may still hold an lc for this group
     int round = 0, cnt = 0;
     for (;;) {
-        if (!have) {
+        if (!have && more) {
             unsigned long long t = 0;
-            if (l8 == 0) t = atomicAdd(&wb.cnt->ticket[4], 1ULL);
-            t = __shfl_sync(omask, t, 0, 8);
-            if (t < (unsigned long long)n_list) {
-                const int lci = t < n_front ? wb.rlist[t] : wb.rlist[wb.lc_cap - 1 - (int)(t - n_front)];
+            if (lg == 0) t = atomicAdd(&wb.cnt->ticket[4 + cls - 1], 1ULL);
+            t = __shfl_sync(gmask, t, 0, G);
+            more = t < (unsigned long long)n_list;
+            const int lci = more ? rlist[t] : -1;
+            if (lci >= 0) { // (a negative entry: the list's bookkeeping left a hole; take the next ticket)
                 const WaveLC& L = wb.lcs[lci];
                 const int nq = L.nqPx + L.nqPy + L.nqTx + L.nqTy;
-                __syncwarp(omask); // nobody of the octet still reads the slot
-                if (l8 == 0) {
+                __syncwarp(gmask); // nobody of the group still reads the slot
+                if (lg == 0) {
                     oc.lc.lci = lci;
                     oc.lc.li = L.li;
                     oc.lc.ci = L.ci;
@@ -472,18 +501,20 @@ __global__ void __launch_bounds__(RES_THREADS, VLR_RES_MIN_CTAS) vlr_wave_reside
                 round = 0;
             }
         }
-        if (!__any_sync(0xffffffffu, have)) break;
+        if (!__any_sync(0xffffffffu, have || more)) break;
         __syncwarp();
-        if (have) {
-            // lanes per task: a function of the lc's task count alone (bitwise reproducible results)
-            const int H = cnt <= 1 ? 8 : (cnt <= 2 ? 4 : (cnt <= 4 ? 2 : 1));
-            const int q = l8 / H;
-            if (q < cnt) {
+        {
+            // lanes per task: a function of the lc's class and task count alone (bitwise reproducible results)
+            const int H = cnt <= 1 ? G : (cnt <= 2 ? G / 2 : (cnt <= 4 ? G / 4 : G / 8));
+            const int q = lg / H;
+            const bool runs = have && q < cnt;
+            const unsigned wmask = __ballot_sync(0xffffffffu, runs); // the warp's task lanes of this round
+            if (runs) {
                 WSplit sp;
                 sp.H = H;
-                sp.h = l8 & (H - 1);
-                sp.mask = ((1u << H) - 1u) << (lane & ~(H - 1));
-                r_task(&p.sc, p.wp, wb, oc, q, cnt, rows_x + (size_t)q * W_GCAP, rows_m + (size_t)q * W_GCAP, rows_e + (size_t)q * W_GCAP, sp);
+                sp.h = lg & (H - 1);
+                sp.mask = H == 32 ? 0xffffffffu : (((1u << H) - 1u) << (lane & ~(H - 1)));
+                r_task(&p.sc, p.wp, wb, oc, q, cnt, rows_x + (size_t)q * W_GCAP, rows_m + (size_t)q * W_GCAP, rows_e + (size_t)q * W_GCAP, sp, wmask);
             }
         }
         __syncwarp();
@@ -494,6 +525,14 @@ __global__ void __launch_bounds__(RES_THREADS, VLR_RES_MIN_CTAS) vlr_wave_reside
             round++;
         }
     }
+}
+
+__global__ void __launch_bounds__(RES_THREADS, VLR_RES_MIN_CTAS) vlr_wave_resident_kernel(const __grid_constant__ WaveParams p) {
+    wave_resident_body<8>(p, 1, vlr_small::R_SLOT_Q);
+}
+// size classes 2 and 3 (`cls`): a warp per lc, `slot_q` polynomials per slot
+__global__ void __launch_bounds__(RES_THREADS, 2) vlr_wave_resident_deep_kernel(const __grid_constant__ WaveParams p, int cls, int slot_q) {
+    wave_resident_body<32>(p, cls, slot_q);
 }
 
 __global__ void __launch_bounds__(THREADS, 2) vlr_wave_finish_kernel(const __grid_constant__ WaveParams p) {
@@ -696,6 +735,7 @@ struct vlr_ctx {
     bool wave = false;    // two-level chain scenario: the wavefront pipeline serves it (deferring loci it cannot)
     WavePlan wplan;
     int wave_grid_prep = 0, wave_grid_round = 0, wave_grid_finish = 0, wave_grid_res = 0;
+    int wave_grid_deep[2] = {0, 0}; // resident kernels of size classes 2 and 3 (a warp per lc)
     bool resident = true; // VLR_RESIDENT=0: per-round kernels only (A/B measurements)
     bool sets = false;    // all-Set scenario (pedigrees): the all-Set pipeline serves it (engine_sets.cuh)
     SetsPlan splan;
@@ -778,14 +818,18 @@ vlr_status_t launch_wave(vlr_ctx* ctx, Slot& sl, const DevBatch& b, const DevRes
     CK(sl.w_ogf.ensure(sizeof(double) * (size_t)lc_cap * W_OGRID));
     CK(sl.w_coef.ensure(sizeof(double) * (size_t)coef_cap));
     {
-        const size_t n_oct = (size_t)ctx->wave_grid_res * RES_OCTETS;
-        CK(sl.w_rlist.ensure(sizeof(int) * (size_t)lc_cap));
+        // (the deep kernels have two groups per CTA and fewer CTAs: they share the octet kernel's rows)
+        const size_t n_oct = (size_t)std::max(ctx->wave_grid_res * (RES_THREADS / 8),
+                                              std::max(ctx->wave_grid_deep[0], ctx->wave_grid_deep[1]) * (RES_THREADS / 32));
+        CK(sl.w_rlist.ensure(sizeof(int) * (size_t)lc_cap * R_CLASSES));
         CK(sl.w_rgx.ensure(sizeof(double) * n_oct * W_MAXT * W_GCAP));
         CK(sl.w_rgm.ensure(sizeof(double) * n_oct * W_MAXT * W_GCAP));
         CK(sl.w_rge.ensure(sizeof(int) * n_oct * W_MAXT * W_GCAP));
         CK(sl.w_rscratch.ensure(sizeof(double) * n_oct * 3 * W_GCAP));
-        CK(sl.w_cscratch.ensure(sizeof(double) * (size_t)ctx->wave_grid_prep * WARPS_PER_CTA * R_SCRATCH));
     }
+    // scratch of the coefficient kernel: as deep as the deepest locus the workspace was sized for (ensure_workspace)
+    const int cs_reads = std::min<int>(R_MAXREADS, std::max(sl.coef_cap, 256));
+    CK(sl.w_cscratch.ensure(sizeof(double) * (size_t)ctx->wave_grid_prep * WARPS_PER_CTA * 6 * (size_t)cs_reads));
     for (int i = 0; i < 2; ++i) {
         CK(sl.w_tasks[i].ensure(sizeof(WaveTask) * (size_t)lc_cap * W_MAXT));
         CK(sl.w_list[i].ensure(sizeof(int) * (size_t)lc_cap));
@@ -826,6 +870,8 @@ vlr_status_t launch_wave(vlr_ctx* ctx, Slot& sl, const DevBatch& b, const DevRes
     p.wb.rge = (int*)sl.w_rge.p;
     p.wb.rscratch = (double*)sl.w_rscratch.p;
     p.wb.cscratch = (double*)sl.w_cscratch.p;
+    p.wb.cscratch_reads = cs_reads;
+    const bool deep_classes = cs_reads > R_DEG * R_SLOT_Q; // loci deeper than an octet slot can occur
     p.wb.allow_resident = ctx->resident ? 1 : 0;
     p.ws = (WarpWs*)sl.ws.p;
     p.want_be = want_be ? 1 : 0;
@@ -851,10 +897,17 @@ vlr_status_t launch_wave(vlr_ctx* ctx, Slot& sl, const DevBatch& b, const DevRes
         p.sub_lo = lo;
         p.n_sub = (int)std::min<int64_t>(n_sub_cap, locus_end - lo);
         CK(cudaMemsetAsync(sl.w_cnt.p, 0, sizeof(WaveCounters), stream));
+        CK(cudaMemsetAsync(sl.w_rlist.p, 0xff, sizeof(int) * (size_t)lc_cap * R_CLASSES, stream)); // (holes read as -1)
         vlr_wave_pre_kernel<<<ctx->wave_grid_prep, THREADS, ctx->wave_smem_prep, stream>>>(p);
         vlr_wave_lcinit_kernel<<<ctx->n_sms * 4, 256, 0, stream>>>(p);
         vlr_wave_coef_kernel<<<ctx->wave_grid_prep, THREADS, ctx->wave_smem_prep, stream>>>(p);
-        if (ctx->resident) vlr_wave_resident_kernel<<<ctx->wave_grid_res, RES_THREADS, RES_SMEM, stream>>>(p);
+        if (ctx->resident) {
+            vlr_wave_resident_kernel<<<ctx->wave_grid_res, RES_THREADS, res_smem(8, R_SLOT_Q), stream>>>(p);
+            if (deep_classes) { // (pileups that deep exist in this batch)
+                vlr_wave_resident_deep_kernel<<<ctx->wave_grid_deep[0], RES_THREADS, res_smem(32, R_SLOT_QM), stream>>>(p, 2, R_SLOT_QM);
+                vlr_wave_resident_deep_kernel<<<ctx->wave_grid_deep[1], RES_THREADS, res_smem(32, R_SLOT_QL), stream>>>(p, 3, R_SLOT_QL);
+            }
+        }
         for (int round = 0; round < ctx->wplan.max_rounds; ++round) {
             vlr_wave_round_warp_kernel<<<ctx->wave_grid_round, WAVE_ROUND_THREADS, WAVE_ROUND_SMEM, stream>>>(p, round);
             vlr_wave_round_kernel<<<ctx->wave_grid_round, WAVE_ROUND_THREADS, WAVE_ROUND_SMEM, stream>>>(p, round);
@@ -862,7 +915,7 @@ vlr_status_t launch_wave(vlr_ctx* ctx, Slot& sl, const DevBatch& b, const DevRes
         vlr_wave_finish_kernel<<<ctx->wave_grid_finish, THREADS, ctx->wave_smem_prep, stream>>>(p);
         vlr_call_kernel_vlr_small<<<ctx->grid, THREADS, ctx->smem_bytes, stream>>>(gp);
         CK(cudaGetLastError());
-        ctx->launches += 5 + (ctx->resident ? 1 : 0) + 2 * ctx->wplan.max_rounds;
+        ctx->launches += 5 + (ctx->resident ? (deep_classes ? 3 : 1) : 0) + 2 * ctx->wplan.max_rounds;
     }
     return VLR_OK;
 }
@@ -1286,10 +1339,17 @@ vlr_status_t vlr_ctx_create(const vlr_scenario_t* scenario, int32_t device, vlr_
         ctx->wave_grid_finish = std::min(std::max(1, n3) * ctx->n_sms, ctx->grid);
         const char* res_env = getenv("VLR_RESIDENT");
         ctx->resident = !(res_env && res_env[0] == '0');
-        CKB(cudaFuncSetAttribute(vlr_wave_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RES_SMEM));
+        CKB(cudaFuncSetAttribute(vlr_wave_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)res_smem(8, vlr_small::R_SLOT_Q)));
         int n4 = 0;
-        CKB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n4, vlr_wave_resident_kernel, RES_THREADS, RES_SMEM));
+        CKB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n4, vlr_wave_resident_kernel, RES_THREADS, res_smem(8, vlr_small::R_SLOT_Q)));
         ctx->wave_grid_res = std::max(1, n4) * ctx->n_sms;
+        CKB(cudaFuncSetAttribute(vlr_wave_resident_deep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)res_smem(32, vlr_small::R_SLOT_QL)));
+        const int slots[2] = {vlr_small::R_SLOT_QM, vlr_small::R_SLOT_QL};
+        for (int k = 0; k < 2; ++k) {
+            int n5 = 0;
+            CKB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n5, vlr_wave_resident_deep_kernel, RES_THREADS, res_smem(32, slots[k])));
+            ctx->wave_grid_deep[k] = std::max(1, n5) * ctx->n_sms;
+        }
     }
     {
         const char* sets_env = getenv("VLR_SETS"); // VLR_SETS=0: generic engine only (A/B measurements, tests)
