@@ -406,18 +406,22 @@ def run_workload(args, D, cfg, loci, steps, warmup, strong, oracle_legs, n_oracl
         except (OSError, KeyError, ValueError):
             pass
         if cfg == 5 and wave:
-            kernel_name = ("wavefront pipeline: vlr_wave_resident_kernel for the lcs whose pileups fit a shared-memory slot, "
-                           "vlr_wave_round_kernel (CTA per group, per round) for deeper ones")
-        # the bound that matters: fp64. Executed-algorithm flops = joint evaluations x reads of the
-        # integrated pileup x flops per read and abscissa; peak = DFMA microbenchmark on this device.
+            kernel_name = ("wavefront pipeline: vlr_wave_resident_kernel (an octet per lc: both pileups in 240 reads) and "
+                           "vlr_wave_resident_deep_kernel (a warp per lc: slots of ~1000 and ~4100 reads)")
+        # the bound that matters: fp64. ALGORITHMIC flops = joint evaluations x reads of the integrated
+        # pileup x 5 flops per read and abscissa (the model's per-read emission alpha x + beta y + gamma folded into the
+        # pileup product: 2 FMA + 1 MUL; DESIGN §4.3 — the same per-unit figure since round 1); peak = DFMA
+        # microbenchmark on this device. The wavefront pipeline EXECUTES fewer: its pileup polynomials fold five reads
+        # into 5 FMA + 1 MUL (2.2 flops per read), reported beside it.
         reads_leaf = batch.n_reads / max(1, batch.n_loci) / S
-        per_read = FLOPS_POLY if wave else FLOPS_READ
-        flops = joint_evals * batch.n_loci * reads_leaf * per_read
+        flops = joint_evals * batch.n_loci * reads_leaf * FLOPS_READ
+        flops_exec = joint_evals * batch.n_loci * reads_leaf * (FLOPS_POLY if wave else FLOPS_READ)
         try:
             fp64_peak = engine.measure_fp64_peak(local_rank)
         except Exception:  # noqa: BLE001
             fp64_peak = None
         fp64_achieved = flops / (kernel_ms * 1e-3) / 1e12
+        fp64_exec = flops_exec / (kernel_ms * 1e-3) / 1e12
         hbm_achieved = abytes / (kernel_ms * 1e-3) / 1e9
         roofline = {
             "bound": "fp64" if wave else "hbm", "kernel": kernel_name, "kernel_ms": kernel_ms,
@@ -427,12 +431,13 @@ def run_workload(args, D, cfg, loci, steps, warmup, strong, oracle_legs, n_oracl
             "traffic": traffic, "traffic_source": traffic_src,
             "fp64": {"achieved": fp64_achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": (fp64_achieved / fp64_peak) if fp64_peak else None, "flops_per_step": flops,
+                     "executed": {"achieved": fp64_exec, "frac": (fp64_exec / fp64_peak) if fp64_peak else None,
+                                  "flops_per_read_and_abscissa": FLOPS_POLY if wave else FLOPS_READ},
                      "peak_source": "vlr_measure_fp64_peak (DFMA microbenchmark, this device)",
-                     "accounting": "joint evaluations (%.0f per locus) x reads of the integrated pileup (%.0f) x %.1f flops "
-                                   "(%s)" % (joint_evals, reads_leaf, per_read,
-                                             "pileup polynomials: 5 FMA + 1 MUL per five reads and abscissa; the per-read "
-                                             "form of round 1 counted 5 flops for the same evaluation" if wave else
-                                             "2 FMA + 1 MUL per read and abscissa")},
+                     "accounting": "algorithmic: joint evaluations (%.0f per locus) x reads of the integrated pileup (%.0f) "
+                                   "x %.1f flops (2 FMA + 1 MUL per read and abscissa)%s" % (
+                                       joint_evals, reads_leaf, FLOPS_READ,
+                                       "; executed: pileup polynomials, 5 FMA + 1 MUL per five reads" if wave else "")},
             "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
                     "algorithmic_bytes_per_launch": int(abytes), "peak_source": hbm_src},
             "note": "kernel_ms = all kernels of one vlr_call_batch_device step of rank 0 (CUDA events on the launch "

@@ -4,7 +4,7 @@
 // atomic ticket so that the very uneven per-locus work (a few hundred to >100k per-read evaluations)
 // balances dynamically. All per-locus logic lives in engine_core.cuh.
 //
-// Host: vlr_call_batch() streams a host batch through NBUF slots (chunk of loci -> H2D -> kernel -> D2H, one CUDA
+// Host: vlr_call_batch() streams a host batch through 8 slots (chunk of loci -> H2D -> kernel -> D2H, one CUDA
 // stream per slot) so copies overlap compute; vlr_call_batch_device() launches on device-resident buffers.
 // There is no CPU fallback: without a usable CUDA device vlr_ctx_create() fails with VLR_ERR_NO_DEVICE.
 #include <cuda_fp16.h>
@@ -42,7 +42,7 @@ using namespace vlrcore;
 namespace {
 
 constexpr int THREADS = WARPS_PER_CTA * LANES; // WARPS_PER_CTA counts logical warps (engine_types.cuh)
-constexpr int NBUF = 3;
+constexpr int NBUF_MAX = 8; // chunk slots of vlr_call_batch (vlr_ctx::nbuf of them are used)
 
 struct KernelParams {
     DevScenario sc;
@@ -757,7 +757,10 @@ struct vlr_ctx {
     cudaEvent_t ev_done = nullptr; // end of the previous device-entry call: calls share one workspace, so a call on
     bool have_done = false;        // another stream waits for it (an event chain instead of a rule for the caller)
     int n_aux = 3; // measured on 512k config-2 loci: 1 stream 4.05, 2: 4.43, 3: 4.48, 4: 4.51 M loci/s
-    Slot slots[NBUF];
+    Slot slots[NBUF_MAX];
+    int nbuf = 8; // chunks in flight (VLR_NBUF). Measured (1M config-2 / config-3 loci, packed columns): 3: 6.10 / 9.0,
+                  // 6: 6.38 / 10.9, 8: 6.53 / 11.3 M loci/s — with 3 the streams ran in phase and the SMs idled during every
+                  // wave of copies
     int64_t reserve_reads = 4096;
     int64_t launches = 0;
     std::string err;
@@ -1393,7 +1396,11 @@ vlr_status_t vlr_ctx_create(const vlr_scenario_t* scenario, int32_t device, vlr_
     }
     CKB(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     CKB(cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming));
-    for (int i = 0; i < NBUF; ++i) CKB(cudaStreamCreateWithFlags(&ctx->slots[i].stream, cudaStreamNonBlocking));
+    if (const char* e = getenv("VLR_NBUF")) {
+        const int v = atoi(e);
+        if (v >= 1 && v <= NBUF_MAX) ctx->nbuf = v;
+    }
+    for (int i = 0; i < NBUF_MAX; ++i) CKB(cudaStreamCreateWithFlags(&ctx->slots[i].stream, cudaStreamNonBlocking));
 #undef CKB
     *out = ctx;
     return VLR_OK;
@@ -1520,14 +1527,31 @@ static vlr_status_t call_batch_host(vlr_ctx_t* ctx, const vlr_packed_batch_t* ba
     ctx->launches = 0;
     int64_t unpack_launches = 0;
     const int S = ctx->S, E = ctx->E;
+    const int nbuf = ctx->nbuf;
     const int64_t L = batch->n_loci;
     if (L == 0) return VLR_OK;
     const int64_t* off = batch->read_offsets;
     if (off[L * S] != batch->n_reads) return ctx->fail(VLR_ERR_INVALID_ARGUMENT, "read_offsets[n_loci*S] != n_reads");
     // chunking: a chunk must hold many more loci than the 2368 resident warps (dynamic load balance inside the kernel)
     // and tens of MB of columns (PCIe efficiency); 3 slots of <= 16M reads (512 MB) stay far below the HBM size
-    const int64_t target_reads = 16 << 20;
-    const int64_t max_loci_chunk = 1 << 16;
+    int64_t target_reads = 16 << 20;
+    int64_t max_loci_chunk = 1 << 16;
+    if (const char* e = getenv("VLR_CHUNK_LOCI")) { // tuning knob (measurements): loci and reads per chunk scale together
+        const long v = atol(e);
+        if (v >= 1024 && v <= (1 << 22)) {
+            max_loci_chunk = v;
+            target_reads = std::max<int64_t>(target_reads, v * 256);
+        }
+    }
+    {
+        // equal chunks, a multiple of the nbuf streams of them: the streams finish together (a greedy cut leaves the last
+        // chunks alone on the device)
+        int64_t n_chunks = std::max((L + max_loci_chunk - 1) / max_loci_chunk, (batch->n_reads + target_reads - 1) / target_reads);
+        if (n_chunks > 1) n_chunks = (n_chunks + nbuf - 1) / nbuf * nbuf;
+        n_chunks = std::max<int64_t>(n_chunks, 1);
+        max_loci_chunk = std::min(max_loci_chunk, (L + n_chunks - 1) / n_chunks);
+        target_reads = std::min(target_reads, batch->n_reads / n_chunks + batch->n_reads / (n_chunks * 64) + 1);
+    }
     const int cap = results->afd_capacity;
     static const size_t enc_bytes[5] = {4, 2, 2, 1, 0}; // VLR_ENC_*: bytes per read on the link
     bool any_packed = false;
@@ -1535,6 +1559,15 @@ static vlr_status_t call_batch_host(vlr_ctx_t* ctx, const vlr_packed_batch_t* ba
     int64_t lo = 0;
     int k = 0;
     vlr_status_t st = VLR_OK;
+    const bool timing = getenv("VLR_CHUNK_TIMING") != nullptr; // measurements: per-chunk timeline on stderr
+    std::vector<cudaEvent_t> tev;
+    auto mark = [&](cudaStream_t s) {
+        if (!timing) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, s);
+        tev.push_back(e);
+    };
     while (lo < L) {
         int64_t hi = lo, max_reads = 0;
         const int64_t r0 = off[lo * S];
@@ -1546,12 +1579,14 @@ static vlr_status_t call_batch_host(vlr_ctx_t* ctx, const vlr_packed_batch_t* ba
             ++hi;
         }
         const int64_t r1 = off[hi * S], nl = hi - lo, nr = r1 - r0;
-        Slot& sl = ctx->slots[k % NBUF];
+        Slot& sl = ctx->slots[k % nbuf];
         cudaStream_t s = sl.stream;
-        // the slot's previous chunk (k - NBUF) must have drained before its buffers are reused
-        CK(cudaStreamSynchronize(s));
+        // the slot's buffers are reused in stream order (copies and kernels of chunk k - nbuf precede this chunk's on the
+        // same stream), so the host does not wait for that chunk: it queues the whole batch and every stream always
+        // has its next chunk behind the running one. A buffer that has to grow is freed first, which synchronises.
         st = ensure_workspace(ctx, sl, max_reads, cap > 0);
         if (st != VLR_OK) break;
+        mark(s);
         CK(sl.offsets.ensure(sizeof(int64_t) * (size_t)(nl * S + 1)));
         CK(cudaMemcpyAsync(sl.offsets.p, off + lo * S, sizeof(int64_t) * (size_t)(nl * S + 1), cudaMemcpyHostToDevice, s));
         // columns: plain ones go straight into place, encoded ones into the slot's staging buffers (with their
@@ -1578,7 +1613,7 @@ static vlr_status_t call_batch_host(vlr_ctx_t* ctx, const vlr_packed_batch_t* ba
                 up.src[c] = sl.pk[c].p;
             }
             if (col.n_dict > 0) {
-                if (k < NBUF) {
+                if (k < nbuf) {
                     CK(sl.pk_dict[c].ensure(sizeof(uint32_t) * (size_t)col.n_dict));
                     CK(cudaMemcpyAsync(sl.pk_dict[c].p, col.dict, sizeof(uint32_t) * (size_t)col.n_dict, cudaMemcpyHostToDevice, s));
                 }
@@ -1645,8 +1680,10 @@ static vlr_status_t call_batch_host(vlr_ctx_t* ctx, const vlr_packed_batch_t* ba
         r.afd_count = (int32_t*)sl.afd_count.p;
         r.afd_vaf = (double*)sl.afd_vaf.p;
         r.afd_logp = (double*)sl.afd_logp.p;
+        mark(s);
         st = launch(ctx, sl, b, r, s, nl > 0 ? (nr + nl - 1) / nl : 0);
         if (st != VLR_OK) break;
+        mark(s);
         // D2H
         CK(cudaMemcpyAsync(results->log_posteriors + lo * (E + 1), r.log_post, sizeof(double) * (size_t)(nl * (E + 1)), cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(results->map_vaf + lo * S, r.map_vaf, sizeof(double) * (size_t)(nl * S), cudaMemcpyDeviceToHost, s));
@@ -1660,13 +1697,22 @@ static vlr_status_t call_batch_host(vlr_ctx_t* ctx, const vlr_packed_batch_t* ba
             CK(cudaMemcpyAsync(results->afd_vaf + lo * S * cap, r.afd_vaf, sizeof(double) * (size_t)(nl * S * cap), cudaMemcpyDeviceToHost, s));
             CK(cudaMemcpyAsync(results->afd_logp + lo * S * cap, r.afd_logp, sizeof(double) * (size_t)(nl * S * cap), cudaMemcpyDeviceToHost, s));
         }
+        mark(s);
         lo = hi;
         ++k;
     }
     ctx->launches += unpack_launches;
-    for (int i = 0; i < NBUF; ++i) {
+    for (int i = 0; i < nbuf; ++i) {
         cudaError_t e = cudaStreamSynchronize(ctx->slots[i].stream);
         if (e != cudaSuccess && st == VLR_OK) st = ctx->fail_cuda(e, "cudaStreamSynchronize", __LINE__);
+    }
+    if (timing && !tev.empty()) {
+        for (size_t c = 0; c + 3 < tev.size(); c += 4) {
+            float t[4];
+            for (int j = 0; j < 4; ++j) cudaEventElapsedTime(&t[j], tev[0], tev[c + j]);
+            fprintf(stderr, "chunk %2zu stream %zu: h2d %7.2f .. %7.2f  kernels .. %7.2f  d2h .. %7.2f ms\n", c / 4, (c / 4) % (size_t)nbuf, t[0], t[1], t[2], t[3]);
+        }
+        for (cudaEvent_t e : tev) cudaEventDestroy(e);
     }
     return st;
 }
