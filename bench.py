@@ -396,18 +396,15 @@ def run_workload(args, D, cfg, loci, steps, warmup, strong, oracle_legs, n_oracl
         traffic, traffic_src = None, None
         kernel_name = "vlr_call_kernel_vlr_small (warp per locus)"
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r2_wave.json" if wave else
+            tr = json.load(open(os.path.join(ROOT, "profiles", ("traffic_r2_cfg5.json" if cfg == 5 else "traffic_r2_wave.json") if wave else
                                              ("traffic_r2_cfg3.json" if sets else "traffic_r1.json"))))
-            if cfg in (2, 3, 4):
+            if cfg in (2, 3, 4, 5):
                 traffic = int(tr["dram_bytes_per_locus"] * batch.n_loci)
                 traffic_src = "static: %s (ncu dram__bytes of one sub-chunk of this workload, scaled by loci)" % tr.get("source", "profiles/")
             if wave or sets:
                 kernel_name = tr["kernels"]
         except (OSError, KeyError, ValueError):
             pass
-        if cfg == 5 and wave:
-            kernel_name = ("wavefront pipeline: vlr_wave_resident_kernel (an octet per lc: both pileups in 240 reads) and "
-                           "vlr_wave_resident_deep_kernel (a warp per lc: slots of ~1000 and ~4100 reads)")
         # the bound that matters: fp64. ALGORITHMIC flops = joint evaluations x reads of the integrated
         # pileup x 5 flops per read and abscissa (the model's per-read emission alpha x + beta y + gamma folded into the
         # pileup product: 2 FMA + 1 MUL; DESIGN §4.3 — the same per-unit figure since round 1); peak = DFMA
