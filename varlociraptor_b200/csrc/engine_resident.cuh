@@ -24,9 +24,10 @@
 constexpr int R_DEG = 5;          // reads per polynomial
 constexpr int R_QW = R_DEG + 1;   // coefficients (doubles) per polynomial: 48 bytes = 3 x 16
 constexpr int R_SLOT_Q = 48;      // polynomials per octet slot (parent and leaf pileup of one lc): 2304 bytes
-constexpr int R_SLOT_QM = 208;    // ... of a warp's slot, medium class (~1000 reads): 9984 bytes
-constexpr int R_SLOT_QL = 832;    // ... of a warp's slot, large class (~4100 reads): 39936 bytes
-constexpr int R_CLASSES = 3;      // 1: an octet per lc; 2, 3: a warp per lc (deep pileups, depth skew)
+constexpr int R_SLOT_QM = 208;    // ... of a warp's slot, class 2 (~1000 reads): 9984 bytes
+constexpr int R_SLOT_QD = 416;    // ... class 3 (~2000 reads): 19968 bytes
+constexpr int R_SLOT_QL = 832;    // ... class 4 (~4100 reads): 39936 bytes
+constexpr int R_CLASSES = W_RCLASSES; // 1: an octet per lc; 2..4: a warp per lc (deep pileups, depth skew)
 constexpr int R_POOL_N = 400;     // sorted-list nodes per lc, shared by the tasks of a round: one 32-bit word each,
                                   // (24-bit key << 8) | next node (a task visits ~60 points at resolution 0.01)
 constexpr int R_POOL_D = R_POOL_N / 2; // ... as doubles: 1600 bytes
@@ -38,12 +39,12 @@ constexpr int R_MAXREADS = R_DEG * R_SLOT_QL; // no resident lc has more kept re
 // resident lc the workspace allows (WaveBufs::cscratch_reads <= R_MAXREADS)
 // upper bound of the polynomials of a pileup of n reads (two groups, each rounded up)
 VLR_DEV int r_qcap(int n) { return n / R_DEG + 2; }
-VLR_DEV int r_slot_q(int cls) { return cls == 1 ? R_SLOT_Q : (cls == 2 ? R_SLOT_QM : R_SLOT_QL); }
+VLR_DEV int r_slot_q(int cls) { return cls == 1 ? R_SLOT_Q : (cls == 2 ? R_SLOT_QM : (cls == 3 ? R_SLOT_QD : R_SLOT_QL)); }
 // size class of an lc whose pileups hold nP and nT kept reads (0: not resident, the per-round kernels serve it)
 VLR_DEV int r_class(int nP, int nT, int scratch_reads) {
     if (nP + nT > scratch_reads) return 0;
     const int q = r_qcap(nP) + r_qcap(nT);
-    return q <= R_SLOT_Q ? 1 : (q <= R_SLOT_QM ? 2 : (q <= R_SLOT_QL ? 3 : 0));
+    return q <= R_SLOT_Q ? 1 : (q <= R_SLOT_QM ? 2 : (q <= R_SLOT_QD ? 3 : (q <= R_SLOT_QL ? 4 : 0)));
 }
 
 struct MV { // value = m * 2^e with m in [1, 2), or exactly zero (m = 0, e = R_ZERO_E); a NaN m is a NaN value

@@ -51,6 +51,8 @@ VLR_DEV unsigned wa_add_u32(unsigned* p, unsigned v) { return atomicAdd(p, v); }
 VLR_DEV unsigned long long wa_add_u64(unsigned long long* p, unsigned long long v) { return atomicAdd(p, v); }
 #endif
 
+constexpr int W_RCLASSES = 4; // size classes of the lc-resident round kernels (engine_resident.cuh: r_class)
+
 struct WaveCounters {
     unsigned long long ticket[8]; // pre, finish, deferred (generic kernel), coefficients, resident rounds (4 + class - 1)
     unsigned long long coef_used; // doubles allocated in the coefficient arena
@@ -63,8 +65,8 @@ struct WaveCounters {
     // as good as sorting by the number of joint evaluations known afterwards (scripts/exp_sorted.py).
     // One list per size class (engine_resident.cuh: r_class), laid out by KEY: the pre-pass counts the lcs of every key
     // (rkey_n), the lc-init kernel places them behind the exclusive prefix sums through the cursors (rkey_cur).
-    unsigned int rlist_total[3];
-    unsigned int rkey_n[3][128], rkey_cur[3][128];
+    unsigned int rlist_total[W_RCLASSES];
+    unsigned int rkey_n[W_RCLASSES][128], rkey_cur[W_RCLASSES][128];
     unsigned int list_n[W_MAXROUNDS + 2];  // lcs of the round whose pileups fit a coefficient slot
     unsigned int dlist_n[W_MAXROUNDS + 2]; // lcs of the round with a deeper pileup
     unsigned int task_n[W_MAXROUNDS + 2];
@@ -76,7 +78,7 @@ struct WaveLocus {
     uint32_t status;
     // what the per-lc kernels need from the pre-pass
     uint32_t lf;
-    int resident;   // size class (r_class, 1..3) when the locus' lcs are served by the lc-resident round kernel
+    int resident;   // size class (r_class, 1..4) when the locus' lcs are served by the lc-resident round kernel
                     // (polynomial arena format), else 0
     int cost_bin;   // 8 * bin(leaf pileup) + bin(parent pileup) of the shares of reads not favouring the reference
     int lc_doubles; // arena doubles per lc
@@ -95,7 +97,7 @@ struct WaveLC { // one (locus, artifact config)
     int ci, art_id;
     int nP, nT;
     int m0P, m0T; // every kept read of the sample has prob_sample_alt == 0
-    int resident;               // size class (1..3): the arena holds pileup polynomials (engine_resident.cuh), else 0: per-read coefficients
+    int resident;               // size class (1..4): the arena holds pileup polynomials (engine_resident.cuh), else 0: per-read coefficients
     int nqPx, nqPy, nqTx, nqTy; // ... this many per group, parent pileup at coefP, leaf pileup right behind it
     int task_base, task_count;
     uint32_t status, n_base;

@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(WAVE_ROUND_THREADS, VLR_ROUND_MIN_CTAS) vlr_wa
 // (2) the group closes the round: trapezoids, MAP, the outer integration's next abscissae = the next round's tasks.
 // Only __syncwarp between the phases; a group whose lc is complete takes the next one while its neighbours go on.
 // G = 8 (an octet per lc, four lcs per warp) serves lcs of size class 1 (both pileups in 48 polynomials = 240 reads);
-// G = 32 (a warp per lc) the deeper classes 2 and 3 (up to ~1000 and ~4100 reads: config 5's depth skew), where the
+// G = 32 (a warp per lc) the deeper classes 2..4 (up to ~1000, ~2000 and ~4100 reads: config 5's depth skew), where the
 // evaluation itself (reads / H polynomial blocks per lane) outweighs the bookkeeping.
 constexpr int RES_THREADS = 64; // two warps: eight octets (36 KB of shared memory, six CTAs per SM) or two warp groups
 #ifndef VLR_RES_MIN_CTAS
@@ -530,7 +530,7 @@ __device__ __forceinline__ void wave_resident_body(const WaveParams& p, const in
 __global__ void __launch_bounds__(RES_THREADS, VLR_RES_MIN_CTAS) vlr_wave_resident_kernel(const __grid_constant__ WaveParams p) {
     wave_resident_body<8>(p, 1, vlr_small::R_SLOT_Q);
 }
-// size classes 2 and 3 (`cls`): a warp per lc, `slot_q` polynomials per slot
+// size classes 2..4 (`cls`): a warp per lc, `slot_q` polynomials per slot
 __global__ void __launch_bounds__(RES_THREADS, 2) vlr_wave_resident_deep_kernel(const __grid_constant__ WaveParams p, int cls, int slot_q) {
     wave_resident_body<32>(p, cls, slot_q);
 }
@@ -735,7 +735,7 @@ struct vlr_ctx {
     bool wave = false;    // two-level chain scenario: the wavefront pipeline serves it (deferring loci it cannot)
     WavePlan wplan;
     int wave_grid_prep = 0, wave_grid_round = 0, wave_grid_finish = 0, wave_grid_res = 0;
-    int wave_grid_deep[2] = {0, 0}; // resident kernels of size classes 2 and 3 (a warp per lc)
+    int wave_grid_deep[3] = {0, 0, 0}; // resident kernels of size classes 2..4 (a warp per lc)
     bool resident = true; // VLR_RESIDENT=0: per-round kernels only (A/B measurements)
     bool sets = false;    // all-Set scenario (pedigrees): the all-Set pipeline serves it (engine_sets.cuh)
     SetsPlan splan;
@@ -823,7 +823,7 @@ vlr_status_t launch_wave(vlr_ctx* ctx, Slot& sl, const DevBatch& b, const DevRes
     {
         // (the deep kernels have two groups per CTA and fewer CTAs: they share the octet kernel's rows)
         const size_t n_oct = (size_t)std::max(ctx->wave_grid_res * (RES_THREADS / 8),
-                                              std::max(ctx->wave_grid_deep[0], ctx->wave_grid_deep[1]) * (RES_THREADS / 32));
+                                              std::max(ctx->wave_grid_deep[0], std::max(ctx->wave_grid_deep[1], ctx->wave_grid_deep[2])) * (RES_THREADS / 32));
         CK(sl.w_rlist.ensure(sizeof(int) * (size_t)lc_cap * R_CLASSES));
         CK(sl.w_rgx.ensure(sizeof(double) * n_oct * W_MAXT * W_GCAP));
         CK(sl.w_rgm.ensure(sizeof(double) * n_oct * W_MAXT * W_GCAP));
@@ -907,8 +907,9 @@ vlr_status_t launch_wave(vlr_ctx* ctx, Slot& sl, const DevBatch& b, const DevRes
         if (ctx->resident) {
             vlr_wave_resident_kernel<<<ctx->wave_grid_res, RES_THREADS, res_smem(8, R_SLOT_Q), stream>>>(p);
             if (deep_classes) { // (pileups that deep exist in this batch)
-                vlr_wave_resident_deep_kernel<<<ctx->wave_grid_deep[0], RES_THREADS, res_smem(32, R_SLOT_QM), stream>>>(p, 2, R_SLOT_QM);
-                vlr_wave_resident_deep_kernel<<<ctx->wave_grid_deep[1], RES_THREADS, res_smem(32, R_SLOT_QL), stream>>>(p, 3, R_SLOT_QL);
+                const int slot_q[3] = {R_SLOT_QM, R_SLOT_QD, R_SLOT_QL};
+                for (int cls = 2; cls <= R_CLASSES; ++cls)
+                    vlr_wave_resident_deep_kernel<<<ctx->wave_grid_deep[cls - 2], RES_THREADS, res_smem(32, slot_q[cls - 2]), stream>>>(p, cls, slot_q[cls - 2]);
             }
         }
         for (int round = 0; round < ctx->wplan.max_rounds; ++round) {
@@ -918,7 +919,7 @@ vlr_status_t launch_wave(vlr_ctx* ctx, Slot& sl, const DevBatch& b, const DevRes
         vlr_wave_finish_kernel<<<ctx->wave_grid_finish, THREADS, ctx->wave_smem_prep, stream>>>(p);
         vlr_call_kernel_vlr_small<<<ctx->grid, THREADS, ctx->smem_bytes, stream>>>(gp);
         CK(cudaGetLastError());
-        ctx->launches += 5 + (ctx->resident ? (deep_classes ? 3 : 1) : 0) + 2 * ctx->wplan.max_rounds;
+        ctx->launches += 5 + (ctx->resident ? (deep_classes ? R_CLASSES : 1) : 0) + 2 * ctx->wplan.max_rounds;
     }
     return VLR_OK;
 }
@@ -1347,8 +1348,8 @@ vlr_status_t vlr_ctx_create(const vlr_scenario_t* scenario, int32_t device, vlr_
         CKB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n4, vlr_wave_resident_kernel, RES_THREADS, res_smem(8, vlr_small::R_SLOT_Q)));
         ctx->wave_grid_res = std::max(1, n4) * ctx->n_sms;
         CKB(cudaFuncSetAttribute(vlr_wave_resident_deep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)res_smem(32, vlr_small::R_SLOT_QL)));
-        const int slots[2] = {vlr_small::R_SLOT_QM, vlr_small::R_SLOT_QL};
-        for (int k = 0; k < 2; ++k) {
+        const int slots[3] = {vlr_small::R_SLOT_QM, vlr_small::R_SLOT_QD, vlr_small::R_SLOT_QL};
+        for (int k = 0; k < 3; ++k) {
             int n5 = 0;
             CKB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n5, vlr_wave_resident_deep_kernel, RES_THREADS, res_smem(32, slots[k])));
             ctx->wave_grid_deep[k] = std::max(1, n5) * ctx->n_sms;
