@@ -338,6 +338,20 @@ vlr_status_t vlr_contamination_posterior(int32_t device, const vlr_contamination
 vlr_status_t vlr_contamination_posterior_device(int32_t device, const vlr_contamination_input_t* in,
                                                 vlr_contamination_output_t* out, void* cuda_stream);
 
+/* VariantObservation::new (contamination.rs:44-82) for a whole batch of calls without leaving the device: `results`
+ * holds DEVICE pointers as written by vlr_call_batch_device() with afd_capacity > 0 for `n_loci` calls of a context with
+ * `n_samples` samples and `n_events` events. Keeps the calls that have a MAP estimate outside the artifact events and
+ * exp(ln P(`denovo_event`)) >= `min_prob` (reference: 0.95), and packs {ln P(denovo), MAP allele frequency of `sample`,
+ * its allele frequency distribution} into the CSR columns vlr_contamination_posterior_device() reads. All output
+ * pointers are DEVICE buffers of the caller: prob_denovo, max_posterior_vaf, kept_loci (optional, the call index of
+ * every observation) [n_loci], afd_offsets [n_loci + 1], afd_vaf / afd_logp [n_loci * afd_capacity]. `n_obs` is a HOST
+ * pointer: the call waits on `cuda_stream` for this one number (the posterior's launch geometry depends on it). */
+vlr_status_t vlr_contamination_gather_device(int32_t device, const vlr_results_t* results, int64_t n_loci,
+                                             int32_t n_samples, int32_t n_events, int32_t sample, int32_t denovo_event,
+                                             double min_prob, double* prob_denovo, double* max_posterior_vaf,
+                                             int64_t* afd_offsets, double* afd_vaf, double* afd_logp, int64_t* kept_loci,
+                                             int64_t* n_obs, void* cuda_stream);
+
 /* Number of kernels the last vlr_call_batch* launched (for bench accounting). */
 int64_t vlr_last_launch_count(const vlr_ctx_t* ctx);
 /* The context's stream (cudaStream_t) so callers can time with CUDA events. */

@@ -321,3 +321,57 @@ def test_random_small_inputs_agree_everywhere():
             fin = np.isfinite(a)
             assert not fin.any() or np.max(np.abs(a[fin] - b[fin])) <= 1e-9, case
         assert np.array_equal(np.isnan(lik), np.isnan(got.ln_likelihood)), case
+
+
+@pytest.mark.gpu
+def test_device_resident_observations_match_the_call_processor():
+    """`estimate contamination` without the calls leaving the device (contamination.rs:44-82 + :163-240 on the GPU):
+    vlr_call_batch_device -> vlr_contamination_gather_device -> vlr_contamination_posterior_device. The selection, the
+    packed AFDs and the posterior are exactly what the CallProcessor route (host results -> VariantObservation::new per
+    call -> vlr_contamination_posterior) produces."""
+    import torch
+    from varlociraptor_b200 import Scenario, engine
+    sc = Scenario.from_yaml(ct.CONTAMINATION_SCENARIO)
+    flat = sc.flatten()
+    names = list(flat.sample_names)
+    s_idx, e_denovo = names.index("sample"), flat.event_names.index("denovo")
+    _, b = synth.tumor_normal(700, seed=31, depth=24)  # normal = 0, tumor = 1
+    if names.index("contaminant") != 0:  # the batch's sample order follows the scenario's
+        off = b.read_offsets
+        idx = np.concatenate([np.arange(off[2 * i + 1 - s], off[2 * i + 2 - s]) for i in range(b.n_loci) for s in (0, 1)])
+        lens = np.array([off[2 * i + 2 - s] - off[2 * i + 1 - s] for i in range(b.n_loci) for s in (0, 1)])
+        b = LocusBatch(2, np.concatenate([[0], np.cumsum(lens)]), {k: v[idx] for k, v in b.columns.items()}, b.read_flags[idx],
+                       b.locus_flags)
+    cap = 256
+    eng = engine.PosteriorEngine(flat)
+    host = eng.call_batch(b, afd_capacity=cap)
+    obs, kept = [], []
+    for i in range(b.n_loci):
+        lp = float(host.log_posteriors[i, e_denovo])
+        if (host.status[i] & abi.ST_NO_MAP) or host.map_config[i] != 0 or math.exp(lp) < 0.95:
+            continue
+        v, p = host.afd(i, s_idx)
+        obs.append(ct.VariantObservation(lp, list(zip(v.tolist(), p.tolist())), float(host.map_vaf[i, s_idx]), "1", i))
+        kept.append(i)
+    assert 10 < len(obs) < b.n_loci
+    prior = ct.PriorEstimate(0.2, 25)
+    want = ct.contamination_posterior(obs, prior, device=0)
+
+    db = engine.DeviceBatch(b)
+    dr = engine.DeviceResults(b.n_loci, 2, flat.n_events, cap)
+    eng.call_batch_device(db, dr)
+    torch.cuda.synchronize()
+    dobs = ct.DeviceObservations(dr, s_idx, e_denovo)
+    assert dobs.n_obs == len(obs)
+    assert dobs.kept_loci[:dobs.n_obs].cpu().tolist() == kept
+    offs = dobs.afd_offsets[:dobs.n_obs + 1].cpu().numpy()
+    assert np.array_equal(np.diff(offs), [len(o.vafs) for o in obs])
+    assert np.array_equal(dobs.afd_vaf[:offs[-1]].cpu().numpy(), np.concatenate([o.vafs for o in obs]))
+    assert np.array_equal(dobs.afd_logp[:offs[-1]].cpu().numpy(), np.concatenate([o.densities for o in obs]))
+    got = ct.contamination_posterior_device(dobs, prior)
+    assert got.max_vaf == want.max_vaf and (got.ln_marginal == want.ln_marginal or (math.isnan(got.ln_marginal) and math.isnan(want.ln_marginal)))
+    assert np.array_equal(got.ln_posterior, want.ln_posterior, equal_nan=True)
+    assert np.array_equal(got.ln_likelihood, want.ln_likelihood, equal_nan=True)
+    # nothing passes a threshold of 1.0 + epsilon: an empty observation set is valid
+    none = ct.DeviceObservations(dr, s_idx, e_denovo, min_prob=1.5)
+    assert none.n_obs == 0 and np.isfinite(ct.contamination_posterior_device(none, None).ln_marginal)

@@ -194,6 +194,65 @@ def contamination_posterior(observations: Sequence[VariantObservation], prior_es
     return ContaminationPosterior(post, lik, float(marginal[0]), float(max_vaf[0]), tuple(float(x) for x in emsv))
 
 
+class DeviceObservations:
+    """The VariantObservations of a batch of calls, selected and packed on the device from device-resident results
+    (`vlr_contamination_gather_device`: VariantObservation::new, contamination.rs:44-82, for every call at once). torch
+    tensors are only the allocator."""
+
+    def __init__(self, dev_results, sample: int, denovo_event: int, min_prob: float = 0.95, device: int = 0, stream: int = 0):
+        import torch
+        from .engine import EngineError, lib
+        n, S, cap = dev_results.n_loci, dev_results.n_samples, dev_results.afd_capacity
+        if cap < 1:
+            raise ValueError("the calls carry no allele frequency distributions (afd_capacity = 0)")
+        dev = dev_results.log_posteriors.device
+        f64 = dict(dtype=torch.float64, device=dev)
+        self.prob_denovo = torch.empty(max(n, 1), **f64)
+        self.max_posterior_vaf = torch.empty(max(n, 1), **f64)
+        self.afd_offsets = torch.empty(n + 1, dtype=torch.int64, device=dev)
+        self.afd_vaf = torch.empty(max(n * cap, 1), **f64)
+        self.afd_logp = torch.empty(max(n * cap, 1), **f64)
+        self.kept_loci = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+        n_obs = C.c_int64(0)
+        cr = dev_results.as_c()
+        rc = lib().vlr_contamination_gather_device(
+            device, C.byref(cr), n, S, dev_results.n_events, sample, denovo_event, float(min_prob),
+            C.c_void_p(self.prob_denovo.data_ptr()), C.c_void_p(self.max_posterior_vaf.data_ptr()),
+            C.c_void_p(self.afd_offsets.data_ptr()), C.c_void_p(self.afd_vaf.data_ptr()), C.c_void_p(self.afd_logp.data_ptr()),
+            C.c_void_p(self.kept_loci.data_ptr()), C.byref(n_obs), C.c_void_p(stream or None))
+        if rc != 0:
+            raise EngineError("vlr_contamination_gather_device failed: %s" % lib().vlr_status_string(rc).decode())
+        self.n_obs = int(n_obs.value)
+        self.device = device
+
+
+def contamination_posterior_device(obs: DeviceObservations, prior_estimate: Optional[PriorEstimate] = None, n_grid: int = N_GRID,
+                                   expected_max_somatic_vafs: Sequence[float] = EXPECTED_MAX_SOMATIC_VAFS,
+                                   stream: int = 0) -> ContaminationPosterior:
+    """The second model over observations that never left the device (`vlr_contamination_posterior_device`)."""
+    import torch
+    from .engine import EngineError, lib
+    dev = obs.prob_denovo.device
+    emsv = torch.tensor(list(expected_max_somatic_vafs), dtype=torch.float64, device=dev)
+    ln_prior = torch.from_numpy(Prior(prior_estimate).table(n_grid)).to(dev)
+    post = torch.empty((len(emsv), n_grid), dtype=torch.float64, device=dev)
+    lik = torch.empty_like(post)
+    scal = torch.zeros(2, dtype=torch.float64, device=dev)  # marginal, max_vaf
+    p = lambda t, ct: abi.devptr(t.data_ptr(), ct)  # noqa: E731
+    cin = abi.ContaminationInput(obs.n_obs, p(obs.prob_denovo, C.c_double), p(obs.max_posterior_vaf, C.c_double),
+                                 p(obs.afd_offsets, C.c_int64), p(obs.afd_vaf, C.c_double), p(obs.afd_logp, C.c_double),
+                                 n_grid, len(emsv), p(emsv, C.c_double), p(ln_prior, C.c_double))
+    cout = abi.ContaminationOutput(p(post, C.c_double), p(lik, C.c_double), abi.devptr(scal.data_ptr(), C.c_double),
+                                   abi.devptr(scal.data_ptr() + 8, C.c_double))
+    rc = lib().vlr_contamination_posterior_device(obs.device, C.byref(cin), C.byref(cout), C.c_void_p(stream or None))
+    if rc != 0:
+        raise EngineError("vlr_contamination_posterior_device failed: %s" % lib().vlr_status_string(rc).decode())
+    torch.cuda.synchronize()
+    sc = scal.cpu().numpy()
+    return ContaminationPosterior(post.cpu().numpy(), lik.cpu().numpy(), float(sc[0]), float(sc[1]),
+                                  tuple(float(x) for x in expected_max_somatic_vafs))
+
+
 class ContaminationEstimator(CallProcessor):
     """contamination.rs:282-395. `posterior_fn` exists for the host tests (an emulated engine); the product default
     is the CUDA path."""

@@ -206,4 +206,99 @@ vlr_contam_finish_kernel(const double* __restrict__ partial, int n_chunks, const
 }
 #endif
 
+
+// ---- VariantObservation::new for a batch of calls, on the device (contamination.rs:44-82) ----------------------------
+// The estimator is a CallProcessor on `call_generic` (contamination.rs:282-306): per call it keeps {P(denovo), the
+// sample's allele frequency distribution, its MAP allele frequency} when P(denovo) >= 0.95 and an AFD exists. With
+// device-resident results of vlr_call_batch_device the same selection and the CSR packing of the kept AFDs run on the
+// device: a single CTA counts and scans (calls x 2 ints: tiny), a warp per kept call copies.
+struct GatherArgs {
+    const double* log_post;    // [n][E + 1]
+    const double* map_vaf;     // [n][S]
+    const int32_t* map_config; // [n]
+    const uint32_t* status;    // [n]
+    const int32_t* afd_count;  // [n][S]
+    const double* afd_vaf;     // [n][S][cap]
+    const double* afd_logp;
+    int64_t n;
+    int S, E1, cap, sample, event;
+    double min_prob;
+    // out
+    double* prob_denovo;
+    double* max_posterior_vaf;
+    int64_t* afd_offsets;
+    double* out_vaf;
+    double* out_logp;
+    int64_t* kept; // optional: call index of every observation
+    int64_t* n_obs;
+    // scratch
+    int64_t* obs_index; // [n]: observation number of the call, or -1
+    int64_t* pt_offset; // [n]
+};
+
+VLR_DEV bool gather_keeps(const GatherArgs& a, int64_t l) {
+    if (a.status[l] & VLR_ST_NO_MAP) return false;                 // sample_infos returned None
+    if (a.map_config[l] != 0) return false;                       // artifact MAP: no allele frequency distribution
+    return m_exp(a.log_post[l * a.E1 + a.event]) >= a.min_prob;   // prob_denovo.exp() >= 0.95
+}
+
+__global__ void __launch_bounds__(1024) vlr_contam_gather_scan_kernel(const GatherArgs a) {
+    __shared__ long long s_obs[1024], s_pts[1024];
+    const int t = (int)threadIdx.x, T = (int)blockDim.x;
+    const int64_t chunk = (a.n + T - 1) / T, lo = min(a.n, (int64_t)t * chunk), hi = min(a.n, lo + chunk);
+    long long n_obs = 0, n_pts = 0;
+    for (int64_t l = lo; l < hi; ++l)
+        if (gather_keeps(a, l)) {
+            n_obs++;
+            n_pts += a.afd_count[l * a.S + a.sample];
+        }
+    s_obs[t] = n_obs;
+    s_pts[t] = n_pts;
+    __syncthreads();
+    for (int o = 1; o < T; o <<= 1) { // inclusive scan (Hillis-Steele: 1024 entries)
+        const long long vo = t >= o ? s_obs[t - o] : 0, vp = t >= o ? s_pts[t - o] : 0;
+        __syncthreads();
+        s_obs[t] += vo;
+        s_pts[t] += vp;
+        __syncthreads();
+    }
+    long long obs = s_obs[t] - n_obs, pts = s_pts[t] - n_pts; // exclusive
+    for (int64_t l = lo; l < hi; ++l) {
+        if (gather_keeps(a, l)) {
+            a.obs_index[l] = obs;
+            a.pt_offset[l] = pts;
+            obs++;
+            pts += a.afd_count[l * a.S + a.sample];
+        } else {
+            a.obs_index[l] = -1;
+        }
+    }
+    if (t == T - 1) {
+        *a.n_obs = s_obs[t];
+        a.afd_offsets[s_obs[t]] = s_pts[t];
+    }
+}
+
+__global__ void __launch_bounds__(256) vlr_contam_gather_copy_kernel(const GatherArgs a) {
+    const int lane = (int)(threadIdx.x & 31);
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t l = warp; l < a.n; l += n_warps) {
+        const int64_t o = a.obs_index[l];
+        if (o < 0) continue;
+        const int64_t at = a.pt_offset[l];
+        const int cnt = a.afd_count[l * a.S + a.sample];
+        if (lane == 0) {
+            a.prob_denovo[o] = a.log_post[l * a.E1 + a.event];
+            a.max_posterior_vaf[o] = a.map_vaf[l * a.S + a.sample];
+            a.afd_offsets[o] = at;
+            if (a.kept) a.kept[o] = l;
+        }
+        const int64_t src = (l * a.S + a.sample) * a.cap;
+        for (int k = lane; k < cnt; k += 32) {
+            a.out_vaf[at + k] = a.afd_vaf[src + k];
+            a.out_logp[at + k] = a.afd_logp[src + k];
+        }
+    }
+}
+
 } // namespace vlrcontam

@@ -1170,6 +1170,64 @@ vlr_status_t vlr_contamination_posterior_device(int32_t device, const vlr_contam
     return st;
 }
 
+vlr_status_t vlr_contamination_gather_device(int32_t device, const vlr_results_t* results, int64_t n_loci,
+                                             int32_t n_samples, int32_t n_events, int32_t sample, int32_t denovo_event,
+                                             double min_prob, double* prob_denovo, double* max_posterior_vaf,
+                                             int64_t* afd_offsets, double* afd_vaf, double* afd_logp, int64_t* kept_loci,
+                                             int64_t* n_obs, void* cuda_stream) {
+    using namespace vlrcontam;
+    if (!results || !n_obs || n_loci < 0 || n_samples < 1 || n_events < 1 || sample < 0 || sample >= n_samples ||
+        denovo_event < 0 || denovo_event >= n_events)
+        return VLR_ERR_INVALID_ARGUMENT;
+    if (results->afd_capacity < 1 || !results->afd_count || !results->afd_vaf || !results->afd_logp || !results->log_posteriors ||
+        !results->map_vaf || !results->map_config || !results->status)
+        return VLR_ERR_INVALID_ARGUMENT;
+    if (!prob_denovo || !max_posterior_vaf || !afd_offsets || !afd_vaf || !afd_logp) return VLR_ERR_INVALID_ARGUMENT;
+    int n_sms = 0;
+    vlr_status_t st = contamination_device_ok(device, &n_sms);
+    if (st != VLR_OK) return st;
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    int64_t* d_tmp = nullptr; // obs_index [n], pt_offset [n], n_obs [1]
+    if (cudaMallocAsync(&d_tmp, sizeof(int64_t) * (size_t)(2 * n_loci + 1), s) != cudaSuccess) {
+        cudaGetLastError();
+        return VLR_ERR_OUT_OF_MEMORY;
+    }
+    GatherArgs a;
+    a.log_post = results->log_posteriors;
+    a.map_vaf = results->map_vaf;
+    a.map_config = results->map_config;
+    a.status = results->status;
+    a.afd_count = results->afd_count;
+    a.afd_vaf = results->afd_vaf;
+    a.afd_logp = results->afd_logp;
+    a.n = n_loci;
+    a.S = n_samples;
+    a.E1 = n_events + 1;
+    a.cap = results->afd_capacity;
+    a.sample = sample;
+    a.event = denovo_event;
+    a.min_prob = min_prob;
+    a.prob_denovo = prob_denovo;
+    a.max_posterior_vaf = max_posterior_vaf;
+    a.afd_offsets = afd_offsets;
+    a.out_vaf = afd_vaf;
+    a.out_logp = afd_logp;
+    a.kept = kept_loci;
+    a.obs_index = d_tmp;
+    a.pt_offset = d_tmp + n_loci;
+    a.n_obs = d_tmp + 2 * n_loci;
+    vlr_contam_gather_scan_kernel<<<1, 1024, 0, s>>>(a);
+    if (n_loci > 0) {
+        const int blocks = (int)std::min<int64_t>((n_loci + 7) / 8, (int64_t)n_sms * 8);
+        vlr_contam_gather_copy_kernel<<<blocks, 256, 0, s>>>(a);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(n_obs, a.n_obs, sizeof(int64_t), cudaMemcpyDeviceToHost, s);
+    cudaFreeAsync(d_tmp, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    return e == cudaSuccess ? VLR_OK : VLR_ERR_CUDA;
+}
+
 vlr_status_t vlr_contamination_posterior(int32_t device, const vlr_contamination_input_t* in,
                                          vlr_contamination_output_t* out) {
     if (!contamination_args_ok(in, out)) return VLR_ERR_INVALID_ARGUMENT;

@@ -63,6 +63,10 @@ def lib():
         l.vlr_contamination_posterior_device.restype = C.c_int32
         l.vlr_contamination_posterior_device.argtypes = [C.c_int32, C.POINTER(abi.ContaminationInput),
                                                          C.POINTER(abi.ContaminationOutput), C.c_void_p]
+        l.vlr_contamination_gather_device.restype = C.c_int32
+        l.vlr_contamination_gather_device.argtypes = [C.c_int32, C.POINTER(abi.Results), C.c_int64, C.c_int32, C.c_int32,
+                                                      C.c_int32, C.c_int32, C.c_double] + [C.c_void_p] * 6 + \
+            [C.POINTER(C.c_int64), C.c_void_p]
         l.vlr_pack_batch.restype = C.c_int32
         l.vlr_pack_batch.argtypes = [C.POINTER(abi.Batch), C.c_int32, C.POINTER(C.POINTER(abi.PackedBatch))]
         l.vlr_packed_batch_free.restype = None
@@ -80,7 +84,7 @@ def lib():
 EXPORTED_SYMBOLS = ["vlr_ctx_create", "vlr_ctx_destroy", "vlr_call_batch", "vlr_call_batch_device", "vlr_ctx_reserve",
                     "vlr_host_alloc", "vlr_host_free", "vlr_last_launch_count", "vlr_ctx_stream", "vlr_last_error",
                     "vlr_status_string", "vlr_abi_version", "vlr_measure_fp64_peak", "vlr_contamination_posterior",
-                    "vlr_contamination_posterior_device", "vlr_pack_batch", "vlr_packed_batch_free",
+                    "vlr_contamination_posterior_device", "vlr_contamination_gather_device", "vlr_pack_batch", "vlr_packed_batch_free",
                     "vlr_packed_batch_bytes", "vlr_call_batch_packed"]
 
 
