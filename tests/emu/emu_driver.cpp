@@ -190,9 +190,10 @@ extern "C" int32_t vlr_emu_wave_call_batch(const vlr_scenario_t* sc, const vlr_b
                 oc->lc.nqTy = L.nqTy;
                 oc->lc.ksumP = L.ksumP;
                 oc->lc.ksumT = L.ksumT;
-                const int nq = L.nqPx + L.nqPy + L.nqTx + L.nqTy;
+                const int nqP = L.nqPx + L.nqPy, nq = L.nqTx + L.nqTy;
                 if (nq > r_slot_q(cls)) return -VLR_ERR_INVALID_ARGUMENT;
-                std::memcpy(oc->q, wb.coef + L.coefP, sizeof(double) * R_QW * (size_t)nq);
+                oc->lc.qP = wb.coef + L.coefP;
+                std::memcpy(oc->q, wb.coef + L.coefP + (size_t)nqP * R_QW, sizeof(double) * R_QW * (size_t)nq);
                 int n_tasks = r_first_tasks(&ds, wp, wb, lci, oc->task, one);
                 for (int round = 0; n_tasks > 0; ++round) {
                     for (int t = 0; t < n_tasks; ++t)

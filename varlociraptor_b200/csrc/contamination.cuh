@@ -242,6 +242,7 @@ VLR_DEV bool gather_keeps(const GatherArgs& a, int64_t l) {
     return m_exp(a.log_post[l * a.E1 + a.event]) >= a.min_prob;   // prob_denovo.exp() >= 0.95
 }
 
+#ifndef VLR_HOST_EMU
 __global__ void __launch_bounds__(1024) vlr_contam_gather_scan_kernel(const GatherArgs a) {
     __shared__ long long s_obs[1024], s_pts[1024];
     const int t = (int)threadIdx.x, T = (int)blockDim.x;
@@ -300,5 +301,7 @@ __global__ void __launch_bounds__(256) vlr_contam_gather_copy_kernel(const Gathe
         }
     }
 }
+
+#endif // VLR_HOST_EMU
 
 } // namespace vlrcontam

@@ -23,10 +23,12 @@
 
 constexpr int R_DEG = 5;          // reads per polynomial
 constexpr int R_QW = R_DEG + 1;   // coefficients (doubles) per polynomial: 48 bytes = 3 x 16
-constexpr int R_SLOT_Q = 48;      // polynomials per octet slot (parent and leaf pileup of one lc): 2304 bytes
-constexpr int R_SLOT_QM = 208;    // ... of a warp's slot, class 2 (~1000 reads): 9984 bytes
-constexpr int R_SLOT_QD = 416;    // ... class 3 (~2000 reads): 19968 bytes
-constexpr int R_SLOT_QL = 832;    // ... class 4 (~4100 reads): 39936 bytes
+// A slot holds the polynomials of the LEAF pileup (evaluated ~30 times per task); the parent pileup is evaluated once per
+// task and round and is read from the arena (L2): half the shared memory per lc, a third more lcs per SM.
+constexpr int R_SLOT_Q = 24;      // polynomials per octet slot (a pileup of <= 110 reads): 1152 bytes
+constexpr int R_SLOT_QM = 104;    // ... of a warp's slot, class 2 (~500 reads): 4992 bytes
+constexpr int R_SLOT_QD = 208;    // ... class 3 (~1000 reads): 9984 bytes
+constexpr int R_SLOT_QL = 416;    // ... class 4 (~2070 reads): 19968 bytes
 constexpr int R_CLASSES = W_RCLASSES; // 1: an octet per lc; 2..4: a warp per lc (deep pileups, depth skew)
 constexpr int R_POOL_N = 400;     // sorted-list nodes per lc, shared by the tasks of a round: one 32-bit word each,
                                   // (24-bit key << 8) | next node (a task visits ~60 points at resolution 0.01)
@@ -34,16 +36,18 @@ constexpr int R_POOL_D = R_POOL_N / 2; // ... as doubles: 1600 bytes
 constexpr int R_SORT = 64;        // points of the OUTER grid sorted in the (then idle) pool (larger: global scratch)
 constexpr int R_NONE = 255;       // end of a sorted list
 constexpr int R_ZERO_E = -(1 << 29);
-constexpr int R_MAXREADS = R_DEG * R_SLOT_QL; // no resident lc has more kept reads (r_class)
+constexpr int R_MAXREADS = 2 * R_DEG * R_SLOT_QL; // no resident lc has more kept reads in its two pileups (r_class)
 // coefficient kernel, per warp: 4 doubles per read + (c, d) pairs of a pileup = 6 doubles per read of the deepest
 // resident lc the workspace allows (WaveBufs::cscratch_reads <= R_MAXREADS)
 // upper bound of the polynomials of a pileup of n reads (two groups, each rounded up)
 VLR_DEV int r_qcap(int n) { return n / R_DEG + 2; }
 VLR_DEV int r_slot_q(int cls) { return cls == 1 ? R_SLOT_Q : (cls == 2 ? R_SLOT_QM : (cls == 3 ? R_SLOT_QD : R_SLOT_QL)); }
-// size class of an lc whose pileups hold nP and nT kept reads (0: not resident, the per-round kernels serve it)
+// size class of an lc whose pileups hold nP and nT kept reads (0: not resident, the per-round kernels serve it): by the
+// deeper of the two (the slot holds the leaf pileup; a parent pileup of another order of magnitude, read from L2 by
+// the few lanes of an octet's task, would stall the octet's neighbours)
 VLR_DEV int r_class(int nP, int nT, int scratch_reads) {
     if (nP + nT > scratch_reads) return 0;
-    const int q = r_qcap(nP) + r_qcap(nT);
+    const int q = r_qcap(nP > nT ? nP : nT);
     return q <= R_SLOT_Q ? 1 : (q <= R_SLOT_QM ? 2 : (q <= R_SLOT_QD ? 3 : (q <= R_SLOT_QL ? 4 : 0)));
 }
 
@@ -165,11 +169,12 @@ VLR_DEV double r_horner(const double2 q01, const double2 q23, const double2 q45,
 // Product of the polynomials [0, nqx) at x and [nqx, nqx + nqy) at y for NP abscissae at once; the H lanes of a task
 // (WSplit) take every H-th polynomial and combine their partial products with an xor butterfly (bitwise identical in
 // all H lanes: their control flow stays identical). Returns true when some product left the safe range.
-template <int NP>
+// SM: `q` points into the CTA's dynamic shared memory (LDS instead of generic loads).
+template <int NP, bool SM>
 VLR_DEV bool r_eval(const double* __restrict__ q, int nqx, int nqy, const double* x, const double* y, MV* out, const WSplit sp) {
     const double2* __restrict__ q2 = reinterpret_cast<const double2*>(q);
 #ifndef VLR_HOST_EMU
-    q2 = reinterpret_cast<const double2*>(vlr_smem + (__cvta_generic_to_shared(q) - __cvta_generic_to_shared(vlr_smem)));
+    if (SM) q2 = reinterpret_cast<const double2*>(vlr_smem + (__cvta_generic_to_shared(q) - __cvta_generic_to_shared(vlr_smem)));
 #endif
     double acc[NP];
     int ex[NP];
@@ -262,9 +267,9 @@ VLR_DEV_NOINLINE MV r_eval_careful(const double* q, int nqx, int nqy, double x, 
     return MV{acc, ex};
 }
 
-template <int NP>
+template <int NP, bool SM>
 VLR_DEV void r_pileup(const double* q, int nqx, int nqy, const double* x, const double* y, int nvalid, MV* out, const WSplit sp) {
-    if (r_eval<NP>(q, nqx, nqy, x, y, out, sp)) { // rare: every lane of the task re-evaluates (identical values)
+    if (r_eval<NP, SM>(q, nqx, nqy, x, y, out, sp)) { // rare: every lane of the task re-evaluates (identical values)
 #pragma unroll
         for (int k = 0; k < NP; ++k)
             if (k < nvalid) out[k] = r_eval_careful(q, nqx, nqy, x[k], y[k]);
@@ -285,9 +290,10 @@ struct RTask {
 
 struct RLc { // what the rounds need from the lc record, read once
     int lci, li, ci;
-    int nqPx, nqPy, nqTx, nqTy; // polynomials of the parent pileup (slot offset 0) and of the leaf pileup
+    int nqPx, nqPy, nqTx, nqTy; // polynomials of the parent pileup (arena, qP) and of the leaf pileup (the slot)
     int pad;
     double ksumP, ksumT;
+    const double* qP;
 };
 
 struct alignas(16) ROct { // per lc group (octet or warp) in shared memory; the slot of polynomials follows it
@@ -297,6 +303,7 @@ struct alignas(16) ROct { // per lc group (octet or warp) in shared memory; the 
     RLc lc;
     unsigned long long bar; // mbarrier of the slot's bulk copy
     double* q;              // the slot: r_slot_q(class) polynomials (128-bit loads, 16-byte bulk copies)
+    unsigned long long pad;
 };
 static_assert(sizeof(ROct) % 16 == 0, "the slot behind the record must stay 16-byte aligned");
 
@@ -370,7 +377,7 @@ VLR_DEV void r_task_run(const DevScenario* sc, const WavePlan& wp, const ROct& o
     }
     const double px = t.parent_x;
     const double vby = smT.contamination_by >= 0 ? px : 0.0;
-    const double* qT = oc.q + (size_t)(oc.lc.nqPx + oc.lc.nqPy) * R_QW;
+    const double* qT = oc.q;
     const int nqx = oc.lc.nqTx, nqy = oc.lc.nqTy;
     const double res = smT.resolution;
     int n = 0, n_evals = 0;
@@ -463,7 +470,7 @@ VLR_DEV void r_task_run(const DevScenario* sc, const WavePlan& wp, const ROct& o
                 X[k] = w.xu;
                 Y[k] = w.Yp;
             }
-            r_pileup<3>(qT, nqx, nqy, X, Y, nvalid, v, sp);
+            r_pileup<3, true>(qT, nqx, nqy, X, Y, nvalid, v, sp);
         }
         const int i0 = visit(xs[0], v[0]);
         const int i1 = visit(xs[1], v[1]);
@@ -703,7 +710,7 @@ VLR_DEV void r_task(const DevScenario* sc, const WavePlan& wp, const WaveBufs& w
     if (oc.lc.nqPx + oc.lc.nqPy > 0) {
         const WArgs ap = wave_args(1.0, 0.0, px, 0.0);
         MV v;
-        r_pileup<1>(oc.q, oc.lc.nqPx, oc.lc.nqPy, &ap.xu, &ap.Yp, 1, &v, sp);
+        r_pileup<1, false>(oc.lc.qP, oc.lc.nqPx, oc.lc.nqPy, &ap.xu, &ap.Yp, 1, &v, sp); // (from the arena)
         lh = v.m != v.m ? NAN : (mv_ln(v) + oc.lc.ksumP);
     }
     const double prior = wave_prior_ok(sc, wp.P, px) ? 0.0 : neg_inf();

@@ -467,7 +467,7 @@ __device__ __forceinline__ void wave_resident_body(const WaveParams& p, const in
             const int lci = more ? rlist[t] : -1;
             if (lci >= 0) { // (a negative entry: the list's bookkeeping left a hole; take the next ticket)
                 const WaveLC& L = wb.lcs[lci];
-                const int nq = L.nqPx + L.nqPy + L.nqTx + L.nqTy;
+                const int nqP = L.nqPx + L.nqPy, nq = L.nqTx + L.nqTy; // the slot takes the leaf pileup's polynomials
                 __syncwarp(gmask); // nobody of the group still reads the slot
                 if (lg == 0) {
                     oc.lc.lci = lci;
@@ -479,13 +479,14 @@ __device__ __forceinline__ void wave_resident_body(const WaveParams& p, const in
                     oc.lc.nqTy = L.nqTy;
                     oc.lc.ksumP = L.ksumP;
                     oc.lc.ksumT = L.ksumT;
+                    oc.lc.qP = wb.coef + L.coefP;
                     const unsigned bytes = (unsigned)nq * (unsigned)(R_QW * sizeof(double));
                     // the slot was last read through the generic proxy: order those reads before the bulk write
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
                     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                                      smem_u32(oc.q)),
-                                 "l"(wb.coef + L.coefP), "r"(bytes), "r"(bar)
+                                 "l"(wb.coef + L.coefP + (size_t)nqP * R_QW), "r"(bytes), "r"(bar)
                                  : "memory");
                 }
                 cnt = r_first_tasks(&p.sc, p.wp, wb, lci, oc.task, grp); // while the copy is in flight
