@@ -1405,6 +1405,10 @@ vlr_status_t vlr_ctx_create(const vlr_scenario_t* scenario, int32_t device, vlr_
         CKB(cudaFuncSetAttribute(vlr_wave_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)res_smem(8, vlr_small::R_SLOT_Q)));
         int n4 = 0;
         CKB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n4, vlr_wave_resident_kernel, RES_THREADS, res_smem(8, vlr_small::R_SLOT_Q)));
+        if (const char* e = getenv("VLR_RES_CTAS")) { // measurements: fewer CTAs of the octet kernel per SM
+            const int v = atoi(e);
+            if (v >= 1 && v < n4) n4 = v;
+        }
         ctx->wave_grid_res = std::max(1, n4) * ctx->n_sms;
         CKB(cudaFuncSetAttribute(vlr_wave_resident_deep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)res_smem(32, vlr_small::R_SLOT_QL)));
         const int slots[3] = {vlr_small::R_SLOT_QM, vlr_small::R_SLOT_QD, vlr_small::R_SLOT_QL};
