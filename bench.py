@@ -37,6 +37,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # one hardware queue per stream of the host entry (engine.py)
 
 METRIC = "loci_per_sec"
 UNIT = "loci/s"

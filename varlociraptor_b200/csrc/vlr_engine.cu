@@ -4,7 +4,7 @@
 // atomic ticket so that the very uneven per-locus work (a few hundred to >100k per-read evaluations)
 // balances dynamically. All per-locus logic lives in engine_core.cuh.
 //
-// Host: vlr_call_batch() streams a host batch through 8 slots (chunk of loci -> H2D -> kernel -> D2H, one CUDA
+// Host: vlr_call_batch() streams a host batch through 6 slots (chunk of loci -> H2D -> kernel -> D2H, one CUDA
 // stream per slot) so copies overlap compute; vlr_call_batch_device() launches on device-resident buffers.
 // There is no CPU fallback: without a usable CUDA device vlr_ctx_create() fails with VLR_ERR_NO_DEVICE.
 #include <cuda_fp16.h>
@@ -725,6 +725,7 @@ struct DevBuf {
 
 struct Slot { // one in-flight chunk of vlr_call_batch
     cudaStream_t stream = nullptr;
+    cudaEvent_t ev_ready = nullptr, ev_free = nullptr; // inputs of the chunk are on the device / its kernels have read them
     DevBuf offsets, cols[7], rflags, hart, hvar, lflags, het, semr;
     DevBuf pk[VLR_N_PACKED_COLUMNS], pk_dict[VLR_N_PACKED_COLUMNS]; // packed chunk (vlr_call_batch_packed) and its dictionaries
     DevBuf log_post, log_marginal, map_vaf, map_config, best_event, status, n_base, afd_count, afd_vaf, afd_logp;
@@ -772,9 +773,11 @@ struct vlr_ctx {
     bool have_done = false;        // another stream waits for it (an event chain instead of a rule for the caller)
     int n_aux = 3; // measured on 512k config-2 loci: 1 stream 4.05, 2: 4.43, 3: 4.48, 4: 4.51 M loci/s
     Slot slots[NBUF_MAX];
-    int nbuf = 8; // chunks in flight (VLR_NBUF). Measured (1M config-2 / config-3 loci, packed columns): 3: 6.10 / 9.0,
-                  // 6: 6.38 / 10.9, 8: 6.53 / 11.3 M loci/s — with 3 the streams ran in phase and the SMs idled during every
-                  // wave of copies
+    cudaStream_t copy_stream = nullptr; // all host -> device copies of the host entries (prefetch ahead of the kernels)
+    int nbuf = 6; // chunk slots in use (VLR_NBUF): nbuf / 2 compute streams + one copy stream that runs ahead of them.
+                  // Measured (1M config-2 / config-3 loci, packed columns): 4, 6, 8 slots: 6.83 / 11.9 M loci/s each; before
+                  // the copy stream (every slot its own stream for copies and kernels) 3: 6.10 / 9.0, 8: 6.53 / 11.3 — the
+                  // streams ran in phase and the SMs idled during every wave of copies
     int64_t reserve_reads = 4096;
     int64_t launches = 0;
     std::string err;
@@ -1478,7 +1481,12 @@ vlr_status_t vlr_ctx_create(const vlr_scenario_t* scenario, int32_t device, vlr_
         const int v = atoi(e);
         if (v >= 1 && v <= NBUF_MAX) ctx->nbuf = v;
     }
-    for (int i = 0; i < NBUF_MAX; ++i) CKB(cudaStreamCreateWithFlags(&ctx->slots[i].stream, cudaStreamNonBlocking));
+    for (int i = 0; i < NBUF_MAX; ++i) {
+        CKB(cudaStreamCreateWithFlags(&ctx->slots[i].stream, cudaStreamNonBlocking));
+        CKB(cudaEventCreateWithFlags(&ctx->slots[i].ev_ready, cudaEventDisableTiming));
+        CKB(cudaEventCreateWithFlags(&ctx->slots[i].ev_free, cudaEventDisableTiming));
+    }
+    CKB(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
 #undef CKB
     *out = ctx;
     return VLR_OK;
@@ -1492,6 +1500,8 @@ void vlr_ctx_destroy(vlr_ctx_t* ctx) {
             cudaStreamSynchronize(s.stream);
             cudaStreamDestroy(s.stream);
         }
+        if (s.ev_ready) cudaEventDestroy(s.ev_ready);
+        if (s.ev_free) cudaEventDestroy(s.ev_free);
         s.offsets.release();
         for (auto& c : s.cols) c.release();
         for (auto& c : s.pk) c.release();
@@ -1507,6 +1517,10 @@ void vlr_ctx_destroy(vlr_ctx_t* ctx) {
     if (ctx->stream) {
         cudaStreamSynchronize(ctx->stream);
         cudaStreamDestroy(ctx->stream);
+    }
+    if (ctx->copy_stream) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamDestroy(ctx->copy_stream);
     }
     free_slot(ctx->dev_slot);
     for (auto& sa : ctx->dev_slot_aux) free_slot(sa);
@@ -1658,15 +1672,18 @@ static vlr_status_t call_batch_host(vlr_ctx_t* ctx, const vlr_packed_batch_t* ba
         }
         const int64_t r1 = off[hi * S], nl = hi - lo, nr = r1 - r0;
         Slot& sl = ctx->slots[k % nbuf];
-        cudaStream_t s = sl.stream;
-        // the slot's buffers are reused in stream order (copies and kernels of chunk k - nbuf precede this chunk's on the
-        // same stream), so the host does not wait for that chunk: it queues the whole batch and every stream always
-        // has its next chunk behind the running one. A buffer that has to grow is freed first, which synchronises.
+        // nbuf slots of buffers, nbuf / 2 compute streams, ONE copy stream: the copies of chunk k start as soon as the
+        // kernels of chunk k - nbuf have read the slot's inputs (ev_free), i.e. while the chunks in front of it are still
+        // computing, and its kernels (on the stream of chunk k - nbuf / 2) start when the copies are done (ev_ready).
+        // The host queues the whole batch without waiting; a buffer that has to grow is freed first, which synchronises.
+        const int ncomp = std::max(1, nbuf / 2);
+        cudaStream_t s = ctx->slots[k % ncomp].stream, hs = ctx->copy_stream;
         st = ensure_workspace(ctx, sl, max_reads, cap > 0);
         if (st != VLR_OK) break;
-        mark(s);
+        if (k >= nbuf) CK(cudaStreamWaitEvent(hs, sl.ev_free, 0));
+        mark(hs);
         CK(sl.offsets.ensure(sizeof(int64_t) * (size_t)(nl * S + 1)));
-        CK(cudaMemcpyAsync(sl.offsets.p, off + lo * S, sizeof(int64_t) * (size_t)(nl * S + 1), cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(sl.offsets.p, off + lo * S, sizeof(int64_t) * (size_t)(nl * S + 1), cudaMemcpyHostToDevice, hs));
         // columns: plain ones go straight into place, encoded ones into the slot's staging buffers (with their
         // dictionaries the first time the slot is used in this call) and are widened on the device
         UnpackParams up;
@@ -1682,40 +1699,43 @@ static vlr_status_t call_batch_host(vlr_ctx_t* ctx, const vlr_packed_batch_t* ba
             up.dict[c] = nullptr;
             const size_t w = enc_bytes[col.encoding];
             if (col.encoding == VLR_ENC_F32) {
-                if (nr) CK(cudaMemcpyAsync(dstb.p, (const char*)col.data + 4 * (size_t)r0, 4 * (size_t)nr, cudaMemcpyHostToDevice, s));
+                if (nr) CK(cudaMemcpyAsync(dstb.p, (const char*)col.data + 4 * (size_t)r0, 4 * (size_t)nr, cudaMemcpyHostToDevice, hs));
                 continue;
             }
             if (w) {
                 CK(sl.pk[c].ensure(w * (size_t)std::max<int64_t>(nr, 4)));
-                if (nr) CK(cudaMemcpyAsync(sl.pk[c].p, (const char*)col.data + w * (size_t)r0, w * (size_t)nr, cudaMemcpyHostToDevice, s));
+                if (nr) CK(cudaMemcpyAsync(sl.pk[c].p, (const char*)col.data + w * (size_t)r0, w * (size_t)nr, cudaMemcpyHostToDevice, hs));
                 up.src[c] = sl.pk[c].p;
             }
             if (col.n_dict > 0) {
                 if (k < nbuf) {
                     CK(sl.pk_dict[c].ensure(sizeof(uint32_t) * (size_t)col.n_dict));
-                    CK(cudaMemcpyAsync(sl.pk_dict[c].p, col.dict, sizeof(uint32_t) * (size_t)col.n_dict, cudaMemcpyHostToDevice, s));
+                    CK(cudaMemcpyAsync(sl.pk_dict[c].p, col.dict, sizeof(uint32_t) * (size_t)col.n_dict, cudaMemcpyHostToDevice, hs));
                 }
                 up.dict[c] = (const uint32_t*)sl.pk_dict[c].p;
             }
-        }
-        if (any_packed && nr) {
-            const int bx = (int)std::min<int64_t>((nr / 4 + 255) / 256 + 1, (int64_t)ctx->n_sms * 8);
-            vlr_unpack_kernel<<<dim3(bx, VLR_N_PACKED_COLUMNS), 256, 0, s>>>(up);
-            CK(cudaGetLastError());
-            unpack_launches++;
         }
         auto opt_up = [&](DevBuf& buf, const float* src, int64_t first, int64_t n) -> cudaError_t {
             if (!src) return cudaSuccess;
             cudaError_t e = buf.ensure(sizeof(float) * (size_t)std::max<int64_t>(n, 1));
             if (e != cudaSuccess || n == 0) return e;
-            return cudaMemcpyAsync(buf.p, src + first, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, s);
+            return cudaMemcpyAsync(buf.p, src + first, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, hs);
         };
         CK(opt_up(sl.hart, batch->prob_homopolymer_artifact, r0, nr));
         CK(opt_up(sl.hvar, batch->prob_homopolymer_variant, r0, nr));
         CK(opt_up(sl.het, batch->locus_heterozygosity_phred, lo, nl));
         CK(opt_up(sl.semr, batch->locus_semr_phred, lo, nl));
         CK(sl.lflags.ensure(sizeof(uint32_t) * (size_t)nl));
-        CK(cudaMemcpyAsync(sl.lflags.p, batch->locus_flags + lo, sizeof(uint32_t) * (size_t)nl, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(sl.lflags.p, batch->locus_flags + lo, sizeof(uint32_t) * (size_t)nl, cudaMemcpyHostToDevice, hs));
+        CK(cudaEventRecord(sl.ev_ready, hs));
+        mark(hs);
+        CK(cudaStreamWaitEvent(s, sl.ev_ready, 0));
+        if (any_packed && nr) {
+            const int bx = (int)std::min<int64_t>((nr / 4 + 255) / 256 + 1, (int64_t)ctx->n_sms * 8);
+            vlr_unpack_kernel<<<dim3(bx, VLR_N_PACKED_COLUMNS), 256, 0, s>>>(up);
+            CK(cudaGetLastError());
+            unpack_launches++;
+        }
         // results
         CK(sl.log_post.ensure(sizeof(double) * (size_t)(nl * (E + 1))));
         CK(sl.log_marginal.ensure(sizeof(double) * (size_t)nl));
@@ -1761,6 +1781,7 @@ static vlr_status_t call_batch_host(vlr_ctx_t* ctx, const vlr_packed_batch_t* ba
         mark(s);
         st = launch(ctx, sl, b, r, s, nl > 0 ? (nr + nl - 1) / nl : 0);
         if (st != VLR_OK) break;
+        CK(cudaEventRecord(sl.ev_free, s));
         mark(s);
         // D2H
         CK(cudaMemcpyAsync(results->log_posteriors + lo * (E + 1), r.log_post, sizeof(double) * (size_t)(nl * (E + 1)), cudaMemcpyDeviceToHost, s));
@@ -1780,15 +1801,15 @@ static vlr_status_t call_batch_host(vlr_ctx_t* ctx, const vlr_packed_batch_t* ba
         ++k;
     }
     ctx->launches += unpack_launches;
-    for (int i = 0; i < nbuf; ++i) {
-        cudaError_t e = cudaStreamSynchronize(ctx->slots[i].stream);
+    for (int i = 0; i <= nbuf; ++i) {
+        cudaError_t e = cudaStreamSynchronize(i < nbuf ? ctx->slots[i].stream : ctx->copy_stream);
         if (e != cudaSuccess && st == VLR_OK) st = ctx->fail_cuda(e, "cudaStreamSynchronize", __LINE__);
     }
     if (timing && !tev.empty()) {
-        for (size_t c = 0; c + 3 < tev.size(); c += 4) {
-            float t[4];
-            for (int j = 0; j < 4; ++j) cudaEventElapsedTime(&t[j], tev[0], tev[c + j]);
-            fprintf(stderr, "chunk %2zu stream %zu: h2d %7.2f .. %7.2f  kernels .. %7.2f  d2h .. %7.2f ms\n", c / 4, (c / 4) % (size_t)nbuf, t[0], t[1], t[2], t[3]);
+        for (size_t c = 0; c + 4 < tev.size(); c += 5) {
+            float t[5];
+            for (int j = 0; j < 5; ++j) cudaEventElapsedTime(&t[j], tev[0], tev[c + j]);
+            fprintf(stderr, "chunk %2zu slot %zu: h2d %7.2f .. %7.2f  kernels %7.2f .. %7.2f  d2h .. %7.2f ms\n", c / 5, (c / 5) % (size_t)nbuf, t[0], t[1], t[2], t[3], t[4]);
         }
         for (cudaEvent_t e : tev) cudaEventDestroy(e);
     }

@@ -16,6 +16,12 @@ import numpy as np
 from . import abi
 from .batch import CallResults, LocusBatch
 
+# The host entries keep eight chunks in flight on eight streams, next to the context's own ones. With the default of 8
+# hardware connections some of those streams share a queue and a chunk waits for the whole chunk in front of it on
+# that queue (seen in the VLR_CHUNK_TIMING timeline: chunks 4..7 started when chunks 0..3 had finished). Has to be set
+# before the process creates its CUDA context; a host application sets it in its environment.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 _LIB_PATH = os.environ.get("VLR_ENGINE_LIB",  # developer override for tuning experiments (another CUDA build)
                            os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libvlr_engine.so"))
 _lib = None
