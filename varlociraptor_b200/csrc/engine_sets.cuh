@@ -180,13 +180,23 @@ VLR_DEV void sets_pre_locus(const DevScenario* sc, const DevBatch* b, const Sets
 
 // ---------------------------------------------------------------------------------------------- lc (warp per lc)
 // `coef`: the warp's coefficient arena (SETS_SM_READS reads), `ll`: SETS_MAXF doubles of warp-private scratch.
+// The warps of a CTA run the three phases of their lcs together (`phased`: a CTA barrier between coefficients, folds
+// and leaves; `lci` < 0: this warp has no lc in this iteration but keeps the barriers): the kernel's text is 170 KB and
+// the phases share almost none of it, so warps in different phases evicted each other's instructions
+// (stall_no_instruction 3.4 cycles per issue before, profiles/ncu_r2b_sets_lc_summary.csv).
+#ifdef VLR_HOST_EMU
+VLR_DEV void sets_phase_sync() {}
+#else
+VLR_DEV void sets_phase_sync() { __syncthreads(); }
+#endif
 VLR_DEV void sets_lc(const DevScenario* sc, const DevBatch* b, const SetsPlan& sp, const SetsBufs& sb, int lci, int64_t sub_lo,
-                     bool want_be, Ctx& c, double* coef, double* ll) {
-    SetsLC& lc = sb.lcs[lci];
-    const int li = lc.li, ci = lc.ci;
-    if (li < 0) return; // dead
+                     bool want_be, Ctx& c, double* coef, double* ll, bool phased = false) {
+    const bool live = lci >= 0 && sb.lcs[lci].li >= 0; // (li < 0: dead)
+    SetsLC& lc = sb.lcs[live ? lci : 0];
+    const int li = live ? lc.li : 0, ci = lc.ci;
     const SetsLocus& wl = sb.loci[li];
     const int S = sc->S, E = sc->E;
+    if (live) {
     c.sc = sc;
     c.b = b;
     c.locus = sub_lo + li;
@@ -215,13 +225,19 @@ VLR_DEV void sets_lc(const DevScenario* sc, const DevBatch* b, const SetsPlan& s
     warp_sync();
     if (!sets_prior_ready(sp, c.vartype)) sets_fill_prior(c, sp, c.vartype);
     for (int s = 0; s < S; ++s) read_coefficients(c, s);
+    }
+    if (phased) sets_phase_sync();
     // ---- folds: the pileup ln-likelihoods the leaves look up
-    for (int f = 0; f < sp.n_folds; ++f) {
-        const SetsFold fd = sp.folds[f];
-        const double v = sample_likelihood_call(c, fd.sample, fd.vaf, fd.vaf_by);
-        if (lane_id() == 0) ll[f] = v;
+    if (live) {
+        for (int f = 0; f < sp.n_folds; ++f) {
+            const SetsFold fd = sp.folds[f];
+            const double v = sample_likelihood_call(c, fd.sample, fd.vaf, fd.vaf_by);
+            if (lane_id() == 0) ll[f] = v;
+        }
     }
     warp_sync();
+    if (phased) sets_phase_sync();
+    if (!live) return;
     // ---- leaves and events
     const double* prior = sp.prior_val + (size_t)c.vartype * sp.n_leaves;
     const uint32_t* pside = sp.prior_side + (size_t)c.vartype * sp.n_leaves;

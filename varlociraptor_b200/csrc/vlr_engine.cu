@@ -597,12 +597,13 @@ __global__ void __launch_bounds__(THREADS, 2) vlr_sets_lc_kernel(const __grid_co
     double* arena = reinterpret_cast<double*>(vlr_smem + (size_t)WARPS_PER_CTA * CTX_LEAN) +
                     (size_t)group_in_cta() * (4 * SETS_SM_READS + SETS_MAXF);
     const unsigned long long n_lc = min(p.sb.cnt->n_lc, (unsigned)p.sb.lc_cap);
-    for (;;) {
+    for (;;) { // the CTA's warps take one lc each and go through its phases together (sets_lc)
         unsigned long long t = 0;
         if (lane_id() == 0) t = atomicAdd(&p.sb.cnt->ticket[1], 1ULL);
         t = __shfl_sync(FULL, t, 0, LANES);
-        if (t >= n_lc) break;
-        sets_lc(&p.sc, &p.b, p.sp, p.sb, (int)t, p.sub_lo, p.want_be != 0, c, arena, arena + 4 * SETS_SM_READS);
+        const bool mine = t < n_lc;
+        if (!__syncthreads_or(mine ? 1 : 0)) break;
+        sets_lc(&p.sc, &p.b, p.sp, p.sb, mine ? (int)t : -1, p.sub_lo, p.want_be != 0, c, arena, arena + 4 * SETS_SM_READS, true);
         warp_sync();
     }
 }
