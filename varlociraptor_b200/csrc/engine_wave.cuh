@@ -526,17 +526,11 @@ VLR_DEV double grp_sum_d(double v, const WGroup&) { return v; }
 VLR_DEV unsigned grp_bcast_u(unsigned v, const WGroup&) { return v; }
 #else
 VLR_DEV void grp_sync(const WGroup& g) { __syncwarp(g.mask); }
-VLR_DEV double grp_sum_d(double v, const WGroup& g) { // identical bits in every lane of the group
-    if ((g.n & (g.n - 1)) == 0) { // xor butterfly
-        for (int o = g.n >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(g.mask, v, o);
-        return v;
-    }
-    const int base = __ffs(g.mask) - 1; // six lanes (the sextet kernel): every lane adds the six values in lane order
-    double s = 0.0;
-    for (int j = 0; j < g.n; ++j) s += __shfl_sync(g.mask, v, base + j);
-    return s;
+VLR_DEV double grp_sum_d(double v, const WGroup& g) { // xor butterfly: identical bits in every lane of the group
+    for (int o = g.n >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(g.mask, v, o);
+    return v;
 }
-VLR_DEV unsigned grp_bcast_u(unsigned v, const WGroup& g) { return __shfl_sync(g.mask, v, __ffs(g.mask) - 1); }
+VLR_DEV unsigned grp_bcast_u(unsigned v, const WGroup& g) { return __shfl_sync(g.mask, v, 0, g.n); }
 #endif
 
 // ---------------------------------------------------------------------------------------------- closing trapezoid (lane group)

@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(THREADS, VLR_PREP_MIN_CTAS) vlr_wave_coef_kern
         unsigned long long t = 0;
         if (lane_id() == 0) t = atomicAdd(&p.wb.cnt->ticket[3], 1ULL);
         t = __shfl_sync(FULL, t, 0, LANES);
-        if (t >= n_lc) break;
+        if (t >= n_lc) break; // (phasing the CTA's warps like vlr_sets_lc_kernel: -1 % on config 2, -12 % on config 5's depth skew)
         wave_lc_coef(&p.sc, &p.b, p.wp, p.wb, (int)t, p.sub_lo, p.want_be != 0, c, (int)(blockIdx.x * WARPS_PER_CTA) + group_in_cta());
         warp_sync();
     }
@@ -422,9 +422,8 @@ constexpr int RES_THREADS = 64; // two warps: eight octets (36 KB of shared memo
 #ifndef VLR_RES_MIN_CTAS
 #define VLR_RES_MIN_CTAS 6
 #endif
-constexpr int res_groups(int G) { return (RES_THREADS / 32) * (32 / G); } // lc groups per CTA
 constexpr size_t res_smem(int G, int slot_q) {
-    return (size_t)res_groups(G) * (sizeof(vlr_small::ROct) + (size_t)slot_q * vlr_small::R_QW * sizeof(double));
+    return (size_t)(RES_THREADS / G) * (sizeof(vlr_small::ROct) + (size_t)slot_q * vlr_small::R_QW * sizeof(double));
 }
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -433,14 +432,11 @@ template <int G>
 __device__ __forceinline__ void wave_resident_body(const WaveParams& p, const int cls, const int slot_q) {
     using namespace vlr_small;
     const WaveBufs& wb = p.wb;
-    constexpr int GPW = 32 / G;                       // groups per warp: 5 sextets (lanes 30, 31 idle), 4 octets, 1 warp
-    constexpr int GROUPS = (RES_THREADS / 32) * GPW;  // per CTA
+    constexpr int GROUPS = RES_THREADS / G; // per CTA
     const size_t gstride = sizeof(ROct) + (size_t)slot_q * R_QW * sizeof(double);
-    const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool lane_ok = lane < GPW * G;
-    const int gw = lane_ok ? lane / G : GPW - 1, gbase = gw * G, gi = warp * GPW + gw, lg = lane - gbase;
+    const int tid = (int)threadIdx.x, lane = tid & 31, gi = tid / G, lg = tid % G;
     ROct& oc = *reinterpret_cast<ROct*>(vlr_smem + (size_t)gi * gstride);
-    const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << gbase);
+    const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
     WGroup grp;
     grp.lane = lg;
     grp.n = G;
@@ -453,20 +449,20 @@ __device__ __forceinline__ void wave_resident_body(const WaveParams& p, const in
     const int* rlist = wb.rlist + (size_t)(cls - 1) * wb.lc_cap;
     const unsigned n_list = min(wb.cnt->rlist_total[cls - 1], (unsigned)wb.lc_cap);
     const unsigned bar = smem_u32(&oc.bar);
-    if (lane_ok && lg == 0) {
+    if (lg == 0) {
         oc.q = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(&oc) + sizeof(ROct));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
     unsigned parity = 0;
-    bool have = false, more = lane_ok; // more: the list may still hold an lc for this group
+    bool have = false, more = true; // more: the list may still hold an lc for this group
     int round = 0, cnt = 0;
     for (;;) {
         if (!have && more) {
             unsigned long long t = 0;
             if (lg == 0) t = atomicAdd(&wb.cnt->ticket[4 + cls - 1], 1ULL);
-            t = __shfl_sync(gmask, t, gbase);
+            t = __shfl_sync(gmask, t, 0, G);
             more = t < (unsigned long long)n_list;
             const int lci = more ? rlist[t] : -1;
             if (lci >= 0) { // (a negative entry: the list's bookkeeping left a hole; take the next ticket)
@@ -509,23 +505,17 @@ __device__ __forceinline__ void wave_resident_body(const WaveParams& p, const in
         if (!__any_sync(0xffffffffu, have || more)) break;
         __syncwarp();
         {
-            // lanes per task: a function of the group width and the lc's task count alone (bitwise reproducible
-            // results). A sextet runs up to three tasks on two lanes each, up to six on one; more take a second pass.
-            const int H = G == 6 ? (cnt <= 3 ? 2 : 1) : (cnt <= 1 ? G : (cnt <= 2 ? G / 2 : (cnt <= 4 ? G / 4 : G / 8)));
-            const int per_pass = G / H;
-            for (int pass = 0;; ++pass) {
-                const int q = lg / H + pass * per_pass;
-                const bool runs = have && lane_ok && lg / H < per_pass && q < cnt;
-                const unsigned wmask = __ballot_sync(0xffffffffu, runs); // the warp's task lanes of this pass
-                if (wmask == 0u) break;
-                if (runs) {
-                    WSplit sp;
-                    sp.H = H;
-                    sp.h = lg & (H - 1);
-                    sp.mask = H == 32 ? 0xffffffffu : (((1u << H) - 1u) << (lane & ~(H - 1)));
-                    r_task(&p.sc, p.wp, wb, oc, q, cnt, rows_x + (size_t)q * W_GCAP, rows_m + (size_t)q * W_GCAP, rows_e + (size_t)q * W_GCAP, sp, wmask);
-                }
-                __syncwarp();
+            // lanes per task: a function of the lc's class and task count alone (bitwise reproducible results)
+            const int H = cnt <= 1 ? G : (cnt <= 2 ? G / 2 : (cnt <= 4 ? G / 4 : G / 8));
+            const int q = lg / H;
+            const bool runs = have && q < cnt;
+            const unsigned wmask = __ballot_sync(0xffffffffu, runs); // the warp's task lanes of this round
+            if (runs) {
+                WSplit sp;
+                sp.H = H;
+                sp.h = lg & (H - 1);
+                sp.mask = H == 32 ? 0xffffffffu : (((1u << H) - 1u) << (lane & ~(H - 1)));
+                r_task(&p.sc, p.wp, wb, oc, q, cnt, rows_x + (size_t)q * W_GCAP, rows_m + (size_t)q * W_GCAP, rows_e + (size_t)q * W_GCAP, sp, wmask);
             }
         }
         __syncwarp();
@@ -538,11 +528,8 @@ __device__ __forceinline__ void wave_resident_body(const WaveParams& p, const in
     }
 }
 
-#ifndef VLR_RES_GROUP
-#define VLR_RES_GROUP 6 // lanes per lc of the class-1 kernel: 6 (five lcs per warp) or 8 (four)
-#endif
 __global__ void __launch_bounds__(RES_THREADS, VLR_RES_MIN_CTAS) vlr_wave_resident_kernel(const __grid_constant__ WaveParams p) {
-    wave_resident_body<VLR_RES_GROUP>(p, 1, vlr_small::R_SLOT_Q);
+    wave_resident_body<8>(p, 1, vlr_small::R_SLOT_Q);
 }
 // size classes 2..4 (`cls`): a warp per lc, `slot_q` polynomials per slot
 __global__ void __launch_bounds__(RES_THREADS, 2) vlr_wave_resident_deep_kernel(const __grid_constant__ WaveParams p, int cls, int slot_q) {
@@ -840,7 +827,7 @@ vlr_status_t launch_wave(vlr_ctx* ctx, Slot& sl, const DevBatch& b, const DevRes
     CK(sl.w_coef.ensure(sizeof(double) * (size_t)coef_cap));
     {
         // (the deep kernels have two groups per CTA and fewer CTAs: they share the octet kernel's rows)
-        const size_t n_oct = (size_t)std::max(ctx->wave_grid_res * res_groups(VLR_RES_GROUP),
+        const size_t n_oct = (size_t)std::max(ctx->wave_grid_res * (RES_THREADS / 8),
                                               std::max(ctx->wave_grid_deep[0], std::max(ctx->wave_grid_deep[1], ctx->wave_grid_deep[2])) * (RES_THREADS / 32));
         CK(sl.w_rlist.ensure(sizeof(int) * (size_t)lc_cap * R_CLASSES));
         CK(sl.w_rgx.ensure(sizeof(double) * n_oct * W_MAXT * W_GCAP));
@@ -923,7 +910,7 @@ vlr_status_t launch_wave(vlr_ctx* ctx, Slot& sl, const DevBatch& b, const DevRes
         vlr_wave_lcinit_kernel<<<ctx->n_sms * 4, 256, 0, stream>>>(p);
         vlr_wave_coef_kernel<<<ctx->wave_grid_prep, THREADS, ctx->wave_smem_prep, stream>>>(p);
         if (ctx->resident) {
-            vlr_wave_resident_kernel<<<ctx->wave_grid_res, RES_THREADS, res_smem(VLR_RES_GROUP, R_SLOT_Q), stream>>>(p);
+            vlr_wave_resident_kernel<<<ctx->wave_grid_res, RES_THREADS, res_smem(8, R_SLOT_Q), stream>>>(p);
             if (deep_classes) { // (pileups that deep exist in this batch)
                 const int slot_q[3] = {R_SLOT_QM, R_SLOT_QD, R_SLOT_QL};
                 for (int cls = 2; cls <= R_CLASSES; ++cls)
@@ -1419,10 +1406,10 @@ vlr_status_t vlr_ctx_create(const vlr_scenario_t* scenario, int32_t device, vlr_
         ctx->wave_grid_finish = std::min(std::max(1, n3) * ctx->n_sms, ctx->grid);
         const char* res_env = getenv("VLR_RESIDENT");
         ctx->resident = !(res_env && res_env[0] == '0');
-        CKB(cudaFuncSetAttribute(vlr_wave_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)res_smem(VLR_RES_GROUP, vlr_small::R_SLOT_Q)));
+        CKB(cudaFuncSetAttribute(vlr_wave_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)res_smem(8, vlr_small::R_SLOT_Q)));
         int n4 = 0;
-        CKB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n4, vlr_wave_resident_kernel, RES_THREADS, res_smem(VLR_RES_GROUP, vlr_small::R_SLOT_Q)));
-        if (getenv("VLR_WAVE_DEBUG")) fprintf(stderr, "vlr: class-1 resident kernel: %d CTAs per SM (%d lanes per lc, %zu bytes of shared memory per CTA)\n", n4, VLR_RES_GROUP, res_smem(VLR_RES_GROUP, vlr_small::R_SLOT_Q));
+        CKB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n4, vlr_wave_resident_kernel, RES_THREADS, res_smem(8, vlr_small::R_SLOT_Q)));
+        if (getenv("VLR_WAVE_DEBUG")) fprintf(stderr, "vlr: class-1 resident kernel: %d CTAs per SM (%zu bytes of shared memory per CTA)\n", n4, res_smem(8, vlr_small::R_SLOT_Q));
         if (const char* e = getenv("VLR_RES_CTAS")) { // measurements: fewer CTAs of the octet kernel per SM
             const int v = atoi(e);
             if (v >= 1 && v < n4) n4 = v;
