@@ -48,6 +48,31 @@ def test_depth_skew(engine_call):
     _compare(oracle.call_batch(flat, b, n_threads=4), engine_call(flat, b))
 
 
+def _tn_with_depths(depths, seed):
+    """Tumor-normal SNV loci of the synthetic generator with the given (normal, tumor) depths."""
+    import numpy as np
+    rng = np.random.Generator(np.random.PCG64(seed))
+    depths = np.asarray(depths, dtype=np.int64)
+    n = len(depths)
+    cls = rng.choice(5, size=n, p=[0.3, 0.3, 0.2, 0.1, 0.1])
+    t = np.where(cls == 0, 0.0, np.where(cls == 2, 0.5, np.where(cls == 3, 1.0, rng.uniform(0.05, 0.6, n))))
+    nn = np.where(cls == 2, 0.5, np.where(cls == 3, 1.0, np.where(cls == 4, rng.uniform(0.05, 0.3, n), 0.0)))
+    eff = np.stack([nn, 0.75 * t + 0.25 * nn], axis=1)
+    return Scenario.tumor_normal(purity=0.75), synth._assemble(2, depths, eff, rng, synth._snv_locus_flags(rng, n))
+
+
+def test_resident_size_classes_at_their_boundaries(engine_call):
+    """The lc-resident round kernels serve an lc by the deeper of its two pileups: an octet per lc up to 110 reads,
+    a warp per lc with slots of 104 / 208 / 416 polynomials (about 510 / 1030 / 2070 reads) above, the per-round kernels
+    beyond (engine_resident.cuh: r_class). Depth pairs on both sides of every boundary, shallow against deep in both
+    orders, with allele frequency distributions."""
+    pairs = [(109, 109), (110, 110), (111, 60), (60, 111), (12, 509), (510, 510), (511, 40), (40, 515), (1029, 1030),
+             (1031, 25), (25, 1035), (2069, 2070), (2071, 300), (300, 2075), (10, 10), (2600, 2600)]
+    sc, b = _tn_with_depths(pairs, seed=17)
+    flat = sc.flatten()
+    _compare(oracle.call_batch(flat, b, afd_capacity=64, n_threads=4), engine_call(flat, b, afd_capacity=64))
+
+
 def test_golden_and_real_pileups(engine_call, golden_dir):
     exp = json.load(open(os.path.join(golden_dir, "flamegraph_expected.json")))
     flat = Scenario.from_yaml(exp["scenario_yaml"]).flatten()
