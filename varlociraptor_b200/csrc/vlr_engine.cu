@@ -502,8 +502,12 @@ __device__ __forceinline__ void wave_resident_body(const WaveParams& p, const in
                 round = 0;
             }
         }
+#ifdef VLR_RES_CTA_SYNC // experiment: the CTA's warps enter the task and advance phases together (instruction caches)
+        if (!__syncthreads_or((have || more) ? 1 : 0)) break;
+#else
         if (!__any_sync(0xffffffffu, have || more)) break;
         __syncwarp();
+#endif
         {
             // lanes per task: a function of the lc's class and task count alone (bitwise reproducible results)
             const int H = cnt <= 1 ? G : (cnt <= 2 ? G / 2 : (cnt <= 4 ? G / 4 : G / 8));
@@ -518,7 +522,11 @@ __device__ __forceinline__ void wave_resident_body(const WaveParams& p, const in
                 r_task(&p.sc, p.wp, wb, oc, q, cnt, rows_x + (size_t)q * W_GCAP, rows_m + (size_t)q * W_GCAP, rows_e + (size_t)q * W_GCAP, sp, wmask);
             }
         }
+#ifdef VLR_RES_CTA_SYNC
+        __syncthreads();
+#else
         __syncwarp();
+#endif
         if (have) {
             const int next = r_advance(&p.sc, p.wp, wb, oc, round, cnt, rows_x, rows_m, rows_e, big, p.want_be != 0, grp);
             if (next == 0) have = false;
