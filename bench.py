@@ -5,8 +5,9 @@ oracle on a sample of the same batch (BASELINE.json's metric has both halves).
 One "step" = one pass of the hot path over the whole locus batch.
   value     whole-job loci/s with the batch already resident in HBM (CUDA events on the launch stream)
   e2e       the same metric through the C-ABI with pinned HOST buffers (chunked H2D, kernels and D2H all inside the
-            timed region): `vlr_call_batch_packed` (losslessly encoded columns, widened on the device) as the headline,
-            `vlr_call_batch` (plain f32 columns, 32 bytes per read) beside it as e2e.f32_columns
+            timed region): `vlr_call_batch` (plain f32 columns, 32 bytes per read, nothing prepared outside the timed
+            region) as the headline, `vlr_call_batch_packed` (losslessly encoded columns, widened on the device; the
+            encoding is done once outside the timed region and its time reported) beside it as e2e.packed_columns
   roofline  the bound of this path is the fp64 pipe (SURVEY §8(d)): executed-algorithm flops / measured DFMA peak;
             the HBM view (algorithmic bytes / measured copy bandwidth) is kept beside it
   parity    engine vs oracle on the first loci of the same batch: max |d ln posterior|, MAP mismatches, fraction of loci
@@ -350,6 +351,7 @@ def run_workload(args, D, cfg, loci, steps, warmup, strong, oracle_legs, n_oracl
         eng.call_batch(batch, out=pres)
     torch.cuda.synchronize()
     e2e_plain_s = time.perf_counter() - t0
+    e2e_plain_launches = eng.launches
     # ... and through vlr_call_batch_packed: the same columns in their smallest lossless encoding (vlr_pack_batch, host
     # work of the producer, done once outside the timed region and reported), widened on the device
     t0 = time.perf_counter()
@@ -450,20 +452,25 @@ def run_workload(args, D, cfg, loci, steps, warmup, strong, oracle_legs, n_oracl
                        "parallelism": ("one batch cut into %d contiguous ranges of equal estimated work" % world) if strong
                        else "loci sharded, %d rank(s), every rank its own batch" % world,
                        "l2": "inputs (%.1f GB per step and GPU) are larger than L2" % (abytes / 1e9)},
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(packed_bytes),
+            # headline: plain f32 columns, nothing prepared outside the timed region; beside it the packed entry
+            "e2e": {"value": total_loci * steps / (e2e_plain_ms * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": int(batch.nbytes()),
                     "d2h_bytes_per_step": int(batch.n_loci * (8 * (E + 1) + 8 * S + 8 + 4 * 4)),
-                    "launches_per_step": int(e2e_launches),
-                    "entry": "vlr_call_batch_packed: pinned host columns in their smallest lossless encoding "
-                             "(f32 | f16 | 16-bit dictionary | 8-bit dictionary | constant; exact f32 bit patterns), "
-                             "widened on the device by vlr_unpack_kernel inside the timed region",
-                    "encodings": {k: "%s[%d]" % v if v[1] else v[0] for k, v in packed_enc.items()},
-                    "pack_s_once": pack_s,
-                    "pack_note": "vlr_pack_batch on all host threads, once, outside the timed region (the producer's "
-                                 "job, like filling the f32 columns); synthetic reads draw base qualities and MAPQs "
-                                 "from small tables, real pair-HMM columns would stay f32 (4 bytes)",
-                    "results_bitwise_equal_to_device_entry": e2e_same,
-                    "f32_columns": {"value": total_loci * steps / (e2e_plain_ms * 1e-3), "unit": UNIT,
-                                    "h2d_bytes_per_step": int(batch.nbytes()), "entry": "vlr_call_batch"}},
+                    "launches_per_step": int(e2e_plain_launches),
+                    "entry": "vlr_call_batch: pinned host f32 columns (32 bytes per read), chunked H2D on a copy stream that "
+                             "runs ahead of the kernels, D2H of the result arrays, all inside the timed region",
+                    "packed_columns": {
+                        "value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(packed_bytes),
+                        "launches_per_step": int(e2e_launches),
+                        "entry": "vlr_call_batch_packed: the same columns in their smallest lossless encoding (f32 | f16 | "
+                                 "16-bit dictionary | 8-bit dictionary | constant; exact f32 bit patterns), widened on the "
+                                 "device by vlr_unpack_kernel inside the timed region",
+                        "encodings": {k: "%s[%d]" % v if v[1] else v[0] for k, v in packed_enc.items()},
+                        "pack_s_once": pack_s,
+                        "pack_note": "vlr_pack_batch on all host threads, once, OUTSIDE the timed region (a producer "
+                                     "fills dictionaries while it decodes observation records); synthetic reads draw base "
+                                     "qualities and MAPQs from small tables, real pair-HMM columns would stay f32",
+                        "results_bitwise_equal_to_device_entry": e2e_same}},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "clocks": clocks,
