@@ -1673,7 +1673,7 @@ static vlr_status_t call_batch_host(vlr_ctx_t* ctx, const vlr_packed_batch_t* ba
         // computing, and its kernels (on the stream of chunk k - nbuf / 2) start when the copies are done (ev_ready).
         // The host queues the whole batch without waiting; a buffer that has to grow is freed first, which synchronises.
         const int ncomp = std::max(1, nbuf / 2);
-        cudaStream_t s = ctx->slots[k % ncomp].stream, hs = ctx->copy_stream;
+        cudaStream_t s = ctx->slots[(k % nbuf) % ncomp].stream, hs = ctx->copy_stream; // a slot always computes on the same stream
         st = ensure_workspace(ctx, sl, max_reads, cap > 0);
         if (st != VLR_OK) break;
         if (k >= nbuf) CK(cudaStreamWaitEvent(hs, sl.ev_free, 0));
