@@ -45,6 +45,7 @@ struct Ops { // generic.rs LikelihoodOperands
 struct Art { // bias::Artifacts restricted to "none" or exactly one artifact (bias/mod.rs:131-218)
     int id;  // 0 none; 1 ALB 2 HE 3 SCB 4 RPB 5 ROB_F1R2 6 ROB_F2R1 7 SB_FWD 8 SB_REV
     double forward_rate;
+    double ln_fwd, ln_rev; // ln(forward_rate), ln(1 - forward_rate): computed once per locus (BiasPlan)
     bool has_alt_loci;
 };
 
@@ -305,6 +306,7 @@ struct BiasPlan {
     int surviving[NCFG];   // config ids that pass is_possible && is_informative && is_likely
     int n_surviving;
     double forward_rate;
+    double ln_fwd, ln_rev; // ln(forward_rate), ln(1 - forward_rate)
     bool has_alt_loci;
 };
 
@@ -489,6 +491,8 @@ VLR_DEV_NOINLINE void locus_prepass(Ctx& c_, BiasPlan& plan) {
             sb_informative = true;
         }
     }
+    plan.ln_fwd = m_log(plan.forward_rate);
+    plan.ln_rev = m_log(1.0 - plan.forward_rate);
     plan.has_alt_loci = (g_flags & 1u) != 0;
     // read orientation bias (read_orientation_bias.rs:38-97)
     bool rob_informative = false;
@@ -595,7 +599,7 @@ VLR_DEV_NOINLINE void read_coefficients(Ctx& c_, int s) {
     // most of their arguments repeat: the strand rate is a per-locus constant, MAPQ and prob_hit_base take a handful of
     // values. Same function of the same argument = same bits, so one-entry per-lane memos and the exact special values
     // (exp(0) = 1, exp(-inf) = 0, ln(1 - e^-inf) = -0) change nothing numerically.
-    const double ln_rate_fwd = m_log(a.forward_rate), ln_rate_rev = m_log(1.0 - a.forward_rate);
+    const double ln_rate_fwd = a.ln_fwd, ln_rate_rev = a.ln_rev;
     double memo_pm = NAN, memo_pmis = 0.0, memo_phb = NAN, memo_l1m_phb = 0.0, memo_pdo = NAN, memo_l1m_pdo = 0.0;
     for (int64_t row0 = lo; row0 < hi; row0 += LANES) {
         int64_t row = row0 + lane_id();
@@ -680,9 +684,13 @@ VLR_DEV_NOINLINE void read_coefficients(Ctx& c_, int s) {
             } else if (K == neg_inf()) {
                 dead = true;
             } else {
-                al_ = lnA == K ? 1.0 : (lnA == neg_inf() ? 0.0 : m_exp(lnA - K));
-                be_ = lnR == K ? 1.0 : (lnR == neg_inf() ? 0.0 : m_exp(lnR - K));
-                ga_ = lnC == K ? 1.0 : (lnC == neg_inf() ? 0.0 : m_exp(lnC - K));
+                // two exps for the three terms: the largest is exp(0) = 1, e1 and e2 are the other two (exp(0) = 1 and
+                // exp(-inf) = 0 exactly: the same bits as a guarded call per term, one call site less per read)
+                const bool aK = lnA == K, cK = lnC == K;
+                const double e1 = m_exp((aK ? lnR : lnA) - K), e2 = m_exp((cK ? lnR : lnC) - K);
+                al_ = aK ? 1.0 : e1;
+                be_ = aK ? e1 : (cK ? e2 : 1.0);
+                ga_ = cK ? 1.0 : e2;
                 ksum += K;
             }
             double* o = out + (int64_t)pos * 4;
@@ -2493,6 +2501,8 @@ VLR_DEV void process_locus(const DevScenario* sc, const DevBatch* b, const DevRe
         for (int ci = 0; ci <= plan.n_surviving; ++ci) {
             c.art.id = ci == 0 ? 0 : plan.surviving[ci - 1];
             c.art.forward_rate = plan.forward_rate;
+            c.art.ln_fwd = plan.ln_fwd;
+            c.art.ln_rev = plan.ln_rev;
             c.art.has_alt_loci = plan.has_alt_loci;
             for (int s = 0; s < S; ++s) {
                 c.lc_n[s] = 0;

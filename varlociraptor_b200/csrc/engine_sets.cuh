@@ -33,7 +33,7 @@ struct SetsLocus {
     int n_obs[MAXS], s_one[MAXS], s_gt1[MAXS], coef_off[MAXS];
     int surviving[NCFG];
     int64_t singleton_row;
-    double forward_rate;
+    double forward_rate, ln_fwd, ln_rev;
 };
 
 struct SetsLC { // one (locus, artifact config)
@@ -160,6 +160,8 @@ VLR_DEV void sets_pre_locus(const DevScenario* sc, const DevBatch* b, const Sets
     wl.coef_total = c.coef_total;
     wl.singleton_row = c.singleton_row;
     wl.forward_rate = plan.forward_rate;
+    wl.ln_fwd = plan.ln_fwd;
+    wl.ln_rev = plan.ln_rev;
     int clear = 0;
     for (int s = 0; s < S; ++s) {
         wl.n_obs[s] = c.n_obs[s];
@@ -211,6 +213,8 @@ VLR_DEV void sets_lc(const DevScenario* sc, const DevBatch* b, const SetsPlan& s
     c.n_pileup_evals = 0;
     c.art.id = ci == 0 ? 0 : wl.surviving[ci - 1];
     c.art.forward_rate = wl.forward_rate;
+    c.art.ln_fwd = wl.ln_fwd;
+    c.art.ln_rev = wl.ln_rev;
     c.art.has_alt_loci = wl.has_alt_loci != 0;
     c.coef = coef;
     c.coef_in_sm = 1;

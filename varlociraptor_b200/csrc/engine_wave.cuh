@@ -86,7 +86,7 @@ struct WaveLocus {
     int n_obs[2], s_one[2], coef_off[2];
     int surviving[NCFG];
     int64_t coef_base, singleton_row;
-    double forward_rate;
+    double forward_rate, ln_fwd, ln_rev;
     double pa, pb;                    // limits of the outer (root Range) integration
     double ev_a[MAXE], ev_b[MAXE];    // limits of the leaf integration per event
     int8_t ev_kind[MAXE];             // 0 pruned, 1 leaf task under a discrete parent, 2 point, 3 outer
@@ -901,6 +901,8 @@ VLR_DEV void wave_pre_locus(const DevScenario* sc, const DevBatch* b, const Wave
     wl.lc_doubles = lc_doubles;
     wl.singleton_row = c.singleton_row;
     wl.forward_rate = plan.forward_rate;
+    wl.ln_fwd = plan.ln_fwd;
+    wl.ln_rev = plan.ln_rev;
     wl.has_alt_loci = plan.has_alt_loci ? 1 : 0;
     for (int k = 0; k < NCFG; ++k) wl.surviving[k] = k < plan.n_surviving ? plan.surviving[k] : 0;
     for (int s = 0; s < 2; ++s) {
@@ -1021,6 +1023,8 @@ VLR_DEV void wave_lc_coef(const DevScenario* sc, const DevBatch* b, const WavePl
     c.n_pileup_evals = 0;
     c.art.id = ci == 0 ? 0 : wl.surviving[ci - 1];
     c.art.forward_rate = wl.forward_rate;
+    c.art.ln_fwd = wl.ln_fwd;
+    c.art.ln_rev = wl.ln_rev;
     c.art.has_alt_loci = wl.has_alt_loci != 0;
     // resident lcs: per-read coefficients into the warp's scratch (the point events below evaluate them there), then
     // multiplied out into the arena's pileup polynomials; other lcs: per-read coefficients straight into the arena
