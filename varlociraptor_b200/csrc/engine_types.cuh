@@ -448,7 +448,7 @@ VLR_DEV_NOINLINE Range range_intersect(const Range& a, const Range& o) {
 VLR_DEV_NOINLINE double range_observable_max(const Range& r, int n) { // formula.rs:1202-1224
     if (n < 10 || !((double)n * (r.end - r.start) > 1.0)) return r.end;
     double c = (double)n * r.end;
-    if (r.rex && fmod(c, 1.0) == 0.0) c -= 1.0;
+    if (r.rex && c == floor(c)) c -= 1.0; // (c % 1.0 == 0.0 of the reference: c is a whole number; fmod is a loop on the device)
     c = floor(c);
     if (c == 0.0) return r.end;
     return c / (double)n;
@@ -459,7 +459,7 @@ VLR_DEV_NOINLINE double range_observable_min(const Range& r, int n) { // formula
         min_vaf = r.start;
     } else {
         double c = (double)n * r.start;
-        if (r.lex && fmod(c, 1.0) == 0.0) {
+        if (r.lex && c == floor(c)) {
             double adjusted_end = range_observable_max(r, n);
             double s1 = ceil(c + 1.0) / (double)n;
             if (s1 <= 1.0 && s1 <= adjusted_end) return s1;
