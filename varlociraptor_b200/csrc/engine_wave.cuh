@@ -737,8 +737,9 @@ VLR_DEV_NOINLINE void wave_lc_advance(const WavePlan& wp, const WaveBufs& wb, in
 constexpr int W_BINS = 64;          // 8 x 8 cost bins
 constexpr int W_KEYS = 2 * W_BINS;  // lcs with an outer integration, then the single-round ones (WaveCounters::rkey_n)
 VLR_DEV int wave_share_bin(int n_alt, int n) { // share of the pileup's reads that do not favour the reference
-    const int pct = n > 0 ? (100 * n_alt) / n : 0;
-    return pct < 1 ? 0 : (pct < 3 ? 1 : (pct < 8 ? 2 : (pct < 20 ? 3 : (pct < 40 ? 4 : (pct < 70 ? 5 : 6)))));
+    const long long a = 100LL * n_alt, m = n; // floor(100 n_alt / n) < k  <=>  100 n_alt < k n: no division
+    if (n <= 0 || a < m) return 0;
+    return a < 3 * m ? 1 : (a < 8 * m ? 2 : (a < 20 * m ? 3 : (a < 40 * m ? 4 : (a < 70 * m ? 5 : 6))));
 }
 // Tasks of round 0 of config `ci` of a locus, and whether an outer integration is among them (artifact configs only
 // evaluate the events that have a twin).
