@@ -370,11 +370,12 @@ def run_workload(args, D, cfg, loci, steps, warmup, strong, oracle_legs, n_oracl
     packed.close()
 
     t = torch.tensor([ms_total, e2e_s * 1e3, kernel_ms, e2e_plain_s * 1e3], dtype=torch.float64, device=device)
-    busy = [kernel_ms]
+    busy, e2e_rank_ms = [kernel_ms], [e2e_plain_s * 1e3 / steps]
     if world > 1:
-        allk = [torch.zeros(1, dtype=torch.float64, device=device) for _ in range(world)]
-        dist.all_gather(allk, t[2:3].clone())
-        busy = [float(x[0]) for x in allk]
+        allk = [torch.zeros(4, dtype=torch.float64, device=device) for _ in range(world)]
+        dist.all_gather(allk, t.clone())
+        busy = [float(x[2]) for x in allk]
+        e2e_rank_ms = [float(x[3]) / steps for x in allk]  # host-entry step of every rank: host memory placement shows here
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, e2e_ms, e2e_plain_ms = float(t[0]), float(t[1]), float(t[3])
     got = dres.to_host()
@@ -479,6 +480,7 @@ def run_workload(args, D, cfg, loci, steps, warmup, strong, oracle_legs, n_oracl
         if world > 1:
             out["rank_busy_ms"] = busy
             out["rank_busy_spread"] = (max(busy) - min(busy)) / max(busy) if max(busy) > 0 else 0.0
+            out["e2e"]["rank_ms_per_step"] = e2e_rank_ms
         if shard_info:
             out["sharding"] = shard_info
         if oracle_legs:
@@ -523,7 +525,7 @@ def main():
     if not args.no_also and cfg == 2:
         extra = []
         if D.world == 1:  # the other single-GPU configs, short
-            extra = [(3, 250_000, False, 20_000), (5, 100_000, False, 400)]
+            extra = [(3, 1_000_000, False, 20_000), (5, 100_000, False, 400)]  # config 3 at BASELINE's full size
         else:  # the strong-scaling configs of BASELINE.json (config 4 is defined at 8 GPUs)
             extra = [(5, STRONG_TOTAL[5], True, 0)] + ([(4, STRONG_TOTAL[4], True, 0)] if D.world == 8 else [])
         also = []

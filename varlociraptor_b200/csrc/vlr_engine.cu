@@ -11,7 +11,13 @@
 #include <cuda_pipeline.h>
 #include <cuda_runtime.h>
 
+#ifdef __linux__
+#include <sys/syscall.h>
+#include <unistd.h>
+#endif
+
 #include <algorithm>
+#include <cctype>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -1304,9 +1310,51 @@ vlr_status_t vlr_contamination_posterior(int32_t device, const vlr_contamination
     return done(e == cudaSuccess ? VLR_OK : VLR_ERR_CUDA);
 }
 
+// NUMA node the current device hangs off (/sys/bus/pci/devices/<bus id>/numa_node), -1 when unknown.
+static int device_numa_node() {
+    int dev = 0;
+    char bus[32] = {0};
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetPCIBusId(bus, (int)sizeof bus, dev) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    for (char* c = bus; *c; ++c) *c = (char)tolower((unsigned char)*c);
+    char path[96];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    int node = -1;
+    if (FILE* f = fopen(path, "r")) {
+        if (fscanf(f, "%d", &node) != 1) node = -1;
+        fclose(f);
+    }
+    return node;
+}
+
+// The pages of a pinned buffer are placed by the calling thread's memory policy when cudaHostAlloc faults them in. On a
+// two-socket host with eight GPUs the default (the node the thread happens to run on) sends the copy engines of half
+// the GPUs across the socket interconnect, which then bounds the host entries of ALL ranks of a job. Prefer the node
+// of the current device for the duration of the allocation (MPOL_PREFERRED: falls back to other nodes when that one is
+// full; a refused syscall - seccomp, no CAP_SYS_NICE - leaves the default placement). VLR_NUMA=0 switches it off.
 void* vlr_host_alloc(size_t bytes) {
     void* p = nullptr;
-    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+    bool policy_set = false;
+#ifdef __linux__
+    int old_mode = 0;
+    unsigned long old_mask[16] = {0};
+    const char* env = getenv("VLR_NUMA");
+    const int node = (env && env[0] == '0') ? -1 : device_numa_node();
+    if (node >= 0 && node < (int)(sizeof old_mask * 8) &&
+        syscall(SYS_get_mempolicy, &old_mode, old_mask, sizeof old_mask * 8, nullptr, 0UL) == 0) {
+        unsigned long mask[16] = {0};
+        mask[node / (8 * sizeof(unsigned long))] = 1UL << (node % (8 * sizeof(unsigned long)));
+        policy_set = syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, mask, sizeof mask * 8) == 0;
+        if (getenv("VLR_NUMA_DEBUG")) fprintf(stderr, "vlr_host_alloc: %zu bytes, device node %d, policy %s\n", bytes, node, policy_set ? "set" : "refused");
+    }
+#endif
+    const cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault);
+#ifdef __linux__
+    if (policy_set) syscall(SYS_set_mempolicy, old_mode, old_mode == 0 ? nullptr : old_mask, old_mode == 0 ? 0UL : sizeof old_mask * 8);
+#endif
+    if (e != cudaSuccess) {
         cudaGetLastError();
         return nullptr;
     }
