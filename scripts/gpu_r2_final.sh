@@ -6,7 +6,7 @@ mkdir -p gpurun_out
   VLR_NUMA_DEBUG=1 python -c "from varlociraptor_b200 import engine; import numpy as np; a = engine.pinned_empty(1 << 20, np.float32); print('pinned ok', a.nbytes)"; } > gpurun_out/r2f_numa.log 2>&1
 tail -4 gpurun_out/r2f_numa.log
 for tool in memcheck synccheck; do
-  timeout 400 compute-sanitizer --tool $tool --error-exitcode 9 python scripts/sanitize_r2.py > gpurun_out/r2f_$tool.log 2>&1
+  timeout 240 compute-sanitizer --tool $tool --error-exitcode 9 python scripts/sanitize_r2.py > gpurun_out/r2f_$tool.log 2>&1
   echo "$tool rc=$?"; grep -E "ERROR SUMMARY|bitwise" gpurun_out/r2f_$tool.log | tail -4
 done
 timeout 900 python -m pytest tests -q -m gpu -x > gpurun_out/r2f_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r2f_pytest_gpu.log
