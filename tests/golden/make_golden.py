@@ -93,8 +93,27 @@ def real_pileups():
             continue
         with open(scen) as f:
             scenario = f.read()
+        # the expectations the reference's own test of this testcase checks on the call (testcase.yaml `expected:`,
+        # evaluated by src/testcase/runner/common/mod.rs:330-395), verbatim with the comments next to them
+        import yaml
+        with open(os.path.join(root, name, "testcase.yaml")) as f:
+            text = f.read()
+        tc_yaml = yaml.safe_load(text)
+        expected = tc_yaml.get("expected") or {}
+        exp_lines = []
+        for line in text.split("\n"):
+            if line.startswith("expected:"):
+                exp_lines = [line]
+            elif exp_lines and (line.startswith(" ") or line.startswith("#")):
+                exp_lines.append(line)
+            elif exp_lines:
+                break
         batches.append(b)
         meta.append({"testcase": name, "n_loci": b.n_loci, "n_reads": b.n_reads,
+                     "expected": {"allelefreqs": expected.get("allelefreqs") or [],
+                                  "posteriors": expected.get("posteriors") or [],
+                                  "omit": sorted(k for k, v in tc_yaml.items() if k.startswith("omit_") and v),
+                                  "yaml_text": "\n".join(exp_lines)},
                      "records": [{"chrom": r["chrom"], "pos": r["pos"], "ref": r["ref"], "alt": r["alt"]}
                                  for r in recs], "scenario_yaml": scenario})
         print("%s: %d loci, %d reads" % (name, b.n_loci, b.n_reads))
