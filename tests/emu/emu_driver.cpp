@@ -288,7 +288,9 @@ extern "C" int32_t vlr_emu_sets_call_batch(const vlr_scenario_t* sc, const vlr_b
     std::vector<double> arena((size_t)4 * SETS_SM_READS + SETS_MAXF);
     for (int64_t i = 0; i < L; ++i) sets_pre_locus(&ds, &db, sb, i, (int)i, want_be, *c);
     const int n_lc = (int)std::min<unsigned>(cnt.n_lc, (unsigned)lc_cap);
-    for (int k = 0; k < n_lc; ++k) sets_lc(&ds, &db, sp, sb, k, 0, want_be, *c, arena.data(), arena.data() + 4 * SETS_SM_READS);
+    static MemoTab memo; // the table path of read_coefficients (cleared per call like the kernel does per launch)
+    memo_clear(&memo);
+    for (int k = 0; k < n_lc; ++k) sets_lc(&ds, &db, sp, sb, k, 0, want_be, *c, arena.data(), arena.data() + 4 * SETS_SM_READS, false, &memo);
     for (int64_t i = 0; i < L; ++i) sets_finish_locus(&ds, &db, &dr, sp, sb, ws, i, (int)i, *c);
     std::vector<double> coef2((size_t)max_reads * 4);
     std::vector<double> be2((size_t)BE_CAP * (2 + S));

@@ -585,7 +585,33 @@ VLR_DEV_NOINLINE void locus_prepass(Ctx& c_, BiasPlan& plan) {
 //   ln beta'  = prob_mapping + prob_ref + bias.prob_ref      (likelihood.rs:215)
 //   ln gamma' = prob_mismapping + prob_missed_allele + bias.prob_any   (likelihood.rs:186-188)
 //   K_r = max of the three; x = effective alt-sampling probability (likelihood.rs:43-53, :98-103).
-VLR_DEV_NOINLINE void read_coefficients(Ctx& c_, int s) {
+// Per-warp table of ln(1 - e^{prob_mapping}) keyed by the f32 bits of prob_mapping (read_observation.rs:283-286): MAPQs
+// come from a dictionary of a few dozen values, but 32 lanes with one-entry memos miss somewhere in almost every
+// iteration (5 % of the reads differ from their lane's previous one), and a warp pays for ln_one_minus_exp (an expm1 or
+// an exp, and a log) whenever ONE lane needs it. Direct mapped, filled by the warp itself at converged points only
+// (one elected lane per slot writes value and key: entries are never torn), read in between: same function of the same
+// argument, so the coefficients are bitwise what they were. The kernel that owns the table clears it (memo_clear).
+struct MemoTab {
+    static constexpr int N = 128;
+    uint32_t k[N];
+    double v[N];
+};
+constexpr uint32_t MEMO_EMPTY = 0xffffffffu; // a NaN pattern: never a key (NaNs bypass the table)
+VLR_DEV void memo_clear(MemoTab* t) { // warp cooperative
+    for (int i = lane_id(); i < MemoTab::N; i += LANES) t->k[i] = MEMO_EMPTY;
+    warp_sync();
+}
+VLR_DEV uint32_t memo_bits(float f) {
+#ifdef VLR_HOST_EMU
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    return u;
+#else
+    return __float_as_uint(f);
+#endif
+}
+
+VLR_DEV_NOINLINE void read_coefficients(Ctx& c_, int s, MemoTab* tab = nullptr) {
     Ctx& c = warp_ctx(c_);
     const DevBatch* b = c.b;
     const int S = c.sc->S;
@@ -610,6 +636,8 @@ VLR_DEV_NOINLINE void read_coefficients(Ctx& c_, int s) {
             r = load_read(b, row);
             kept = rd_kept(c.lf, r.f);
         }
+        bool memo_miss = false; // this lane computed a value the table does not hold yet
+        uint32_t memo_h = 0, memo_key = 0;
 #ifdef VLR_HOST_EMU
         int pos = base;
         int n_kept = kept ? 1 : 0;
@@ -671,7 +699,16 @@ VLR_DEV_NOINLINE void read_coefficients(Ctx& c_, int s) {
             double bAny = LN_05 + LN_05 + rpb_any + 0.0 + 0.0 + LN_05;
             if (r.pm != memo_pm) {
                 memo_pm = r.pm;
-                memo_pmis = ln_one_minus_exp(r.pm);
+                const float pf = (float)r.pm;
+                const bool tabbed = tab != nullptr && (double)pf == r.pm; // (the column is f32: always, unless NaN)
+                memo_key = memo_bits(pf);
+                memo_h = (memo_key * 0x9E3779B1u) >> 25;
+                if (tabbed && tab->k[memo_h] == memo_key) {
+                    memo_pmis = tab->v[memo_h];
+                } else {
+                    memo_pmis = ln_one_minus_exp(r.pm);
+                    memo_miss = tabbed;
+                }
             }
             const double pmis = memo_pmis; // read_observation.rs:283-286
             double lnA = r.pm + (bA + pa);
@@ -698,6 +735,23 @@ VLR_DEV_NOINLINE void read_coefficients(Ctx& c_, int s) {
             o[1] = be_;
             o[2] = ga_;
             o[3] = r.psa == 0.0 ? -0.0 : -m_expm1(r.psa); // u_r = 1 - s_r, s_r = e^{prob_sample_alt}: 0 when prob_sample_alt = 0
+        }
+        if (tab != nullptr) { // the warp is converged here: new values go into the table, one writer per slot
+#ifdef VLR_HOST_EMU
+            if (memo_miss) {
+                tab->v[memo_h] = memo_pmis;
+                tab->k[memo_h] = memo_key;
+            }
+#else
+            if (w_any(memo_miss)) {
+                const unsigned grp = __match_any_sync(FULL, memo_miss ? memo_h : MEMO_EMPTY);
+                if (memo_miss && (int)(threadIdx.x & 31u) == __ffs(grp) - 1) {
+                    tab->v[memo_h] = memo_pmis;
+                    tab->k[memo_h] = memo_key;
+                }
+                warp_sync();
+            }
+#endif
         }
         base += n_kept;
     }

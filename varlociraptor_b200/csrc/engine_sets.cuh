@@ -192,7 +192,7 @@ VLR_DEV void sets_phase_sync() {}
 VLR_DEV void sets_phase_sync() { __syncthreads(); }
 #endif
 VLR_DEV void sets_lc(const DevScenario* sc, const DevBatch* b, const SetsPlan& sp, const SetsBufs& sb, int lci, int64_t sub_lo,
-                     bool want_be, Ctx& c, double* coef, double* ll, bool phased = false) {
+                     bool want_be, Ctx& c, double* coef, double* ll, bool phased = false, MemoTab* memo = nullptr) {
     const bool live = lci >= 0 && sb.lcs[lci].li >= 0; // (li < 0: dead)
     SetsLC& lc = sb.lcs[live ? lci : 0];
     const int li = live ? lc.li : 0, ci = lc.ci;
@@ -228,7 +228,7 @@ VLR_DEV void sets_lc(const DevScenario* sc, const DevBatch* b, const SetsPlan& s
     }
     warp_sync();
     if (!sets_prior_ready(sp, c.vartype)) sets_fill_prior(c, sp, c.vartype);
-    for (int s = 0; s < S; ++s) read_coefficients(c, s);
+    for (int s = 0; s < S; ++s) read_coefficients(c, s, memo);
     }
     if (phased) sets_phase_sync();
     // ---- folds: the pileup ln-likelihoods the leaves look up

@@ -1009,7 +1009,7 @@ VLR_DEV int wave_lc_init(const DevScenario* sc, const WavePlan& wp, const WaveBu
 // One warp per lc: the per-read coefficients of both samples under the lc's artifact config, and the point events
 // (both nodes a single VAF, e.g. the absent event): one joint evaluation each, like joint() of the generic engine.
 VLR_DEV void wave_lc_coef(const DevScenario* sc, const DevBatch* b, const WavePlan& wp, const WaveBufs& wb, int lci,
-                          int64_t sub_lo, bool want_be, Ctx& c, int warp_global) {
+                          int64_t sub_lo, bool want_be, Ctx& c, int warp_global, MemoTab* memo = nullptr) {
     WaveLC& lc = wb.lcs[lci];
     const int li = lc.li, ci = lc.ci;
     if (li < 0) return; // dead
@@ -1041,7 +1041,7 @@ VLR_DEV void wave_lc_coef(const DevScenario* sc, const DevBatch* b, const WavePl
         c.coef_off[s] = wl.coef_off[s];
     }
     warp_sync();
-    for (int s = 0; s < 2; ++s) read_coefficients(c, s);
+    for (int s = 0; s < 2; ++s) read_coefficients(c, s, memo);
     double* be = want_be ? wb.be + (size_t)li * BE_CAP * 4 : nullptr;
     uint32_t n_base = 0;
     for (int e = 0; e < E; ++e) {

@@ -157,6 +157,8 @@ __global__ void __launch_bounds__(256) vlr_wave_lcinit_kernel(const __grid_const
 __global__ void __launch_bounds__(THREADS, VLR_PREP_MIN_CTAS) vlr_wave_coef_kernel(const __grid_constant__ WaveParams p) {
     using namespace vlr_small;
     Ctx& c = *reinterpret_cast<Ctx*>(vlr_smem + (size_t)group_in_cta() * CTX_STRIDE);
+    // (no MemoTab here, unlike vlr_sets_lc_kernel: measured -3 % on configs 2 and 5 - its 12 KB of shared memory per CTA
+    // are taken from the resident kernels of the other sub-chunks that share the SM)
     const unsigned long long n_lc = min(p.wb.cnt->n_lc, (unsigned)p.wb.lc_cap);
     for (;;) {
         unsigned long long t = 0;
@@ -597,6 +599,9 @@ __global__ void __launch_bounds__(THREADS, 2) vlr_sets_lc_kernel(const __grid_co
     Ctx& c = *reinterpret_cast<Ctx*>(vlr_smem + (size_t)group_in_cta() * CTX_LEAN);
     double* arena = reinterpret_cast<double*>(vlr_smem + (size_t)WARPS_PER_CTA * CTX_LEAN) +
                     (size_t)group_in_cta() * (4 * SETS_SM_READS + SETS_MAXF);
+    __shared__ MemoTab memo_tabs[WARPS_PER_CTA]; // ln(1 - e^{prob_mapping}) per MAPQ value, one table per warp (read_coefficients)
+    MemoTab* const memo = &memo_tabs[group_in_cta()];
+    memo_clear(memo);
     const unsigned long long n_lc = min(p.sb.cnt->n_lc, (unsigned)p.sb.lc_cap);
     for (;;) { // the CTA's warps take one lc each and go through its phases together (sets_lc)
         unsigned long long t = 0;
@@ -604,7 +609,7 @@ __global__ void __launch_bounds__(THREADS, 2) vlr_sets_lc_kernel(const __grid_co
         t = __shfl_sync(FULL, t, 0, LANES);
         const bool mine = t < n_lc;
         if (!__syncthreads_or(mine ? 1 : 0)) break;
-        sets_lc(&p.sc, &p.b, p.sp, p.sb, mine ? (int)t : -1, p.sub_lo, p.want_be != 0, c, arena, arena + 4 * SETS_SM_READS, true);
+        sets_lc(&p.sc, &p.b, p.sp, p.sb, mine ? (int)t : -1, p.sub_lo, p.want_be != 0, c, arena, arena + 4 * SETS_SM_READS, true, memo);
         warp_sync();
     }
 }
