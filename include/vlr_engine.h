@@ -295,7 +295,9 @@ vlr_status_t vlr_call_batch_device(vlr_ctx_t* ctx, const vlr_batch_t* batch, vlr
 vlr_status_t vlr_ctx_reserve(vlr_ctx_t* ctx, int64_t max_reads_per_locus);
 
 /* Page-locked host memory for batch columns and result arrays: vlr_call_batch() overlaps its chunked host<->device
- * copies with compute only when the caller's buffers are pinned (pageable memory still works, staged by the driver). */
+ * copies with compute only when the caller's buffers are pinned (pageable memory still works, staged by the driver).
+ * The pages are placed on the NUMA node of the CURRENT CUDA device when the host exposes it (call cudaSetDevice /
+ * create the context first; VLR_NUMA=0 keeps the default placement). */
 void* vlr_host_alloc(size_t bytes);
 void vlr_host_free(void* p);
 
