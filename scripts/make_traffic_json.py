@@ -11,6 +11,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1] if len(sys.argv) > 1 else "r2f"
 for cfg, name, loci in ((2, "wave", 65536), (3, "cfg3", 65536), (5, "cfg5", 16384)):
     src = "profiles/traffic_%s_cfg%d.csv" % (tag, cfg)
+    if not os.path.exists(os.path.join(ROOT, src)):
+        continue
     rows = [r for r in csv.reader(open(os.path.join(ROOT, src))) if len(r) > 10]
     hdr = rows[0]
     ki, mi, vi, idi = (hdr.index(k) for k in ("Kernel Name", "Metric Name", "Metric Value", "ID"))
