@@ -116,7 +116,9 @@ constexpr size_t WAVE_ROUND_SMEM = (size_t)vlr_small::W_GROUP * vlr_small::W_SLO
 // prep, split in three so that each kernel's text fits the instruction caches (engine_wave.cuh "prep")
 __global__ void __launch_bounds__(THREADS, VLR_PREP_MIN_CTAS) vlr_wave_pre_kernel(const __grid_constant__ WaveParams p) {
     using namespace vlr_small;
-    Ctx& c = *reinterpret_cast<Ctx*>(vlr_smem + (size_t)group_in_cta() * CTX_STRIDE);
+    // (lean context: the pre-pass, the coefficients, a pileup evaluation and locus_tail never touch the tree walk's state;
+    // 2.6 instead of 7.7 KB of shared memory per warp leave the SM's shared memory to the resident kernels next to them)
+    Ctx& c = *reinterpret_cast<Ctx*>(vlr_smem + (size_t)group_in_cta() * CTX_LEAN);
     for (;;) {
         unsigned long long t = 0;
         if (lane_id() == 0) t = atomicAdd(&p.wb.cnt->ticket[0], 1ULL);
@@ -156,16 +158,21 @@ __global__ void __launch_bounds__(256) vlr_wave_lcinit_kernel(const __grid_const
 
 __global__ void __launch_bounds__(THREADS, VLR_PREP_MIN_CTAS) vlr_wave_coef_kernel(const __grid_constant__ WaveParams p) {
     using namespace vlr_small;
-    Ctx& c = *reinterpret_cast<Ctx*>(vlr_smem + (size_t)group_in_cta() * CTX_STRIDE);
-    // (no MemoTab here, unlike vlr_sets_lc_kernel: measured -3 % on configs 2 and 5 - its 12 KB of shared memory per CTA
-    // are taken from the resident kernels of the other sub-chunks that share the SM)
+    Ctx& c = *reinterpret_cast<Ctx*>(vlr_smem + (size_t)group_in_cta() * CTX_LEAN);
+#ifdef VLR_COEF_MEMO // experiment: the MAPQ table of vlr_sets_lc_kernel here too - measured neutral (7.199 against 7.194 M loci/s)
+    __shared__ MemoTab memo_tabs[WARPS_PER_CTA];
+    MemoTab* const memo = &memo_tabs[group_in_cta()];
+    memo_clear(memo);
+#else
+    MemoTab* const memo = nullptr;
+#endif
     const unsigned long long n_lc = min(p.wb.cnt->n_lc, (unsigned)p.wb.lc_cap);
     for (;;) {
         unsigned long long t = 0;
         if (lane_id() == 0) t = atomicAdd(&p.wb.cnt->ticket[3], 1ULL);
         t = __shfl_sync(FULL, t, 0, LANES);
         if (t >= n_lc) break; // (phasing the CTA's warps like vlr_sets_lc_kernel: -1 % on config 2, -12 % on config 5's depth skew)
-        wave_lc_coef(&p.sc, &p.b, p.wp, p.wb, (int)t, p.sub_lo, p.want_be != 0, c, (int)(blockIdx.x * WARPS_PER_CTA) + group_in_cta());
+        wave_lc_coef(&p.sc, &p.b, p.wp, p.wb, (int)t, p.sub_lo, p.want_be != 0, c, (int)(blockIdx.x * WARPS_PER_CTA) + group_in_cta(), memo);
         warp_sync();
     }
 }
@@ -552,9 +559,12 @@ __global__ void __launch_bounds__(RES_THREADS, 2) vlr_wave_resident_deep_kernel(
     wave_resident_body<32>(p, cls, slot_q);
 }
 
-__global__ void __launch_bounds__(THREADS, 2) vlr_wave_finish_kernel(const __grid_constant__ WaveParams p) {
+#ifndef VLR_FIN_MIN_CTAS
+#define VLR_FIN_MIN_CTAS 3 // (80 registers, no spills; 2 -> 3 CTAs per SM: +0.6 % on config 2)
+#endif
+__global__ void __launch_bounds__(THREADS, VLR_FIN_MIN_CTAS) vlr_wave_finish_kernel(const __grid_constant__ WaveParams p) {
     using namespace vlr_small;
-    Ctx& c = *reinterpret_cast<Ctx*>(vlr_smem + (size_t)group_in_cta() * CTX_STRIDE);
+    Ctx& c = *reinterpret_cast<Ctx*>(vlr_smem + (size_t)group_in_cta() * CTX_LEAN);
     WarpWs* ws = p.ws + (blockIdx.x * WARPS_PER_CTA + group_in_cta());
     for (;;) {
         unsigned long long t = 0;
@@ -825,12 +835,16 @@ vlr_status_t launch_wave(vlr_ctx* ctx, Slot& sl, const DevBatch& b, const DevRes
                          int64_t locus_begin, int64_t locus_end) {
     using namespace vlr_small;
     const bool want_be = r.afd_capacity > 0;
-    // sub-chunk: <= 65536 loci (8192 with an AFD: the base-event log is 128 KB per locus) and <= ~16M reads, so that
-    // deep batches keep the workspace bounded; arena and lc table sized for 6 artifact configs per locus on average
-    // (config 2 has 2.2, the depth-skewed config 5 ~4); what does not fit is deferred to the generic engine, never lost
+    // sub-chunk: <= 131072 loci (8192 with an AFD: the base-event log is 128 KB per locus) and <= ~32M reads, so that
+    // deep batches keep the workspace bounded, and no more than the range holds; arena and lc table sized for 6
+    // artifact configs per locus on average (config 2 has 2.2, the depth-skewed config 5 ~4); what does not fit is
+    // deferred to the generic engine, never lost. Measured on 1 M config-2 loci (three streams): sub-chunks of 65 536
+    // loci 7.04, 131 072: 7.30, 262 144 (four streams, 94 GB of workspace): 7.44 M loci/s - every sub-chunk ends in a
+    // tail of straggling lcs; config 5 (100 k loci): 5 592 loci per sub-chunk 1.35, 11 184: 1.51, 22 368: 1.51.
     if (avg_reads < 16) avg_reads = 16;
-    int n_sub_cap = want_be ? 8192 : 65536;
-    n_sub_cap = (int)std::min<int64_t>(n_sub_cap, std::max<int64_t>(4096, ((int64_t)1 << 24) / avg_reads));
+    int n_sub_cap = want_be ? 8192 : 131072;
+    n_sub_cap = (int)std::min<int64_t>(n_sub_cap, std::max<int64_t>(4096, ((int64_t)1 << 25) / avg_reads));
+    n_sub_cap = (int)std::min<int64_t>(n_sub_cap, std::max<int64_t>(4096, locus_end - locus_begin));
     if (const char* e = getenv("VLR_WAVE_SUB")) { // tuning knob: loci per sub-chunk
         const int v = atoi(e);
         if (v >= 256 && v <= (1 << 20)) n_sub_cap = want_be ? std::min(v, 8192) : v;
@@ -1450,7 +1464,7 @@ vlr_status_t vlr_ctx_create(const vlr_scenario_t* scenario, int32_t device, vlr_
     ctx->wave = ctx->small && ctx->wplan.eligible && ctx->wplan.max_rounds <= vlr_small::W_MAXROUNDS &&
                 !(wave_env && wave_env[0] == '0');
     if (ctx->wave) {
-        ctx->wave_smem_prep = (size_t)WARPS_PER_CTA * (size_t)ctx->ctx_stride;
+        ctx->wave_smem_prep = (size_t)WARPS_PER_CTA * (size_t)vlr_small::CTX_LEAN;
         CKB(cudaFuncSetAttribute(vlr_wave_pre_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->wave_smem_prep));
         CKB(cudaFuncSetAttribute(vlr_wave_coef_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->wave_smem_prep));
         CKB(cudaFuncSetAttribute(vlr_wave_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->wave_smem_prep));
@@ -1633,7 +1647,11 @@ vlr_status_t vlr_call_batch_device(vlr_ctx_t* ctx, const vlr_batch_t* batch, vlr
     r.afd_vaf = results->afd_vaf;
     r.afd_logp = results->afd_logp;
     const int64_t avg_reads = batch->n_loci > 0 ? (batch->n_reads + batch->n_loci - 1) / batch->n_loci : 0;
-    if (ctx->wave && ctx->n_aux > 1 && batch->n_loci >= (1 << 17)) {
+    // a batch is split over the internal streams from 131 072 loci or ~100 M reads on (100 000 config-5 loci = 150 M
+    // reads: one stream 1.43, three 1.51 M loci/s)
+    int64_t split_min = batch->n_reads >= 3 * ((int64_t)1 << 25) ? 1 << 14 : 1 << 17;
+    if (const char* e = getenv("VLR_WAVE_SPLIT_MIN")) split_min = std::max<long>(1024, atol(e)); // tuning knob (measurements)
+    if (ctx->wave && ctx->n_aux > 1 && batch->n_loci >= split_min) {
         // large batch on the wavefront pipeline: its parts run on internal streams (own workspaces), forked from and
         // joined to the caller's stream, so that one part's kernels fill the grid tails and the straggler rounds of
         // the others (the host entry gets the same effect from its three chunk streams)
