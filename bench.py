@@ -497,6 +497,19 @@ def run_workload(args, D, cfg, loci, steps, warmup, strong, oracle_legs, n_oracl
                                              "ranges (upstream is single-threaded)" % (n, dt, threads),
                                    "single_thread": {"value": n1 / dt1, "cores": 1,
                                                      "sample": "first %d loci, %.1f s" % (n1, dt1)}}
+        elif world > 1 and not args.no_cpu_baseline:
+            # N > 1: the checker still looks at rank 0's shard (its first loci), after the timed region; no CPU timing
+            # (the other ranks' processes spin on the same host cores meanwhile)
+            try:
+                from oracle import oracle
+                oracle.build()
+                threads = os.cpu_count() or 1
+                n_sample = {2: 2000, 3: 8000, 4: 2000, 5: 200}[cfg]
+                want, n, _ = oracle_sample(flat, batch, n_sample, threads)
+                out["parity"] = parity_block(want, got.slice(0, n))
+                out["parity"]["note"] += "; first %d loci of rank 0's shard" % n
+            except Exception as e:  # noqa: BLE001 (the checker must never cost the measured line)
+                out["parity"] = {"error": "%s: %s" % (type(e).__name__, e)}
     del dbatch, dres, pres, batch, eng
     torch.cuda.empty_cache()
     return out
