@@ -1,0 +1,245 @@
+"""Independent restatement of the whole per-locus path for tumor-normal loci WITHOUT a surviving artifact config:
+GenericPosterior::density (generic.rs:191-422), the adaptive integration (adaptive_integration.rs:25-141), the
+observable range limits (formula.rs:1172-1224), the contaminated / single sample likelihoods (likelihood.rs) with the
+learned forward-strand rate (strand_bias.rs:79-123) and the posterior normalisation, written here straight from the
+reference's files in Python: abscissae in f64 exactly as the reference computes them, likelihood VALUES with 50
+significant digits in linear space (mpmath). The oracle (and with it the engines) must reproduce event posteriors
+within 1e-9 and the same MAP allele frequencies on loci whose decisions are not knife-edge.
+
+What this adds to the golden pair (single sample, printed precision): nested integration over two samples, the
+contaminated sample model, Set and Range nodes under clear-reference pruning - at full precision. What it does not
+cover: artifact events (loci are chosen so that no artifact config is possible, informative and likely)."""
+import math
+
+import mpmath as mp
+import numpy as np
+import pytest
+
+from oracle import oracle
+from varlociraptor_b200 import Scenario, abi, synth
+
+mp.mp.dps = 50
+HALF = mp.mpf("0.5")
+
+
+def _e(x):
+    x = float(x)
+    return mp.mpf(0) if x == -math.inf else mp.e ** mp.mpf(x)
+
+
+class Pileup:
+    """Per-read linear coefficients of one sample's pileup under Artifacts::none(): value(x) = c0 + c1 x, x the
+    effective alt-sampling probability (every read of these batches has prob_sample_alt = 0: likelihood.rs:43-53)."""
+
+    def __init__(self, b, lo, hi, forward_rate):
+        c = b.columns
+        self.n = hi - lo
+        self.c0, self.c1, self.pos_ref = [], [], True
+        for r in range(lo, hi):
+            assert float(c["prob_sample_alt"][r]) == 0.0
+            f = int(b.read_flags[r])
+            strand = (f >> abi.RF_STRAND_SHIFT) & 3
+            pdo = _e(c["prob_double_overlap"][r])
+            phb = _e(c["prob_hit_base"][r])
+            rpb = phb if f & abi.RF_READPOS_MAJOR else 1 - phb
+            sb_alt = {0: forward_rate * (1 - pdo), 1: (1 - forward_rate) * (1 - pdo), 2: pdo, 3: mp.mpf(1)}[strand]
+            b_alt = sb_alt * HALF * rpb * HALF   # strand, orientation, position, softclip = homopolymer = 1, alt locus
+            b_ref = HALF * HALF * rpb * HALF
+            b_any = HALF * HALF * rpb * HALF
+            pm = _e(c["prob_mapping"][r])
+            a_term = pm * b_alt * _e(c["prob_alt"][r])
+            r_term = pm * b_ref * _e(c["prob_ref"][r])
+            self.c0.append(r_term + (1 - pm) * _e(c["prob_missed_allele"][r]) * b_any)
+            self.c1.append(a_term - r_term)
+            # is_positive_ref_support (read_observation.rs:443-446): Kass-Raftery of exp(prob_ref - prob_alt) > 3
+            if not math.exp(float(c["prob_ref"][r]) - float(c["prob_alt"][r])) > 3.0:
+                self.pos_ref = False
+        self.clear_ref = self.n > 10 and self.pos_ref  # generic.rs:270-291
+
+    def value(self, x):
+        x = mp.mpf(x)
+        p = mp.mpf(1)
+        for c0, c1 in zip(self.c0, self.c1):
+            p *= c0 + c1 * x
+        return p
+
+
+def _forward_rate(b, rows):
+    """StrandBias::estimate_forward_rate over all samples' reads (strand_bias.rs:79-123), else 0.5 (:69-77)."""
+    c = b.columns
+    strong_all = strong_fwd = 0.0
+    for r in rows:
+        strand = (int(b.read_flags[r]) >> abi.RF_STRAND_SHIFT) & 3
+        strong_ref = math.exp(float(c["prob_ref"][r]) - float(c["prob_alt"][r])) > 20.0  # >= KassRaftery::Strong
+        if strong_ref and strand != 2:
+            strong_all += math.exp(float(c["prob_mapping"][r]))
+        if strong_ref and strand == 0:
+            strong_fwd += math.exp(float(c["prob_mapping"][r]))
+    if strong_all > 2.0:
+        frac = strong_fwd / strong_all
+        if strong_all > 100.0 and 0.0 < frac < 1.0:
+            return mp.mpf(frac)
+        if 0.4 <= frac <= 0.6:
+            return HALF
+    return HALF
+
+
+def _observable_max(rg, n_obs):
+    if n_obs < 10 or not (n_obs * (rg.end - rg.start) > 1.0):
+        return rg.end
+    cnt = n_obs * rg.end
+    if rg.right_exclusive and cnt % 1.0 == 0.0:
+        cnt -= 1.0
+    cnt = math.floor(cnt)
+    return rg.end if cnt == 0.0 else math.floor(cnt) / n_obs
+
+
+def _observable_min(rg, n_obs):
+    if n_obs < 10 or not (n_obs * (rg.end - rg.start) > 1.0):
+        mn = rg.start
+    else:
+        cnt = n_obs * rg.start
+        adjust = lambda k: math.ceil(k) / n_obs  # noqa: E731
+        mn = None
+        if rg.left_exclusive and cnt % 1.0 == 0.0:
+            end = _observable_max(rg, n_obs)
+            for off in (1.0, 0.0):
+                s = adjust(cnt + off)
+                if s <= 1.0 and s <= end:
+                    mn = s
+                    break
+        if mn is None:
+            mn = adjust(cnt)
+    return rg.start if mn >= _observable_max(rg, n_obs) else mn
+
+
+def _integrate(density, lo, hi, res):
+    """adaptive_integration.rs:25-141; density returns a LINEAR value; the integral is returned linear."""
+    probs = {}
+
+    def gp(x):
+        probs[x] = density(x)
+        return x
+    left, right = gp(lo), gp(hi)
+    first_middle = middle = None
+    while ((right - left) >= res and left < right) or middle is None:
+        middle = gp((right + left) / 2.0)
+        m1 = gp((middle + left) / 2.0)
+        m2 = gp((right + middle) / 2.0)
+        if first_middle is None:
+            first_middle = middle
+        xs = [left, m1, m2, right]
+        best = 0
+        for k in range(4):
+            if probs[xs[k]] > probs[xs[best]]:
+                best = k
+        left, right = (xs[best - 1] if best > 0 else xs[best]), (xs[best + 1] if best < 3 else xs[best])
+    gp((first_middle + hi) / 2.0 if middle < first_middle else (lo + first_middle) / 2.0)
+    a = max(middle - res * 3.0, lo)
+    step = (middle - a) / 3.0
+    for i in range(3):
+        gp(a + step * i)
+    z = min(middle + res * 3.0, hi)
+    step = (z - middle) / 3.0
+    for i in range(1, 4):
+        gp(middle + step * i)
+    xs = sorted(probs)
+    return sum(((probs[x0] + probs[x1]) / 2 * (mp.mpf(x1) - mp.mpf(x0)) for x0, x1 in zip(xs, xs[1:])), mp.mpf(0))
+
+
+class Locus:
+    def __init__(self, b, locus, flat):
+        S = 2
+        offs = [int(b.read_offsets[locus * S + k]) for k in range(S + 1)]
+        fr = _forward_rate(b, range(offs[0], offs[2]))
+        self.normal, self.tumor = Pileup(b, offs[0], offs[1], fr), Pileup(b, offs[1], offs[2], fr)
+        self.res = [0.1, 0.01]                      # cli.rs:1151-1173: normal 0.1, tumor 0.01
+        self.purity = mp.mpf(1) - mp.mpf(0.25)      # tumor contaminated by normal, fraction = 1 - purity
+        self.base = {}                              # (vn, vt) -> joint, in evaluation order (first entry kept)
+        self.n_joint = 0
+        self._ln = {}
+
+    def joint(self, vn, vt):
+        """Prior (flat inside the universes: prior.rs:398-406) x normal pileup x contaminated tumor pileup."""
+        self.n_joint += 1
+        if vn not in self._ln:
+            self._ln[vn] = self.normal.value(vn)
+        x_eff = self.purity * mp.mpf(vt) + (1 - self.purity) * mp.mpf(vn)   # likelihood.rs:108-135, s_r = 1
+        j = self._ln[vn] * self.tumor.value(x_eff)
+        self.base.setdefault((vn, vt), j)
+        return j
+
+    def node(self, nd, fixed):
+        """density() of a Sample node; `fixed` = allele frequency of the enclosing (normal) node or None."""
+        pile, res = (self.normal, self.res[0]) if nd.sample == 0 else (self.tumor, self.res[1])
+
+        def below(v):
+            if nd.children:
+                return self.node(nd.children[0], v)
+            return self.joint(fixed, v)
+        if nd.kind == 0:  # Set
+            vafs = sorted(nd.vafs)
+            if pile.clear_ref and all(v > 0.0 for v in vafs):
+                return mp.mpf(0)
+            return sum((below(v) for v in vafs), mp.mpf(0))
+        rg = nd.vafs
+        if pile.clear_ref and rg.start > 0.0:
+            return mp.mpf(0)
+        mn, mx = _observable_min(rg, pile.n), _observable_max(rg, pile.n)
+        assert mn <= mx and (mx - mn) >= res and pile.n >= 5  # (no Simpson fallback on these loci)
+        return _integrate(below, mn, mx, res)
+
+
+def _chosen_loci(o, b, want=9):
+    """Loci the restatement covers: no artifact event, nothing adjusted or filtered, decisions not knife-edge; a mix of
+    best events."""
+    ok = np.isneginf(o.log_posteriors[:, -1]) & (o.status == 0) & ~o.knife_edge()
+    picked, seen = [], {}
+    for i in np.nonzero(ok)[0]:
+        k = int(o.best_event[i]) // 2
+        if seen.get(k, 0) < 2:
+            seen[k] = seen.get(k, 0) + 1
+            picked.append(int(i))
+        if len(picked) >= want:
+            break
+    return picked
+
+
+@pytest.mark.parametrize("n_loci,seed", [(80, 21), (120, 22)])
+def test_tumor_normal_posteriors_against_the_high_precision_restatement(n_loci, seed):
+    sc, b = synth.tumor_normal(n_loci, seed=seed)
+    flat = sc.flatten()
+    o = oracle.call_batch(flat, b, afd_capacity=0, n_threads=4)
+    trees = dict(sc.event_trees())
+    names = list(flat.event_names)
+    loci = _chosen_loci(o, b)
+    assert len(loci) >= 5
+    worst = 0.0
+    for i in loci:
+        L = Locus(b, i, flat)
+        dens = []
+        for name in names:
+            roots = trees[name]
+            dens.append(sum((L.node(r, None) for r in roots), mp.mpf(0)))
+        total = sum(dens, mp.mpf(0))
+        for k, d in enumerate(dens):
+            got = float(o.log_posteriors[i, k])
+            if d == 0:
+                assert got == -math.inf, (i, names[k], got)
+                continue
+            want = mp.log(d / total)
+            delta = abs(float(mp.mpf(got) - want))
+            worst = max(worst, delta)
+            assert delta <= 1e-9, (i, names[k], got, float(want), delta)
+        assert L.n_joint == int(o.n_base_events[i])  # the same number of joint evaluations: identical adaptive grids
+        best = max(range(len(dens)), key=lambda k: dens[k])
+        assert 2 * best == int(o.best_event[i])  # index into the event universe: 2 e (plain), 2 e + 1 (artifact twin)
+        # MAP: the strongest base event the best event contains (calling.rs:851-864); here: of its own tree
+        L2 = Locus(b, i, flat)
+        for r in trees[names[best]]:
+            L2.node(r, None)
+        (vn, vt), _ = max(L2.base.items(), key=lambda kv: kv[1])
+        assert (vn, vt) == (float(o.map_vaf[i, 0]), float(o.map_vaf[i, 1])), (i, names[best], vn, vt, o.map_vaf[i])
+    assert worst > 0.0
+    if seed == 22:  # this batch has somatic_normal calls without artifact events: the nested Range x Range integration
+        assert any(int(o.best_event[i]) // 2 == names.index("somatic_normal") for i in loci)
