@@ -243,3 +243,115 @@ def test_tumor_normal_posteriors_against_the_high_precision_restatement(n_loci, 
     assert worst > 0.0
     if seed == 22:  # this batch has somatic_normal calls without artifact events: the nested Range x Range integration
         assert any(int(o.best_event[i]) // 2 == names.index("somatic_normal") for i in loci)
+
+
+# ---------------------------------------------------------------------------------------------- pedigree (config 3)
+class GeneralPileup(Pileup):
+    """Single-sample pileup value at an allele frequency with per-read prob_sample_alt (likelihood.rs:43-53, :198-220)."""
+
+    def __init__(self, b, lo, hi, forward_rate):
+        c = b.columns
+        self.n = hi - lo
+        self.rows, self.pos_ref = [], True
+        for r in range(lo, hi):
+            f = int(b.read_flags[r])
+            strand = (f >> abi.RF_STRAND_SHIFT) & 3
+            pdo = _e(c["prob_double_overlap"][r])
+            phb = _e(c["prob_hit_base"][r])
+            rpb = phb if f & abi.RF_READPOS_MAJOR else 1 - phb
+            sb_alt = {0: forward_rate * (1 - pdo), 1: (1 - forward_rate) * (1 - pdo), 2: pdo, 3: mp.mpf(1)}[strand]
+            pm = _e(c["prob_mapping"][r])
+            self.rows.append((pm * sb_alt * HALF * rpb * HALF * _e(c["prob_alt"][r]),
+                              pm * HALF * HALF * rpb * HALF * _e(c["prob_ref"][r]),
+                              (1 - pm) * _e(c["prob_missed_allele"][r]) * HALF * HALF * rpb * HALF,
+                              _e(c["prob_sample_alt"][r])))
+            if not math.exp(float(c["prob_ref"][r]) - float(c["prob_alt"][r])) > 3.0:
+                self.pos_ref = False
+        self.clear_ref = self.n > 10 and self.pos_ref
+
+    def value(self, vaf):
+        v = mp.mpf(vaf)
+        p = mp.mpf(1)
+        for a, r, m, sa in self.rows:
+            s = mp.mpf(1) if v == 1 else min(v * sa, mp.mpf(1))
+            p *= s * a + (1 - s) * r + m
+        return p
+
+
+def _pedigree_prior(vafs, names, het):
+    """Prior::compute in its default absent-only mode (prior.rs:737-754) for the simple pedigree (mother, father
+    founders; child Mendelian; ploidy 2): P(all absent) = population term with m = 0 over the founders' four alleles
+    (prior.rs:554-582) x Mendelian term 1; any other possible combination gets 1 - P(all absent); impossible ones (the
+    child carries fewer alt alleles than a homozygous parent must pass on: prior.rs:600-678) get 0."""
+    n_alt = {nm: int(round(2 * v)) for nm, v in zip(names, vafs)}
+    p_absent = 1 - sum(het / m for m in range(1, 5))
+    if all(k == 0 for k in n_alt.values()):
+        return p_absent
+    must = (n_alt["mother"] == 2) + (n_alt["father"] == 2)
+    return mp.mpf(0) if n_alt["child"] < must else 1 - p_absent
+
+
+def test_pedigree_posteriors_against_the_high_precision_restatement():
+    sc, b = synth.pedigree(150, seed=31)
+    flat = sc.flatten()
+    names = list(sc.sample_names)
+    events = list(flat.event_names)
+    S = len(names)
+    o = oracle.call_batch(flat, b, afd_capacity=0, n_threads=4)
+    trees = dict(sc.event_trees())
+    ok = np.isneginf(o.log_posteriors[:, -1]) & (o.status == 0) & ~o.knife_edge()
+    picked, seen = [], {}
+    for i in np.nonzero(ok)[0]:
+        key = (int(o.best_event[i]) // 2, int((b.locus_flags[i] >> abi.LF_VARTYPE_SHIFT) & 3))
+        if seen.get(key, 0) < 2:
+            seen[key] = seen.get(key, 0) + 1
+            picked.append(int(i))
+    assert len(picked) >= 6 and len({k[1] for k in seen}) >= 2  # SNV and indel loci (their heterozygosities differ)
+    worst = 0.0
+    for i in picked:
+        offs = [int(b.read_offsets[i * S + k]) for k in range(S + 1)]
+        fr = _forward_rate(b, range(offs[0], offs[S]))
+        piles = [GeneralPileup(b, offs[k], offs[k + 1], fr) for k in range(S)]
+        vartype = int((b.locus_flags[i] >> abi.LF_VARTYPE_SHIFT) & 3)
+        het = mp.mpf("0.001") * (1 if vartype == 0 else mp.mpf("0.0125"))  # grammar/mod.rs:375-415, prior.rs:243-271
+        cache = {}
+        n_joint = 0
+
+        def lh(s, v):
+            if (s, v) not in cache:
+                cache[(s, v)] = piles[s].value(v)
+            return cache[(s, v)]
+
+        def walk(nd, vafs):
+            nonlocal n_joint
+            assert nd.kind == 0
+            vs = sorted(nd.vafs)
+            if piles[nd.sample].clear_ref and all(v > 0.0 for v in vs):  # generic.rs:294-299
+                return mp.mpf(0)
+            tot = mp.mpf(0)
+            for v in vs:
+                cur = dict(vafs)
+                cur[nd.sample] = v
+                if nd.children:
+                    tot += sum((walk(ch, cur) for ch in nd.children), mp.mpf(0))
+                else:
+                    n_joint += 1
+                    vv = [cur[k] for k in range(S)]
+                    j = _pedigree_prior(vv, names, het)
+                    for k in range(S):  # sample-index order (generic.rs:511-551)
+                        j *= lh(k, vv[k])
+                    tot += j
+            return tot
+        dens = [sum((walk(r, {}) for r in trees[e]), mp.mpf(0)) for e in events]
+        total = sum(dens, mp.mpf(0))
+        for k, d in enumerate(dens):
+            got = float(o.log_posteriors[i, k])
+            if d == 0:
+                assert got == -math.inf, (i, events[k], got)
+                continue
+            delta = abs(float(mp.mpf(got) - mp.log(d / total)))
+            worst = max(worst, delta)
+            assert delta <= 1e-9, (i, events[k], got, delta)
+        assert n_joint == int(o.n_base_events[i])
+        assert 2 * max(range(len(dens)), key=lambda k: dens[k]) == int(o.best_event[i])
+    assert worst > 0.0
