@@ -216,6 +216,11 @@ def test_tumor_normal_posteriors_against_the_high_precision_restatement(n_loci, 
     assert len(loci) >= 5
     worst = 0.0
     for i in loci:
+        # the restated selection rules (further down) agree that no artifact config survives here: >= 10 strong alt reads
+        # without a two-thirds majority for any bias, or nothing but reference support
+        offs = [int(b.read_offsets[i * 2 + k]) for k in range(3)]
+        piles = [Reads(b, offs[0], offs[1]), Reads(b, offs[1], offs[2])]
+        assert _surviving_configs(piles, _forward_rate_opt([d for p in piles for d in p.rows]) is not None) == []
         L = Locus(b, i, flat)
         dens = []
         for name in names:
@@ -355,3 +360,196 @@ def test_pedigree_posteriors_against_the_high_precision_restatement():
         assert n_joint == int(o.n_base_events[i])
         assert 2 * max(range(len(dens)), key=lambda k: dens[k]) == int(o.best_event[i])
     assert worst > 0.0
+
+
+# ---------------------------------------------------------------------------------------------- artifact events (a3)
+# The artifact configs of an SNV record with all six checks on (bias/mod.rs:128-216: exactly one bias active; the
+# homopolymer error only exists for homopolymer indels), their per-read terms (strand_bias.rs:28-53,
+# read_orientation_bias.rs:17-35, read_position_bias.rs:17-45, softclip_bias.rs:14-27, alt_locus_bias.rs:62-112) and the
+# three selection rules (bias/mod.rs:37-104 + the per-bias is_informative) restated from those files.
+ARTIFACT_CONFIGS = ("sb_fwd", "sb_rev", "rob_f1r2", "rob_f2r1", "rpb", "scb", "alb")
+
+
+class Reads:
+    def __init__(self, b, lo, hi):
+        c = b.columns
+        self.rows = []
+        for r in range(lo, hi):
+            f = int(b.read_flags[r])
+            self.rows.append(dict(
+                strand=(f >> abi.RF_STRAND_SHIFT) & 3, orient=(f >> abi.RF_ORIENT_SHIFT) & 15,
+                major=bool(f & abi.RF_READPOS_MAJOR), softclip=bool(f & abi.RF_SOFTCLIPPED), maxq=bool(f & abi.RF_MAX_MAPQ),
+                altlocus=(f >> abi.RF_ALTLOCUS_SHIFT) & 3,
+                pm=float(c["prob_mapping"][r]), pa=float(c["prob_alt"][r]), pr=float(c["prob_ref"][r]),
+                e_pm=_e(c["prob_mapping"][r]), e_pa=_e(c["prob_alt"][r]), e_pr=_e(c["prob_ref"][r]),
+                e_miss=_e(c["prob_missed_allele"][r]), e_pdo=_e(c["prob_double_overlap"][r]), e_phb=_e(c["prob_hit_base"][r]),
+                psa=float(c["prob_sample_alt"][r])))
+        for d in self.rows:
+            bf_ref, bf_alt = math.exp(d["pr"] - d["pa"]), math.exp(d["pa"] - d["pr"])
+            d["strong_ref"], d["strong_alt"] = bf_ref > 20.0, bf_alt > 20.0      # >= KassRaftery::Strong
+            d["pos_ref"] = bf_ref > 3.0                                          # >= KassRaftery::Positive
+            d["ref_support"] = d["pr"] > d["pa"]
+            d["unique"] = d["pm"] >= math.log(0.95)
+
+
+def _bias_alt(cfg, d, fr):
+    """(strand, orientation, position, softclip, alt locus) factors of Artifacts::prob_alt for config `cfg` (None = none)."""
+    if cfg in ("sb_fwd", "sb_rev"):
+        want = 0 if cfg == "sb_fwd" else 1
+        sb = mp.mpf(1) if d["strand"] == 3 else (mp.mpf(1) if d["strand"] == want else mp.mpf(0))
+    else:
+        sb = {0: fr * (1 - d["e_pdo"]), 1: (1 - fr) * (1 - d["e_pdo"]), 2: d["e_pdo"], 3: mp.mpf(1)}[d["strand"]]
+    if cfg in ("rob_f1r2", "rob_f2r1"):
+        want = abi.ORIENT_F1R2 if cfg == "rob_f1r2" else abi.ORIENT_F2R1
+        other = abi.ORIENT_F2R1 if cfg == "rob_f1r2" else abi.ORIENT_F1R2
+        rob = mp.mpf(1) if d["orient"] == want else (mp.mpf(0) if d["orient"] == other else HALF)
+    else:
+        rob = HALF
+    rpb_any = d["e_phb"] if d["major"] else 1 - d["e_phb"]
+    rpb = (mp.mpf(1) if d["major"] else mp.mpf(0)) if cfg == "rpb" else rpb_any
+    scb = (mp.mpf(1) if d["softclip"] else mp.mpf(0)) if cfg == "scb" else mp.mpf(1)
+    alb = (mp.mpf(0) if d["maxq"] else mp.mpf(1)) if cfg == "alb" else HALF        # (no alt loci in these pileups)
+    return sb, rob, rpb, scb, alb, rpb_any
+
+
+class ConfigPileup(Pileup):
+    """c0 + c1 x per read under one artifact config (prob_sample_alt = 0 for every read)."""
+
+    def __init__(self, reads, cfg, fr):
+        self.n = len(reads.rows)
+        self.c0, self.c1 = [], []
+        for d in reads.rows:
+            assert d["psa"] == 0.0
+            sb, rob, rpb, scb, alb, rpb_any = _bias_alt(cfg, d, fr)
+            b_alt = sb * rob * rpb * scb * alb
+            b_ref = HALF * HALF * rpb_any * 1 * HALF   # prob_ref = prob_any for every bias (MAPQ-only alt locus bias: 0.5)
+            b_any = HALF * HALF * rpb_any * 1 * HALF
+            a_term, r_term = d["e_pm"] * b_alt * d["e_pa"], d["e_pm"] * b_ref * d["e_pr"]
+            self.c0.append(r_term + (1 - d["e_pm"]) * d["e_miss"] * b_any)
+            self.c1.append(a_term - r_term)
+        self.clear_ref = self.n > 10 and all(d["pos_ref"] for d in reads.rows)
+
+
+def _surviving_configs(piles, fr_estimated):
+    """is_possible && is_informative && is_likely of the artifact configs over the pileups (bias/mod.rs:37-104)."""
+    every = [d for p in piles for d in p.rows]
+
+    def evidence(cfg, d):  # prob_alt of the active bias != ln 0
+        if cfg in ("sb_fwd", "sb_rev"):
+            return d["strand"] == 3 or d["strand"] == (0 if cfg == "sb_fwd" else 1)
+        if cfg in ("rob_f1r2", "rob_f2r1"):
+            return d["orient"] != (abi.ORIENT_F2R1 if cfg == "rob_f1r2" else abi.ORIENT_F1R2)
+        if cfg == "rpb":
+            return d["major"]
+        if cfg == "scb":
+            return d["softclip"]
+        return not d["maxq"]
+
+    def informative(cfg):
+        if cfg in ("sb_fwd", "sb_rev"):
+            return fr_estimated
+        if cfg in ("rob_f1r2", "rob_f2r1"):
+            std = (abi.ORIENT_F1R2, abi.ORIENT_F2R1)
+            n_uncertain = sum(d["orient"] not in std for d in every)
+            strong = [d for d in every if d["strong_ref"] and d["orient"] in std]
+            uniform = len(strong) > 2 and 0.3 <= sum(d["orient"] == abi.ORIENT_F1R2 for d in strong) / len(strong) <= 0.7
+            return n_uncertain < len(every) / 2.0 and uniform
+        if cfg == "rpb":
+            for p in piles:
+                exp_all = sum(math.exp(d["pm"]) for d in p.rows if d["strong_ref"])
+                if exp_all > 10.0:
+                    exp_major = sum(math.exp(d["pm"]) for d in p.rows if d["strong_ref"] and d["major"])
+                    exp_rate = sum(math.exp(d["pm"]) * float(d["e_phb"]) for d in p.rows if d["strong_ref"])
+                    if exp_major > 0.0 and abs(exp_major / exp_all - exp_rate) < 0.05:
+                        return True
+            return False
+        if cfg == "scb":
+            return any(d["softclip"] for d in every)
+        n_alt = sum(d["strong_alt"] for d in every)
+        nm_alt = sum(d["strong_alt"] and not d["maxq"] for d in every)
+        n_ref = sum(d["strong_ref"] for d in every)
+        nm_ref = sum(d["strong_ref"] and not d["maxq"] for d in every)
+        enough_alt = n_alt > 0 and nm_alt > n_alt * 0.1 and (n_alt - nm_alt) < 10
+        return enough_alt and (n_ref > 0 and nm_ref < n_ref * 0.9)   # (has_alt_loci is false here)
+
+    def likely(cfg):
+        for p in piles:
+            strong = [d for d in p.rows if d["unique"] and d["strong_alt"]]
+            if len(strong) >= 10:
+                if sum(evidence(cfg, d) for d in strong) / len(strong) >= 0.66666:
+                    return True
+            elif all(d["ref_support"] for d in p.rows):
+                continue
+            elif not p.rows:
+                continue
+            else:
+                return True
+        return False
+    return [c for c in ARTIFACT_CONFIGS if any(evidence(c, d) for d in every) and informative(c) and likely(c)]
+
+
+def _forward_rate_opt(every):
+    strong_all = sum(math.exp(d["pm"]) for d in every if d["strong_ref"] and d["strand"] != 2)
+    strong_fwd = sum(math.exp(d["pm"]) for d in every if d["strong_ref"] and d["strand"] == 0)
+    if strong_all > 2.0:
+        frac = strong_fwd / strong_all
+        if strong_all > 100.0 and 0.0 < frac < 1.0:
+            return mp.mpf(frac)
+        if 0.4 <= frac <= 0.6:
+            return HALF
+    return None
+
+
+class ConfigLocus(Locus):
+    def __init__(self, normal, tumor):
+        self.normal, self.tumor = normal, tumor
+        self.res = [0.1, 0.01]
+        self.purity = mp.mpf(1) - mp.mpf(0.25)
+        self.base, self.n_joint, self._ln = {}, 0, {}
+
+
+def test_tumor_normal_artifact_events_against_the_high_precision_restatement():
+    sc, b = synth.tumor_normal(120, seed=22)
+    flat = sc.flatten()
+    o = oracle.call_batch(flat, b, afd_capacity=0, n_threads=4)
+    trees = dict(sc.event_trees())
+    names = list(flat.event_names)
+    E = len(names)
+    ok = np.isfinite(o.log_posteriors[:, -1]) & ((o.status & np.uint32(0xffffffff ^ abi.ST_IS_ARTIFACT)) == 0) & ~o.knife_edge()
+    order = np.argsort(-o.log_posteriors[:, -1], kind="stable")       # the strongest artifact posteriors first
+    loci = [int(i) for i in order if ok[i]][:3] + [int(i) for i in np.nonzero(ok)[0][:3]]
+    loci = list(dict.fromkeys(loci))
+    assert len(loci) >= 4
+    worst, n_cfg_seen = 0.0, set()
+    for i in loci:
+        offs = [int(b.read_offsets[i * 2 + k]) for k in range(3)]
+        piles = [Reads(b, offs[0], offs[1]), Reads(b, offs[1], offs[2])]
+        fr_opt = _forward_rate_opt([d for p in piles for d in p.rows])
+        fr = fr_opt if fr_opt is not None else HALF
+        surviving = _surviving_configs(piles, fr_opt is not None)
+        assert surviving, i
+        n_cfg_seen.update(surviving)
+        n_joint = 0
+        dens = {}
+        for cfg in [None] + surviving:
+            L = ConfigLocus(ConfigPileup(piles[0], cfg, fr), ConfigPileup(piles[1], cfg, fr))
+            for name in names:
+                if cfg is not None and name == "absent":
+                    continue  # the absent event has no artifact twin (calling.rs:654-659)
+                dens[(cfg, name)] = sum((L.node(r, None) for r in trees[name]), mp.mpf(0))
+            n_joint += L.n_joint
+        plain = [HALF * dens[(None, n)] for n in names]
+        twin = [sum((HALF / len(ARTIFACT_CONFIGS) * dens[(c, n)] for c in surviving), mp.mpf(0)) if n != "absent" else mp.mpf(0)
+                for n in names]
+        total = sum(plain, mp.mpf(0)) + sum(twin, mp.mpf(0))
+        want = [p / total for p in plain] + [sum(twin, mp.mpf(0)) / total]
+        for k in range(E + 1):
+            got = float(o.log_posteriors[i, k])
+            if want[k] == 0:
+                assert got == -math.inf, (i, k, got)
+                continue
+            delta = abs(float(mp.mpf(got) - mp.log(want[k])))
+            worst = max(worst, delta)
+            assert delta <= 1e-9, (i, k, surviving, got, float(mp.log(want[k])), delta)
+        assert n_joint == int(o.n_base_events[i]), (i, surviving, n_joint, int(o.n_base_events[i]))
+    assert worst > 0.0 and len(n_cfg_seen) >= 2
