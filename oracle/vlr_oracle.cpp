@@ -24,14 +24,18 @@
 // pinned against the reference's own golden pair tests/resources/flamegraph_profiling/
 // {normal.vcf -> calls.vcf} (f32 PHRED / AFD text precision) and the likelihood.rs unit
 // tests (tests/test_oracle_*.py). At 1e-9 in log space parity is "unpinned" by the
-// reference's tests; the oracle defines that target.
+// reference's tests; the oracle defines that target. Beside those pins it is cross-checked at
+// full precision against restatements written independently from the reference's files in
+// Python with 50-60 significant digits (tests/test_oracle_highprec.py: the likelihood model;
+// tests/test_posterior_highprec.py: whole tumor-normal and pedigree loci, artifact events and
+// their selection rules included): posteriors within 1e-9, identical adaptive grids and MAPs.
 //
 // Where the reference is run-to-run non-deterministic (HashMap iteration order:
 // adaptive_integration.rs:70-82, calling.rs:762-769,851) the oracle fixes: candidates in
 // ascending x, first maximum wins; events in scenario order, last maximum wins for the best
 // event (itertools minmax); base events in first-recorded order for MAP ties.
 //
-// Build: see oracle/Makefile (g++ -O2 -ffp-contract=off: Rust never contracts a*b+c).
+// Build: see oracle/Makefile (g++ -O3 -ffp-contract=off: Rust never contracts a*b+c).
 
 #include <algorithm>
 #include <atomic>
