@@ -392,7 +392,7 @@ class Reads:
             d["unique"] = d["pm"] >= math.log(0.95)
 
 
-def _bias_alt(cfg, d, fr):
+def _bias_alt(cfg, d, fr, has_alt_loci=False):
     """(strand, orientation, position, softclip, alt locus) factors of Artifacts::prob_alt for config `cfg` (None = none)."""
     if cfg in ("sb_fwd", "sb_rev"):
         want = 0 if cfg == "sb_fwd" else 1
@@ -408,21 +408,28 @@ def _bias_alt(cfg, d, fr):
     rpb_any = d["e_phb"] if d["major"] else 1 - d["e_phb"]
     rpb = (mp.mpf(1) if d["major"] else mp.mpf(0)) if cfg == "rpb" else rpb_any
     scb = (mp.mpf(1) if d["softclip"] else mp.mpf(0)) if cfg == "scb" else mp.mpf(1)
-    alb = (mp.mpf(0) if d["maxq"] else mp.mpf(1)) if cfg == "alb" else HALF        # (no alt loci in these pileups)
+    if cfg != "alb":
+        alb = HALF
+    elif has_alt_loci:
+        alb = mp.mpf(1) if d["altlocus"] == abi.ALTLOCUS_MAJOR else mp.mpf(0)
+    else:
+        alb = mp.mpf(0) if d["maxq"] else mp.mpf(1)
     return sb, rob, rpb, scb, alb, rpb_any
 
 
 class ConfigPileup(Pileup):
     """c0 + c1 x per read under one artifact config (prob_sample_alt = 0 for every read)."""
 
-    def __init__(self, reads, cfg, fr):
+    def __init__(self, reads, cfg, fr, has_alt_loci=False):
         self.n = len(reads.rows)
         self.c0, self.c1 = [], []
         for d in reads.rows:
             assert d["psa"] == 0.0
-            sb, rob, rpb, scb, alb, rpb_any = _bias_alt(cfg, d, fr)
+            sb, rob, rpb, scb, alb, rpb_any = _bias_alt(cfg, d, fr, has_alt_loci)
             b_alt = sb * rob * rpb * scb * alb
-            b_ref = HALF * HALF * rpb_any * 1 * HALF   # prob_ref = prob_any for every bias (MAPQ-only alt locus bias: 0.5)
+            # prob_ref = prob_any for every bias, except the alt locus bias with real alt loci (alt_locus_bias.rs:85-104)
+            alb_ref = (mp.mpf(0) if d["altlocus"] == abi.ALTLOCUS_MAJOR else mp.mpf(1)) if cfg == "alb" and has_alt_loci else HALF
+            b_ref = HALF * HALF * rpb_any * 1 * alb_ref
             b_any = HALF * HALF * rpb_any * 1 * HALF
             a_term, r_term = d["e_pm"] * b_alt * d["e_pa"], d["e_pm"] * b_ref * d["e_pr"]
             self.c0.append(r_term + (1 - d["e_pm"]) * d["e_miss"] * b_any)
@@ -430,7 +437,7 @@ class ConfigPileup(Pileup):
         self.clear_ref = self.n > 10 and all(d["pos_ref"] for d in reads.rows)
 
 
-def _surviving_configs(piles, fr_estimated):
+def _surviving_configs(piles, fr_estimated, has_alt_loci=False):
     """is_possible && is_informative && is_likely of the artifact configs over the pileups (bias/mod.rs:37-104)."""
     every = [d for p in piles for d in p.rows]
 
@@ -443,7 +450,7 @@ def _surviving_configs(piles, fr_estimated):
             return d["major"]
         if cfg == "scb":
             return d["softclip"]
-        return not d["maxq"]
+        return d["altlocus"] == abi.ALTLOCUS_MAJOR if has_alt_loci else not d["maxq"]
 
     def informative(cfg):
         if cfg in ("sb_fwd", "sb_rev"):
@@ -470,7 +477,7 @@ def _surviving_configs(piles, fr_estimated):
         n_ref = sum(d["strong_ref"] for d in every)
         nm_ref = sum(d["strong_ref"] and not d["maxq"] for d in every)
         enough_alt = n_alt > 0 and nm_alt > n_alt * 0.1 and (n_alt - nm_alt) < 10
-        return enough_alt and (n_ref > 0 and nm_ref < n_ref * 0.9)   # (has_alt_loci is false here)
+        return enough_alt and (has_alt_loci or (n_ref > 0 and nm_ref < n_ref * 0.9))
 
     def likely(cfg):
         for p in piles:
@@ -553,3 +560,77 @@ def test_tumor_normal_artifact_events_against_the_high_precision_restatement():
             assert delta <= 1e-9, (i, k, surviving, got, float(mp.log(want[k])), delta)
         assert n_joint == int(o.n_base_events[i]), (i, surviving, n_joint, int(o.n_base_events[i]))
     assert worst > 0.0 and len(n_cfg_seen) >= 2
+
+
+def _artifact_posteriors(b, i, names, trees):
+    """The E + 1 posteriors of tumor-normal locus i (plain events + the artifact event) and the number of joint evaluations."""
+    offs = [int(b.read_offsets[i * 2 + k]) for k in range(3)]
+    piles = [Reads(b, offs[0], offs[1]), Reads(b, offs[1], offs[2])]
+    every = [d for p in piles for d in p.rows]
+    fr_opt = _forward_rate_opt(every)
+    fr = fr_opt if fr_opt is not None else HALF
+    has_alt_loci = any(d["altlocus"] != abi.ALTLOCUS_NONE for d in every)   # AltLocusBias::learn_parameters
+    surviving = _surviving_configs(piles, fr_opt is not None, has_alt_loci)
+    n_joint, dens = 0, {}
+    for cfg in [None] + surviving:
+        L = ConfigLocus(ConfigPileup(piles[0], cfg, fr, has_alt_loci), ConfigPileup(piles[1], cfg, fr, has_alt_loci))
+        for name in names:
+            if cfg is None or name != "absent":
+                dens[(cfg, name)] = sum((L.node(r, None) for r in trees[name]), mp.mpf(0))
+        n_joint += L.n_joint
+    plain = [HALF * dens[(None, n)] for n in names]
+    twin = sum((HALF / len(ARTIFACT_CONFIGS) * dens[(c, n)] for c in surviving for n in names if n != "absent"), mp.mpf(0))
+    total = sum(plain, mp.mpf(0)) + twin
+    return [p / total for p in plain] + [twin / total], n_joint, surviving
+
+
+def test_constructed_pileups_for_the_other_artifact_configs():
+    """Softclip, read position and alt locus (with real alt loci) configs, and the two-thirds rule of is_likely."""
+    from tests.util import batch_from_reads, read
+    q = dict(prob_mapping=np.log1p(-1e-6), prob_double_overlap=-np.inf)
+    hi, lo = np.log1p(-1e-3), np.log(1e-3 / 3)
+
+    def ref(k, **kw):
+        return read(prob_ref=hi, prob_alt=lo, strand=k % 2, orientation=(k // 2) % 2, **{**q, **kw})
+
+    def alt(k, **kw):
+        return read(prob_ref=lo, prob_alt=hi, strand=k % 2, orientation=(k // 2) % 2, **{**q, **kw})
+    # has_valid_major_rate (read_position_bias.rs:62-122) compares the major FRACTION of the strong reference reads with
+    # the SUM of their e^(prob_mapping + prob_hit_base) (upstream does not normalise it): 40 reads x 0.005 = 0.2 = 8 / 40
+    phb = dict(prob_hit_base=math.log(0.005))
+    loci = [
+        # softclip bias: every alt read is softclipped, a few reference reads too
+        [[ref(k, softclipped=k < 3) for k in range(30)],
+         [ref(k) for k in range(24)] + [alt(k, softclipped=True) for k in range(6)]],
+        # read position bias: alt reads at the major position; a fifth of the reference reads too (= prob_hit_base)
+        [[ref(k, major=k % 5 == 0, **phb) for k in range(40)],
+         [ref(k, major=k % 5 == 0, **phb) for k in range(30)] + [alt(k, major=True, **phb) for k in range(7)]],
+        # alt locus bias with alt loci: alt reads point to the major alt locus and have low MAPQs
+        [[ref(k) for k in range(30)],
+         [ref(k) for k in range(25)] + [alt(k, alt_locus=abi.ALTLOCUS_MAJOR, max_mapq=False,
+                                           prob_mapping=np.log1p(-1e-2)) for k in range(6)]],
+        # is_likely by the two-thirds rule: 12 strong alt reads, 10 of them on the forward strand; normal all reference
+        [[ref(k) for k in range(30)],
+         [ref(k) for k in range(28)] + [alt(2 * (k % 2)) for k in range(10)] + [alt(1), alt(3)]],  # (orientations balanced)
+        # ... and 12 strong alt reads spread evenly: no config is likely
+        [[ref(k) for k in range(30)], [ref(k) for k in range(28)] + [alt(k) for k in range(12)]],
+    ]
+    b = batch_from_reads(loci)
+    sc = Scenario.tumor_normal(0.75)
+    flat = sc.flatten()
+    trees, names = dict(sc.event_trees()), list(flat.event_names)
+    o = oracle.call_batch(flat, b, afd_capacity=0)
+    expect = ["scb", "rpb", "alb", "sb_fwd", None]
+    for i, must in enumerate(expect):
+        assert not o.knife_edge()[i] and (int(o.status[i]) & ~abi.ST_IS_ARTIFACT) == 0, (i, int(o.status[i]))
+        want, n_joint, surviving = _artifact_posteriors(b, i, names, trees)
+        assert (must in surviving) if must else surviving == [], (i, surviving)
+        if must == "sb_fwd":
+            assert surviving == ["sb_fwd"]  # (the other configs fail the two-thirds rule)
+        for k, w in enumerate(want):
+            got = float(o.log_posteriors[i, k])
+            if w == 0:
+                assert got == -math.inf, (i, k, got)
+            else:
+                assert abs(float(mp.mpf(got) - mp.log(w))) <= 1e-9, (i, k, surviving, got, float(mp.log(w)))
+        assert n_joint == int(o.n_base_events[i]), (i, surviving, n_joint, int(o.n_base_events[i]))
