@@ -186,7 +186,11 @@ class Locus:
         if pile.clear_ref and rg.start > 0.0:
             return mp.mpf(0)
         mn, mx = _observable_min(rg, pile.n), _observable_max(rg, pile.n)
-        assert mn <= mx and (mx - mn) >= res and pile.n >= 5  # (no Simpson fallback on these loci)
+        assert mn <= mx
+        if (mx - mn) < res:       # generic.rs:357-394
+            return _simpson(below, mn, mx, 3)
+        if pile.n < 5:
+            return _simpson(below, mn, mx, 11)
         return _integrate(below, mn, mx, res)
 
 
@@ -376,6 +380,8 @@ class Reads:
         self.rows = []
         for r in range(lo, hi):
             f = int(b.read_flags[r])
+            if ((f >> abi.RF_ORIENT_SHIFT) & 15) not in (abi.ORIENT_F1R2, abi.ORIENT_F2R1, abi.ORIENT_NONE):
+                continue  # Pileup::remove_nonstandard_alignments (pileup.rs:26-43; SNV / MNV records, calling.rs:596-603)
             self.rows.append(dict(
                 strand=(f >> abi.RF_STRAND_SHIFT) & 3, orient=(f >> abi.RF_ORIENT_SHIFT) & 15,
                 major=bool(f & abi.RF_READPOS_MAJOR), softclip=bool(f & abi.RF_SOFTCLIPPED), maxq=bool(f & abi.RF_MAX_MAPQ),
@@ -390,6 +396,25 @@ class Reads:
             d["pos_ref"] = bf_ref > 3.0                                          # >= KassRaftery::Positive
             d["ref_support"] = d["pr"] > d["pa"]
             d["unique"] = d["pm"] >= math.log(0.95)
+
+
+def _adjust_singleton_evidence(piles):
+    """read_observation.rs:548-562: exactly one read over all pileups favours the alt allele -> its prob_alt() and
+    prob_ref() become ln 0.5 (the likelihood reads those; the Kass-Raftery predicates keep reading the raw fields)."""
+    alts = [d for p in piles for d in p.rows if d["pa"] > d["pr"]]
+    if len(alts) == 1:
+        alts[0]["e_pa"] = alts[0]["e_pr"] = HALF
+    return len(alts) == 1
+
+
+def _simpson(density, lo, hi, n):
+    """rust-bio LogProb::ln_simpsons_integrate_exp in linear space: n odd points, weights 1 4 2 4 ... 4 1."""
+    step = (hi - lo) / (n - 1)
+    xs = [lo + step * k for k in range(n)]  # itertools-num linspace
+    tot = density(xs[0]) + density(xs[-1])
+    for k in range(1, n - 1):
+        tot += (4 if k % 2 else 2) * density(xs[k])
+    return tot * (mp.mpf(hi) - mp.mpf(lo)) / (n - 1) / 3
 
 
 def _bias_alt(cfg, d, fr, has_alt_loci=False):
@@ -566,6 +591,7 @@ def _artifact_posteriors(b, i, names, trees):
     """The E + 1 posteriors of tumor-normal locus i (plain events + the artifact event) and the number of joint evaluations."""
     offs = [int(b.read_offsets[i * 2 + k]) for k in range(3)]
     piles = [Reads(b, offs[0], offs[1]), Reads(b, offs[1], offs[2])]
+    _adjust_singleton_evidence(piles)
     every = [d for p in piles for d in p.rows]
     fr_opt = _forward_rate_opt(every)
     fr = fr_opt if fr_opt is not None else HALF
@@ -627,6 +653,48 @@ def test_constructed_pileups_for_the_other_artifact_configs():
         assert (must in surviving) if must else surviving == [], (i, surviving)
         if must == "sb_fwd":
             assert surviving == ["sb_fwd"]  # (the other configs fail the two-thirds rule)
+        for k, w in enumerate(want):
+            got = float(o.log_posteriors[i, k])
+            if w == 0:
+                assert got == -math.inf, (i, k, got)
+            else:
+                assert abs(float(mp.mpf(got) - mp.log(w))) <= 1e-9, (i, k, surviving, got, float(mp.log(w)))
+        assert n_joint == int(o.n_base_events[i]), (i, surviving, n_joint, int(o.n_base_events[i]))
+
+
+def test_small_pileups_singleton_evidence_and_filtered_reads():
+    """Simpson fallbacks (fewer than 5 reads: 11 points; fewer than 10: the range bounds themselves are the limits),
+    the singleton-evidence adjustment and the orientation filter of SNV records."""
+    from tests.util import batch_from_reads, read
+    q = dict(prob_mapping=np.log1p(-1e-5), prob_double_overlap=-np.inf)
+
+    def err(k):  # base error rates differ from read to read: no exact ties between abscissae
+        return 10.0 ** -(2.0 + 0.13 * (k % 11))
+
+    def ref(k, **kw):
+        return read(**{**dict(prob_ref=np.log1p(-err(k)), prob_alt=np.log(err(k) / 3), strand=k % 2,
+                              orientation=(k // 2) % 2), **q, **kw})
+
+    def alt(k, **kw):
+        return read(**{**dict(prob_ref=np.log(err(k + 5) / 3), prob_alt=np.log1p(-err(k + 5)), strand=k % 2,
+                              orientation=(k // 2) % 2), **q, **kw})
+    loci = [
+        [[ref(0), ref(1), ref(2)], [ref(0), alt(1), alt(2), ref(3)]],                  # 3 and 4 reads: Simpson 11
+        [[ref(k) for k in range(7)], [ref(k) for k in range(5)] + [alt(0), alt(3)]],   # 7 reads each: adaptive, raw bounds
+        [[ref(k) for k in range(30)], [ref(k) for k in range(29)] + [alt(0)]],         # singleton evidence
+        [[ref(k) for k in range(20)] + [alt(0, orientation=abi.ORIENT_F1F2)],          # filtered: leaves no alt read there
+         [ref(k) for k in range(20)] + [alt(1), alt(2), ref(0, orientation=abi.ORIENT_R1R2)]],
+        [[], [ref(0), alt(1)]],                                                         # an empty pileup
+    ]
+    b = batch_from_reads(loci)
+    sc = Scenario.tumor_normal(0.75)
+    flat = sc.flatten()
+    trees, names = dict(sc.event_trees()), list(flat.event_names)
+    o = oracle.call_batch(flat, b, afd_capacity=0)
+    assert int(o.status[2]) & abi.ST_SINGLETON_ADJUSTED and int(o.status[3]) & abi.ST_FILTERED_NONSTANDARD
+    assert o.knife_edge().sum() <= 1
+    for i in np.nonzero(~o.knife_edge())[0]:
+        want, n_joint, surviving = _artifact_posteriors(b, i, names, trees)
         for k, w in enumerate(want):
             got = float(o.log_posteriors[i, k])
             if w == 0:
