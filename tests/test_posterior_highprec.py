@@ -375,14 +375,22 @@ ARTIFACT_CONFIGS = ("sb_fwd", "sb_rev", "rob_f1r2", "rob_f2r1", "rpb", "scb", "a
 
 
 class Reads:
-    def __init__(self, b, lo, hi):
+    def __init__(self, b, lo, hi, filter_nonstandard=True):
         c = b.columns
         self.rows = []
+
+        def opt(col, r):  # Option<LogProb> columns: NaN = None
+            if col is None or np.isnan(col[r]):
+                return None
+            return _e(col[r])
         for r in range(lo, hi):
             f = int(b.read_flags[r])
-            if ((f >> abi.RF_ORIENT_SHIFT) & 15) not in (abi.ORIENT_F1R2, abi.ORIENT_F2R1, abi.ORIENT_NONE):
+            if filter_nonstandard and ((f >> abi.RF_ORIENT_SHIFT) & 15) not in (abi.ORIENT_F1R2, abi.ORIENT_F2R1, abi.ORIENT_NONE):
                 continue  # Pileup::remove_nonstandard_alignments (pileup.rs:26-43; SNV / MNV records, calling.rs:596-603)
+            hlen = ((f >> abi.RF_HOMOPOLYMER_LEN_SHIFT) & 0xff) if f & abi.RF_HAS_HOMOPOLYMER_LEN else 0
             self.rows.append(dict(
+                hlen=hlen - 256 if hlen > 127 else hlen, hart=opt(b.prob_homopolymer_artifact, r),
+                hvar=opt(b.prob_homopolymer_variant, r),
                 strand=(f >> abi.RF_STRAND_SHIFT) & 3, orient=(f >> abi.RF_ORIENT_SHIFT) & 15,
                 major=bool(f & abi.RF_READPOS_MAJOR), softclip=bool(f & abi.RF_SOFTCLIPPED), maxq=bool(f & abi.RF_MAX_MAPQ),
                 altlocus=(f >> abi.RF_ALTLOCUS_SHIFT) & 3,
@@ -433,6 +441,9 @@ def _bias_alt(cfg, d, fr, has_alt_loci=False):
     rpb_any = d["e_phb"] if d["major"] else 1 - d["e_phb"]
     rpb = (mp.mpf(1) if d["major"] else mp.mpf(0)) if cfg == "rpb" else rpb_any
     scb = (mp.mpf(1) if d["softclip"] else mp.mpf(0)) if cfg == "scb" else mp.mpf(1)
+    d["_he"] = (d["hart"] if cfg == "he" else d["hvar"])  # homopolymer_error.rs:22-40: the same term for alt and ref
+    if d["_he"] is None:
+        d["_he"] = mp.mpf(1)
     if cfg != "alb":
         alb = HALF
     elif has_alt_loci:
@@ -451,10 +462,11 @@ class ConfigPileup(Pileup):
         for d in reads.rows:
             assert d["psa"] == 0.0
             sb, rob, rpb, scb, alb, rpb_any = _bias_alt(cfg, d, fr, has_alt_loci)
-            b_alt = sb * rob * rpb * scb * alb
-            # prob_ref = prob_any for every bias, except the alt locus bias with real alt loci (alt_locus_bias.rs:85-104)
+            b_alt = sb * rob * rpb * scb * d["_he"] * alb
+            # prob_ref = prob_any for every bias, except the homopolymer error (= its prob_alt) and the alt locus bias with
+            # real alt loci (alt_locus_bias.rs:85-104)
             alb_ref = (mp.mpf(0) if d["altlocus"] == abi.ALTLOCUS_MAJOR else mp.mpf(1)) if cfg == "alb" and has_alt_loci else HALF
-            b_ref = HALF * HALF * rpb_any * 1 * alb_ref
+            b_ref = HALF * HALF * rpb_any * 1 * d["_he"] * alb_ref
             b_any = HALF * HALF * rpb_any * 1 * HALF
             a_term, r_term = d["e_pm"] * b_alt * d["e_pa"], d["e_pm"] * b_ref * d["e_pr"]
             self.c0.append(r_term + (1 - d["e_pm"]) * d["e_miss"] * b_any)
@@ -462,7 +474,7 @@ class ConfigPileup(Pileup):
         self.clear_ref = self.n > 10 and all(d["pos_ref"] for d in reads.rows)
 
 
-def _surviving_configs(piles, fr_estimated, has_alt_loci=False):
+def _surviving_configs(piles, fr_estimated, has_alt_loci=False, configs=ARTIFACT_CONFIGS):
     """is_possible && is_informative && is_likely of the artifact configs over the pileups (bias/mod.rs:37-104)."""
     every = [d for p in piles for d in p.rows]
 
@@ -517,7 +529,17 @@ def _surviving_configs(piles, fr_estimated, has_alt_loci=False):
             else:
                 return True
         return False
-    return [c for c in ARTIFACT_CONFIGS if any(evidence(c, d) for d in every) and informative(c) and likely(c)]
+    def homopolymer_ok():  # HomopolymerError::is_informative = is_possible = is_likely (homopolymer_error.rs:46-75)
+        return all(not any(d["strong_alt"] for d in p.rows)
+                   or (any(d["hlen"] > 0 for d in p.rows) and any(d["hlen"] < 0 for d in p.rows)) for p in piles)
+    out = []
+    for c in configs:
+        if c == "he":
+            if homopolymer_ok():
+                out.append(c)
+        elif any(evidence(c, d) for d in every) and informative(c) and likely(c):
+            out.append(c)
+    return out
 
 
 def _forward_rate_opt(every):
@@ -590,13 +612,18 @@ def test_tumor_normal_artifact_events_against_the_high_precision_restatement():
 def _artifact_posteriors(b, i, names, trees):
     """The E + 1 posteriors of tumor-normal locus i (plain events + the artifact event) and the number of joint evaluations."""
     offs = [int(b.read_offsets[i * 2 + k]) for k in range(3)]
-    piles = [Reads(b, offs[0], offs[1]), Reads(b, offs[1], offs[2])]
+    lf = int(b.locus_flags[i])
+    configs = [c for c, bit in (("sb_fwd", abi.LF_CHECK_SB), ("sb_rev", abi.LF_CHECK_SB), ("rob_f1r2", abi.LF_CHECK_ROB),
+                                ("rob_f2r1", abi.LF_CHECK_ROB), ("rpb", abi.LF_CHECK_RPB), ("scb", abi.LF_CHECK_SCB),
+                                ("he", abi.LF_CHECK_HE), ("alb", abi.LF_CHECK_ALB)) if lf & bit]  # calling.rs:559-566
+    flt = bool(lf & abi.LF_FILTER_NONSTANDARD)
+    piles = [Reads(b, offs[0], offs[1], flt), Reads(b, offs[1], offs[2], flt)]
     _adjust_singleton_evidence(piles)
     every = [d for p in piles for d in p.rows]
     fr_opt = _forward_rate_opt(every)
     fr = fr_opt if fr_opt is not None else HALF
     has_alt_loci = any(d["altlocus"] != abi.ALTLOCUS_NONE for d in every)   # AltLocusBias::learn_parameters
-    surviving = _surviving_configs(piles, fr_opt is not None, has_alt_loci)
+    surviving = _surviving_configs(piles, fr_opt is not None, has_alt_loci, configs)
     n_joint, dens = 0, {}
     for cfg in [None] + surviving:
         L = ConfigLocus(ConfigPileup(piles[0], cfg, fr, has_alt_loci), ConfigPileup(piles[1], cfg, fr, has_alt_loci))
@@ -605,7 +632,7 @@ def _artifact_posteriors(b, i, names, trees):
                 dens[(cfg, name)] = sum((L.node(r, None) for r in trees[name]), mp.mpf(0))
         n_joint += L.n_joint
     plain = [HALF * dens[(None, n)] for n in names]
-    twin = sum((HALF / len(ARTIFACT_CONFIGS) * dens[(c, n)] for c in surviving for n in names if n != "absent"), mp.mpf(0))
+    twin = sum((HALF / len(configs) * dens[(c, n)] for c in surviving for n in names if n != "absent"), mp.mpf(0))
     total = sum(plain, mp.mpf(0)) + twin
     return [p / total for p in plain] + [twin / total], n_joint, surviving
 
@@ -695,6 +722,59 @@ def test_small_pileups_singleton_evidence_and_filtered_reads():
     assert o.knife_edge().sum() <= 1
     for i in np.nonzero(~o.knife_edge())[0]:
         want, n_joint, surviving = _artifact_posteriors(b, i, names, trees)
+        for k, w in enumerate(want):
+            got = float(o.log_posteriors[i, k])
+            if w == 0:
+                assert got == -math.inf, (i, k, got)
+            else:
+                assert abs(float(mp.mpf(got) - mp.log(w))) <= 1e-9, (i, k, surviving, got, float(mp.log(w)))
+        assert n_joint == int(o.n_base_events[i]), (i, surviving, n_joint, int(o.n_base_events[i]))
+
+
+def test_homopolymer_indel_records():
+    """Indel records: no read-orientation / read-position / softclip configs and no orientation filter
+    (calling.rs:559-566, :596-603); the homopolymer error model (homopolymer_error.rs) for homopolymer indels."""
+    from tests.util import batch_from_reads, read
+    from varlociraptor_b200 import obs_codec
+    q = dict(prob_mapping=np.log1p(-1e-5), prob_double_overlap=-np.inf)
+
+    def err(k):
+        return 10.0 ** -(2.0 + 0.13 * (k % 11))
+
+    def ref(k, **kw):
+        return read(**{**dict(prob_ref=np.log1p(-err(k)), prob_alt=np.log(err(k) / 3), strand=k % 2,
+                              orientation=(k // 2) % 2), **q, **kw})
+
+    def alt(k, **kw):
+        return read(**{**dict(prob_ref=np.log(err(k + 5) / 3), prob_alt=np.log1p(-err(k + 5)), strand=k % 2,
+                              orientation=(k // 2) % 2), **q, **kw})
+    h = lambda k, n: dict(hlen=n, hart=math.log(0.05 + 0.01 * (k % 5)), hvar=math.log(0.6 + 0.02 * (k % 7)))  # noqa: E731
+    loci = [
+        # homopolymer indel, insertions and deletions among the reads: the homopolymer config is considered
+        [[ref(k, **h(k, 0)) for k in range(25)] + [alt(0, **h(0, 1)), ref(2, **h(2, -2))],
+         [ref(k, **h(k, 0)) for k in range(20)] + [alt(k, **h(k, 1)) for k in range(6)] + [alt(7, **h(7, -1)), ref(3, **h(3, -1))]],
+        # ... insertions only in the sample with strong alt reads: it is not
+        [[ref(k, **h(k, 0)) for k in range(25)],
+         [ref(k, **h(k, 0)) for k in range(20)] + [alt(k, **h(k, 1)) for k in range(6)]],
+        # an ordinary indel with reads in non-standard orientations (kept: the filter is for SNVs and MNVs)
+        [[ref(k) for k in range(25)] + [ref(0, orientation=abi.ORIENT_F1F2)],
+         [ref(k) for k in range(20)] + [alt(k) for k in range(5)] + [alt(1, orientation=abi.ORIENT_R1R2)]],
+    ]
+    hom = obs_codec.locus_flags_for("A", "AT", True)
+    plain = obs_codec.locus_flags_for("A", "AT", False)
+    b = batch_from_reads(loci, locus_flags=[hom, hom, plain])
+    sc = Scenario.tumor_normal(0.75)
+    flat = sc.flatten()
+    trees, names = dict(sc.event_trees()), list(flat.event_names)
+    o = oracle.call_batch(flat, b, afd_capacity=0)
+    expect = [True, False, None]
+    for i in range(len(loci)):
+        assert not o.knife_edge()[i]
+        assert not int(o.status[i]) & abi.ST_FILTERED_NONSTANDARD
+        want, n_joint, surviving = _artifact_posteriors(b, i, names, trees)
+        if expect[i] is not None:
+            assert ("he" in surviving) == expect[i], (i, surviving)
+        assert not {"rob_f1r2", "rob_f2r1", "rpb", "scb"} & set(surviving)
         for k, w in enumerate(want):
             got = float(o.log_posteriors[i, k])
             if w == 0:
