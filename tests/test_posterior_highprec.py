@@ -782,3 +782,170 @@ def test_homopolymer_indel_records():
             else:
                 assert abs(float(mp.mpf(got) - mp.log(w))) <= 1e-9, (i, k, surviving, got, float(mp.log(w)))
         assert n_joint == int(o.n_base_events[i]), (i, surviving, n_joint, int(o.n_base_events[i]))
+
+
+# ---------------------------------------------------------------------------------------------- priors with somatic rates
+class TreeLocus:
+    """density() over arbitrary Set / Range trees of S uncontaminated samples with a prior function of the VAF vector."""
+
+    def __init__(self, piles, res, prior):
+        self.piles, self.res, self.prior = piles, res, prior
+        self.n_joint, self._lh = 0, {}
+
+    def joint(self, vafs):
+        self.n_joint += 1
+        j = self.prior([vafs[k] for k in range(len(self.piles))])
+        for k in range(len(self.piles)):  # sample-index order (generic.rs:511-551)
+            if (k, vafs[k]) not in self._lh:
+                self._lh[(k, vafs[k])] = self.piles[k].value(vafs[k])
+            j *= self._lh[(k, vafs[k])]
+        return j
+
+    def node(self, nd, vafs):
+        pile, res = self.piles[nd.sample], self.res[nd.sample]
+
+        def below(v):
+            cur = dict(vafs)
+            cur[nd.sample] = v
+            if nd.children:  # one child: recurse; several: ln_sum_exp over them (generic.rs:199-226)
+                return sum((self.node(ch, cur) for ch in nd.children), mp.mpf(0))
+            return self.joint(cur)
+        if nd.kind == 0:
+            vs = sorted(nd.vafs)
+            if pile.clear_ref and all(v > 0.0 for v in vs):
+                return mp.mpf(0)
+            return sum((below(v) for v in vs), mp.mpf(0))
+        rg = nd.vafs
+        if pile.clear_ref and rg.start > 0.0:
+            return mp.mpf(0)
+        mn, mx = _observable_min(rg, pile.n), _observable_max(rg, pile.n)
+        assert mn <= mx
+        if (mx - mn) < res:
+            return _simpson(below, mn, mx, 3)
+        if pile.n < 5:
+            return _simpson(below, mn, mx, 11)
+        return _integrate(below, mn, mx, res)
+
+
+def _tumor_normal_prior(full_prior):
+    """Prior::compute (prior.rs:718-761) for the reference's tests/resources/prior/scenarios/tumor-normal scenario:
+    normal = germline only (heterozygosity 0.001, ploidy 2), tumor = clonal from normal (somatic: false) with a somatic
+    effective mutation rate of 1e-6. calc_prob (:298-438): the normal's allele frequency must be a germline one
+    (:237-241); population term over the normal (:554-582); the tumor's germline equals the normal's (:458-470) and what
+    is left of its allele frequency is somatic: rate if != 0 else 1 - rate (:440-456). Samples sorted: normal, tumor."""
+    het, rate = mp.mpf("0.001"), mp.mpf("1e-6")
+
+    def full(vafs):
+        vn, vt = vafs
+        n_alt = 2 * vn
+        if n_alt != round(n_alt):
+            return mp.mpf(0)
+        m = int(round(n_alt))
+        pop = het / m if m > 0 else 1 - (het / 1 + het / 2)
+        return pop * ((1 - rate) if vt - vn == 0.0 else rate)
+
+    def absent_only(vafs):  # the default mode (:737-754)
+        if all(v == 0.0 for v in vafs):
+            return full(vafs)
+        return mp.mpf(0) if full(vafs) == 0 else 1 - full([0.0, 0.0])
+    return full if full_prior else absent_only
+
+
+@pytest.mark.parametrize("full_prior", [False, True])
+def test_somatic_rate_and_clonal_inheritance_prior(golden_dir, full_prior):
+    import json
+    import os
+    text = json.load(open(os.path.join(golden_dir, "prior_scenarios.json")))["scenarios"]["tumor-normal"]
+    sc = Scenario.from_yaml(text, full_prior=full_prior).for_contig("all")
+    assert list(sc.sample_names) == ["normal", "tumor"]
+    flat = sc.flatten()
+    trees, names = dict(sc.event_trees()), list(flat.event_names)
+    b = synth.tumor_normal(60, seed=41, depth=30)[1]
+    o = oracle.call_batch(flat, b, afd_capacity=0, n_threads=4)
+    prior = _tumor_normal_prior(full_prior)
+    checked, worst = 0, 0.0
+    for i in range(b.n_loci):
+        if o.knife_edge()[i] or int(o.status[i]) & ~abi.ST_IS_ARTIFACT:
+            continue
+        offs = [int(b.read_offsets[i * 2 + k]) for k in range(3)]
+        piles = [Reads(b, offs[0], offs[1]), Reads(b, offs[1], offs[2])]
+        every = [d for p in piles for d in p.rows]
+        fr_opt = _forward_rate_opt(every)
+        fr = fr_opt if fr_opt is not None else HALF
+        surviving = _surviving_configs(piles, fr_opt is not None)
+        if len(surviving) > 2 and checked >= 4:
+            continue  # (every surviving config is another pass over all trees: keep the test short)
+        n_joint, dens = 0, {}
+        for cfg in [None] + surviving:
+            L = TreeLocus([ConfigPileup(p, cfg, fr) for p in piles], [0.01, 0.01], prior)
+            for name in names:
+                if cfg is None or name != "absent":
+                    dens[(cfg, name)] = sum((L.node(r, {}) for r in trees[name]), mp.mpf(0))
+            n_joint += L.n_joint
+        plain = [HALF * dens[(None, n)] for n in names]
+        twin = sum((HALF / len(ARTIFACT_CONFIGS) * dens[(c, n)] for c in surviving for n in names if n != "absent"), mp.mpf(0))
+        total = sum(plain, mp.mpf(0)) + twin
+        for k, w in enumerate([p / total for p in plain] + [twin / total]):
+            got = float(o.log_posteriors[i, k])
+            if w == 0:
+                assert got == -math.inf, (i, k, got)
+            else:
+                delta = abs(float(mp.mpf(got) - mp.log(w)))
+                worst = max(worst, delta)
+                assert delta <= 1e-9, (i, k, surviving, got, float(mp.log(w)))
+        assert n_joint == int(o.n_base_events[i]), (i, surviving, n_joint, int(o.n_base_events[i]))
+        checked += 1
+        if checked >= 8:
+            break
+    assert checked >= 6 and worst > 0.0
+
+
+@pytest.mark.parametrize("full_prior", [False, True])
+def test_population_prior_of_two_founders(golden_dir, full_prior):
+    """tests/resources/prior/scenarios/population: two unrelated diploid samples, heterozygosity 0.001: the population
+    term counts the alt alleles of BOTH (prior.rs:554-582): het / m for m > 0, 1 - sum_{m=1..4} het / m for none."""
+    import json
+    import os
+    text = json.load(open(os.path.join(golden_dir, "prior_scenarios.json")))["scenarios"]["population"]
+    sc = Scenario.from_yaml(text, full_prior=full_prior).for_contig("all")
+    flat = sc.flatten()
+    trees, names = dict(sc.event_trees()), list(flat.event_names)
+    het = mp.mpf("0.001")
+    p_absent = 1 - sum(het / m for m in range(1, 5))
+
+    def prior(vafs):
+        m = sum(int(round(2 * v)) for v in vafs)
+        if m == 0:
+            return p_absent
+        return het / m if full_prior else 1 - p_absent
+    b = synth.tumor_normal(40, seed=43, depth=30)[1]
+    o = oracle.call_batch(flat, b, afd_capacity=0, n_threads=4)
+    checked = 0
+    for i in range(b.n_loci):
+        if o.knife_edge()[i] or int(o.status[i]) & ~abi.ST_IS_ARTIFACT:
+            continue
+        offs = [int(b.read_offsets[i * 2 + k]) for k in range(3)]
+        piles = [Reads(b, offs[0], offs[1]), Reads(b, offs[1], offs[2])]
+        every = [d for p in piles for d in p.rows]
+        fr_opt = _forward_rate_opt(every)
+        fr = fr_opt if fr_opt is not None else HALF
+        surviving = _surviving_configs(piles, fr_opt is not None)
+        n_joint, dens = 0, {}
+        for cfg in [None] + surviving:
+            L = TreeLocus([ConfigPileup(p, cfg, fr) for p in piles], [0.01, 0.01], prior)
+            for name in names:
+                if cfg is None or name != "absent":
+                    dens[(cfg, name)] = sum((L.node(r, {}) for r in trees[name]), mp.mpf(0))
+            n_joint += L.n_joint
+        plain = [HALF * dens[(None, n)] for n in names]
+        twin = sum((HALF / len(ARTIFACT_CONFIGS) * dens[(c, n)] for c in surviving for n in names if n != "absent"), mp.mpf(0))
+        total = sum(plain, mp.mpf(0)) + twin
+        for k, w in enumerate([p / total for p in plain] + [twin / total]):
+            got = float(o.log_posteriors[i, k])
+            if w == 0:
+                assert got == -math.inf, (i, k, got)
+            else:
+                assert abs(float(mp.mpf(got) - mp.log(w))) <= 1e-9, (i, k, surviving, got, float(mp.log(w)))
+        assert n_joint == int(o.n_base_events[i])
+        checked += 1
+    assert checked >= 20
