@@ -788,8 +788,8 @@ def test_homopolymer_indel_records():
 class TreeLocus:
     """density() over arbitrary Set / Range trees of S uncontaminated samples with a prior function of the VAF vector."""
 
-    def __init__(self, piles, res, prior):
-        self.piles, self.res, self.prior = piles, res, prior
+    def __init__(self, piles, res, prior, snv=None):
+        self.piles, self.res, self.prior, self.snv = piles, res, prior, snv
         self.n_joint, self._lh = 0, {}
 
     def joint(self, vafs):
@@ -802,6 +802,17 @@ class TreeLocus:
         return j
 
     def node(self, nd, vafs):
+        if nd.kind == abi.NODE_VARIANT:  # generic.rs:398-420: gate on the record's SNV bases (IUPAC masks), then skip the node
+            if self.snv is not None:
+                mask = {"A": 1, "C": 2, "G": 4, "T": 8}
+                contains = bool(nd.refmask & mask[self.snv[0]]) and bool(nd.altmask & mask[self.snv[1]])
+                if nd.positive != contains:
+                    return mp.mpf(0)
+            elif nd.positive:
+                return mp.mpf(0)
+            if nd.children:
+                return sum((self.node(ch, vafs) for ch in nd.children), mp.mpf(0))
+            return self.joint(vafs)
         pile, res = self.piles[nd.sample], self.res[nd.sample]
 
         def below(v):
@@ -949,3 +960,54 @@ def test_population_prior_of_two_founders(golden_dir, full_prior):
         assert n_joint == int(o.n_base_events[i])
         checked += 1
     assert checked >= 20
+
+
+def test_variant_nodes_gate_on_the_snv_bases():
+    """`C>T & s:]0,1]` / `!C>T & s:]0,1]` (generic.rs:398-420, formula.rs:23-43) on single-sample SNV loci."""
+    from varlociraptor_b200 import LocusBatch
+    sc = Scenario.from_yaml("""
+samples:
+  s:
+    universe: "[0.0,1.0]"
+events:
+  ct: "C>T & s:]0.0,1.0]"
+  other: "!C>T & s:]0.0,1.0]"
+""")
+    flat = sc.flatten()
+    trees, names = dict(sc.event_trees()), list(flat.event_names)
+    _, b2 = synth.tumor_normal(24, seed=22, depth=25)
+    b = LocusBatch(1, b2.read_offsets[::2].copy(), dict(b2.columns), b2.read_flags, b2.locus_flags)  # one sample of 50 reads
+    o = oracle.call_batch(flat, b, afd_capacity=0)
+    res = float(flat.c.samples[0].resolution)
+    n_ct = checked = 0
+    for i in range(b.n_loci):
+        if o.knife_edge()[i] or int(o.status[i]) & ~abi.ST_IS_ARTIFACT:
+            continue
+        lf = int(b.locus_flags[i])
+        snv = (chr((lf >> abi.LF_REFBASE_SHIFT) & 0xff), chr((lf >> abi.LF_ALTBASE_SHIFT) & 0xff)) if lf & abi.LF_HAS_SNV else None
+        piles = [Reads(b, int(b.read_offsets[i]), int(b.read_offsets[i + 1]))]
+        fr_opt = _forward_rate_opt(piles[0].rows)
+        fr = fr_opt if fr_opt is not None else HALF
+        surviving = _surviving_configs(piles, fr_opt is not None)
+        n_joint, dens = 0, {}
+        for cfg in [None] + surviving:
+            L = TreeLocus([ConfigPileup(piles[0], cfg, fr)], [res], lambda v: mp.mpf(1), snv)
+            for name in names:
+                if cfg is None or name != "absent":
+                    dens[(cfg, name)] = sum((L.node(r, {}) for r in trees[name]), mp.mpf(0))
+            n_joint += L.n_joint
+        plain = [HALF * dens[(None, n)] for n in names]
+        twin = sum((HALF / len(ARTIFACT_CONFIGS) * dens[(c, n)] for c in surviving for n in names if n != "absent"), mp.mpf(0))
+        total = sum(plain, mp.mpf(0)) + twin
+        for k, w in enumerate([p / total for p in plain] + [twin / total]):
+            got = float(o.log_posteriors[i, k])
+            if w == 0:
+                assert got == -math.inf, (i, k, got)
+            else:
+                assert abs(float(mp.mpf(got) - mp.log(w))) <= 1e-9, (i, k, snv, surviving, got, float(mp.log(w)))
+        assert n_joint == int(o.n_base_events[i]), (i, n_joint, int(o.n_base_events[i]))
+        is_ct = snv == ("C", "T")
+        assert (dens[(None, "ct")] > 0) == is_ct or piles[0].clear_ref
+        n_ct += is_ct
+        checked += 1
+    assert checked >= 12 and 0 < n_ct < checked
