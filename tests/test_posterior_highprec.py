@@ -156,6 +156,7 @@ class Locus:
         self.res = [0.1, 0.01]                      # cli.rs:1151-1173: normal 0.1, tumor 0.01
         self.purity = mp.mpf(1) - mp.mpf(0.25)      # tumor contaminated by normal, fraction = 1 - purity
         self.base = {}                              # (vn, vt) -> joint, in evaluation order (first entry kept)
+        self.base_full, self._disc = {}, {}
         self.n_joint = 0
         self._ln = {}
 
@@ -167,6 +168,8 @@ class Locus:
         x_eff = self.purity * mp.mpf(vt) + (1 - self.purity) * mp.mpf(vn)   # likelihood.rs:108-135, s_r = 1
         j = self._ln[vn] * self.tumor.value(x_eff)
         self.base.setdefault((vn, vt), j)
+        # base events as the reference keys them (LikelihoodOperands: allele frequency AND is_discrete per sample)
+        self.base_full.setdefault((vn, self._disc.get(0, True), vt, self._disc.get(1, True)), j)
         return j
 
     def node(self, nd, fixed):
@@ -177,6 +180,7 @@ class Locus:
             if nd.children:
                 return self.node(nd.children[0], v)
             return self.joint(fixed, v)
+        self._disc[nd.sample] = nd.kind == 0  # push_base_event(.., is_discrete): Set values true, integration points false
         if nd.kind == 0:  # Set
             vafs = sorted(nd.vafs)
             if pile.clear_ref and all(v > 0.0 for v in vafs):
@@ -213,7 +217,7 @@ def _chosen_loci(o, b, want=9):
 def test_tumor_normal_posteriors_against_the_high_precision_restatement(n_loci, seed):
     sc, b = synth.tumor_normal(n_loci, seed=seed)
     flat = sc.flatten()
-    o = oracle.call_batch(flat, b, afd_capacity=0, n_threads=4)
+    o = oracle.call_batch(flat, b, afd_capacity=192, n_threads=4)
     trees = dict(sc.event_trees())
     names = list(flat.event_names)
     loci = _chosen_loci(o, b)
@@ -249,6 +253,35 @@ def test_tumor_normal_posteriors_against_the_high_precision_restatement(n_loci, 
             L2.node(r, None)
         (vn, vt), _ = max(L2.base.items(), key=lambda kv: kv[1])
         assert (vn, vt) == (float(o.map_vaf[i, 0]), float(o.map_vaf[i, 1])), (i, names[best], vn, vt, o.map_vaf[i])
+        # allele frequency distributions (calling.rs:891-928): per sample, the base events of ALL events that the best
+        # event contains when that sample is ignored and whose other sample equals the MAP (frequency and discreteness)
+        (mvn, mdn, mvt, mdt), _ = max(L2.base_full.items(), key=lambda kv: kv[1])
+        assert (mvn, mvt) == (vn, vt)
+
+        def inside(nd, v):
+            if nd.kind == 0:
+                return v in nd.vafs
+            r = nd.vafs
+            return (r.start < v or (v == r.start and not r.left_exclusive)) and (v < r.end or (v == r.end and not r.right_exclusive))
+        for sample in (0, 1):
+            want_afd = {}
+            for (bn, dn, bt, dt), j in L.base_full.items():
+                ok_other = (bt, dt) == (mvt, mdt) if sample == 0 else (bn, dn) == (mvn, mdn)
+                compatible = any(inside(r.children[0], bt) if sample == 0 else inside(r, bn) for r in trees[names[best]])
+                if ok_other and compatible:
+                    # posterior of a base event = joint - marginal; the joint carries no bias prior, the marginal is over
+                    # the events' ln 0.5 + density (rust-bio Model::compute, generic.rs:430-460)
+                    want_afd.setdefault(bn if sample == 0 else bt, []).append(
+                        mp.log(j / (HALF * total)) if j > 0 else mp.mpf("-inf"))
+            vaf, logp = o.afd(i, sample)
+            assert sorted(want_afd) == sorted(set(float(v) for v in vaf)), (i, sample, sorted(want_afd)[:5], sorted(vaf)[:5])
+            assert len(vaf) == sum(len(v) for v in want_afd.values())
+            for v, lp in zip(vaf, logp):
+                cands = want_afd[float(v)]
+                if lp == -math.inf:
+                    assert any(c == mp.mpf("-inf") for c in cands)
+                else:
+                    assert min(abs(float(mp.mpf(float(lp)) - c)) for c in cands if c != mp.mpf("-inf")) <= 1e-9, (i, sample, v, lp)
     assert worst > 0.0
     if seed == 22:  # this batch has somatic_normal calls without artifact events: the nested Range x Range integration
         assert any(int(o.best_event[i]) // 2 == names.index("somatic_normal") for i in loci)
@@ -560,6 +593,7 @@ class ConfigLocus(Locus):
         self.res = [0.1, 0.01]
         self.purity = mp.mpf(1) - mp.mpf(0.25)
         self.base, self.n_joint, self._ln = {}, 0, {}
+        self.base_full, self._disc = {}, {}
 
 
 def test_tumor_normal_artifact_events_against_the_high_precision_restatement():
