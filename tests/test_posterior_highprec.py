@@ -608,7 +608,7 @@ def test_tumor_normal_artifact_events_against_the_high_precision_restatement():
     loci = [int(i) for i in order if ok[i]][:3] + [int(i) for i in np.nonzero(ok)[0][:3]]
     loci = list(dict.fromkeys(loci))
     assert len(loci) >= 4
-    worst, n_cfg_seen = 0.0, set()
+    worst, n_cfg_seen, n_artifact_calls = 0.0, set(), 0
     for i in loci:
         offs = [int(b.read_offsets[i * 2 + k]) for k in range(3)]
         piles = [Reads(b, offs[0], offs[1]), Reads(b, offs[1], offs[2])]
@@ -640,7 +640,14 @@ def test_tumor_normal_artifact_events_against_the_high_precision_restatement():
             worst = max(worst, delta)
             assert delta <= 1e-9, (i, k, surviving, got, float(mp.log(want[k])), delta)
         assert n_joint == int(o.n_base_events[i]), (i, surviving, n_joint, int(o.n_base_events[i]))
-    assert worst > 0.0 and len(n_cfg_seen) >= 2
+        # the call is an artifact iff the artifact event beats every other event (calling.rs:800-818); its samples then
+        # report an allele frequency of 0 and the bias (calling.rs:866-876)
+        is_artifact = all(want[E] > w for w in want[:E])
+        assert is_artifact == bool(int(o.status[i]) & abi.ST_IS_ARTIFACT), (i, [float(w) for w in want])
+        if is_artifact:
+            n_artifact_calls += 1
+            assert not o.map_vaf[i].any() and int(o.map_config[i]) != 0
+    assert worst > 0.0 and len(n_cfg_seen) >= 2 and n_artifact_calls >= 1
 
 
 def _artifact_posteriors(b, i, names, trees):
