@@ -213,14 +213,27 @@ def _chosen_loci(o, b, want=9):
     return picked
 
 
+def _results(source, flat, b, afd_capacity):
+    """What is checked against the restatement: the oracle, or the engine itself (the single-lane host build of the
+    kernel source, tests/emu) - the loci are chosen by the oracle's diagnostics either way."""
+    o = oracle.call_batch(flat, b, afd_capacity=afd_capacity, n_threads=4)
+    if source == "oracle":
+        return o, o
+    from tests import emu
+    if source == "pipeline":  # the wavefront pipeline (engine_wave.cuh + engine_resident.cuh) instead of the generic engine
+        return o, emu.wave_call_batch(flat, b, afd_capacity=afd_capacity)[0]
+    return o, emu.call_batch(flat, b, afd_capacity=afd_capacity)
+
+
+@pytest.mark.parametrize("source", ["oracle", "engine", "pipeline"])
 @pytest.mark.parametrize("n_loci,seed", [(80, 21), (120, 22)])
-def test_tumor_normal_posteriors_against_the_high_precision_restatement(n_loci, seed):
+def test_tumor_normal_posteriors_against_the_high_precision_restatement(n_loci, seed, source):
     sc, b = synth.tumor_normal(n_loci, seed=seed)
     flat = sc.flatten()
-    o = oracle.call_batch(flat, b, afd_capacity=192, n_threads=4)
+    diag, o = _results(source, flat, b, 192)
     trees = dict(sc.event_trees())
     names = list(flat.event_names)
-    loci = _chosen_loci(o, b)
+    loci = _chosen_loci(diag, b)
     assert len(loci) >= 5
     worst = 0.0
     for i in loci:
@@ -333,15 +346,19 @@ def _pedigree_prior(vafs, names, het):
     return mp.mpf(0) if n_alt["child"] < must else 1 - p_absent
 
 
-def test_pedigree_posteriors_against_the_high_precision_restatement():
+@pytest.mark.parametrize("source", ["oracle", "engine", "all-Set pipeline"])
+def test_pedigree_posteriors_against_the_high_precision_restatement(source):
     sc, b = synth.pedigree(150, seed=31)
     flat = sc.flatten()
     names = list(sc.sample_names)
     events = list(flat.event_names)
     S = len(names)
-    o = oracle.call_batch(flat, b, afd_capacity=0, n_threads=4)
+    diag = o = oracle.call_batch(flat, b, afd_capacity=0, n_threads=4)
+    if source != "oracle":
+        from tests import emu
+        o = emu.call_batch(flat, b) if source == "engine" else emu.sets_call_batch(flat, b)[0]
     trees = dict(sc.event_trees())
-    ok = np.isneginf(o.log_posteriors[:, -1]) & (o.status == 0) & ~o.knife_edge()
+    ok = np.isneginf(diag.log_posteriors[:, -1]) & (diag.status == 0) & ~diag.knife_edge()
     picked, seen = [], {}
     for i in np.nonzero(ok)[0]:
         key = (int(o.best_event[i]) // 2, int((b.locus_flags[i] >> abi.LF_VARTYPE_SHIFT) & 3))
@@ -596,15 +613,16 @@ class ConfigLocus(Locus):
         self.base_full, self._disc = {}, {}
 
 
-def test_tumor_normal_artifact_events_against_the_high_precision_restatement():
+@pytest.mark.parametrize("source", ["oracle", "pipeline"])
+def test_tumor_normal_artifact_events_against_the_high_precision_restatement(source):
     sc, b = synth.tumor_normal(120, seed=22)
     flat = sc.flatten()
-    o = oracle.call_batch(flat, b, afd_capacity=0, n_threads=4)
+    diag, o = _results(source, flat, b, 0)
     trees = dict(sc.event_trees())
     names = list(flat.event_names)
     E = len(names)
-    ok = np.isfinite(o.log_posteriors[:, -1]) & ((o.status & np.uint32(0xffffffff ^ abi.ST_IS_ARTIFACT)) == 0) & ~o.knife_edge()
-    order = np.argsort(-o.log_posteriors[:, -1], kind="stable")       # the strongest artifact posteriors first
+    ok = np.isfinite(diag.log_posteriors[:, -1]) & ((diag.status & np.uint32(0xffffffff ^ abi.ST_IS_ARTIFACT)) == 0) & ~diag.knife_edge()
+    order = np.argsort(-diag.log_posteriors[:, -1], kind="stable")       # the strongest artifact posteriors first
     loci = [int(i) for i in order if ok[i]][:3] + [int(i) for i in np.nonzero(ok)[0][:3]]
     loci = list(dict.fromkeys(loci))
     assert len(loci) >= 4
