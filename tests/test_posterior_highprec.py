@@ -100,16 +100,13 @@ def _observable_min(rg, n_obs):
     else:
         cnt = n_obs * rg.start
         adjust = lambda k: math.ceil(k) / n_obs  # noqa: E731
-        mn = None
         if rg.left_exclusive and cnt % 1.0 == 0.0:
             end = _observable_max(rg, n_obs)
             for off in (1.0, 0.0):
                 s = adjust(cnt + off)
                 if s <= 1.0 and s <= end:
-                    mn = s
-                    break
-        if mn is None:
-            mn = adjust(cnt)
+                    return s  # (a `return` inside the block upstream: the order check below is not applied to it)
+        mn = adjust(cnt)
     return rg.start if mn >= _observable_max(rg, n_obs) else mn
 
 
@@ -844,6 +841,67 @@ def test_homopolymer_indel_records():
 
 
 # ---------------------------------------------------------------------------------------------- priors with somatic rates
+import collections  # noqa: E402
+
+_Rg = collections.namedtuple("_Rg", "start end left_exclusive right_exclusive")
+
+
+def _log2(x):
+    return math.log2(x) if x > 0.0 else -math.inf
+
+
+def _lfc_true(cmp_, v, lfc):  # Log2FoldChangePredicate::is_true (log2_fold_change.rs:40-52)
+    if lfc != lfc:
+        raise AssertionError("NaN log2 fold change")
+    return {abi.CMP_EQ: abs(lfc - v) <= 2.220446049250313e-16 * max(abs(lfc), abs(v), 1.0) if False else lfc == v,
+            abi.CMP_GT: lfc > v, abi.CMP_GE: lfc >= v, abi.CMP_LT: lfc < v, abi.CMP_LE: lfc <= v, abi.CMP_NE: lfc != v}[cmp_]
+
+
+def _rg_empty(r):
+    return r.start == r.end and (r.left_exclusive or r.right_exclusive)
+
+
+def _rg_contains(r, v):
+    return (r.start < v if r.left_exclusive else r.start <= v) and (r.end > v if r.right_exclusive else r.end >= v)
+
+
+def _rg_intersect(a, o):  # VAFRange::intersect (formula.rs:1230-1262) with overlap() == None -> empty (:1140-1160)
+    if a != o and ((a.end < o.start or a.start > o.end)
+                   or (a.end <= o.start and (a.right_exclusive or o.left_exclusive))
+                   or (a.start >= o.end and (a.left_exclusive or o.right_exclusive))):
+        return _Rg(0.0, 0.0, True, True)
+    lex = a.left_exclusive if a.start > o.start else (o.left_exclusive if a.start < o.start else a.left_exclusive or o.left_exclusive)
+    rex = a.right_exclusive if a.end < o.end else (o.right_exclusive if a.end > o.end else a.right_exclusive or o.right_exclusive)
+    return _Rg(max(a.start, o.start), min(a.end, o.end), lex, rex)
+
+
+def _infer_vaf_bounds(cmp_, value, vaf):  # Log2FoldChangePredicate::infer_vaf_bounds (log2_fold_change.rs:54-93)
+    proj = vaf / 2.0 ** value
+    if proj < 0.0 or proj > 1.0:
+        return _Rg(0.0, 0.0, True, True)
+    return {abi.CMP_EQ: _Rg(proj, proj, False, False), abi.CMP_GT: _Rg(0.0, proj, False, True),
+            abi.CMP_GE: _Rg(0.0, proj, False, False), abi.CMP_LT: _Rg(proj, 1.0, True, False),
+            abi.CMP_LE: _Rg(proj, 1.0, False, False), abi.CMP_NE: _Rg(0.0, 1.0, False, False)}[cmp_]
+
+
+_INVERT = {abi.CMP_EQ: (abi.CMP_EQ, 1), abi.CMP_GT: (abi.CMP_LE, -1), abi.CMP_GE: (abi.CMP_LT, -1),
+           abi.CMP_LT: (abi.CMP_GE, -1), abi.CMP_LE: (abi.CMP_GT, -1), abi.CMP_NE: (abi.CMP_NE, 1)}  # invert() (:95-124)
+
+
+def _lfc_bounds(vafs, sample):
+    acc = None
+    for a, b, cmp_, value in vafs.get("lfcs", ()):
+        bounds = None
+        if a == sample and b in vafs:
+            c2, sign = _INVERT[cmp_]
+            bounds = _infer_vaf_bounds(c2, sign * value, vafs[b])
+        elif b == sample and a in vafs:
+            bounds = _infer_vaf_bounds(cmp_, value, vafs[a])
+        if bounds is not None:
+            acc = bounds if acc is None else _rg_intersect(acc, bounds)
+    return acc
+
+
 class TreeLocus:
     """density() over arbitrary Set / Range trees of S uncontaminated samples with a prior function of the VAF vector."""
 
@@ -853,6 +911,11 @@ class TreeLocus:
 
     def joint(self, vafs):
         self.n_joint += 1
+        for a, bb, cmp_, value in vafs.get("lfcs", ()):  # GenericLikelihood::compute step 1 (generic.rs:503-509)
+            va, vb = vafs[a], vafs[bb]
+            lfc = 0.0 if va == 0.0 and vb == 0.0 else _log2(va) - _log2(vb)    # log2_fold_change.rs:17-27, in f64
+            if not _lfc_true(cmp_, value, lfc):
+                return mp.mpf(0)
         j = self.prior([vafs[k] for k in range(len(self.piles))])
         for k in range(len(self.piles)):  # sample-index order (generic.rs:511-551)
             if (k, vafs[k]) not in self._lh:
@@ -872,6 +935,12 @@ class TreeLocus:
             if nd.children:
                 return sum((self.node(ch, vafs) for ch in nd.children), mp.mpf(0))
             return self.joint(vafs)
+        if nd.kind == abi.NODE_LFC:  # generic.rs:233-244: remember the predicate, go on below
+            cur = dict(vafs)
+            cur["lfcs"] = tuple(vafs.get("lfcs", ())) + ((nd.sample, nd.sample_b, nd.cmp, nd.lfc_value),)
+            if nd.children:
+                return sum((self.node(ch, cur) for ch in nd.children), mp.mpf(0))
+            return self.joint(cur)
         pile, res = self.piles[nd.sample], self.res[nd.sample]
 
         def below(v):
@@ -880,14 +949,25 @@ class TreeLocus:
             if nd.children:  # one child: recurse; several: ln_sum_exp over them (generic.rs:199-226)
                 return sum((self.node(ch, cur) for ch in nd.children), mp.mpf(0))
             return self.joint(cur)
+        bounds = _lfc_bounds(vafs, nd.sample)           # generic.rs:148-174
+        if bounds is not None and _rg_empty(bounds):
+            return mp.mpf(0)
         if nd.kind == 0:
             vs = sorted(nd.vafs)
             if pile.clear_ref and all(v > 0.0 for v in vs):
                 return mp.mpf(0)
+            if bounds is not None:
+                vs = [v for v in vs if _rg_contains(bounds, v)]
             return sum((below(v) for v in vs), mp.mpf(0))
         rg = nd.vafs
+        if bounds is not None:
+            rg = _rg_intersect(_Rg(rg.start, rg.end, rg.left_exclusive, rg.right_exclusive), bounds)
+        if _rg_empty(rg):
+            return mp.mpf(0)
         if pile.clear_ref and rg.start > 0.0:
             return mp.mpf(0)
+        if rg.start == rg.end:  # singleton: a point event (generic.rs:349-355)
+            return below(rg.start)
         mn, mx = _observable_min(rg, pile.n), _observable_max(rg, pile.n)
         assert mn <= mx
         if (mx - mn) < res:
@@ -1070,3 +1150,50 @@ events:
         n_ct += is_ct
         checked += 1
     assert checked >= 12 and 0 < n_ct < checked
+
+
+def test_log2_fold_change_nodes():
+    """l2fc(a, b) >= 1 / < 1 over two full ranges (generic.rs:148-174, :233-244, :503-509; log2_fold_change.rs): the
+    limits inferred from the predicate, their intersection with the node's range, the predicate check of every joint
+    evaluation. The predicate is evaluated in f64 with the platform's log2 like the reference does (abscissae ON the
+    threshold hang on its last bit: the same libm here, in the oracle and in the emulation)."""
+    from tests.test_emu_parity import LFC_YAML
+    sc = Scenario.from_yaml(LFC_YAML)
+    flat = sc.flatten()
+    trees, names = dict(sc.event_trees()), list(flat.event_names)
+    _, b = synth.tumor_normal(30, seed=21, depth=30)
+    o = oracle.call_batch(flat, b, afd_capacity=0, n_threads=4)
+    res = [float(flat.c.samples[k].resolution) for k in range(2)]
+    checked = 0
+    for i in range(b.n_loci):
+        if o.knife_edge()[i] or int(o.status[i]) & ~abi.ST_IS_ARTIFACT:
+            continue
+        offs = [int(b.read_offsets[i * 2 + k]) for k in range(3)]
+        piles = [Reads(b, offs[0], offs[1]), Reads(b, offs[1], offs[2])]
+        every = [d for p in piles for d in p.rows]
+        fr_opt = _forward_rate_opt(every)
+        fr = fr_opt if fr_opt is not None else HALF
+        surviving = _surviving_configs(piles, fr_opt is not None)
+        if len(surviving) > 2:
+            continue
+        n_joint, dens = 0, {}
+        for cfg in [None] + surviving:
+            L = TreeLocus([ConfigPileup(p, cfg, fr) for p in piles], res, lambda v: mp.mpf(1))
+            for name in names:
+                if cfg is None or name != "absent":
+                    dens[(cfg, name)] = sum((L.node(r, {}) for r in trees[name]), mp.mpf(0))
+            n_joint += L.n_joint
+        plain = [HALF * dens[(None, n)] for n in names]
+        twin = sum((HALF / len(ARTIFACT_CONFIGS) * dens[(c, n)] for c in surviving for n in names if n != "absent"), mp.mpf(0))
+        total = sum(plain, mp.mpf(0)) + twin
+        for k, w in enumerate([p / total for p in plain] + [twin / total]):
+            got = float(o.log_posteriors[i, k])
+            if w == 0:
+                assert got == -math.inf, (i, k, got)
+            else:
+                assert abs(float(mp.mpf(got) - mp.log(w))) <= 1e-9, (i, names, k, surviving, got, float(mp.log(w)))
+        assert n_joint == int(o.n_base_events[i]), (i, surviving, n_joint, int(o.n_base_events[i]))
+        checked += 1
+        if checked >= 8:
+            break
+    assert checked >= 5
