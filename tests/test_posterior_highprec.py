@@ -222,8 +222,8 @@ def _results(source, flat, b, afd_capacity):
     return o, emu.call_batch(flat, b, afd_capacity=afd_capacity)
 
 
-@pytest.mark.parametrize("source", ["oracle", "engine", "pipeline"])
-@pytest.mark.parametrize("n_loci,seed", [(80, 21), (120, 22)])
+@pytest.mark.parametrize("n_loci,seed,source", [(80, 21, "oracle"), (120, 22, "oracle"), (120, 22, "engine"),
+                                                (120, 22, "pipeline")])
 def test_tumor_normal_posteriors_against_the_high_precision_restatement(n_loci, seed, source):
     sc, b = synth.tumor_normal(n_loci, seed=seed)
     flat = sc.flatten()
