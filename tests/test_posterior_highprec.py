@@ -1197,3 +1197,99 @@ def test_log2_fold_change_nodes():
         if checked >= 8:
             break
     assert checked >= 5
+
+
+def _hypergeom_pmf(N, K, n, k):
+    """statrs Hypergeometric::new(N, K, n).pmf(k): k successes in n draws without replacement from N with K successes."""
+    if k > K or n - k > N - K or k < 0 or n - k < 0:
+        return mp.mpf(0)
+    return mp.binomial(K, k) * mp.binomial(N - K, n - k) / mp.binomial(N, n)
+
+
+def _mendelian(pl_parents, pl_child, alt_parents, alt_child, mu):
+    """prob_mendelian_alt_counts (prior.rs:600-678): meiotic splits of both parents, de novo mutations for the rest."""
+    def cases(p):
+        return [p // 2] if p % 2 == 0 else [p // 2, p // 2 + 1]
+    total, valid = mp.mpf(0), False
+    for p1 in cases(pl_parents[0]):
+        for p2 in cases(pl_parents[1]):
+            if p1 + p2 != pl_child:
+                continue
+            valid = True
+            for a1 in range(0, min(alt_parents[0], p1) + 1):
+                for a2 in range(0, min(alt_parents[1], p2) + 1):
+                    if a1 + a2 <= alt_child:
+                        total += (_hypergeom_pmf(pl_parents[0], alt_parents[0], p1, a1)
+                                  * _hypergeom_pmf(pl_parents[1], alt_parents[1], p2, a2) * mu ** (alt_child - a1 - a2))
+    assert valid
+    return total
+
+
+@pytest.mark.parametrize("full_prior", [False, True])
+@pytest.mark.parametrize("contig", ["all", "X", "Y"])
+def test_pedigree_with_sex_chromosome_ploidies(golden_dir, contig, full_prior):
+    """tests/resources/prior/scenarios/pedigree (mother, father, son, daughter) on an autosome, X and Y: per-sample
+    ploidies 2/2/2/2, 2/1/1/2, 0/1/1/0; population term over the founders, Mendelian terms with odd and zero ploidies."""
+    import json
+    import os
+    from tests.util import four_sample_batch
+    text = json.load(open(os.path.join(golden_dir, "prior_scenarios.json")))["scenarios"]["pedigree"]
+    sc = Scenario.from_yaml(text, full_prior=full_prior).for_contig(contig)
+    flat = sc.flatten()
+    names, events, trees = list(sc.sample_names), list(flat.event_names), dict(sc.event_trees())
+    S = len(names)
+    ploidy = {n: sc.ploidy(n) for n in names}
+    het, mu = mp.mpf("0.001"), mp.mpf("1e-3")
+
+    def full(vafs):
+        v = dict(zip(names, vafs))
+        alts = {}
+        for n in names:
+            if ploidy[n] == 0 and v[n] != 0.0:
+                return mp.mpf(0)
+            k = ploidy[n] * v[n]
+            if k != round(k):
+                return mp.mpf(0)
+            alts[n] = int(round(k))
+        m = alts["mother"] + alts["father"]
+        p = het / m if m > 0 else 1 - sum(het / k for k in range(1, ploidy["mother"] + ploidy["father"] + 1))
+        for kid in ("child", "sibling"):
+            p *= _mendelian((ploidy["mother"], ploidy["father"]), ploidy[kid], (alts["mother"], alts["father"]), alts[kid], mu)
+        return p
+
+    def prior(vafs):
+        if full_prior or all(x == 0.0 for x in vafs):
+            return full(vafs)
+        return mp.mpf(0) if full(vafs) == 0 else 1 - full([0.0] * S)
+    b = four_sample_batch(24, seed=51, depth=16)
+    o = oracle.call_batch(flat, b, afd_capacity=0, n_threads=4)
+    checked = 0
+    for i in range(b.n_loci):
+        if o.knife_edge()[i] or int(o.status[i]) & ~abi.ST_IS_ARTIFACT:
+            continue
+        offs = [int(b.read_offsets[i * S + k]) for k in range(S + 1)]
+        piles = [Reads(b, offs[k], offs[k + 1]) for k in range(S)]
+        fr_opt = _forward_rate_opt([d for p in piles for d in p.rows])
+        fr = fr_opt if fr_opt is not None else HALF
+        surviving = _surviving_configs(piles, fr_opt is not None)
+        n_joint, dens = 0, {}
+        for cfg in [None] + surviving:
+            L = TreeLocus([ConfigPileup(p, cfg, fr) for p in piles], [0.01] * S, prior)
+            for name in events:
+                if cfg is None or name != "absent":
+                    dens[(cfg, name)] = sum((L.node(r, {}) for r in trees[name]), mp.mpf(0))
+            n_joint += L.n_joint
+        plain = [HALF * dens[(None, n)] for n in events]
+        twin = sum((HALF / len(ARTIFACT_CONFIGS) * dens[(c, n)] for c in surviving for n in events if n != "absent"), mp.mpf(0))
+        total = sum(plain, mp.mpf(0)) + twin
+        for k, w in enumerate([p / total for p in plain] + [twin / total]):
+            got = float(o.log_posteriors[i, k])
+            if w == 0:
+                assert got == -math.inf, (i, k, got)
+            else:
+                assert abs(float(mp.mpf(got) - mp.log(w))) <= 1e-9, (contig, i, k, surviving, got, float(mp.log(w)))
+        assert n_joint == int(o.n_base_events[i]), (i, surviving, n_joint, int(o.n_base_events[i]))
+        checked += 1
+        if checked >= 6:
+            break
+    assert checked >= 4
