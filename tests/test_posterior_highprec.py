@@ -1293,3 +1293,61 @@ def test_pedigree_with_sex_chromosome_ploidies(golden_dir, contig, full_prior):
         if checked >= 6:
             break
     assert checked >= 4
+
+
+@pytest.mark.parametrize("full_prior", [False, True])
+def test_tumor_relapse_scenario_with_a_uniform_prior_sample(golden_dir, full_prior):
+    """tests/resources/prior/scenarios/tumor-relapse: normal (germline), tumor (clonal from normal, somatic rate 1e-6) and
+    a relapse sample that only declares a universe: it gets a flat prior inside it and its germline counts as 0
+    (prior.rs:398-406), the others keep theirs - two full ranges nested around a three-valued set."""
+    import json
+    import os
+    text = json.load(open(os.path.join(golden_dir, "prior_scenarios.json")))["scenarios"]["tumor-relapse"]
+    sc = Scenario.from_yaml(text, full_prior=full_prior).for_contig("all")
+    assert list(sc.sample_names) == ["normal", "relapse", "tumor"]
+    flat = sc.flatten()
+    trees, names = dict(sc.event_trees()), list(flat.event_names)
+    het, rate = mp.mpf("0.001"), mp.mpf("1e-6")
+
+    def full(vafs):
+        vn, vr, vt = vafs
+        if not 0.0 <= vr <= 1.0:
+            return mp.mpf(0)
+        k = 2 * vn
+        if k != round(k):
+            return mp.mpf(0)
+        m = int(round(k))
+        pop = het / m if m > 0 else 1 - (het / 1 + het / 2)
+        return pop * ((1 - rate) if vt - vn == 0.0 else rate)
+
+    def prior(vafs):
+        if full_prior or all(v == 0.0 for v in vafs):
+            return full(vafs)
+        return mp.mpf(0) if full(vafs) == 0 else 1 - full([0.0, 0.0, 0.0])
+    b = synth.pedigree(30, seed=61, depth=30)[1]
+    o = oracle.call_batch(flat, b, afd_capacity=0, n_threads=4)
+    checked = 0
+    for i in range(b.n_loci):
+        if o.knife_edge()[i] or int(o.status[i]) & ~abi.ST_IS_ARTIFACT or (int(b.locus_flags[i]) >> abi.LF_VARTYPE_SHIFT) & 3:
+            continue  # (SNV loci: the variant-type fractions are covered by the pedigree test)
+        offs = [int(b.read_offsets[i * 3 + k]) for k in range(4)]
+        piles = [Reads(b, offs[k], offs[k + 1]) for k in range(3)]
+        fr_opt = _forward_rate_opt([d for p in piles for d in p.rows])
+        fr = fr_opt if fr_opt is not None else HALF
+        surviving = _surviving_configs(piles, fr_opt is not None)
+        if surviving:
+            continue  # (every config is another pass over ~10^4 joint evaluations)
+        L = TreeLocus([ConfigPileup(p, None, fr) for p in piles], [0.01] * 3, prior)
+        dens = [sum((L.node(r, {}) for r in trees[n]), mp.mpf(0)) for n in names]
+        total = sum(dens, mp.mpf(0))
+        for k, d in enumerate(dens):
+            got = float(o.log_posteriors[i, k])
+            if d == 0:
+                assert got == -math.inf, (i, k, got)
+            else:
+                assert abs(float(mp.mpf(got) - mp.log(d / total))) <= 1e-9, (i, names[k], got, float(mp.log(d / total)))
+        assert o.log_posteriors[i, -1] == -math.inf and L.n_joint == int(o.n_base_events[i]), (i, L.n_joint, int(o.n_base_events[i]))
+        checked += 1
+        if checked >= 3:
+            break
+    assert checked >= 2
