@@ -1351,3 +1351,96 @@ def test_tumor_relapse_scenario_with_a_uniform_prior_sample(golden_dir, full_pri
         if checked >= 3:
             break
     assert checked >= 2
+
+
+SUBCLONAL_YAML = """
+species:
+  heterozygosity: 0.001
+  ploidy: 2
+  genome-size: 3.5e9
+
+samples:
+  tumor:
+    somatic-effective-mutation-rate: 1e-6
+    inheritance:
+      clonal:
+        from: normal
+        somatic: false
+  relapse:
+    somatic-effective-mutation-rate: 1e-5
+    inheritance:
+      subclonal:
+        from: tumor
+  normal:
+    somatic-effective-mutation-rate: 1e-10
+
+events:
+  tumor_only: "normal:0.0 & tumor:0.25 & relapse:0.0"
+  relapse_only: "normal:0.0 & tumor:0.0 & relapse:0.25"
+  kept: "normal:0.0 & tumor:0.25 & relapse:0.5"
+  germline: "normal:0.5 & tumor:0.5 & relapse:0.5"
+  loh: "normal:0.5 & tumor:1.0 & relapse:]0.5,1.0]"
+"""
+
+
+@pytest.mark.parametrize("full_prior", [False, True])
+def test_subclonal_inheritance_prior(full_prior):
+    """The samples of the reference's tumor-normal-relapse scenario (somatic rates everywhere: the germline odometer of
+    calc_prob, prior.rs:400-421; clonal and subclonal inheritance, :458-552) with events on few allele frequencies, so
+    that a locus stays at a few hundred joint evaluations."""
+    sc = Scenario.from_yaml(SUBCLONAL_YAML, full_prior=full_prior).for_contig("all")
+    assert list(sc.sample_names) == ["normal", "relapse", "tumor"]
+    flat = sc.flatten()
+    trees, names = dict(sc.event_trees()), list(flat.event_names)
+    het = mp.mpf("0.001")
+    rate = {"normal": mp.mpf("1e-10"), "tumor": mp.mpf("1e-6"), "relapse": mp.mpf("1e-5")}
+
+    def som(who, d):  # prob_somatic_mutation (:440-456); relative_eq!(d, 0.0) with epsilon = f64::EPSILON
+        return 1 - rate[who] if abs(d) <= 2.220446049250313e-16 else rate[who]
+
+    def full(vafs):
+        vn, vr, vt = vafs
+        total = mp.mpf(0)
+        for g in (0.0, 0.5, 1.0):  # every sample has somatic variation: germline alt counts 0..ploidy each; clonal and
+            m = int(round(2 * g))  # subclonal inheritance leave only equal germlines (:466, :521)
+            pop = het / m if m > 0 else 1 - (het / 1 + het / 2)
+            sub = som("relapse", vr) if (vt == 0.0 and g == 0.0) else mp.mpf(1)
+            total += pop * som("normal", vn - g) * som("tumor", vt - g) * sub
+        return total
+
+    def prior(vafs):
+        if full_prior or all(v == 0.0 for v in vafs):
+            return full(vafs)
+        return mp.mpf(0) if full(vafs) == 0 else 1 - full([0.0, 0.0, 0.0])
+    b = synth.pedigree(40, seed=71, depth=30)[1]
+    o = oracle.call_batch(flat, b, afd_capacity=0, n_threads=4)
+    checked = 0
+    for i in range(b.n_loci):
+        if o.knife_edge()[i] or int(o.status[i]) & ~abi.ST_IS_ARTIFACT or (int(b.locus_flags[i]) >> abi.LF_VARTYPE_SHIFT) & 3:
+            continue
+        offs = [int(b.read_offsets[i * 3 + k]) for k in range(4)]
+        piles = [Reads(b, offs[k], offs[k + 1]) for k in range(3)]
+        fr_opt = _forward_rate_opt([d for p in piles for d in p.rows])
+        fr = fr_opt if fr_opt is not None else HALF
+        surviving = _surviving_configs(piles, fr_opt is not None)
+        n_joint, dens = 0, {}
+        for cfg in [None] + surviving:
+            L = TreeLocus([ConfigPileup(p, cfg, fr) for p in piles], [0.01] * 3, prior)
+            for name in names:
+                if cfg is None or name != "absent":
+                    dens[(cfg, name)] = sum((L.node(r, {}) for r in trees[name]), mp.mpf(0))
+            n_joint += L.n_joint
+        plain = [HALF * dens[(None, n)] for n in names]
+        twin = sum((HALF / len(ARTIFACT_CONFIGS) * dens[(c, n)] for c in surviving for n in names if n != "absent"), mp.mpf(0))
+        total = sum(plain, mp.mpf(0)) + twin
+        for k, w in enumerate([p / total for p in plain] + [twin / total]):
+            got = float(o.log_posteriors[i, k])
+            if w == 0:
+                assert got == -math.inf, (i, k, got)
+            else:
+                assert abs(float(mp.mpf(got) - mp.log(w))) <= 1e-9, (i, k, surviving, got, float(mp.log(w)))
+        assert n_joint == int(o.n_base_events[i])
+        checked += 1
+        if checked >= 10:
+            break
+    assert checked >= 6
